@@ -1,0 +1,688 @@
+// C ABI of cpvs_b200 (include/cpvs_b200.h): handle management and the host-side orchestration of the
+// device pipeline  depth -> pyramid -> SVO levels -> bottom-up merge -> compressed DAG -> lookups.
+//
+// No CPU fallback lives here: every entry point either drives the CUDA kernels or returns an error.
+#include "../../include/cpvs_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+using namespace cpvs;
+
+namespace {
+
+thread_local std::string gLastError;
+
+int fail(int code, const char* fmt, ...) {
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	gLastError = buf;
+	return code;
+}
+
+#define CPVS_CUDA(expr)                                                                                      \
+	do {                                                                                                     \
+		cudaError_t _e = (expr);                                                                             \
+		if (_e != cudaSuccess)                                                                               \
+			return fail(_e == cudaErrorMemoryAllocation ? CPVS_ENOMEM : CPVS_ECUDA, "%s: %s (%s:%d)", #expr, \
+					cudaGetErrorString(_e), __FILE__, __LINE__);                                             \
+	} while (0)
+
+inline bool isPow2(u64 v) { return v && !(v & (v - 1)); }
+inline u64 pow2AtLeast(u64 v) {
+	u64 p = 1;
+	while (p < v) p <<= 1;
+	return p;
+}
+
+__global__ void storeU64Kernel(u64* dst, u64 value) { *dst = value; }
+
+}  // namespace
+
+struct cpvs_ctx {
+	int device;
+	cudaStream_t own;
+	cudaStream_t stream;
+	u64 launches;
+};
+
+struct cpvs_minmax {
+	cpvs_ctx* ctx;
+	int n;
+	int numLevels;
+	float* ownedDepth;   // device copy when built from host memory
+	float* levelStorage; // levels 1.. in one allocation
+	const float* level[kMaxLevels];
+};
+
+struct cpvs_shadow {
+	cpvs_ctx* ctx;
+	u32* dag;
+	cpvs_shadow_info info;
+};
+
+struct ContainerCell {
+	u32* words = nullptr;  // device copy owned by the container
+	u64 count = 0;
+	u32 numLevels = 0;
+	int leafmasks = 0;
+	u32 rootMask = 0;
+	bool set = false;
+};
+
+struct cpvs_container {
+	cpvs_ctx* ctx;
+	u32 length;
+	u32 filterSize;
+	std::vector<ContainerCell> cells;
+	u32* dag = nullptr;
+	u32* grid = nullptr;
+	u64 dagWords = 0;
+	u32 dagLevels = 0, gridLevels = 0;
+	int leafmasks = 0;
+	bool finalized = false;
+};
+
+namespace {
+
+// Stream-ordered scratch allocations released together when the call ends.
+struct Scratch {
+	cudaStream_t stream;
+	std::vector<void*> blocks;
+	explicit Scratch(cudaStream_t s) : stream(s) {}
+	~Scratch() {
+		for (void* p : blocks) cudaFreeAsync(p, stream);
+	}
+	template <typename T>
+	cudaError_t alloc(T** out, u64 count) {
+		void* p = nullptr;
+		cudaError_t e = cudaMallocAsync(&p, (count ? count : 1) * sizeof(T), stream);
+		if (e == cudaSuccess) blocks.push_back(p);
+		*out = static_cast<T*>(p);
+		return e;
+	}
+};
+
+struct LevelArrays {
+	u64 n = 0;
+	u64* coords = nullptr;
+	u16* masks = nullptr;
+	u32* firstChild = nullptr;
+	u32* uid = nullptr;
+	u32* firstList = nullptr;
+	u32* wordOffset = nullptr;
+	u64* leafBits = nullptr;
+	u64* leafHash = nullptr;
+};
+
+}  // namespace
+
+extern "C" {
+
+const char* cpvs_last_error(void) { return gLastError.c_str(); }
+const char* cpvs_version(void) { return "cpvs_b200 0.1 (sm_100a)"; }
+
+int cpvs_ctx_create(int device, cpvs_ctx** out) {
+	if (!out) return fail(CPVS_EINVAL, "cpvs_ctx_create: out is NULL");
+	*out = nullptr;
+	int count = 0;
+	CPVS_CUDA(cudaGetDeviceCount(&count));
+	if (device < 0 || device >= count) return fail(CPVS_EINVAL, "cpvs_ctx_create: device %d of %d", device, count);
+	cudaDeviceProp prop;
+	CPVS_CUDA(cudaGetDeviceProperties(&prop, device));
+	if (prop.major != 10) return fail(CPVS_ECUDA, "cpvs_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+	CPVS_CUDA(cudaSetDevice(device));
+	cudaMemPool_t pool;
+	CPVS_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+	unsigned long long keep = ~0ull;  // keep freed scratch cached in the pool between calls
+	CPVS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+	cpvs_ctx* ctx = new (std::nothrow) cpvs_ctx;
+	if (!ctx) return fail(CPVS_ENOMEM, "cpvs_ctx_create: host allocation");
+	ctx->device = device;
+	ctx->launches = 0;
+	cudaError_t e = cudaStreamCreateWithFlags(&ctx->own, cudaStreamNonBlocking);
+	if (e != cudaSuccess) {
+		delete ctx;
+		return fail(CPVS_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+	}
+	ctx->stream = ctx->own;
+	*out = ctx;
+	return CPVS_OK;
+}
+
+int cpvs_ctx_destroy(cpvs_ctx* ctx) {
+	if (!ctx) return CPVS_OK;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	cudaStreamDestroy(ctx->own);
+	delete ctx;
+	return CPVS_OK;
+}
+
+int cpvs_ctx_set_stream(cpvs_ctx* ctx, void* cuda_stream) {
+	if (!ctx) return fail(CPVS_EINVAL, "cpvs_ctx_set_stream: ctx is NULL");
+	ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own;
+	return CPVS_OK;
+}
+void* cpvs_ctx_get_stream(const cpvs_ctx* ctx) { return ctx ? ctx->stream : nullptr; }
+
+int cpvs_ctx_synchronize(cpvs_ctx* ctx) {
+	if (!ctx) return fail(CPVS_EINVAL, "cpvs_ctx_synchronize: ctx is NULL");
+	CPVS_CUDA(cudaSetDevice(ctx->device));
+	CPVS_CUDA(cudaStreamSynchronize(ctx->stream));
+	return CPVS_OK;
+}
+uint64_t cpvs_ctx_launch_count(const cpvs_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+/* ---- MinMaxHierarchy ------------------------------------------------------------------------ */
+
+int cpvs_minmax_build(cpvs_ctx* ctx, const float* depth, int n, int mem, cpvs_minmax** out) {
+	if (!ctx || !depth || !out) return fail(CPVS_EINVAL, "cpvs_minmax_build: NULL argument");
+	*out = nullptr;
+	if (n < 2 || !isPow2((u64)n) || n > (1 << 19)) return fail(CPVS_EINVAL, "cpvs_minmax_build: side %d is not a power of two in [2, 2^19]", n);
+	if (mem != CPVS_MEM_HOST && mem != CPVS_MEM_DEVICE) return fail(CPVS_EINVAL, "cpvs_minmax_build: mem %d", mem);
+	CPVS_CUDA(cudaSetDevice(ctx->device));
+	cpvs_minmax* mm = new (std::nothrow) cpvs_minmax;
+	if (!mm) return fail(CPVS_ENOMEM, "cpvs_minmax_build: host allocation");
+	std::memset(mm, 0, sizeof(*mm));
+	mm->ctx = ctx;
+	mm->n = n;
+	int levels = 1;
+	while ((1 << (levels - 1)) < n) ++levels;  // log2(n) + 1 (src/MinMaxHierarchy.cpp:17, .h:60-62)
+	mm->numLevels = levels;
+
+	u64 offsets[kMaxLevels] = {0}, total = 0;
+	for (int k = 1; k < levels; ++k) {
+		offsets[k] = total;
+		const u64 side = (u64)n >> k;
+		total += (side * side * 2 + 63) & ~63ull;  // floats, each level 256-byte aligned
+	}
+	cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&mm->levelStorage), total * sizeof(float), ctx->stream);
+	if (e == cudaSuccess && mem == CPVS_MEM_HOST) {
+		e = cudaMallocAsync(reinterpret_cast<void**>(&mm->ownedDepth), (u64)n * n * sizeof(float), ctx->stream);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(mm->ownedDepth, depth, (u64)n * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+	}
+	if (e != cudaSuccess) {
+		if (mm->levelStorage) cudaFreeAsync(mm->levelStorage, ctx->stream);
+		if (mm->ownedDepth) cudaFreeAsync(mm->ownedDepth, ctx->stream);
+		delete mm;
+		return fail(e == cudaErrorMemoryAllocation ? CPVS_ENOMEM : CPVS_ECUDA, "cpvs_minmax_build: %s", cudaGetErrorString(e));
+	}
+	mm->level[0] = mem == CPVS_MEM_HOST ? mm->ownedDepth : depth;
+	float* lv[kMaxLevels] = {nullptr};
+	for (int k = 1; k < levels; ++k) {
+		lv[k] = mm->levelStorage + offsets[k];
+		mm->level[k] = lv[k];
+	}
+	lv[0] = const_cast<float*>(mm->level[0]);
+	ctx->launches += launchPyramid(mm->level[0], n, lv, levels, ctx->stream);
+	e = cudaGetLastError();
+	if (e != cudaSuccess) {
+		cpvs_minmax_destroy(mm);
+		return fail(CPVS_ECUDA, "pyramid launch: %s", cudaGetErrorString(e));
+	}
+	*out = mm;
+	return CPVS_OK;
+}
+
+int cpvs_minmax_destroy(cpvs_minmax* mm) {
+	if (!mm) return CPVS_OK;
+	cudaSetDevice(mm->ctx->device);
+	if (mm->levelStorage) cudaFreeAsync(mm->levelStorage, mm->ctx->stream);
+	if (mm->ownedDepth) cudaFreeAsync(mm->ownedDepth, mm->ctx->stream);
+	delete mm;
+	return CPVS_OK;
+}
+
+int cpvs_minmax_num_levels(const cpvs_minmax* mm) { return mm ? mm->numLevels : 0; }
+int cpvs_minmax_size(const cpvs_minmax* mm) { return mm ? mm->n : 0; }
+const float* cpvs_minmax_level_device(const cpvs_minmax* mm, int level) {
+	return (mm && level >= 0 && level < mm->numLevels) ? mm->level[level] : nullptr;
+}
+
+int cpvs_minmax_level(const cpvs_minmax* mm, int level, float* out_host) {
+	if (!mm || !out_host) return fail(CPVS_EINVAL, "cpvs_minmax_level: NULL argument");
+	if (level < 0 || level >= mm->numLevels) return fail(CPVS_EINVAL, "cpvs_minmax_level: level %d of %d", level, mm->numLevels);
+	CPVS_CUDA(cudaSetDevice(mm->ctx->device));
+	const u64 side = (u64)mm->n >> level;
+	const u64 bytes = side * side * (level == 0 ? 1 : 2) * sizeof(float);
+	CPVS_CUDA(cudaMemcpyAsync(out_host, mm->level[level], bytes, cudaMemcpyDeviceToHost, mm->ctx->stream));
+	CPVS_CUDA(cudaStreamSynchronize(mm->ctx->stream));
+	return CPVS_OK;
+}
+
+/* ---- CompressedShadow::create ------------------------------------------------------------------ */
+
+int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex, uint32_t zTileNum, int leafmasks, cpvs_shadow** out) {
+	if (!ctx || !mm || !out) return fail(CPVS_EINVAL, "cpvs_shadow_create: NULL argument");
+	*out = nullptr;
+	if (mm->ctx->device != ctx->device) return fail(CPVS_EINVAL, "cpvs_shadow_create: hierarchy lives on device %d, context on %d", mm->ctx->device, ctx->device);
+	const int L = mm->numLevels;
+	if (L <= 3) return fail(CPVS_EINVAL, "cpvs_shadow_create: needs more than 3 levels (side >= 8), got %d", L);  // src/CompressedShadow.cpp:46
+	if (zTileNum == 0 || zTileIndex >= zTileNum) return fail(CPVS_EINVAL, "cpvs_shadow_create: z tile %u of %u", zTileIndex, zTileNum);
+	if ((u64)mm->n * zTileNum > (1ull << 23))
+		return fail(CPVS_EINVAL, "cpvs_shadow_create: side * zTileNum = %llu exceeds 2^23 (depth slices must stay exact in fp32)",
+				(unsigned long long)((u64)mm->n * zTileNum));
+	CPVS_CUDA(cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+
+	const int top = L - 2;
+	const bool useLeaf = leafmasks && (L - 3) >= 2;  // src/CompressedShadow.cpp:20-27
+	const int minLevel = useLeaf ? 2 : 0;            // src/CompressedShadow.cpp:30-32
+	const int lastInner = useLeaf ? 3 : 0;
+
+	cudaEvent_t evStart, evStop;
+	CPVS_CUDA(cudaEventCreate(&evStart));
+	CPVS_CUDA(cudaEventCreate(&evStop));
+	struct EventGuard {
+		cudaEvent_t a, b;
+		~EventGuard() {
+			cudaEventDestroy(a);
+			cudaEventDestroy(b);
+		}
+	} eventGuard{evStart, evStop};
+	CPVS_CUDA(cudaEventRecord(evStart, st));
+
+	Scratch scratch(st);
+	PyramidView pyr;
+	pyr.n = mm->n;
+	pyr.numLevels = L;
+	for (int k = 0; k < kMaxLevels; ++k) pyr.level[k] = k < L ? mm->level[k] : nullptr;
+
+	// device scalars: [0..31] SVO counts, [32..63] unique, [64..95] words, [96..127] bases, [128..159] child totals, [160] total words
+	u64* dScalars;
+	CPVS_CUDA(scratch.alloc(&dScalars, 192));
+	CPVS_CUDA(cudaMemsetAsync(dScalars, 0, 192 * sizeof(u64), st));
+	u64 *dCounts = dScalars, *dUnique = dScalars + 32, *dWords = dScalars + 64, *dBases = dScalars + 96, *dChildTotal = dScalars + 128,
+		*dTotal = dScalars + 160;
+
+	// 1. exact node counts of every level (closed form), so all buffers can be sized up front
+	ctx->launches += launchCountNodes(pyr, zTileIndex, zTileNum, minLevel, dCounts, st);
+	u64 hScalars[192];
+	CPVS_CUDA(cudaMemcpyAsync(hScalars, dCounts, 32 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+	CPVS_CUDA(cudaStreamSynchronize(st));
+	LevelArrays lv[kMaxLevels];
+	lv[top].n = 1;
+	for (int l = top - 1; l >= minLevel; --l) lv[l].n = lv[l + 1].n ? hScalars[l] : 0;
+	for (int l = minLevel; l <= top; ++l)
+		if (lv[l].n >= (1ull << 31)) return fail(CPVS_EOVERFLOW, "level %d has %llu nodes (limit 2^31)", l, (unsigned long long)lv[l].n);
+
+	// 2. per-level arrays
+	u64 scanTiles = 0, scanLaunches = 0, maxTable = 0;
+	for (int l = top; l >= minLevel; --l) {
+		LevelArrays& a = lv[l];
+		if (!a.n) continue;
+		const bool leaf = useLeaf && l == 2;
+		CPVS_CUDA(scratch.alloc(&a.coords, a.n));
+		CPVS_CUDA(scratch.alloc(&a.masks, a.n));
+		CPVS_CUDA(scratch.alloc(&a.uid, a.n));
+		CPVS_CUDA(scratch.alloc(&a.firstList, a.n));
+		CPVS_CUDA(scratch.alloc(&a.wordOffset, a.n));
+		if (leaf) {
+			CPVS_CUDA(scratch.alloc(&a.leafBits, a.n * 8));
+			CPVS_CUDA(scratch.alloc(&a.leafHash, a.n));
+		} else {
+			CPVS_CUDA(scratch.alloc(&a.firstChild, a.n));
+			scanTiles += (a.n + kScanTile - 1) / kScanTile;
+			++scanLaunches;
+		}
+		if (a.n > 1) {
+			scanTiles += (a.n + kScanTile - 1) / kScanTile;
+			++scanLaunches;
+			const u64 t = pow2AtLeast(a.n * 2 < 1024 ? 1024 : a.n * 2);
+			if (t > maxTable) maxTable = t;
+		}
+	}
+	ScanTileState* dTiles;
+	u32* dTickets;
+	u64* dTable = nullptr;
+	CPVS_CUDA(scratch.alloc(&dTiles, scanTiles));
+	CPVS_CUDA(scratch.alloc(&dTickets, scanLaunches));
+	CPVS_CUDA(cudaMemsetAsync(dTiles, 0, (scanTiles ? scanTiles : 1) * sizeof(ScanTileState), st));
+	CPVS_CUDA(cudaMemsetAsync(dTickets, 0, (scanLaunches ? scanLaunches : 1) * sizeof(u32), st));
+	if (maxTable) CPVS_CUDA(scratch.alloc(&dTable, maxTable));
+	u64 tileCursor = 0, launchCursor = 0;
+	auto nextScan = [&](u64 n) {
+		ScanLaunch s{dTickets + launchCursor, dTiles + tileCursor};
+		++launchCursor;
+		tileCursor += (n + kScanTile - 1) / kScanTile;
+		return s;
+	};
+
+	// 3. breadth-first construction, top level first (src/CompressedShadow.cpp:87-169)
+	storeU64Kernel<<<1, 1, 0, st>>>(lv[top].coords, packCoord(0, 0, zTileIndex * 2));
+	++ctx->launches;
+	for (int l = top; l >= lastInner && lv[l].n; --l) {
+		u64* childCoords = (l > minLevel && lv[l - 1].n) ? lv[l - 1].coords : nullptr;
+		ctx->launches += launchExpandLevel(pyr, l, zTileNum, lv[l].coords, lv[l].n, lv[l].masks, lv[l].firstChild, childCoords,
+				dChildTotal + l, nextScan(lv[l].n), st);
+	}
+	if (useLeaf && lv[2].n)  // constructLastLevels (src/CompressedShadow.cpp:171-190)
+		ctx->launches += launchBuildLeaves(pyr, zTileNum, lv[2].coords, lv[2].n, lv[2].leafBits, lv[2].leafHash, lv[2].masks, st);
+
+	// 4. bottom-up merge (src/CompressedShadow.cpp:215-241)
+	for (int l = minLevel; l <= top; ++l) {
+		LevelArrays& a = lv[l];
+		if (!a.n) continue;
+		MergeLevelArgs m;
+		m.n = a.n;
+		m.leaf = (useLeaf && l == 2) ? 1 : 0;
+		m.leafBits = a.leafBits;
+		m.leafHash = a.leafHash;
+		m.masks = a.masks;
+		m.firstChild = a.firstChild;
+		m.childUid = l > minLevel ? lv[l - 1].uid : nullptr;
+		m.table = dTable;
+		m.tableSize = pow2AtLeast(a.n * 2 < 1024 ? 1024 : a.n * 2);
+		m.uid = a.uid;
+		m.firstList = a.firstList;
+		m.wordOffset = a.wordOffset;
+		m.uniqueCount = dUnique + l;
+		m.wordCount = dWords + l;
+		ScanLaunch s{nullptr, nullptr};
+		if (a.n > 1) {
+			CPVS_CUDA(cudaMemsetAsync(dTable, 0xFF, m.tableSize * sizeof(u64), st));
+			s = nextScan(a.n);
+		}
+		ctx->launches += launchMergeLevel(m, s, st);
+	}
+
+	// 5. level bases and the total size (src/CompressedShadow.cpp:326-392)
+	ctx->launches += launchLevelBases(dWords, dBases, top, minLevel, dTotal, st);
+	CPVS_CUDA(cudaMemcpyAsync(hScalars, dScalars, 192 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+	CPVS_CUDA(cudaStreamSynchronize(st));
+	CPVS_CUDA(cudaGetLastError());
+	for (int l = top; l > minLevel; --l)
+		if (lv[l].n && l >= lastInner && hScalars[128 + l] != lv[l - 1].n)
+			return fail(CPVS_EINTERNAL, "level %d: expansion produced %llu nodes, count pass predicted %llu", l - 1,
+					(unsigned long long)hScalars[128 + l], (unsigned long long)lv[l - 1].n);
+	const u64 totalWords = hScalars[160];
+	if (totalWords > (1ull << 32)) return fail(CPVS_EOVERFLOW, "DAG needs %llu words; offsets are 32-bit", (unsigned long long)totalWords);
+
+	cpvs_shadow* s = new (std::nothrow) cpvs_shadow;
+	if (!s) return fail(CPVS_ENOMEM, "cpvs_shadow_create: host allocation");
+	std::memset(s, 0, sizeof(*s));
+	s->ctx = ctx;
+	cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&s->dag), totalWords * sizeof(u32), st);
+	if (e != cudaSuccess) {
+		delete s;
+		return fail(CPVS_ENOMEM, "DAG allocation of %llu words: %s", (unsigned long long)totalWords, cudaGetErrorString(e));
+	}
+
+	// 6. write every unique node once, in its final place
+	for (int l = top; l >= minLevel; --l) {
+		const LevelArrays& a = lv[l];
+		if (!a.n) continue;
+		EmitLevelArgs em;
+		em.n = a.n;
+		em.leaf = (useLeaf && l == 2) ? 1 : 0;
+		em.uniqueCount = dUnique + l;
+		em.firstList = a.firstList;
+		em.wordOffset = a.wordOffset;
+		em.levelBase = dBases + l;
+		em.leafBits = a.leafBits;
+		em.masks = a.masks;
+		em.firstChild = a.firstChild;
+		em.childUid = l > minLevel ? lv[l - 1].uid : nullptr;
+		em.childWordOffset = l > minLevel ? lv[l - 1].wordOffset : nullptr;
+		em.childLevelBase = dBases + (l > minLevel ? l - 1 : l);
+		em.dag = s->dag;
+		ctx->launches += launchEmitLevel(em, st);
+	}
+	u32 rootMask = 0;
+	e = cudaMemcpyAsync(&rootMask, s->dag, sizeof(u32), cudaMemcpyDeviceToHost, st);
+	if (e == cudaSuccess) e = cudaEventRecord(evStop, st);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+	if (e == cudaSuccess) e = cudaGetLastError();
+	float ms = 0.f;
+	if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, evStart, evStop);
+	if (e != cudaSuccess) {
+		cudaFreeAsync(s->dag, st);
+		delete s;
+		return fail(CPVS_ECUDA, "cpvs_shadow_create: %s", cudaGetErrorString(e));
+	}
+	s->info.num_levels = (u32)L;
+	s->info.leafmasks = useLeaf ? 1 : 0;
+	s->info.total_visibility = rootMask == 0x5555u ? CPVS_VISIBLE : (rootMask == 0u ? CPVS_SHADOW : CPVS_PARTIAL);
+	s->info.words = totalWords;
+	for (int l = minLevel; l <= top; ++l) {
+		s->info.svo_nodes[l] = lv[l].n;
+		s->info.dag_nodes[l] = hScalars[32 + l];
+		s->info.dag_words[l] = hScalars[64 + l];
+	}
+	s->info.build_ms = ms;
+	*out = s;
+	return CPVS_OK;
+}
+
+int cpvs_shadow_create_from_depth(cpvs_ctx* ctx, const float* depth, int n, int mem, uint32_t zTileIndex, uint32_t zTileNum, int leafmasks,
+		cpvs_shadow** out) {
+	cpvs_minmax* mm = nullptr;
+	int rc = cpvs_minmax_build(ctx, depth, n, mem, &mm);
+	if (rc != CPVS_OK) return rc;
+	rc = cpvs_shadow_create(ctx, mm, zTileIndex, zTileNum, leafmasks, out);
+	cpvs_minmax_destroy(mm);
+	return rc;
+}
+
+int cpvs_shadow_destroy(cpvs_shadow* s) {
+	if (!s) return CPVS_OK;
+	cudaSetDevice(s->ctx->device);
+	if (s->dag) cudaFreeAsync(s->dag, s->ctx->stream);
+	delete s;
+	return CPVS_OK;
+}
+
+int cpvs_shadow_info_get(const cpvs_shadow* s, cpvs_shadow_info* info) {
+	if (!s || !info) return fail(CPVS_EINVAL, "cpvs_shadow_info_get: NULL argument");
+	*info = s->info;
+	return CPVS_OK;
+}
+
+int cpvs_shadow_copy_dag(const cpvs_shadow* s, uint32_t* out_host) {
+	if (!s || !out_host) return fail(CPVS_EINVAL, "cpvs_shadow_copy_dag: NULL argument");
+	CPVS_CUDA(cudaSetDevice(s->ctx->device));
+	CPVS_CUDA(cudaMemcpyAsync(out_host, s->dag, s->info.words * sizeof(u32), cudaMemcpyDeviceToHost, s->ctx->stream));
+	CPVS_CUDA(cudaStreamSynchronize(s->ctx->stream));
+	return CPVS_OK;
+}
+
+const uint32_t* cpvs_shadow_dag_device(const cpvs_shadow* s) { return s ? s->dag : nullptr; }
+
+}  // extern "C"
+
+namespace {
+
+// Shared by the single-DAG and container lookups: stage host buffers if needed, launch, copy back.
+template <typename Launch>
+int runLookup(cpvs_ctx* ctx, const float* in, u64 inFloats, int mem, unsigned char* out, u64 outBytes, Launch launch) {
+	cudaStream_t st = ctx->stream;
+	if (mem == CPVS_MEM_DEVICE) {
+		ctx->launches += launch(in, out);
+		CPVS_CUDA(cudaGetLastError());
+		return CPVS_OK;
+	}
+	Scratch scratch(st);
+	float* dIn;
+	unsigned char* dOut;
+	CPVS_CUDA(scratch.alloc(&dIn, inFloats));
+	CPVS_CUDA(scratch.alloc(&dOut, outBytes));
+	CPVS_CUDA(cudaMemcpyAsync(dIn, in, inFloats * sizeof(float), cudaMemcpyHostToDevice, st));
+	ctx->launches += launch(dIn, dOut);
+	CPVS_CUDA(cudaGetLastError());
+	CPVS_CUDA(cudaMemcpyAsync(out, dOut, outBytes, cudaMemcpyDeviceToHost, st));
+	CPVS_CUDA(cudaStreamSynchronize(st));
+	return CPVS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cpvs_shadow_lookup_ndc(const cpvs_shadow* s, const float* ndc, int64_t count, int mem, int tryLeafmasks, uint8_t* out) {
+	if (!s || (count > 0 && (!ndc || !out))) return fail(CPVS_EINVAL, "cpvs_shadow_lookup_ndc: NULL argument");
+	if (count < 0) return fail(CPVS_EINVAL, "cpvs_shadow_lookup_ndc: count %lld", (long long)count);
+	if (count == 0) return CPVS_OK;
+	if (tryLeafmasks && !s->info.leafmasks)
+		return fail(CPVS_EINVAL, "cpvs_shadow_lookup_ndc: tryLeafmasks on a DAG built without leafmasks (SURVEY.md T2)");
+	CPVS_CUDA(cudaSetDevice(s->ctx->device));
+	LookupDag d{s->dag, nullptr, s->info.num_levels, 0, tryLeafmasks ? 1 : 0};
+	cudaStream_t st = s->ctx->stream;
+	return runLookup(s->ctx, ndc, (u64)count * 3, mem, out, (u64)count,
+			[&](const float* in, unsigned char* o) { return launchLookupNdc(d, in, count, o, st); });
+}
+
+/* ---- CompressedShadowContainer ---------------------------------------------------------------- */
+
+int cpvs_container_create(cpvs_ctx* ctx, uint32_t length, cpvs_container** out) {
+	if (!ctx || !out) return fail(CPVS_EINVAL, "cpvs_container_create: NULL argument");
+	*out = nullptr;
+	if (!isPow2(length) || length > 64) return fail(CPVS_EINVAL, "cpvs_container_create: length %u must be a power of two <= 64", length);
+	cpvs_container* c = new (std::nothrow) cpvs_container;
+	if (!c) return fail(CPVS_ENOMEM, "cpvs_container_create: host allocation");
+	c->ctx = ctx;
+	c->length = length;
+	c->filterSize = 1;
+	c->cells.resize((size_t)length * length * length);
+	*out = c;
+	return CPVS_OK;
+}
+
+static void releaseContainerBuffers(cpvs_container* c) {
+	if (c->dag) cudaFreeAsync(c->dag, c->ctx->stream);
+	if (c->grid) cudaFreeAsync(c->grid, c->ctx->stream);
+	c->dag = c->grid = nullptr;
+	c->finalized = false;
+}
+
+int cpvs_container_destroy(cpvs_container* c) {
+	if (!c) return CPVS_OK;
+	cudaSetDevice(c->ctx->device);
+	releaseContainerBuffers(c);
+	for (ContainerCell& cell : c->cells)
+		if (cell.words) cudaFreeAsync(cell.words, c->ctx->stream);
+	delete c;
+	return CPVS_OK;
+}
+
+int cpvs_container_set_dag(cpvs_container* c, const uint32_t* words, uint64_t count, int mem, uint32_t numLevels, int leafmasks, uint32_t x,
+		uint32_t y, uint32_t z) {
+	if (!c || !words || !count) return fail(CPVS_EINVAL, "cpvs_container_set_dag: NULL or empty DAG");
+	if (x >= c->length || y >= c->length || z >= c->length)  // assert of src/CompressedShadowContainer.h:35
+		return fail(CPVS_EINVAL, "cpvs_container_set_dag: cell (%u,%u,%u) outside length %u", x, y, z, c->length);
+	CPVS_CUDA(cudaSetDevice(c->ctx->device));
+	cudaStream_t st = c->ctx->stream;
+	ContainerCell& cell = c->cells[((size_t)z * c->length + y) * c->length + x];  // src/CompressedShadowContainer.h:37-38
+	if (cell.words) CPVS_CUDA(cudaFreeAsync(cell.words, st));
+	cell = ContainerCell();
+	CPVS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&cell.words), count * sizeof(u32), st));
+	CPVS_CUDA(cudaMemcpyAsync(cell.words, words, count * sizeof(u32), mem == CPVS_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+	CPVS_CUDA(cudaMemcpyAsync(&cell.rootMask, cell.words, sizeof(u32), cudaMemcpyDeviceToHost, st));
+	CPVS_CUDA(cudaStreamSynchronize(st));
+	cell.count = count;
+	cell.numLevels = numLevels;
+	cell.leafmasks = leafmasks;
+	cell.set = true;
+	if (c->finalized) releaseContainerBuffers(c);
+	return CPVS_OK;
+}
+
+int cpvs_container_set(cpvs_container* c, const cpvs_shadow* s, uint32_t x, uint32_t y, uint32_t z) {
+	if (!c || !s) return fail(CPVS_EINVAL, "cpvs_container_set: NULL argument");
+	if (s->ctx->device != c->ctx->device) return fail(CPVS_EINVAL, "cpvs_container_set: shadow lives on another device; use cpvs_container_set_dag");
+	return cpvs_container_set_dag(c, s->dag, s->info.words, CPVS_MEM_DEVICE, s->info.num_levels, (int)s->info.leafmasks, x, y, z);
+}
+
+int cpvs_container_finalize(cpvs_container* c) {
+	if (!c) return fail(CPVS_EINVAL, "cpvs_container_finalize: NULL argument");
+	CPVS_CUDA(cudaSetDevice(c->ctx->device));
+	cudaStream_t st = c->ctx->stream;
+	u64 total = 0;
+	for (size_t i = 0; i < c->cells.size(); ++i) {
+		const ContainerCell& cell = c->cells[i];
+		if (!cell.set) return fail(CPVS_EINVAL, "cpvs_container_finalize: cell %zu was never set", i);
+		if (cell.numLevels != c->cells[0].numLevels || cell.leafmasks != c->cells[0].leafmasks)
+			return fail(CPVS_EINVAL, "cpvs_container_finalize: cell %zu differs in levels/leafmasks from cell 0 (src/CompressedShadowContainer.cpp:39-40)", i);
+		total += cell.count;
+	}
+	if (total > (1ull << 32)) return fail(CPVS_EOVERFLOW, "combined DAG needs %llu words; offsets are 32-bit", (unsigned long long)total);
+	releaseContainerBuffers(c);
+	std::vector<u32> grid(c->cells.size());
+	CPVS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&c->dag), total * sizeof(u32), st));
+	CPVS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&c->grid), grid.size() * sizeof(u32), st));
+	u64 offset = 0;
+	for (size_t i = 0; i < c->cells.size(); ++i) {  // combineDAGs (:52-69) + createTopLevelGrid (:71-91)
+		const ContainerCell& cell = c->cells[i];
+		grid[i] = cell.rootMask == 0u ? CPVS_GRID_CELL_SHADOWED : (cell.rootMask == 0x5555u ? CPVS_GRID_CELL_VISIBLE : (u32)offset);
+		CPVS_CUDA(cudaMemcpyAsync(c->dag + offset, cell.words, cell.count * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+		offset += cell.count;
+	}
+	CPVS_CUDA(cudaMemcpyAsync(c->grid, grid.data(), grid.size() * sizeof(u32), cudaMemcpyHostToDevice, st));
+	CPVS_CUDA(cudaStreamSynchronize(st));
+	c->dagWords = total;
+	c->dagLevels = c->cells[0].numLevels;  // src/CompressedShadowContainer.cpp:40
+	c->gridLevels = 0;                     // log8(#cells) (:42-43), exact here
+	while ((1u << c->gridLevels) < c->length) ++c->gridLevels;
+	c->leafmasks = c->cells[0].leafmasks;
+	c->finalized = true;
+	return CPVS_OK;
+}
+
+int cpvs_container_info(const cpvs_container* c, uint64_t* dagWords, uint32_t* gridCells, uint32_t* dagLevels, uint32_t* gridLevels) {
+	if (!c || !c->finalized) return fail(CPVS_EINVAL, "cpvs_container_info: container not finalized");
+	if (dagWords) *dagWords = c->dagWords;
+	if (gridCells) *gridCells = (u32)c->cells.size();
+	if (dagLevels) *dagLevels = c->dagLevels;
+	if (gridLevels) *gridLevels = c->gridLevels;
+	return CPVS_OK;
+}
+
+int cpvs_container_copy(const cpvs_container* c, uint32_t* dagOut, uint32_t* gridOut) {
+	if (!c || !c->finalized) return fail(CPVS_EINVAL, "cpvs_container_copy: container not finalized");
+	CPVS_CUDA(cudaSetDevice(c->ctx->device));
+	if (dagOut) CPVS_CUDA(cudaMemcpyAsync(dagOut, c->dag, c->dagWords * sizeof(u32), cudaMemcpyDeviceToHost, c->ctx->stream));
+	if (gridOut) CPVS_CUDA(cudaMemcpyAsync(gridOut, c->grid, c->cells.size() * sizeof(u32), cudaMemcpyDeviceToHost, c->ctx->stream));
+	CPVS_CUDA(cudaStreamSynchronize(c->ctx->stream));
+	return CPVS_OK;
+}
+
+int cpvs_container_lookup_ndc(const cpvs_container* c, const float* ndc, int64_t count, int mem, uint8_t* out) {
+	if (!c || !c->finalized) return fail(CPVS_EINVAL, "cpvs_container_lookup_ndc: container not finalized");
+	if (count < 0 || (count > 0 && (!ndc || !out))) return fail(CPVS_EINVAL, "cpvs_container_lookup_ndc: bad arguments");
+	if (count == 0) return CPVS_OK;
+	CPVS_CUDA(cudaSetDevice(c->ctx->device));
+	LookupDag d{c->dag, c->grid, c->dagLevels, c->gridLevels, c->leafmasks};
+	cudaStream_t st = c->ctx->stream;
+	return runLookup(c->ctx, ndc, (u64)count * 3, mem, out, (u64)count,
+			[&](const float* in, unsigned char* o) { return launchLookupNdc(d, in, count, o, st); });
+}
+
+int cpvs_container_evaluate(const cpvs_container* c, const float* positions, uint32_t width, uint32_t height, int mem, const float m[16],
+		uint8_t* visibilities) {
+	if (!c || !c->finalized) return fail(CPVS_EINVAL, "cpvs_container_evaluate: container not finalized");
+	if (!positions || !m || !visibilities) return fail(CPVS_EINVAL, "cpvs_container_evaluate: NULL argument");
+	const long long count = (long long)width * height;
+	if (count == 0) return CPVS_OK;
+	CPVS_CUDA(cudaSetDevice(c->ctx->device));
+	LookupDag d{c->dag, c->grid, c->dagLevels, c->gridLevels, c->leafmasks};
+	cudaStream_t st = c->ctx->stream;
+	return runLookup(c->ctx, positions, (u64)count * 4, mem, visibilities, (u64)count,
+			[&](const float* in, unsigned char* o) { return launchEvaluate(d, in, count, m, o, st); });
+}
+
+int cpvs_container_set_filter_size(cpvs_container* c, uint32_t size) {
+	if (!c) return fail(CPVS_EINVAL, "cpvs_container_set_filter_size: NULL argument");
+	c->filterSize = size;
+	return CPVS_OK;
+}
+
+}  // extern "C"

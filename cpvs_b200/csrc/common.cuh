@@ -1,0 +1,194 @@
+// Shared device helpers for the cpvs_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cpvs {
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef uint16_t u16;
+
+constexpr int kMaxLevels = 32;
+constexpr int kScanThreads = 256;  // threads per scan tile
+constexpr int kScanItems = 4;      // items per thread
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+// Node coordinates packed for the breadth-first work lists: x:20 | y:20 | z:24.
+__host__ __device__ inline u64 packCoord(u32 x, u32 y, u32 z) { return (u64)x | ((u64)y << 20) | ((u64)z << 40); }
+__host__ __device__ inline void unpackCoord(u64 c, u32& x, u32& y, u32& z) {
+	x = (u32)(c & 0xFFFFFu);
+	y = (u32)((c >> 20) & 0xFFFFFu);
+	z = (u32)(c >> 40);
+}
+
+// ---- classification, literally as the reference writes it (no FMA contraction: explicit _rn ops) ----
+// cs::visible (reference src/CompressedShadowUtil.h:35-44): 1 visible, 0 shadow, 2 partial.
+__device__ __forceinline__ u32 classifyRange(float minZ, float maxZ, float minDepth, float maxDepth) {
+	if (maxZ <= minDepth) return 1u;
+	if (minZ >= maxDepth) return 0u;
+	return 2u;
+}
+// cs::absoluteVisible (reference src/CompressedShadowUtil.h:51-57).
+__device__ __forceinline__ u32 classifyPoint(float minZ, float maxZ, float depth) {
+	const float midZ = __fmul_rn(__fadd_rn(minZ, maxZ), 0.5f);
+	return (midZ <= depth) ? 1u : 0u;
+}
+// std::min / std::max as MinMaxHierarchy uses them (reference src/MinMaxHierarchy.cpp:29-33,46-47).
+__device__ __forceinline__ float stdMin(float a, float b) { return (b < a) ? b : a; }
+__device__ __forceinline__ float stdMax(float a, float b) { return (a < b) ? b : a; }
+
+__device__ __forceinline__ u64 mix64(u64 h) {
+	h ^= h >> 33;
+	h *= 0xFF51AFD7ED558CCDull;
+	h ^= h >> 33;
+	h *= 0xC4CEB9FE1A85EC53ull;
+	h ^= h >> 33;
+	return h;
+}
+
+// ---- single-pass prefix sums over tiles (decoupled look-back) -----------------------------------
+// One ScanTileState per tile. A tile publishes its own aggregate (flag 1), then, once it knows the
+// sum of everything in front of it, its inclusive prefix (flag 2). Payload words are written before
+// the flag with release semantics and read after it with acquire semantics.
+struct ScanTileState {
+	u32 flag;
+	u32 pad;
+	u64 agg[2];
+	u64 incl[2];
+};
+
+struct ScanLaunch {
+	u32* ticket;           // zeroed counter handing out tile indices in start order
+	ScanTileState* tiles;  // zeroed, one per tile
+};
+
+__device__ __forceinline__ u32 ldAcquire(const u32* p) {
+	u32 v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void stRelease(u32* p, u32 v) {
+	asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ u64 ldRelaxed64(const u64* p) {
+	u64 v;
+	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void stRelaxed64(u64* p, u64 v) {
+	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Tile index in start order, so every tile in front of this one is already running or done.
+__device__ __forceinline__ u32 scanAcquireTile(const ScanLaunch& sl) {
+	__shared__ u32 sTile;
+	if (threadIdx.x == 0) sTile = atomicAdd(sl.ticket, 1u);
+	__syncthreads();
+	return sTile;
+}
+
+// Block-wide exclusive scan of one (a,b) pair per thread. Returns this thread's exclusive prefix
+// inside the block in (a,b) and the block totals in (totA,totB). kScanThreads threads.
+__device__ __forceinline__ void blockExclusiveScan2(u64& a, u64& b, u64& totA, u64& totB) {
+	__shared__ u64 sA[kScanThreads / 32], sB[kScanThreads / 32];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	u64 ia = a, ib = b;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const u64 ua = __shfl_up_sync(0xFFFFFFFFu, ia, d), ub = __shfl_up_sync(0xFFFFFFFFu, ib, d);
+		if (lane >= d) {
+			ia += ua;
+			ib += ub;
+		}
+	}
+	if (lane == 31) {
+		sA[warp] = ia;
+		sB[warp] = ib;
+	}
+	__syncthreads();
+	u64 offA = 0, offB = 0, tA = 0, tB = 0;
+#pragma unroll
+	for (int w = 0; w < kScanThreads / 32; ++w) {
+		if (w < warp) {
+			offA += sA[w];
+			offB += sB[w];
+		}
+		tA += sA[w];
+		tB += sB[w];
+	}
+	__syncthreads();
+	a = offA + ia - a;
+	b = offB + ib - b;
+	totA = tA;
+	totB = tB;
+}
+
+// Publishes this tile's totals and returns the sum over all tiles in front of it (all threads get it).
+__device__ __forceinline__ void scanLookback2(const ScanLaunch& sl, u32 tile, u64 totA, u64 totB, u64& preA, u64& preB) {
+	__shared__ u64 sPre[2];
+	ScanTileState* st = sl.tiles;
+	if (threadIdx.x < 32) {
+		const int lane = threadIdx.x;
+		if (lane == 0) {
+			if (tile == 0) {
+				stRelaxed64(&st[0].incl[0], totA);
+				stRelaxed64(&st[0].incl[1], totB);
+				stRelease(&st[0].flag, 2u);
+			} else {
+				stRelaxed64(&st[tile].agg[0], totA);
+				stRelaxed64(&st[tile].agg[1], totB);
+				stRelease(&st[tile].flag, 1u);
+			}
+		}
+		u64 runA = 0, runB = 0;
+		if (tile > 0) {
+			long long look = (long long)tile - 1;
+			for (;;) {
+				const long long idx = look - lane;
+				u32 flag = 2u;
+				if (idx >= 0) {
+					do {
+						flag = ldAcquire(&st[idx].flag);
+					} while (flag == 0u);
+				}
+				u64 vA = 0, vB = 0;
+				if (idx >= 0) {
+					vA = ldRelaxed64(flag == 2u ? &st[idx].incl[0] : &st[idx].agg[0]);
+					vB = ldRelaxed64(flag == 2u ? &st[idx].incl[1] : &st[idx].agg[1]);
+				}
+				// lanes whose index falls in front of tile 0 report "inclusive, 0"
+				const u32 done = __ballot_sync(0xFFFFFFFFu, flag == 2u);
+				const int first = __ffs(done) - 1;  // nearest tile that already knows its inclusive prefix
+				if (done != 0u && lane > first) {
+					vA = 0;
+					vB = 0;
+				}
+#pragma unroll
+				for (int d = 16; d > 0; d >>= 1) {
+					vA += __shfl_xor_sync(0xFFFFFFFFu, vA, d);
+					vB += __shfl_xor_sync(0xFFFFFFFFu, vB, d);
+				}
+				runA += vA;
+				runB += vB;
+				if (done != 0u) break;
+				look -= 32;
+			}
+			if (lane == 0) {
+				stRelaxed64(&st[tile].incl[0], runA + totA);
+				stRelaxed64(&st[tile].incl[1], runB + totB);
+				stRelease(&st[tile].flag, 2u);
+			}
+		}
+		if (lane == 0) {
+			sPre[0] = runA;
+			sPre[1] = runB;
+		}
+	}
+	__syncthreads();
+	preA = sPre[0];
+	preB = sPre[1];
+	__syncthreads();
+}
+
+}  // namespace cpvs

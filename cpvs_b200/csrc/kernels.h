@@ -1,0 +1,83 @@
+// Host-callable launchers of the cpvs_b200 kernels. Every launcher enqueues on `stream` and returns
+// the number of kernels it launched (for cpvs_ctx_launch_count).
+#pragma once
+#include "common.cuh"
+
+namespace cpvs {
+
+// ---- pyramid.cu: MinMaxHierarchy (reference src/MinMaxHierarchy.cpp:9-97) ----
+// levels[k] (k >= 1) points at (n>>k)^2 float2 (min,max); levels[0] = depth.
+int launchPyramid(const float* depth, int n, float* const* levels, int numLevels, cudaStream_t stream);
+
+// ---- svo.cu: constructSvo (reference src/CompressedShadow.cpp:87-190) ----
+struct PyramidView {
+	const float* level[kMaxLevels];  // level[0] = depth, level[k] = (min,max) pairs
+	int n;
+	int numLevels;
+};
+
+// counts[l] += number of SVO nodes at level l, for l in [minLevel, numLevels-3]; counts must be zeroed.
+int launchCountNodes(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, int minLevel, u64* counts, cudaStream_t stream);
+
+// One breadth-first step: masks of the n nodes of `level`, index of each node's first child in the
+// next level, and the next level's coordinate list. childTotal receives the next level's node count.
+int launchExpandLevel(const PyramidView& pyr, int level, u32 zTileNum, const u64* coords, u64 n, u16* masks,
+		u32* firstChild, u64* childCoords, u64* childTotal, ScanLaunch scan, cudaStream_t stream);
+
+// Level-2 nodes: 8 x u64 slice masks per leaf (bits[leaf*8 + z']), a 64-bit content hash and the
+// 16-bit 1x1x8 childmask (2 bits per slice).
+int launchBuildLeaves(const PyramidView& pyr, u32 zTileNum, const u64* coords, u64 n, u64* bits, u64* hashes, u16* masks,
+		cudaStream_t stream);
+
+// ---- merge.cu: mergeCommonSubtrees (reference src/CompressedShadow.cpp:215-304, Util.h:154-182) ----
+struct MergeLevelArgs {
+	u64 n;                 // nodes in this level
+	int leaf;              // 1: level of leafmask nodes
+	const u64* leafBits;   // leaf: 8 words per node
+	const u64* leafHash;   // leaf: content hash per node
+	const u16* masks;      // inner: childmask per node
+	const u32* firstChild; // inner: index of first child in the level below
+	const u32* childUid;   // inner: unique id of every node of the level below
+	u64* table;            // open-addressing table, tableSize slots, pre-filled with 0xFF bytes
+	u64 tableSize;         // power of two
+	u32* uid;              // out: unique id (first-occurrence rank) per node
+	u32* firstList;        // out: node index of the r-th unique node
+	u32* wordOffset;       // out: compressed word offset (inside the level) of the r-th unique node
+	u64* uniqueCount;      // out: number of unique nodes
+	u64* wordCount;        // out: compressed words of the level
+};
+int launchMergeLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaStream_t stream);
+
+// ---- emit.cu: compress (reference src/CompressedShadow.cpp:326-392) ----
+struct EmitLevelArgs {
+	u64 n;                    // upper bound on unique nodes (= SVO nodes of the level)
+	int leaf;
+	const u64* uniqueCount;   // device: unique nodes of this level
+	const u32* firstList;
+	const u32* wordOffset;
+	const u64* levelBase;     // device: word offset of this level in the DAG
+	const u64* leafBits;
+	const u16* masks;
+	const u32* firstChild;
+	const u32* childUid;        // unique ids of the level below
+	const u32* childWordOffset; // word offsets of the level below's unique nodes
+	const u64* childLevelBase;  // device: word offset of the level below in the DAG
+	u32* dag;
+};
+int launchEmitLevel(const EmitLevelArgs& a, cudaStream_t stream);
+// bases[l] for l = top..minLevel from words[l]; total -> *totalWords. One thread.
+int launchLevelBases(const u64* words, u64* bases, int topLevel, int minLevel, u64* totalWords, cudaStream_t stream);
+
+// ---- lookup.cu: traverse (reference src/CompressedShadow.cpp:404-463, shader/traverse.cs) ----
+struct LookupDag {
+	const u32* dag;
+	const u32* grid;   // NULL: single DAG
+	u32 dagLevels;
+	u32 gridLevels;
+	int leafmasks;
+};
+int launchLookupNdc(const LookupDag& d, const float* ndc, long long count, unsigned char* out, cudaStream_t stream);
+int launchEvaluate(const LookupDag& d, const float* positions, long long count, const float* matrix, unsigned char* out,
+		cudaStream_t stream);
+
+}  // namespace cpvs

@@ -1,0 +1,165 @@
+/* cpvs_b200 -- C ABI of the B200-native compact-precomputed-voxelized-shadow path.
+ *
+ * This header is the drop-in boundary: plain C, opaque handles, plain pointers and sizes. Each entry
+ * point names the reference interface (TobiasRp/cpvs, path:line) it stands in for. The reference has
+ * no FFI layer of its own -- its boundary is the C++ class API of cpvs_lib (CMakeLists.txt:36) -- so
+ * the functions below are what a binding for that class API binds; the headers under include/cpvs/ put the
+ * reference's class names back on top for C++ callers, and INTEGRATION.md shows the maintainer-side
+ * change.
+ *
+ * Everything runs on one CUDA device per context (sm_100a). There is no CPU fallback: a call either
+ * runs the CUDA path or returns an error code; cpvs_last_error() describes the failure.
+ *
+ * Conventions
+ *   - depth maps: float32, square, side a power of two, row-major, one channel
+ *     (Image<float>, src/Image.h:35-40).
+ *   - `mem`: CPVS_MEM_HOST pointers are copied to / from the device inside the call;
+ *     CPVS_MEM_DEVICE pointers are used in place on the context's stream.
+ *   - all work is enqueued on the context's stream; calls that return sizes or host data
+ *     synchronise that stream, the rest are asynchronous.
+ *   - NodeVisibility values (src/CompressedShadow.h:22-26): 0 shadow, 1 visible (lit), 2 partial.
+ */
+#ifndef CPVS_B200_H
+#define CPVS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CPVS_API __attribute__((visibility("default")))
+#else
+#define CPVS_API
+#endif
+
+#define CPVS_OK 0
+#define CPVS_EINVAL 1    /* bad argument: not square / not a power of two / too small / null */
+#define CPVS_ENOMEM 2    /* device or host allocation failed */
+#define CPVS_ECUDA 3     /* CUDA runtime error, or no sm_100-class device */
+#define CPVS_EOVERFLOW 4 /* a DAG would need more than 2^32 words (32-bit offsets are the format) */
+#define CPVS_EINTERNAL 5 /* internal consistency check failed */
+
+#define CPVS_MEM_HOST 0
+#define CPVS_MEM_DEVICE 1
+
+#define CPVS_SHADOW 0
+#define CPVS_VISIBLE 1
+#define CPVS_PARTIAL 2
+
+#define CPVS_MAX_LEVELS 32
+
+/* Grid sentinels written by CompressedShadowContainer::createTopLevelGrid
+ * (src/CompressedShadowContainer.cpp:8-9). The lookup tests these same values. */
+#define CPVS_GRID_CELL_SHADOWED 0x0FFFFFFFu
+#define CPVS_GRID_CELL_VISIBLE 0x0FFFFFFEu
+
+typedef struct cpvs_ctx cpvs_ctx;
+typedef struct cpvs_minmax cpvs_minmax;
+typedef struct cpvs_shadow cpvs_shadow;
+typedef struct cpvs_container cpvs_container;
+
+/* ---- context ------------------------------------------------------------------------------- */
+
+/* One context per GPU; owns a stream and the stream-ordered scratch pool. */
+CPVS_API int cpvs_ctx_create(int device, cpvs_ctx** out);
+CPVS_API int cpvs_ctx_destroy(cpvs_ctx* ctx);
+/* Run on a caller stream (cudaStream_t passed as void*); NULL restores the context's own stream. */
+CPVS_API int cpvs_ctx_set_stream(cpvs_ctx* ctx, void* cuda_stream);
+CPVS_API void* cpvs_ctx_get_stream(const cpvs_ctx* ctx);
+CPVS_API int cpvs_ctx_synchronize(cpvs_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+CPVS_API uint64_t cpvs_ctx_launch_count(const cpvs_ctx* ctx);
+/* Message for the last non-OK status on the calling thread. */
+CPVS_API const char* cpvs_last_error(void);
+CPVS_API const char* cpvs_version(void);
+
+/* ---- MinMaxHierarchy (src/MinMaxHierarchy.h:23-72, src/MinMaxHierarchy.cpp:9-97) ------------- */
+
+/* MinMaxHierarchy::MinMaxHierarchy(const ImageF&) (src/MinMaxHierarchy.cpp:9-27).
+ * n: side of the depth map (power of two, >= 2). A CPVS_MEM_DEVICE depth map is borrowed, not
+ * copied: it must stay alive and unchanged for as long as the hierarchy is used. */
+CPVS_API int cpvs_minmax_build(cpvs_ctx* ctx, const float* depth, int n, int mem, cpvs_minmax** out);
+CPVS_API int cpvs_minmax_destroy(cpvs_minmax* mm);
+/* getNumLevels() (src/MinMaxHierarchy.h:60-62): log2(n) + 1. */
+CPVS_API int cpvs_minmax_num_levels(const cpvs_minmax* mm);
+CPVS_API int cpvs_minmax_size(const cpvs_minmax* mm);
+/* getLevel(level) (src/MinMaxHierarchy.h:67-72) copied to the host: level 0 is n*n depths, level k>=1
+ * is (n>>k)^2 interleaved (min,max) pairs -- the layout getMin/getMax index (src/MinMaxHierarchy.h:31-55). */
+CPVS_API int cpvs_minmax_level(const cpvs_minmax* mm, int level, float* out_host);
+/* Device pointer of a level (same layout), for zero-copy consumers. */
+CPVS_API const float* cpvs_minmax_level_device(const cpvs_minmax* mm, int level);
+
+/* ---- CompressedShadow (src/CompressedShadow.h:20-126) ---------------------------------------- */
+
+typedef struct cpvs_shadow_info {
+	uint32_t num_levels;       /* getNumLevels() (src/CompressedShadow.h:71) */
+	uint32_t leafmasks;        /* 1 if level 2 holds 64-bit leafmasks (src/CompressedShadow.cpp:20-27) */
+	uint32_t total_visibility; /* getTotalVisibility() (src/CompressedShadow.cpp:66-72) */
+	uint32_t reserved;
+	uint64_t words;                      /* getDAG().size() */
+	uint64_t svo_nodes[CPVS_MAX_LEVELS]; /* nodes per level before merging, index = level */
+	uint64_t dag_nodes[CPVS_MAX_LEVELS]; /* nodes per level after merging, index = level */
+	uint64_t dag_words[CPVS_MAX_LEVELS]; /* compressed words per level */
+	float build_ms;                      /* device time of the create call (CUDA events) */
+	float reserved_f;
+} cpvs_shadow_info;
+
+/* CompressedShadow::create(const MinMaxHierarchy&, zTileIndex, zTileNum)
+ * (src/CompressedShadow.h:48-49, src/CompressedShadow.cpp:49-59): SVO construction, common-subtree
+ * merge and pointer compression, all on the device. The result is word-for-word the reference's
+ * getDAG(). `leafmasks` selects the reference's compile-time LEAFMASKS switch
+ * (src/CompressedShadow.cpp:17); as there, maps smaller than 16^2 never use leafmasks.
+ * z_tile_num is passed by value (the reference keeps it in a file-static). */
+CPVS_API int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t z_tile_index, uint32_t z_tile_num,
+		int leafmasks, cpvs_shadow** out);
+/* CompressedShadow::create(const ShadowMap*, ...) (src/CompressedShadow.cpp:61-64): temporary hierarchy. */
+CPVS_API int cpvs_shadow_create_from_depth(cpvs_ctx* ctx, const float* depth, int n, int mem, uint32_t z_tile_index,
+		uint32_t z_tile_num, int leafmasks, cpvs_shadow** out);
+CPVS_API int cpvs_shadow_destroy(cpvs_shadow* s);
+CPVS_API int cpvs_shadow_info_get(const cpvs_shadow* s, cpvs_shadow_info* info);
+/* getDAG() (src/CompressedShadow.h:75) copied to the host; `out_host` holds info.words words. */
+CPVS_API int cpvs_shadow_copy_dag(const cpvs_shadow* s, uint32_t* out_host);
+CPVS_API const uint32_t* cpvs_shadow_dag_device(const cpvs_shadow* s);
+/* CompressedShadow::traverse(vec3 ndc, bool tryLeafmasks) (src/CompressedShadow.cpp:404-463) for
+ * `count` points: ndc = count x (x,y,z) floats in [-1,1]^3, out = count NodeVisibility bytes. Points
+ * outside the cube are clamped to it. */
+CPVS_API int cpvs_shadow_lookup_ndc(const cpvs_shadow* s, const float* ndc, int64_t count, int mem, int try_leafmasks,
+		uint8_t* out);
+
+/* ---- CompressedShadowContainer (src/CompressedShadowContainer.h:18-92) + shader/traverse.cs ----- */
+
+/* CompressedShadowContainer(uint length) (src/CompressedShadowContainer.h:21-25): length^3 cells. */
+CPVS_API int cpvs_container_create(cpvs_ctx* ctx, uint32_t length, cpvs_container** out);
+CPVS_API int cpvs_container_destroy(cpvs_container* c);
+/* set(unique_ptr<CompressedShadow>, x, y, z) (src/CompressedShadowContainer.h:34-39). The container
+ * copies what it needs; the caller keeps ownership of `s` and may destroy it afterwards. */
+CPVS_API int cpvs_container_set(cpvs_container* c, const cpvs_shadow* s, uint32_t x, uint32_t y, uint32_t z);
+/* Same, for a cell built elsewhere (another GPU / rank): the finished DAG words are handed over. */
+CPVS_API int cpvs_container_set_dag(cpvs_container* c, const uint32_t* words, uint64_t count, int mem, uint32_t num_levels,
+		int leafmasks, uint32_t x, uint32_t y, uint32_t z);
+/* copyToGPU() (src/CompressedShadowContainer.cpp:31-46): combineDAGs (:52-69) + createTopLevelGrid
+ * (:71-91) into two device buffers. Every cell must have been set. */
+CPVS_API int cpvs_container_finalize(cpvs_container* c);
+CPVS_API int cpvs_container_info(const cpvs_container* c, uint64_t* dag_words, uint32_t* grid_cells, uint32_t* dag_levels,
+		uint32_t* grid_levels);
+/* Host copies of the combined DAG and of the grid (either pointer may be NULL). */
+CPVS_API int cpvs_container_copy(const cpvs_container* c, uint32_t* dag_out_host, uint32_t* grid_out_host);
+/* traverse.cs traverse() (shader/traverse.cs:75-133) on NDC points: path over the whole virtual
+ * volume, grid cell pick, sentinels, DAG descent. out = count NodeVisibility bytes (0 or 1). */
+CPVS_API int cpvs_container_lookup_ndc(const cpvs_container* c, const float* ndc, int64_t count, int mem, uint8_t* out);
+/* evaluate(positionsWS, lightViewProj, visibilities) (src/CompressedShadowContainer.cpp:93-124,
+ * shader/traverse.cs:135-149): positions = width*height rgba32f texels (xyz used), light_view_proj =
+ * column-major mat4 (glm::value_ptr order), visibilities = width*height r8 texels (0 or 255). */
+CPVS_API int cpvs_container_evaluate(const cpvs_container* c, const float* positions, uint32_t width, uint32_t height, int mem,
+		const float light_view_proj[16], uint8_t* visibilities);
+/* setFilterSize (src/CompressedShadowContainer.h:71-73): stored, unused -- as in the reference
+ * (shader/traverse.cs:16-17). */
+CPVS_API int cpvs_container_set_filter_size(cpvs_container* c, uint32_t size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPVS_B200_H */

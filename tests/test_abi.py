@@ -1,0 +1,76 @@
+"""CPU suite: the C-ABI library builds for sm_100a, loads, and exports every symbol the header declares.
+No compute call is made here (there is no GPU in the build container)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    from cpvs_b200 import build
+    return build.build()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "cpvs_b200.h")).read()
+    return sorted(set(re.findall(r"CPVS_API[^;(]*?\b(cpvs_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_expected_surface():
+    names = declared_symbols()
+    assert len(names) >= 30
+    for required in ("cpvs_minmax_build", "cpvs_shadow_create", "cpvs_shadow_copy_dag", "cpvs_shadow_lookup_ndc",
+                     "cpvs_container_set", "cpvs_container_finalize", "cpvs_container_evaluate"):
+        assert required in names
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    for name in declared_symbols():
+        assert hasattr(lib, name), name
+
+
+def test_python_bindings_cover_header(lib_path):
+    import cpvs_b200
+    assert sorted(cpvs_b200.SIGNATURES) == declared_symbols()
+    cpvs_b200.load_library()
+    assert b"sm_100a" in cpvs_b200.load_library().cpvs_version()
+
+
+def test_header_compiles_as_plain_c(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text('#include "cpvs_b200.h"\nint main(void){ cpvs_shadow_info i; (void)i; return CPVS_OK; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "t.o")])
+
+
+def test_sass_is_sm100a_only(lib_path):
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "--list-elf", lib_path], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_gpu_fails_loudly(lib_path):
+    """Without a B200 the product must refuse to work, not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import cpvs_b200
+    with pytest.raises(cpvs_b200.CpvsError):
+        cpvs_b200.Context(0)
+
+
+def test_product_does_not_reference_oracle():
+    """The shipped package must not import, link or execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "cpvs_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "pyoracle" not in text and "oracle_port" not in text and "libcpvs_ref" not in text and "libcpvs_oracle" not in text, f
+    for f in os.listdir(os.path.join(ROOT, "include")):
+        assert "oracle" not in open(os.path.join(ROOT, "include", f)).read().lower() or f.endswith(".md")

@@ -1,0 +1,275 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle and the
+committed golden vectors. Bit-exact throughout: pyramid floats, DAG words, per-level node counts,
+lookup results. Nothing here reads /root/reference."""
+import numpy as np
+import pytest
+
+import cpvs_b200
+from cpvs_b200 import synth
+from test_oracle import TRAVERSE_8, TRAVERSE_16, TRAVERSE_32, sweep_points_32
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(ctx, depth, zt=0, zn=1, leaf=True):
+    mm = cpvs_b200.MinMaxHierarchy(depth, ctx)
+    return mm, cpvs_b200.CompressedShadow.create(mm, zt, zn, leaf)
+
+
+def _assert_same_dag(gpu_shadow, ora_shadow, tag):
+    a, b = gpu_shadow.getDAG(), ora_shadow.dag()
+    assert a.size == b.size, (tag, a.size, b.size)
+    bad = np.nonzero(a != b)[0]
+    assert bad.size == 0, (tag, "first differing word", int(bad[0]), hex(a[bad[0]]), hex(b[bad[0]]))
+
+
+# ---- pyramid -------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("n", [2, 4, 8, 16, 64, 128, 256, 1024])
+def test_pyramid_bits(gpu_ctx, oracle, n):
+    rng = np.random.default_rng(n)
+    d = rng.random((n, n), dtype=np.float32)
+    d[rng.random((n, n)) < 0.05] = 0.0
+    d[rng.random((n, n)) < 0.02] = -0.0
+    mm = cpvs_b200.MinMaxHierarchy(d, gpu_ctx)
+    om = oracle.MinMax(d)
+    assert mm.getNumLevels() == om.num_levels()
+    for lvl in range(mm.getNumLevels()):
+        assert np.array_equal(mm.getLevel(lvl).view(np.uint32), om.level(lvl).view(np.uint32)), lvl
+
+
+def test_pyramid_reference_vectors(gpu_ctx, golden):
+    vec, _ = golden
+    for name in ("depths8x8", "depths16x16", "depths32x32", "minmax8x8", "minmax4x4"):
+        mm = cpvs_b200.MinMaxHierarchy(vec[name], gpu_ctx)
+        for lvl in range(1, mm.getNumLevels()):
+            assert np.array_equal(mm.getLevel(lvl).view(np.uint32), vec["%s.minmax%d" % (name, lvl)].view(np.uint32))
+    mm = cpvs_b200.MinMaxHierarchy(vec["minmax8x8"], gpu_ctx)  # MinMaxTest.get (reference test/MinMaxTest.cpp:41-55)
+    assert mm.getNumLevels() == 4
+    assert mm.getMin(0, 0, 0) == 0.0 and mm.getMax(1, 0, 0) == np.float32(0.9) and mm.getMax(2, 0, 0) == 1.0
+    assert mm.getMax(3, 0, 0) == 1.0 and mm.getMin(3, 0, 0) == 0.0
+
+
+# ---- DAG words -----------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["depths8x8", "depths16x16", "depths32x32", "minmax8x8"])
+def test_reference_fixture_dags(gpu_ctx, golden, name):
+    vec, _ = golden
+    _, sh = _build(gpu_ctx, vec[name])
+    assert np.array_equal(sh.getDAG(), vec[name + ".dag"])
+    _, sh = _build(gpu_ctx, vec[name], leaf=False)
+    assert np.array_equal(sh.getDAG(), vec[name + ".dag_noleaf"])
+    if name == "depths16x16":
+        for t in (0, 1):
+            _, sh = _build(gpu_ctx, vec[name], t, 2)
+            assert np.array_equal(sh.getDAG(), vec["%s.dag_z%dof2" % (name, t)])
+
+
+def test_constant_maps(gpu_ctx, golden):
+    vec, _ = golden
+    for val, vis in ((0.0, cpvs_b200.SHADOW), (1.0, cpvs_b200.VISIBLE), (0.5, cpvs_b200.PARTIAL)):
+        _, sh = _build(gpu_ctx, np.full((64, 64), val, np.float32))
+        assert np.array_equal(sh.getDAG(), vec["const%.1f.dag" % val])
+        assert sh.getTotalVisibility() == vis
+
+
+def test_golden_synthetic_table(gpu_ctx, golden):
+    """Words, FNV digests and lookup digests the unmodified reference produced (tests/golden)."""
+    _, meta = golden
+    pts = synth.lookups(meta["lookups"]["count"], meta["lookups"]["seed"])
+    for row in meta["synthetic"]:
+        _, sh = _build(gpu_ctx, synth.depth_map(row["kind"], row["n"]), row["z_tile"], row["z_num"], row["leafmasks"])
+        dag = sh.getDAG()
+        assert dag.size == row["words"], row
+        assert "%016x" % synth.fnv64(dag) == row["fnv64"], row
+        vis = sh.traverse(pts, row["leafmasks"])
+        assert int((vis == 1).sum()) == row["lit"], row
+        assert "%016x" % synth.fnv64(vis.astype(np.uint32)) == row["vis_fnv64"], row
+
+
+@pytest.mark.parametrize("kind", ["plane", "terrain", "city"])
+@pytest.mark.parametrize("n", [8, 16, 32, 128, 512, 2048])
+def test_dag_equals_oracle(gpu_ctx, oracle, kind, n):
+    d = synth.depth_map(kind, n)
+    om = oracle.MinMax(d)
+    mm = cpvs_b200.MinMaxHierarchy(d, gpu_ctx)
+    cases = [(0, 1, True), (0, 1, False)] if n <= 128 else [(0, 1, True)]
+    if n >= 16:
+        cases += [(1, 2, True), (2, 4, True), (1, 3, True)]
+    for zt, zn, leaf in cases:
+        g = cpvs_b200.CompressedShadow.create(mm, zt, zn, leaf)
+        o = oracle.Shadow(om, zt, zn, leaf)
+        _assert_same_dag(g, o, (kind, n, zt, zn, leaf))
+        svo, dagn, _ = g.level_counts()
+        osvo, ouniq = o.level_counts()
+        assert np.array_equal(svo, osvo), (kind, n, zt, zn, leaf)
+        assert np.array_equal(dagn, ouniq), (kind, n, zt, zn, leaf)
+        assert g.getTotalVisibility() == o.total_visibility()
+
+
+def test_random_maps_equal_oracle(gpu_ctx, oracle):
+    """High-entropy and plateau maps: many unique leaves, many duplicates, edge depths."""
+    rng = np.random.default_rng(7)
+    for n in (8, 16, 32, 64, 256):
+        for trial in range(4):
+            d = rng.random((n, n), dtype=np.float32)
+            if trial == 1:
+                d = (np.round(d * 8) / np.float32(8) * np.float32(0.999) + np.float32(0.0004)).astype(np.float32)
+            if trial == 2:  # depths sitting exactly on slice mid-points and slice boundaries
+                k = rng.integers(0, n, size=(n, n))
+                d = ((k + rng.choice([0.0, 0.5], size=(n, n))) / n).astype(np.float32)
+                d = np.clip(d + np.float32(1e-3) * (rng.random((n, n)) < 0.5), 0.001, 0.999).astype(np.float32)
+            if trial == 3:
+                d = np.repeat(np.repeat(rng.random((n // 8, n // 8), dtype=np.float32), 8, 0), 8, 1) * np.float32(0.97) + np.float32(0.013)
+            for leaf in (True, False) if n <= 64 else (True,):
+                _, g = _build(gpu_ctx, d, leaf=leaf)
+                o = oracle.Shadow(oracle.MinMax(d), leafmasks=leaf)
+                _assert_same_dag(g, o, (n, trial, leaf))
+
+
+def test_z_boundary_depths(gpu_ctx, oracle):
+    """Depths whose d*H lands exactly on integers / half-integers, and tiny depths (k rounding)."""
+    n = 64
+    vals = np.array([(i + f) / n for i in range(0, n, 3) for f in (0.0, 0.5, 0.4999999, 0.5000001)] +
+                    [1e-8, 0.0078124995, 0.007812501, 0.99999994, 0.2499999, 0.25000003], np.float32)
+    rng = np.random.default_rng(1)
+    d = rng.choice(vals, size=(n, n)).astype(np.float32)
+    d[:8, :8] = np.float32(0.3)  # keep the root PARTIAL but avoid SURVEY.md N2 (fully dyadic levels)
+    d[8:16, :8] = np.float32(0.71)
+    for zt, zn in ((0, 1), (1, 2)):
+        _, g = _build(gpu_ctx, d, zt, zn)
+        o = oracle.Shadow(oracle.MinMax(d), zt, zn)
+        _assert_same_dag(g, o, (zt, zn))
+
+
+# ---- lookups ---------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name,table,leaf", [("depths8x8", TRAVERSE_8, False), ("depths16x16", TRAVERSE_16, True),
+                                             ("depths32x32", TRAVERSE_32, True)])
+def test_traverse_known_answers(gpu_ctx, golden, name, table, leaf):
+    """The reference's own traverse tests (test/CompressedShadowTest.cpp:50-152) on the CUDA lookup."""
+    vec, _ = golden
+    _, sh = _build(gpu_ctx, vec[name])
+    pts = np.array([p for p, _ in table], np.float32)
+    assert list(sh.traverse(pts, leaf)) == [v for _, v in table]
+    if name == "depths32x32":
+        vis, sha = sweep_points_32()
+        assert (sh.traverse(vis) == 1).all() and (sh.traverse(sha) == 0).all()
+
+
+@pytest.mark.parametrize("kind", ["plane", "terrain", "city"])
+def test_lookups_equal_oracle(gpu_ctx, oracle, kind):
+    pts = synth.lookups(300000)
+    pts[:16] = np.array([[-1, -1, -1], [1, 1, 1], [1, -1, 1], [-1, 1, -1]] * 4, np.float32)
+    for n, zt, zn, leaf in ((1024, 0, 1, True), (256, 1, 2, True), (64, 0, 1, False)):
+        d = synth.depth_map(kind, n)
+        _, g = _build(gpu_ctx, d, zt, zn, leaf)
+        o = oracle.Shadow(oracle.MinMax(d), zt, zn, leaf)
+        assert np.array_equal(g.traverse(pts, leaf), o.traverse(pts, leaf)), (kind, n)
+
+
+def test_lookup_clamps_out_of_range(gpu_ctx, oracle):
+    d = synth.depth_map("terrain", 128)
+    _, g = _build(gpu_ctx, d)
+    o = oracle.Shadow(oracle.MinMax(d))
+    pts = np.array([[-3, 0, 0], [3, 0, 0], [0, -2, 5], [0, 0, -9], [np.nan, 0, 0], [np.inf, -np.inf, 0]], np.float32)
+    assert np.array_equal(g.traverse(pts), o.traverse(pts))
+
+
+def test_empty_lookup(gpu_ctx):
+    _, g = _build(gpu_ctx, synth.depth_map("plane", 64))
+    assert g.traverse(np.zeros((0, 3), np.float32)).size == 0
+
+
+# ---- container / top-level grid -----------------------------------------------------------------------
+
+@pytest.mark.parametrize("kind,n,length", [("terrain", 64, 2), ("city", 128, 2), ("plane", 32, 4)])
+def test_container_equals_oracle(gpu_ctx, oracle, kind, n, length):
+    cont = cpvs_b200.CompressedShadowContainer(length, gpu_ctx)
+    ocont = oracle.Container(length)
+    keep = []
+    for y in range(length):
+        for x in range(length):
+            d = synth.depth_map(kind, n, (x, y), length)
+            mm = cpvs_b200.MinMaxHierarchy(d, gpu_ctx)
+            om = oracle.MinMax(d)
+            for z in range(length):  # createShadowTiles (reference src/DeferredRenderer.cpp:150-163)
+                cont.set(cpvs_b200.CompressedShadow.create(mm, z, length), x, y, z)
+                osh = oracle.Shadow(om, z, length)
+                keep.append(osh)
+                ocont.set(osh, x, y, z)
+    cont.copyToGPU()
+    ocont.finalize()
+    dag, grid = cont.dag_and_grid()
+    odag, ogrid = ocont.dag_and_grid()
+    assert np.array_equal(grid, ogrid) and np.array_equal(dag, odag)
+    info = cont.info()
+    assert info["grid_levels"] == {2: 1, 4: 2}[length] and info["grid_cells"] == length ** 3
+    pts = synth.lookups(200000, seed=5)
+    assert np.array_equal(cont.lookup_ndc(pts), ocont.lookup_ndc(pts))
+    # evaluate(): world positions through an orthographic light matrix (column-major, glm order)
+    rng = np.random.default_rng(0)
+    pos = np.concatenate([rng.uniform(-10, 10, (48, 64, 3)), np.ones((48, 64, 1))], axis=2).astype(np.float32)
+    m = np.array([[0.09, 0, 0, 0], [0, 0.1, 0, 0], [0.01, 0.02, 0.095, 0], [0.03, -0.02, 0.01, 1]], np.float32)  # m[col][row]
+    assert np.array_equal(cont.evaluate(pos, m), ocont.evaluate(pos, m))
+
+
+def test_single_shadow_container(gpu_ctx, oracle):
+    """CompressedShadowContainer(unique_ptr<CompressedShadow>) (reference src/CompressedShadowContainer.h:28-32)."""
+    d = synth.depth_map("city", 256)
+    _, g = _build(gpu_ctx, d)
+    cont = cpvs_b200.CompressedShadowContainer(g)
+    cont.copyToGPU()
+    pts = synth.lookups(50000, seed=8)
+    assert np.array_equal(cont.lookup_ndc(pts), g.traverse(pts))
+    dag, grid = cont.dag_and_grid()
+    assert np.array_equal(dag, g.getDAG()) and list(grid) == [0]
+
+
+# ---- full-size, size-independent properties ----------------------------------------------------------
+
+@pytest.mark.parametrize("kind", ["terrain", "city"])
+def test_large_map_decodes_to_depth(gpu_ctx, kind):
+    """4096^2 (the oracle would take minutes): every looked-up voxel must decode to z+0.5 <= d*H, the
+    per-level counts must be consistent, and a rebuild must give identical words (determinism)."""
+    n = 4096
+    d = synth.depth_map(kind, n)
+    _, g = _build(gpu_ctx, d)
+    pts = synth.lookups(1000000)
+    path = (((pts + np.float32(1)) * np.float32(0.5)) * np.float32(n - 1)).astype(np.int32)
+    lit = (path[:, 2].astype(np.float32) + np.float32(0.5)) <= d[path[:, 1], path[:, 0]] * np.float32(n)
+    assert np.array_equal(g.traverse(pts), lit.astype(np.uint8))
+    svo, dagn, words = g.level_counts()
+    assert (dagn <= svo).all() and int(words.sum()) == int(g.info.words) and dagn[g.getNumLevels() - 2] == 1
+    _, g2 = _build(gpu_ctx, d)
+    assert synth.fnv64(g.getDAG()) == synth.fnv64(g2.getDAG())
+
+
+def test_survey_4096_digests(gpu_ctx):
+    """words / FNV of the reference at 4096^2 (libm-free generators only)."""
+    for kind, words, digest in (("plane", 17495, "6cebb7d538e96084"), ("city", 176032, "ea44abc8910b0f2c")):
+        _, g = _build(gpu_ctx, synth.depth_map(kind, 4096))
+        dag = g.getDAG()
+        assert dag.size == words and "%016x" % synth.fnv64(dag) == digest
+
+
+# ---- errors ----------------------------------------------------------------------------------------
+
+def test_argument_errors(gpu_ctx):
+    with pytest.raises(cpvs_b200.CpvsError) as e:
+        cpvs_b200.MinMaxHierarchy(np.zeros((12, 12), np.float32), gpu_ctx)
+    assert e.value.code == cpvs_b200.EINVAL
+    with pytest.raises(cpvs_b200.CpvsError):
+        cpvs_b200.MinMaxHierarchy(np.zeros((8, 16), np.float32), gpu_ctx)
+    mm = cpvs_b200.MinMaxHierarchy(np.zeros((4, 4), np.float32), gpu_ctx)
+    with pytest.raises(cpvs_b200.CpvsError):  # numLevels > 3 (reference src/CompressedShadow.cpp:46)
+        cpvs_b200.CompressedShadow.create(mm)
+    mm = cpvs_b200.MinMaxHierarchy(synth.depth_map("plane", 64), gpu_ctx)
+    with pytest.raises(cpvs_b200.CpvsError):
+        cpvs_b200.CompressedShadow.create(mm, 2, 2)
+    sh = cpvs_b200.CompressedShadow.create(cpvs_b200.MinMaxHierarchy(synth.depth_map("plane", 8), gpu_ctx))
+    with pytest.raises(cpvs_b200.CpvsError):
+        sh.traverse(np.zeros((1, 3), np.float32), True)
+    cont = cpvs_b200.CompressedShadowContainer(2, gpu_ctx)
+    with pytest.raises(cpvs_b200.CpvsError):
+        cont.copyToGPU()
