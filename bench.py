@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the cpvs hot path on B200 (BASELINE.json: DAG build Msamples/s at
+16K^2, shadow lookups G/s, % of HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl own|reference]
+
+One step = one pass of the hot path over one depth map: MinMaxHierarchy + CompressedShadow::create on
+the device (N=1: BASELINE configs[1], one 16K^2 terrain map, leafmasks on, single DAG; N>1: configs[2],
+every rank builds one 16K^2 xy-tile of the 4x4 virtual 64K^2 map with its 4 z-slices, no collective on
+the data path). `value` is measured with the depth map resident in HBM; `e2e` goes through the same
+C-ABI calls with the depth map in pinned host memory. Lookups (1M random NDC points) are timed next to
+it. `--impl reference` times the reference's own CPU implementation (oracle/_ref, the unmodified
+sources compiled by oracle/Makefile) on bounded samples of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "dag_build_msamples_per_s"
+UNIT = "Msamples/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--size", type=int, default=16384, help="side of one depth map")
+    ap.add_argument("--kind", default="terrain", choices=["plane", "terrain", "city"])
+    ap.add_argument("--lookups", type=int, default=1000000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="do not run the nvidia-smi sampler (debugging)")
+    ap.add_argument("--ref-sample", type=int, default=1024, help="side of one reference sample window")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """SM clock and throttle reasons sampled through NVML while the timed region runs (the same counters
+    as the nvidia-smi line of B200_PROFILING.md; NVML in-process because a concurrently starting
+    nvidia-smi process stalls CUDA API calls of the timed steps for tens of milliseconds)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.handle = None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = int(visible.split(",")[device]) if visible and visible.split(",")[device].isdigit() else device
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception as exc:  # noqa: BLE001
+            self.error = str(exc)
+            self.handle = None
+
+    def _poll(self):
+        nv = self.nvml
+        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksEventReasonHwPowerBrakeSlowdown: "hw_power_brake_slowdown"}
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop_flag.wait(0.02)
+
+    def start(self):
+        if self.handle is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+
+    def stop(self):
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: %s" % getattr(self, "error", "not started")]}
+        self.stop_flag.set()
+        self.thread.join()
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.sm_max,
+                "samples": len(self.samples), "reasons": sorted(self.reasons), "source": "nvml"}
+
+
+# ---- reference arm / cpu baseline -----------------------------------------------------------------
+
+def reference_sample(size, kind, window, threads, steps, warmup):
+    """Unmodified reference (oracle/_ref) on `threads` independent windows of the workload per step, one
+    host thread each (the reference's create is single-threaded; its tile driver runs one create per
+    thread, src/DeferredRenderer.cpp:150-163). Returns (Msamples/s, ms per step, description, kind)."""
+    from oracle import pyoracle as O
+    from cpvs_b200 import synth
+    kind_used = "reference" if O.have_ref() else "port"
+    tiles = size // window
+    maps = [synth.depth_map(kind, window, (t % tiles, (t // tiles) % tiles), tiles, threads=1) for t in range(threads)]
+
+    def one(d):
+        if kind_used == "reference":
+            O.ref_time_build(d)
+        else:
+            O.Shadow(O.MinMax(d, "port")).dag()
+
+    def step():
+        ths = [threading.Thread(target=one, args=(m,)) for m in maps]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    samples = threads * window * window * steps
+    desc = ("%d windows of %dx%d texels of the %dx%d %s map per step, one %s MinMaxHierarchy+CompressedShadow::create per host thread"
+            % (threads, window, window, size, size, kind, "reference" if kind_used == "reference" else "oracle-port"))
+    return samples / dt / 1e6, dt / steps * 1e3, desc, kind_used
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, 64))
+    value, ms, desc, kind_used = reference_sample(args.size, args.kind, args.ref_sample, threads, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32/u32", "data": "synthetic", "config": workload_config(args, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind_used, "sample": desc},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args, n_gpus):
+    if n_gpus == 1:
+        return {"workload": "configs[1]: %dx%d synthetic %s depth map, leafmasks on, single DAG (MinMaxHierarchy + CompressedShadow::create) "
+                            "+ %d random NDC lookups" % (args.size, args.size, args.kind, args.lookups),
+                "depth_map": "%dx%d f32 (%.0f MiB) > L2, regenerated state per step; no explicit L2 flush needed" % (args.size, args.size, args.size * args.size * 4 / 2**20),
+                "tiles_per_rank": 1, "z_slices": 1}
+    return {"workload": "configs[2]: 64K^2 virtual %s map as 4x4x4 CompressedShadowContainer grid; every rank builds one %dx%d xy-tile "
+                        "(1 pyramid + 4 z-slice DAGs) per step, host-side gather of sizes only" % (args.kind, args.size, args.size),
+            "depth_map": "%dx%d f32 per rank > L2" % (args.size, args.size), "tiles_per_rank": 1, "z_slices": 4}
+
+
+# ---- own arm -----------------------------------------------------------------------------------------
+
+def build_bytes(n, info, leaf):
+    """SURVEY.md 8(d) algorithmic bytes of one build from the actual per-level node counts."""
+    nl = int(info.num_levels)
+    w_svo = w_merged = nodes = 0
+    for lvl in range(nl - 1):
+        size = 17 if (leaf and lvl == 2) else 9
+        w_svo += size * int(info.svo_nodes[lvl])
+        w_merged += size * int(info.dag_nodes[lvl])
+        nodes += int(info.svo_nodes[lvl])
+    return (40.0 / 3.0) * n * n + 8.0 * w_svo + 4.0 * w_merged + 8.0 * nodes + 4.0 * int(info.words)
+
+
+def run_own(args):
+    import torch
+    import torch.distributed as dist
+    import cpvs_b200
+    from cpvs_b200 import build as cbuild, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        cbuild.build()
+    if world > 1:
+        dist.barrier()
+    n, K, W = args.size, args.steps, args.warmup
+    stream = torch.cuda.current_stream()
+    ctx = cpvs_b200.Context(local, stream=stream.cuda_stream)
+
+    # workload: N=1 whole map, one DAG; N>1 xy-tile `rank` of the 4x4 virtual map, 4 z-slices
+    if world == 1:
+        tile, tps, z_slices = (0, 0), 1, 1
+    else:
+        tile, tps, z_slices = (rank % 4, (rank // 4) % 4), 4, 4
+    host = torch.empty((n, n), dtype=torch.float32, pin_memory=True)
+    depth_np = host.numpy()
+    synth.depth_map(args.kind, n, tile, tps, out=depth_np)
+    depth = host.to("cuda", non_blocking=True)
+    torch.cuda.synchronize()
+
+    def step(src, keep=False):
+        mm = cpvs_b200.MinMaxHierarchy(src, ctx, n=n)
+        shadows = [cpvs_b200.CompressedShadow.create(mm, z, z_slices) for z in range(z_slices)]
+        if keep:
+            return mm, shadows
+        infos = [s.info for s in shadows]
+        timing = (mm.timing(), [s.phase_ms() for s in shadows], [s.info.build_ms for s in shadows])
+        for s in shadows:
+            s.close()
+        mm.close()
+        return infos, timing
+
+    # parity property on the bench workload itself: every looked-up voxel decodes to z + 0.5 <= d * H.
+    # These handles stay alive (the lookups below run on them), so they are built before the warm-up.
+    mm, shadows = step(depth, keep=True)
+    pts_np = synth.lookups(args.lookups)
+    res = n * z_slices  # z resolution of the whole tile column
+    path = (((pts_np + np.float32(1)) * np.float32(0.5)) * np.float32(n - 1)).astype(np.int32)
+    for z, sh in enumerate(shadows):
+        vis = sh.traverse(pts_np)
+        zz = path[:, 2] + z * n
+        lit = (zz.astype(np.float32) + np.float32(0.5)) <= depth_np[path[:, 1], path[:, 0]] * np.float32(res)
+        if not np.array_equal(vis, lit.astype(np.uint8)):
+            raise SystemExit("bench.py: lookup results do not decode to the depth map (z-slice %d)" % z)
+    main_shadow = max(shadows, key=lambda s: int(s.info.words))
+    info0 = main_shadow.info
+    leaf = bool(info0.leafmasks)
+    for _ in range(W):
+        step(depth)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed: device-resident input ----
+    sampler = ClockSampler(local)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    launches0 = ctx.launch_count
+    if not args.no_clocks:
+        sampler.start()
+    ev0.record(stream)
+    timings = []
+    for _ in range(K):
+        timings.append(step(depth)[1])
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / K
+    value = world * n * n / (ms_step * 1e-3) / 1e6
+
+    # ---- timed: end to end from pinned host memory through the C ABI ----
+    for _ in range(min(W, 2)):
+        step(depth_np)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step(depth_np)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / K
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = world * n * n / (e2e_ms * 1e-3) / 1e6
+    d2h = z_slices * (192 * 8 + 32 * 8 + 4)  # size scalars read back per create
+
+    # ---- lookups on the resident DAG ----
+    pts = torch.from_numpy(pts_np).cuda()
+    out = torch.empty(args.lookups, dtype=torch.uint8, device="cuda")
+    for _ in range(W):
+        main_shadow.traverse(pts, True, out)
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    l0.record(stream)
+    for _ in range(K):
+        main_shadow.traverse(pts, True, out)
+    l1.record(stream)
+    torch.cuda.synchronize()
+    lookup_ms = l0.elapsed_time(l1) / K
+    t0 = time.perf_counter()
+    for _ in range(K):
+        main_shadow.traverse(pts_np)
+    lookup_e2e_ms = (time.perf_counter() - t0) * 1e3 / K
+
+    # ---- gather of sizes on the host (the only cross-rank step of a tiled build) ----
+    sizes = [(int(s.info.words), int(s.info.total_visibility)) for s in shadows]
+    gathered = [sizes]
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, sizes)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        # per-phase device time, averaged over the timed steps (sum over z-slices within a step)
+        names = cpvs_b200.PHASE_NAMES
+        phase = {nm: statistics.mean(sum(p[nm] for p in tm[1]) for tm in timings) for nm in names}
+        pyr_total = statistics.mean(tm[0][0] for tm in timings)
+        pyr_base = statistics.mean(tm[0][1] for tm in timings)
+        create_ms = statistics.mean(sum(tm[2]) for tm in timings)
+        n_leaves = int(info0.svo_nodes[2]) if leaf else 0
+        u_leaves = int(info0.dag_nodes[2]) if leaf else 0
+        # algorithmic bytes per launch of the single-kernel phases (DESIGN.md "kernels")
+        kernels = {
+            "pyramid_base": ((4.0 + 8.0 * (1 / 4 + 1 / 16 + 1 / 64 + 1 / 256 + 1 / 1024)) * n * n, pyr_base),
+            "leaves": (n_leaves * (256.0 + 8 + 64 + 8 + 2), phase["leaves"] / z_slices),
+            "leaf_insert": (n_leaves * (8.0 + 4 + 8) + (n_leaves - u_leaves) * 128.0, phase["leaf_insert"] / z_slices),
+            "emit_leaves": (u_leaves * (4.0 + 4 + 2 + 64) + 4.0 * int(info0.dag_words[2] if leaf else 0), phase["emit_leaves"] / z_slices),
+        }
+        dom = max(kernels, key=lambda k: kernels[k][1])
+        dom_bytes, dom_ms = kernels[dom]
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        bbytes = build_bytes(n, info0, leaf)
+        step_ms_device = pyr_total + create_ms
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/u32", "data": "synthetic",
+            "config": workload_config(args, world), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": n * n * 4, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
+                         "kernels": {k: {"algorithmic_bytes": v[0], "ms": v[1], "gbs": (v[0] / (v[1] * 1e-3) / 1e9 if v[1] > 0 else 0.0)}
+                                     for k, v in kernels.items()}},
+            "build_roofline": {"algorithmic_bytes": bbytes, "roofline_ms": bbytes / (peak * 1e9) * 1e3, "device_ms": step_ms_device,
+                               "frac": (bbytes / (peak * 1e9) * 1e3) / step_ms_device, "formula": "SURVEY.md 8(d)"},
+            "phases_ms": dict(phase, pyramid=pyr_total, pyramid_base=pyr_base, create_total=create_ms),
+            "dag": {"words": int(info0.words), "mbytes": int(info0.words) * 4 / 1e6, "num_levels": int(info0.num_levels),
+                    "svo_nodes": [int(v) for v in info0.svo_nodes[:info0.num_levels - 1]],
+                    "dag_nodes": [int(v) for v in info0.dag_nodes[:info0.num_levels - 1]]},
+            "lookups": {"count": args.lookups, "value": args.lookups / (lookup_ms * 1e-3) / 1e9, "unit": "Glookups/s", "ms": lookup_ms,
+                        "e2e_value": args.lookups / (lookup_e2e_ms * 1e-3) / 1e9, "e2e_ms": lookup_e2e_ms,
+                        "stream_bytes": args.lookups * 13},
+            "grid_gather": {"cells": sum(len(g) for g in gathered), "words": sum(w for g in gathered for w, _ in g)},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = max(1, min(os.cpu_count() or 1, 64))
+            v, ms, desc, kind_used = reference_sample(n, args.kind, args.ref_sample, cores, 3, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind_used, "sample": desc, "ms_per_step": ms}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -21,6 +21,8 @@ OK, EINVAL, ENOMEM, ECUDA, EOVERFLOW, EINTERNAL = range(6)
 MEM_HOST, MEM_DEVICE = 0, 1
 SHADOW, VISIBLE, PARTIAL = 0, 1, 2
 MAX_LEVELS = 32
+NUM_PHASES = 9
+PHASE_NAMES = ["count", "expand", "leaves", "leaf_insert", "leaf_resolve", "inner_merge", "bases", "emit_inner", "emit_leaves"]
 GRID_CELL_SHADOWED = 0x0FFFFFFF
 GRID_CELL_VISIBLE = 0x0FFFFFFE
 
@@ -35,7 +37,7 @@ class ShadowInfo(ctypes.Structure):
     _fields_ = [("num_levels", ctypes.c_uint32), ("leafmasks", ctypes.c_uint32), ("total_visibility", ctypes.c_uint32),
                 ("reserved", ctypes.c_uint32), ("words", ctypes.c_uint64), ("svo_nodes", ctypes.c_uint64 * MAX_LEVELS),
                 ("dag_nodes", ctypes.c_uint64 * MAX_LEVELS), ("dag_words", ctypes.c_uint64 * MAX_LEVELS),
-                ("build_ms", ctypes.c_float), ("reserved_f", ctypes.c_float)]
+                ("build_ms", ctypes.c_float), ("phase_ms", ctypes.c_float * NUM_PHASES)]
 
 
 # name -> (restype, argtypes); also the list tests check against include/cpvs_b200.h
@@ -56,6 +58,7 @@ SIGNATURES = {
     "cpvs_minmax_size": (_I, [_VP]),
     "cpvs_minmax_level": (_I, [_VP, _I, _VP]),
     "cpvs_minmax_level_device": (_VP, [_VP, _I]),
+    "cpvs_minmax_timing": (_I, [_VP, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
     "cpvs_shadow_create": (_I, [_VP, _VP, _U32, _U32, _I, _PP]),
     "cpvs_shadow_create_from_depth": (_I, [_VP, _VP, _I, _I, _U32, _U32, _I, _PP]),
     "cpvs_shadow_destroy": (_I, [_VP]),
@@ -182,6 +185,12 @@ class MinMaxHierarchy:
         _check(self._lib.cpvs_minmax_level(self.handle, level, out.ctypes.data))
         return out
 
+    def timing(self):
+        """(total ms, fused base kernel ms) of the build, from CUDA events."""
+        total, base = ctypes.c_float(), ctypes.c_float()
+        _check(self._lib.cpvs_minmax_timing(self.handle, ctypes.byref(total), ctypes.byref(base)))
+        return total.value, base.value
+
     def getMin(self, level, x, y):
         lvl = self.getLevel(level)
         return float(lvl[y, x] if level == 0 else lvl[y, x, 0])
@@ -236,6 +245,9 @@ class CompressedShadow:
     @property
     def dag_device_ptr(self):
         return int(self._lib.cpvs_shadow_dag_device(self.handle) or 0)
+
+    def phase_ms(self):
+        return {name: float(self.info.phase_ms[i]) for i, name in enumerate(PHASE_NAMES)}
 
     def level_counts(self):
         """(SVO nodes, DAG nodes, DAG words) per level, index = level."""

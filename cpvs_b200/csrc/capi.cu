@@ -4,9 +4,12 @@
 // No CPU fallback lives here: every entry point either drives the CUDA kernels or returns an error.
 #include "../../include/cpvs_b200.h"
 
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -46,6 +49,19 @@ inline u64 pow2AtLeast(u64 v) {
 
 __global__ void storeU64Kernel(u64* dst, u64 value) { *dst = value; }
 
+// CPVS_TRACE=1: host wall-clock between orchestration steps, to stderr.
+struct HostTrace {
+	bool on;
+	std::chrono::steady_clock::time_point last;
+	HostTrace() : on(std::getenv("CPVS_TRACE") != nullptr), last(std::chrono::steady_clock::now()) {}
+	void mark(const char* what) {
+		if (!on) return;
+		const auto now = std::chrono::steady_clock::now();
+		fprintf(stderr, "[cpvs trace] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
+		last = now;
+	}
+};
+
 }  // namespace
 
 struct cpvs_ctx {
@@ -53,6 +69,13 @@ struct cpvs_ctx {
 	cudaStream_t own;
 	cudaStream_t stream;
 	u64 launches;
+	// Scratch arena for cpvs_shadow_create: one device allocation, grown when a build needs more and
+	// kept between calls, carved by bump pointer -- no allocator traffic in steady state. Builds on one
+	// context are serialised by `buildLock` (use one context per host thread for concurrent builds).
+	std::mutex buildLock;
+	char* arena;
+	size_t arenaBytes;
+	u64* scalars;  // 192 device words: per-level counters of the build in flight
 };
 
 struct cpvs_minmax {
@@ -62,6 +85,7 @@ struct cpvs_minmax {
 	float* ownedDepth;   // device copy when built from host memory
 	float* levelStorage; // levels 1.. in one allocation
 	const float* level[kMaxLevels];
+	cudaEvent_t evStart, evBase, evStop;
 };
 
 struct cpvs_shadow {
@@ -112,6 +136,20 @@ struct Scratch {
 	}
 };
 
+// Bump-pointer carving of the context arena; run once with base == nullptr to size it.
+struct ArenaCarver {
+	char* base;
+	size_t offset = 0;
+	explicit ArenaCarver(char* b) : base(b) {}
+	template <typename T>
+	T* take(u64 count) {
+		offset = (offset + 255) & ~size_t(255);
+		T* p = base ? reinterpret_cast<T*>(base + offset) : nullptr;
+		offset += (count ? count : 1) * sizeof(T);
+		return p;
+	}
+};
+
 struct LevelArrays {
 	u64 n = 0;
 	u64* coords = nullptr;
@@ -149,10 +187,14 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 	if (!ctx) return fail(CPVS_ENOMEM, "cpvs_ctx_create: host allocation");
 	ctx->device = device;
 	ctx->launches = 0;
+	ctx->arena = nullptr;
+	ctx->arenaBytes = 0;
+	ctx->scalars = nullptr;
 	cudaError_t e = cudaStreamCreateWithFlags(&ctx->own, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->scalars), 192 * sizeof(u64));
 	if (e != cudaSuccess) {
 		delete ctx;
-		return fail(CPVS_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+		return fail(CPVS_ECUDA, "cpvs_ctx_create: %s", cudaGetErrorString(e));
 	}
 	ctx->stream = ctx->own;
 	*out = ctx;
@@ -163,6 +205,8 @@ int cpvs_ctx_destroy(cpvs_ctx* ctx) {
 	if (!ctx) return CPVS_OK;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
+	if (ctx->arena) cudaFree(ctx->arena);
+	if (ctx->scalars) cudaFree(ctx->scalars);
 	cudaStreamDestroy(ctx->own);
 	delete ctx;
 	return CPVS_OK;
@@ -170,6 +214,9 @@ int cpvs_ctx_destroy(cpvs_ctx* ctx) {
 
 int cpvs_ctx_set_stream(cpvs_ctx* ctx, void* cuda_stream) {
 	if (!ctx) return fail(CPVS_EINVAL, "cpvs_ctx_set_stream: ctx is NULL");
+	std::lock_guard<std::mutex> guard(ctx->buildLock);
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);  // the arena is ordered on the old stream
 	ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own;
 	return CPVS_OK;
 }
@@ -224,7 +271,12 @@ int cpvs_minmax_build(cpvs_ctx* ctx, const float* depth, int n, int mem, cpvs_mi
 		mm->level[k] = lv[k];
 	}
 	lv[0] = const_cast<float*>(mm->level[0]);
-	ctx->launches += launchPyramid(mm->level[0], n, lv, levels, ctx->stream);
+	cudaEventCreate(&mm->evStart);
+	cudaEventCreate(&mm->evBase);
+	cudaEventCreate(&mm->evStop);
+	cudaEventRecord(mm->evStart, ctx->stream);
+	ctx->launches += launchPyramid(mm->level[0], n, lv, levels, mm->evBase, ctx->stream);
+	cudaEventRecord(mm->evStop, ctx->stream);
 	e = cudaGetLastError();
 	if (e != cudaSuccess) {
 		cpvs_minmax_destroy(mm);
@@ -239,7 +291,24 @@ int cpvs_minmax_destroy(cpvs_minmax* mm) {
 	cudaSetDevice(mm->ctx->device);
 	if (mm->levelStorage) cudaFreeAsync(mm->levelStorage, mm->ctx->stream);
 	if (mm->ownedDepth) cudaFreeAsync(mm->ownedDepth, mm->ctx->stream);
+	if (mm->evStart) {
+		cudaEventDestroy(mm->evStart);
+		cudaEventDestroy(mm->evBase);
+		cudaEventDestroy(mm->evStop);
+	}
 	delete mm;
+	return CPVS_OK;
+}
+
+int cpvs_minmax_timing(const cpvs_minmax* mm, float* totalMs, float* baseKernelMs) {
+	if (!mm) return fail(CPVS_EINVAL, "cpvs_minmax_timing: NULL argument");
+	CPVS_CUDA(cudaSetDevice(mm->ctx->device));
+	CPVS_CUDA(cudaEventSynchronize(mm->evStop));
+	float total = 0.f, base = 0.f;
+	CPVS_CUDA(cudaEventElapsedTime(&total, mm->evStart, mm->evStop));
+	CPVS_CUDA(cudaEventElapsedTime(&base, mm->evStart, mm->evBase));
+	if (totalMs) *totalMs = total;
+	if (baseKernelMs) *baseKernelMs = mm->n >= 128 ? base : 0.f;
 	return CPVS_OK;
 }
 
@@ -280,76 +349,102 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	const int minLevel = useLeaf ? 2 : 0;            // src/CompressedShadow.cpp:30-32
 	const int lastInner = useLeaf ? 3 : 0;
 
-	cudaEvent_t evStart, evStop;
-	CPVS_CUDA(cudaEventCreate(&evStart));
-	CPVS_CUDA(cudaEventCreate(&evStop));
-	struct EventGuard {
-		cudaEvent_t a, b;
-		~EventGuard() {
-			cudaEventDestroy(a);
-			cudaEventDestroy(b);
+	// ev[i] opens phase i (CPVS_PHASE_*), ev[CPVS_NUM_PHASES] closes the last one
+	struct PhaseEvents {
+		cudaEvent_t ev[CPVS_NUM_PHASES + 1];
+		PhaseEvents() { std::memset(ev, 0, sizeof(ev)); }
+		~PhaseEvents() {
+			for (cudaEvent_t e : ev)
+				if (e) cudaEventDestroy(e);
 		}
-	} eventGuard{evStart, evStop};
-	CPVS_CUDA(cudaEventRecord(evStart, st));
+	} phases;
+	for (cudaEvent_t& e : phases.ev) CPVS_CUDA(cudaEventCreate(&e));
+	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_COUNT], st));
 
-	Scratch scratch(st);
+	std::lock_guard<std::mutex> buildGuard(ctx->buildLock);
 	PyramidView pyr;
 	pyr.n = mm->n;
 	pyr.numLevels = L;
 	for (int k = 0; k < kMaxLevels; ++k) pyr.level[k] = k < L ? mm->level[k] : nullptr;
 
 	// device scalars: [0..31] SVO counts, [32..63] unique, [64..95] words, [96..127] bases, [128..159] child totals, [160] total words
-	u64* dScalars;
-	CPVS_CUDA(scratch.alloc(&dScalars, 192));
+	u64* dScalars = ctx->scalars;
 	CPVS_CUDA(cudaMemsetAsync(dScalars, 0, 192 * sizeof(u64), st));
 	u64 *dCounts = dScalars, *dUnique = dScalars + 32, *dWords = dScalars + 64, *dBases = dScalars + 96, *dChildTotal = dScalars + 128,
 		*dTotal = dScalars + 160;
 
+	HostTrace trace;
+	trace.mark("setup");
 	// 1. exact node counts of every level (closed form), so all buffers can be sized up front
 	ctx->launches += launchCountNodes(pyr, zTileIndex, zTileNum, minLevel, dCounts, st);
 	u64 hScalars[192];
 	CPVS_CUDA(cudaMemcpyAsync(hScalars, dCounts, 32 * sizeof(u64), cudaMemcpyDeviceToHost, st));
 	CPVS_CUDA(cudaStreamSynchronize(st));
+	trace.mark("count kernels + sync");
 	LevelArrays lv[kMaxLevels];
 	lv[top].n = 1;
 	for (int l = top - 1; l >= minLevel; --l) lv[l].n = lv[l + 1].n ? hScalars[l] : 0;
 	for (int l = minLevel; l <= top; ++l)
 		if (lv[l].n >= (1ull << 31)) return fail(CPVS_EOVERFLOW, "level %d has %llu nodes (limit 2^31)", l, (unsigned long long)lv[l].n);
 
-	// 2. per-level arrays
+	// 2. per-level arrays, carved out of the context arena
 	u64 scanTiles = 0, scanLaunches = 0, maxTable = 0;
 	for (int l = top; l >= minLevel; --l) {
-		LevelArrays& a = lv[l];
-		if (!a.n) continue;
-		const bool leaf = useLeaf && l == 2;
-		CPVS_CUDA(scratch.alloc(&a.coords, a.n));
-		CPVS_CUDA(scratch.alloc(&a.masks, a.n));
-		CPVS_CUDA(scratch.alloc(&a.uid, a.n));
-		CPVS_CUDA(scratch.alloc(&a.firstList, a.n));
-		CPVS_CUDA(scratch.alloc(&a.wordOffset, a.n));
-		if (leaf) {
-			CPVS_CUDA(scratch.alloc(&a.leafBits, a.n * 8));
-			CPVS_CUDA(scratch.alloc(&a.leafHash, a.n));
-		} else {
-			CPVS_CUDA(scratch.alloc(&a.firstChild, a.n));
-			scanTiles += (a.n + kScanTile - 1) / kScanTile;
+		const u64 n = lv[l].n;
+		if (!n) continue;
+		if (!(useLeaf && l == 2)) {
+			scanTiles += (n + kScanTile - 1) / kScanTile;
 			++scanLaunches;
 		}
-		if (a.n > 1) {
-			scanTiles += (a.n + kScanTile - 1) / kScanTile;
+		if (n > 1) {
+			scanTiles += (n + kScanTile - 1) / kScanTile;
 			++scanLaunches;
-			const u64 t = pow2AtLeast(a.n * 2 < 1024 ? 1024 : a.n * 2);
+			const u64 t = pow2AtLeast(n * 2 < 1024 ? 1024 : n * 2);
 			if (t > maxTable) maxTable = t;
 		}
 	}
-	ScanTileState* dTiles;
-	u32* dTickets;
+	ScanTileState* dTiles = nullptr;
+	u32* dTickets = nullptr;
 	u64* dTable = nullptr;
-	CPVS_CUDA(scratch.alloc(&dTiles, scanTiles));
-	CPVS_CUDA(scratch.alloc(&dTickets, scanLaunches));
-	CPVS_CUDA(cudaMemsetAsync(dTiles, 0, (scanTiles ? scanTiles : 1) * sizeof(ScanTileState), st));
-	CPVS_CUDA(cudaMemsetAsync(dTickets, 0, (scanLaunches ? scanLaunches : 1) * sizeof(u32), st));
-	if (maxTable) CPVS_CUDA(scratch.alloc(&dTable, maxTable));
+	auto carve = [&](ArenaCarver& ar) {
+		dTiles = ar.take<ScanTileState>(scanTiles);
+		dTickets = ar.take<u32>(scanLaunches);
+		dTable = ar.take<u64>(maxTable);
+		for (int l = top; l >= minLevel; --l) {
+			LevelArrays& a = lv[l];
+			if (!a.n) continue;
+			a.coords = ar.take<u64>(a.n);
+			a.masks = ar.take<u16>(a.n);
+			a.uid = ar.take<u32>(a.n);
+			a.firstList = ar.take<u32>(a.n);
+			a.wordOffset = ar.take<u32>(a.n);
+			if (useLeaf && l == 2) {
+				a.leafBits = ar.take<u64>(a.n * 8);
+				a.leafHash = ar.take<u64>(a.n);
+			} else {
+				a.firstChild = ar.take<u32>(a.n);
+			}
+		}
+	};
+	ArenaCarver sizing(nullptr);
+	carve(sizing);
+	if (sizing.offset > ctx->arenaBytes) {
+		if (ctx->arena) CPVS_CUDA(cudaFree(ctx->arena));
+		ctx->arena = nullptr;
+		ctx->arenaBytes = 0;
+		const size_t want = sizing.offset + sizing.offset / 8;
+		cudaError_t ae = cudaMalloc(reinterpret_cast<void**>(&ctx->arena), want);
+		if (ae != cudaSuccess) return fail(CPVS_ENOMEM, "scratch arena of %zu bytes: %s", want, cudaGetErrorString(ae));
+		ctx->arenaBytes = want;
+	}
+	ArenaCarver real(ctx->arena);
+	carve(real);
+	trace.mark("arena carve");
+	// tile states and tickets sit at the front of the arena: one memset clears both
+	CPVS_CUDA(cudaMemsetAsync(ctx->arena, 0, reinterpret_cast<char*>(dTable) - ctx->arena, st));
+	auto tableSizeFor = [](u64 n) { return pow2AtLeast(n * 2 < 1024 ? 1024 : n * 2); };
+	// the table of the first (lowest) level is cleared here so that its insert phase is one kernel
+	if (lv[minLevel].n > 1) CPVS_CUDA(cudaMemsetAsync(dTable, 0xFF, tableSizeFor(lv[minLevel].n) * sizeof(u64), st));
 	u64 tileCursor = 0, launchCursor = 0;
 	auto nextScan = [&](u64 n) {
 		ScanLaunch s{dTickets + launchCursor, dTiles + tileCursor};
@@ -358,7 +453,9 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		return s;
 	};
 
+	trace.mark("memsets");
 	// 3. breadth-first construction, top level first (src/CompressedShadow.cpp:87-169)
+	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_EXPAND], st));
 	storeU64Kernel<<<1, 1, 0, st>>>(lv[top].coords, packCoord(0, 0, zTileIndex * 2));
 	++ctx->launches;
 	for (int l = top; l >= lastInner && lv[l].n; --l) {
@@ -366,13 +463,20 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		ctx->launches += launchExpandLevel(pyr, l, zTileNum, lv[l].coords, lv[l].n, lv[l].masks, lv[l].firstChild, childCoords,
 				dChildTotal + l, nextScan(lv[l].n), st);
 	}
+	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAVES], st));
 	if (useLeaf && lv[2].n)  // constructLastLevels (src/CompressedShadow.cpp:171-190)
 		ctx->launches += launchBuildLeaves(pyr, zTileNum, lv[2].coords, lv[2].n, lv[2].leafBits, lv[2].leafHash, lv[2].masks, st);
 
 	// 4. bottom-up merge (src/CompressedShadow.cpp:215-241)
+	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAF_INSERT], st));
+	if (!(useLeaf && lv[2].n)) {
+		CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAF_RESOLVE], st));
+		CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_INNER_MERGE], st));
+	}
 	for (int l = minLevel; l <= top; ++l) {
 		LevelArrays& a = lv[l];
 		if (!a.n) continue;
+		const bool leafLevel = useLeaf && l == 2;
 		MergeLevelArgs m;
 		m.n = a.n;
 		m.leaf = (useLeaf && l == 2) ? 1 : 0;
@@ -382,7 +486,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		m.firstChild = a.firstChild;
 		m.childUid = l > minLevel ? lv[l - 1].uid : nullptr;
 		m.table = dTable;
-		m.tableSize = pow2AtLeast(a.n * 2 < 1024 ? 1024 : a.n * 2);
+		m.tableSize = tableSizeFor(a.n);
 		m.uid = a.uid;
 		m.firstList = a.firstList;
 		m.wordOffset = a.wordOffset;
@@ -390,16 +494,20 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		m.wordCount = dWords + l;
 		ScanLaunch s{nullptr, nullptr};
 		if (a.n > 1) {
-			CPVS_CUDA(cudaMemsetAsync(dTable, 0xFF, m.tableSize * sizeof(u64), st));
+			if (l != minLevel) CPVS_CUDA(cudaMemsetAsync(dTable, 0xFF, m.tableSize * sizeof(u64), st));
 			s = nextScan(a.n);
 		}
-		ctx->launches += launchMergeLevel(m, s, st);
+		ctx->launches += launchMergeLevel(m, s, leafLevel ? phases.ev[CPVS_PHASE_LEAF_RESOLVE] : nullptr, st);
+		if (leafLevel) CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_INNER_MERGE], st));
 	}
+	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_BASES], st));
 
 	// 5. level bases and the total size (src/CompressedShadow.cpp:326-392)
 	ctx->launches += launchLevelBases(dWords, dBases, top, minLevel, dTotal, st);
+	trace.mark("enqueue expand..bases");
 	CPVS_CUDA(cudaMemcpyAsync(hScalars, dScalars, 192 * sizeof(u64), cudaMemcpyDeviceToHost, st));
 	CPVS_CUDA(cudaStreamSynchronize(st));
+	trace.mark("sync after bases");
 	CPVS_CUDA(cudaGetLastError());
 	for (int l = top; l > minLevel; --l)
 		if (lv[l].n && l >= lastInner && hScalars[128 + l] != lv[l - 1].n)
@@ -418,10 +526,13 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		return fail(CPVS_ENOMEM, "DAG allocation of %llu words: %s", (unsigned long long)totalWords, cudaGetErrorString(e));
 	}
 
+	trace.mark("dag alloc");
 	// 6. write every unique node once, in its final place
+	cudaEventRecord(phases.ev[CPVS_PHASE_EMIT_INNER], st);
 	for (int l = top; l >= minLevel; --l) {
 		const LevelArrays& a = lv[l];
 		if (!a.n) continue;
+		if (useLeaf && l == 2) cudaEventRecord(phases.ev[CPVS_PHASE_EMIT_LEAVES], st);
 		EmitLevelArgs em;
 		em.n = a.n;
 		em.leaf = (useLeaf && l == 2) ? 1 : 0;
@@ -438,13 +549,16 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		em.dag = s->dag;
 		ctx->launches += launchEmitLevel(em, st);
 	}
+	if (!(useLeaf && lv[2].n)) cudaEventRecord(phases.ev[CPVS_PHASE_EMIT_LEAVES], st);
 	u32 rootMask = 0;
 	e = cudaMemcpyAsync(&rootMask, s->dag, sizeof(u32), cudaMemcpyDeviceToHost, st);
-	if (e == cudaSuccess) e = cudaEventRecord(evStop, st);
+	if (e == cudaSuccess) e = cudaEventRecord(phases.ev[CPVS_NUM_PHASES], st);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(st);
 	if (e == cudaSuccess) e = cudaGetLastError();
-	float ms = 0.f;
-	if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, evStart, evStop);
+	trace.mark("emit + final sync");
+	float ms = 0.f, phaseMs[CPVS_NUM_PHASES] = {0};
+	if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, phases.ev[0], phases.ev[CPVS_NUM_PHASES]);
+	for (int i = 0; i < CPVS_NUM_PHASES && e == cudaSuccess; ++i) e = cudaEventElapsedTime(&phaseMs[i], phases.ev[i], phases.ev[i + 1]);
 	if (e != cudaSuccess) {
 		cudaFreeAsync(s->dag, st);
 		delete s;
@@ -460,6 +574,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		s->info.dag_words[l] = hScalars[64 + l];
 	}
 	s->info.build_ms = ms;
+	for (int i = 0; i < CPVS_NUM_PHASES; ++i) s->info.phase_ms[i] = phaseMs[i];
 	*out = s;
 	return CPVS_OK;
 }

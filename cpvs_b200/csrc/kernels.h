@@ -7,7 +7,8 @@ namespace cpvs {
 
 // ---- pyramid.cu: MinMaxHierarchy (reference src/MinMaxHierarchy.cpp:9-97) ----
 // levels[k] (k >= 1) points at (n>>k)^2 float2 (min,max); levels[0] = depth.
-int launchPyramid(const float* depth, int n, float* const* levels, int numLevels, cudaStream_t stream);
+// afterBase (optional) is recorded right after the fused base kernel.
+int launchPyramid(const float* depth, int n, float* const* levels, int numLevels, cudaEvent_t afterBase, cudaStream_t stream);
 
 // ---- svo.cu: constructSvo (reference src/CompressedShadow.cpp:87-190) ----
 struct PyramidView {
@@ -46,7 +47,8 @@ struct MergeLevelArgs {
 	u64* uniqueCount;      // out: number of unique nodes
 	u64* wordCount;        // out: compressed words of the level
 };
-int launchMergeLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaStream_t stream);
+// afterInsert (optional) is recorded between the insert kernel and the rank scan.
+int launchMergeLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaEvent_t afterInsert, cudaStream_t stream);
 
 // ---- emit.cu: compress (reference src/CompressedShadow.cpp:326-392) ----
 struct EmitLevelArgs {

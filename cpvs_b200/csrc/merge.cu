@@ -159,9 +159,10 @@ __global__ void singleNodeKernel(const u16* __restrict__ masks, int leaf, u32* u
 
 }  // namespace
 
-int launchMergeLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaStream_t stream) {
+int launchMergeLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaEvent_t afterInsert, cudaStream_t stream) {
 	if (a.n == 1) {
 		singleNodeKernel<<<1, 1, 0, stream>>>(a.masks, a.leaf, a.uid, a.firstList, a.wordOffset, a.uniqueCount, a.wordCount);
+		if (afterInsert) cudaEventRecord(afterInsert, stream);
 		return 1;
 	}
 	const unsigned blocks = (unsigned)((a.n + 255) / 256);
@@ -169,6 +170,7 @@ int launchMergeLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaStream_t stre
 		insertLeavesKernel<<<blocks, 256, 0, stream>>>(a.leafBits, a.leafHash, a.n, a.table, a.tableSize - 1, a.uid);
 	else
 		insertInnerKernel<<<blocks, 256, 0, stream>>>(a.masks, a.firstChild, a.childUid, a.n, a.table, a.tableSize - 1, a.uid);
+	if (afterInsert) cudaEventRecord(afterInsert, stream);
 	const u32 tiles = (u32)((a.n + kScanTile - 1) / kScanTile);
 	resolveKernel<<<tiles, kScanThreads, 0, stream>>>(a.table, a.masks, a.leaf, a.n, a.uid, a.firstList, a.wordOffset, a.uniqueCount,
 			a.wordCount, scan, tiles);

@@ -96,7 +96,7 @@ __global__ void pyramidLevelKernel(const float* __restrict__ src, int srcChannel
 
 }  // namespace
 
-int launchPyramid(const float* depth, int n, float* const* levels, int numLevels, cudaStream_t stream) {
+int launchPyramid(const float* depth, int n, float* const* levels, int numLevels, cudaEvent_t afterBase, cudaStream_t stream) {
 	int launches = 0;
 	int next = 1;
 	if (n >= 128) {
@@ -106,6 +106,7 @@ int launchPyramid(const float* depth, int n, float* const* levels, int numLevels
 		++launches;
 		next = 6;
 	}
+	if (afterBase) cudaEventRecord(afterBase, stream);
 	for (int k = next; k < numLevels; ++k) {
 		const int side = n >> k;
 		dim3 block(side >= 16 ? 16 : side, side >= 16 ? 16 : side);

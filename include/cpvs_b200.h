@@ -51,6 +51,19 @@ extern "C" {
 
 #define CPVS_MAX_LEVELS 32
 
+/* Phases of cpvs_shadow_create timed with CUDA events on the context's stream (cpvs_shadow_info.phase_ms).
+ * Phases marked (1 kernel) bracket exactly one kernel launch. */
+#define CPVS_PHASE_COUNT 0        /* closed-form node counts per level + host read-back */
+#define CPVS_PHASE_EXPAND 1       /* breadth-first expansion of all inner levels */
+#define CPVS_PHASE_LEAVES 2       /* leaf build (1 kernel) */
+#define CPVS_PHASE_LEAF_INSERT 3  /* leaf level: hash-table insert (1 kernel) */
+#define CPVS_PHASE_LEAF_RESOLVE 4 /* leaf level: table clear + rank scan + unique ids */
+#define CPVS_PHASE_INNER_MERGE 5  /* all inner levels: clear + insert + rank scan + unique ids */
+#define CPVS_PHASE_BASES 6        /* level bases + host read-back of sizes */
+#define CPVS_PHASE_EMIT_INNER 7   /* compressed inner nodes, all levels */
+#define CPVS_PHASE_EMIT_LEAVES 8  /* compressed leaves (1 kernel) */
+#define CPVS_NUM_PHASES 9
+
 /* Grid sentinels written by CompressedShadowContainer::createTopLevelGrid
  * (src/CompressedShadowContainer.cpp:8-9). The lookup tests these same values. */
 #define CPVS_GRID_CELL_SHADOWED 0x0FFFFFFFu
@@ -89,6 +102,9 @@ CPVS_API int cpvs_minmax_size(const cpvs_minmax* mm);
 /* getLevel(level) (src/MinMaxHierarchy.h:67-72) copied to the host: level 0 is n*n depths, level k>=1
  * is (n>>k)^2 interleaved (min,max) pairs -- the layout getMin/getMax index (src/MinMaxHierarchy.h:31-55). */
 CPVS_API int cpvs_minmax_level(const cpvs_minmax* mm, int level, float* out_host);
+/* Device time of the build (CUDA events on the context's stream): whole call, and the fused base
+ * kernel that produces levels 1..5 alone (0 when the map is too small for it). Synchronises. */
+CPVS_API int cpvs_minmax_timing(const cpvs_minmax* mm, float* total_ms, float* base_kernel_ms);
 /* Device pointer of a level (same layout), for zero-copy consumers. */
 CPVS_API const float* cpvs_minmax_level_device(const cpvs_minmax* mm, int level);
 
@@ -104,7 +120,7 @@ typedef struct cpvs_shadow_info {
 	uint64_t dag_nodes[CPVS_MAX_LEVELS]; /* nodes per level after merging, index = level */
 	uint64_t dag_words[CPVS_MAX_LEVELS]; /* compressed words per level */
 	float build_ms;                      /* device time of the create call (CUDA events) */
-	float reserved_f;
+	float phase_ms[CPVS_NUM_PHASES];     /* see CPVS_PHASE_* */
 } cpvs_shadow_info;
 
 /* CompressedShadow::create(const MinMaxHierarchy&, zTileIndex, zTileNum)
