@@ -21,8 +21,8 @@ OK, EINVAL, ENOMEM, ECUDA, EOVERFLOW, EINTERNAL = range(6)
 MEM_HOST, MEM_DEVICE = 0, 1
 SHADOW, VISIBLE, PARTIAL = 0, 1, 2
 MAX_LEVELS = 32
-NUM_PHASES = 9
-PHASE_NAMES = ["count", "expand", "leaves", "leaf_insert", "leaf_resolve", "inner_merge", "bases", "emit_inner", "emit_leaves"]
+NUM_PHASES = 10
+PHASE_NAMES = ["count", "expand", "leaves", "leaf_table", "leaf_insert", "leaf_resolve", "inner_merge", "bases", "emit_inner", "emit_leaves"]
 GRID_CELL_SHADOWED = 0x0FFFFFFF
 GRID_CELL_VISIBLE = 0x0FFFFFFE
 

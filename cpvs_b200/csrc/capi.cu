@@ -158,7 +158,7 @@ struct LevelArrays {
 	u32* uid = nullptr;
 	u32* firstList = nullptr;
 	u32* wordOffset = nullptr;
-	u64* leafBits = nullptr;
+	u32* leafCodes = nullptr;
 	u64* leafHash = nullptr;
 };
 
@@ -406,9 +406,12 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	ScanTileState* dTiles = nullptr;
 	u32* dTickets = nullptr;
 	u64* dTable = nullptr;
+	u32* dSketch = nullptr;
+	const bool needSketch = useLeaf && lv[2].n > 0, haveLeaves = useLeaf && lv[2].n > 1;
 	auto carve = [&](ArenaCarver& ar) {
 		dTiles = ar.take<ScanTileState>(scanTiles);
 		dTickets = ar.take<u32>(scanLaunches);
+		dSketch = ar.take<u32>(needSketch ? kSketchWords : 0);
 		dTable = ar.take<u64>(maxTable);
 		for (int l = top; l >= minLevel; --l) {
 			LevelArrays& a = lv[l];
@@ -419,7 +422,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 			a.firstList = ar.take<u32>(a.n);
 			a.wordOffset = ar.take<u32>(a.n);
 			if (useLeaf && l == 2) {
-				a.leafBits = ar.take<u64>(a.n * 8);
+				a.leafCodes = ar.take<u32>(a.n * 8);
 				a.leafHash = ar.take<u64>(a.n);
 			} else {
 				a.firstChild = ar.take<u32>(a.n);
@@ -440,11 +443,14 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	ArenaCarver real(ctx->arena);
 	carve(real);
 	trace.mark("arena carve");
-	// tile states and tickets sit at the front of the arena: one memset clears both
+	// tile states, tickets and the leaf sketch sit at the front of the arena: one memset clears them all
 	CPVS_CUDA(cudaMemsetAsync(ctx->arena, 0, reinterpret_cast<char*>(dTable) - ctx->arena, st));
 	auto tableSizeFor = [](u64 n) { return pow2AtLeast(n * 2 < 1024 ? 1024 : n * 2); };
-	// the table of the first (lowest) level is cleared here so that its insert phase is one kernel
-	if (lv[minLevel].n > 1) CPVS_CUDA(cudaMemsetAsync(dTable, 0xFF, tableSizeFor(lv[minLevel].n) * sizeof(u64), st));
+	// the table of the lowest level is cleared here so that its insert phase is one kernel (the leaf
+	// level instead sizes and clears its table on the device, once the sketch is filled)
+	if (!useLeaf && lv[minLevel].n > 1) CPVS_CUDA(cudaMemsetAsync(dTable, 0xFF, tableSizeFor(lv[minLevel].n) * sizeof(u64), st));
+	u64 *dSketchBits = dScalars + 161, *dLeafTableMask = dScalars + 162;
+	u32* dErrorFlag = reinterpret_cast<u32*>(dScalars + 163);
 	u64 tileCursor = 0, launchCursor = 0;
 	auto nextScan = [&](u64 n) {
 		ScanLaunch s{dTickets + launchCursor, dTiles + tileCursor};
@@ -465,9 +471,15 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	}
 	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAVES], st));
 	if (useLeaf && lv[2].n)  // constructLastLevels (src/CompressedShadow.cpp:171-190)
-		ctx->launches += launchBuildLeaves(pyr, zTileNum, lv[2].coords, lv[2].n, lv[2].leafBits, lv[2].leafHash, lv[2].masks, st);
+		ctx->launches += launchBuildLeaves(pyr, zTileNum, lv[2].coords, lv[2].n, lv[2].leafCodes, lv[2].leafHash, lv[2].masks,
+				dSketch, st);
 
 	// 4. bottom-up merge (src/CompressedShadow.cpp:215-241)
+	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAF_TABLE], st));
+	if (haveLeaves) {
+		ctx->launches += launchSketchPopcount(dSketch, dSketchBits, st);
+		ctx->launches += launchSizeLeafTable(dTable, tableSizeFor(lv[2].n), dSketchBits, dLeafTableMask, st);
+	}
 	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAF_INSERT], st));
 	if (!(useLeaf && lv[2].n)) {
 		CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAF_RESOLVE], st));
@@ -480,13 +492,16 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		MergeLevelArgs m;
 		m.n = a.n;
 		m.leaf = (useLeaf && l == 2) ? 1 : 0;
-		m.leafBits = a.leafBits;
+		m.leafCodes = a.leafCodes;
 		m.leafHash = a.leafHash;
 		m.masks = a.masks;
 		m.firstChild = a.firstChild;
 		m.childUid = l > minLevel ? lv[l - 1].uid : nullptr;
 		m.table = dTable;
 		m.tableSize = tableSizeFor(a.n);
+		m.sketchBits = dSketchBits;
+		m.tableMaskDev = dLeafTableMask;
+		m.errorFlag = dErrorFlag;
 		m.uid = a.uid;
 		m.firstList = a.firstList;
 		m.wordOffset = a.wordOffset;
@@ -513,6 +528,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		if (lv[l].n && l >= lastInner && hScalars[128 + l] != lv[l - 1].n)
 			return fail(CPVS_EINTERNAL, "level %d: expansion produced %llu nodes, count pass predicted %llu", l - 1,
 					(unsigned long long)hScalars[128 + l], (unsigned long long)lv[l - 1].n);
+	if (hScalars[163] != 0) return fail(CPVS_EINTERNAL, "merge table overflow (leaf table mask %llu)", (unsigned long long)hScalars[162]);
 	const u64 totalWords = hScalars[160];
 	if (totalWords > (1ull << 32)) return fail(CPVS_EOVERFLOW, "DAG needs %llu words; offsets are 32-bit", (unsigned long long)totalWords);
 
@@ -540,7 +556,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		em.firstList = a.firstList;
 		em.wordOffset = a.wordOffset;
 		em.levelBase = dBases + l;
-		em.leafBits = a.leafBits;
+		em.leafCodes = a.leafCodes;
 		em.masks = a.masks;
 		em.firstChild = a.firstChild;
 		em.childUid = l > minLevel ? lv[l - 1].uid : nullptr;

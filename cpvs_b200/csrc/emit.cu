@@ -35,7 +35,16 @@ __global__ void __launch_bounds__(256) emitInnerKernel(EmitLevelArgs a) {
 	}
 }
 
-// Two lanes... no: one thread per unique leaf; 64 B read, <= 68 B written.
+// One thread per unique leaf: expands the k-code (nibble x of word y = lit slices of texel (x,y)) into
+// the 64-bit masks of the PARTIAL slices, bit x + 8y = lit (createLeafmask, src/CompressedShadowUtil.cpp:59-78).
+__device__ __forceinline__ u32 rowBits(u32 code, u32 slice) {
+	// nibble k > slice  <=>  bit 3 of (k + 7 - slice); nibbles are <= 8 so nothing carries
+	u32 y = ((code + (7u - slice) * 0x11111111u) >> 3) & 0x11111111u;
+	y = (y | (y >> 3)) & 0x03030303u;
+	y = (y | (y >> 6)) & 0x000F000Fu;
+	return (y | (y >> 12)) & 0xFFu;
+}
+
 __global__ void __launch_bounds__(256) emitLeavesKernel(EmitLevelArgs a) {
 	const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= *a.uniqueCount) return;
@@ -43,18 +52,12 @@ __global__ void __launch_bounds__(256) emitLeavesKernel(EmitLevelArgs a) {
 	const u32 mask = a.masks[j];
 	u32* out = a.dag + (*a.levelBase + a.wordOffset[r]);
 	*out++ = mask;
-	const ulonglong2* src = reinterpret_cast<const ulonglong2*>(a.leafBits + (u64)j * 8);
-#pragma unroll
-	for (int i = 0; i < 4; ++i) {
-		const ulonglong2 v = src[i];
-		if ((mask >> (4 * i)) & 2u) {
-			*out++ = (u32)v.x;
-			*out++ = (u32)(v.x >> 32);
-		}
-		if ((mask >> (4 * i + 2)) & 2u) {
-			*out++ = (u32)v.y;
-			*out++ = (u32)(v.y >> 32);
-		}
+	const uint4* src = reinterpret_cast<const uint4*>(a.leafCodes + (u64)j * 8);
+	const uint4 c0 = src[0], c1 = src[1];
+	for (u32 slice = 0; slice < 8; ++slice) {
+		if (!((mask >> (2 * slice)) & 2u)) continue;
+		*out++ = rowBits(c0.x, slice) | (rowBits(c0.y, slice) << 8) | (rowBits(c0.z, slice) << 16) | (rowBits(c0.w, slice) << 24);
+		*out++ = rowBits(c1.x, slice) | (rowBits(c1.y, slice) << 8) | (rowBits(c1.z, slice) << 16) | (rowBits(c1.w, slice) << 24);
 	}
 }
 

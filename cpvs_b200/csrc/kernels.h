@@ -25,28 +25,38 @@ int launchCountNodes(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, int m
 int launchExpandLevel(const PyramidView& pyr, int level, u32 zTileNum, const u64* coords, u64 n, u16* masks,
 		u32* firstChild, u64* childCoords, u64* childTotal, ScanLaunch scan, cudaStream_t stream);
 
-// Level-2 nodes: 8 x u64 slice masks per leaf (bits[leaf*8 + z']), a 64-bit content hash and the
-// 16-bit 1x1x8 childmask (2 bits per slice).
-int launchBuildLeaves(const PyramidView& pyr, u32 zTileNum, const u64* coords, u64 n, u64* bits, u64* hashes, u16* masks,
+// Level-2 nodes: the leaf's k-code (codes[leaf*8 + row], nibble x = lit slices of texel (x,row)), a
+// 64-bit hash of it and the 16-bit 1x1x8 childmask (2 bits per slice).
+// Also sets one bit per leaf hash in `sketch` (kSketchWords zeroed words): a linear-counting estimate of
+// the number of distinct leaves, used to size the merge table so that it stays resident in L2.
+constexpr u32 kSketchWords = 1u << 22;  // 2^27 bits, 16 MiB
+int launchBuildLeaves(const PyramidView& pyr, u32 zTileNum, const u64* coords, u64 n, u32* codes, u64* hashes, u16* masks, u32* sketch,
 		cudaStream_t stream);
+int launchSketchPopcount(const u32* sketch, u64* setBits, cudaStream_t stream);
 
 // ---- merge.cu: mergeCommonSubtrees (reference src/CompressedShadow.cpp:215-304, Util.h:154-182) ----
 struct MergeLevelArgs {
 	u64 n;                 // nodes in this level
 	int leaf;              // 1: level of leafmask nodes
-	const u64* leafBits;   // leaf: 8 words per node
+	const u32* leafCodes;  // leaf: k-code, 8 words per node
 	const u64* leafHash;   // leaf: content hash per node
 	const u16* masks;      // inner: childmask per node
 	const u32* firstChild; // inner: index of first child in the level below
 	const u32* childUid;   // inner: unique id of every node of the level below
-	u64* table;            // open-addressing table, tableSize slots, pre-filled with 0xFF bytes
-	u64 tableSize;         // power of two
+	u64* table;            // open-addressing table, pre-filled with 0xFF bytes (inner levels) or cleared by
+	                       // the sizing kernel (leaves)
+	u64 tableSize;         // allocated slots, power of two
+	const u64* sketchBits; // leaf level: set bits of the distinct-count sketch (device)
+	u64* tableMaskDev;     // leaf level: (chosen capacity - 1), written by the sizing kernel (device)
+	u32* errorFlag;        // device: set if a probe sequence wraps the whole table
 	u32* uid;              // out: unique id (first-occurrence rank) per node
 	u32* firstList;        // out: node index of the r-th unique node
 	u32* wordOffset;       // out: compressed word offset (inside the level) of the r-th unique node
 	u64* uniqueCount;      // out: number of unique nodes
 	u64* wordCount;        // out: compressed words of the level
 };
+// Leaf level only: picks the table capacity from the sketch's set-bit count and clears that many slots.
+int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* tableMaskDev, cudaStream_t stream);
 // afterInsert (optional) is recorded between the insert kernel and the rank scan.
 int launchMergeLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaEvent_t afterInsert, cudaStream_t stream);
 
@@ -58,7 +68,7 @@ struct EmitLevelArgs {
 	const u32* firstList;
 	const u32* wordOffset;
 	const u64* levelBase;     // device: word offset of this level in the DAG
-	const u64* leafBits;
+	const u32* leafCodes;
 	const u16* masks;
 	const u32* firstChild;
 	const u32* childUid;        // unique ids of the level below

@@ -6,7 +6,8 @@
 // The reference keeps, for every distinct node tuple of a level, its FIRST occurrence, in order, and
 // rewrites the parents' pointers. Here a node tuple is (childmask, unique ids of its PARTIAL
 // children) -- equal tuples <=> equal 9-word reference nodes once the level below is merged -- or,
-// for leaves, the eight 64-bit slice masks. Per level:
+// for leaves, the 32-byte k-code that determines the eight 64-bit slice masks (svo.cu). Per level:
+//   0. (leaves)  the table is sized from a distinct-count sketch filled while the leaves were built.
 //   1. insert:   every node finds its group's slot in an open-addressing table (linear probing). A
 //                slot is (32-bit fingerprint << 32 | smallest node index seen so far); a node joins a
 //                slot only after comparing its full tuple against a member of the group, so grouping
@@ -25,11 +26,11 @@ constexpr u64 kEmpty = ~0ull;
 constexpr u32 kFirstFlag = 0x80000000u;
 
 template <typename Equal>
-__device__ __forceinline__ u32 findGroupSlot(u64* __restrict__ table, u64 tableMask, u64 hash, u32 self, Equal sameTuple) {
+__device__ __forceinline__ u32 findGroupSlot(u64* __restrict__ table, u64 tableMask, u64 hash, u32 self, u32* errorFlag, Equal sameTuple) {
 	const u64 fp = hash >> 32;
 	const u64 key = (fp << 32) | self;
 	u64 slot = hash & tableMask;
-	for (;;) {
+	for (u64 probes = 0; probes <= tableMask; ++probes) {
 		u64 v = ldRelaxed64(table + slot);
 		if (v == kEmpty) {
 			const u64 old = atomicCAS(reinterpret_cast<unsigned long long*>(table + slot), (unsigned long long)kEmpty, (unsigned long long)key);
@@ -39,33 +40,49 @@ __device__ __forceinline__ u32 findGroupSlot(u64* __restrict__ table, u64 tableM
 		if ((v >> 32) == fp) {
 			const u32 other = (u32)v;
 			if (other == self || sameTuple(other)) {
-				atomicMin(reinterpret_cast<unsigned long long*>(table + slot), (unsigned long long)key);
+				// the slot only ever decreases: nothing to do if an earlier node already holds it
+				if (other > self) atomicMin(reinterpret_cast<unsigned long long*>(table + slot), (unsigned long long)key);
 				return (u32)slot;
 			}
 		}
 		slot = (slot + 1) & tableMask;
 	}
+	atomicExch(errorFlag, 1u);  // table full: cannot happen with a sane size estimate; reported to the host
+	return 0u;
 }
 
-__global__ void __launch_bounds__(256) insertLeavesKernel(const u64* __restrict__ bits, const u64* __restrict__ hashes, u64 n, u64* __restrict__ table,
-		u64 tableMask, u32* __restrict__ slotOf) {
+// Leaf table capacity from the distinct-count sketch (linear counting: u ~ -m ln(zero fraction)), rounded
+// up to a power of two with >= 1.5x headroom, then cleared. The result does not depend on the capacity,
+// only the speed does: a table sized for the distinct leaves (not for all leaves) stays in L2.
+__global__ void __launch_bounds__(256) sizeAndClearLeafTableKernel(u64* __restrict__ table, u64 maxSlots, const u64* __restrict__ setBits,
+		u64* __restrict__ tableMaskDev) {
+	const float m = (float)kSketchWords * 32.0f;
+	const float frac = fminf((float)*setBits / m, 0.999f);
+	const float distinct = -m * log1pf(-frac);
+	u64 want = (u64)(distinct * 1.5f) + 4096u;
+	u64 cap = 4096;
+	while (cap < want && cap < maxSlots) cap <<= 1;
+	if (cap > maxSlots) cap = maxSlots;
+	if (blockIdx.x == 0 && threadIdx.x == 0) *tableMaskDev = cap - 1;
+	ulonglong2* t2 = reinterpret_cast<ulonglong2*>(table);
+	for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap / 2; i += (u64)gridDim.x * blockDim.x) t2[i] = make_ulonglong2(kEmpty, kEmpty);
+}
+
+__global__ void __launch_bounds__(256) insertLeavesKernel(const u32* __restrict__ codes, const u64* __restrict__ hashes, u64 n, u64* __restrict__ table,
+		const u64* __restrict__ tableMaskDev, u32* __restrict__ slotOf, u32* errorFlag) {
 	const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= n) return;
-	const ulonglong2* mine = reinterpret_cast<const ulonglong2*>(bits + j * 8);
-	slotOf[j] = findGroupSlot(table, tableMask, hashes[j], (u32)j, [&](u32 other) {
-		const ulonglong2* theirs = reinterpret_cast<const ulonglong2*>(bits + (u64)other * 8);
-		bool same = true;
-#pragma unroll
-		for (int i = 0; i < 4; ++i) {
-			const ulonglong2 a = mine[i], b = theirs[i];
-			same = same && a.x == b.x && a.y == b.y;
-		}
-		return same;
+	const u64 tableMask = *tableMaskDev;
+	const uint4* mine = reinterpret_cast<const uint4*>(codes + j * 8);
+	slotOf[j] = findGroupSlot(table, tableMask, hashes[j], (u32)j, errorFlag, [&](u32 other) {
+		const uint4* theirs = reinterpret_cast<const uint4*>(codes + (u64)other * 8);
+		const uint4 a0 = mine[0], a1 = mine[1], b0 = theirs[0], b1 = theirs[1];
+		return a0.x == b0.x && a0.y == b0.y && a0.z == b0.z && a0.w == b0.w && a1.x == b1.x && a1.y == b1.y && a1.z == b1.z && a1.w == b1.w;
 	});
 }
 
 __global__ void __launch_bounds__(256) insertInnerKernel(const u16* __restrict__ masks, const u32* __restrict__ firstChild,
-		const u32* __restrict__ childUid, u64 n, u64* __restrict__ table, u64 tableMask, u32* __restrict__ slotOf) {
+		const u32* __restrict__ childUid, u64 n, u64* __restrict__ table, u64 tableMask, u32* __restrict__ slotOf, u32* errorFlag) {
 	const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= n) return;
 	const u32 mask = masks[j];
@@ -81,7 +98,7 @@ __global__ void __launch_bounds__(256) insertInnerKernel(const u16* __restrict__
 			h = mix64(h ^ ((u64)uid[c] + 0x9E3779B97F4A7C15ull * (c + 1)));
 		}
 	}
-	slotOf[j] = findGroupSlot(table, tableMask, h, (u32)j, [&](u32 other) {
+	slotOf[j] = findGroupSlot(table, tableMask, h, (u32)j, errorFlag, [&](u32 other) {
 		if (masks[other] != mask) return false;
 		const u32* theirs = childUid + firstChild[other];
 		bool same = true;
@@ -159,6 +176,11 @@ __global__ void singleNodeKernel(const u16* __restrict__ masks, int leaf, u32* u
 
 }  // namespace
 
+int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* tableMaskDev, cudaStream_t stream) {
+	sizeAndClearLeafTableKernel<<<148 * 8, 256, 0, stream>>>(table, maxSlots, setBits, tableMaskDev);
+	return 1;
+}
+
 int launchMergeLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaEvent_t afterInsert, cudaStream_t stream) {
 	if (a.n == 1) {
 		singleNodeKernel<<<1, 1, 0, stream>>>(a.masks, a.leaf, a.uid, a.firstList, a.wordOffset, a.uniqueCount, a.wordCount);
@@ -167,9 +189,9 @@ int launchMergeLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaEvent_t after
 	}
 	const unsigned blocks = (unsigned)((a.n + 255) / 256);
 	if (a.leaf)
-		insertLeavesKernel<<<blocks, 256, 0, stream>>>(a.leafBits, a.leafHash, a.n, a.table, a.tableSize - 1, a.uid);
+		insertLeavesKernel<<<blocks, 256, 0, stream>>>(a.leafCodes, a.leafHash, a.n, a.table, a.tableMaskDev, a.uid, a.errorFlag);
 	else
-		insertInnerKernel<<<blocks, 256, 0, stream>>>(a.masks, a.firstChild, a.childUid, a.n, a.table, a.tableSize - 1, a.uid);
+		insertInnerKernel<<<blocks, 256, 0, stream>>>(a.masks, a.firstChild, a.childUid, a.n, a.table, a.tableSize - 1, a.uid, a.errorFlag);
 	if (afterInsert) cudaEventRecord(afterInsert, stream);
 	const u32 tiles = (u32)((a.n + kScanTile - 1) / kScanTile);
 	resolveKernel<<<tiles, kScanThreads, 0, stream>>>(a.table, a.masks, a.leaf, a.n, a.uid, a.firstList, a.wordOffset, a.uniqueCount,

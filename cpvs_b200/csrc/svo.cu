@@ -121,71 +121,91 @@ __global__ void __launch_bounds__(kScanThreads) expandLevelKernel(const float* _
 //
 // Slice z' of texel i is lit iff (z0+z') + 0.5 <= d_i*H0 (absoluteVisible with minZ=z, maxZ=z+1; exact
 // because z < 2^23). Lit slices form a prefix 0..k_i-1 with k_i = clamp(floor(d_i*H0 - (z0 - 0.5)), 0, 8);
-// the subtraction is rounded toward -inf so the floor is that of the exact difference. Byte i of `t`
-// is the thermometer code (1<<k_i)-1; an 8x8 bit transpose turns texel-major into slice-major bytes,
-// and a byte exchange across the eight lanes leaves lane z' with the 64-bit mask of slice z'.
-__device__ __forceinline__ u64 transpose8x8(u64 x) {
-	u64 t;
-	t = (x ^ (x >> 7)) & 0x00AA00AA00AA00AAull;
-	x = x ^ t ^ (t << 7);
-	t = (x ^ (x >> 14)) & 0x0000CCCC0000CCCCull;
-	x = x ^ t ^ (t << 14);
-	t = (x ^ (x >> 28)) & 0x00000000F0F0F0F0ull;
-	x = x ^ t ^ (t << 28);
-	return x;
+// the subtraction is rounded toward -inf so the floor is that of the exact difference. The 64 counts
+// k_i determine the eight 64-bit slice masks and vice versa, so a leaf is kept as its "k-code": one
+// 32-bit word per row, nibble x = k of texel (x, row). Merging compares k-codes (32 B instead of the
+// reference's 68 B leaf); only the leaves that survive merging are expanded to slice masks (emit.cu).
+//
+// The 1x1x8 childmask needs min k / max k only; k is monotone in depth, so they come from the 8x8
+// block's (min,max) texel of pyramid level 3.
+__device__ __forceinline__ u32 litCountBits(float depth, float heightF, float zc) {
+	const float v = __fadd_rd(__fmul_rn(depth, heightF), -zc);
+	const float kf = fminf(fmaxf(v, 0.0f), 8.0f);  // NaN -> 0: never lit, as midZ <= NaN is false
+	return (u32)__float_as_int(__fadd_rd(kf, 8388608.0f));  // 0x4B000000 + k
 }
 
-__global__ void __launch_bounds__(256) buildLeavesKernel(const float* __restrict__ depth, u32 n, float heightF, const u64* __restrict__ coords,
-		u64 numLeaves, u64* __restrict__ bits, u64* __restrict__ hashes, u16* __restrict__ masks) {
-	const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-	const u32 r = threadIdx.x & 7u;
-	u64 leaf = gid >> 3;
-	const bool live = leaf < numLeaves;
-	if (!live) leaf = numLeaves - 1;  // keep the lane in the shuffles
+// 256 leaves per CTA, in two phases.
+//  1. Lane pairs load one 32-byte depth row each (one L1 wavefront per row and instruction: a warp
+//     instruction covers two whole leaves), turn their four texels into four nibbles and park the
+//     16-bit piece in shared memory. Each warp does its 32 leaves in 8 rounds of 2x2.
+//  2. One thread per leaf reads the finished 32-byte k-code back, hashes it, derives the 1x1x8
+//     childmask from the block's (min,max) pyramid texel, marks the distinct-count bitmap and stores.
+constexpr int kLeavesPerCta = 256;
+
+__global__ void __launch_bounds__(256) buildLeavesKernel(const float* __restrict__ depth, u32 n, float heightF, const float2* __restrict__ level3,
+		const u64* __restrict__ coords, u64 numLeaves, u32* __restrict__ codes, u64* __restrict__ hashes, u16* __restrict__ masks,
+		u32* __restrict__ bitmap, u32 bitmapWordMask) {
+	__shared__ __align__(16) u16 sCode[kLeavesPerCta][16];
+	const u64 ctaBase = (u64)blockIdx.x * kLeavesPerCta;
+	const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	const u32 half = lane & 1u, row = (lane >> 1) & 7u, which = lane >> 4;
+	const u64 last = numLeaves - 1;
+#pragma unroll 2
+	for (u32 q = 0; q < 8; ++q) {
+		const u32 la = warp * 32u + q * 4u + which, lb = la + 2u;
+		const u64 ca = coords[min(ctaBase + la, last)], cb = coords[min(ctaBase + lb, last)];
+		u32 ax, ay, az, bx, by, bz;
+		unpackCoord(ca, ax, ay, az);
+		unpackCoord(cb, bx, by, bz);
+		const float4 da = *reinterpret_cast<const float4*>(depth + (size_t)(ay * 4u + row) * n + ax * 4u + half * 4u);
+		const float4 db = *reinterpret_cast<const float4*>(depth + (size_t)(by * 4u + row) * n + bx * 4u + half * 4u);
+		const float zca = __fadd_rn(__uint2float_rn(az * 4u), -0.5f), zcb = __fadd_rn(__uint2float_rn(bz * 4u), -0.5f);
+		// Horner over the raw float bit patterns: their exponent bits (0x4B000000) shift out of the low 16
+		const u32 pa = ((litCountBits(da.w, heightF, zca) * 16u + litCountBits(da.z, heightF, zca)) * 16u + litCountBits(da.y, heightF, zca)) * 16u +
+					   litCountBits(da.x, heightF, zca);
+		const u32 pb = ((litCountBits(db.w, heightF, zcb) * 16u + litCountBits(db.z, heightF, zcb)) * 16u + litCountBits(db.y, heightF, zcb)) * 16u +
+					   litCountBits(db.x, heightF, zcb);
+		sCode[la][row * 2u + half] = (u16)pa;
+		sCode[lb][row * 2u + half] = (u16)pb;
+	}
+	__syncthreads();
+
+	const u64 leaf = ctaBase + threadIdx.x;
+	if (leaf >= numLeaves) return;
+	const uint4 c0 = *reinterpret_cast<const uint4*>(&sCode[threadIdx.x][0]), c1 = *reinterpret_cast<const uint4*>(&sCode[threadIdx.x][8]);
+	u64 h = 0x9E3779B97F4A7C15ull;
+	h = (h ^ (((u64)c0.y << 32) | c0.x)) * 0xFF51AFD7ED558CCDull;
+	h = (h ^ (h >> 32) ^ (((u64)c0.w << 32) | c0.z)) * 0xC4CEB9FE1A85EC53ull;
+	h = (h ^ (h >> 32) ^ (((u64)c1.y << 32) | c1.x)) * 0xFF51AFD7ED558CCDull;
+	h = (h ^ (h >> 32) ^ (((u64)c1.w << 32) | c1.z)) * 0xC4CEB9FE1A85EC53ull;
+	h = mix64(h);
 	u32 ox, oy, oz;
 	unpackCoord(coords[leaf], ox, oy, oz);
-	const float* row = depth + (size_t)(oy * 4u + r) * n + ox * 4u;
-	const float4 a = *reinterpret_cast<const float4*>(row), b = *reinterpret_cast<const float4*>(row + 4);
 	const float zc = __fadd_rn(__uint2float_rn(oz * 4u), -0.5f);
-	const float d[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-	u32 lo = 0, hi = 0;
+	const float2 mm = level3[(size_t)(oy >> 1) * (n >> 3) + (ox >> 1)];
+	const u32 kmin = litCountBits(mm.x, heightF, zc) & 15u, kmax = litCountBits(mm.y, heightF, zc) & 15u;
+	// slices below kmin are lit (01), slices from kmax up are shadowed (00), the rest PARTIAL (10)
+	const u32 below = (1u << (2u * kmin)) - 1u;
+	masks[leaf] = (u16)((0x5555u & below) | (0xAAAAu & ((1u << (2u * kmax)) - 1u) & ~below));
+	hashes[leaf] = h;
+	uint4* dst = reinterpret_cast<uint4*>(codes + leaf * 8);
+	dst[0] = c0;
+	dst[1] = c1;
+	// distinct-count sketch (linear counting): one bit per hash value, read back by sizeLeafTable
+	const u32 bit = (u32)(h >> 20);
+	atomicOr(bitmap + ((bit >> 5) & bitmapWordMask), 1u << (bit & 31u));
+}
+
+// Number of set bits of the sketch -> *setBits (zeroed beforehand).
+__global__ void __launch_bounds__(256) sketchPopcountKernel(const uint4* __restrict__ bitmap, u32 numVec, u64* __restrict__ setBits) {
+	u32 local = 0;
+	for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < numVec; i += gridDim.x * blockDim.x) {
+		const uint4 v = bitmap[i];
+		local += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+	}
 #pragma unroll
-	for (int i = 0; i < 8; ++i) {
-		const float v = __fadd_rd(__fmul_rn(d[i], heightF), -zc);
-		const float kf = fminf(fmaxf(v, 0.0f), 8.0f);  // NaN -> 0: never lit, as midZ <= NaN is false
-		const u32 k = (u32)__float_as_int(__fadd_rd(kf, 8388608.0f)) & 15u;
-		const u32 therm = (1u << k) - 1u;
-		if (i < 4)
-			lo |= therm << (8 * i);
-		else
-			hi |= therm << (8 * (i - 4));
-	}
-	const u64 rows = transpose8x8(((u64)hi << 32) | lo);  // byte z' = this row's 8 texels in slice z'
-	const u32 rlo = (u32)rows, rhi = (u32)(rows >> 32);
-	const int group = (threadIdx.x & 31) & ~7;
-	u64 slice = 0;
-#pragma unroll
-	for (int s = 0; s < 8; ++s) {
-		const u32 olo = __shfl_sync(0xFFFFFFFFu, rlo, group + s), ohi = __shfl_sync(0xFFFFFFFFu, rhi, group + s);
-		const u32 byte = ((r < 4u ? olo : ohi) >> (8u * (r & 3u))) & 0xFFu;
-		slice |= (u64)byte << (8 * s);
-	}
-	// lane r now holds the mask of slice z' = r
-	u32 code = (slice == ~0ull) ? 1u : (slice == 0ull ? 0u : 2u);
-	u32 mask = code << (2u * r);
-	u64 h = mix64(slice + (u64)(r + 1u) * 0x9E3779B97F4A7C15ull);
-#pragma unroll
-	for (int dlt = 1; dlt < 8; dlt <<= 1) {
-		mask |= __shfl_xor_sync(0xFFFFFFFFu, mask, dlt);
-		h += __shfl_xor_sync(0xFFFFFFFFu, h, dlt);
-	}
-	if (live) {
-		bits[leaf * 8 + r] = slice;
-		if (r == 0) {
-			hashes[leaf] = mix64(h);
-			masks[leaf] = (u16)mask;
-		}
-	}
+	for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, d);
+	if ((threadIdx.x & 31) == 0 && local) atomicAdd(reinterpret_cast<unsigned long long*>(setBits), (unsigned long long)local);
 }
 
 }  // namespace
@@ -216,11 +236,16 @@ int launchExpandLevel(const PyramidView& pyr, int level, u32 zTileNum, const u64
 	return 1;
 }
 
-int launchBuildLeaves(const PyramidView& pyr, u32 zTileNum, const u64* coords, u64 n, u64* bits, u64* hashes, u16* masks,
+int launchBuildLeaves(const PyramidView& pyr, u32 zTileNum, const u64* coords, u64 n, u32* codes, u64* hashes, u16* masks, u32* sketch,
 		cudaStream_t stream) {
 	const float heightF = (float)((u32)pyr.n * zTileNum);
-	const u64 threads = n * 8;
-	buildLeavesKernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(pyr.level[0], (u32)pyr.n, heightF, coords, n, bits, hashes, masks);
+	buildLeavesKernel<<<(unsigned)((n + kLeavesPerCta - 1) / kLeavesPerCta), 256, 0, stream>>>(pyr.level[0], (u32)pyr.n, heightF,
+			reinterpret_cast<const float2*>(pyr.level[3]), coords, n, codes, hashes, masks, sketch, kSketchWords - 1);
+	return 1;
+}
+
+int launchSketchPopcount(const u32* sketch, u64* setBits, cudaStream_t stream) {
+	sketchPopcountKernel<<<148 * 4, 256, 0, stream>>>(reinterpret_cast<const uint4*>(sketch), kSketchWords / 4, setBits);
 	return 1;
 }
 

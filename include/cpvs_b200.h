@@ -56,13 +56,14 @@ extern "C" {
 #define CPVS_PHASE_COUNT 0        /* closed-form node counts per level + host read-back */
 #define CPVS_PHASE_EXPAND 1       /* breadth-first expansion of all inner levels */
 #define CPVS_PHASE_LEAVES 2       /* leaf build (1 kernel) */
-#define CPVS_PHASE_LEAF_INSERT 3  /* leaf level: hash-table insert (1 kernel) */
-#define CPVS_PHASE_LEAF_RESOLVE 4 /* leaf level: table clear + rank scan + unique ids */
-#define CPVS_PHASE_INNER_MERGE 5  /* all inner levels: clear + insert + rank scan + unique ids */
-#define CPVS_PHASE_BASES 6        /* level bases + host read-back of sizes */
-#define CPVS_PHASE_EMIT_INNER 7   /* compressed inner nodes, all levels */
-#define CPVS_PHASE_EMIT_LEAVES 8  /* compressed leaves (1 kernel) */
-#define CPVS_NUM_PHASES 9
+#define CPVS_PHASE_LEAF_TABLE 3   /* leaf level: distinct-count sketch read-out, table sizing + clear */
+#define CPVS_PHASE_LEAF_INSERT 4  /* leaf level: hash-table insert (1 kernel) */
+#define CPVS_PHASE_LEAF_RESOLVE 5 /* leaf level: rank scan + unique ids */
+#define CPVS_PHASE_INNER_MERGE 6  /* all inner levels: clear + insert + rank scan + unique ids */
+#define CPVS_PHASE_BASES 7        /* level bases + host read-back of sizes */
+#define CPVS_PHASE_EMIT_INNER 8   /* compressed inner nodes, all levels */
+#define CPVS_PHASE_EMIT_LEAVES 9  /* compressed leaves (1 kernel) */
+#define CPVS_NUM_PHASES 10
 
 /* Grid sentinels written by CompressedShadowContainer::createTopLevelGrid
  * (src/CompressedShadowContainer.cpp:8-9). The lookup tests these same values. */
