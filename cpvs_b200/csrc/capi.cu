@@ -385,7 +385,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	lv[top].n = 1;
 	for (int l = top - 1; l >= minLevel; --l) lv[l].n = lv[l + 1].n ? hScalars[l] : 0;
 	for (int l = minLevel; l <= top; ++l)
-		if (lv[l].n >= (1ull << 31)) return fail(CPVS_EOVERFLOW, "level %d has %llu nodes (limit 2^31)", l, (unsigned long long)lv[l].n);
+		if (lv[l].n >= (1ull << 30)) return fail(CPVS_EOVERFLOW, "level %d has %llu nodes (limit 2^30)", l, (unsigned long long)lv[l].n);
 
 	// 2. per-level arrays, carved out of the context arena
 	u64 scanTiles = 0, scanLaunches = 0, maxTable = 0;
@@ -553,6 +553,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		em.n = a.n;
 		em.leaf = (useLeaf && l == 2) ? 1 : 0;
 		em.uniqueCount = dUnique + l;
+		em.wordCount = dWords + l;
 		em.firstList = a.firstList;
 		em.wordOffset = a.wordOffset;
 		em.levelBase = dBases + l;

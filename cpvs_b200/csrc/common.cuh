@@ -10,6 +10,9 @@ typedef uint64_t u64;
 typedef uint16_t u16;
 
 constexpr int kMaxLevels = 32;
+// Per-node unique ids are stored with bit 31 set once final (merge.cu); consumers strip it.
+constexpr uint32_t kResolvedFlag = 0x80000000u;
+constexpr uint32_t kUidMask = 0x7FFFFFFFu;
 constexpr int kScanThreads = 256;  // threads per scan tile
 constexpr int kScanItems = 4;      // items per thread
 constexpr int kScanTile = kScanThreads * kScanItems;
@@ -38,6 +41,15 @@ __device__ __forceinline__ u32 classifyPoint(float minZ, float maxZ, float depth
 __device__ __forceinline__ float stdMin(float a, float b) { return (b < a) ? b : a; }
 __device__ __forceinline__ float stdMax(float a, float b) { return (a < b) ? b : a; }
 
+// 128-bit read-only load that asks L2 to fetch the whole 128-byte line on a miss. Used where a warp
+// touches isolated 32-byte sectors whose neighbours are needed by nearby work items moments later:
+// DRAM then sees full-line bursts instead of scattered sectors.
+__device__ __forceinline__ float4 ldLine128(const float* p) {
+	float4 v;
+	asm volatile("ld.global.nc.L2::128B.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+	return v;
+}
+
 __device__ __forceinline__ u64 mix64(u64 h) {
 	h ^= h >> 33;
 	h *= 0xFF51AFD7ED558CCDull;
@@ -48,28 +60,29 @@ __device__ __forceinline__ u64 mix64(u64 h) {
 }
 
 // ---- single-pass prefix sums over tiles (decoupled look-back) -----------------------------------
-// One ScanTileState per tile. A tile publishes its own aggregate (flag 1), then, once it knows the
-// sum of everything in front of it, its inclusive prefix (flag 2). Payload words are written before
-// the flag with release semantics and read after it with acquire semantics.
+// One ScanTileState per tile, two running sums (a, b) per scan. A tile publishes its own aggregate
+// (status 1), then, once it knows the sum of everything in front of it, its inclusive prefix (status
+// 2). Each 64-bit word carries its status in the top two bits next to the value, so a word is valid on
+// its own: plain relaxed 64-bit loads and stores suffice, no fences (release/acquire pairs compile to
+// MEMBAR.ALL.GPU / CCTL.IVALL here, far too heavy for a per-tile handshake).
 struct ScanTileState {
-	u32 flag;
-	u32 pad;
-	u64 agg[2];
-	u64 incl[2];
+	u64 a;
+	u64 b;
 };
+constexpr u64 kScanValueMask = (1ull << 62) - 1;
 
 struct ScanLaunch {
 	u32* ticket;           // zeroed counter handing out tile indices in start order
 	ScanTileState* tiles;  // zeroed, one per tile
 };
 
-__device__ __forceinline__ u32 ldAcquire(const u32* p) {
+__device__ __forceinline__ u32 ldRelaxed32(const u32* p) {
 	u32 v;
-	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
 	return v;
 }
-__device__ __forceinline__ void stRelease(u32* p, u32 v) {
-	asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void stRelaxed32(u32* p, u32 v) {
+	asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ u64 ldRelaxed64(const u64* p) {
 	u64 v;
@@ -131,35 +144,25 @@ __device__ __forceinline__ void scanLookback2(const ScanLaunch& sl, u32 tile, u6
 	if (threadIdx.x < 32) {
 		const int lane = threadIdx.x;
 		if (lane == 0) {
-			if (tile == 0) {
-				stRelaxed64(&st[0].incl[0], totA);
-				stRelaxed64(&st[0].incl[1], totB);
-				stRelease(&st[0].flag, 2u);
-			} else {
-				stRelaxed64(&st[tile].agg[0], totA);
-				stRelaxed64(&st[tile].agg[1], totB);
-				stRelease(&st[tile].flag, 1u);
-			}
+			const u64 status = tile == 0 ? (2ull << 62) : (1ull << 62);
+			stRelaxed64(&st[tile].a, status | totA);
+			stRelaxed64(&st[tile].b, status | totB);
 		}
 		u64 runA = 0, runB = 0;
 		if (tile > 0) {
 			long long look = (long long)tile - 1;
 			for (;;) {
 				const long long idx = look - lane;
-				u32 flag = 2u;
+				u64 wa = 2ull << 62, wb = 2ull << 62;  // lanes in front of tile 0 report "inclusive, 0"
 				if (idx >= 0) {
-					do {
-						flag = ldAcquire(&st[idx].flag);
-					} while (flag == 0u);
+					do {  // both words present and in the same state (the writer updates a, then b)
+						wa = ldRelaxed64(&st[idx].a);
+						wb = ldRelaxed64(&st[idx].b);
+					} while ((wa >> 62) == 0 || (wa >> 62) != (wb >> 62));
 				}
-				u64 vA = 0, vB = 0;
-				if (idx >= 0) {
-					vA = ldRelaxed64(flag == 2u ? &st[idx].incl[0] : &st[idx].agg[0]);
-					vB = ldRelaxed64(flag == 2u ? &st[idx].incl[1] : &st[idx].agg[1]);
-				}
-				// lanes whose index falls in front of tile 0 report "inclusive, 0"
-				const u32 done = __ballot_sync(0xFFFFFFFFu, flag == 2u);
+				const u32 done = __ballot_sync(0xFFFFFFFFu, (wa >> 62) == 2);
 				const int first = __ffs(done) - 1;  // nearest tile that already knows its inclusive prefix
+				u64 vA = wa & kScanValueMask, vB = wb & kScanValueMask;
 				if (done != 0u && lane > first) {
 					vA = 0;
 					vB = 0;
@@ -175,9 +178,8 @@ __device__ __forceinline__ void scanLookback2(const ScanLaunch& sl, u32 tile, u6
 				look -= 32;
 			}
 			if (lane == 0) {
-				stRelaxed64(&st[tile].incl[0], runA + totA);
-				stRelaxed64(&st[tile].incl[1], runB + totB);
-				stRelease(&st[tile].flag, 2u);
+				stRelaxed64(&st[tile].a, (2ull << 62) | (runA + totA));
+				stRelaxed64(&st[tile].b, (2ull << 62) | (runB + totB));
 			}
 		}
 		if (lane == 0) {

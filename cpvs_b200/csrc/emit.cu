@@ -20,23 +20,42 @@ __global__ void levelBasesKernel(const u64* __restrict__ words, u64* __restrict_
 	*totalWords = running;
 }
 
-__global__ void __launch_bounds__(256) emitInnerKernel(EmitLevelArgs a) {
-	const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-	if (r >= *a.uniqueCount) return;
-	const u32 j = a.firstList[r];
-	const u32 mask = a.masks[j];
-	const u32 k = __popc(mask & 0xAAAAu);
-	u32* out = a.dag + (*a.levelBase + a.wordOffset[r]);
-	out[0] = mask;
-	if (k) {
-		const u32* kids = a.childUid + a.firstChild[j];
-		const u32 childBase = (u32)*a.childLevelBase;
-		for (u32 c = 0; c < k; ++c) out[1 + c] = childBase + a.childWordOffset[kids[c]];
-	}
+// Both emit kernels give one thread one unique node; the 256 nodes of a CTA occupy one contiguous run
+// of the DAG, which is assembled in shared memory and written out with fully coalesced stores (a
+// thread-per-node store of 1+k words would touch a different 32-byte sector per thread and word).
+constexpr int kEmitThreads = 256;
+
+__device__ __forceinline__ void emitRun(const EmitLevelArgs& a, const u32* sOut, u64 runStart, u32 runWords) {
+	u32* out = a.dag + *a.levelBase + runStart;
+	for (u32 i = threadIdx.x; i < runWords; i += kEmitThreads) out[i] = sOut[i];
 }
 
-// One thread per unique leaf: expands the k-code (nibble x of word y = lit slices of texel (x,y)) into
-// the 64-bit masks of the PARTIAL slices, bit x + 8y = lit (createLeafmask, src/CompressedShadowUtil.cpp:59-78).
+__global__ void __launch_bounds__(kEmitThreads) emitInnerKernel(EmitLevelArgs a) {
+	__shared__ u32 sOut[kEmitThreads * 9];
+	const u64 unique = *a.uniqueCount;
+	const u64 r0 = (u64)blockIdx.x * kEmitThreads;
+	if (r0 >= unique) return;
+	const u64 r = r0 + threadIdx.x;
+	const u32 runStart = a.wordOffset[r0];
+	const u32 runEnd = (r0 + kEmitThreads < unique) ? a.wordOffset[r0 + kEmitThreads] : (u32)*a.wordCount;
+	if (r < unique) {
+		const u32 j = a.firstList[r];
+		const u32 mask = a.masks[j];
+		const u32 k = __popc(mask & 0xAAAAu);
+		u32* out = sOut + (a.wordOffset[r] - runStart);
+		out[0] = mask;
+		if (k) {
+			const u32* kids = a.childUid + a.firstChild[j];
+			const u32 childBase = (u32)*a.childLevelBase;
+			for (u32 c = 0; c < k; ++c) out[1 + c] = childBase + a.childWordOffset[kids[c] & kUidMask];
+		}
+	}
+	__syncthreads();
+	emitRun(a, sOut, runStart, runEnd - runStart);
+}
+
+// Leaves: expands the k-code (nibble x of word y = lit slices of texel (x,y)) into the 64-bit masks of
+// the PARTIAL slices, bit x + 8y = lit (createLeafmask, src/CompressedShadowUtil.cpp:59-78).
 __device__ __forceinline__ u32 rowBits(u32 code, u32 slice) {
 	// nibble k > slice  <=>  bit 3 of (k + 7 - slice); nibbles are <= 8 so nothing carries
 	u32 y = ((code + (7u - slice) * 0x11111111u) >> 3) & 0x11111111u;
@@ -45,20 +64,29 @@ __device__ __forceinline__ u32 rowBits(u32 code, u32 slice) {
 	return (y | (y >> 12)) & 0xFFu;
 }
 
-__global__ void __launch_bounds__(256) emitLeavesKernel(EmitLevelArgs a) {
-	const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-	if (r >= *a.uniqueCount) return;
-	const u32 j = a.firstList[r];
-	const u32 mask = a.masks[j];
-	u32* out = a.dag + (*a.levelBase + a.wordOffset[r]);
-	*out++ = mask;
-	const uint4* src = reinterpret_cast<const uint4*>(a.leafCodes + (u64)j * 8);
-	const uint4 c0 = src[0], c1 = src[1];
-	for (u32 slice = 0; slice < 8; ++slice) {
-		if (!((mask >> (2 * slice)) & 2u)) continue;
-		*out++ = rowBits(c0.x, slice) | (rowBits(c0.y, slice) << 8) | (rowBits(c0.z, slice) << 16) | (rowBits(c0.w, slice) << 24);
-		*out++ = rowBits(c1.x, slice) | (rowBits(c1.y, slice) << 8) | (rowBits(c1.z, slice) << 16) | (rowBits(c1.w, slice) << 24);
+__global__ void __launch_bounds__(kEmitThreads) emitLeavesKernel(EmitLevelArgs a) {
+	__shared__ u32 sOut[kEmitThreads * 17];
+	const u64 unique = *a.uniqueCount;
+	const u64 r0 = (u64)blockIdx.x * kEmitThreads;
+	if (r0 >= unique) return;
+	const u64 r = r0 + threadIdx.x;
+	const u32 runStart = a.wordOffset[r0];
+	const u32 runEnd = (r0 + kEmitThreads < unique) ? a.wordOffset[r0 + kEmitThreads] : (u32)*a.wordCount;
+	if (r < unique) {
+		const u32 j = a.firstList[r];
+		const u32 mask = a.masks[j];
+		u32* out = sOut + (a.wordOffset[r] - runStart);
+		*out++ = mask;
+		const uint4* src = reinterpret_cast<const uint4*>(a.leafCodes + (u64)j * 8);
+		const uint4 c0 = src[0], c1 = src[1];
+		for (u32 slice = 0; slice < 8; ++slice) {
+			if (!((mask >> (2 * slice)) & 2u)) continue;
+			*out++ = rowBits(c0.x, slice) | (rowBits(c0.y, slice) << 8) | (rowBits(c0.z, slice) << 16) | (rowBits(c0.w, slice) << 24);
+			*out++ = rowBits(c1.x, slice) | (rowBits(c1.y, slice) << 8) | (rowBits(c1.z, slice) << 16) | (rowBits(c1.w, slice) << 24);
+		}
 	}
+	__syncthreads();
+	emitRun(a, sOut, runStart, runEnd - runStart);
 }
 
 }  // namespace

@@ -67,6 +67,7 @@ struct EmitLevelArgs {
 	const u64* uniqueCount;   // device: unique nodes of this level
 	const u32* firstList;
 	const u32* wordOffset;
+	const u64* wordCount;     // device: compressed words of this level
 	const u64* levelBase;     // device: word offset of this level in the DAG
 	const u32* leafCodes;
 	const u16* masks;

@@ -15,7 +15,7 @@
 //   2. resolve:  representative = slot's final index; nodes that are their own representative are
 //                the unique nodes. One look-back scan ranks them (first-occurrence order = the
 //                reference's layout) and prefix-sums their compressed sizes.
-//   3. finalize: every node's unique id = rank of its representative (the parents' remap table).
+//                Every other node then takes the rank of its representative (the parents' remap table).
 #include "kernels.h"
 
 namespace cpvs {
@@ -23,7 +23,6 @@ namespace cpvs {
 namespace {
 
 constexpr u64 kEmpty = ~0ull;
-constexpr u32 kFirstFlag = 0x80000000u;
 
 template <typename Equal>
 __device__ __forceinline__ u32 findGroupSlot(u64* __restrict__ table, u64 tableMask, u64 hash, u32 self, u32* errorFlag, Equal sameTuple) {
@@ -94,7 +93,7 @@ __global__ void __launch_bounds__(256) insertInnerKernel(const u16* __restrict__
 	for (u32 c = 0; c < 8; ++c) {
 		uid[c] = 0;
 		if (c < k) {
-			uid[c] = kids[c];
+			uid[c] = kids[c] & kUidMask;
 			h = mix64(h ^ ((u64)uid[c] + 0x9E3779B97F4A7C15ull * (c + 1)));
 		}
 	}
@@ -104,12 +103,18 @@ __global__ void __launch_bounds__(256) insertInnerKernel(const u16* __restrict__
 		bool same = true;
 #pragma unroll
 		for (u32 c = 0; c < 8; ++c)
-			if (c < k) same = same && theirs[c] == uid[c];
+			if (c < k) same = same && (theirs[c] & kUidMask) == uid[c];
 		return same;
 	});
 }
 
-// slotOf[j] (in) -> uid[j] (out): rank | kFirstFlag for first occurrences, representative index otherwise.
+// slotOf[j] (in) -> uid[j] (out) = unique id | kResolvedFlag. Readers strip the flag (kUidMask).
+//
+// First occurrences get their rank from the look-back scan and publish it (value and flag share one word). Every
+// other node needs the rank of its representative, which always sits at a smaller index, i.e. in this
+// tile or in a tile that started earlier (tiles are handed out in start order): it polls that entry
+// until the flag shows up. No tile ever waits on a later one, so this cannot deadlock, and the extra
+// "rank of my representative" pass over the level disappears.
 __global__ void __launch_bounds__(kScanThreads) resolveKernel(const u64* __restrict__ table, const u16* __restrict__ masks, int leaf, u64 n,
 		u32* __restrict__ uid, u32* __restrict__ firstList, u32* __restrict__ wordOffset, u64* __restrict__ uniqueCount,
 		u64* __restrict__ wordCount, ScanLaunch scan, u32 numTiles) {
@@ -142,32 +147,32 @@ __global__ void __launch_bounds__(kScanThreads) resolveKernel(const u64* __restr
 	u64 rank = tileC + preC, woff = tileW + preW;
 #pragma unroll
 	for (int i = 0; i < kScanItems; ++i) {
-		if (base + i >= n) break;
-		if (words[i]) {
+		if (base + i < n && words[i]) {
 			firstList[rank] = (u32)(base + i);
 			wordOffset[rank] = (u32)woff;
-			uid[base + i] = (u32)rank | kFirstFlag;
+			stRelaxed32(uid + base + i, (u32)rank | kResolvedFlag);
 			++rank;
 			woff += words[i];
-		} else {
-			uid[base + i] = rep[i];
 		}
 	}
-}
-
-// Safe in place: a first occurrence only ever loses its flag bit, which readers mask off.
-__global__ void finalizeUidKernel(u32* __restrict__ uid, u64 n) {
-	const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= n) return;
-	const u32 v = uid[j];
-	uid[j] = (v & kFirstFlag) ? (v & ~kFirstFlag) : (reinterpret_cast<volatile u32*>(uid)[v] & ~kFirstFlag);
+	__syncthreads();
+#pragma unroll
+	for (int i = 0; i < kScanItems; ++i) {
+		if (base + i < n && !words[i]) {
+			u32 v;
+			do {
+				v = ldRelaxed32(uid + rep[i]);
+			} while (!(v & kResolvedFlag));
+			uid[base + i] = v;
+		}
+	}
 }
 
 // A level with a single node (the root, which the reference never merges).
 __global__ void singleNodeKernel(const u16* __restrict__ masks, int leaf, u32* uid, u32* firstList, u32* wordOffset, u64* uniqueCount,
 		u64* wordCount) {
 	const u32 k = __popc(masks[0] & 0xAAAAu);
-	uid[0] = 0;
+	uid[0] = kResolvedFlag;
 	firstList[0] = 0;
 	wordOffset[0] = 0;
 	*uniqueCount = 1;
@@ -196,8 +201,7 @@ int launchMergeLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaEvent_t after
 	const u32 tiles = (u32)((a.n + kScanTile - 1) / kScanTile);
 	resolveKernel<<<tiles, kScanThreads, 0, stream>>>(a.table, a.masks, a.leaf, a.n, a.uid, a.firstList, a.wordOffset, a.uniqueCount,
 			a.wordCount, scan, tiles);
-	finalizeUidKernel<<<blocks, 256, 0, stream>>>(a.uid, a.n);
-	return 3;
+	return 2;
 }
 
 }  // namespace cpvs

@@ -9,6 +9,7 @@
 // level's coordinate list in the reference's order: parent order, then child index x | y<<1 | z<<2.
 // Leaves (level 2) are built by eight lanes per node straight from the depth map.
 #include "kernels.h"
+#include <cstdlib>
 
 namespace cpvs {
 
@@ -142,31 +143,38 @@ __device__ __forceinline__ u32 litCountBits(float depth, float heightF, float zc
 //     childmask from the block's (min,max) pyramid texel, marks the distinct-count bitmap and stores.
 constexpr int kLeavesPerCta = 256;
 
-__global__ void __launch_bounds__(256) buildLeavesKernel(const float* __restrict__ depth, u32 n, float heightF, const float2* __restrict__ level3,
+__global__ void __launch_bounds__(256, 4) buildLeavesKernel(const float* __restrict__ depth, u32 n, float heightF, const float2* __restrict__ level3,
 		const u64* __restrict__ coords, u64 numLeaves, u32* __restrict__ codes, u64* __restrict__ hashes, u16* __restrict__ masks,
-		u32* __restrict__ bitmap, u32 bitmapWordMask) {
+		u32* __restrict__ bitmap, u32 bitmapWordMask, int tiledProbe) {
 	__shared__ __align__(16) u16 sCode[kLeavesPerCta][16];
+	__shared__ u64 sCoord[kLeavesPerCta];
 	const u64 ctaBase = (u64)blockIdx.x * kLeavesPerCta;
 	const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	const u32 half = lane & 1u, row = (lane >> 1) & 7u, which = lane >> 4;
-	const u64 last = numLeaves - 1;
-#pragma unroll 2
-	for (u32 q = 0; q < 8; ++q) {
-		const u32 la = warp * 32u + q * 4u + which, lb = la + 2u;
-		const u64 ca = coords[min(ctaBase + la, last)], cb = coords[min(ctaBase + lb, last)];
-		u32 ax, ay, az, bx, by, bz;
-		unpackCoord(ca, ax, ay, az);
-		unpackCoord(cb, bx, by, bz);
-		const float4 da = *reinterpret_cast<const float4*>(depth + (size_t)(ay * 4u + row) * n + ax * 4u + half * 4u);
-		const float4 db = *reinterpret_cast<const float4*>(depth + (size_t)(by * 4u + row) * n + bx * 4u + half * 4u);
-		const float zca = __fadd_rn(__uint2float_rn(az * 4u), -0.5f), zcb = __fadd_rn(__uint2float_rn(bz * 4u), -0.5f);
-		// Horner over the raw float bit patterns: their exponent bits (0x4B000000) shift out of the low 16
-		const u32 pa = ((litCountBits(da.w, heightF, zca) * 16u + litCountBits(da.z, heightF, zca)) * 16u + litCountBits(da.y, heightF, zca)) * 16u +
-					   litCountBits(da.x, heightF, zca);
-		const u32 pb = ((litCountBits(db.w, heightF, zcb) * 16u + litCountBits(db.z, heightF, zcb)) * 16u + litCountBits(db.y, heightF, zcb)) * 16u +
-					   litCountBits(db.x, heightF, zcb);
-		sCode[la][row * 2u + half] = (u16)pa;
-		sCode[lb][row * 2u + half] = (u16)pb;
+	sCoord[threadIdx.x] = coords[min(ctaBase + threadIdx.x, numLeaves - 1)];
+	__syncthreads();
+	// all loads of four rounds (eight 128-bit loads per lane) are issued before any of them is used
+#pragma unroll
+	for (u32 q0 = 0; q0 < 8; q0 += 4) {
+		float4 d[8];
+		float zc[8];
+#pragma unroll
+		for (u32 i = 0; i < 8; ++i) {
+			const u32 l = warp * 32u + (q0 + (i >> 1)) * 4u + which + (i & 1u) * 2u;
+			u32 x, y, z;
+			unpackCoord(sCoord[l], x, y, z);
+			d[i] = tiledProbe ? ldLine128(depth + ((size_t)(y >> 1) * (n >> 3) + (x >> 1)) * 64u + row * 8u + half * 4u)
+							  : ldLine128(depth + (size_t)(y * 4u + row) * n + x * 4u + half * 4u);
+			zc[i] = __fadd_rn(__uint2float_rn(z * 4u), -0.5f);
+		}
+#pragma unroll
+		for (u32 i = 0; i < 8; ++i) {
+			const u32 l = warp * 32u + (q0 + (i >> 1)) * 4u + which + (i & 1u) * 2u;
+			// Horner over the raw float bit patterns: their exponent bits (0x4B000000) shift out of the low 16
+			const u32 p = ((litCountBits(d[i].w, heightF, zc[i]) * 16u + litCountBits(d[i].z, heightF, zc[i])) * 16u +
+						   litCountBits(d[i].y, heightF, zc[i])) * 16u + litCountBits(d[i].x, heightF, zc[i]);
+			sCode[l][row * 2u + half] = (u16)p;
+		}
 	}
 	__syncthreads();
 
@@ -180,7 +188,7 @@ __global__ void __launch_bounds__(256) buildLeavesKernel(const float* __restrict
 	h = (h ^ (h >> 32) ^ (((u64)c1.w << 32) | c1.z)) * 0xC4CEB9FE1A85EC53ull;
 	h = mix64(h);
 	u32 ox, oy, oz;
-	unpackCoord(coords[leaf], ox, oy, oz);
+	unpackCoord(sCoord[threadIdx.x], ox, oy, oz);
 	const float zc = __fadd_rn(__uint2float_rn(oz * 4u), -0.5f);
 	const float2 mm = level3[(size_t)(oy >> 1) * (n >> 3) + (ox >> 1)];
 	const u32 kmin = litCountBits(mm.x, heightF, zc) & 15u, kmax = litCountBits(mm.y, heightF, zc) & 15u;
@@ -192,8 +200,11 @@ __global__ void __launch_bounds__(256) buildLeavesKernel(const float* __restrict
 	dst[0] = c0;
 	dst[1] = c1;
 	// distinct-count sketch (linear counting): one bit per hash value, read back by sizeLeafTable
+	// (read first: on repetitive maps nearly every leaf finds its bit already set, and the atomics of a
+	// popular hash would otherwise serialise on one address)
 	const u32 bit = (u32)(h >> 20);
-	atomicOr(bitmap + ((bit >> 5) & bitmapWordMask), 1u << (bit & 31u));
+	u32* word = bitmap + ((bit >> 5) & bitmapWordMask);
+	if (!(__ldcg(word) & (1u << (bit & 31u)))) atomicOr(word, 1u << (bit & 31u));
 }
 
 // Number of set bits of the sketch -> *setBits (zeroed beforehand).
@@ -240,7 +251,8 @@ int launchBuildLeaves(const PyramidView& pyr, u32 zTileNum, const u64* coords, u
 		cudaStream_t stream) {
 	const float heightF = (float)((u32)pyr.n * zTileNum);
 	buildLeavesKernel<<<(unsigned)((n + kLeavesPerCta - 1) / kLeavesPerCta), 256, 0, stream>>>(pyr.level[0], (u32)pyr.n, heightF,
-			reinterpret_cast<const float2*>(pyr.level[3]), coords, n, codes, hashes, masks, sketch, kSketchWords - 1);
+			reinterpret_cast<const float2*>(pyr.level[3]), coords, n, codes, hashes, masks, sketch, kSketchWords - 1,
+			getenv("CPVS_TILED_PROBE") ? 1 : 0);
 	return 1;
 }
 
