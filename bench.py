@@ -326,12 +326,18 @@ def run_own(args):
         create_ms = statistics.mean(sum(tm[2]) for tm in timings)
         n_leaves = int(info0.svo_nodes[2]) if leaf else 0
         u_leaves = int(info0.dag_nodes[2]) if leaf else 0
-        # algorithmic bytes per launch of the single-kernel phases (DESIGN.md "kernels")
+        # algorithmic (compulsory HBM) bytes per launch of the single-kernel phases -- DESIGN.md "Kernels":
+        #   pyramid_base  depth read once + levels 1..5 written
+        #   leaves        depth read once (L2 serves the ~3.3 z-block re-reads) + per leaf: 8 B coordinate in, 32 B k-code,
+        #                 8 B hash, 2 B mask out
+        #   leaf_insert   per leaf: 8 B hash + 32 B own k-code in, 4 B slot out; per duplicate: 32 B representative k-code
+        #                 (the table itself is sized to stay in L2)
+        #   emit_leaves   per unique leaf: 4 B index + 4 B offset + 2 B mask + 32 B k-code in; compressed words out
         kernels = {
             "pyramid_base": ((4.0 + 8.0 * (1 / 4 + 1 / 16 + 1 / 64 + 1 / 256 + 1 / 1024)) * n * n, pyr_base),
-            "leaves": (n_leaves * (256.0 + 8 + 64 + 8 + 2), phase["leaves"] / z_slices),
-            "leaf_insert": (n_leaves * (8.0 + 4 + 8) + (n_leaves - u_leaves) * 128.0, phase["leaf_insert"] / z_slices),
-            "emit_leaves": (u_leaves * (4.0 + 4 + 2 + 64) + 4.0 * int(info0.dag_words[2] if leaf else 0), phase["emit_leaves"] / z_slices),
+            "leaves": (4.0 * n * n + n_leaves * (8.0 + 32 + 8 + 2), phase["leaves"] / z_slices),
+            "leaf_insert": (n_leaves * (8.0 + 32 + 4) + (n_leaves - u_leaves) * 32.0, phase["leaf_insert"] / z_slices),
+            "emit_leaves": (u_leaves * (4.0 + 4 + 2 + 32) + 4.0 * int(info0.dag_words[2] if leaf else 0), phase["emit_leaves"] / z_slices),
         }
         dom = max(kernels, key=lambda k: kernels[k][1])
         dom_bytes, dom_ms = kernels[dom]

@@ -58,6 +58,7 @@ SIGNATURES = {
     "cpvs_minmax_size": (_I, [_VP]),
     "cpvs_minmax_level": (_I, [_VP, _I, _VP]),
     "cpvs_minmax_level_device": (_VP, [_VP, _I]),
+    "cpvs_minmax_childmask": (_I, [_VP, _U32, _U32, _U32, _U32, _U32, ctypes.POINTER(_U32)]),
     "cpvs_minmax_timing": (_I, [_VP, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
     "cpvs_shadow_create": (_I, [_VP, _VP, _U32, _U32, _I, _PP]),
     "cpvs_shadow_create_from_depth": (_I, [_VP, _VP, _I, _I, _U32, _U32, _I, _PP]),
@@ -184,6 +185,12 @@ class MinMaxHierarchy:
         out = np.empty((side, side) if level == 0 else (side, side, 2), np.float32)
         _check(self._lib.cpvs_minmax_level(self.handle, level, out.ctypes.data))
         return out
+
+    def createChildmask(self, level, x, y, z, zTileNum=1):
+        """``cs::createChildmask(minMax, level, ivec3(x, y, z))`` (reference src/CompressedShadowUtil.cpp:20-54)."""
+        out = _U32()
+        _check(self._lib.cpvs_minmax_childmask(self.handle, level, x, y, z, zTileNum, ctypes.byref(out)))
+        return out.value
 
     def timing(self):
         """(total ms, fused base kernel ms) of the build, from CUDA events."""

@@ -329,6 +329,24 @@ int cpvs_minmax_level(const cpvs_minmax* mm, int level, float* out_host) {
 	return CPVS_OK;
 }
 
+int cpvs_minmax_childmask(const cpvs_minmax* mm, uint32_t level, uint32_t x, uint32_t y, uint32_t z, uint32_t zTileNum, uint32_t* out) {
+	if (!mm || !out) return fail(CPVS_EINVAL, "cpvs_minmax_childmask: NULL argument");
+	const u32 side = level < (u32)mm->numLevels ? ((u32)mm->n >> level) : 0;
+	if (side < 2 || x + 1 >= side || y + 1 >= side || zTileNum == 0) return fail(CPVS_EINVAL, "cpvs_minmax_childmask: node (%u,%u) outside level %u", x, y, level);
+	cpvs_ctx* ctx = mm->ctx;
+	CPVS_CUDA(cudaSetDevice(ctx->device));
+	std::lock_guard<std::mutex> guard(ctx->buildLock);
+	PyramidView pyr;
+	pyr.n = mm->n;
+	pyr.numLevels = mm->numLevels;
+	for (int k = 0; k < kMaxLevels; ++k) pyr.level[k] = k < mm->numLevels ? mm->level[k] : nullptr;
+	u32* dOut = reinterpret_cast<u32*>(ctx->scalars + 191);
+	ctx->launches += launchChildmask(pyr, (int)level, zTileNum, x, y, z, dOut, ctx->stream);
+	CPVS_CUDA(cudaMemcpyAsync(out, dOut, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+	CPVS_CUDA(cudaStreamSynchronize(ctx->stream));
+	return CPVS_OK;
+}
+
 /* ---- CompressedShadow::create ------------------------------------------------------------------ */
 
 int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex, uint32_t zTileNum, int leafmasks, cpvs_shadow** out) {

@@ -49,6 +49,17 @@ __device__ __forceinline__ float4 ldLine128(const float* p) {
 	asm volatile("ld.global.nc.L2::128B.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
 	return v;
 }
+// Same, 256 bits per lane (LDG.E.256, new with sm_100): one lane fetches a whole 32-byte sector.
+struct Float8 {
+	float v[8];
+};
+__device__ __forceinline__ Float8 ldSector256(const float* p) {
+	Float8 r;
+	asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+				 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+				 : "l"(p));
+	return r;
+}
 
 __device__ __forceinline__ u64 mix64(u64 h) {
 	h ^= h >> 33;

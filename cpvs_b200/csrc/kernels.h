@@ -17,6 +17,9 @@ struct PyramidView {
 	int numLevels;
 };
 
+// cs::createChildmask for one node (known-answer tests): *out = 16-bit mask of the node at `level`.
+int launchChildmask(const PyramidView& pyr, int level, u32 zTileNum, u32 x, u32 y, u32 z, u32* out, cudaStream_t stream);
+
 // counts[l] += number of SVO nodes at level l, for l in [minLevel, numLevels-3]; counts must be zeroed.
 int launchCountNodes(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, int minLevel, u64* counts, cudaStream_t stream);
 

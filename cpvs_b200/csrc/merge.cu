@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) insertInnerKernel(const u16* __restrict__
 // tile or in a tile that started earlier (tiles are handed out in start order): it polls that entry
 // until the flag shows up. No tile ever waits on a later one, so this cannot deadlock, and the extra
 // "rank of my representative" pass over the level disappears.
-__global__ void __launch_bounds__(kScanThreads) resolveKernel(const u64* __restrict__ table, const u16* __restrict__ masks, int leaf, u64 n,
+__global__ void __launch_bounds__(kScanThreads, 8) resolveKernel(const u64* __restrict__ table, const u16* __restrict__ masks, int leaf, u64 n,
 		u32* __restrict__ uid, u32* __restrict__ firstList, u32* __restrict__ wordOffset, u64* __restrict__ uniqueCount,
 		u64* __restrict__ wordCount, ScanLaunch scan, u32 numTiles) {
 	const u32 tile = scanAcquireTile(scan);

@@ -9,7 +9,6 @@
 // level's coordinate list in the reference's order: parent order, then child index x | y<<1 | z<<2.
 // Leaves (level 2) are built by eight lanes per node straight from the depth map.
 #include "kernels.h"
-#include <cstdlib>
 
 namespace cpvs {
 
@@ -136,51 +135,51 @@ __device__ __forceinline__ u32 litCountBits(float depth, float heightF, float zc
 }
 
 // 256 leaves per CTA, in two phases.
-//  1. Lane pairs load one 32-byte depth row each (one L1 wavefront per row and instruction: a warp
-//     instruction covers two whole leaves), turn their four texels into four nibbles and park the
-//     16-bit piece in shared memory. Each warp does its 32 leaves in 8 rounds of 2x2.
+//  1. Each lane loads one 32-byte depth row with a single 256-bit load (a warp instruction covers four
+//     consecutive leaves; leaves that are x-neighbours share their 128-byte lines, which is what bounds
+//     this kernel: L1 tag wavefronts), turns its eight texels into eight nibbles and parks the row word
+//     in shared memory. Each warp does its 32 leaves in 8 rounds of 4.
 //  2. One thread per leaf reads the finished 32-byte k-code back, hashes it, derives the 1x1x8
 //     childmask from the block's (min,max) pyramid texel, marks the distinct-count bitmap and stores.
 constexpr int kLeavesPerCta = 256;
 
 __global__ void __launch_bounds__(256, 4) buildLeavesKernel(const float* __restrict__ depth, u32 n, float heightF, const float2* __restrict__ level3,
 		const u64* __restrict__ coords, u64 numLeaves, u32* __restrict__ codes, u64* __restrict__ hashes, u16* __restrict__ masks,
-		u32* __restrict__ bitmap, u32 bitmapWordMask, int tiledProbe) {
-	__shared__ __align__(16) u16 sCode[kLeavesPerCta][16];
+		u32* __restrict__ bitmap, u32 bitmapWordMask) {
+	__shared__ __align__(16) u32 sCode[kLeavesPerCta][8];
 	__shared__ u64 sCoord[kLeavesPerCta];
 	const u64 ctaBase = (u64)blockIdx.x * kLeavesPerCta;
 	const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-	const u32 half = lane & 1u, row = (lane >> 1) & 7u, which = lane >> 4;
+	const u32 row = lane & 7u, which = lane >> 3;
 	sCoord[threadIdx.x] = coords[min(ctaBase + threadIdx.x, numLeaves - 1)];
 	__syncthreads();
-	// all loads of four rounds (eight 128-bit loads per lane) are issued before any of them is used
+	// the loads of four rounds are issued before any of them is used
 #pragma unroll
 	for (u32 q0 = 0; q0 < 8; q0 += 4) {
-		float4 d[8];
-		float zc[8];
+		Float8 d[4];
+		float zc[4];
 #pragma unroll
-		for (u32 i = 0; i < 8; ++i) {
-			const u32 l = warp * 32u + (q0 + (i >> 1)) * 4u + which + (i & 1u) * 2u;
+		for (u32 i = 0; i < 4; ++i) {
+			const u32 l = warp * 32u + (q0 + i) * 4u + which;
 			u32 x, y, z;
 			unpackCoord(sCoord[l], x, y, z);
-			d[i] = tiledProbe ? ldLine128(depth + ((size_t)(y >> 1) * (n >> 3) + (x >> 1)) * 64u + row * 8u + half * 4u)
-							  : ldLine128(depth + (size_t)(y * 4u + row) * n + x * 4u + half * 4u);
+			d[i] = ldSector256(depth + (size_t)(y * 4u + row) * n + x * 4u);
 			zc[i] = __fadd_rn(__uint2float_rn(z * 4u), -0.5f);
 		}
 #pragma unroll
-		for (u32 i = 0; i < 8; ++i) {
-			const u32 l = warp * 32u + (q0 + (i >> 1)) * 4u + which + (i & 1u) * 2u;
-			// Horner over the raw float bit patterns: their exponent bits (0x4B000000) shift out of the low 16
-			const u32 p = ((litCountBits(d[i].w, heightF, zc[i]) * 16u + litCountBits(d[i].z, heightF, zc[i])) * 16u +
-						   litCountBits(d[i].y, heightF, zc[i])) * 16u + litCountBits(d[i].x, heightF, zc[i]);
-			sCode[l][row * 2u + half] = (u16)p;
+		for (u32 i = 0; i < 4; ++i) {
+			const u32 l = warp * 32u + (q0 + i) * 4u + which;
+			u32 code = 0;
+#pragma unroll
+			for (int t = 7; t >= 0; --t) code = code * 16u + litCountBits(d[i].v[t], heightF, zc[i]);
+			sCode[l][row] = code - 0x4B000000u * 0x11111111u;  // strips the float exponent bits of all eight terms
 		}
 	}
 	__syncthreads();
 
 	const u64 leaf = ctaBase + threadIdx.x;
 	if (leaf >= numLeaves) return;
-	const uint4 c0 = *reinterpret_cast<const uint4*>(&sCode[threadIdx.x][0]), c1 = *reinterpret_cast<const uint4*>(&sCode[threadIdx.x][8]);
+	const uint4 c0 = *reinterpret_cast<const uint4*>(&sCode[threadIdx.x][0]), c1 = *reinterpret_cast<const uint4*>(&sCode[threadIdx.x][4]);
 	u64 h = 0x9E3779B97F4A7C15ull;
 	h = (h ^ (((u64)c0.y << 32) | c0.x)) * 0xFF51AFD7ED558CCDull;
 	h = (h ^ (h >> 32) ^ (((u64)c0.w << 32) | c0.z)) * 0xC4CEB9FE1A85EC53ull;
@@ -219,7 +218,17 @@ __global__ void __launch_bounds__(256) sketchPopcountKernel(const uint4* __restr
 	if ((threadIdx.x & 31) == 0 && local) atomicAdd(reinterpret_cast<unsigned long long*>(setBits), (unsigned long long)local);
 }
 
+__global__ void childmaskKernel(const float* tex, u32 side, float heightF, int level0, u32 x, u32 y, u32 z, u32* out) {
+	*out = level0 ? childmaskLevel0(tex, side, heightF, x, y, z) : childmaskInner(reinterpret_cast<const float2*>(tex), side, heightF, x, y, z);
+}
+
 }  // namespace
+
+int launchChildmask(const PyramidView& pyr, int level, u32 zTileNum, u32 x, u32 y, u32 z, u32* out, cudaStream_t stream) {
+	const u32 side = (u32)pyr.n >> level;
+	childmaskKernel<<<1, 1, 0, stream>>>(pyr.level[level], side, (float)(side * zTileNum), level == 0 ? 1 : 0, x, y, z, out);
+	return 1;
+}
 
 int launchCountNodes(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, int minLevel, u64* counts, cudaStream_t stream) {
 	int launches = 0;
@@ -251,8 +260,7 @@ int launchBuildLeaves(const PyramidView& pyr, u32 zTileNum, const u64* coords, u
 		cudaStream_t stream) {
 	const float heightF = (float)((u32)pyr.n * zTileNum);
 	buildLeavesKernel<<<(unsigned)((n + kLeavesPerCta - 1) / kLeavesPerCta), 256, 0, stream>>>(pyr.level[0], (u32)pyr.n, heightF,
-			reinterpret_cast<const float2*>(pyr.level[3]), coords, n, codes, hashes, masks, sketch, kSketchWords - 1,
-			getenv("CPVS_TILED_PROBE") ? 1 : 0);
+			reinterpret_cast<const float2*>(pyr.level[3]), coords, n, codes, hashes, masks, sketch, kSketchWords - 1);
 	return 1;
 }
 

@@ -1,0 +1,74 @@
+"""Tile-grid driver: the caller contract of the reference's ``DeferredRenderer::renderWithTiles`` /
+``createShadowTiles`` (reference ``src/DeferredRenderer.cpp:150-187``) spread over the GPUs of one box.
+
+The virtual shadow map is a ``length x length`` grid of depth tiles; every xy tile yields ``length``
+z-slice DAGs from one pyramid, and the cells are independent. Each rank builds the xy tiles it owns on
+its own GPU; the only cross-rank step is a host-side gather of the finished cells -- no collective on
+the data path (BASELINE.json north_star). Rank 0 (or every rank) then assembles the container exactly
+as ``CompressedShadowContainer::combineDAGs`` / ``createTopLevelGrid`` do
+(reference ``src/CompressedShadowContainer.cpp:52-91``).
+
+The builder is injected (``build_cells``): the CUDA path in production, anything with the same return
+shape in host-logic tests.
+"""
+import numpy as np
+
+GRID_CELL_SHADOWED = 0x0FFFFFFF  # reference src/CompressedShadowContainer.cpp:8
+GRID_CELL_VISIBLE = 0x0FFFFFFE   # reference src/CompressedShadowContainer.cpp:9
+
+
+def xy_tiles(length):
+    """xy tiles in the reference's loop order: y outer, x inner (src/DeferredRenderer.cpp:170-171)."""
+    return [(x, y) for y in range(length) for x in range(length)]
+
+
+def tiles_of_rank(length, rank, world):
+    """Round-robin ownership of xy tiles: tile t = y*length + x belongs to rank t % world."""
+    return [t for i, t in enumerate(xy_tiles(length)) if i % world == rank]
+
+
+def cell_index(x, y, z, length):
+    """Cell index inside the container (reference src/CompressedShadowContainer.h:37-38)."""
+    return (z * length + y) * length + x
+
+
+def top_level_grid(cells, length):
+    """``createTopLevelGrid`` (reference src/CompressedShadowContainer.cpp:71-91) from per-cell
+    ``(words, root_mask)``; cells in container order. Returns (grid uint32[length^3], total words)."""
+    grid = np.empty(length ** 3, np.uint32)
+    offset = 0
+    for i, (words, root_mask) in enumerate(cells):
+        if root_mask == 0:
+            grid[i] = GRID_CELL_SHADOWED
+        elif root_mask == 0x5555:
+            grid[i] = GRID_CELL_VISIBLE
+        else:
+            grid[i] = offset
+        offset += words  # advances for every cell (reference :88)
+    if offset > 2 ** 32:
+        raise OverflowError("combined DAG needs %d words; offsets are 32-bit" % offset)
+    return grid, offset
+
+
+def build_distributed(length, rank, world, build_cells, gather):
+    """Builds this rank's tiles and gathers all cells on every rank.
+
+    build_cells(x, y) -> list of ``length`` numpy uint32 DAGs (z = 0..length-1) for xy tile (x, y)
+    gather(obj)       -> list of every rank's obj (e.g. torch.distributed.all_gather_object wrapper)
+
+    Returns (dags in container order, grid, total words).
+    """
+    mine = {}
+    for (x, y) in tiles_of_rank(length, rank, world):
+        dags = build_cells(x, y)
+        assert len(dags) == length
+        for z, dag in enumerate(dags):
+            mine[cell_index(x, y, z, length)] = np.ascontiguousarray(dag, dtype=np.uint32)
+    everyone = gather(mine)
+    cells = {}
+    for part in everyone:
+        cells.update(part)
+    assert len(cells) == length ** 3, "some cell was never built"
+    ordered = [cells[i] for i in range(length ** 3)]
+    grid, total = top_level_grid([(d.size, int(d[0])) for d in ordered], length)
+    return ordered, grid, total

@@ -106,6 +106,12 @@ CPVS_API int cpvs_minmax_level(const cpvs_minmax* mm, int level, float* out_host
 /* Device time of the build (CUDA events on the context's stream): whole call, and the fused base
  * kernel that produces levels 1..5 alone (0 when the map is too small for it). Synchronises. */
 CPVS_API int cpvs_minmax_timing(const cpvs_minmax* mm, float* total_ms, float* base_kernel_ms);
+/* cs::createChildmask(minMax, level, offset) (src/CompressedShadowUtil.cpp:20-54) for one node: the
+ * 16-bit child mask (2 bits per child x | y<<1 | z<<2: 00 shadow, 01 lit, 10 partial) of the node whose
+ * children are texels (x..x+1, y..y+1) of pyramid level `level` at depth slices z..z+1. For
+ * known-answer tests; the builder classifies whole levels at once. */
+CPVS_API int cpvs_minmax_childmask(const cpvs_minmax* mm, uint32_t level, uint32_t x, uint32_t y, uint32_t z, uint32_t z_tile_num,
+		uint32_t* out);
 /* Device pointer of a level (same layout), for zero-copy consumers. */
 CPVS_API const float* cpvs_minmax_level_device(const cpvs_minmax* mm, int level);
 

@@ -26,6 +26,9 @@ def build(ref=True):
     subprocess.check_call(["make", "-s", "-C", HERE, "port"])
     if ref and os.path.isdir(REFERENCE_DIR):
         subprocess.check_call(["make", "-s", "-C", HERE, "ref", "REF=" + REFERENCE_DIR])
+        if os.path.exists(os.path.join(HERE, "..", "cpvs_b200", "libcpvs_b200.so")):
+            # the reference's gtests against this repo's C++ facade + CUDA library (run on the GPU box)
+            subprocess.check_call(["make", "-s", "-C", HERE, "facade-tests", "REF=" + REFERENCE_DIR])
 
 
 def have_ref():
