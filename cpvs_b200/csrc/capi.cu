@@ -76,6 +76,11 @@ struct cpvs_ctx {
 	char* arena;
 	size_t arenaBytes;
 	u64* scalars;  // 192 device words: per-level counters of the build in flight
+	// High-priority side stream for a short chain of small kernels that is independent of a bulk kernel
+	// on the main stream (the inner levels' emission next to the leaf level's): its CTAs are scheduled
+	// ahead of the bulk kernel's queued ones. Fork/join through the two events.
+	cudaStream_t aux;
+	cudaEvent_t evFork, evJoin, evAuxStart;
 };
 
 struct cpvs_minmax {
@@ -86,6 +91,9 @@ struct cpvs_minmax {
 	float* levelStorage; // levels 1.. in one allocation
 	const float* level[kMaxLevels];
 	cudaEvent_t evStart, evBase, evStop;
+	// Levels 1 and 2 are not needed by the leafmask builder and are only produced on first use.
+	std::mutex lowLock;
+	bool lowLevelsBuilt;
 };
 
 struct cpvs_shadow {
@@ -192,6 +200,14 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 	ctx->scalars = nullptr;
 	cudaError_t e = cudaStreamCreateWithFlags(&ctx->own, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->scalars), 192 * sizeof(u64));
+	ctx->aux = nullptr;
+	ctx->evFork = ctx->evJoin = ctx->evAuxStart = nullptr;
+	int prioLeast = 0, prioGreatest = 0;
+	if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prioLeast, &prioGreatest);
+	if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, prioGreatest);
+	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming);
+	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming);
+	if (e == cudaSuccess) e = cudaEventCreate(&ctx->evAuxStart);
 	if (e != cudaSuccess) {
 		delete ctx;
 		return fail(CPVS_ECUDA, "cpvs_ctx_create: %s", cudaGetErrorString(e));
@@ -207,6 +223,10 @@ int cpvs_ctx_destroy(cpvs_ctx* ctx) {
 	cudaStreamSynchronize(ctx->stream);
 	if (ctx->arena) cudaFree(ctx->arena);
 	if (ctx->scalars) cudaFree(ctx->scalars);
+	if (ctx->aux) cudaStreamDestroy(ctx->aux);
+	if (ctx->evFork) cudaEventDestroy(ctx->evFork);
+	if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
+	if (ctx->evAuxStart) cudaEventDestroy(ctx->evAuxStart);
 	cudaStreamDestroy(ctx->own);
 	delete ctx;
 	return CPVS_OK;
@@ -238,9 +258,12 @@ int cpvs_minmax_build(cpvs_ctx* ctx, const float* depth, int n, int mem, cpvs_mi
 	if (n < 2 || !isPow2((u64)n) || n > (1 << 19)) return fail(CPVS_EINVAL, "cpvs_minmax_build: side %d is not a power of two in [2, 2^19]", n);
 	if (mem != CPVS_MEM_HOST && mem != CPVS_MEM_DEVICE) return fail(CPVS_EINVAL, "cpvs_minmax_build: mem %d", mem);
 	CPVS_CUDA(cudaSetDevice(ctx->device));
-	cpvs_minmax* mm = new (std::nothrow) cpvs_minmax;
+	cpvs_minmax* mm = new (std::nothrow) cpvs_minmax();
 	if (!mm) return fail(CPVS_ENOMEM, "cpvs_minmax_build: host allocation");
-	std::memset(mm, 0, sizeof(*mm));
+	mm->ownedDepth = nullptr;
+	mm->levelStorage = nullptr;
+	mm->evStart = mm->evBase = mm->evStop = nullptr;
+	for (int k = 0; k < kMaxLevels; ++k) mm->level[k] = nullptr;
 	mm->ctx = ctx;
 	mm->n = n;
 	int levels = 1;
@@ -275,7 +298,8 @@ int cpvs_minmax_build(cpvs_ctx* ctx, const float* depth, int n, int mem, cpvs_mi
 	cudaEventCreate(&mm->evBase);
 	cudaEventCreate(&mm->evStop);
 	cudaEventRecord(mm->evStart, ctx->stream);
-	ctx->launches += launchPyramid(mm->level[0], n, lv, levels, mm->evBase, ctx->stream);
+	mm->lowLevelsBuilt = n < 128;  // small maps take the generic path, which writes every level
+	ctx->launches += launchPyramid(mm->level[0], n, lv, levels, false, mm->evBase, ctx->stream);
 	cudaEventRecord(mm->evStop, ctx->stream);
 	e = cudaGetLastError();
 	if (e != cudaSuccess) {
@@ -300,6 +324,28 @@ int cpvs_minmax_destroy(cpvs_minmax* mm) {
 	return CPVS_OK;
 }
 
+}  // extern "C"
+
+namespace {
+// Levels 1 and 2 on demand (accessors, cs::createChildmask, leafmask-less builds).
+int ensureLowLevels(const cpvs_minmax* cmm, int level) {
+	cpvs_minmax* mm = const_cast<cpvs_minmax*>(cmm);
+	if (level < 1 || level > 2) return CPVS_OK;
+	std::lock_guard<std::mutex> guard(mm->lowLock);
+	if (mm->lowLevelsBuilt) return CPVS_OK;
+	CPVS_CUDA(cudaSetDevice(mm->ctx->device));
+	float* lv[kMaxLevels];
+	for (int k = 0; k < kMaxLevels; ++k) lv[k] = const_cast<float*>(mm->level[k]);
+	mm->ctx->launches += launchPyramidLowLevels(mm->level[0], mm->n, lv, mm->ctx->stream);
+	CPVS_CUDA(cudaGetLastError());
+	CPVS_CUDA(cudaStreamSynchronize(mm->ctx->stream));  // other contexts / streams may read them next
+	mm->lowLevelsBuilt = true;
+	return CPVS_OK;
+}
+}  // namespace
+
+extern "C" {
+
 int cpvs_minmax_timing(const cpvs_minmax* mm, float* totalMs, float* baseKernelMs) {
 	if (!mm) return fail(CPVS_EINVAL, "cpvs_minmax_timing: NULL argument");
 	CPVS_CUDA(cudaSetDevice(mm->ctx->device));
@@ -315,13 +361,15 @@ int cpvs_minmax_timing(const cpvs_minmax* mm, float* totalMs, float* baseKernelM
 int cpvs_minmax_num_levels(const cpvs_minmax* mm) { return mm ? mm->numLevels : 0; }
 int cpvs_minmax_size(const cpvs_minmax* mm) { return mm ? mm->n : 0; }
 const float* cpvs_minmax_level_device(const cpvs_minmax* mm, int level) {
-	return (mm && level >= 0 && level < mm->numLevels) ? mm->level[level] : nullptr;
+	if (!mm || level < 0 || level >= mm->numLevels || ensureLowLevels(mm, level) != CPVS_OK) return nullptr;
+	return mm->level[level];
 }
 
 int cpvs_minmax_level(const cpvs_minmax* mm, int level, float* out_host) {
 	if (!mm || !out_host) return fail(CPVS_EINVAL, "cpvs_minmax_level: NULL argument");
 	if (level < 0 || level >= mm->numLevels) return fail(CPVS_EINVAL, "cpvs_minmax_level: level %d of %d", level, mm->numLevels);
 	CPVS_CUDA(cudaSetDevice(mm->ctx->device));
+	if (int rc = ensureLowLevels(mm, level)) return rc;
 	const u64 side = (u64)mm->n >> level;
 	const u64 bytes = side * side * (level == 0 ? 1 : 2) * sizeof(float);
 	CPVS_CUDA(cudaMemcpyAsync(out_host, mm->level[level], bytes, cudaMemcpyDeviceToHost, mm->ctx->stream));
@@ -335,6 +383,7 @@ int cpvs_minmax_childmask(const cpvs_minmax* mm, uint32_t level, uint32_t x, uin
 	if (side < 2 || x + 1 >= side || y + 1 >= side || zTileNum == 0) return fail(CPVS_EINVAL, "cpvs_minmax_childmask: node (%u,%u) outside level %u", x, y, level);
 	cpvs_ctx* ctx = mm->ctx;
 	CPVS_CUDA(cudaSetDevice(ctx->device));
+	if (int rc = ensureLowLevels(mm, (int)level)) return rc;
 	std::lock_guard<std::mutex> guard(ctx->buildLock);
 	PyramidView pyr;
 	pyr.n = mm->n;
@@ -366,6 +415,8 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	const bool useLeaf = leafmasks && (L - 3) >= 2;  // src/CompressedShadow.cpp:20-27
 	const int minLevel = useLeaf ? 2 : 0;            // src/CompressedShadow.cpp:30-32
 	const int lastInner = useLeaf ? 3 : 0;
+	if (!useLeaf)
+		if (int rc = ensureLowLevels(mm, 1)) return rc;  // the leafmask-less octree descends through levels 2 and 1
 
 	// ev[i] opens phase i (CPVS_PHASE_*), ev[CPVS_NUM_PHASES] closes the last one
 	struct PhaseEvents {
@@ -561,15 +612,24 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	}
 
 	trace.mark("dag alloc");
-	// 6. write every unique node once, in its final place
+	// 6. write every unique node once, in its final place. The levels are independent of each other
+	// now; the leaf level (most of the words) stays on the main stream, the chain of inner levels runs on
+	// the high-priority side stream next to it.
+	// phase EMIT_INNER: fork .. join on the main stream; phase EMIT_LEAVES: the leaf kernel alone (they overlap).
 	cudaEventRecord(phases.ev[CPVS_PHASE_EMIT_INNER], st);
-	for (int l = top; l >= minLevel; --l) {
+	const bool leafEmit = useLeaf && lv[2].n;
+	if (leafEmit) {
+		cudaEventRecord(ctx->evFork, st);
+		cudaStreamWaitEvent(ctx->aux, ctx->evFork, 0);
+	}
+	for (int l = minLevel; l <= top; ++l) {
 		const LevelArrays& a = lv[l];
 		if (!a.n) continue;
-		if (useLeaf && l == 2) cudaEventRecord(phases.ev[CPVS_PHASE_EMIT_LEAVES], st);
+		const bool isLeaf = useLeaf && l == 2;
+		cudaStream_t es = (leafEmit && !isLeaf) ? ctx->aux : st;
 		EmitLevelArgs em;
 		em.n = a.n;
-		em.leaf = (useLeaf && l == 2) ? 1 : 0;
+		em.leaf = isLeaf ? 1 : 0;
 		em.uniqueCount = dUnique + l;
 		em.wordCount = dWords + l;
 		em.firstList = a.firstList;
@@ -582,9 +642,16 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		em.childWordOffset = l > minLevel ? lv[l - 1].wordOffset : nullptr;
 		em.childLevelBase = dBases + (l > minLevel ? l - 1 : l);
 		em.dag = s->dag;
-		ctx->launches += launchEmitLevel(em, st);
+		if (isLeaf) cudaEventRecord(ctx->evAuxStart, es);
+		ctx->launches += launchEmitLevel(em, es);
+		if (isLeaf) cudaEventRecord(phases.ev[CPVS_PHASE_EMIT_LEAVES], es);  // closes the leaf kernel
 	}
-	if (!(useLeaf && lv[2].n)) cudaEventRecord(phases.ev[CPVS_PHASE_EMIT_LEAVES], st);
+	if (leafEmit) {
+		cudaEventRecord(ctx->evJoin, ctx->aux);
+		cudaStreamWaitEvent(st, ctx->evJoin, 0);
+	} else {
+		cudaEventRecord(phases.ev[CPVS_PHASE_EMIT_LEAVES], st);
+	}
 	u32 rootMask = 0;
 	e = cudaMemcpyAsync(&rootMask, s->dag, sizeof(u32), cudaMemcpyDeviceToHost, st);
 	if (e == cudaSuccess) e = cudaEventRecord(phases.ev[CPVS_NUM_PHASES], st);
@@ -593,7 +660,9 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	trace.mark("emit + final sync");
 	float ms = 0.f, phaseMs[CPVS_NUM_PHASES] = {0};
 	if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, phases.ev[0], phases.ev[CPVS_NUM_PHASES]);
-	for (int i = 0; i < CPVS_NUM_PHASES && e == cudaSuccess; ++i) e = cudaEventElapsedTime(&phaseMs[i], phases.ev[i], phases.ev[i + 1]);
+	for (int i = 0; i < CPVS_PHASE_EMIT_INNER && e == cudaSuccess; ++i) e = cudaEventElapsedTime(&phaseMs[i], phases.ev[i], phases.ev[i + 1]);
+	if (e == cudaSuccess) e = cudaEventElapsedTime(&phaseMs[CPVS_PHASE_EMIT_INNER], phases.ev[CPVS_PHASE_EMIT_INNER], phases.ev[CPVS_NUM_PHASES]);
+	if (e == cudaSuccess && leafEmit) e = cudaEventElapsedTime(&phaseMs[CPVS_PHASE_EMIT_LEAVES], ctx->evAuxStart, phases.ev[CPVS_PHASE_EMIT_LEAVES]);
 	if (e != cudaSuccess) {
 		cudaFreeAsync(s->dag, st);
 		delete s;

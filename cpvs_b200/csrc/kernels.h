@@ -7,8 +7,11 @@ namespace cpvs {
 
 // ---- pyramid.cu: MinMaxHierarchy (reference src/MinMaxHierarchy.cpp:9-97) ----
 // levels[k] (k >= 1) points at (n>>k)^2 float2 (min,max); levels[0] = depth.
-// afterBase (optional) is recorded right after the fused base kernel.
-int launchPyramid(const float* depth, int n, float* const* levels, int numLevels, cudaEvent_t afterBase, cudaStream_t stream);
+// afterBase (optional) is recorded right after the fused base kernel. With writeLowLevels == false (and
+// n >= 128) levels 1 and 2 are left unwritten; launchPyramidLowLevels produces them later if needed.
+int launchPyramid(const float* depth, int n, float* const* levels, int numLevels, bool writeLowLevels, cudaEvent_t afterBase,
+		cudaStream_t stream);
+int launchPyramidLowLevels(const float* depth, int n, float* const* levels, cudaStream_t stream);
 
 // ---- svo.cu: constructSvo (reference src/CompressedShadow.cpp:87-190) ----
 struct PyramidView {

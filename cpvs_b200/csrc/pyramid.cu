@@ -19,6 +19,10 @@ __device__ __forceinline__ float2 reduce4(float2 a, float2 b, float2 c, float2 d
 }
 
 // 256 threads, one 128 (x) by 32 (y) depth tile per CTA. Requires n >= 128.
+// kWriteLow = false skips the stores of levels 1 and 2: the leafmask builder never reads them (it
+// classifies against levels >= 3 and builds leaves from level 0), and they are 37% of this kernel's
+// traffic. They are produced on demand (launchPyramidLowLevels) for accessors and the leafmask-less mode.
+template <bool kWriteLow>
 __global__ void __launch_bounds__(256) pyramidBaseKernel(const float* __restrict__ depth, int n, float2* __restrict__ l1,
 		float2* __restrict__ l2, float2* __restrict__ l3, float2* __restrict__ l4, float2* __restrict__ l5) {
 	__shared__ float2 s2[8][32];
@@ -40,13 +44,15 @@ __global__ void __launch_bounds__(256) pyramidBaseKernel(const float* __restrict
 		m[i][1] = make_float2(stdMin(stdMin(t.z, t.w), stdMin(b.z, b.w)), stdMax(stdMax(t.z, t.w), stdMax(b.z, b.w)));
 	}
 	const int n1 = n >> 1, n2 = n >> 2, n3 = n >> 3, n4 = n >> 4, n5 = n >> 5;
+	if (kWriteLow) {
 #pragma unroll
-	for (int i = 0; i < 2; ++i)
-		*reinterpret_cast<float4*>(l1 + (size_t)(y0 / 2 + i) * n1 + x0 / 2) = make_float4(m[i][0].x, m[i][0].y, m[i][1].x, m[i][1].y);
+		for (int i = 0; i < 2; ++i)
+			*reinterpret_cast<float4*>(l1 + (size_t)(y0 / 2 + i) * n1 + x0 / 2) = make_float4(m[i][0].x, m[i][0].y, m[i][1].x, m[i][1].y);
+	}
 
 	// level 2: one texel per thread
 	const float2 v2 = reduce4(m[0][0], m[0][1], m[1][0], m[1][1]);
-	l2[(size_t)(y0 / 4) * n2 + x0 / 4] = v2;
+	if (kWriteLow) l2[(size_t)(y0 / 4) * n2 + x0 / 4] = v2;
 	s2[warp][lane] = v2;
 	__syncthreads();
 
@@ -94,20 +100,70 @@ __global__ void pyramidLevelKernel(const float* __restrict__ src, int srcChannel
 	dst[(size_t)y * outSide + x] = reduce4(a, b, c, d);
 }
 
+// All remaining levels in one CTA once a level fits in shared memory (side <= 64): the top of the
+// pyramid is a chain of tiny dependent steps, cheaper as barriers than as kernel launches.
+struct TailLevels {
+	float2* level[kMaxLevels];  // level[k] for k in (first, last]
+};
+__global__ void __launch_bounds__(1024) pyramidTailKernel(const float2* __restrict__ src, int srcSide, TailLevels out, int firstLevel, int lastLevel) {
+	__shared__ float2 sA[64 * 64], sB[32 * 32];
+	for (int i = threadIdx.x; i < srcSide * srcSide; i += blockDim.x) sA[i] = src[i];
+	__syncthreads();
+	float2* cur = sA;
+	float2* nxt = sB;
+	int side = srcSide;
+	for (int k = firstLevel + 1; k <= lastLevel; ++k) {
+		const int o = side >> 1;
+		for (int i = threadIdx.x; i < o * o; i += blockDim.x) {
+			const int x = i % o, y = i / o;
+			const float2 v = reduce4(cur[(2 * y) * side + 2 * x], cur[(2 * y) * side + 2 * x + 1], cur[(2 * y + 1) * side + 2 * x],
+					cur[(2 * y + 1) * side + 2 * x + 1]);
+			nxt[i] = v;
+			out.level[k][i] = v;
+		}
+		__syncthreads();
+		float2* t = cur;
+		cur = nxt;
+		nxt = t;
+		side = o;
+	}
+}
+
 }  // namespace
 
-int launchPyramid(const float* depth, int n, float* const* levels, int numLevels, cudaEvent_t afterBase, cudaStream_t stream) {
+int launchPyramidLowLevels(const float* depth, int n, float* const* levels, cudaStream_t stream) {
+	for (int k = 1; k <= 2; ++k) {
+		const int side = n >> k;
+		dim3 block(16, 16), grid((side + 15) / 16, (side + 15) / 16);
+		pyramidLevelKernel<<<grid, block, 0, stream>>>(k == 1 ? depth : levels[1], k == 1 ? 1 : 2, side, reinterpret_cast<float2*>(levels[k]));
+	}
+	return 2;
+}
+
+int launchPyramid(const float* depth, int n, float* const* levels, int numLevels, bool writeLowLevels, cudaEvent_t afterBase, cudaStream_t stream) {
 	int launches = 0;
 	int next = 1;
 	if (n >= 128) {
 		dim3 grid(n / 128, n / 32);
-		pyramidBaseKernel<<<grid, 256, 0, stream>>>(depth, n, reinterpret_cast<float2*>(levels[1]), reinterpret_cast<float2*>(levels[2]),
-				reinterpret_cast<float2*>(levels[3]), reinterpret_cast<float2*>(levels[4]), reinterpret_cast<float2*>(levels[5]));
+		float2 *l1 = reinterpret_cast<float2*>(levels[1]), *l2 = reinterpret_cast<float2*>(levels[2]), *l3 = reinterpret_cast<float2*>(levels[3]),
+			   *l4 = reinterpret_cast<float2*>(levels[4]), *l5 = reinterpret_cast<float2*>(levels[5]);
+		if (writeLowLevels)
+			pyramidBaseKernel<true><<<grid, 256, 0, stream>>>(depth, n, l1, l2, l3, l4, l5);
+		else
+			pyramidBaseKernel<false><<<grid, 256, 0, stream>>>(depth, n, l1, l2, l3, l4, l5);
 		++launches;
 		next = 6;
 	}
 	if (afterBase) cudaEventRecord(afterBase, stream);
 	for (int k = next; k < numLevels; ++k) {
+		const int srcSide = n >> (k - 1);
+		if (k >= 2 && srcSide <= 64) {  // levels[k-1] is a (min,max) level that fits in shared memory
+			TailLevels t;
+			for (int j = 0; j < kMaxLevels; ++j) t.level[j] = j < numLevels ? reinterpret_cast<float2*>(levels[j]) : nullptr;
+			pyramidTailKernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const float2*>(levels[k - 1]), srcSide, t, k - 1, numLevels - 1);
+			++launches;
+			break;
+		}
 		const int side = n >> k;
 		dim3 block(side >= 16 ? 16 : side, side >= 16 ? 16 : side);
 		dim3 grid((side + block.x - 1) / block.x, (side + block.y - 1) / block.y);

@@ -17,8 +17,18 @@ namespace {
 // ---- node counts per level, for exact allocation (closed form of the classification) ------------
 // A level-l node exists for every voxel (x,y,z) of pyramid level l+1 that classifies PARTIAL:
 // !(z+1 <= min*H) && !(z >= max*H)  <=>  floor(min*H) <= z <= ceil(max*H)-1, inside the z-tile.
-__global__ void countNodesKernel(const float2* __restrict__ texels, u64 numTexels, float heightF, float zLoF, float zHiF,
-		u64* __restrict__ count) {
+struct CountLevels {
+	const float2* texels[kMaxLevels];  // pyramid level l+1 for node level l
+	u64 numTexels[kMaxLevels];
+	float heightF[kMaxLevels], zLoF[kMaxLevels], zHiF[kMaxLevels];
+	int minLevel;
+};
+// blockIdx.y picks the node level; all levels are counted by one launch.
+__global__ void __launch_bounds__(256) countNodesKernel(CountLevels p, u64* __restrict__ counts) {
+	const int level = p.minLevel + blockIdx.y;
+	const float2* __restrict__ texels = p.texels[level];
+	const u64 numTexels = p.numTexels[level];
+	const float heightF = p.heightF[level], zLoF = p.zLoF[level], zHiF = p.zHiF[level];
 	u64 local = 0;
 	for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < numTexels; i += (u64)gridDim.x * blockDim.x) {
 		const float2 t = texels[i];
@@ -36,7 +46,7 @@ __global__ void countNodesKernel(const float2* __restrict__ texels, u64 numTexel
 	if (threadIdx.x == 0) {
 		u64 total = 0;
 		for (int w = 0; w < (int)(blockDim.x >> 5); ++w) total += sWarp[w];
-		if (total) atomicAdd(reinterpret_cast<unsigned long long*>(count), (unsigned long long)total);
+		if (total) atomicAdd(reinterpret_cast<unsigned long long*>(counts + level), (unsigned long long)total);
 	}
 }
 
@@ -231,19 +241,25 @@ int launchChildmask(const PyramidView& pyr, int level, u32 zTileNum, u32 x, u32 
 }
 
 int launchCountNodes(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, int minLevel, u64* counts, cudaStream_t stream) {
-	int launches = 0;
+	const int numCounted = pyr.numLevels - 2 - minLevel;  // levels minLevel .. numLevels-3
+	if (numCounted <= 0) return 0;
+	CountLevels p;
+	p.minLevel = minLevel;
+	u64 maxTexels = 0;
 	for (int level = minLevel; level <= pyr.numLevels - 3; ++level) {
 		const u32 side = (u32)pyr.n >> (level + 1);
-		const u64 texels = (u64)side * side;
-		const float heightF = (float)(side * zTileNum);
-		const float zLo = (float)(zTileIndex * side), zHi = (float)(zTileIndex * side + side - 1);
-		u64 blocks = (texels + 255) / 256;
-		if (blocks > 148 * 16) blocks = 148 * 16;
-		countNodesKernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const float2*>(pyr.level[level + 1]), texels, heightF, zLo, zHi,
-				counts + level);
-		++launches;
+		p.texels[level] = reinterpret_cast<const float2*>(pyr.level[level + 1]);
+		p.numTexels[level] = (u64)side * side;
+		p.heightF[level] = (float)(side * zTileNum);
+		p.zLoF[level] = (float)(zTileIndex * side);
+		p.zHiF[level] = (float)(zTileIndex * side + side - 1);
+		if (p.numTexels[level] > maxTexels) maxTexels = p.numTexels[level];
 	}
-	return launches;
+	u64 blocks = (maxTexels + 256 * 8 - 1) / (256 * 8);
+	if (blocks > 148 * 8) blocks = 148 * 8;
+	if (blocks < 1) blocks = 1;
+	countNodesKernel<<<dim3((unsigned)blocks, (unsigned)numCounted), 256, 0, stream>>>(p, counts);
+	return 1;
 }
 
 int launchExpandLevel(const PyramidView& pyr, int level, u32 zTileNum, const u64* coords, u64 n, u16* masks, u32* firstChild,

@@ -61,8 +61,8 @@ extern "C" {
 #define CPVS_PHASE_LEAF_RESOLVE 5 /* leaf level: rank scan + unique ids */
 #define CPVS_PHASE_INNER_MERGE 6  /* all inner levels: clear + insert + rank scan + unique ids */
 #define CPVS_PHASE_BASES 7        /* level bases + host read-back of sizes */
-#define CPVS_PHASE_EMIT_INNER 8   /* compressed inner nodes, all levels */
-#define CPVS_PHASE_EMIT_LEAVES 9  /* compressed leaves (1 kernel) */
+#define CPVS_PHASE_EMIT_INNER 8   /* whole emission: inner levels on the main stream, leaves on a side stream */
+#define CPVS_PHASE_EMIT_LEAVES 9  /* compressed leaves (1 kernel); runs concurrently, inside phase 8 */
 #define CPVS_NUM_PHASES 10
 
 /* Grid sentinels written by CompressedShadowContainer::createTopLevelGrid
