@@ -456,11 +456,16 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	for (int l = minLevel; l <= top; ++l)
 		if (lv[l].n >= (1ull << 30)) return fail(CPVS_EOVERFLOW, "level %d has %llu nodes (limit 2^30)", l, (unsigned long long)lv[l].n);
 
+	// The top levels up to kSmallMaxNodes nodes each ("small": smallLow..top) are handled by single-CTA
+	// kernels, one launch per phase instead of one or more per level.
+	int smallLow = top + 1;
+	for (int l = top; l >= lastInner && lv[l].n && lv[l].n <= kSmallMaxNodes; --l) smallLow = l;
+
 	// 2. per-level arrays, carved out of the context arena
-	u64 scanTiles = 0, scanLaunches = 0, maxTable = 0;
+	u64 scanTiles = 0, scanLaunches = 0, maxTable = 2 * kSmallMaxNodes;
 	for (int l = top; l >= minLevel; --l) {
 		const u64 n = lv[l].n;
-		if (!n) continue;
+		if (!n || l >= smallLow) continue;
 		if (!(useLeaf && l == 2)) {
 			scanTiles += (n + kScanTile - 1) / kScanTile;
 			++scanLaunches;
@@ -533,7 +538,24 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_EXPAND], st));
 	storeU64Kernel<<<1, 1, 0, st>>>(lv[top].coords, packCoord(0, 0, zTileIndex * 2));
 	++ctx->launches;
-	for (int l = top; l >= lastInner && lv[l].n; --l) {
+	{
+		SmallExpandArgs sx;
+		sx.count = 0;
+		for (int l = top; l >= smallLow; --l) {
+			SmallExpandLevel& e = sx.lv[sx.count++];
+			e.side = (u32)mm->n >> l;
+			e.tex = pyr.level[l];
+			e.heightF = (float)(e.side * zTileNum);
+			e.level0 = l == 0 ? 1 : 0;
+			e.coords = lv[l].coords;
+			e.masks = lv[l].masks;
+			e.firstChild = lv[l].firstChild;
+			e.childCoords = (l > minLevel && lv[l - 1].n) ? lv[l - 1].coords : nullptr;
+			e.childTotal = dChildTotal + l;
+		}
+		ctx->launches += launchExpandSmallLevels(sx, st);
+	}
+	for (int l = smallLow - 1; l >= lastInner && lv[l].n; --l) {
 		u64* childCoords = (l > minLevel && lv[l - 1].n) ? lv[l - 1].coords : nullptr;
 		ctx->launches += launchExpandLevel(pyr, l, zTileNum, lv[l].coords, lv[l].n, lv[l].masks, lv[l].firstChild, childCoords,
 				dChildTotal + l, nextScan(lv[l].n), st);
@@ -554,7 +576,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAF_RESOLVE], st));
 		CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_INNER_MERGE], st));
 	}
-	for (int l = minLevel; l <= top; ++l) {
+	for (int l = minLevel; l < smallLow; ++l) {
 		LevelArrays& a = lv[l];
 		if (!a.n) continue;
 		const bool leafLevel = useLeaf && l == 2;
@@ -583,6 +605,26 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		}
 		ctx->launches += launchMergeLevel(m, s, leafLevel ? phases.ev[CPVS_PHASE_LEAF_RESOLVE] : nullptr, st);
 		if (leafLevel) CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_INNER_MERGE], st));
+	}
+	{
+		SmallMergeArgs sm;
+		sm.count = 0;
+		sm.table = dTable;
+		sm.errorFlag = dErrorFlag;
+		for (int l = smallLow; l <= top; ++l) {
+			if (!lv[l].n) continue;
+			SmallMergeLevel& m = sm.lv[sm.count++];
+			m.n = (u32)lv[l].n;
+			m.masks = lv[l].masks;
+			m.firstChild = lv[l].firstChild;
+			m.childUid = l > minLevel ? lv[l - 1].uid : nullptr;
+			m.uid = lv[l].uid;
+			m.firstList = lv[l].firstList;
+			m.wordOffset = lv[l].wordOffset;
+			m.uniqueCount = dUnique + l;
+			m.wordCount = dWords + l;
+		}
+		ctx->launches += launchMergeSmallLevels(sm, st);
 	}
 	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_BASES], st));
 
@@ -622,11 +664,12 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		cudaEventRecord(ctx->evFork, st);
 		cudaStreamWaitEvent(ctx->aux, ctx->evFork, 0);
 	}
+	EmitMultiArgs inner;
+	inner.count = 0;
 	for (int l = minLevel; l <= top; ++l) {
 		const LevelArrays& a = lv[l];
 		if (!a.n) continue;
 		const bool isLeaf = useLeaf && l == 2;
-		cudaStream_t es = (leafEmit && !isLeaf) ? ctx->aux : st;
 		EmitLevelArgs em;
 		em.n = a.n;
 		em.leaf = isLeaf ? 1 : 0;
@@ -642,10 +685,15 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		em.childWordOffset = l > minLevel ? lv[l - 1].wordOffset : nullptr;
 		em.childLevelBase = dBases + (l > minLevel ? l - 1 : l);
 		em.dag = s->dag;
-		if (isLeaf) cudaEventRecord(ctx->evAuxStart, es);
-		ctx->launches += launchEmitLevel(em, es);
-		if (isLeaf) cudaEventRecord(phases.ev[CPVS_PHASE_EMIT_LEAVES], es);  // closes the leaf kernel
+		if (isLeaf) {
+			cudaEventRecord(ctx->evAuxStart, st);
+			ctx->launches += launchEmitLevel(em, st);
+			cudaEventRecord(phases.ev[CPVS_PHASE_EMIT_LEAVES], st);  // closes the leaf kernel
+		} else if (inner.count < kMaxEmitLevels) {
+			inner.lv[inner.count++] = em;
+		}
 	}
+	ctx->launches += launchEmitInnerLevels(inner, leafEmit ? ctx->aux : st);
 	if (leafEmit) {
 		cudaEventRecord(ctx->evJoin, ctx->aux);
 		cudaStreamWaitEvent(st, ctx->evJoin, 0);

@@ -30,10 +30,9 @@ __device__ __forceinline__ void emitRun(const EmitLevelArgs& a, const u32* sOut,
 	for (u32 i = threadIdx.x; i < runWords; i += kEmitThreads) out[i] = sOut[i];
 }
 
-__global__ void __launch_bounds__(kEmitThreads) emitInnerKernel(EmitLevelArgs a) {
-	__shared__ u32 sOut[kEmitThreads * 9];
+__device__ __forceinline__ void emitInnerBlock(const EmitLevelArgs& a, u32 block, u32* sOut) {
 	const u64 unique = *a.uniqueCount;
-	const u64 r0 = (u64)blockIdx.x * kEmitThreads;
+	const u64 r0 = (u64)block * kEmitThreads;
 	if (r0 >= unique) return;
 	const u64 r = r0 + threadIdx.x;
 	const u32 runStart = a.wordOffset[r0];
@@ -52,6 +51,19 @@ __global__ void __launch_bounds__(kEmitThreads) emitInnerKernel(EmitLevelArgs a)
 	}
 	__syncthreads();
 	emitRun(a, sOut, runStart, runEnd - runStart);
+}
+
+__global__ void __launch_bounds__(kEmitThreads) emitInnerKernel(EmitLevelArgs a) {
+	__shared__ u32 sOut[kEmitThreads * 9];
+	emitInnerBlock(a, blockIdx.x, sOut);
+}
+
+// All inner levels in one launch: blockStart[] maps a block to its level.
+__global__ void __launch_bounds__(kEmitThreads) emitInnerLevelsKernel(EmitMultiArgs m) {
+	__shared__ u32 sOut[kEmitThreads * 9];
+	int s = 0;
+	while (s + 1 < m.count && blockIdx.x >= m.blockStart[s + 1]) ++s;
+	emitInnerBlock(m.lv[s], blockIdx.x - m.blockStart[s], sOut);
 }
 
 // Leaves: expands the k-code (nibble x of word y = lit slices of texel (x,y)) into the 64-bit masks of
@@ -93,6 +105,18 @@ __global__ void __launch_bounds__(kEmitThreads) emitLeavesKernel(EmitLevelArgs a
 
 int launchLevelBases(const u64* words, u64* bases, int topLevel, int minLevel, u64* totalWords, cudaStream_t stream) {
 	levelBasesKernel<<<1, 1, 0, stream>>>(words, bases, topLevel, minLevel, totalWords);
+	return 1;
+}
+
+int launchEmitInnerLevels(EmitMultiArgs& m, cudaStream_t stream) {
+	if (m.count <= 0) return 0;
+	u32 blocks = 0;
+	for (int s = 0; s < m.count; ++s) {
+		m.blockStart[s] = blocks;
+		blocks += (u32)((m.lv[s].n + kEmitThreads - 1) / kEmitThreads);
+	}
+	m.blockStart[m.count] = blocks;
+	emitInnerLevelsKernel<<<blocks, kEmitThreads, 0, stream>>>(m);
 	return 1;
 }
 

@@ -31,6 +31,26 @@ int launchCountNodes(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, int m
 int launchExpandLevel(const PyramidView& pyr, int level, u32 zTileNum, const u64* coords, u64 n, u16* masks,
 		u32* firstChild, u64* childCoords, u64* childTotal, ScanLaunch scan, cudaStream_t stream);
 
+// The small top levels (<= kSmallMaxNodes nodes each, root first) expanded by a single CTA.
+constexpr int kSmallThreads = 1024;
+constexpr u32 kSmallMaxNodes = 4096;
+struct SmallExpandLevel {
+	const float* tex;  // pyramid level the children are classified against
+	u32 side;
+	float heightF;
+	int level0;
+	const u64* coords;
+	u16* masks;
+	u32* firstChild;
+	u64* childCoords;  // next level's coordinate list (may be null when no child can exist)
+	u64* childTotal;
+};
+struct SmallExpandArgs {
+	SmallExpandLevel lv[kMaxLevels];
+	int count;
+};
+int launchExpandSmallLevels(const SmallExpandArgs& a, cudaStream_t stream);
+
 // Level-2 nodes: the leaf's k-code (codes[leaf*8 + row], nibble x = lit slices of texel (x,row)), a
 // 64-bit hash of it and the 16-bit 1x1x8 childmask (2 bits per slice).
 // Also sets one bit per leaf hash in `sketch` (kSketchWords zeroed words): a linear-counting estimate of
@@ -61,6 +81,26 @@ struct MergeLevelArgs {
 	u64* uniqueCount;      // out: number of unique nodes
 	u64* wordCount;        // out: compressed words of the level
 };
+// The small top levels merged bottom-up by a single CTA (same result as launchMergeLevel per level).
+struct SmallMergeLevel {
+	u32 n;
+	const u16* masks;
+	const u32* firstChild;
+	const u32* childUid;
+	u32* uid;
+	u32* firstList;
+	u32* wordOffset;
+	u64* uniqueCount;
+	u64* wordCount;
+};
+struct SmallMergeArgs {
+	SmallMergeLevel lv[kMaxLevels];
+	int count;
+	u64* table;  // >= 2 * kSmallMaxNodes slots
+	u32* errorFlag;
+};
+int launchMergeSmallLevels(const SmallMergeArgs& a, cudaStream_t stream);
+
 // Leaf level only: picks the table capacity from the sketch's set-bit count and clears that many slots.
 int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* tableMaskDev, cudaStream_t stream);
 // afterInsert (optional) is recorded between the insert kernel and the rank scan.
@@ -84,6 +124,14 @@ struct EmitLevelArgs {
 	u32* dag;
 };
 int launchEmitLevel(const EmitLevelArgs& a, cudaStream_t stream);
+// Several inner levels in one launch (block ranges per level).
+constexpr int kMaxEmitLevels = 24;
+struct EmitMultiArgs {
+	EmitLevelArgs lv[kMaxEmitLevels];
+	u32 blockStart[kMaxEmitLevels + 1];
+	int count;
+};
+int launchEmitInnerLevels(EmitMultiArgs& a, cudaStream_t stream);
 // bases[l] for l = top..minLevel from words[l]; total -> *totalWords. One thread.
 int launchLevelBases(const u64* words, u64* bases, int topLevel, int minLevel, u64* totalWords, cudaStream_t stream);
 

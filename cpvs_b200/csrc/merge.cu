@@ -80,10 +80,8 @@ __global__ void __launch_bounds__(256) insertLeavesKernel(const u32* __restrict_
 	});
 }
 
-__global__ void __launch_bounds__(256) insertInnerKernel(const u16* __restrict__ masks, const u32* __restrict__ firstChild,
-		const u32* __restrict__ childUid, u64 n, u64* __restrict__ table, u64 tableMask, u32* __restrict__ slotOf, u32* errorFlag) {
-	const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= n) return;
+__device__ __forceinline__ u32 insertInnerNode(u32 j, const u16* __restrict__ masks, const u32* __restrict__ firstChild,
+		const u32* __restrict__ childUid, u64* __restrict__ table, u64 tableMask, u32* errorFlag) {
 	const u32 mask = masks[j];
 	const u32 k = __popc(mask & 0xAAAAu);
 	const u32* kids = childUid + firstChild[j];
@@ -97,7 +95,7 @@ __global__ void __launch_bounds__(256) insertInnerKernel(const u16* __restrict__
 			h = mix64(h ^ ((u64)uid[c] + 0x9E3779B97F4A7C15ull * (c + 1)));
 		}
 	}
-	slotOf[j] = findGroupSlot(table, tableMask, h, (u32)j, errorFlag, [&](u32 other) {
+	return findGroupSlot(table, tableMask, h, j, errorFlag, [&](u32 other) {
 		if (masks[other] != mask) return false;
 		const u32* theirs = childUid + firstChild[other];
 		bool same = true;
@@ -106,6 +104,13 @@ __global__ void __launch_bounds__(256) insertInnerKernel(const u16* __restrict__
 			if (c < k) same = same && (theirs[c] & kUidMask) == uid[c];
 		return same;
 	});
+}
+
+__global__ void __launch_bounds__(256) insertInnerKernel(const u16* __restrict__ masks, const u32* __restrict__ firstChild,
+		const u32* __restrict__ childUid, u64 n, u64* __restrict__ table, u64 tableMask, u32* __restrict__ slotOf, u32* errorFlag) {
+	const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	slotOf[j] = insertInnerNode((u32)j, masks, firstChild, childUid, table, tableMask, errorFlag);
 }
 
 // slotOf[j] (in) -> uid[j] (out) = unique id | kResolvedFlag. Readers strip the flag (kUidMask).
@@ -168,6 +173,89 @@ __global__ void __launch_bounds__(kScanThreads, 8) resolveKernel(const u64* __re
 	}
 }
 
+// The small top levels, bottom-up, by one CTA: clear, insert, rank, resolve with block barriers in
+// between. Same tuples, same first-occurrence rule, same outputs as the per-level kernels.
+__global__ void __launch_bounds__(kSmallThreads) mergeSmallLevelsKernel(SmallMergeArgs a) {
+	__shared__ u32 sWarpC[kSmallThreads / 32], sWarpW[kSmallThreads / 32];
+	constexpr u64 kSlots = 2 * kSmallMaxNodes;
+	const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	for (int s = 0; s < a.count; ++s) {
+		const SmallMergeLevel& L = a.lv[s];
+		if (L.n == 1) {
+			if (threadIdx.x == 0) {
+				L.uid[0] = kResolvedFlag;
+				L.firstList[0] = 0;
+				L.wordOffset[0] = 0;
+				*L.uniqueCount = 1;
+				*L.wordCount = 1 + __popc(L.masks[0] & 0xAAAAu);
+			}
+			__syncthreads();
+			continue;
+		}
+		for (u32 i = threadIdx.x; i < kSlots; i += kSmallThreads) a.table[i] = kEmpty;
+		__syncthreads();
+		for (u32 j = threadIdx.x; j < L.n; j += kSmallThreads) L.uid[j] = insertInnerNode(j, L.masks, L.firstChild, L.childUid, a.table, kSlots - 1, a.errorFlag);
+		__syncthreads();
+		u32 carryC = 0, carryW = 0;
+		for (u32 base = 0; base < L.n; base += kSmallThreads) {
+			const u32 j = base + threadIdx.x;
+			u32 rep = 0xFFFFFFFFu, words = 0;
+			if (j < L.n) {
+				rep = (u32)ldRelaxed64(a.table + L.uid[j]);
+				if (rep == j) words = 1 + __popc(L.masks[j] & 0xAAAAu);
+			}
+			u32 inclC = words ? 1u : 0u, inclW = words;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const u32 uc = __shfl_up_sync(0xFFFFFFFFu, inclC, d), uw = __shfl_up_sync(0xFFFFFFFFu, inclW, d);
+				if ((int)lane >= d) {
+					inclC += uc;
+					inclW += uw;
+				}
+			}
+			if (lane == 31) {
+				sWarpC[warp] = inclC;
+				sWarpW[warp] = inclW;
+			}
+			__syncthreads();
+			u32 beforeC = 0, beforeW = 0, totC = 0, totW = 0;
+#pragma unroll
+			for (u32 w = 0; w < kSmallThreads / 32; ++w) {
+				const u32 c = sWarpC[w], v = sWarpW[w];
+				if (w < warp) {
+					beforeC += c;
+					beforeW += v;
+				}
+				totC += c;
+				totW += v;
+			}
+			__syncthreads();
+			if (j < L.n) {
+				if (words) {
+					const u32 rank = carryC + beforeC + inclC - 1;
+					L.firstList[rank] = j;
+					L.wordOffset[rank] = carryW + beforeW + inclW - words;
+					L.uid[j] = rank | kResolvedFlag;
+				} else {
+					L.uid[j] = rep;  // resolved below, once every first occurrence of the level has its rank
+				}
+			}
+			carryC += totC;
+			carryW += totW;
+		}
+		__syncthreads();
+		for (u32 j = threadIdx.x; j < L.n; j += kSmallThreads) {
+			const u32 v = L.uid[j];
+			if (!(v & kResolvedFlag)) L.uid[j] = L.uid[v];
+		}
+		if (threadIdx.x == 0) {
+			*L.uniqueCount = carryC;
+			*L.wordCount = carryW;
+		}
+		__syncthreads();
+	}
+}
+
 // A level with a single node (the root, which the reference never merges).
 __global__ void singleNodeKernel(const u16* __restrict__ masks, int leaf, u32* uid, u32* firstList, u32* wordOffset, u64* uniqueCount,
 		u64* wordCount) {
@@ -180,6 +268,12 @@ __global__ void singleNodeKernel(const u16* __restrict__ masks, int leaf, u32* u
 }
 
 }  // namespace
+
+int launchMergeSmallLevels(const SmallMergeArgs& a, cudaStream_t stream) {
+	if (a.count <= 0) return 0;
+	mergeSmallLevelsKernel<<<1, kSmallThreads, 0, stream>>>(a);
+	return 1;
+}
 
 int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* tableMaskDev, cudaStream_t stream) {
 	sizeAndClearLeafTableKernel<<<148 * 8, 256, 0, stream>>>(table, maxSlots, setBits, tableMaskDev);

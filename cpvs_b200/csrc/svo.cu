@@ -126,6 +126,66 @@ __global__ void __launch_bounds__(kScanThreads) expandLevelKernel(const float* _
 	}
 }
 
+// The top of the octree: levels of at most kSmallMaxNodes nodes are a chain of tiny dependent steps.
+// One CTA walks them all (barriers instead of kernel launches and look-back handshakes).
+__global__ void __launch_bounds__(kSmallThreads) expandSmallLevelsKernel(SmallExpandArgs a) {
+	__shared__ u32 sWarp[kSmallThreads / 32];
+	const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	u32 n = 1;  // the first level is the root
+	for (int s = 0; s < a.count; ++s) {
+		const SmallExpandLevel& L = a.lv[s];
+		u32 carry = 0;
+		for (u32 base = 0; base < n; base += kSmallThreads) {
+			const u32 j = base + threadIdx.x;
+			u64 c = 0;
+			u32 m = 0;
+			if (j < n) {
+				c = L.coords[j];
+				u32 x, y, z;
+				unpackCoord(c, x, y, z);
+				m = L.level0 ? childmaskLevel0(L.tex, L.side, L.heightF, x, y, z)
+							 : childmaskInner(reinterpret_cast<const float2*>(L.tex), L.side, L.heightF, x, y, z);
+			}
+			const u32 cnt = __popc(m & 0xAAAAu);
+			u32 incl = cnt;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const u32 up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+				if ((int)lane >= d) incl += up;
+			}
+			if (lane == 31) sWarp[warp] = incl;
+			__syncthreads();
+			u32 before = 0, total = 0;
+#pragma unroll
+			for (u32 w = 0; w < kSmallThreads / 32; ++w) {
+				const u32 v = sWarp[w];
+				if (w < warp) before += v;
+				total += v;
+			}
+			__syncthreads();
+			if (j < n) {
+				u32 pos = carry + before + incl - cnt;
+				L.masks[j] = (u16)m;
+				L.firstChild[j] = pos;
+				u32 partial = m & 0xAAAAu;
+				if (partial) {
+					u32 x, y, z;
+					unpackCoord(c, x, y, z);
+					while (partial) {
+						const u32 child = (__ffs(partial) - 1) >> 1;
+						partial &= partial - 1;
+						L.childCoords[pos++] = packCoord((x + (child & 1u)) * 2u, (y + ((child >> 1) & 1u)) * 2u, (z + (child >> 2)) * 2u);
+					}
+				}
+			}
+			carry += total;
+		}
+		if (threadIdx.x == 0) *L.childTotal = carry;
+		n = carry;
+		__syncthreads();  // the next level reads the coordinates written above
+	}
+}
+
 // ---- leaves: cs::createChildmask1x1x8 + createLeafmask (src/CompressedShadowUtil.cpp:59-99) -------
 // Eight lanes per level-2 node, lane r owns depth row r of the node's 8x8 texels.
 //
@@ -259,6 +319,12 @@ int launchCountNodes(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, int m
 	if (blocks > 148 * 8) blocks = 148 * 8;
 	if (blocks < 1) blocks = 1;
 	countNodesKernel<<<dim3((unsigned)blocks, (unsigned)numCounted), 256, 0, stream>>>(p, counts);
+	return 1;
+}
+
+int launchExpandSmallLevels(const SmallExpandArgs& a, cudaStream_t stream) {
+	if (a.count <= 0) return 0;
+	expandSmallLevelsKernel<<<1, kSmallThreads, 0, stream>>>(a);
 	return 1;
 }
 
