@@ -81,6 +81,10 @@ struct cpvs_ctx {
 	// ahead of the bulk kernel's queued ones. Fork/join through the two events.
 	cudaStream_t aux;
 	cudaEvent_t evFork, evJoin, evAuxStart;
+	// Normal-priority side stream for the per-level rank scans, which only the final emission needs and
+	// which therefore run next to the following levels' inserts.
+	cudaStream_t aux2, aux3;  // the ranks of different levels are independent: alternate between the two
+	cudaEvent_t evRankStart, evRankStop, evJoin3, evClear;
 };
 
 struct cpvs_minmax {
@@ -168,6 +172,9 @@ struct LevelArrays {
 	u32* wordOffset = nullptr;
 	u32* leafCodes = nullptr;
 	u64* leafHash = nullptr;
+	u64* table = nullptr;      // merge table of this level (large levels own one; small levels share)
+	u64 tableSlots = 0;
+	u32* slotOffset = nullptr; // per table slot: word offset of the group's node
 };
 
 }  // namespace
@@ -208,6 +215,14 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming);
 	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming);
 	if (e == cudaSuccess) e = cudaEventCreate(&ctx->evAuxStart);
+	ctx->aux2 = ctx->aux3 = nullptr;
+	ctx->evRankStart = ctx->evRankStop = ctx->evJoin3 = ctx->evClear = nullptr;
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux2, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux3, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evJoin3, cudaEventDisableTiming);
+	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evClear, cudaEventDisableTiming);
+	if (e == cudaSuccess) e = cudaEventCreate(&ctx->evRankStart);
+	if (e == cudaSuccess) e = cudaEventCreate(&ctx->evRankStop);
 	if (e != cudaSuccess) {
 		delete ctx;
 		return fail(CPVS_ECUDA, "cpvs_ctx_create: %s", cudaGetErrorString(e));
@@ -227,6 +242,12 @@ int cpvs_ctx_destroy(cpvs_ctx* ctx) {
 	if (ctx->evFork) cudaEventDestroy(ctx->evFork);
 	if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
 	if (ctx->evAuxStart) cudaEventDestroy(ctx->evAuxStart);
+	if (ctx->aux2) cudaStreamDestroy(ctx->aux2);
+	if (ctx->aux3) cudaStreamDestroy(ctx->aux3);
+	if (ctx->evJoin3) cudaEventDestroy(ctx->evJoin3);
+	if (ctx->evClear) cudaEventDestroy(ctx->evClear);
+	if (ctx->evRankStart) cudaEventDestroy(ctx->evRankStart);
+	if (ctx->evRankStop) cudaEventDestroy(ctx->evRankStop);
 	cudaStreamDestroy(ctx->own);
 	delete ctx;
 	return CPVS_OK;
@@ -462,7 +483,8 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	for (int l = top; l >= lastInner && lv[l].n && lv[l].n <= kSmallMaxNodes; --l) smallLow = l;
 
 	// 2. per-level arrays, carved out of the context arena
-	u64 scanTiles = 0, scanLaunches = 0, maxTable = 2 * kSmallMaxNodes;
+	u64 scanTiles = 0, scanLaunches = 0;
+	const u64 maxTable = 2 * kSmallMaxNodes;  // shared by the small levels; large levels own their tables
 	for (int l = top; l >= minLevel; --l) {
 		const u64 n = lv[l].n;
 		if (!n || l >= smallLow) continue;
@@ -473,8 +495,6 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		if (n > 1) {
 			scanTiles += (n + kScanTile - 1) / kScanTile;
 			++scanLaunches;
-			const u64 t = pow2AtLeast(n * 2 < 1024 ? 1024 : n * 2);
-			if (t > maxTable) maxTable = t;
 		}
 	}
 	ScanTileState* dTiles = nullptr;
@@ -495,6 +515,14 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 			a.uid = ar.take<u32>(a.n);
 			a.firstList = ar.take<u32>(a.n);
 			a.wordOffset = ar.take<u32>(a.n);
+			if (l >= smallLow) {
+				a.table = dTable;
+				a.tableSlots = 2 * kSmallMaxNodes;
+			} else {
+				a.tableSlots = pow2AtLeast(a.n * 2 < 1024 ? 1024 : a.n * 2);
+				a.table = ar.take<u64>(a.tableSlots);
+			}
+			a.slotOffset = ar.take<u32>(a.tableSlots);
 			if (useLeaf && l == 2) {
 				a.leafCodes = ar.take<u32>(a.n * 8);
 				a.leafHash = ar.take<u64>(a.n);
@@ -519,10 +547,20 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	trace.mark("arena carve");
 	// tile states, tickets and the leaf sketch sit at the front of the arena: one memset clears them all
 	CPVS_CUDA(cudaMemsetAsync(ctx->arena, 0, reinterpret_cast<char*>(dTable) - ctx->arena, st));
-	auto tableSizeFor = [](u64 n) { return pow2AtLeast(n * 2 < 1024 ? 1024 : n * 2); };
-	// the table of the lowest level is cleared here so that its insert phase is one kernel (the leaf
-	// level instead sizes and clears its table on the device, once the sketch is filled)
-	if (!useLeaf && lv[minLevel].n > 1) CPVS_CUDA(cudaMemsetAsync(dTable, 0xFF, tableSizeFor(lv[minLevel].n) * sizeof(u64), st));
+	// the large inner levels' tables are cleared up front (the leaf level sizes and clears its table on
+	// the device, once the sketch is filled; the small levels clear theirs inside their kernel)
+	// -- on a side stream, next to the expansion; the first inner insert waits for it.
+	bool tablesClearing = false;
+	for (int l = minLevel; l < smallLow; ++l)
+		if (lv[l].n > 1 && !(useLeaf && l == 2)) {
+			if (!tablesClearing) {
+				CPVS_CUDA(cudaEventRecord(ctx->evFork, st));  // the arena may still be in use by the previous build
+				CPVS_CUDA(cudaStreamWaitEvent(ctx->aux3, ctx->evFork, 0));
+				tablesClearing = true;
+			}
+			CPVS_CUDA(cudaMemsetAsync(lv[l].table, 0xFF, lv[l].tableSlots * sizeof(u64), ctx->aux3));
+		}
+	if (tablesClearing) CPVS_CUDA(cudaEventRecord(ctx->evClear, ctx->aux3));
 	u64 *dSketchBits = dScalars + 161, *dLeafTableMask = dScalars + 162;
 	u32* dErrorFlag = reinterpret_cast<u32*>(dScalars + 163);
 	u64 tileCursor = 0, launchCursor = 0;
@@ -565,46 +603,66 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		ctx->launches += launchBuildLeaves(pyr, zTileNum, lv[2].coords, lv[2].n, lv[2].leafCodes, lv[2].leafHash, lv[2].masks,
 				dSketch, st);
 
-	// 4. bottom-up merge (src/CompressedShadow.cpp:215-241)
-	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAF_TABLE], st));
+	// 4. bottom-up merge (src/CompressedShadow.cpp:215-241). The chain of inserts is the critical path and
+	// runs on the high-priority stream `ms`, so that its CTAs are dispatched ahead of the queued CTAs of
+	// the rank scans running beside it; the main stream rejoins before the bases.
+	cudaStream_t mergeStream = ctx->aux;
+	CPVS_CUDA(cudaEventRecord(ctx->evFork, st));
+	CPVS_CUDA(cudaStreamWaitEvent(mergeStream, ctx->evFork, 0));
+	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAF_TABLE], mergeStream));
 	if (haveLeaves) {
-		ctx->launches += launchSketchPopcount(dSketch, dSketchBits, st);
-		ctx->launches += launchSizeLeafTable(dTable, tableSizeFor(lv[2].n), dSketchBits, dLeafTableMask, st);
+		ctx->launches += launchSketchPopcount(dSketch, dSketchBits, mergeStream);
+		ctx->launches += launchSizeLeafTable(lv[2].table, lv[2].tableSlots, dSketchBits, dLeafTableMask, mergeStream);
 	}
-	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAF_INSERT], st));
+	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAF_INSERT], mergeStream));
 	if (!(useLeaf && lv[2].n)) {
-		CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAF_RESOLVE], st));
-		CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_INNER_MERGE], st));
+		CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAF_RESOLVE], mergeStream));
+		CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_INNER_MERGE], mergeStream));
 	}
+	// Per level: insert on the main stream (gives every node its group id, all the next level needs),
+	// rank on the side stream (orders the unique nodes; only the emission needs it).
+	bool ranksPending = false;
 	for (int l = minLevel; l < smallLow; ++l) {
 		LevelArrays& a = lv[l];
 		if (!a.n) continue;
 		const bool leafLevel = useLeaf && l == 2;
 		MergeLevelArgs m;
 		m.n = a.n;
-		m.leaf = (useLeaf && l == 2) ? 1 : 0;
+		m.leaf = leafLevel ? 1 : 0;
 		m.leafCodes = a.leafCodes;
 		m.leafHash = a.leafHash;
 		m.masks = a.masks;
 		m.firstChild = a.firstChild;
 		m.childUid = l > minLevel ? lv[l - 1].uid : nullptr;
-		m.table = dTable;
-		m.tableSize = tableSizeFor(a.n);
+		m.table = a.table;
+		m.tableSize = a.tableSlots;
 		m.sketchBits = dSketchBits;
 		m.tableMaskDev = dLeafTableMask;
 		m.errorFlag = dErrorFlag;
 		m.uid = a.uid;
 		m.firstList = a.firstList;
 		m.wordOffset = a.wordOffset;
+		m.slotOffset = a.slotOffset;
 		m.uniqueCount = dUnique + l;
 		m.wordCount = dWords + l;
-		ScanLaunch s{nullptr, nullptr};
-		if (a.n > 1) {
-			if (l != minLevel) CPVS_CUDA(cudaMemsetAsync(dTable, 0xFF, m.tableSize * sizeof(u64), st));
-			s = nextScan(a.n);
+		if (!leafLevel && tablesClearing) {
+			CPVS_CUDA(cudaStreamWaitEvent(mergeStream, ctx->evClear, 0));
+			tablesClearing = false;
 		}
-		ctx->launches += launchMergeLevel(m, s, leafLevel ? phases.ev[CPVS_PHASE_LEAF_RESOLVE] : nullptr, st);
-		if (leafLevel) CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_INNER_MERGE], st));
+		ctx->launches += launchInsertLevel(m, mergeStream);
+		if (leafLevel) {
+			CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAF_RESOLVE], mergeStream));
+			CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_INNER_MERGE], mergeStream));
+		}
+		if (a.n > 1) {
+			cudaStream_t rs = (l & 1) ? ctx->aux3 : ctx->aux2;
+			CPVS_CUDA(cudaEventRecord(ctx->evFork, mergeStream));
+			CPVS_CUDA(cudaStreamWaitEvent(rs, ctx->evFork, 0));
+			if (leafLevel) CPVS_CUDA(cudaEventRecord(ctx->evRankStart, rs));
+			ctx->launches += launchRankLevel(m, nextScan(a.n), rs);
+			if (leafLevel) CPVS_CUDA(cudaEventRecord(ctx->evRankStop, rs));
+			ranksPending = true;
+		}
 	}
 	{
 		SmallMergeArgs sm;
@@ -621,11 +679,20 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 			m.uid = lv[l].uid;
 			m.firstList = lv[l].firstList;
 			m.wordOffset = lv[l].wordOffset;
+			m.slotOffset = lv[l].slotOffset;
 			m.uniqueCount = dUnique + l;
 			m.wordCount = dWords + l;
 		}
-		ctx->launches += launchMergeSmallLevels(sm, st);
+		ctx->launches += launchMergeSmallLevels(sm, mergeStream);
 	}
+	if (ranksPending || tablesClearing) {  // join: the level sizes feed the bases
+		CPVS_CUDA(cudaEventRecord(ctx->evJoin, ctx->aux2));
+		CPVS_CUDA(cudaStreamWaitEvent(mergeStream, ctx->evJoin, 0));
+		CPVS_CUDA(cudaEventRecord(ctx->evJoin3, ctx->aux3));
+		CPVS_CUDA(cudaStreamWaitEvent(mergeStream, ctx->evJoin3, 0));
+	}
+	CPVS_CUDA(cudaEventRecord(ctx->evJoin, mergeStream));
+	CPVS_CUDA(cudaStreamWaitEvent(st, ctx->evJoin, 0));
 	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_BASES], st));
 
 	// 5. level bases and the total size (src/CompressedShadow.cpp:326-392)
@@ -682,7 +749,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		em.masks = a.masks;
 		em.firstChild = a.firstChild;
 		em.childUid = l > minLevel ? lv[l - 1].uid : nullptr;
-		em.childWordOffset = l > minLevel ? lv[l - 1].wordOffset : nullptr;
+		em.childSlotOffset = l > minLevel ? lv[l - 1].slotOffset : nullptr;
 		em.childLevelBase = dBases + (l > minLevel ? l - 1 : l);
 		em.dag = s->dag;
 		if (isLeaf) {
@@ -711,6 +778,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	for (int i = 0; i < CPVS_PHASE_EMIT_INNER && e == cudaSuccess; ++i) e = cudaEventElapsedTime(&phaseMs[i], phases.ev[i], phases.ev[i + 1]);
 	if (e == cudaSuccess) e = cudaEventElapsedTime(&phaseMs[CPVS_PHASE_EMIT_INNER], phases.ev[CPVS_PHASE_EMIT_INNER], phases.ev[CPVS_NUM_PHASES]);
 	if (e == cudaSuccess && leafEmit) e = cudaEventElapsedTime(&phaseMs[CPVS_PHASE_EMIT_LEAVES], ctx->evAuxStart, phases.ev[CPVS_PHASE_EMIT_LEAVES]);
+	if (e == cudaSuccess && haveLeaves) e = cudaEventElapsedTime(&phaseMs[CPVS_PHASE_LEAF_RESOLVE], ctx->evRankStart, ctx->evRankStop);
 	if (e != cudaSuccess) {
 		cudaFreeAsync(s->dag, st);
 		delete s;

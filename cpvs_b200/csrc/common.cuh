@@ -10,9 +10,6 @@ typedef uint64_t u64;
 typedef uint16_t u16;
 
 constexpr int kMaxLevels = 32;
-// Per-node unique ids are stored with bit 31 set once final (merge.cu); consumers strip it.
-constexpr uint32_t kResolvedFlag = 0x80000000u;
-constexpr uint32_t kUidMask = 0x7FFFFFFFu;
 constexpr int kScanThreads = 256;  // threads per scan tile
 constexpr int kScanItems = 4;      // items per thread
 constexpr int kScanTile = kScanThreads * kScanItems;

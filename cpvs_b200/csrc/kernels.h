@@ -75,9 +75,10 @@ struct MergeLevelArgs {
 	const u64* sketchBits; // leaf level: set bits of the distinct-count sketch (device)
 	u64* tableMaskDev;     // leaf level: (chosen capacity - 1), written by the sizing kernel (device)
 	u32* errorFlag;        // device: set if a probe sequence wraps the whole table
-	u32* uid;              // out: unique id (first-occurrence rank) per node
-	u32* firstList;        // out: node index of the r-th unique node
-	u32* wordOffset;       // out: compressed word offset (inside the level) of the r-th unique node
+	u32* uid;              // out (insert): group id per node = its group's table slot
+	u32* firstList;        // out (rank): node index of the r-th unique node
+	u32* wordOffset;       // out (rank): compressed word offset (inside the level) of the r-th unique node
+	u32* slotOffset;       // out (rank): per table slot, the word offset of the group's node
 	u64* uniqueCount;      // out: number of unique nodes
 	u64* wordCount;        // out: compressed words of the level
 };
@@ -90,6 +91,7 @@ struct SmallMergeLevel {
 	u32* uid;
 	u32* firstList;
 	u32* wordOffset;
+	u32* slotOffset;  // 2 * kSmallMaxNodes entries
 	u64* uniqueCount;
 	u64* wordCount;
 };
@@ -103,8 +105,10 @@ int launchMergeSmallLevels(const SmallMergeArgs& a, cudaStream_t stream);
 
 // Leaf level only: picks the table capacity from the sketch's set-bit count and clears that many slots.
 int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* tableMaskDev, cudaStream_t stream);
-// afterInsert (optional) is recorded between the insert kernel and the rank scan.
-int launchMergeLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaEvent_t afterInsert, cudaStream_t stream);
+// Insert assigns group ids (all the parent level needs); rank orders the unique nodes and may run
+// concurrently with the next level's insert as long as this level's table is left alone.
+int launchInsertLevel(const MergeLevelArgs& a, cudaStream_t stream);
+int launchRankLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaStream_t stream);
 
 // ---- emit.cu: compress (reference src/CompressedShadow.cpp:326-392) ----
 struct EmitLevelArgs {
@@ -118,8 +122,8 @@ struct EmitLevelArgs {
 	const u32* leafCodes;
 	const u16* masks;
 	const u32* firstChild;
-	const u32* childUid;        // unique ids of the level below
-	const u32* childWordOffset; // word offsets of the level below's unique nodes
+	const u32* childUid;        // group ids (table slots) of the level below
+	const u32* childSlotOffset; // word offset per slot of the level below
 	const u64* childLevelBase;  // device: word offset of the level below in the DAG
 	u32* dag;
 };

@@ -12,10 +12,12 @@
 //                slot is (32-bit fingerprint << 32 | smallest node index seen so far); a node joins a
 //                slot only after comparing its full tuple against a member of the group, so grouping
 //                is exact, never hash-trusting. atomicMin keeps the first occurrence.
-//   2. resolve:  representative = slot's final index; nodes that are their own representative are
-//                the unique nodes. One look-back scan ranks them (first-occurrence order = the
-//                reference's layout) and prefix-sums their compressed sizes.
-//                Every other node then takes the rank of its representative (the parents' remap table).
+//                The slot index is the node's group id: equal nodes share it, which is all the parent
+//                level needs to compare tuples, so the next level's insert can start right away.
+//   2. rank:     (off the critical path, on a side stream) representative = slot's final index; nodes
+//                that are their own representative are the unique nodes. One look-back scan ranks them
+//                (first-occurrence order = the reference's layout), prefix-sums their compressed sizes
+//                and leaves each group's word offset next to its slot for the parents' pointers.
 #include "kernels.h"
 
 namespace cpvs {
@@ -72,10 +74,13 @@ __global__ void __launch_bounds__(256) insertLeavesKernel(const u32* __restrict_
 	const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= n) return;
 	const u64 tableMask = *tableMaskDev;
+	// own code and hash are fetched up front so that their latency overlaps the first table probe
 	const uint4* mine = reinterpret_cast<const uint4*>(codes + j * 8);
-	slotOf[j] = findGroupSlot(table, tableMask, hashes[j], (u32)j, errorFlag, [&](u32 other) {
+	const uint4 a0 = __ldcs(mine), a1 = __ldcs(mine + 1);
+	const u64 hash = __ldcs(hashes + j);
+	slotOf[j] = findGroupSlot(table, tableMask, hash, (u32)j, errorFlag, [&](u32 other) {
 		const uint4* theirs = reinterpret_cast<const uint4*>(codes + (u64)other * 8);
-		const uint4 a0 = mine[0], a1 = mine[1], b0 = theirs[0], b1 = theirs[1];
+		const uint4 b0 = theirs[0], b1 = theirs[1];
 		return a0.x == b0.x && a0.y == b0.y && a0.z == b0.z && a0.w == b0.w && a1.x == b1.x && a1.y == b1.y && a1.z == b1.z && a1.w == b1.w;
 	});
 }
@@ -91,7 +96,7 @@ __device__ __forceinline__ u32 insertInnerNode(u32 j, const u16* __restrict__ ma
 	for (u32 c = 0; c < 8; ++c) {
 		uid[c] = 0;
 		if (c < k) {
-			uid[c] = kids[c] & kUidMask;
+			uid[c] = kids[c];
 			h = mix64(h ^ ((u64)uid[c] + 0x9E3779B97F4A7C15ull * (c + 1)));
 		}
 	}
@@ -101,7 +106,7 @@ __device__ __forceinline__ u32 insertInnerNode(u32 j, const u16* __restrict__ ma
 		bool same = true;
 #pragma unroll
 		for (u32 c = 0; c < 8; ++c)
-			if (c < k) same = same && (theirs[c] & kUidMask) == uid[c];
+			if (c < k) same = same && theirs[c] == uid[c];
 		return same;
 	});
 }
@@ -113,27 +118,23 @@ __global__ void __launch_bounds__(256) insertInnerKernel(const u16* __restrict__
 	slotOf[j] = insertInnerNode((u32)j, masks, firstChild, childUid, table, tableMask, errorFlag);
 }
 
-// slotOf[j] (in) -> uid[j] (out) = unique id | kResolvedFlag. Readers strip the flag (kUidMask).
-//
-// First occurrences get their rank from the look-back scan and publish it (value and flag share one word). Every
-// other node needs the rank of its representative, which always sits at a smaller index, i.e. in this
-// tile or in a tile that started earlier (tiles are handed out in start order): it polls that entry
-// until the flag shows up. No tile ever waits on a later one, so this cannot deadlock, and the extra
-// "rank of my representative" pass over the level disappears.
-__global__ void __launch_bounds__(kScanThreads, 8) resolveKernel(const u64* __restrict__ table, const u16* __restrict__ masks, int leaf, u64 n,
-		u32* __restrict__ uid, u32* __restrict__ firstList, u32* __restrict__ wordOffset, u64* __restrict__ uniqueCount,
-		u64* __restrict__ wordCount, ScanLaunch scan, u32 numTiles) {
+// gid[j] = slot of node j's group. Ranks the first occurrences (slot's final index == j) in order,
+// prefix-sums their compressed sizes, and records firstList[rank], wordOffset[rank] and, per group,
+// slotOffset[slot] = word offset of the group's node inside the level.
+__global__ void __launch_bounds__(kScanThreads, 8) rankKernel(const u64* __restrict__ table, const u16* __restrict__ masks, int leaf, u64 n,
+		const u32* __restrict__ gid, u32* __restrict__ firstList, u32* __restrict__ wordOffset, u32* __restrict__ slotOffset,
+		u64* __restrict__ uniqueCount, u64* __restrict__ wordCount, ScanLaunch scan, u32 numTiles) {
 	const u32 tile = scanAcquireTile(scan);
 	const u64 base = (u64)tile * kScanTile + (u64)threadIdx.x * kScanItems;
-	u32 rep[kScanItems], words[kScanItems];
+	u32 slot[kScanItems], words[kScanItems];
 	u64 cnt = 0, wsum = 0;
 #pragma unroll
 	for (int i = 0; i < kScanItems; ++i) {
-		rep[i] = 0xFFFFFFFFu;
+		slot[i] = 0;
 		words[i] = 0;
 		if (base + i < n) {
-			rep[i] = (u32)table[uid[base + i]];
-			if (rep[i] == (u32)(base + i)) {
+			slot[i] = gid[base + i];
+			if ((u32)table[slot[i]] == (u32)(base + i)) {
 				const u32 k = __popc(masks[base + i] & 0xAAAAu);
 				words[i] = 1 + (leaf ? 2 * k : k);
 				cnt += 1;
@@ -155,26 +156,15 @@ __global__ void __launch_bounds__(kScanThreads, 8) resolveKernel(const u64* __re
 		if (base + i < n && words[i]) {
 			firstList[rank] = (u32)(base + i);
 			wordOffset[rank] = (u32)woff;
-			stRelaxed32(uid + base + i, (u32)rank | kResolvedFlag);
+			slotOffset[slot[i]] = (u32)woff;
 			++rank;
 			woff += words[i];
 		}
 	}
-	__syncthreads();
-#pragma unroll
-	for (int i = 0; i < kScanItems; ++i) {
-		if (base + i < n && !words[i]) {
-			u32 v;
-			do {
-				v = ldRelaxed32(uid + rep[i]);
-			} while (!(v & kResolvedFlag));
-			uid[base + i] = v;
-		}
-	}
 }
 
-// The small top levels, bottom-up, by one CTA: clear, insert, rank, resolve with block barriers in
-// between. Same tuples, same first-occurrence rule, same outputs as the per-level kernels.
+// The small top levels, bottom-up, by one CTA: clear, insert, rank with block barriers in between.
+// Same tuples, same first-occurrence rule, same outputs as the per-level kernels.
 __global__ void __launch_bounds__(kSmallThreads) mergeSmallLevelsKernel(SmallMergeArgs a) {
 	__shared__ u32 sWarpC[kSmallThreads / 32], sWarpW[kSmallThreads / 32];
 	constexpr u64 kSlots = 2 * kSmallMaxNodes;
@@ -183,7 +173,8 @@ __global__ void __launch_bounds__(kSmallThreads) mergeSmallLevelsKernel(SmallMer
 		const SmallMergeLevel& L = a.lv[s];
 		if (L.n == 1) {
 			if (threadIdx.x == 0) {
-				L.uid[0] = kResolvedFlag;
+				L.uid[0] = 0;
+				L.slotOffset[0] = 0;
 				L.firstList[0] = 0;
 				L.wordOffset[0] = 0;
 				*L.uniqueCount = 1;
@@ -199,10 +190,10 @@ __global__ void __launch_bounds__(kSmallThreads) mergeSmallLevelsKernel(SmallMer
 		u32 carryC = 0, carryW = 0;
 		for (u32 base = 0; base < L.n; base += kSmallThreads) {
 			const u32 j = base + threadIdx.x;
-			u32 rep = 0xFFFFFFFFu, words = 0;
+			u32 slot = 0, words = 0;
 			if (j < L.n) {
-				rep = (u32)ldRelaxed64(a.table + L.uid[j]);
-				if (rep == j) words = 1 + __popc(L.masks[j] & 0xAAAAu);
+				slot = L.uid[j];
+				if ((u32)ldRelaxed64(a.table + slot) == j) words = 1 + __popc(L.masks[j] & 0xAAAAu);
 			}
 			u32 inclC = words ? 1u : 0u, inclW = words;
 #pragma unroll
@@ -230,23 +221,14 @@ __global__ void __launch_bounds__(kSmallThreads) mergeSmallLevelsKernel(SmallMer
 				totW += v;
 			}
 			__syncthreads();
-			if (j < L.n) {
-				if (words) {
-					const u32 rank = carryC + beforeC + inclC - 1;
-					L.firstList[rank] = j;
-					L.wordOffset[rank] = carryW + beforeW + inclW - words;
-					L.uid[j] = rank | kResolvedFlag;
-				} else {
-					L.uid[j] = rep;  // resolved below, once every first occurrence of the level has its rank
-				}
+			if (j < L.n && words) {
+				const u32 rank = carryC + beforeC + inclC - 1, woff = carryW + beforeW + inclW - words;
+				L.firstList[rank] = j;
+				L.wordOffset[rank] = woff;
+				L.slotOffset[slot] = woff;
 			}
 			carryC += totC;
 			carryW += totW;
-		}
-		__syncthreads();
-		for (u32 j = threadIdx.x; j < L.n; j += kSmallThreads) {
-			const u32 v = L.uid[j];
-			if (!(v & kResolvedFlag)) L.uid[j] = L.uid[v];
 		}
 		if (threadIdx.x == 0) {
 			*L.uniqueCount = carryC;
@@ -257,10 +239,11 @@ __global__ void __launch_bounds__(kSmallThreads) mergeSmallLevelsKernel(SmallMer
 }
 
 // A level with a single node (the root, which the reference never merges).
-__global__ void singleNodeKernel(const u16* __restrict__ masks, int leaf, u32* uid, u32* firstList, u32* wordOffset, u64* uniqueCount,
-		u64* wordCount) {
+__global__ void singleNodeKernel(const u16* __restrict__ masks, int leaf, u32* gid, u32* firstList, u32* wordOffset, u32* slotOffset,
+		u64* uniqueCount, u64* wordCount) {
 	const u32 k = __popc(masks[0] & 0xAAAAu);
-	uid[0] = kResolvedFlag;
+	gid[0] = 0;
+	slotOffset[0] = 0;
 	firstList[0] = 0;
 	wordOffset[0] = 0;
 	*uniqueCount = 1;
@@ -280,10 +263,9 @@ int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* table
 	return 1;
 }
 
-int launchMergeLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaEvent_t afterInsert, cudaStream_t stream) {
+int launchInsertLevel(const MergeLevelArgs& a, cudaStream_t stream) {
 	if (a.n == 1) {
-		singleNodeKernel<<<1, 1, 0, stream>>>(a.masks, a.leaf, a.uid, a.firstList, a.wordOffset, a.uniqueCount, a.wordCount);
-		if (afterInsert) cudaEventRecord(afterInsert, stream);
+		singleNodeKernel<<<1, 1, 0, stream>>>(a.masks, a.leaf, a.uid, a.firstList, a.wordOffset, a.slotOffset, a.uniqueCount, a.wordCount);
 		return 1;
 	}
 	const unsigned blocks = (unsigned)((a.n + 255) / 256);
@@ -291,11 +273,15 @@ int launchMergeLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaEvent_t after
 		insertLeavesKernel<<<blocks, 256, 0, stream>>>(a.leafCodes, a.leafHash, a.n, a.table, a.tableMaskDev, a.uid, a.errorFlag);
 	else
 		insertInnerKernel<<<blocks, 256, 0, stream>>>(a.masks, a.firstChild, a.childUid, a.n, a.table, a.tableSize - 1, a.uid, a.errorFlag);
-	if (afterInsert) cudaEventRecord(afterInsert, stream);
+	return 1;
+}
+
+int launchRankLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaStream_t stream) {
+	if (a.n == 1) return 0;  // done by launchInsertLevel
 	const u32 tiles = (u32)((a.n + kScanTile - 1) / kScanTile);
-	resolveKernel<<<tiles, kScanThreads, 0, stream>>>(a.table, a.masks, a.leaf, a.n, a.uid, a.firstList, a.wordOffset, a.uniqueCount,
+	rankKernel<<<tiles, kScanThreads, 0, stream>>>(a.table, a.masks, a.leaf, a.n, a.uid, a.firstList, a.wordOffset, a.slotOffset, a.uniqueCount,
 			a.wordCount, scan, tiles);
-	return 2;
+	return 1;
 }
 
 }  // namespace cpvs

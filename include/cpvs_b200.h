@@ -58,8 +58,8 @@ extern "C" {
 #define CPVS_PHASE_LEAVES 2       /* leaf build (1 kernel) */
 #define CPVS_PHASE_LEAF_TABLE 3   /* leaf level: distinct-count sketch read-out, table sizing + clear */
 #define CPVS_PHASE_LEAF_INSERT 4  /* leaf level: hash-table insert (1 kernel) */
-#define CPVS_PHASE_LEAF_RESOLVE 5 /* leaf level: rank scan + unique ids */
-#define CPVS_PHASE_INNER_MERGE 6  /* all inner levels: clear + insert + rank scan + unique ids */
+#define CPVS_PHASE_LEAF_RESOLVE 5 /* leaf level: rank scan (1 kernel) on a side stream, concurrent with phase 6 */
+#define CPVS_PHASE_INNER_MERGE 6  /* inner levels: inserts on the main stream (rank scans beside them), join */
 #define CPVS_PHASE_BASES 7        /* level bases + host read-back of sizes */
 #define CPVS_PHASE_EMIT_INNER 8   /* whole emission: inner levels on the main stream, leaves on a side stream */
 #define CPVS_PHASE_EMIT_LEAVES 9  /* compressed leaves (1 kernel); runs concurrently, inside phase 8 */
