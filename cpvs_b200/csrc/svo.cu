@@ -213,7 +213,7 @@ __device__ __forceinline__ u32 litCountBits(float depth, float heightF, float zc
 //     childmask from the block's (min,max) pyramid texel, marks the distinct-count bitmap and stores.
 constexpr int kLeavesPerCta = 256;
 
-__global__ void __launch_bounds__(256, 4) buildLeavesKernel(const float* __restrict__ depth, u32 n, float heightF, const float2* __restrict__ level3,
+__global__ void __launch_bounds__(256, 8) buildLeavesKernel(const float* __restrict__ depth, u32 n, float heightF, const float2* __restrict__ level3,
 		const u64* __restrict__ coords, u64 numLeaves, u32* __restrict__ codes, u64* __restrict__ hashes, u16* __restrict__ masks,
 		u32* __restrict__ bitmap, u32 bitmapWordMask) {
 	__shared__ __align__(16) u32 sCode[kLeavesPerCta][8];
