@@ -104,6 +104,10 @@ struct cpvs_shadow {
 	cpvs_ctx* ctx;
 	u32* dag;
 	cpvs_shadow_info info;
+	// lookup shortcut over the top levels, built on the first lookup (see LookupDag::skip)
+	std::mutex skipLock;
+	u32* skip;
+	u32 skipLevels;
 };
 
 struct ContainerCell {
@@ -122,6 +126,8 @@ struct cpvs_container {
 	std::vector<ContainerCell> cells;
 	u32* dag = nullptr;
 	u32* grid = nullptr;
+	u32* skip = nullptr;  // lookup shortcut over the top levels of every cell (see LookupDag::skip)
+	u32 skipLevels = 0;
 	u64 dagWords = 0;
 	u32 dagLevels = 0, gridLevels = 0;
 	int leafmasks = 0;
@@ -710,9 +716,12 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	const u64 totalWords = hScalars[160];
 	if (totalWords > (1ull << 32)) return fail(CPVS_EOVERFLOW, "DAG needs %llu words; offsets are 32-bit", (unsigned long long)totalWords);
 
-	cpvs_shadow* s = new (std::nothrow) cpvs_shadow;
+	cpvs_shadow* s = new (std::nothrow) cpvs_shadow();
 	if (!s) return fail(CPVS_ENOMEM, "cpvs_shadow_create: host allocation");
-	std::memset(s, 0, sizeof(*s));
+	std::memset(&s->info, 0, sizeof(s->info));
+	s->dag = nullptr;
+	s->skip = nullptr;
+	s->skipLevels = 0;
 	s->ctx = ctx;
 	cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&s->dag), totalWords * sizeof(u32), st);
 	if (e != cudaSuccess) {
@@ -813,6 +822,7 @@ int cpvs_shadow_destroy(cpvs_shadow* s) {
 	if (!s) return CPVS_OK;
 	cudaSetDevice(s->ctx->device);
 	if (s->dag) cudaFreeAsync(s->dag, s->ctx->stream);
+	if (s->skip) cudaFreeAsync(s->skip, s->ctx->stream);
 	delete s;
 	return CPVS_OK;
 }
@@ -870,8 +880,23 @@ int cpvs_shadow_lookup_ndc(const cpvs_shadow* s, const float* ndc, int64_t count
 	if (tryLeafmasks && !s->info.leafmasks)
 		return fail(CPVS_EINVAL, "cpvs_shadow_lookup_ndc: tryLeafmasks on a DAG built without leafmasks (SURVEY.md T2)");
 	CPVS_CUDA(cudaSetDevice(s->ctx->device));
-	LookupDag d{s->dag, nullptr, s->info.num_levels, 0, tryLeafmasks ? 1 : 0};
 	cudaStream_t st = s->ctx->stream;
+	LookupDag d{s->dag, nullptr, s->info.num_levels, 0, tryLeafmasks ? 1 : 0, nullptr, 0};
+	if ((tryLeafmasks != 0) == (s->info.leafmasks != 0)) {  // shortcut grid, built once
+		cpvs_shadow* ms = const_cast<cpvs_shadow*>(s);
+		std::lock_guard<std::mutex> guard(ms->skipLock);
+		if (!ms->skip) {
+			const u32 g = skipLevelsFor(d.dagLevels, d.leafmasks, 0);
+			if (g) {
+				CPVS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ms->skip), (sizeof(u32) << (3 * g)), st));
+				d.skipLevels = g;
+				s->ctx->launches += launchBuildSkipGrid(d, ms->skip, st);
+				ms->skipLevels = g;
+			}
+		}
+		d.skip = ms->skip;
+		d.skipLevels = ms->skipLevels;
+	}
 	return runLookup(s->ctx, ndc, (u64)count * 3, mem, out, (u64)count,
 			[&](const float* in, unsigned char* o) { return launchLookupNdc(d, in, count, o, st); });
 }
@@ -895,7 +920,9 @@ int cpvs_container_create(cpvs_ctx* ctx, uint32_t length, cpvs_container** out) 
 static void releaseContainerBuffers(cpvs_container* c) {
 	if (c->dag) cudaFreeAsync(c->dag, c->ctx->stream);
 	if (c->grid) cudaFreeAsync(c->grid, c->ctx->stream);
-	c->dag = c->grid = nullptr;
+	if (c->skip) cudaFreeAsync(c->skip, c->ctx->stream);
+	c->dag = c->grid = c->skip = nullptr;
+	c->skipLevels = 0;
 	c->finalized = false;
 }
 
@@ -968,6 +995,13 @@ int cpvs_container_finalize(cpvs_container* c) {
 	c->gridLevels = 0;                     // log8(#cells) (:42-43), exact here
 	while ((1u << c->gridLevels) < c->length) ++c->gridLevels;
 	c->leafmasks = c->cells[0].leafmasks;
+	c->skipLevels = skipLevelsFor(c->dagLevels, c->leafmasks, c->gridLevels);
+	if (c->skipLevels) {
+		CPVS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&c->skip), sizeof(u32) << (3 * (c->gridLevels + c->skipLevels)), st));
+		LookupDag d{c->dag, c->grid, c->dagLevels, c->gridLevels, c->leafmasks, nullptr, c->skipLevels};
+		c->ctx->launches += launchBuildSkipGrid(d, c->skip, st);
+		CPVS_CUDA(cudaGetLastError());
+	}
 	c->finalized = true;
 	return CPVS_OK;
 }
@@ -995,7 +1029,7 @@ int cpvs_container_lookup_ndc(const cpvs_container* c, const float* ndc, int64_t
 	if (count < 0 || (count > 0 && (!ndc || !out))) return fail(CPVS_EINVAL, "cpvs_container_lookup_ndc: bad arguments");
 	if (count == 0) return CPVS_OK;
 	CPVS_CUDA(cudaSetDevice(c->ctx->device));
-	LookupDag d{c->dag, c->grid, c->dagLevels, c->gridLevels, c->leafmasks};
+	LookupDag d{c->dag, c->grid, c->dagLevels, c->gridLevels, c->leafmasks, c->skip, c->skipLevels};
 	cudaStream_t st = c->ctx->stream;
 	return runLookup(c->ctx, ndc, (u64)count * 3, mem, out, (u64)count,
 			[&](const float* in, unsigned char* o) { return launchLookupNdc(d, in, count, o, st); });
@@ -1008,10 +1042,10 @@ int cpvs_container_evaluate(const cpvs_container* c, const float* positions, uin
 	const long long count = (long long)width * height;
 	if (count == 0) return CPVS_OK;
 	CPVS_CUDA(cudaSetDevice(c->ctx->device));
-	LookupDag d{c->dag, c->grid, c->dagLevels, c->gridLevels, c->leafmasks};
+	LookupDag d{c->dag, c->grid, c->dagLevels, c->gridLevels, c->leafmasks, c->skip, c->skipLevels};
 	cudaStream_t st = c->ctx->stream;
 	return runLookup(c->ctx, positions, (u64)count * 4, mem, visibilities, (u64)count,
-			[&](const float* in, unsigned char* o) { return launchEvaluate(d, in, count, m, o, st); });
+			[&](const float* in, unsigned char* o) { return launchEvaluate(d, in, width, height, m, o, st); });
 }
 
 int cpvs_container_set_filter_size(cpvs_container* c, uint32_t size) {

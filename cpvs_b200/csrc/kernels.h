@@ -146,9 +146,26 @@ struct LookupDag {
 	u32 dagLevels;
 	u32 gridLevels;
 	int leafmasks;
+	// Optional shortcut over the top `skipLevels` levels of every DAG: one entry per cell of the
+	// (2^(gridLevels+skipLevels))^3 grid over the whole volume, holding what the descent would have reached
+	// there -- kSkipShadow / kSkipVisible, or the word offset (relative to the cell's DAG) of the node to
+	// continue from. Private to the lookup; the DAG words themselves are untouched.
+	const u32* skip;
+	u32 skipLevels;
 };
+constexpr u32 kSkipShadow = 0xFFFFFFFFu, kSkipVisible = 0xFFFFFFFEu;
+constexpr u32 kMaxSkipLevels = 6;
+// Number of levels the shortcut can cover for a DAG of dagLevels (0: none).
+inline u32 skipLevelsFor(u32 dagLevels, int leafmasks, u32 gridLevels) {
+	const int inner = (int)dagLevels - 1 - (leafmasks ? 3 : 0);  // inner levels dagLevels-2 .. (3 | 0)
+	int g = inner - 1 < (int)kMaxSkipLevels ? inner - 1 : (int)kMaxSkipLevels;
+	while (g > 0 && 3 * (g + (int)gridLevels) > 21) --g;  // at most 2^21 entries (8 MiB)
+	return g > 0 ? (u32)g : 0u;
+}
+// Fills d.skip (writable here) for all cells; d.skipLevels must be set.
+int launchBuildSkipGrid(const LookupDag& d, u32* skip, cudaStream_t stream);
 int launchLookupNdc(const LookupDag& d, const float* ndc, long long count, unsigned char* out, cudaStream_t stream);
-int launchEvaluate(const LookupDag& d, const float* positions, long long count, const float* matrix, unsigned char* out,
+int launchEvaluate(const LookupDag& d, const float* positions, unsigned width, unsigned height, const float* matrix, unsigned char* out,
 		cudaStream_t stream);
 
 }  // namespace cpvs

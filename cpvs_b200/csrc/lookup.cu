@@ -27,10 +27,10 @@ __device__ __forceinline__ int pathCoord(float ndc, int resolution) {
 // getChildOffset (src/CompressedShadow.cpp:394-402): rank among PARTIAL children; childBits = 2*index.
 __device__ __forceinline__ u32 childRank(u32 mask, u32 childBits) { return __popc(mask & (0xAAAAu >> (16u - childBits))); }
 
-__device__ __forceinline__ u32 descend(const u32* __restrict__ dag, u32 dagLevels, bool leaf, int px, int py, int pz) {
-	u32 offset = 0;
+// Descends from the node at `offset`, whose children are picked by path bit `startLevel`.
+__device__ __forceinline__ u32 descend(const u32* __restrict__ dag, u32 offset, int startLevel, bool leaf, int px, int py, int pz) {
 	const int minLevel = leaf ? 3 : 0;
-	for (int level = (int)dagLevels - 2; level >= minLevel; --level) {
+	for (int level = startLevel; level >= minLevel; --level) {
 		const u32 idx = ((px >> level) & 1) | (((py >> level) & 1) << 1) | (((pz >> level) & 1) << 2);
 		const u32 mask = __ldg(dag + offset);
 		const u32 vis = (mask >> (idx * 2)) & 3u;
@@ -58,7 +58,47 @@ __device__ __forceinline__ u32 lookupOne(const LookupDag& d, float x, float y, f
 		if (cell == kCellVisible) return 1u;
 		dag += cell;
 	}
-	return descend(dag, d.dagLevels, d.leafmasks != 0, px, py, pz);
+	int startLevel = (int)d.dagLevels - 2;
+	u32 offset = 0;
+	if (d.skip) {  // the first skipLevels steps of the descent, precomputed per cell
+		const u32 shift = d.dagLevels - 1 - d.skipLevels, res = 1u << (d.gridLevels + d.skipLevels);
+		const u32 entry = __ldg(d.skip + ((u32)(pz >> shift) * res + (u32)(py >> shift)) * res + (u32)(px >> shift));
+		if (entry == kSkipShadow) return 0u;
+		if (entry == kSkipVisible) return 1u;
+		offset = entry;
+		startLevel -= (int)d.skipLevels;
+	}
+	return descend(dag, offset, startLevel, d.leafmasks != 0, px, py, pz);
+}
+
+// One thread per shortcut cell: runs the first skipLevels steps of the descent for the cell's path prefix.
+__global__ void __launch_bounds__(256) buildSkipGridKernel(LookupDag d, u32* __restrict__ skip) {
+	const u32 bits = d.gridLevels + d.skipLevels, res = 1u << bits;
+	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= res * res * res) return;
+	const u32 cx = i & (res - 1), cy = (i >> bits) & (res - 1), cz = i >> (2 * bits);
+	const u32* dag = d.dag;
+	if (d.grid) {
+		const u32 gres = 1u << d.gridLevels;
+		const u32 cell = d.grid[((cz >> d.skipLevels) * gres + (cy >> d.skipLevels)) * gres + (cx >> d.skipLevels)];
+		if (cell == kCellShadowed || cell == kCellVisible) {
+			skip[i] = cell == kCellShadowed ? kSkipShadow : kSkipVisible;
+			return;
+		}
+		dag += cell;
+	}
+	u32 offset = 0;
+	for (int step = (int)d.skipLevels - 1; step >= 0; --step) {  // path bit dagLevels-2-k of the voxel = bit `step` of the cell
+		const u32 idx = ((cx >> step) & 1u) | (((cy >> step) & 1u) << 1) | (((cz >> step) & 1u) << 2);
+		const u32 mask = dag[offset];
+		const u32 vis = (mask >> (idx * 2)) & 3u;
+		if (vis != 2u) {
+			skip[i] = vis ? kSkipVisible : kSkipShadow;
+			return;
+		}
+		offset = dag[offset + 1 + childRank(mask, idx * 2)];
+	}
+	skip[i] = offset;
 }
 
 __global__ void __launch_bounds__(256) lookupNdcKernel(LookupDag d, const float* __restrict__ ndc, long long count, unsigned char* __restrict__ out) {
@@ -72,10 +112,13 @@ struct Mat4 {
 };
 
 // traverse.cs main() (:135-149) with glm's evaluation order for mat4*vec4 and the divide by w.
-__global__ void __launch_bounds__(256) evaluateKernel(LookupDag d, const float4* __restrict__ pos, long long count, Mat4 mat,
+// 8x4-pixel warps (blockDim 8x32): neighbouring pixels share most of their path through the DAG, so a
+// compact footprint per warp means fewer distinct nodes per load instruction than a 32x1 strip.
+__global__ void __launch_bounds__(256) evaluateKernel(LookupDag d, const float4* __restrict__ pos, u32 width, u32 height, Mat4 mat,
 		unsigned char* __restrict__ out) {
-	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= count) return;
+	const u32 x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x >= width || y >= height) return;
+	const size_t i = (size_t)y * width + x;
 	const float4 p = pos[i];
 	float v[4];
 #pragma unroll
@@ -88,18 +131,26 @@ __global__ void __launch_bounds__(256) evaluateKernel(LookupDag d, const float4*
 
 }  // namespace
 
+int launchBuildSkipGrid(const LookupDag& d, u32* skip, cudaStream_t stream) {
+	const u32 bits = 3 * (d.gridLevels + d.skipLevels);
+	const u32 cells = 1u << bits;
+	buildSkipGridKernel<<<(cells + 255) / 256, 256, 0, stream>>>(d, skip);
+	return 1;
+}
+
 int launchLookupNdc(const LookupDag& d, const float* ndc, long long count, unsigned char* out, cudaStream_t stream) {
 	if (count <= 0) return 0;
 	lookupNdcKernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(d, ndc, count, out);
 	return 1;
 }
 
-int launchEvaluate(const LookupDag& d, const float* positions, long long count, const float* matrix, unsigned char* out,
+int launchEvaluate(const LookupDag& d, const float* positions, unsigned width, unsigned height, const float* matrix, unsigned char* out,
 		cudaStream_t stream) {
-	if (count <= 0) return 0;
+	if (!width || !height) return 0;
 	Mat4 m;
 	for (int i = 0; i < 16; ++i) m.m[i] = matrix[i];
-	evaluateKernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(d, reinterpret_cast<const float4*>(positions), count, m, out);
+	const dim3 block(8, 32), grid((width + 7) / 8, (height + 31) / 32);
+	evaluateKernel<<<grid, block, 0, stream>>>(d, reinterpret_cast<const float4*>(positions), width, height, m, out);
 	return 1;
 }
 
