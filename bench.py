@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="do not run the nvidia-smi sampler (debugging)")
     ap.add_argument("--ref-sample", type=int, default=1024, help="side of one reference sample window")
+    ap.add_argument("--z-slices", type=int, default=1,
+                    help="z-slice DAGs built per depth map (createShadowTiles); 4 = the cubic 4x4x4 container of BASELINE configs[2]")
     return ap.parse_args()
 
 
@@ -165,10 +167,11 @@ def workload_config(args, n_gpus):
         return {"workload": "configs[1]: %dx%d synthetic %s depth map, leafmasks on, single DAG (MinMaxHierarchy + CompressedShadow::create) "
                             "+ %d random NDC lookups" % (args.size, args.size, args.kind, args.lookups),
                 "depth_map": "%dx%d f32 (%.0f MiB) > L2, regenerated state per step; no explicit L2 flush needed" % (args.size, args.size, args.size * args.size * 4 / 2**20),
-                "tiles_per_rank": 1, "z_slices": 1}
-    return {"workload": "configs[2]: 64K^2 virtual %s map as 4x4x4 CompressedShadowContainer grid; every rank builds one %dx%d xy-tile "
-                        "(1 pyramid + 4 z-slice DAGs) per step, host-side gather of sizes only" % (args.kind, args.size, args.size),
-            "depth_map": "%dx%d f32 per rank > L2" % (args.size, args.size), "tiles_per_rank": 1, "z_slices": 4}
+                "tiles_per_rank": 1, "z_slices": args.z_slices}
+    return {"workload": "configs[2] sharding: 64K^2 virtual %s map cut into 4x4 xy-tiles of %dx%d; rank r builds tile r (1 pyramid + %d z-slice "
+                        "DAG(s)) per step -- the same unit of work as at N=1 --, host-side gather of sizes only"
+                        % (args.kind, args.size, args.size, args.z_slices),
+            "depth_map": "%dx%d f32 per rank > L2" % (args.size, args.size), "tiles_per_rank": 1, "z_slices": args.z_slices}
 
 
 # ---- own arm -----------------------------------------------------------------------------------------
@@ -210,10 +213,12 @@ def run_own(args):
     ctx = cpvs_b200.Context(local, stream=stream.cuda_stream)
 
     # workload: N=1 whole map, one DAG; N>1 xy-tile `rank` of the 4x4 virtual map, 4 z-slices
+    # the unit of work is the same at every N (weak scaling): one 16K^2 depth map -> pyramid + z_slices DAGs
+    z_slices = args.z_slices
     if world == 1:
-        tile, tps, z_slices = (0, 0), 1, 1
+        tile, tps = (0, 0), 1
     else:
-        tile, tps, z_slices = (rank % 4, (rank // 4) % 4), 4, 4
+        tile, tps = (rank % 4, (rank // 4) % 4), 4
     host = torch.empty((n, n), dtype=torch.float32, pin_memory=True)
     depth_np = host.numpy()
     synth.depth_map(args.kind, n, tile, tps, out=depth_np)
@@ -387,6 +392,14 @@ def run_own(args):
         }
         dom = max(kernels, key=lambda k: kernels[k][1])
         dom_bytes, dom_ms = kernels[dom]
+        # measured DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (profiles/)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")
+        if os.path.exists(tpath) and n == 16384 and args.kind == "terrain" and world == 1:
+            names = {"leaves": "buildLeavesKernel", "leaf_insert": "insertLeavesKernel", "emit_leaves": "emitLeavesKernel",
+                     "pyramid_base": "pyramidBaseKernel<0>"}
+            with open(tpath) as f:
+                traffic = json.load(f)["dram_bytes_per_launch"].get(names[dom])
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
         bbytes = build_bytes(n, info0, leaf)
         step_ms_device = pyr_total + create_ms
@@ -397,7 +410,7 @@ def run_own(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": n * n * 4, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
+                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
                          "kernels": {k: {"algorithmic_bytes": v[0], "ms": v[1], "gbs": (v[0] / (v[1] * 1e-3) / 1e9 if v[1] > 0 else 0.0)}
                                      for k, v in kernels.items()}},
             "build_roofline": {"algorithmic_bytes": bbytes, "roofline_ms": bbytes / (peak * 1e9) * 1e3, "device_ms": step_ms_device,
