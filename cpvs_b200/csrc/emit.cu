@@ -46,7 +46,7 @@ __device__ __forceinline__ void emitInnerBlock(const EmitLevelArgs& a, u32 block
 		if (k) {
 			const u32* kids = a.childUid + a.firstChild[j];
 			const u32 childBase = (u32)*a.childLevelBase;
-			for (u32 c = 0; c < k; ++c) out[1 + c] = childBase + a.childSlotOffset[kids[c]];
+			for (u32 c = 0; c < k; ++c) out[1 + c] = childBase + a.childSlotOffset[kids[c] & 0x7FFFFFFFu];
 		}
 	}
 	__syncthreads();

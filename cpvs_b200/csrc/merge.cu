@@ -25,6 +25,8 @@ namespace cpvs {
 namespace {
 
 constexpr u64 kEmpty = ~0ull;
+// gid = table slot (< 2^31) | kCandidateFlag; consumers of the group id strip the flag (kGidMask).
+constexpr u32 kCandidateFlag = 0x80000000u, kGidMask = 0x7FFFFFFFu;
 
 template <typename Equal>
 __device__ __forceinline__ u32 findGroupSlot(u64* __restrict__ table, u64 tableMask, u64 hash, u32 self, u32* errorFlag, Equal sameTuple) {
@@ -35,15 +37,19 @@ __device__ __forceinline__ u32 findGroupSlot(u64* __restrict__ table, u64 tableM
 		u64 v = ldRelaxed64(table + slot);
 		if (v == kEmpty) {
 			const u64 old = atomicCAS(reinterpret_cast<unsigned long long*>(table + slot), (unsigned long long)kEmpty, (unsigned long long)key);
-			if (old == kEmpty) return (u32)slot;
+			if (old == kEmpty) return (u32)slot | kCandidateFlag;
 			v = old;
 		}
 		if ((v >> 32) == fp) {
 			const u32 other = (u32)v;
 			if (other == self || sameTuple(other)) {
-				// the slot only ever decreases: nothing to do if an earlier node already holds it
-				if (other > self) atomicMin(reinterpret_cast<unsigned long long*>(table + slot), (unsigned long long)key);
-				return (u32)slot;
+				// the slot only ever decreases: nothing to do if an earlier node already holds it. A node
+				// that never lowered its slot cannot be the first occurrence; the ones that did are marked
+				// as candidates, which spares the rank scan the table look-up for everybody else.
+				u32 lowered = 0;
+				if (other > self)
+					lowered = atomicMin(reinterpret_cast<unsigned long long*>(table + slot), (unsigned long long)key) > key ? kCandidateFlag : 0u;
+				return (u32)slot | lowered;
 			}
 		}
 		slot = (slot + 1) & tableMask;
@@ -96,7 +102,7 @@ __device__ __forceinline__ u32 insertInnerNode(u32 j, const u16* __restrict__ ma
 	for (u32 c = 0; c < 8; ++c) {
 		uid[c] = 0;
 		if (c < k) {
-			uid[c] = kids[c];
+			uid[c] = kids[c] & kGidMask;
 			h = mix64(h ^ ((u64)uid[c] + 0x9E3779B97F4A7C15ull * (c + 1)));
 		}
 	}
@@ -106,7 +112,7 @@ __device__ __forceinline__ u32 insertInnerNode(u32 j, const u16* __restrict__ ma
 		bool same = true;
 #pragma unroll
 		for (u32 c = 0; c < 8; ++c)
-			if (c < k) same = same && theirs[c] == uid[c];
+			if (c < k) same = same && (theirs[c] & kGidMask) == uid[c];
 		return same;
 	});
 }
@@ -133,8 +139,9 @@ __global__ void __launch_bounds__(kScanThreads, 8) rankKernel(const u64* __restr
 		slot[i] = 0;
 		words[i] = 0;
 		if (base + i < n) {
-			slot[i] = gid[base + i];
-			if ((u32)table[slot[i]] == (u32)(base + i)) {
+			const u32 g = gid[base + i];
+			slot[i] = g & kGidMask;
+			if ((g & kCandidateFlag) && (u32)table[slot[i]] == (u32)(base + i)) {
 				const u32 k = __popc(masks[base + i] & 0xAAAAu);
 				words[i] = 1 + (leaf ? 2 * k : k);
 				cnt += 1;
@@ -192,7 +199,7 @@ __global__ void __launch_bounds__(kSmallThreads) mergeSmallLevelsKernel(SmallMer
 			const u32 j = base + threadIdx.x;
 			u32 slot = 0, words = 0;
 			if (j < L.n) {
-				slot = L.uid[j];
+				slot = L.uid[j] & kGidMask;
 				if ((u32)ldRelaxed64(a.table + slot) == j) words = 1 + __popc(L.masks[j] & 0xAAAAu);
 			}
 			u32 inclC = words ? 1u : 0u, inclW = words;

@@ -273,3 +273,69 @@ def test_argument_errors(gpu_ctx):
     cont = cpvs_b200.CompressedShadowContainer(2, gpu_ctx)
     with pytest.raises(cpvs_b200.CpvsError):
         cont.copyToGPU()
+
+
+# ---- an octree that stops early (the reference reads out of bounds there) ----------------
+
+@pytest.mark.parametrize("value", [0.25, 0.75, 0.5, 0.125])
+def test_early_terminating_octree_decodes(gpu_ctx, oracle, value):
+    """Dyadic constant planes make d*H an exact integer on every level: some level has nodes but no PARTIAL
+    child. Not a parity target against the reference (undefined behaviour there); the defined result is a
+    valid, shorter DAG -- identical to the oracle port's -- whose every voxel decodes to z + 0.5 <= d*H."""
+    n = 64
+    d = np.full((n, n), value, np.float32)
+    for leaf in (True, False):
+        _, g = _build(gpu_ctx, d, leaf=leaf)
+        o = oracle.Shadow(oracle.MinMax(d), leafmasks=leaf)
+        _assert_same_dag(g, o, (value, leaf))
+        zs = (np.arange(n, dtype=np.float32) + np.float32(0.5)) / np.float32(n) * 2 - 1
+        pts = np.array([[x, y, z] for z in zs for (x, y) in ((-0.9, -0.9), (0.3, 0.7))], np.float32)
+        path = (((pts + np.float32(1)) * np.float32(0.5)) * np.float32(n - 1)).astype(np.int32)
+        lit = (path[:, 2].astype(np.float32) + np.float32(0.5)) <= np.float32(value) * np.float32(n)
+        assert np.array_equal(g.traverse(pts, leaf), lit.astype(np.uint8)), (value, leaf)
+
+
+def test_mixed_map_with_flat_regions(gpu_ctx, oracle):
+    """Half the map is a dyadic constant (subtrees that stop early), half is terrain."""
+    n = 256
+    d = synth.depth_map("terrain", n)
+    d[:, : n // 2] = np.float32(0.5)
+    d[: n // 4, :] = np.float32(1.0)
+    for zt, zn in ((0, 1), (1, 2)):
+        _, g = _build(gpu_ctx, d, zt, zn)
+        o = oracle.Shadow(oracle.MinMax(d), zt, zn)
+        _assert_same_dag(g, o, (zt, zn))
+        pts = synth.lookups(100000, seed=21)
+        assert np.array_equal(g.traverse(pts), o.traverse(pts))
+
+
+def test_lazy_low_levels_and_childmask(gpu_ctx, oracle, golden):
+    """Levels 1 and 2 are only materialised on demand (n >= 128): accessors, createChildmask and a
+    leafmask-less build after a leafmask build must all see them."""
+    d = synth.depth_map("city", 256)
+    mm = cpvs_b200.MinMaxHierarchy(d, gpu_ctx)
+    a = cpvs_b200.CompressedShadow.create(mm)  # leafmask build first: levels 1-2 not built yet
+    om = oracle.MinMax(d)
+    assert mm.createChildmask(1, 10, 20, 30) == om.childmask(1, 10, 20, 30)
+    for lvl in (1, 2):
+        assert np.array_equal(mm.getLevel(lvl).view(np.uint32), om.level(lvl).view(np.uint32))
+    b = cpvs_b200.CompressedShadow.create(mm, leafmasks=False)
+    assert np.array_equal(b.getDAG(), oracle.Shadow(om, leafmasks=False).dag())
+    assert np.array_equal(a.getDAG(), oracle.Shadow(om).dag())
+    vec, _ = golden  # testCreateChildmask.test8x8 (reference test/CompressedShadowUtilTest.cpp:14-19)
+    assert cpvs_b200.MinMaxHierarchy(vec["depths8x8"], gpu_ctx).createChildmask(1, 2, 0, 0) == 0x88AA
+
+
+def test_many_z_tiles(gpu_ctx, oracle):
+    """16 z-slices of one pyramid (createShadowTiles with numSlices = 16): most slices are trivial."""
+    n, zn = 128, 16
+    d = synth.depth_map("terrain", n)
+    mm = cpvs_b200.MinMaxHierarchy(d, gpu_ctx)
+    om = oracle.MinMax(d)
+    trivial = 0
+    for zt in range(zn):
+        g = cpvs_b200.CompressedShadow.create(mm, zt, zn)
+        o = oracle.Shadow(om, zt, zn)
+        _assert_same_dag(g, o, zt)
+        trivial += int(g.info.words == 1)
+    assert trivial >= 8
