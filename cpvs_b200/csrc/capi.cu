@@ -747,7 +747,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		if (!a.n) continue;
 		const bool isLeaf = useLeaf && l == 2;
 		EmitLevelArgs em;
-		em.n = a.n;
+		em.n = hScalars[32 + l];  // unique nodes of the level (read back with the sizes): exact grid
 		em.leaf = isLeaf ? 1 : 0;
 		em.uniqueCount = dUnique + l;
 		em.wordCount = dWords + l;

@@ -112,7 +112,7 @@ int launchRankLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaStream_t strea
 
 // ---- emit.cu: compress (reference src/CompressedShadow.cpp:326-392) ----
 struct EmitLevelArgs {
-	u64 n;                    // upper bound on unique nodes (= SVO nodes of the level)
+	u64 n;                    // unique nodes of the level (or any upper bound: sizes the grid)
 	int leaf;
 	const u64* uniqueCount;   // device: unique nodes of this level
 	const u32* firstList;
