@@ -181,6 +181,7 @@ struct LevelArrays {
 	u64* table = nullptr;      // merge table of this level (large levels own one; small levels share)
 	u64 tableSlots = 0;
 	u32* slotOffset = nullptr; // per table slot: word offset of the group's node
+	unsigned char* sizeOf = nullptr;  // rank scratch, one byte per node (large levels)
 };
 
 }  // namespace
@@ -529,6 +530,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 				a.table = ar.take<u64>(a.tableSlots);
 			}
 			a.slotOffset = ar.take<u32>(a.tableSlots);
+			if (l < smallLow) a.sizeOf = ar.take<unsigned char>(a.n + 4);
 			if (useLeaf && l == 2) {
 				a.leafCodes = ar.take<u32>(a.n * 8);
 				a.leafHash = ar.take<u64>(a.n);
@@ -649,6 +651,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		m.firstList = a.firstList;
 		m.wordOffset = a.wordOffset;
 		m.slotOffset = a.slotOffset;
+		m.sizeOf = a.sizeOf;
 		m.uniqueCount = dUnique + l;
 		m.wordCount = dWords + l;
 		if (!leafLevel && tablesClearing) {

@@ -79,6 +79,7 @@ struct MergeLevelArgs {
 	u32* firstList;        // out (rank): node index of the r-th unique node
 	u32* wordOffset;       // out (rank): compressed word offset (inside the level) of the r-th unique node
 	u32* slotOffset;       // out (rank): per table slot, the word offset of the group's node
+	unsigned char* sizeOf; // scratch (rank): compressed size of node j if it is a first occurrence, else 0
 	u64* uniqueCount;      // out: number of unique nodes
 	u64* wordCount;        // out: compressed words of the level
 };

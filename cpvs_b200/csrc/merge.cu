@@ -127,21 +127,22 @@ __global__ void __launch_bounds__(256) insertInnerKernel(const u16* __restrict__
 // gid[j] = slot of node j's group. Ranks the first occurrences (slot's final index == j) in order,
 // prefix-sums their compressed sizes, and records firstList[rank], wordOffset[rank] and, per group,
 // slotOffset[slot] = word offset of the group's node inside the level.
-__global__ void __launch_bounds__(kScanThreads, 8) rankKernel(const u64* __restrict__ table, const u16* __restrict__ masks, int leaf, u64 n,
-		const u32* __restrict__ gid, u32* __restrict__ firstList, u32* __restrict__ wordOffset, u32* __restrict__ slotOffset,
-		u64* __restrict__ uniqueCount, u64* __restrict__ wordCount, ScanLaunch scan, u32 numTiles) {
-	const u32 tile = scanAcquireTile(scan);
-	const u64 base = (u64)tile * kScanTile + (u64)threadIdx.x * kScanItems;
-	u32 slot[kScanItems], words[kScanItems];
+//
+// Three plain kernels instead of one look-back scan: (1) per 1024-node tile, find the first occurrences
+// (the only part with random accesses) and leave each node's compressed size in a byte plus the tile's
+// totals; (2) one CTA prefix-sums the tile totals; (3) per tile, a block scan of the bytes and the writes.
+// No CTA ever waits for another one, which matters more here than the extra byte per node of traffic.
+__global__ void __launch_bounds__(kScanThreads, 8) rankCountKernel(const u64* __restrict__ table, const u16* __restrict__ masks, int leaf, u64 n,
+		const u32* __restrict__ gid, unsigned char* __restrict__ sizeOf, ScanTileState* __restrict__ tiles) {
+	const u64 base = (u64)blockIdx.x * kScanTile + (u64)threadIdx.x * kScanItems;
+	u32 words[kScanItems];
 	u64 cnt = 0, wsum = 0;
 #pragma unroll
 	for (int i = 0; i < kScanItems; ++i) {
-		slot[i] = 0;
 		words[i] = 0;
 		if (base + i < n) {
 			const u32 g = gid[base + i];
-			slot[i] = g & kGidMask;
-			if ((g & kCandidateFlag) && (u32)table[slot[i]] == (u32)(base + i)) {
+			if ((g & kCandidateFlag) && (u32)table[g & kGidMask] == (u32)(base + i)) {
 				const u32 k = __popc(masks[base + i] & 0xAAAAu);
 				words[i] = 1 + (leaf ? 2 * k : k);
 				cnt += 1;
@@ -149,21 +150,99 @@ __global__ void __launch_bounds__(kScanThreads, 8) rankKernel(const u64* __restr
 			}
 		}
 	}
+	if (base + kScanItems <= n) {
+		static_assert(kScanItems == 4, "packed size store");
+		*reinterpret_cast<u32*>(sizeOf + base) = words[0] | (words[1] << 8) | (words[2] << 16) | (words[3] << 24);
+	} else {
+#pragma unroll
+		for (int i = 0; i < kScanItems; ++i)
+			if (base + i < n) sizeOf[base + i] = (unsigned char)words[i];
+	}
 	u64 preC = cnt, preW = wsum, totC, totW;
 	blockExclusiveScan2(preC, preW, totC, totW);
-	u64 tileC, tileW;
-	scanLookback2(scan, tile, totC, totW, tileC, tileW);
-	if (tile == numTiles - 1 && threadIdx.x == 0) {
-		*uniqueCount = tileC + totC;
-		*wordCount = tileW + totW;
+	if (threadIdx.x == 0) {
+		tiles[blockIdx.x].a = totC;
+		tiles[blockIdx.x].b = totW;
 	}
-	u64 rank = tileC + preC, woff = tileW + preW;
+}
+
+// Exclusive prefix sums of the tile totals, in place; one CTA.
+__global__ void __launch_bounds__(1024) rankScanTilesKernel(ScanTileState* __restrict__ tiles, u32 numTiles, u64* __restrict__ uniqueCount,
+		u64* __restrict__ wordCount) {
+	__shared__ u64 sA[32], sB[32];
+	const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	u64 carryA = 0, carryB = 0;
+	for (u32 base = 0; base < numTiles; base += 1024) {
+		const u32 t = base + threadIdx.x;
+		const u64 a = t < numTiles ? tiles[t].a : 0, b = t < numTiles ? tiles[t].b : 0;
+		u64 ia = a, ib = b;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const u64 ua = __shfl_up_sync(0xFFFFFFFFu, ia, d), ub = __shfl_up_sync(0xFFFFFFFFu, ib, d);
+			if ((int)lane >= d) {
+				ia += ua;
+				ib += ub;
+			}
+		}
+		if (lane == 31) {
+			sA[warp] = ia;
+			sB[warp] = ib;
+		}
+		__syncthreads();
+		u64 offA = 0, offB = 0, totA = 0, totB = 0;
+#pragma unroll
+		for (u32 w = 0; w < 32; ++w) {
+			if (w < warp) {
+				offA += sA[w];
+				offB += sB[w];
+			}
+			totA += sA[w];
+			totB += sB[w];
+		}
+		__syncthreads();
+		if (t < numTiles) {
+			tiles[t].a = carryA + offA + ia - a;
+			tiles[t].b = carryB + offB + ib - b;
+		}
+		carryA += totA;
+		carryB += totB;
+	}
+	if (threadIdx.x == 0) {
+		*uniqueCount = carryA;
+		*wordCount = carryB;
+	}
+}
+
+__global__ void __launch_bounds__(kScanThreads, 8) rankWriteKernel(const unsigned char* __restrict__ sizeOf, const u32* __restrict__ gid, u64 n,
+		const ScanTileState* __restrict__ tiles, u32* __restrict__ firstList, u32* __restrict__ wordOffset, u32* __restrict__ slotOffset) {
+	const u64 base = (u64)blockIdx.x * kScanTile + (u64)threadIdx.x * kScanItems;
+	u32 words[kScanItems] = {0, 0, 0, 0};
+	if (base + kScanItems <= n) {
+		const u32 packed = *reinterpret_cast<const u32*>(sizeOf + base);
+		words[0] = packed & 0xFFu;
+		words[1] = (packed >> 8) & 0xFFu;
+		words[2] = (packed >> 16) & 0xFFu;
+		words[3] = packed >> 24;
+	} else {
+#pragma unroll
+		for (int i = 0; i < kScanItems; ++i)
+			if (base + i < n) words[i] = sizeOf[base + i];
+	}
+	u64 cnt = 0, wsum = 0;
 #pragma unroll
 	for (int i = 0; i < kScanItems; ++i) {
-		if (base + i < n && words[i]) {
+		cnt += words[i] ? 1 : 0;
+		wsum += words[i];
+	}
+	u64 preC = cnt, preW = wsum, totC, totW;
+	blockExclusiveScan2(preC, preW, totC, totW);
+	u64 rank = tiles[blockIdx.x].a + preC, woff = tiles[blockIdx.x].b + preW;
+#pragma unroll
+	for (int i = 0; i < kScanItems; ++i) {
+		if (words[i]) {
 			firstList[rank] = (u32)(base + i);
 			wordOffset[rank] = (u32)woff;
-			slotOffset[slot[i]] = (u32)woff;
+			slotOffset[gid[base + i] & kGidMask] = (u32)woff;
 			++rank;
 			woff += words[i];
 		}
@@ -286,9 +365,10 @@ int launchInsertLevel(const MergeLevelArgs& a, cudaStream_t stream) {
 int launchRankLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaStream_t stream) {
 	if (a.n == 1) return 0;  // done by launchInsertLevel
 	const u32 tiles = (u32)((a.n + kScanTile - 1) / kScanTile);
-	rankKernel<<<tiles, kScanThreads, 0, stream>>>(a.table, a.masks, a.leaf, a.n, a.uid, a.firstList, a.wordOffset, a.slotOffset, a.uniqueCount,
-			a.wordCount, scan, tiles);
-	return 1;
+	rankCountKernel<<<tiles, kScanThreads, 0, stream>>>(a.table, a.masks, a.leaf, a.n, a.uid, a.sizeOf, scan.tiles);
+	rankScanTilesKernel<<<1, 1024, 0, stream>>>(scan.tiles, tiles, a.uniqueCount, a.wordCount);
+	rankWriteKernel<<<tiles, kScanThreads, 0, stream>>>(a.sizeOf, a.uid, a.n, scan.tiles, a.firstList, a.wordOffset, a.slotOffset);
+	return 3;
 }
 
 }  // namespace cpvs
