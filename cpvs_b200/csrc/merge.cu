@@ -28,13 +28,14 @@ constexpr u64 kEmpty = ~0ull;
 // gid = table slot (< 2^31) | kCandidateFlag; consumers of the group id strip the flag (kGidMask).
 constexpr u32 kCandidateFlag = 0x80000000u, kGidMask = 0x7FFFFFFFu;
 
-template <typename Equal>
+// kShared: the table lives in shared memory (single-CTA kernels for the small levels).
+template <bool kShared = false, typename Equal>
 __device__ __forceinline__ u32 findGroupSlot(u64* __restrict__ table, u64 tableMask, u64 hash, u32 self, u32* errorFlag, Equal sameTuple) {
 	const u64 fp = hash >> 32;
 	const u64 key = (fp << 32) | self;
 	u64 slot = hash & tableMask;
 	for (u64 probes = 0; probes <= tableMask; ++probes) {
-		u64 v = ldRelaxed64(table + slot);
+		u64 v = kShared ? *reinterpret_cast<volatile u64*>(table + slot) : ldRelaxed64(table + slot);
 		if (v == kEmpty) {
 			const u64 old = atomicCAS(reinterpret_cast<unsigned long long*>(table + slot), (unsigned long long)kEmpty, (unsigned long long)key);
 			if (old == kEmpty) return (u32)slot | kCandidateFlag;
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(256) insertLeavesKernel(const u32* __restrict_
 	});
 }
 
+template <bool kShared = false>
 __device__ __forceinline__ u32 insertInnerNode(u32 j, const u16* __restrict__ masks, const u32* __restrict__ firstChild,
 		const u32* __restrict__ childUid, u64* __restrict__ table, u64 tableMask, u32* errorFlag) {
 	const u32 mask = masks[j];
@@ -106,7 +108,7 @@ __device__ __forceinline__ u32 insertInnerNode(u32 j, const u16* __restrict__ ma
 			h = mix64(h ^ ((u64)uid[c] + 0x9E3779B97F4A7C15ull * (c + 1)));
 		}
 	}
-	return findGroupSlot(table, tableMask, h, j, errorFlag, [&](u32 other) {
+	return findGroupSlot<kShared>(table, tableMask, h, j, errorFlag, [&](u32 other) {
 		if (masks[other] != mask) return false;
 		const u32* theirs = childUid + firstChild[other];
 		bool same = true;
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(kScanThreads, 8) rankWriteKernel(const unsigne
 // Same tuples, same first-occurrence rule, same outputs as the per-level kernels.
 __global__ void __launch_bounds__(kSmallThreads) mergeSmallLevelsKernel(SmallMergeArgs a) {
 	__shared__ u32 sWarpC[kSmallThreads / 32], sWarpW[kSmallThreads / 32];
-	constexpr u64 kSlots = 2 * kSmallMaxNodes;
+	extern __shared__ __align__(16) u64 sTable[];  // 2 * kSmallMaxNodes slots: probes and atomics stay on chip
 	const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	for (int s = 0; s < a.count; ++s) {
 		const SmallMergeLevel& L = a.lv[s];
@@ -269,9 +271,13 @@ __global__ void __launch_bounds__(kSmallThreads) mergeSmallLevelsKernel(SmallMer
 			__syncthreads();
 			continue;
 		}
-		for (u32 i = threadIdx.x; i < kSlots; i += kSmallThreads) a.table[i] = kEmpty;
+		// table sized to the level (power of two >= 2n), cleared and probed in shared memory
+		u32 slots = 64;
+		while (slots < 2 * L.n) slots <<= 1;
+		for (u32 i = threadIdx.x; i < slots; i += kSmallThreads) sTable[i] = kEmpty;
 		__syncthreads();
-		for (u32 j = threadIdx.x; j < L.n; j += kSmallThreads) L.uid[j] = insertInnerNode(j, L.masks, L.firstChild, L.childUid, a.table, kSlots - 1, a.errorFlag);
+		for (u32 j = threadIdx.x; j < L.n; j += kSmallThreads)
+			L.uid[j] = insertInnerNode<true>(j, L.masks, L.firstChild, L.childUid, sTable, slots - 1, a.errorFlag);
 		__syncthreads();
 		u32 carryC = 0, carryW = 0;
 		for (u32 base = 0; base < L.n; base += kSmallThreads) {
@@ -279,7 +285,7 @@ __global__ void __launch_bounds__(kSmallThreads) mergeSmallLevelsKernel(SmallMer
 			u32 slot = 0, words = 0;
 			if (j < L.n) {
 				slot = L.uid[j] & kGidMask;
-				if ((u32)ldRelaxed64(a.table + slot) == j) words = 1 + __popc(L.masks[j] & 0xAAAAu);
+				if ((u32)sTable[slot] == j) words = 1 + __popc(L.masks[j] & 0xAAAAu);
 			}
 			u32 inclC = words ? 1u : 0u, inclW = words;
 #pragma unroll
@@ -340,7 +346,13 @@ __global__ void singleNodeKernel(const u16* __restrict__ masks, int leaf, u32* g
 
 int launchMergeSmallLevels(const SmallMergeArgs& a, cudaStream_t stream) {
 	if (a.count <= 0) return 0;
-	mergeSmallLevelsKernel<<<1, kSmallThreads, 0, stream>>>(a);
+	constexpr size_t kBytes = 2 * kSmallMaxNodes * sizeof(u64);
+	static bool configured = false;  // > 48 KiB of dynamic shared memory needs the opt-in, once per process
+	if (!configured) {
+		cudaFuncSetAttribute(mergeSmallLevelsKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBytes);
+		configured = true;
+	}
+	mergeSmallLevelsKernel<<<1, kSmallThreads, kBytes, stream>>>(a);
 	return 1;
 }
 
