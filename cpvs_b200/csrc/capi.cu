@@ -527,9 +527,9 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 				a.tableSlots = 2 * kSmallMaxNodes;
 			} else {
 				a.tableSlots = pow2AtLeast(a.n * 2 < 1024 ? 1024 : a.n * 2);
-				a.table = ar.take<u64>(a.tableSlots);
+				a.table = ar.take<u64>(a.tableSlots + kDirectSlots);
 			}
-			a.slotOffset = ar.take<u32>(a.tableSlots);
+			a.slotOffset = ar.take<u32>(a.tableSlots + kDirectSlots);
 			if (l < smallLow) a.sizeOf = ar.take<unsigned char>(a.n + 4);
 			if (useLeaf && l == 2) {
 				a.leafCodes = ar.take<u32>(a.n * 8);
@@ -566,7 +566,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 				CPVS_CUDA(cudaStreamWaitEvent(ctx->aux3, ctx->evFork, 0));
 				tablesClearing = true;
 			}
-			CPVS_CUDA(cudaMemsetAsync(lv[l].table, 0xFF, lv[l].tableSlots * sizeof(u64), ctx->aux3));
+			CPVS_CUDA(cudaMemsetAsync(lv[l].table, 0xFF, (lv[l].tableSlots + kDirectSlots) * sizeof(u64), ctx->aux3));
 		}
 	if (tablesClearing) CPVS_CUDA(cudaEventRecord(ctx->evClear, ctx->aux3));
 	u64 *dSketchBits = dScalars + 161, *dLeafTableMask = dScalars + 162;

@@ -61,6 +61,8 @@ int launchBuildLeaves(const PyramidView& pyr, u32 zTileNum, const u64* coords, u
 int launchSketchPopcount(const u32* sketch, u64* setBits, cudaStream_t stream);
 
 // ---- merge.cu: mergeCommonSubtrees (reference src/CompressedShadow.cpp:215-304, Util.h:154-182) ----
+// Inner-level tables carry kDirectSlots extra slots behind the tableSize hashed ones (merge.cu).
+constexpr u32 kDirectSlots = 256;
 struct MergeLevelArgs {
 	u64 n;                 // nodes in this level
 	int leaf;              // 1: level of leafmask nodes

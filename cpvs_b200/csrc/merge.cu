@@ -25,6 +25,7 @@ namespace cpvs {
 namespace {
 
 constexpr u64 kEmpty = ~0ull;
+static_assert(kDirectSlots == 256, "one direct slot per thread of the insert CTA");
 // gid = table slot (< 2^31) | kCandidateFlag; consumers of the group id strip the flag (kGidMask).
 constexpr u32 kCandidateFlag = 0x80000000u, kGidMask = 0x7FFFFFFFu;
 
@@ -119,11 +120,39 @@ __device__ __forceinline__ u32 insertInnerNode(u32 j, const u16* __restrict__ ma
 	});
 }
 
+// Nodes without PARTIAL children are their mask: eight 1-bit child codes, 256 possible tuples. On
+// repetitive maps (and on the bottom level of a leafmask-less octree, where no child is ever PARTIAL)
+// millions of nodes share a handful of them, and probing would hammer a few table slots. They bypass
+// the hash: each tuple owns one of kDirectSlots slots behind the hashed region, the CTA reduces its
+// first occurrences in shared memory and touches each slot at most once.
+__device__ __forceinline__ u32 compactLitBits(u32 mask) {
+	u32 x = mask & 0x5555u;
+	x = (x | (x >> 1)) & 0x3333u;
+	x = (x | (x >> 2)) & 0x0F0Fu;
+	return (x | (x >> 4)) & 0x00FFu;
+}
+
 __global__ void __launch_bounds__(256) insertInnerKernel(const u16* __restrict__ masks, const u32* __restrict__ firstChild,
 		const u32* __restrict__ childUid, u64 n, u64* __restrict__ table, u64 tableMask, u32* __restrict__ slotOf, u32* errorFlag) {
+	__shared__ u32 sFirst[kDirectSlots];
 	const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= n) return;
-	slotOf[j] = insertInnerNode((u32)j, masks, firstChild, childUid, table, tableMask, errorFlag);
+	sFirst[threadIdx.x] = 0xFFFFFFFFu;
+	__syncthreads();
+	const bool live = j < n;
+	const u32 mask = live ? masks[j] : 0xAAAAu;
+	const bool direct = live && (mask & 0xAAAAu) == 0;
+	const u32 c = compactLitBits(mask);
+	if (direct)
+		atomicMin(&sFirst[c], (u32)j);
+	else if (live)
+		slotOf[j] = insertInnerNode((u32)j, masks, firstChild, childUid, table, tableMask, errorFlag);
+	__syncthreads();
+	const u32 mine = sFirst[threadIdx.x];
+	if (mine != 0xFFFFFFFFu) {
+		u64* slot = table + tableMask + 1 + threadIdx.x;  // key = (fingerprint 0, index): plain minimum, kEmpty is the maximum
+		if ((u32)ldRelaxed64(slot) > mine) atomicMin(reinterpret_cast<unsigned long long*>(slot), (unsigned long long)mine);
+	}
+	if (direct) slotOf[j] = (u32)(tableMask + 1 + c) | (sFirst[c] == (u32)j ? kCandidateFlag : 0u);
 }
 
 // gid[j] = slot of node j's group. Ranks the first occurrences (slot's final index == j) in order,
