@@ -438,6 +438,9 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 				(unsigned long long)((u64)mm->n * zTileNum));
 	CPVS_CUDA(cudaSetDevice(ctx->device));
 	cudaStream_t st = ctx->stream;
+	// a hierarchy built by another context (createShadowTiles: one pyramid, one builder per z-slice) may
+	// still be in flight on that context's stream
+	if (mm->ctx != ctx && mm->evStop) CPVS_CUDA(cudaStreamWaitEvent(st, mm->evStop, 0));
 
 	const int top = L - 2;
 	const bool useLeaf = leafmasks && (L - 3) >= 2;  // src/CompressedShadow.cpp:20-27

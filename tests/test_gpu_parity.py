@@ -339,3 +339,31 @@ def test_many_z_tiles(gpu_ctx, oracle):
         _assert_same_dag(g, o, zt)
         trivial += int(g.info.words == 1)
     assert trivial >= 8
+
+
+def test_concurrent_z_slices_share_one_pyramid(gpu_ctx, oracle):
+    """createShadowTiles (reference src/DeferredRenderer.cpp:150-163): one thread per z-slice, all reading the
+    same MinMaxHierarchy. Here every thread has its own context (stream + scratch arena)."""
+    import threading
+    n, zn = 256, 4
+    d = synth.depth_map("terrain", n)
+    mm = cpvs_b200.MinMaxHierarchy(d, gpu_ctx)
+    om = oracle.MinMax(d)
+    results, errors = {}, []
+
+    def work(z):
+        try:
+            ctx = cpvs_b200.Context(0)
+            for _ in range(3):
+                results[z] = cpvs_b200.CompressedShadow.create(mm, z, zn, ctx=ctx).getDAG()
+        except Exception as exc:  # noqa: BLE001
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(z,)) for z in range(zn)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for z in range(zn):
+        assert np.array_equal(results[z], oracle.Shadow(om, z, zn).dag()), z
