@@ -77,6 +77,8 @@ SIGNATURES = {
     "cpvs_container_lookup_ndc": (_I, [_VP, _VP, _I64, _I, _VP]),
     "cpvs_container_evaluate": (_I, [_VP, _VP, _U32, _U32, _I, _VP, _VP]),
     "cpvs_container_set_filter_size": (_I, [_VP, _U32]),
+    "cpvs_container_save": (_I, [_VP, ctypes.c_char_p]),
+    "cpvs_container_load": (_I, [_VP, ctypes.c_char_p, _PP]),
 }
 
 _lib = None
@@ -309,6 +311,22 @@ class CompressedShadowContainer:
 
     def set(self, shadow, x, y, z):
         _check(self._lib.cpvs_container_set(self.handle, shadow.handle, x, y, z))
+
+    def save(self, path):
+        """Writes the finalized container (grid + combined DAG) to ``path``."""
+        _check(self._lib.cpvs_container_save(self.handle, os.fsencode(path)))
+
+    @classmethod
+    def load(cls, path, ctx=None):
+        """A finalized container from a file written by :meth:`save`; ready for lookups."""
+        self = cls.__new__(cls)
+        self.ctx = ctx or default_context()
+        self._lib = self.ctx._lib
+        h = ctypes.c_void_p()
+        _check(self._lib.cpvs_container_load(self.ctx.handle, os.fsencode(path), ctypes.byref(h)))
+        self.handle = h
+        self.length = round(self.info()["grid_cells"] ** (1.0 / 3.0))
+        return self
 
     def set_dag(self, words, num_levels, leafmasks, x, y, z):
         """A cell built on another GPU / rank: hand over its finished DAG words."""

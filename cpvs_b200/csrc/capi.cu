@@ -1054,6 +1054,98 @@ int cpvs_container_evaluate(const cpvs_container* c, const float* positions, uin
 			[&](const float* in, unsigned char* o) { return launchEvaluate(d, in, width, height, m, o, st); });
 }
 
+namespace {
+struct ContainerFileHeader {
+	char magic[8];
+	u32 version, length, dagLevels, gridLevels, leafmasks, reserved;
+	u64 dagWords, gridCells, fnv64;
+	u64 pad;
+};
+static_assert(sizeof(ContainerFileHeader) == 64, "on-disk header is 64 bytes");
+u64 fnv64Words(const u32* w, u64 n) {
+	u64 h = 14695981039346656037ull;
+	for (u64 i = 0; i < n; ++i) {
+		h ^= w[i];
+		h *= 1099511628211ull;
+	}
+	return h;
+}
+}  // namespace
+
+int cpvs_container_save(const cpvs_container* c, const char* path) {
+	if (!c || !c->finalized || !path) return fail(CPVS_EINVAL, "cpvs_container_save: container not finalized or NULL path");
+	std::vector<u32> dag(c->dagWords), grid(c->cells.size());
+	int rc = cpvs_container_copy(c, dag.data(), grid.data());
+	if (rc != CPVS_OK) return rc;
+	ContainerFileHeader h;
+	std::memset(&h, 0, sizeof(h));
+	std::memcpy(h.magic, "CPVSDAG1", 8);
+	h.version = 1;
+	h.length = c->length;
+	h.dagLevels = c->dagLevels;
+	h.gridLevels = c->gridLevels;
+	h.leafmasks = (u32)c->leafmasks;
+	h.dagWords = c->dagWords;
+	h.gridCells = grid.size();
+	h.fnv64 = fnv64Words(dag.data(), dag.size());
+	FILE* f = std::fopen(path, "wb");
+	if (!f) return fail(CPVS_EINVAL, "cpvs_container_save: cannot open %s", path);
+	const bool ok = std::fwrite(&h, sizeof(h), 1, f) == 1 && std::fwrite(grid.data(), sizeof(u32), grid.size(), f) == grid.size() &&
+					std::fwrite(dag.data(), sizeof(u32), dag.size(), f) == dag.size();
+	std::fclose(f);
+	return ok ? CPVS_OK : fail(CPVS_EINVAL, "cpvs_container_save: short write to %s", path);
+}
+
+int cpvs_container_load(cpvs_ctx* ctx, const char* path, cpvs_container** out) {
+	if (!ctx || !path || !out) return fail(CPVS_EINVAL, "cpvs_container_load: NULL argument");
+	*out = nullptr;
+	FILE* f = std::fopen(path, "rb");
+	if (!f) return fail(CPVS_EINVAL, "cpvs_container_load: cannot open %s", path);
+	ContainerFileHeader h;
+	std::vector<u32> dag, grid;
+	bool ok = std::fread(&h, sizeof(h), 1, f) == 1 && std::memcmp(h.magic, "CPVSDAG1", 8) == 0 && h.version == 1 && isPow2(h.length) &&
+			  h.length <= 64 && h.gridCells == (u64)h.length * h.length * h.length && h.dagWords > 0 && h.dagWords <= (1ull << 32) &&
+			  h.dagLevels > 3 && h.dagLevels < kMaxLevels;
+	if (ok) {
+		grid.resize(h.gridCells);
+		dag.resize(h.dagWords);
+		ok = std::fread(grid.data(), sizeof(u32), grid.size(), f) == grid.size() && std::fread(dag.data(), sizeof(u32), dag.size(), f) == dag.size() &&
+			 fnv64Words(dag.data(), dag.size()) == h.fnv64;
+	}
+	std::fclose(f);
+	if (!ok) return fail(CPVS_EINVAL, "cpvs_container_load: %s is not a valid container file (header, size or checksum)", path);
+	cpvs_container* c = nullptr;
+	int rc = cpvs_container_create(ctx, h.length, &c);
+	if (rc != CPVS_OK) return rc;
+	cudaStream_t st = ctx->stream;
+	cudaError_t e = cudaSetDevice(ctx->device);
+	if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(&c->dag), dag.size() * sizeof(u32), st);
+	if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(&c->grid), grid.size() * sizeof(u32), st);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(c->dag, dag.data(), dag.size() * sizeof(u32), cudaMemcpyHostToDevice, st);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(c->grid, grid.data(), grid.size() * sizeof(u32), cudaMemcpyHostToDevice, st);
+	c->dagWords = h.dagWords;
+	c->dagLevels = h.dagLevels;
+	c->gridLevels = h.gridLevels;
+	c->leafmasks = (int)h.leafmasks;
+	c->skipLevels = skipLevelsFor(c->dagLevels, c->leafmasks, c->gridLevels);
+	if (e == cudaSuccess && c->skipLevels) {
+		e = cudaMallocAsync(reinterpret_cast<void**>(&c->skip), sizeof(u32) << (3 * (c->gridLevels + c->skipLevels)), st);
+		if (e == cudaSuccess) {
+			LookupDag d{c->dag, c->grid, c->dagLevels, c->gridLevels, c->leafmasks, nullptr, c->skipLevels};
+			ctx->launches += launchBuildSkipGrid(d, c->skip, st);
+			e = cudaGetLastError();
+		}
+	}
+	if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the host staging buffers go away
+	if (e != cudaSuccess) {
+		cpvs_container_destroy(c);
+		return fail(CPVS_ECUDA, "cpvs_container_load: %s", cudaGetErrorString(e));
+	}
+	c->finalized = true;
+	*out = c;
+	return CPVS_OK;
+}
+
 int cpvs_container_set_filter_size(cpvs_container* c, uint32_t size) {
 	if (!c) return fail(CPVS_EINVAL, "cpvs_container_set_filter_size: NULL argument");
 	c->filterSize = size;

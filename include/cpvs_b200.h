@@ -178,6 +178,12 @@ CPVS_API int cpvs_container_lookup_ndc(const cpvs_container* c, const float* ndc
  * column-major mat4 (glm::value_ptr order), visibilities = width*height r8 texels (0 or 255). */
 CPVS_API int cpvs_container_evaluate(const cpvs_container* c, const float* positions, uint32_t width, uint32_t height, int mem,
 		const float light_view_proj[16], uint8_t* visibilities);
+/* On-disk container (the reference has no serialisation and rebuilds on every launch).
+ * File = 64-byte header {"CPVSDAG1", version, length, dag_levels, grid_levels, leafmasks, dag_words,
+ * grid_cells, fnv64 of the DAG words} + grid words + DAG words, little endian. A loaded container is
+ * finalized and ready for lookups; its cells cannot be re-set. */
+CPVS_API int cpvs_container_save(const cpvs_container* c, const char* path);
+CPVS_API int cpvs_container_load(cpvs_ctx* ctx, const char* path, cpvs_container** out);
 /* setFilterSize (src/CompressedShadowContainer.h:71-73): stored, unused -- as in the reference
  * (shader/traverse.cs:16-17). */
 CPVS_API int cpvs_container_set_filter_size(cpvs_container* c, uint32_t size);

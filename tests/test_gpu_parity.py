@@ -367,3 +367,31 @@ def test_concurrent_z_slices_share_one_pyramid(gpu_ctx, oracle):
     assert not errors, errors
     for z in range(zn):
         assert np.array_equal(results[z], oracle.Shadow(om, z, zn).dag()), z
+
+
+def test_container_file_round_trip(gpu_ctx, tmp_path):
+    """On-disk container format: save, load, identical words and lookups; corrupt
+    files are rejected."""
+    n, length = 64, 2
+    cont = cpvs_b200.CompressedShadowContainer(length, gpu_ctx)
+    for y in range(length):
+        for x in range(length):
+            mm = cpvs_b200.MinMaxHierarchy(synth.depth_map("city", n, (x, y), length), gpu_ctx)
+            for z in range(length):
+                cont.set(cpvs_b200.CompressedShadow.create(mm, z, length), x, y, z)
+    cont.copyToGPU()
+    path = str(tmp_path / "shadow.cpvs")
+    cont.save(path)
+    back = cpvs_b200.CompressedShadowContainer.load(path, gpu_ctx)
+    assert back.info() == cont.info()
+    dag, grid = cont.dag_and_grid()
+    dag2, grid2 = back.dag_and_grid()
+    assert np.array_equal(dag, dag2) and np.array_equal(grid, grid2)
+    pts = synth.lookups(50000, seed=4)
+    assert np.array_equal(cont.lookup_ndc(pts), back.lookup_ndc(pts))
+    raw = bytearray(open(path, "rb").read())
+    raw[-5] ^= 0x40
+    bad = str(tmp_path / "bad.cpvs")
+    open(bad, "wb").write(raw)
+    with pytest.raises(cpvs_b200.CpvsError):
+        cpvs_b200.CompressedShadowContainer.load(bad, gpu_ctx)
