@@ -94,7 +94,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
-            self.stop_flag.wait(0.02)
+            self.stop_flag.wait(0.004)
 
     def start(self):
         if self.handle is not None:

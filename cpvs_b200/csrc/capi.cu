@@ -76,6 +76,7 @@ struct cpvs_ctx {
 	char* arena;
 	size_t arenaBytes;
 	u64* scalars;  // 192 device words: per-level counters of the build in flight
+	u64* hostScalars;  // pinned mirror for the two read-backs of a build (pageable copies are staged)
 	// High-priority side stream for a short chain of small kernels that is independent of a bulk kernel
 	// on the main stream (the inner levels' emission next to the leaf level's): its CTAs are scheduled
 	// ahead of the bulk kernel's queued ones. Fork/join through the two events.
@@ -214,6 +215,8 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 	ctx->scalars = nullptr;
 	cudaError_t e = cudaStreamCreateWithFlags(&ctx->own, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->scalars), 192 * sizeof(u64));
+	ctx->hostScalars = nullptr;
+	if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->hostScalars), 192 * sizeof(u64));
 	ctx->aux = nullptr;
 	ctx->evFork = ctx->evJoin = ctx->evAuxStart = nullptr;
 	int prioLeast = 0, prioGreatest = 0;
@@ -245,6 +248,7 @@ int cpvs_ctx_destroy(cpvs_ctx* ctx) {
 	cudaStreamSynchronize(ctx->stream);
 	if (ctx->arena) cudaFree(ctx->arena);
 	if (ctx->scalars) cudaFree(ctx->scalars);
+	if (ctx->hostScalars) cudaFreeHost(ctx->hostScalars);
 	if (ctx->aux) cudaStreamDestroy(ctx->aux);
 	if (ctx->evFork) cudaEventDestroy(ctx->evFork);
 	if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
@@ -477,7 +481,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	trace.mark("setup");
 	// 1. exact node counts of every level (closed form), so all buffers can be sized up front
 	ctx->launches += launchCountNodes(pyr, zTileIndex, zTileNum, minLevel, dCounts, st);
-	u64 hScalars[192];
+	u64* hScalars = ctx->hostScalars;
 	CPVS_CUDA(cudaMemcpyAsync(hScalars, dCounts, 32 * sizeof(u64), cudaMemcpyDeviceToHost, st));
 	CPVS_CUDA(cudaStreamSynchronize(st));
 	trace.mark("count kernels + sync");
