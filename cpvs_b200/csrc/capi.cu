@@ -503,7 +503,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		const u64 n = lv[l].n;
 		if (!n || l >= smallLow) continue;
 		if (!(useLeaf && l == 2)) {
-			scanTiles += (n + kScanTile - 1) / kScanTile;
+			scanTiles += (n + kExpandTileNodes - 1) / kExpandTileNodes;
 			++scanLaunches;
 		}
 		if (n > 1) {
@@ -579,10 +579,10 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	u64 *dSketchBits = dScalars + 161, *dLeafTableMask = dScalars + 162;
 	u32* dErrorFlag = reinterpret_cast<u32*>(dScalars + 163);
 	u64 tileCursor = 0, launchCursor = 0;
-	auto nextScan = [&](u64 n) {
+	auto nextScan = [&](u64 n, u64 tileNodes = kScanTile) {
 		ScanLaunch s{dTickets + launchCursor, dTiles + tileCursor};
 		++launchCursor;
-		tileCursor += (n + kScanTile - 1) / kScanTile;
+		tileCursor += (n + tileNodes - 1) / tileNodes;
 		return s;
 	};
 
@@ -611,7 +611,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	for (int l = smallLow - 1; l >= lastInner && lv[l].n; --l) {
 		u64* childCoords = (l > minLevel && lv[l - 1].n) ? lv[l - 1].coords : nullptr;
 		ctx->launches += launchExpandLevel(pyr, l, zTileNum, lv[l].coords, lv[l].n, lv[l].masks, lv[l].firstChild, childCoords,
-				dChildTotal + l, nextScan(lv[l].n), st);
+				dChildTotal + l, nextScan(lv[l].n, kExpandTileNodes), st);
 	}
 	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAVES], st));
 	if (useLeaf && lv[2].n)  // constructLastLevels (src/CompressedShadow.cpp:171-190)

@@ -110,9 +110,10 @@ __device__ __forceinline__ u32 scanAcquireTile(const ScanLaunch& sl) {
 }
 
 // Block-wide exclusive scan of one (a,b) pair per thread. Returns this thread's exclusive prefix
-// inside the block in (a,b) and the block totals in (totA,totB). kScanThreads threads.
+// inside the block in (a,b) and the block totals in (totA,totB). kThreads threads per block.
+template <int kThreads = kScanThreads>
 __device__ __forceinline__ void blockExclusiveScan2(u64& a, u64& b, u64& totA, u64& totB) {
-	__shared__ u64 sA[kScanThreads / 32], sB[kScanThreads / 32];
+	__shared__ u64 sA[kThreads / 32], sB[kThreads / 32];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	u64 ia = a, ib = b;
 #pragma unroll
@@ -130,7 +131,7 @@ __device__ __forceinline__ void blockExclusiveScan2(u64& a, u64& b, u64& totA, u
 	__syncthreads();
 	u64 offA = 0, offB = 0, tA = 0, tB = 0;
 #pragma unroll
-	for (int w = 0; w < kScanThreads / 32; ++w) {
+	for (int w = 0; w < kThreads / 32; ++w) {
 		if (w < warp) {
 			offA += sA[w];
 			offB += sB[w];

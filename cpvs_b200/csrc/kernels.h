@@ -26,6 +26,7 @@ int launchChildmask(const PyramidView& pyr, int level, u32 zTileNum, u32 x, u32 
 // counts[l] += number of SVO nodes at level l, for l in [minLevel, numLevels-3]; counts must be zeroed.
 int launchCountNodes(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, int minLevel, u64* counts, cudaStream_t stream);
 
+constexpr u64 kExpandTileNodes = 128 * kScanItems;  // nodes per look-back tile of launchExpandLevel
 // One breadth-first step: masks of the n nodes of `level`, index of each node's first child in the
 // next level, and the next level's coordinate list. childTotal receives the next level's node count.
 int launchExpandLevel(const PyramidView& pyr, int level, u32 zTileNum, const u64* coords, u64 n, u16* masks,

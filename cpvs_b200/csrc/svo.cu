@@ -80,12 +80,16 @@ __device__ __forceinline__ u32 childmaskLevel0(const float* __restrict__ depth, 
 	return mask;
 }
 
-// One tile = kScanTile consecutive nodes of the level; thread t owns nodes [4t, 4t+4) of the tile.
-__global__ void __launch_bounds__(kScanThreads) expandLevelKernel(const float* __restrict__ tex, u32 side, float heightF, int level0,
+// One tile = kExpandTile consecutive nodes of the level; thread t owns nodes [4t, 4t+4) of the tile.
+// (128-thread tiles: more, shorter-lived CTAs per SM hide the per-tile load -> scan -> look-back -> store
+// chain better than 256-thread ones.)
+constexpr int kExpandThreads = 128;
+constexpr int kExpandTile = kExpandThreads * kScanItems;
+__global__ void __launch_bounds__(kExpandThreads) expandLevelKernel(const float* __restrict__ tex, u32 side, float heightF, int level0,
 		const u64* __restrict__ coords, u64 n, u16* __restrict__ masks, u32* __restrict__ firstChild, u64* __restrict__ childCoords,
 		u64* __restrict__ childTotal, ScanLaunch scan, u32 numTiles) {
 	const u32 tile = scanAcquireTile(scan);
-	const u64 base = (u64)tile * kScanTile + (u64)threadIdx.x * kScanItems;
+	const u64 base = (u64)tile * kExpandTile + (u64)threadIdx.x * kScanItems;
 	u64 c[kScanItems];
 	u32 m[kScanItems];
 	u64 mine = 0;
@@ -103,7 +107,7 @@ __global__ void __launch_bounds__(kScanThreads) expandLevelKernel(const float* _
 		}
 	}
 	u64 pre = mine, dummy = 0, tot, totDummy;
-	blockExclusiveScan2(pre, dummy, tot, totDummy);
+	blockExclusiveScan2<kExpandThreads>(pre, dummy, tot, totDummy);
 	u64 tilePre, tilePreB;
 	scanLookback2(scan, tile, tot, 0, tilePre, tilePreB);
 	if (tile == numTiles - 1 && threadIdx.x == 0) *childTotal = tilePre + tot;
@@ -332,8 +336,8 @@ int launchExpandLevel(const PyramidView& pyr, int level, u32 zTileNum, const u64
 		u64* childCoords, u64* childTotal, ScanLaunch scan, cudaStream_t stream) {
 	const u32 side = (u32)pyr.n >> level;
 	const float heightF = (float)(side * zTileNum);
-	const u32 tiles = (u32)((n + kScanTile - 1) / kScanTile);
-	expandLevelKernel<<<tiles, kScanThreads, 0, stream>>>(pyr.level[level], side, heightF, level == 0 ? 1 : 0, coords, n, masks, firstChild,
+	const u32 tiles = (u32)((n + kExpandTile - 1) / kExpandTile);
+	expandLevelKernel<<<tiles, kExpandThreads, 0, stream>>>(pyr.level[level], side, heightF, level == 0 ? 1 : 0, coords, n, masks, firstChild,
 			childCoords, childTotal, scan, tiles);
 	return 1;
 }
