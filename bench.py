@@ -168,9 +168,9 @@ def workload_config(args, n_gpus):
                             "+ %d random NDC lookups" % (args.size, args.size, args.kind, args.lookups),
                 "depth_map": "%dx%d f32 (%.0f MiB) > L2, regenerated state per step; no explicit L2 flush needed" % (args.size, args.size, args.size * args.size * 4 / 2**20),
                 "tiles_per_rank": 1, "z_slices": args.z_slices}
-    return {"workload": "configs[2] sharding: 64K^2 virtual %s map cut into 4x4 xy-tiles of %dx%d; rank r builds tile r (1 pyramid + %d z-slice "
-                        "DAG(s)) per step -- the same unit of work as at N=1 --, host-side gather of sizes only"
-                        % (args.kind, args.size, args.size, args.z_slices),
+    return {"workload": "configs[2] sharding: a 4x4 grid of %dx%d %s xy-tiles at the texel density of configs[1] (64K^2 texels in all); rank r "
+                        "builds tile r (1 pyramid + %d z-slice DAG(s)) per step -- the same unit of work as at N=1 --, host-side gather "
+                        "of sizes only" % (args.size, args.size, args.kind, args.z_slices),
             "depth_map": "%dx%d f32 per rank > L2" % (args.size, args.size), "tiles_per_rank": 1, "z_slices": args.z_slices}
 
 
@@ -215,10 +215,9 @@ def run_own(args):
     # workload: N=1 whole map, one DAG; N>1 xy-tile `rank` of the 4x4 virtual map, 4 z-slices
     # the unit of work is the same at every N (weak scaling): one 16K^2 depth map -> pyramid + z_slices DAGs
     z_slices = args.z_slices
-    if world == 1:
-        tile, tps = (0, 0), 1
-    else:
-        tile, tps = (rank % 4, (rank // 4) % 4), 4
+    # rank r takes the 16K^2 map whose origin is shifted by (r % 4, r // 4) maps in the same analytic scene at
+    # the same texel density: statistically the same work as rank 0's configs[1] map, different data
+    tile, tps = (rank % 4, (rank // 4) % 4), 1
     host = torch.empty((n, n), dtype=torch.float32, pin_memory=True)
     depth_np = host.numpy()
     synth.depth_map(args.kind, n, tile, tps, out=depth_np)
