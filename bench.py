@@ -147,6 +147,25 @@ def reference_sample(size, kind, window, threads, steps, warmup):
     return samples / dt / 1e6, dt / steps * 1e3, desc, kind_used
 
 
+def reference_lookups(size, kind, window, threads, count):
+    """CompressedShadow::traverse of the reference (or the port) on `count` random NDC points against the DAG of one
+    window: (M lookups/s on 1 thread, M lookups/s on `threads` threads)."""
+    from oracle import pyoracle as O
+    from cpvs_b200 import synth
+    tiles = size // window
+    d = synth.depth_map(kind, window, (0, 0), tiles, threads=1)
+    backend = "ref" if O.have_ref() else "port"
+    sh = O.Shadow(O.MinMax(d, backend))
+    pts = synth.lookups(count)
+    t0 = time.perf_counter()
+    sh.traverse(pts)
+    one = count / (time.perf_counter() - t0) / 1e6
+    t0 = time.perf_counter()
+    sh.traverse(pts, threads=threads)
+    many = count / (time.perf_counter() - t0) / 1e6
+    return one, many
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -320,7 +339,7 @@ def run_own(args):
     # ---- BASELINE configs[3]: a 4K G-buffer of world positions on / just off the surface (deepest descent),
     # through CompressedShadowContainer::evaluate (light transform + grid step + DAG descent) ----
     surface = None
-    if world == 1:
+    if world == 1 and z_slices == 1:
         gw, gh = 3840, 2160
         u = (np.arange(gw, dtype=np.float32) + np.float32(0.5)) / np.float32(gw)
         v = (np.arange(gh, dtype=np.float32) + np.float32(0.5)) / np.float32(gh)
@@ -426,7 +445,10 @@ def run_own(args):
         if world == 1 and not args.no_cpu_baseline:
             cores = max(1, min(os.cpu_count() or 1, 64))
             v, ms, desc, kind_used = reference_sample(n, args.kind, args.ref_sample, cores, 3, 1)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind_used, "sample": desc, "ms_per_step": ms}
+            lk1, lkn = reference_lookups(n, args.kind, args.ref_sample, cores, args.lookups)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind_used, "sample": desc, "ms_per_step": ms,
+                                    "lookups_mps_1_thread": lk1, "lookups_mps_all_threads": lkn,
+                                    "lookups_sample": "%d random NDC points, traverse() on the DAG of one %dx%d window" % (args.lookups, args.ref_sample, args.ref_sample)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -8,6 +8,10 @@ the data path (BASELINE.json north_star). Rank 0 (or every rank) then assembles 
 as ``CompressedShadowContainer::combineDAGs`` / ``createTopLevelGrid`` do
 (reference ``src/CompressedShadowContainer.cpp:52-91``).
 
+The z-slices of one tile are built one after the other on the rank's context: unlike the reference's
+one-thread-per-slice CPU loop, a single build already fills the GPU, and four concurrent contexts measured
+slower (5.0 ms against 3.1 ms for the four slices of a 16K^2 terrain tile).
+
 The builder is injected (``build_cells``): the CUDA path in production, anything with the same return
 shape in host-logic tests.
 """
