@@ -491,6 +491,42 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	for (int l = minLevel; l <= top; ++l)
 		if (lv[l].n >= (1ull << 30)) return fail(CPVS_EOVERFLOW, "level %d has %llu nodes (limit 2^30)", l, (unsigned long long)lv[l].n);
 
+	// A z-slice that misses the surface altogether (most slices of a tall tile grid): the root has no PARTIAL
+	// child, the DAG is its one mask word (0x5555 lit / 0x0000 shadow). One tiny kernel instead of the pipeline.
+	if (top - 1 >= minLevel && lv[top - 1].n == 0) {
+		cpvs_shadow* s = new (std::nothrow) cpvs_shadow();
+		if (!s) return fail(CPVS_ENOMEM, "cpvs_shadow_create: host allocation");
+		std::memset(&s->info, 0, sizeof(s->info));
+		s->skip = nullptr;
+		s->skipLevels = 0;
+		s->ctx = ctx;
+		s->dag = nullptr;
+		cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&s->dag), sizeof(u32), st);
+		u32* hMask = reinterpret_cast<u32*>(hScalars + 190);
+		if (e == cudaSuccess) {
+			ctx->launches += launchChildmask(pyr, top, zTileNum, 0, 0, zTileIndex * 2, s->dag, st);
+			e = cudaMemcpyAsync(hMask, s->dag, sizeof(u32), cudaMemcpyDeviceToHost, st);
+		}
+		for (int i = 1; i <= CPVS_NUM_PHASES && e == cudaSuccess; ++i) e = cudaEventRecord(phases.ev[i], st);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+		float ms = 0.f;
+		if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, phases.ev[0], phases.ev[CPVS_NUM_PHASES]);
+		if (e != cudaSuccess) {
+			if (s->dag) cudaFreeAsync(s->dag, st);
+			delete s;
+			return fail(CPVS_ECUDA, "cpvs_shadow_create: %s", cudaGetErrorString(e));
+		}
+		s->info.num_levels = (u32)L;
+		s->info.leafmasks = useLeaf ? 1 : 0;
+		s->info.total_visibility = *hMask == 0x5555u ? CPVS_VISIBLE : (*hMask == 0u ? CPVS_SHADOW : CPVS_PARTIAL);
+		s->info.words = 1;
+		s->info.svo_nodes[top] = s->info.dag_nodes[top] = s->info.dag_words[top] = 1;
+		s->info.build_ms = ms;
+		s->info.phase_ms[CPVS_PHASE_COUNT] = ms;
+		*out = s;
+		return CPVS_OK;
+	}
+
 	// The top levels up to kSmallMaxNodes nodes each ("small": smallLow..top) are handled by single-CTA
 	// kernels, one launch per phase instead of one or more per level.
 	int smallLow = top + 1;

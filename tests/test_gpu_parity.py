@@ -395,3 +395,33 @@ def test_container_file_round_trip(gpu_ctx, tmp_path):
     open(bad, "wb").write(raw)
     with pytest.raises(cpvs_b200.CpvsError):
         cpvs_b200.CompressedShadowContainer.load(bad, gpu_ctx)
+
+
+def test_config2_tile_grid_4x4x4(gpu_ctx, oracle):
+    """BASELINE configs[2] at reduced size: a 4x4 grid of depth tiles, 4 z-slices each = 64 DAGs in one cubic
+    container (renderWithTiles / createShadowTiles, reference src/DeferredRenderer.cpp:150-187). Most outer
+    z-slices miss the surface (one-word DAGs, grid sentinels); words, grid and lookups must equal the oracle's."""
+    n, length = 256, 4
+    cont = cpvs_b200.CompressedShadowContainer(length, gpu_ctx)
+    ocont = oracle.Container(length)
+    keep, trivial = [], 0
+    for (x, y) in [(x, y) for y in range(length) for x in range(length)]:
+        d = synth.depth_map("terrain", n, (x, y), length)
+        mm = cpvs_b200.MinMaxHierarchy(d, gpu_ctx)
+        om = oracle.MinMax(d)
+        for z in range(length):
+            g = cpvs_b200.CompressedShadow.create(mm, z, length)
+            o = oracle.Shadow(om, z, length)
+            keep.append(o)
+            assert g.getTotalVisibility() == o.total_visibility()
+            trivial += int(g.info.words == 1)
+            cont.set(g, x, y, z)
+            ocont.set(o, x, y, z)
+    assert trivial >= 16
+    cont.copyToGPU()
+    ocont.finalize()
+    dag, grid = cont.dag_and_grid()
+    odag, ogrid = ocont.dag_and_grid()
+    assert np.array_equal(grid, ogrid) and np.array_equal(dag, odag)
+    pts = synth.lookups(300000, seed=12)
+    assert np.array_equal(cont.lookup_ndc(pts), ocont.lookup_ndc(pts))
