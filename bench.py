@@ -44,6 +44,13 @@ def parse_args():
     ap.add_argument("--ref-sample", type=int, default=1024, help="side of one reference sample window")
     ap.add_argument("--z-slices", type=int, default=1,
                     help="z-slice DAGs built per depth map (createShadowTiles); 4 = the cubic 4x4x4 container of BASELINE configs[2]")
+    ap.add_argument("--grid", default=None, choices=["64k", "256k"],
+                    help="whole tile-grid build instead of the step bench: 64k = BASELINE configs[2] (4x4x4 cells of 16K^2 terrain "
+                         "tiles), 256k = configs[4] (16x16x16 cells of 16K^2 city tiles); tiles are sharded over --gpus ranks")
+    ap.add_argument("--grid-tile", type=int, default=16384, help="side of one depth tile of --grid (reduce for a quick run)")
+    ap.add_argument("--grid-length", type=int, default=None, help="override the grid length of --grid")
+    ap.add_argument("--grid-kind", default=None, choices=["plane", "terrain", "city"])
+    ap.add_argument("--no-verify", action="store_true", help="--grid: skip the lookups-decode-to-depth checks")
     return ap.parse_args()
 
 
@@ -191,6 +198,60 @@ def workload_config(args, n_gpus):
                         "builds tile r (1 pyramid + %d z-slice DAG(s)) per step -- the same unit of work as at N=1 --, host-side gather "
                         "of sizes only" % (args.size, args.size, args.kind, args.z_slices),
             "depth_map": "%dx%d f32 per rank > L2" % (args.size, args.size), "tiles_per_rank": 1, "z_slices": args.z_slices}
+
+
+# ---- whole tile grids (BASELINE configs[2] and configs[4]) ---------------------------------------
+
+def run_grid(args):
+    import torch
+    import torch.distributed as dist
+    import cpvs_b200
+    from cpvs_b200 import build as cbuild, gridbuild
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        cbuild.build()
+    if world > 1:
+        dist.barrier()
+    length = args.grid_length or (4 if args.grid == "64k" else 16)
+    kind = args.grid_kind or ("terrain" if args.grid == "64k" else "city")
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx = cpvs_b200.Context(local, stream=stream.cuda_stream)
+    sampler = ClockSampler(local)
+    if not args.no_clocks:
+        sampler.start()
+    res = gridbuild.run(ctx, stream, args.grid_tile, length, kind, rank, world, dist if world > 1 else None,
+                        verify=not args.no_verify,
+                        log=(lambda m: print(m, file=sys.stderr, flush=True)) if os.environ.get("CPVS_GRID_LOG") else None)
+    clocks = sampler.stop()
+    if rank == 0:
+        line = {"metric": METRIC, "value": res["build_msamples_per_s"], "unit": UNIT, "n_gpus": world, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32/u32", "data": "synthetic",
+                "config": {"workload": "configs[%d]: %dK^2 virtual %s shadow map as a %dx%dx%d CompressedShadowContainer of %dx%d depth "
+                                       "tiles, xy tiles sharded round-robin over %d GPU(s), host-side gather of sizes only"
+                                       % (2 if args.grid == "64k" else 4, res["virtual_side"] // 1024, kind, length, length, length,
+                                          args.grid_tile, args.grid_tile, world)},
+                "ms_total": res["build_ms_max_rank"], "gpu_launches": res["gpu_launches"], "clocks": clocks, "grid": res}
+        if not args.no_cpu_baseline:
+            # "build time vs reference": the reference itself on a bounded sample of the same virtual map, extrapolated
+            # per sample (its merge is O(n*u) per DAG, so whole 16K^2 tiles would only be slower than this)
+            cores = max(1, min(os.cpu_count() or 1, 64))
+            v, ms, desc, kind_used = reference_sample(res["virtual_side"], kind, args.ref_sample, cores, 2, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind_used, "sample": desc, "ms_per_step": ms,
+                                    "extrapolated_build_s": res["samples"] / (v * 1e6),
+                                    "note": "single z-slice per window; extrapolated linearly in samples"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 # ---- own arm -----------------------------------------------------------------------------------------
@@ -459,6 +520,8 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.grid:
+        run_grid(args)
     else:
         run_own(args)
 

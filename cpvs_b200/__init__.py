@@ -48,6 +48,7 @@ SIGNATURES = {
     "cpvs_ctx_destroy": (_I, [_VP]),
     "cpvs_ctx_set_stream": (_I, [_VP, _VP]),
     "cpvs_ctx_get_stream": (_VP, [_VP]),
+    "cpvs_ctx_reserve": (_I, [_VP, _U64]),
     "cpvs_ctx_synchronize": (_I, [_VP]),
     "cpvs_ctx_launch_count": (_U64, [_VP]),
     "cpvs_last_error": (ctypes.c_char_p, []),
@@ -79,6 +80,7 @@ SIGNATURES = {
     "cpvs_container_set_filter_size": (_I, [_VP, _U32]),
     "cpvs_container_save": (_I, [_VP, ctypes.c_char_p]),
     "cpvs_container_load": (_I, [_VP, ctypes.c_char_p, _PP]),
+    "cpvs_depth_generate": (_I, [_VP, _I, _I, _I, _I, _I, _VP]),
 }
 
 _lib = None
@@ -131,6 +133,10 @@ class Context:
         """``stream``: raw cudaStream_t as int (e.g. ``torch.cuda.current_stream().cuda_stream``) or None."""
         _check(self._lib.cpvs_ctx_set_stream(self.handle, ctypes.c_void_p(stream or 0)))
 
+    def reserve(self, nbytes):
+        """Pre-grows the stream-ordered pool the finished DAGs are allocated from (see cpvs_ctx_reserve)."""
+        _check(self._lib.cpvs_ctx_reserve(self.handle, int(nbytes)))
+
     def synchronize(self):
         _check(self._lib.cpvs_ctx_synchronize(self.handle))
 
@@ -151,6 +157,21 @@ class Context:
 
 
 _default_ctx = {}
+
+
+SCENES = {"plane": 0, "city": 2}  # CPVS_SCENE_*: the scenes with a device generator
+
+
+def generate_depth(kind, n, out, tile=(0, 0), tiles_per_side=1, ctx=None):
+    """Writes window ``tile`` of the synthetic scene ``kind`` into ``out`` (torch CUDA float32 [n, n] or a raw
+    device pointer) on the context's stream: the device-resident depth source of SURVEY.md 8f.3, standing in
+    for the reference's render + read-back (``src/ShadowMap.cpp:23-30``). Same bytes as ``cpvs_b200.synth``."""
+    ctx = ctx or default_context()
+    ptr, mem = _as_ptr(out)
+    if mem != MEM_DEVICE:
+        raise TypeError("generate_depth writes device memory")
+    _check(ctx._lib.cpvs_depth_generate(ctx.handle, SCENES[kind], n, tile[0], tile[1], tiles_per_side, ctypes.c_void_p(ptr)))
+    return out
 
 
 def default_context(device=0):

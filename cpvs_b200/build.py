@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcpvs_b200.so")
-SOURCES = ["capi.cu", "pyramid.cu", "svo.cu", "merge.cu", "emit.cu", "lookup.cu"]
+SOURCES = ["capi.cu", "pyramid.cu", "svo.cu", "merge.cu", "emit.cu", "lookup.cu", "synthgen.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--fmad=false",  # float products feeding comparisons must round like the reference's
@@ -20,7 +20,8 @@ NVCC_FLAGS = [
 
 
 def _newest_source():
-    paths = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "cpvs_b200.h")]
+    paths = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "cpvs_b200.h"),
+                                                                os.path.join(HERE, "synth", "scene.h")]
     return max(os.path.getmtime(p) for p in paths)
 
 

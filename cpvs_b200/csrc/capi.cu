@@ -14,6 +14,7 @@
 #include <string>
 #include <vector>
 
+#include "../synth/scene.h"
 #include "kernels.h"
 
 using namespace cpvs;
@@ -280,6 +281,17 @@ int cpvs_ctx_synchronize(cpvs_ctx* ctx) {
 	CPVS_CUDA(cudaStreamSynchronize(ctx->stream));
 	return CPVS_OK;
 }
+int cpvs_ctx_reserve(cpvs_ctx* ctx, uint64_t bytes) {
+	if (!ctx) return fail(CPVS_EINVAL, "cpvs_ctx_reserve: NULL context");
+	if (!bytes) return CPVS_OK;
+	CPVS_CUDA(cudaSetDevice(ctx->device));
+	void* p = nullptr;
+	CPVS_CUDA(cudaMallocAsync(&p, bytes, ctx->stream));
+	CPVS_CUDA(cudaFreeAsync(p, ctx->stream));  // stays cached: the pool's release threshold is unlimited
+	CPVS_CUDA(cudaStreamSynchronize(ctx->stream));
+	return CPVS_OK;
+}
+
 uint64_t cpvs_ctx_launch_count(const cpvs_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 /* ---- MinMaxHierarchy ------------------------------------------------------------------------ */
@@ -1189,6 +1201,34 @@ int cpvs_container_load(cpvs_ctx* ctx, const char* path, cpvs_container** out) {
 int cpvs_container_set_filter_size(cpvs_container* c, uint32_t size) {
 	if (!c) return fail(CPVS_EINVAL, "cpvs_container_set_filter_size: NULL argument");
 	c->filterSize = size;
+	return CPVS_OK;
+}
+
+int cpvs_depth_generate(cpvs_ctx* ctx, int kind, int n, int tileX, int tileY, int tilesPerSide, float* depthDevice) {
+	if (!ctx || !depthDevice) return fail(CPVS_EINVAL, "cpvs_depth_generate: NULL argument");
+	if (n < 4 || (n & 3) || tilesPerSide < 1 || tileX < 0 || tileY < 0 || tileX >= tilesPerSide || tileY >= tilesPerSide)
+		return fail(CPVS_EINVAL, "cpvs_depth_generate: bad window (n=%d tile=%d,%d of %d)", n, tileX, tileY, tilesPerSide);
+	const long long gn = (long long)n * tilesPerSide;
+	if (gn > (1ll << 24)) return fail(CPVS_EINVAL, "cpvs_depth_generate: virtual side %lld exceeds 2^24 (float texel coordinates)", gn);
+	const long long gx0 = (long long)tileX * n, gy0 = (long long)tileY * n;
+	CPVS_CUDA(cudaSetDevice(ctx->device));
+	if (kind == CPVS_SCENE_PLANE) {
+		ctx->launches += launchPlaneDepth(depthDevice, n, gx0, gy0, gn, ctx->stream);
+	} else if (kind == CPVS_SCENE_CITY) {
+		std::vector<CityBoxDev> boxes;
+		cpvs_synth::forEachCityBox(gn, gx0, gy0, n, [&](const cpvs_synth::CityBox& b) { boxes.push_back(CityBoxDev{b.x0, b.y0, b.x1, b.y1, b.z}); });
+		CityBoxDev* dBoxes = nullptr;
+		if (!boxes.empty()) {
+			CPVS_CUDA(cudaMallocAsync(&dBoxes, boxes.size() * sizeof(CityBoxDev), ctx->stream));
+			// pageable source: the copy is staged before the call returns, so `boxes` may go out of scope
+			CPVS_CUDA(cudaMemcpyAsync(dBoxes, boxes.data(), boxes.size() * sizeof(CityBoxDev), cudaMemcpyHostToDevice, ctx->stream));
+		}
+		ctx->launches += launchCityDepth(depthDevice, n, dBoxes, (int)boxes.size(), cpvs_synth::kCityFarPlane, ctx->stream);
+		if (dBoxes) CPVS_CUDA(cudaFreeAsync(dBoxes, ctx->stream));
+	} else {
+		return fail(CPVS_EINVAL, "cpvs_depth_generate: scene %d has no device generator", kind);
+	}
+	CPVS_CUDA(cudaGetLastError());
 	return CPVS_OK;
 }
 

@@ -172,4 +172,12 @@ int launchLookupNdc(const LookupDag& d, const float* ndc, long long count, unsig
 int launchEvaluate(const LookupDag& d, const float* positions, unsigned width, unsigned height, const float* matrix, unsigned char* out,
 		cudaStream_t stream);
 
+// ---- synthgen.cu: device-resident synthetic depth tiles (scene definition: ../synth/scene.h)
+struct CityBoxDev {
+	int x0, y0, x1, y1;  // window texels [x0,x1) x [y0,y1)
+	float z;
+};
+int launchPlaneDepth(float* out, int n, long long gx0, long long gy0, long long gn, cudaStream_t stream);
+int launchCityDepth(float* out, int n, const CityBoxDev* boxes, int numBoxes, float farPlane, cudaStream_t stream);
+
 }  // namespace cpvs

@@ -19,7 +19,8 @@ KINDS = {"plane": 0, "terrain": 1, "city": 2}
 
 def build(force=False):
     src = os.path.join(_HERE, "synth.cpp")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    newest = max(os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "scene.h")))
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < newest:
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", src, "-o", _LIB_PATH, "-lpthread"])
 
 

@@ -21,18 +21,11 @@
 #include <thread>
 #include <vector>
 
-namespace {
+#include "scene.h"
 
-struct XorShift32 {
-	uint32_t s;
-	explicit XorShift32(uint32_t seed) : s(seed) {}
-	uint32_t next() {
-		s ^= s << 13;
-		s ^= s >> 17;
-		s ^= s << 5;
-		return s;
-	}
-};
+using cpvs_synth::XorShift32;
+
+namespace {
 
 template <typename F>
 void parallelRows(int n, int threads, F rowFn) {
@@ -53,7 +46,7 @@ void parallelRows(int n, int threads, F rowFn) {
 
 extern "C" {
 
-enum { CPVS_SYNTH_PLANE = 0, CPVS_SYNTH_TERRAIN = 1, CPVS_SYNTH_CITY = 2 };
+enum { CPVS_SYNTH_PLANE = cpvs_synth::kPlane, CPVS_SYNTH_TERRAIN = cpvs_synth::kTerrain, CPVS_SYNTH_CITY = cpvs_synth::kCity };
 
 /* out: n*n floats. (tx,ty,tilesPerSide) select a window of the virtual map; (0,0,1) is the whole map. */
 int cpvs_synth_depth(int kind, int n, int tx, int ty, int tilesPerSide, int threads, float* out) {
@@ -83,24 +76,16 @@ int cpvs_synth_depth(int kind, int n, int tx, int ty, int tilesPerSide, int thre
 		return 0;
 	}
 	if (kind == CPVS_SYNTH_CITY) {
-		const size_t count = static_cast<size_t>(n) * n;
-		std::fill(out, out + count, 0.9f);
-		XorShift32 rng(12345u);
-		const uint32_t ugn = static_cast<uint32_t>(gn);
-		const long nb = gn / 8;
-		for (long b = 0; b < nb; ++b) {
-			const long w = 8 + rng.next() % (ugn / 16 + 1);
-			const long h = 8 + rng.next() % (ugn / 16 + 1);
-			const long x0 = rng.next() % ugn;
-			const long y0 = rng.next() % ugn;
-			const float z = 0.2f + 0.6f * (rng.next() % 1024) / 1024.f;
-			const long xa = std::max(x0, gx0), xb = std::min(std::min(x0 + w, gn), gx0 + n);
-			const long ya = std::max(y0, gy0), yb = std::min(std::min(y0 + h, gn), gy0 + n);
-			for (long y = ya; y < yb; ++y) {
-				float* row = out + static_cast<size_t>(y - gy0) * n;
-				for (long x = xa; x < xb; ++x) row[x - gx0] = std::min(row[x - gx0], z);
+		std::vector<cpvs_synth::CityBox> boxes;
+		cpvs_synth::forEachCityBox(gn, gx0, gy0, n, [&](const cpvs_synth::CityBox& box) { boxes.push_back(box); });
+		parallelRows(n, threads, [&boxes, out, n](int y) {
+			float* row = out + static_cast<size_t>(y) * n;
+			std::fill(row, row + n, cpvs_synth::kCityFarPlane);
+			for (const cpvs_synth::CityBox& box : boxes) {
+				if (y < box.y0 || y >= box.y1) continue;
+				for (int x = box.x0; x < box.x1; ++x) row[x] = std::min(row[x], box.z);
 			}
-		}
+		});
 		return 0;
 	}
 	return -1;

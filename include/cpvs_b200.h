@@ -86,6 +86,11 @@ CPVS_API void* cpvs_ctx_get_stream(const cpvs_ctx* ctx);
 CPVS_API int cpvs_ctx_synchronize(cpvs_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 CPVS_API uint64_t cpvs_ctx_launch_count(const cpvs_ctx* ctx);
+/* Grows the device's stream-ordered memory pool by `bytes` now, so that the finished DAGs of the following
+ * builds (kept alive by a tile-grid driver) are carved from memory the pool already owns instead of each
+ * paying a fresh device allocation inside the build. Optional; HBM is 180 GB, a 4x4x4 grid of 16K^2 terrain
+ * tiles keeps 3.8 GB of DAG words. */
+CPVS_API int cpvs_ctx_reserve(cpvs_ctx* ctx, uint64_t bytes);
 /* Message for the last non-OK status on the calling thread. */
 CPVS_API const char* cpvs_last_error(void);
 CPVS_API const char* cpvs_version(void);
@@ -187,6 +192,16 @@ CPVS_API int cpvs_container_load(cpvs_ctx* ctx, const char* path, cpvs_container
 /* setFilterSize (src/CompressedShadowContainer.h:71-73): stored, unused -- as in the reference
  * (shader/traverse.cs:16-17). */
 CPVS_API int cpvs_container_set_filter_size(cpvs_container* c, uint32_t size);
+
+/* ---- device-resident depth source ---------------------------------------------------------
+ * Replaces the reference's render + glGetTexImage read-back of one light-frustum tile
+ * (src/ShadowMap.cpp:23-30, src/DeferredRenderer.cpp:173-177) for the synthetic scenes of SURVEY.md 8d:
+ * writes the n x n window (tile_x, tile_y) of the (n * tiles_per_side)^2 virtual map into device memory on
+ * the context's stream, byte-identical to the host generator (cpvs_b200/synth). kind: CPVS_SCENE_PLANE or
+ * CPVS_SCENE_CITY (the terrain scene depends on the host libm: CPVS_EINVAL). n: multiple of 4. */
+#define CPVS_SCENE_PLANE 0
+#define CPVS_SCENE_CITY 2
+CPVS_API int cpvs_depth_generate(cpvs_ctx* ctx, int kind, int n, int tile_x, int tile_y, int tiles_per_side, float* depth_device);
 
 #ifdef __cplusplus
 }

@@ -425,3 +425,63 @@ def test_config2_tile_grid_4x4x4(gpu_ctx, oracle):
     assert np.array_equal(grid, ogrid) and np.array_equal(dag, odag)
     pts = synth.lookups(300000, seed=12)
     assert np.array_equal(cont.lookup_ndc(pts), ocont.lookup_ndc(pts))
+
+
+# ---- device-resident depth source ----------------------------------------------------
+
+@pytest.mark.parametrize("kind,n,tiles", [("plane", 1024, 1), ("plane", 512, 4), ("city", 1024, 1), ("city", 512, 4),
+                                          ("city", 256, 64), ("city", 16, 2)])
+def test_device_generated_tiles_equal_host_bytes(gpu_ctx, kind, n, tiles):
+    """The CUDA generator must write the same bytes as the host generator the oracle is fed with. 64 tiles per
+    side of 256 texels = a 16K^2 city with 2048 boxes of up to 1032 texels: most of them cover whole 128x32
+    regions of a tile (the scalar path of the kernel), the rest cut through regions."""
+    import torch
+    out = torch.empty((n, n), dtype=torch.float32, device="cuda:0")
+    picks = [(x, y) for y in range(tiles) for x in range(tiles)]
+    if len(picks) > 16:
+        picks = picks[:: len(picks) // 16]
+    for tile in picks:
+        out.fill_(-1.0)
+        torch.cuda.synchronize()  # the context runs on its own stream
+        cpvs_b200.generate_depth(kind, n, out, tile, tiles, gpu_ctx)
+        gpu_ctx.synchronize()
+        host = synth.depth_map(kind, n, tile, tiles)
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), host.view(np.uint32)), (kind, tile)
+
+
+def test_device_generated_tile_grid_equals_oracle(gpu_ctx, oracle):
+    """BASELINE configs[4] at reduced size: city tiles generated on the device, built without leaving it,
+    gathered into a cubic container; the oracle gets the host generator's bytes."""
+    import torch
+    n, length = 128, 4
+    cont = cpvs_b200.CompressedShadowContainer(length, gpu_ctx)
+    ocont = oracle.Container(length)
+    keep = []
+    depth = torch.empty((n, n), dtype=torch.float32, device="cuda:0")
+    for (x, y) in [(x, y) for y in range(length) for x in range(length)]:
+        cpvs_b200.generate_depth("city", n, depth, (x, y), length, gpu_ctx)
+        mm = cpvs_b200.MinMaxHierarchy(depth, gpu_ctx)
+        om = oracle.MinMax(synth.depth_map("city", n, (x, y), length))
+        for z in range(length):
+            g = cpvs_b200.CompressedShadow.create(mm, z, length)
+            o = oracle.Shadow(om, z, length)
+            keep.append(o)
+            cont.set(g, x, y, z)
+            ocont.set(o, x, y, z)
+        mm.close()
+    cont.copyToGPU()
+    ocont.finalize()
+    dag, grid = cont.dag_and_grid()
+    odag, ogrid = ocont.dag_and_grid()
+    assert np.array_equal(grid, ogrid) and np.array_equal(dag, odag)
+    pts = synth.lookups(200000, seed=5)
+    assert np.array_equal(cont.lookup_ndc(pts), ocont.lookup_ndc(pts))
+
+
+def test_depth_generate_errors(gpu_ctx):
+    import torch
+    out = torch.empty((64, 64), dtype=torch.float32, device="cuda:0")
+    lib = cpvs_b200.load_library()
+    assert lib.cpvs_depth_generate(gpu_ctx.handle, 1, 64, 0, 0, 1, out.data_ptr()) == cpvs_b200.EINVAL  # terrain: host libm
+    assert lib.cpvs_depth_generate(gpu_ctx.handle, 0, 64, 2, 0, 2, out.data_ptr()) == cpvs_b200.EINVAL
+    assert lib.cpvs_depth_generate(gpu_ctx.handle, 0, 64, 0, 0, 1, None) == cpvs_b200.EINVAL
