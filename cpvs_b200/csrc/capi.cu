@@ -49,6 +49,7 @@ inline u64 pow2AtLeast(u64 v) {
 }
 
 __global__ void storeU64Kernel(u64* dst, u64 value) { *dst = value; }
+__global__ void storeU32Kernel(u32* dst, u32 value) { *dst = value; }
 
 // CPVS_TRACE=1: host wall-clock between orchestration steps, to stderr.
 struct HostTrace {
@@ -495,6 +496,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	ctx->launches += launchCountNodes(pyr, zTileIndex, zTileNum, minLevel, dCounts, st);
 	u64* hScalars = ctx->hostScalars;
 	CPVS_CUDA(cudaMemcpyAsync(hScalars, dCounts, 32 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_NUM_PHASES], st));  // end of a slice that stops here; re-recorded at the end otherwise
 	CPVS_CUDA(cudaStreamSynchronize(st));
 	trace.mark("count kernels + sync");
 	LevelArrays lv[kMaxLevels];
@@ -513,16 +515,25 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		s->skipLevels = 0;
 		s->ctx = ctx;
 		s->dag = nullptr;
+		// The count launch already reported the root's mask (kRootMaskScalar) and its read-back is complete: store
+		// the word and return without another round trip. build_ms ends at the read-back.
 		cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&s->dag), sizeof(u32), st);
-		u32* hMask = reinterpret_cast<u32*>(hScalars + 190);
-		if (e == cudaSuccess) {
-			ctx->launches += launchChildmask(pyr, top, zTileNum, 0, 0, zTileIndex * 2, s->dag, st);
-			e = cudaMemcpyAsync(hMask, s->dag, sizeof(u32), cudaMemcpyDeviceToHost, st);
-		}
-		for (int i = 1; i <= CPVS_NUM_PHASES && e == cudaSuccess; ++i) e = cudaEventRecord(phases.ev[i], st);
-		if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+		u32 rootMask = 0;
+		u32* hMask = &rootMask;
 		float ms = 0.f;
-		if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, phases.ev[0], phases.ev[CPVS_NUM_PHASES]);
+		if (e == cudaSuccess && (hScalars[kRootMaskScalar] >> 32) == 1ull) {
+			rootMask = (u32)hScalars[kRootMaskScalar];
+			storeU32Kernel<<<1, 1, 0, st>>>(s->dag, rootMask);
+			++ctx->launches;
+			e = cudaEventElapsedTime(&ms, phases.ev[CPVS_PHASE_COUNT], phases.ev[CPVS_NUM_PHASES]);
+		} else if (e == cudaSuccess) {  // no level was counted (tiny maps): ask for the mask
+			ctx->launches += launchChildmask(pyr, top, zTileNum, 0, 0, zTileIndex * 2, s->dag, st);
+			e = cudaMemcpyAsync(hScalars + 190, s->dag, sizeof(u32), cudaMemcpyDeviceToHost, st);
+			if (e == cudaSuccess) e = cudaEventRecord(phases.ev[CPVS_NUM_PHASES], st);
+			if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+			rootMask = *reinterpret_cast<u32*>(hScalars + 190);
+			if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, phases.ev[CPVS_PHASE_COUNT], phases.ev[CPVS_NUM_PHASES]);
+		}
 		if (e != cudaSuccess) {
 			if (s->dag) cudaFreeAsync(s->dag, st);
 			delete s;

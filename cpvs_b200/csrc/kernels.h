@@ -24,6 +24,9 @@ struct PyramidView {
 int launchChildmask(const PyramidView& pyr, int level, u32 zTileNum, u32 x, u32 y, u32 z, u32* out, cudaStream_t stream);
 
 // counts[l] += number of SVO nodes at level l, for l in [minLevel, numLevels-3]; counts must be zeroed.
+// counts[kRootMaskScalar] = 1<<32 | the root's child mask, written by every launch (a slice without nodes below
+// the root is that one word).
+constexpr int kRootMaskScalar = 31;
 int launchCountNodes(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, int minLevel, u64* counts, cudaStream_t stream);
 
 constexpr u64 kExpandTileNodes = 128 * kScanItems;  // nodes per look-back tile of launchExpandLevel

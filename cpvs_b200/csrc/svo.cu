@@ -14,42 +14,6 @@ namespace cpvs {
 
 namespace {
 
-// ---- node counts per level, for exact allocation (closed form of the classification) ------------
-// A level-l node exists for every voxel (x,y,z) of pyramid level l+1 that classifies PARTIAL:
-// !(z+1 <= min*H) && !(z >= max*H)  <=>  floor(min*H) <= z <= ceil(max*H)-1, inside the z-tile.
-struct CountLevels {
-	const float2* texels[kMaxLevels];  // pyramid level l+1 for node level l
-	u64 numTexels[kMaxLevels];
-	float heightF[kMaxLevels], zLoF[kMaxLevels], zHiF[kMaxLevels];
-	int minLevel;
-};
-// blockIdx.y picks the node level; all levels are counted by one launch.
-__global__ void __launch_bounds__(256) countNodesKernel(CountLevels p, u64* __restrict__ counts) {
-	const int level = p.minLevel + blockIdx.y;
-	const float2* __restrict__ texels = p.texels[level];
-	const u64 numTexels = p.numTexels[level];
-	const float heightF = p.heightF[level], zLoF = p.zLoF[level], zHiF = p.zHiF[level];
-	u64 local = 0;
-	for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < numTexels; i += (u64)gridDim.x * blockDim.x) {
-		const float2 t = texels[i];
-		const float a = __fmul_rn(t.x, heightF), b = __fmul_rn(t.y, heightF);
-		// fmaxf/fminf drop a NaN operand: a NaN bound makes every z of the tile PARTIAL, as in the reference
-		const float lo = fmaxf(floorf(a), zLoF);
-		const float hi = fminf(__fadd_rn(ceilf(b), -1.0f), zHiF);
-		if (hi >= lo) local += (u64)(hi - lo) + 1ull;
-	}
-#pragma unroll
-	for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, d);
-	__shared__ u64 sWarp[8];
-	if ((threadIdx.x & 31) == 0) sWarp[threadIdx.x >> 5] = local;
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		u64 total = 0;
-		for (int w = 0; w < (int)(blockDim.x >> 5); ++w) total += sWarp[w];
-		if (total) atomicAdd(reinterpret_cast<unsigned long long*>(counts + level), (unsigned long long)total);
-	}
-}
-
 // ---- cs::createChildmask (src/CompressedShadowUtil.cpp:20-54) ---------------------------------------
 // level >= 1: tex points at (min,max) pairs; level 0: at the depth map (absoluteVisible, never PARTIAL).
 __device__ __forceinline__ u32 childmaskInner(const float2* __restrict__ tex, u32 side, float heightF, u32 ox, u32 oy, u32 oz) {
@@ -78,6 +42,62 @@ __device__ __forceinline__ u32 childmaskLevel0(const float* __restrict__ depth, 
 		for (u32 xy = 0; xy < 4; ++xy) mask |= classifyPoint(z0, z1, d[xy]) << ((xy | (z << 2)) * 2);
 	}
 	return mask;
+}
+
+// ---- node counts per level, for exact allocation (closed form of the classification) ------------
+// A level-l node exists for every voxel (x,y,z) of pyramid level l+1 that classifies PARTIAL:
+// !(z+1 <= min*H) && !(z >= max*H)  <=>  floor(min*H) <= z <= ceil(max*H)-1, inside the z-tile.
+struct CountLevels {
+	const float2* texels[kMaxLevels];  // pyramid level l+1 for node level l
+	u64 numTexels[kMaxLevels];
+	float heightF[kMaxLevels], zLoF[kMaxLevels], zHiF[kMaxLevels];
+	int minLevel;
+	int topCounted;  // level of the root's children
+	u32 rootZ;       // z of the root's first child slab (2 * zTileIndex)
+};
+// blockIdx.y picks the node level; all levels are counted by one launch.
+__global__ void __launch_bounds__(256) countNodesKernel(CountLevels p, u64* __restrict__ counts) {
+	// A z-slice that misses the surface has no node below the root (most slices of a tall tile grid): every
+	// CTA sees that from the four texels under the root and leaves. CTA (0,0) also reports the root's mask,
+	// which is the whole DAG of such a slice.
+	{
+		const float2* __restrict__ under = p.texels[p.topCounted];
+		const float h = p.heightF[p.topCounted], zLo = p.zLoF[p.topCounted], zHi = p.zHiF[p.topCounted];
+		bool any = false;
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			const float2 t = under[i];
+			const float lo = fmaxf(floorf(__fmul_rn(t.x, h)), zLo);
+			const float hi = fminf(__fadd_rn(ceilf(__fmul_rn(t.y, h)), -1.0f), zHi);
+			any |= hi >= lo;
+		}
+		if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+			counts[kRootMaskScalar] = (1ull << 32) | childmaskInner(under, 2u, h, 0u, 0u, p.rootZ);
+		if (!any) return;
+	}
+	const int level = p.minLevel + blockIdx.y;
+	const float2* __restrict__ texels = p.texels[level];
+	const u64 numTexels = p.numTexels[level];
+	const float heightF = p.heightF[level], zLoF = p.zLoF[level], zHiF = p.zHiF[level];
+	u64 local = 0;
+	for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < numTexels; i += (u64)gridDim.x * blockDim.x) {
+		const float2 t = texels[i];
+		const float a = __fmul_rn(t.x, heightF), b = __fmul_rn(t.y, heightF);
+		// fmaxf/fminf drop a NaN operand: a NaN bound makes every z of the tile PARTIAL, as in the reference
+		const float lo = fmaxf(floorf(a), zLoF);
+		const float hi = fminf(__fadd_rn(ceilf(b), -1.0f), zHiF);
+		if (hi >= lo) local += (u64)(hi - lo) + 1ull;
+	}
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, d);
+	__shared__ u64 sWarp[8];
+	if ((threadIdx.x & 31) == 0) sWarp[threadIdx.x >> 5] = local;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		u64 total = 0;
+		for (int w = 0; w < (int)(blockDim.x >> 5); ++w) total += sWarp[w];
+		if (total) atomicAdd(reinterpret_cast<unsigned long long*>(counts + level), (unsigned long long)total);
+	}
 }
 
 // One tile = kExpandTile consecutive nodes of the level; thread t owns nodes [4t, 4t+4) of the tile.
@@ -309,6 +329,8 @@ int launchCountNodes(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, int m
 	if (numCounted <= 0) return 0;
 	CountLevels p;
 	p.minLevel = minLevel;
+	p.topCounted = pyr.numLevels - 3;
+	p.rootZ = zTileIndex * 2;
 	u64 maxTexels = 0;
 	for (int level = minLevel; level <= pyr.numLevels - 3; ++level) {
 		const u32 side = (u32)pyr.n >> (level + 1);

@@ -47,42 +47,63 @@ def run(ctx, stream, tile, length, kind, rank=0, world=1, dist=None, lookups=384
     if res > 2 ** 23:
         raise ValueError("virtual z resolution %d exceeds 2^23" % res)
     on_device = kind in cpvs_b200.SCENES
-    depth = torch.empty((n, n), dtype=torch.float32, device=dev)
+    mine = tiling.tiles_of_rank(length, rank, world)
+    # Depth tiles. Device-generated scenes are produced tile by tile into one buffer. Host-generated ones (terrain:
+    # host libm) are ALL produced and copied before the first timed build -- the metric starts from "depth resident
+    # in device memory", and another rank's generator threads would otherwise steal the CPU from this rank's builds.
+    slots = 1 if on_device else max(1, len(mine))
+    depth_all = torch.empty((slots, n, n), dtype=torch.float32, device=dev)
     host = None if on_device else torch.empty((n, n), dtype=torch.float32, pin_memory=True)
+    resident = {}
 
     def produce(xy):
+        """Depth tile `xy` in device memory -> (tensor, ms spent producing it)."""
+        if xy in resident:
+            return resident[xy], 0.0
         t0 = time.perf_counter()
         if on_device:
-            cpvs_b200.generate_depth(kind, n, depth, xy, length, ctx)
+            buf = depth_all[0]
+            cpvs_b200.generate_depth(kind, n, buf, xy, length, ctx)
         else:
+            buf = depth_all[len(resident)]
             synth.depth_map(kind, n, xy, length, out=host.numpy())
-            depth.copy_(host, non_blocking=True)
+            buf.copy_(host, non_blocking=True)
+            resident[xy] = buf
         torch.cuda.synchronize(dev)
-        return (time.perf_counter() - t0) * 1e3
+        return buf, (time.perf_counter() - t0) * 1e3
 
-    mine = tiling.tiles_of_rank(length, rank, world)
+    produce_ms = 0.0
+    if not on_device:
+        for xy in mine:
+            produce_ms += produce(xy)[1]
+        if world > 1:
+            dist.barrier()
     if reserve_bytes is None:  # the largest tile seen so far (16K^2 terrain) keeps 243 MB of DAG words
         reserve_bytes = min(int(len(mine) * 320e6 * (n / 16384.0) ** 2), 8 << 30)
     ctx.reserve(reserve_bytes)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     cells = {}  # cell index -> CompressedShadow (kept: the DAG words stay in HBM)
-    build_ms, produce_ms, tile_ms = 0.0, 0.0, []
+    build_ms, tile_ms = 0.0, []
     svo_nodes = np.zeros(32, np.int64)
     dag_nodes = np.zeros(32, np.int64)
     checked = 0
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
     if mine:  # untimed warm-up on the first owned tile: module load, scratch arena growth
-        produce(mine[0])
+        depth, _ = produce(mine[0])
         mm = cpvs_b200.MinMaxHierarchy(depth, ctx, n=n)
         for z in range(length):
             cpvs_b200.CompressedShadow.create(mm, z, length, leafmasks).close()
         mm.close()
         ctx.synchronize()
+    if world > 1:
+        dist.barrier()  # nobody starts its timed builds while another rank still generates or warms up
+        torch.cuda.synchronize(dev)
     launches0 = ctx.launch_count
     wall0 = time.perf_counter()
     for (x, y) in mine:
-        produce_ms += produce((x, y))
+        depth, ms = produce((x, y))
+        produce_ms += ms
         ev0.record(stream)
         mm = cpvs_b200.MinMaxHierarchy(depth, ctx, n=n)
         column = [cpvs_b200.CompressedShadow.create(mm, z, length, leafmasks) for z in range(length)]
@@ -209,11 +230,11 @@ def run(ctx, stream, tile, length, kind, rank=0, world=1, dist=None, lookups=384
         cont.lookup_ndc(allp, res_all)
         ctx.synchronize()
         path = (((allp + 1.0) * 0.5) * float(res - 1)).to(torch.int32)
-        for (x, y) in (mine if on_device else mine[:1]):  # host-generated tiles take seconds each: one per rank
+        for (x, y) in mine:
             sel = ((path[:, 0] // n) == x) & ((path[:, 1] // n) == y)
             if not bool(sel.any()):
                 continue
-            produce((x, y))
+            depth, _ = produce((x, y))
             if not torch.equal(res_all[sel], _local_expected(torch, allp[sel], path[sel], depth, res)):
                 raise RuntimeError("container lookups over tile (%d,%d) do not decode to its depth" % (x, y))
             verified += int(sel.sum().item())
@@ -232,7 +253,7 @@ def run(ctx, stream, tile, length, kind, rank=0, world=1, dist=None, lookups=384
     trivial = sum(1 for (w, _, _) in ordered if w == 1)
     result = {
         "virtual_side": res, "tile": n, "length": length, "kind": kind, "leafmasks": bool(leafmasks), "n_gpus": world,
-        "depth_source": "device generator (cpvs_depth_generate)" if on_device else "host generator + H2D copy (untimed)",
+        "depth_source": "device generator (cpvs_depth_generate)" if on_device else "host generator + H2D copy; all owned tiles resident before the timed builds",
         "xy_tiles": length * length, "cells": length ** 3, "one_word_cells": trivial,
         "samples": res * res,
         "build_ms_max_rank": build_max, "build_ms_per_rank": [s[0] for s in stats],
