@@ -101,6 +101,10 @@ struct cpvs_minmax {
 	// Levels 1 and 2 are not needed by the leafmask builder and are only produced on first use.
 	std::mutex lowLock;
 	bool lowLevelsBuilt;
+	// Roots of all z-slices of the column for the zTileNum last asked for (createShadowTiles builds them all
+	// from this one pyramid): slices that miss the surface are answered from here without a device round trip.
+	u32 columnSlices;
+	std::vector<u64> columnRoots;  // [z] = hasNodes << 32 | root mask
 };
 
 struct cpvs_shadow {
@@ -343,6 +347,7 @@ int cpvs_minmax_build(cpvs_ctx* ctx, const float* depth, int n, int mem, cpvs_mi
 	cudaEventCreate(&mm->evBase);
 	cudaEventCreate(&mm->evStop);
 	cudaEventRecord(mm->evStart, ctx->stream);
+	mm->columnSlices = 0;
 	mm->lowLevelsBuilt = n < 128;  // small maps take the generic path, which writes every level
 	ctx->launches += launchPyramid(mm->level[0], n, lv, levels, false, mm->evBase, ctx->stream);
 	cudaEventRecord(mm->evStop, ctx->stream);
@@ -385,6 +390,25 @@ int ensureLowLevels(const cpvs_minmax* cmm, int level) {
 	CPVS_CUDA(cudaGetLastError());
 	CPVS_CUDA(cudaStreamSynchronize(mm->ctx->stream));  // other contexts / streams may read them next
 	mm->lowLevelsBuilt = true;
+	return CPVS_OK;
+}
+
+// hasNodes << 32 | root mask of slice zTileIndex, computing the whole column on first use (one launch, one read-back).
+int columnRoot(cpvs_ctx* ctx, const cpvs_minmax* cmm, const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, u64* root) {
+	cpvs_minmax* mm = const_cast<cpvs_minmax*>(cmm);
+	std::lock_guard<std::mutex> guard(mm->lowLock);
+	if (mm->columnSlices != zTileNum) {
+		u64* dRoots = nullptr;
+		CPVS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dRoots), zTileNum * sizeof(u64), ctx->stream));
+		ctx->launches += launchColumnRoots(pyr, zTileNum, dRoots, ctx->stream);
+		mm->columnRoots.assign(zTileNum, 0);
+		cudaError_t e = cudaMemcpyAsync(mm->columnRoots.data(), dRoots, zTileNum * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+		cudaFreeAsync(dRoots, ctx->stream);
+		if (e != cudaSuccess) return fail(CPVS_ECUDA, "column roots: %s", cudaGetErrorString(e));
+		mm->columnSlices = zTileNum;
+	}
+	*root = mm->columnRoots[zTileIndex];
 	return CPVS_OK;
 }
 }  // namespace
@@ -465,6 +489,41 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	const int lastInner = useLeaf ? 3 : 0;
 	if (!useLeaf)
 		if (int rc = ensureLowLevels(mm, 1)) return rc;  // the leafmask-less octree descends through levels 2 and 1
+
+	// One slice of a column (createShadowTiles, reference src/DeferredRenderer.cpp:150-163): most slices of a tall
+	// grid miss the surface; their DAG is the root's mask word, known for the whole column after one launch.
+	if (zTileNum > 1 && top - 1 >= minLevel) {
+		PyramidView pyrTop;
+		pyrTop.n = mm->n;
+		pyrTop.numLevels = L;
+		for (int k = 0; k < kMaxLevels; ++k) pyrTop.level[k] = k < L ? mm->level[k] : nullptr;
+		u64 root = 0;
+		if (int rc = columnRoot(ctx, mm, pyrTop, zTileIndex, zTileNum, &root)) return rc;
+		if (!(root >> 32)) {
+			cpvs_shadow* s = new (std::nothrow) cpvs_shadow();
+			if (!s) return fail(CPVS_ENOMEM, "cpvs_shadow_create: host allocation");
+			std::memset(&s->info, 0, sizeof(s->info));
+			s->skip = nullptr;
+			s->skipLevels = 0;
+			s->ctx = ctx;
+			s->dag = nullptr;
+			const u32 rootMask = (u32)root;
+			cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&s->dag), sizeof(u32), st);
+			if (e != cudaSuccess) {
+				delete s;
+				return fail(e == cudaErrorMemoryAllocation ? CPVS_ENOMEM : CPVS_ECUDA, "cpvs_shadow_create: %s", cudaGetErrorString(e));
+			}
+			storeU32Kernel<<<1, 1, 0, st>>>(s->dag, rootMask);
+			++ctx->launches;
+			s->info.num_levels = (u32)L;
+			s->info.leafmasks = useLeaf ? 1 : 0;
+			s->info.total_visibility = rootMask == 0x5555u ? CPVS_VISIBLE : (rootMask == 0u ? CPVS_SHADOW : CPVS_PARTIAL);
+			s->info.words = 1;
+			s->info.svo_nodes[top] = s->info.dag_nodes[top] = s->info.dag_words[top] = 1;
+			*out = s;
+			return CPVS_OK;
+		}
+	}
 
 	// ev[i] opens phase i (CPVS_PHASE_*), ev[CPVS_NUM_PHASES] closes the last one
 	struct PhaseEvents {
@@ -608,10 +667,16 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	ArenaCarver sizing(nullptr);
 	carve(sizing);
 	if (sizing.offset > ctx->arenaBytes) {
+		// grow geometrically: a tile grid feeds builds of slowly increasing size, and every regrowth is a
+		// device-synchronising cudaFree + cudaMalloc (tens of ms)
+		const size_t doubled = ctx->arenaBytes * 2;
 		if (ctx->arena) CPVS_CUDA(cudaFree(ctx->arena));
 		ctx->arena = nullptr;
 		ctx->arenaBytes = 0;
-		const size_t want = sizing.offset + sizing.offset / 8;
+		size_t want = sizing.offset + sizing.offset / 4;
+		if (want < doubled) want = doubled;
+		size_t freeBytes = 0, totalBytes = 0;
+		if (cudaMemGetInfo(&freeBytes, &totalBytes) == cudaSuccess && want > freeBytes / 2) want = sizing.offset + sizing.offset / 8;
 		cudaError_t ae = cudaMalloc(reinterpret_cast<void**>(&ctx->arena), want);
 		if (ae != cudaSuccess) return fail(CPVS_ENOMEM, "scratch arena of %zu bytes: %s", want, cudaGetErrorString(ae));
 		ctx->arenaBytes = want;

@@ -24,6 +24,8 @@ struct PyramidView {
 int launchChildmask(const PyramidView& pyr, int level, u32 zTileNum, u32 x, u32 y, u32 z, u32* out, cudaStream_t stream);
 
 // counts[l] += number of SVO nodes at level l, for l in [minLevel, numLevels-3]; counts must be zeroed.
+// All z-slices of a column at once: out[z] = (slice z has nodes below the root) << 32 | the root's child mask.
+int launchColumnRoots(const PyramidView& pyr, u32 zTileNum, u64* out, cudaStream_t stream);
 // counts[kRootMaskScalar] = 1<<32 | the root's child mask, written by every launch (a slice without nodes below
 // the root is that one word).
 constexpr int kRootMaskScalar = 31;

@@ -324,6 +324,31 @@ int launchChildmask(const PyramidView& pyr, int level, u32 zTileNum, u32 x, u32 
 	return 1;
 }
 
+namespace {
+// One thread per z-slice of the column: does the slice reach below the root, and the root's mask.
+__global__ void columnRootsKernel(const float2* __restrict__ under, float heightF, u32 zTileNum, u64* __restrict__ out) {
+	const u32 z = blockIdx.x * blockDim.x + threadIdx.x;
+	if (z >= zTileNum) return;
+	const float zLo = (float)(z * 2u), zHi = (float)(z * 2u + 1u);
+	bool any = false;
+#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		const float2 t = under[i];
+		const float lo = fmaxf(floorf(__fmul_rn(t.x, heightF)), zLo);
+		const float hi = fminf(__fadd_rn(ceilf(__fmul_rn(t.y, heightF)), -1.0f), zHi);
+		any |= hi >= lo;
+	}
+	out[z] = ((u64)(any ? 1u : 0u) << 32) | childmaskInner(under, 2u, heightF, 0u, 0u, z * 2u);
+}
+
+}  // namespace
+
+int launchColumnRoots(const PyramidView& pyr, u32 zTileNum, u64* out, cudaStream_t stream) {
+	const int top = pyr.numLevels - 2;  // 2 x 2 texels under the root
+	columnRootsKernel<<<(zTileNum + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const float2*>(pyr.level[top]), (float)(2u * zTileNum), zTileNum, out);
+	return 1;
+}
+
 int launchCountNodes(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, int minLevel, u64* counts, cudaStream_t stream) {
 	const int numCounted = pyr.numLevels - 2 - minLevel;  // levels minLevel .. numLevels-3
 	if (numCounted <= 0) return 0;

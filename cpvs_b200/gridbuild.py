@@ -4,8 +4,8 @@ configs[4] (256K^2 virtual map, 16x16x16 cells, city occluders).
 What the reference does per frame-of-precomputation in ``DeferredRenderer::renderWithTiles`` /
 ``createShadowTiles`` / ``precomputeShadows`` (reference ``src/DeferredRenderer.cpp:150-235``): for every xy
 tile render a depth map, build one MinMaxHierarchy and ``length`` z-slice DAGs from it, drop them into the
-cubic container, then ``moveToGPU``. Here every rank owns the xy tiles ``t % world == rank``
-(``cpvs_b200.tiling``), produces each depth tile in device memory (CUDA generator for the libm-free scenes,
+cubic container, then ``moveToGPU``. Here every rank owns a rotated round-robin share of the xy tiles
+(``cpvs_b200.tiling.tiles_of_rank``), produces each depth tile in device memory (CUDA generator for the libm-free scenes,
 host generator + copy otherwise), builds its cells, and only the per-cell sizes cross ranks on the host.
 For lookups the finished DAG words are then replicated to every GPU (NCCL broadcast over NVLink -- after the
 build, not on its data path) and the query batch is split by screen rows.

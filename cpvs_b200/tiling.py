@@ -27,8 +27,12 @@ def xy_tiles(length):
 
 
 def tiles_of_rank(length, rank, world):
-    """Round-robin ownership of xy tiles: tile t = y*length + x belongs to rank t % world."""
-    return [t for i, t in enumerate(xy_tiles(length)) if i % world == rank]
+    """Ownership of xy tiles: round-robin over the tiles in loop order, with every row rotated by
+    its index -- tile (x, y) has slot ``y*length + (x + y) % length`` and belongs to rank ``slot % world``. Plain
+    ``t % world`` gives a rank whole columns of the map whenever ``world`` divides ``length``, and the cost of
+    a tile follows the scene (the x = 0 column of the 256K^2 city took twice the average); the rotation hands
+    every rank a diagonal mix with the same tile counts."""
+    return [(x, y) for (x, y) in xy_tiles(length) if (y * length + (x + y) % length) % world == rank]
 
 
 def cell_index(x, y, z, length):
