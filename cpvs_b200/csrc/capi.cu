@@ -252,7 +252,8 @@ int cpvs_ctx_destroy(cpvs_ctx* ctx) {
 	if (!ctx) return CPVS_OK;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
-	if (ctx->arena) cudaFree(ctx->arena);
+	if (ctx->arena) cudaFreeAsync(ctx->arena, ctx->stream);
+	cudaStreamSynchronize(ctx->stream);
 	if (ctx->scalars) cudaFree(ctx->scalars);
 	if (ctx->hostScalars) cudaFreeHost(ctx->hostScalars);
 	if (ctx->aux) cudaStreamDestroy(ctx->aux);
@@ -667,17 +668,19 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	ArenaCarver sizing(nullptr);
 	carve(sizing);
 	if (sizing.offset > ctx->arenaBytes) {
-		// grow geometrically: a tile grid feeds builds of slowly increasing size, and every regrowth is a
-		// device-synchronising cudaFree + cudaMalloc (tens of ms)
+		// Grow geometrically (a tile grid feeds builds of slowly increasing size) and from the stream-ordered
+		// pool: a regrowth served from memory the pool already holds (cpvs_ctx_reserve, earlier frees) costs
+		// microseconds, where cudaFree + cudaMalloc synchronise the device and, with peer access enabled by a
+		// communication library, remap on every GPU (100+ ms). The previous build has completed on all streams.
 		const size_t doubled = ctx->arenaBytes * 2;
-		if (ctx->arena) CPVS_CUDA(cudaFree(ctx->arena));
+		if (ctx->arena) CPVS_CUDA(cudaFreeAsync(ctx->arena, st));
 		ctx->arena = nullptr;
 		ctx->arenaBytes = 0;
 		size_t want = sizing.offset + sizing.offset / 4;
 		if (want < doubled) want = doubled;
 		size_t freeBytes = 0, totalBytes = 0;
 		if (cudaMemGetInfo(&freeBytes, &totalBytes) == cudaSuccess && want > freeBytes / 2) want = sizing.offset + sizing.offset / 8;
-		cudaError_t ae = cudaMalloc(reinterpret_cast<void**>(&ctx->arena), want);
+		cudaError_t ae = cudaMallocAsync(reinterpret_cast<void**>(&ctx->arena), want, st);
 		if (ae != cudaSuccess) return fail(CPVS_ENOMEM, "scratch arena of %zu bytes: %s", want, cudaGetErrorString(ae));
 		ctx->arenaBytes = want;
 	}

@@ -76,10 +76,11 @@ def run(ctx, stream, tile, length, kind, rank=0, world=1, dist=None, lookups=384
     if not on_device:
         for xy in mine:
             produce_ms += produce(xy)[1]
-        if world > 1:
-            dist.barrier()
-    if reserve_bytes is None:  # the largest tile seen so far (16K^2 terrain) keeps 243 MB of DAG words
-        reserve_bytes = min(int(len(mine) * 320e6 * (n / 16384.0) ** 2), 8 << 30)
+    if reserve_bytes is None:
+        # kept DAG words (the largest tile seen so far, 16K^2 terrain, keeps 243 MB) + room for the scratch arena to
+        # regrow inside the pool (4 GB covers the 16K^2 scenes of the survey)
+        scale = (n / 16384.0) ** 2
+        reserve_bytes = int(min(len(mine) * 320e6 * scale, 8 * 2.0 ** 30) + 4e9 * scale)
     ctx.reserve(reserve_bytes)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     cells = {}  # cell index -> CompressedShadow (kept: the DAG words stay in HBM)
@@ -89,16 +90,17 @@ def run(ctx, stream, tile, length, kind, rank=0, world=1, dist=None, lookups=384
     checked = 0
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
-    if mine:  # untimed warm-up on the first owned tile: module load, scratch arena growth
-        depth, _ = produce(mine[0])
-        mm = cpvs_b200.MinMaxHierarchy(depth, ctx, n=n)
-        for z in range(length):
-            cpvs_b200.CompressedShadow.create(mm, z, length, leafmasks).close()
-        mm.close()
-        ctx.synchronize()
     if world > 1:
-        dist.barrier()  # nobody starts its timed builds while another rank still generates or warms up
+        dist.barrier()  # nobody starts its timed builds while another rank still generates depth tiles on the host
         torch.cuda.synchronize(dev)
+    if mine:  # untimed warm-up on the first owned tile, right before the timed builds: module load, scratch arena
+        depth, _ = produce(mine[0])  # growth, and clocks back up after the wait at the barrier
+        for _ in range(2):
+            mm = cpvs_b200.MinMaxHierarchy(depth, ctx, n=n)
+            for z in range(length):
+                cpvs_b200.CompressedShadow.create(mm, z, length, leafmasks).close()
+            mm.close()
+        ctx.synchronize()
     launches0 = ctx.launch_count
     wall0 = time.perf_counter()
     for (x, y) in mine:
