@@ -485,3 +485,38 @@ def test_depth_generate_errors(gpu_ctx):
     assert lib.cpvs_depth_generate(gpu_ctx.handle, 1, 64, 0, 0, 1, out.data_ptr()) == cpvs_b200.EINVAL  # terrain: host libm
     assert lib.cpvs_depth_generate(gpu_ctx.handle, 0, 64, 2, 0, 2, out.data_ptr()) == cpvs_b200.EINVAL
     assert lib.cpvs_depth_generate(gpu_ctx.handle, 0, 64, 0, 0, 1, None) == cpvs_b200.EINVAL
+
+
+# ---- whole tile grids (cpvs_b200.gridbuild: what bench.py --grid runs) -------------------------------
+
+@pytest.mark.parametrize("kind,tile,length", [("city", 256, 4), ("terrain", 128, 4), ("plane", 64, 8)])
+def test_gridbuild_small(kind, tile, length):
+    """The grid driver at a small size: every cell and every container lookup is checked against the depth
+    tiles inside run(); here the grid must also equal the oracle-free host scan and the counts must add up."""
+    import torch
+    from cpvs_b200 import gridbuild
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        ctx = cpvs_b200.Context(0, stream=stream.cuda_stream)
+        res = gridbuild.run(ctx, stream, tile, length, kind, lookups=3840 * 64, lookup_iters=2)
+        ctx.close()
+    assert res["cells"] == length ** 3 and res["verified"]["cell_lookups_vs_depth"] == length ** 3 * 65536
+    assert res["verified"]["container_lookups_vs_depth"] == res["lookups"] == 3840 * 64
+    assert res["grid_cells_with_dag"] + res["one_word_cells"] >= res["cells"] - res["grid_cells_with_dag"]
+    top = str(int(np.log2(tile)) - 1)
+    assert res["dag_nodes_per_level"][top] == length ** 3  # one root per cell
+    assert 0 < res["lookups_lit"] < res["lookups"]
+
+
+def test_reserve_and_kept_dags(gpu_ctx, oracle):
+    """cpvs_ctx_reserve only moves where the memory comes from: words stay identical while many DAGs are kept alive
+    and the scratch arena regrows (a larger map after a smaller one)."""
+    gpu_ctx.reserve(64 << 20)
+    gpu_ctx.reserve(0)
+    kept = []
+    for n, kind in ((64, "terrain"), (256, "city"), (1024, "terrain"), (128, "plane"), (2048, "city")):
+        d = synth.depth_map(kind, n)
+        _, g = _build(gpu_ctx, d)
+        kept.append((g, oracle.Shadow(oracle.MinMax(d))))
+    for g, o in kept:
+        _assert_same_dag(g, o, "kept")
