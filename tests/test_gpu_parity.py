@@ -502,7 +502,7 @@ def test_gridbuild_small(kind, tile, length):
         ctx.close()
     assert res["cells"] == length ** 3 and res["verified"]["cell_lookups_vs_depth"] == length ** 3 * 65536
     assert res["verified"]["container_lookups_vs_depth"] == res["lookups"] == 3840 * 64
-    assert res["grid_cells_with_dag"] + res["one_word_cells"] >= res["cells"] - res["grid_cells_with_dag"]
+    assert res["grid_cells_with_dag"] >= res["cells"] - res["one_word_cells"]  # one-word cells may still mix lit and shadow
     top = str(int(np.log2(tile)) - 1)
     assert res["dag_nodes_per_level"][top] == length ** 3  # one root per cell
     assert 0 < res["lookups_lit"] < res["lookups"]
