@@ -91,8 +91,9 @@ __global__ void __launch_bounds__(kEmitThreads) emitLeavesKernel(EmitLevelArgs a
 		*out++ = mask;
 		const uint4* src = reinterpret_cast<const uint4*>(a.leafCodes + (u64)j * 8);
 		const uint4 c0 = src[0], c1 = src[1];
-		for (u32 slice = 0; slice < 8; ++slice) {
-			if (!((mask >> (2 * slice)) & 2u)) continue;
+		// only the PARTIAL slices, lowest first: the warp iterates as often as its busiest leaf has such slices
+		for (u32 part = mask & 0xAAAAu; part; part &= part - 1u) {
+			const u32 slice = (u32)(__ffs((int)part) - 1) >> 1;
 			*out++ = rowBits(c0.x, slice) | (rowBits(c0.y, slice) << 8) | (rowBits(c0.z, slice) << 16) | (rowBits(c0.w, slice) << 24);
 			*out++ = rowBits(c1.x, slice) | (rowBits(c1.y, slice) << 8) | (rowBits(c1.z, slice) << 16) | (rowBits(c1.w, slice) << 24);
 		}

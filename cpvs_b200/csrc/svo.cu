@@ -222,10 +222,14 @@ __global__ void __launch_bounds__(kSmallThreads) expandSmallLevelsKernel(SmallEx
 //
 // The 1x1x8 childmask needs min k / max k only; k is monotone in depth, so they come from the 8x8
 // block's (min,max) texel of pyramid level 3.
-__device__ __forceinline__ u32 litCountBits(float depth, float heightF, float zc) {
-	const float v = __fadd_rd(__fmul_rn(depth, heightF), -zc);
-	const float kf = fminf(fmaxf(v, 0.0f), 8.0f);  // NaN -> 0: never lit, as midZ <= NaN is false
-	return (u32)__float_as_int(__fadd_rd(kf, 8388608.0f));  // 0x4B000000 + k
+// zc8 = (z0 - 0.5) / 8 (exact). With x = (q - (z0 - 0.5)) / 8 evaluated exactly inside the FMA and rounded toward
+// -inf, RD(x) >= m/8 <=> x >= m/8 for m = 0..8 (m/8 is a float), so floor(8 * sat(RD(x))) = clamp(floor(q - (z0 - 0.5)), 0, 8).
+// NaN saturates to 0: never lit, as midZ <= NaN is false. Four instructions per texel: FMUL, FFMA.RM.SAT, FFMA.RM, IMAD.
+__device__ __forceinline__ u32 litCountBits(float depth, float heightF, float zc8) {
+	const float q = __fmul_rn(depth, heightF);
+	float s;
+	asm("fma.rm.sat.f32 %0, %1, 0f3E000000, %2;" : "=f"(s) : "f"(q), "f"(-zc8));
+	return (u32)__float_as_int(__fmaf_rd(s, 8.0f, 8388608.0f));  // 0x4B000000 + k
 }
 
 // 256 leaves per CTA, in two phases.
@@ -258,7 +262,7 @@ __global__ void __launch_bounds__(256, 8) buildLeavesKernel(const float* __restr
 			u32 x, y, z;
 			unpackCoord(sCoord[l], x, y, z);
 			d[i] = ldSector256(depth + (size_t)(y * 4u + row) * n + x * 4u);
-			zc[i] = __fadd_rn(__uint2float_rn(z * 4u), -0.5f);
+			zc[i] = __fmul_rn(__fadd_rn(__uint2float_rn(z * 4u), -0.5f), 0.125f);
 		}
 #pragma unroll
 		for (u32 i = 0; i < 4; ++i) {
@@ -282,7 +286,7 @@ __global__ void __launch_bounds__(256, 8) buildLeavesKernel(const float* __restr
 	h = mix64(h);
 	u32 ox, oy, oz;
 	unpackCoord(sCoord[threadIdx.x], ox, oy, oz);
-	const float zc = __fadd_rn(__uint2float_rn(oz * 4u), -0.5f);
+	const float zc = __fmul_rn(__fadd_rn(__uint2float_rn(oz * 4u), -0.5f), 0.125f);
 	const float2 mm = level3[(size_t)(oy >> 1) * (n >> 3) + (ox >> 1)];
 	const u32 kmin = litCountBits(mm.x, heightF, zc) & 15u, kmax = litCountBits(mm.y, heightF, zc) & 15u;
 	// slices below kmin are lit (01), slices from kmax up are shadowed (00), the rest PARTIAL (10)
