@@ -87,7 +87,8 @@ struct cpvs_ctx {
 	// Normal-priority side stream for the per-level rank scans, which only the final emission needs and
 	// which therefore run next to the following levels' inserts.
 	cudaStream_t aux2, aux3;  // the ranks of different levels are independent: alternate between the two
-	cudaEvent_t evRankStart, evRankStop, evJoin3, evClear;
+	cudaEvent_t evRankStart, evRankStop, evJoin3, evClear, evCols;
+	bool leafColumns;  // leaves built per column (CPVS_LEAF_COLUMNS=0: per leaf, the older kernel, kept for comparison)
 };
 
 struct cpvs_minmax {
@@ -185,6 +186,7 @@ struct LevelArrays {
 	u32* wordOffset = nullptr;
 	u32* leafCodes = nullptr;
 	u64* leafHash = nullptr;
+	u32* leafAt = nullptr;  // leaf level, built per column: node index by column-order position
 	u64* table = nullptr;      // merge table of this level (large levels own one; small levels share)
 	u64 tableSlots = 0;
 	u32* slotOffset = nullptr; // per table slot: word offset of the group's node
@@ -232,11 +234,16 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming);
 	if (e == cudaSuccess) e = cudaEventCreate(&ctx->evAuxStart);
 	ctx->aux2 = ctx->aux3 = nullptr;
-	ctx->evRankStart = ctx->evRankStop = ctx->evJoin3 = ctx->evClear = nullptr;
+	ctx->evRankStart = ctx->evRankStop = ctx->evJoin3 = ctx->evClear = ctx->evCols = nullptr;
+	{
+		const char* v = std::getenv("CPVS_LEAF_COLUMNS");
+		ctx->leafColumns = !(v && v[0] == '0');
+	}
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux2, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux3, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evJoin3, cudaEventDisableTiming);
 	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evClear, cudaEventDisableTiming);
+	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evCols, cudaEventDisableTiming);
 	if (e == cudaSuccess) e = cudaEventCreate(&ctx->evRankStart);
 	if (e == cudaSuccess) e = cudaEventCreate(&ctx->evRankStop);
 	if (e != cudaSuccess) {
@@ -264,6 +271,7 @@ int cpvs_ctx_destroy(cpvs_ctx* ctx) {
 	if (ctx->aux3) cudaStreamDestroy(ctx->aux3);
 	if (ctx->evJoin3) cudaEventDestroy(ctx->evJoin3);
 	if (ctx->evClear) cudaEventDestroy(ctx->evClear);
+	if (ctx->evCols) cudaEventDestroy(ctx->evCols);
 	if (ctx->evRankStart) cudaEventDestroy(ctx->evRankStart);
 	if (ctx->evRankStop) cudaEventDestroy(ctx->evRankStop);
 	cudaStreamDestroy(ctx->own);
@@ -635,15 +643,27 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	u64* dTable = nullptr;
 	u32* dSketch = nullptr;
 	const bool needSketch = useLeaf && lv[2].n > 0, haveLeaves = useLeaf && lv[2].n > 1;
+	// leaves per column: one more scan (over the columns = texels of pyramid level 3)
+	const bool leafColumns = needSketch && ctx->leafColumns;
+	const u64 numCols = leafColumns ? ((u64)mm->n >> 3) * ((u64)mm->n >> 3) : 0;
+	u32* dColBias = nullptr;
+	if (leafColumns) {
+		scanTiles += (numCols + kScanTile - 1) / kScanTile;
+		++scanLaunches;
+	}
 	auto carve = [&](ArenaCarver& ar) {
 		dTiles = ar.take<ScanTileState>(scanTiles);
 		dTickets = ar.take<u32>(scanLaunches);
 		dSketch = ar.take<u32>(needSketch ? kSketchWords : 0);
 		dTable = ar.take<u64>(maxTable);
+		dColBias = ar.take<u32>(numCols);
 		for (int l = top; l >= minLevel; --l) {
 			LevelArrays& a = lv[l];
 			if (!a.n) continue;
-			a.coords = ar.take<u64>(a.n);
+			if (leafColumns && l == 2)
+				a.leafAt = ar.take<u32>(a.n);
+			else
+				a.coords = ar.take<u64>(a.n);
 			a.masks = ar.take<u16>(a.n);
 			a.uid = ar.take<u32>(a.n);
 			a.firstList = ar.take<u32>(a.n);
@@ -692,6 +712,13 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	// the large inner levels' tables are cleared up front (the leaf level sizes and clears its table on
 	// the device, once the sketch is filled; the small levels clear theirs inside their kernel)
 	// -- on a side stream, next to the expansion; the first inner insert waits for it.
+	if (leafColumns) {
+		CPVS_CUDA(cudaEventRecord(ctx->evFork, st));
+		CPVS_CUDA(cudaStreamWaitEvent(ctx->aux2, ctx->evFork, 0));
+		ScanLaunch colScan{dTickets + scanLaunches - 1, dTiles + scanTiles - (numCols + kScanTile - 1) / kScanTile};
+		ctx->launches += launchColumnBias(pyr, zTileIndex, zTileNum, dColBias, colScan, ctx->aux2);
+		CPVS_CUDA(cudaEventRecord(ctx->evCols, ctx->aux2));
+	}
 	bool tablesClearing = false;
 	for (int l = minLevel; l < smallLow; ++l)
 		if (lv[l].n > 1 && !(useLeaf && l == 2)) {
@@ -732,16 +759,30 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 			e.firstChild = lv[l].firstChild;
 			e.childCoords = (l > minLevel && lv[l - 1].n) ? lv[l - 1].coords : nullptr;
 			e.childTotal = dChildTotal + l;
+			e.colBias = nullptr;
+			e.leafAt = nullptr;
+			e.numLeaves = 0;
+			if (leafColumns && l == 3) {
+				e.numLeaves = (u32)lv[2].n;
+				e.colBias = dColBias;
+				e.leafAt = lv[2].leafAt;
+				CPVS_CUDA(cudaStreamWaitEvent(st, ctx->evCols, 0));
+			}
 		}
 		ctx->launches += launchExpandSmallLevels(sx, st);
 	}
 	for (int l = smallLow - 1; l >= lastInner && lv[l].n; --l) {
 		u64* childCoords = (l > minLevel && lv[l - 1].n) ? lv[l - 1].coords : nullptr;
+		const bool toColumns = leafColumns && l == 3;
+		if (toColumns) CPVS_CUDA(cudaStreamWaitEvent(st, ctx->evCols, 0));
 		ctx->launches += launchExpandLevel(pyr, l, zTileNum, lv[l].coords, lv[l].n, lv[l].masks, lv[l].firstChild, childCoords,
-				dChildTotal + l, nextScan(lv[l].n, kExpandTileNodes), st);
+				dChildTotal + l, nextScan(lv[l].n, kExpandTileNodes), toColumns ? dColBias : nullptr, toColumns ? lv[2].leafAt : nullptr, (u32)lv[2].n, st);
 	}
 	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAVES], st));
-	if (useLeaf && lv[2].n)  // constructLastLevels (src/CompressedShadow.cpp:171-190)
+	if (leafColumns)  // constructLastLevels (src/CompressedShadow.cpp:171-190)
+		ctx->launches += launchBuildLeafColumns(pyr, zTileIndex, zTileNum, dColBias, lv[2].leafAt, (u32)lv[2].n, lv[2].leafCodes, lv[2].leafHash,
+				lv[2].masks, dSketch, st);
+	else if (useLeaf && lv[2].n)
 		ctx->launches += launchBuildLeaves(pyr, zTileNum, lv[2].coords, lv[2].n, lv[2].leafCodes, lv[2].leafHash, lv[2].masks,
 				dSketch, st);
 

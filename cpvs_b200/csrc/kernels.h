@@ -34,8 +34,10 @@ int launchCountNodes(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, int m
 constexpr u64 kExpandTileNodes = 128 * kScanItems;  // nodes per look-back tile of launchExpandLevel
 // One breadth-first step: masks of the n nodes of `level`, index of each node's first child in the
 // next level, and the next level's coordinate list. childTotal receives the next level's node count.
+// With leafAt != NULL the children are leaves built per column (launchBuildLeafColumns): instead of their
+// coordinates, each child's index is stored at its column-order position leafAt[colBias[column] + z].
 int launchExpandLevel(const PyramidView& pyr, int level, u32 zTileNum, const u64* coords, u64 n, u16* masks,
-		u32* firstChild, u64* childCoords, u64* childTotal, ScanLaunch scan, cudaStream_t stream);
+		u32* firstChild, u64* childCoords, u64* childTotal, ScanLaunch scan, const u32* colBias, u32* leafAt, u32 numLeaves, cudaStream_t stream);
 
 // The small top levels (<= kSmallMaxNodes nodes each, root first) expanded by a single CTA.
 constexpr int kSmallThreads = 1024;
@@ -50,6 +52,9 @@ struct SmallExpandLevel {
 	u32* firstChild;
 	u64* childCoords;  // next level's coordinate list (may be null when no child can exist)
 	u64* childTotal;
+	const u32* colBias;  // with leafAt: the children are leaves built per column (see launchExpandLevel)
+	u32* leafAt;
+	u32 numLeaves;
 };
 struct SmallExpandArgs {
 	SmallExpandLevel lv[kMaxLevels];
@@ -64,6 +69,13 @@ int launchExpandSmallLevels(const SmallExpandArgs& a, cudaStream_t stream);
 constexpr u32 kSketchWords = 1u << 22;  // 2^27 bits, 16 MiB
 int launchBuildLeaves(const PyramidView& pyr, u32 zTileNum, const u64* coords, u64 n, u32* codes, u64* hashes, u16* masks, u32* sketch,
 		cudaStream_t stream);
+// The same, one column of leaves (all z-blocks over an 8x8 texel block) at a time: every depth row is read once.
+// launchColumnBias: colBias[c] = (leaves in the columns in front of c, row-major over the (n/8)^2 columns) - first
+// z-block of c; one look-back scan over pyramid level 3. leafAt[colBias[c] + zb] = index of leaf (c, zb) in the
+// level, written by the expansion of level 3.
+int launchColumnBias(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, u32* colBias, ScanLaunch scan, cudaStream_t stream);
+int launchBuildLeafColumns(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, const u32* colBias, const u32* leafAt, u32 numLeaves, u32* codes,
+		u64* hashes, u16* masks, u32* sketch, cudaStream_t stream);
 int launchSketchPopcount(const u32* sketch, u64* setBits, cudaStream_t stream);
 
 // ---- merge.cu: mergeCommonSubtrees (reference src/CompressedShadow.cpp:215-304, Util.h:154-182) ----

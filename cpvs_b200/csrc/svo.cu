@@ -107,7 +107,7 @@ constexpr int kExpandThreads = 128;
 constexpr int kExpandTile = kExpandThreads * kScanItems;
 __global__ void __launch_bounds__(kExpandThreads) expandLevelKernel(const float* __restrict__ tex, u32 side, float heightF, int level0,
 		const u64* __restrict__ coords, u64 n, u16* __restrict__ masks, u32* __restrict__ firstChild, u64* __restrict__ childCoords,
-		u64* __restrict__ childTotal, ScanLaunch scan, u32 numTiles) {
+		u64* __restrict__ childTotal, ScanLaunch scan, u32 numTiles, const u32* __restrict__ colBias, u32* __restrict__ leafAt, u32 numLeaves) {
 	const u32 tile = scanAcquireTile(scan);
 	const u64 base = (u64)tile * kExpandTile + (u64)threadIdx.x * kScanItems;
 	u64 c[kScanItems];
@@ -141,6 +141,17 @@ __global__ void __launch_bounds__(kExpandThreads) expandLevelKernel(const float*
 		if (partial) {
 			u32 x, y, z;
 			unpackCoord(c[i], x, y, z);
+			if (leafAt) {  // the children are leaves: tell their column where they sit in the level (see leaf columns below)
+				while (partial) {
+					const u32 child = (__ffs(partial) - 1) >> 1;
+					partial &= partial - 1;
+					// (positions are in range whenever the pyramid is ordered; a NaN-ridden map fails the count check instead)
+					const u32 at = colBias[(size_t)(y + ((child >> 1) & 1u)) * side + x + (child & 1u)] + z + (child >> 2);
+					if (at < numLeaves) leafAt[at] = (u32)pos;
+					++pos;
+				}
+				continue;
+			}
 			while (partial) {  // ascending child index (cs::getChildCoordinates, Util.cpp:101-117)
 				const u32 child = (__ffs(partial) - 1) >> 1;
 				partial &= partial - 1;
@@ -198,7 +209,12 @@ __global__ void __launch_bounds__(kSmallThreads) expandSmallLevelsKernel(SmallEx
 					while (partial) {
 						const u32 child = (__ffs(partial) - 1) >> 1;
 						partial &= partial - 1;
-						L.childCoords[pos++] = packCoord((x + (child & 1u)) * 2u, (y + ((child >> 1) & 1u)) * 2u, (z + (child >> 2)) * 2u);
+						if (L.leafAt) {
+							const u32 at = L.colBias[(size_t)(y + ((child >> 1) & 1u)) * L.side + x + (child & 1u)] + z + (child >> 2);
+							if (at < L.numLeaves) L.leafAt[at] = pos;
+							++pos;
+						} else
+							L.childCoords[pos++] = packCoord((x + (child & 1u)) * 2u, (y + ((child >> 1) & 1u)) * 2u, (z + (child >> 2)) * 2u);
 					}
 				}
 			}
@@ -304,6 +320,133 @@ __global__ void __launch_bounds__(256, 8) buildLeavesKernel(const float* __restr
 	if (!(__ldcg(word) & (1u << (bit & 31u)))) atomicOr(word, 1u << (bit & 31u));
 }
 
+// ---- leaf columns ---------------------------------------------------------------------------------
+// All leaves over one 8x8 texel block share its 64 depths, and by the closed form above they are the
+// z-blocks lo..hi of the block's (min,max) texel of pyramid level 3. Building them per column reads every
+// depth row once, fully coalesced, instead of once per leaf (3.3 leaves per column on the 16K^2 terrain).
+// A leaf's place in its level is decided by the breadth-first expansion, so the expansion of level 3
+// scatters that index into leafAt[] at the leaf's column-order position colBias[column] + zb, where
+// colBias[c] = (leaves of the columns in front of c, row-major) - lo(c).
+__device__ __forceinline__ void columnRange(float2 t, float heightF, float zLoF, float zHiF, float& lo, u32& cnt) {
+	const float a = __fmul_rn(t.x, heightF), b = __fmul_rn(t.y, heightF);
+	lo = fmaxf(floorf(a), zLoF);  // as countNodesKernel: fmaxf/fminf drop a NaN operand
+	const float hi = fminf(__fadd_rn(ceilf(b), -1.0f), zHiF);
+	cnt = hi >= lo ? (u32)(hi - lo) + 1u : 0u;
+}
+
+__global__ void __launch_bounds__(kScanThreads) columnBiasKernel(const float2* __restrict__ level3, u32 numCols, float heightF, float zLoF,
+		float zHiF, u32* __restrict__ colBias, ScanLaunch scan) {
+	const u32 tile = scanAcquireTile(scan);
+	const u32 base = tile * kScanTile + threadIdx.x * kScanItems;
+	float lo[kScanItems];
+	u32 cnt[kScanItems];
+	u64 mine = 0;
+#pragma unroll
+	for (int i = 0; i < kScanItems; ++i) {
+		lo[i] = 0.f;
+		cnt[i] = 0;
+		if (base + i < numCols) columnRange(level3[base + i], heightF, zLoF, zHiF, lo[i], cnt[i]);
+		mine += cnt[i];
+	}
+	u64 pre = mine, dummy = 0, tot, totDummy;
+	blockExclusiveScan2(pre, dummy, tot, totDummy);
+	u64 tilePre, tilePreB;
+	scanLookback2(scan, tile, tot, 0, tilePre, tilePreB);
+	u32 pos = (u32)(tilePre + pre);
+#pragma unroll
+	for (int i = 0; i < kScanItems; ++i) {
+		if (base + i < numCols) colBias[base + i] = pos - (u32)lo[i];
+		pos += cnt[i];
+	}
+}
+
+// litCountBits with q = depth * H0 already formed and nzc8 = -(z0 - 0.5) / 8.
+__device__ __forceinline__ u32 litCountBitsQ(float q, float nzc8) {
+	float s;
+	asm("fma.rm.sat.f32 %0, %1, 0f3E000000, %2;" : "=f"(s) : "f"(q), "f"(nzc8));
+	return (u32)__float_as_int(__fmaf_rd(s, 8.0f, 8388608.0f));  // 0x4B000000 + k
+}
+
+// Four lanes per column, lane `sub` owns depth rows 2*sub and 2*sub+1 (two 256-bit loads; a warp instruction
+// covers eight x-adjacent columns = four rows of 256 contiguous bytes). The column's leaves are walked in
+// batches of four: every lane forms its two row words of each leaf and stores them (8 lanes-bytes x 4 = the
+// leaf's 32-byte k-code), the 64-bit content hash is a sum of per-lane products folded by two shuffles, and
+// lane j finishes the j-th leaf of the batch (hash, 1x1x8 mask, sketch bit).
+constexpr int kColumnsPerCta = 64;
+__global__ void __launch_bounds__(256) buildLeafColumnsKernel(const float* __restrict__ depth, u32 n, u32 colShift, float heightF,
+		float height3F, float zLoF, float zHiF, const float2* __restrict__ level3, u32 numCols, const u32* __restrict__ colBias,
+		const u32* __restrict__ leafAt, u32 numLeaves, u32* __restrict__ codes, u64* __restrict__ hashes, u16* __restrict__ masks,
+		u32* __restrict__ bitmap, u32 bitmapWordMask) {
+	const u32 lane = threadIdx.x & 31u, sub = lane & 3u;
+	const u32 col = blockIdx.x * kColumnsPerCta + (threadIdx.x >> 2);
+	float lo = 0.f;
+	u32 cnt = 0;
+	float2 mm = make_float2(0.f, 0.f);
+	if (col < numCols) {
+		mm = level3[col];
+		columnRange(mm, height3F, zLoF, zHiF, lo, cnt);
+	}
+	const u32 maxCnt = __reduce_max_sync(0xFFFFFFFFu, cnt);
+	if (maxCnt == 0) return;
+	float q0[8], q1[8];
+	u32 first = 0;  // column-order position of the column's first leaf
+	if (cnt) {
+		const u32 cx = col & ((1u << colShift) - 1u), cy = col >> colShift;
+		const float* p = depth + (size_t)(cy * 8u + sub * 2u) * n + cx * 8u;
+		const Float8 a = ldSector256(p), b = ldSector256(p + n);
+		first = colBias[col] + (u32)lo;
+#pragma unroll
+		for (int t = 0; t < 8; ++t) {
+			q0[t] = __fmul_rn(a.v[t], heightF);
+			q1[t] = __fmul_rn(b.v[t], heightF);
+		}
+	} else {
+#pragma unroll
+		for (int t = 0; t < 8; ++t) q0[t] = q1[t] = 0.f;
+	}
+	const float qMin = __fmul_rn(mm.x, heightF), qMax = __fmul_rn(mm.y, heightF);
+	const u64 mulK = mix64(0x9E3779B97F4A7C15ull * (sub + 1u)) | 1ull, xorK = mix64(0xD6E8FEB86659FD93ull + sub);
+	const u32 groupLane = lane & ~3u;
+	for (u32 m = 0; m < maxCnt; m += 4) {
+		u32 mineIdx = 0xFFFFFFFFu;
+		if (m + sub < cnt && first + m + sub < numLeaves) {
+			mineIdx = leafAt[first + m + sub];
+			if (mineIdx >= numLeaves) mineIdx = 0xFFFFFFFFu;  // cannot happen on an ordered pyramid (see the expansion)
+		}
+		u64 keep = 0;
+#pragma unroll
+		for (u32 j = 0; j < 4; ++j) {
+			const u32 leaf = __shfl_sync(0xFFFFFFFFu, mineIdx, groupLane + j);
+			const float nzc8 = __fsub_rn(0.0625f, __fadd_rn(lo, __uint2float_rn(m + j)));  // -(8 zb - 0.5) / 8, exact
+			u32 w0 = 0, w1 = 0;
+#pragma unroll
+			for (int t = 7; t >= 0; --t) {
+				w0 = w0 * 16u + litCountBitsQ(q0[t], nzc8);
+				w1 = w1 * 16u + litCountBitsQ(q1[t], nzc8);
+			}
+			w0 -= 0x4B000000u * 0x11111111u;  // strips the float exponent bits of all eight terms
+			w1 -= 0x4B000000u * 0x11111111u;
+			if (leaf != 0xFFFFFFFFu) *reinterpret_cast<uint2*>(codes + (u64)leaf * 8u + sub * 2u) = make_uint2(w0, w1);
+			u64 hp = (((((u64)w1) << 32) | w0) ^ xorK) * mulK;
+			hp += __shfl_xor_sync(0xFFFFFFFFu, hp, 1);
+			hp += __shfl_xor_sync(0xFFFFFFFFu, hp, 2);
+			if (j == sub) keep = hp;
+		}
+		if (mineIdx != 0xFFFFFFFFu) {
+			const u64 h = mix64(keep);
+			const float nzc8 = __fsub_rn(0.0625f, __fadd_rn(lo, __uint2float_rn(m + sub)));
+			const u32 kmin = litCountBitsQ(qMin, nzc8) & 15u, kmax = litCountBitsQ(qMax, nzc8) & 15u;
+			// slices below kmin are lit (01), slices from kmax up are shadowed (00), the rest PARTIAL (10)
+			const u32 below = (1u << (2u * kmin)) - 1u;
+			masks[mineIdx] = (u16)((0x5555u & below) | (0xAAAAu & ((1u << (2u * kmax)) - 1u) & ~below));
+			hashes[mineIdx] = h;
+			const u32 bit = (u32)(h >> 20);
+			u32* word = bitmap + ((bit >> 5) & bitmapWordMask);
+			if (!(__ldcg(word) & (1u << (bit & 31u)))) atomicOr(word, 1u << (bit & 31u));
+		}
+	}
+}
+
 // Number of set bits of the sketch -> *setBits (zeroed beforehand).
 __global__ void __launch_bounds__(256) sketchPopcountKernel(const uint4* __restrict__ bitmap, u32 numVec, u64* __restrict__ setBits) {
 	u32 local = 0;
@@ -384,12 +527,12 @@ int launchExpandSmallLevels(const SmallExpandArgs& a, cudaStream_t stream) {
 }
 
 int launchExpandLevel(const PyramidView& pyr, int level, u32 zTileNum, const u64* coords, u64 n, u16* masks, u32* firstChild,
-		u64* childCoords, u64* childTotal, ScanLaunch scan, cudaStream_t stream) {
+		u64* childCoords, u64* childTotal, ScanLaunch scan, const u32* colBias, u32* leafAt, u32 numLeaves, cudaStream_t stream) {
 	const u32 side = (u32)pyr.n >> level;
 	const float heightF = (float)(side * zTileNum);
 	const u32 tiles = (u32)((n + kExpandTile - 1) / kExpandTile);
 	expandLevelKernel<<<tiles, kExpandThreads, 0, stream>>>(pyr.level[level], side, heightF, level == 0 ? 1 : 0, coords, n, masks, firstChild,
-			childCoords, childTotal, scan, tiles);
+			childCoords, childTotal, scan, tiles, colBias, leafAt, numLeaves);
 	return 1;
 }
 
@@ -398,6 +541,24 @@ int launchBuildLeaves(const PyramidView& pyr, u32 zTileNum, const u64* coords, u
 	const float heightF = (float)((u32)pyr.n * zTileNum);
 	buildLeavesKernel<<<(unsigned)((n + kLeavesPerCta - 1) / kLeavesPerCta), 256, 0, stream>>>(pyr.level[0], (u32)pyr.n, heightF,
 			reinterpret_cast<const float2*>(pyr.level[3]), coords, n, codes, hashes, masks, sketch, kSketchWords - 1);
+	return 1;
+}
+
+int launchColumnBias(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, u32* colBias, ScanLaunch scan, cudaStream_t stream) {
+	const u32 side3 = (u32)pyr.n >> 3, numCols = side3 * side3;
+	columnBiasKernel<<<(numCols + kScanTile - 1) / kScanTile, kScanThreads, 0, stream>>>(reinterpret_cast<const float2*>(pyr.level[3]), numCols,
+			(float)(side3 * zTileNum), (float)(zTileIndex * side3), (float)(zTileIndex * side3 + side3 - 1), colBias, scan);
+	return 1;
+}
+
+int launchBuildLeafColumns(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, const u32* colBias, const u32* leafAt, u32 numLeaves, u32* codes,
+		u64* hashes, u16* masks, u32* sketch, cudaStream_t stream) {
+	const u32 side3 = (u32)pyr.n >> 3, numCols = side3 * side3;
+	u32 colShift = 0;
+	while ((1u << colShift) < side3) ++colShift;
+	buildLeafColumnsKernel<<<(numCols + kColumnsPerCta - 1) / kColumnsPerCta, 256, 0, stream>>>(pyr.level[0], (u32)pyr.n, colShift,
+			(float)((u32)pyr.n * zTileNum), (float)(side3 * zTileNum), (float)(zTileIndex * side3), (float)(zTileIndex * side3 + side3 - 1),
+			reinterpret_cast<const float2*>(pyr.level[3]), numCols, colBias, leafAt, numLeaves, codes, hashes, masks, sketch, kSketchWords - 1);
 	return 1;
 }
 
