@@ -458,15 +458,21 @@ def run_own(args):
         u_leaves = int(info0.dag_nodes[2]) if leaf else 0
         # algorithmic (compulsory HBM) bytes per launch of the single-kernel phases -- DESIGN.md "Kernels":
         #   pyramid_base  depth read once + levels 1..5 written
-        #   leaves        depth read once (L2 serves the ~3.3 z-block re-reads) + per leaf: 8 B coordinate in, 32 B k-code,
-        #                 8 B hash, 2 B mask out
-        #   leaf_insert   per leaf: 8 B hash + 32 B own k-code in, 4 B slot out; per duplicate: 32 B representative k-code
-        #                 (the table itself is sized to stay in L2)
+        #   leaves        per column (whole-volume builds with 2..8 leaves per column, the library's own rule): depth read once
+        #                 + per column 8 B level-3 texel and 4 B bias in + per leaf 4 B index in, 32 B k-code and 2 B mask out;
+        #                 per leaf (otherwise): depth read once (L2 serves the z-block re-reads) + per leaf 8 B coordinate in,
+        #                 32 B k-code, 8 B hash, 2 B mask out
+        #   leaf_insert   per leaf: 32 B own k-code (+ 8 B hash on the per-leaf path) in, 4 B slot out; per duplicate: 32 B
+        #                 representative k-code (the table itself is sized to stay in L2)
         #   emit_leaves   per unique leaf: 4 B index + 4 B offset + 2 B mask + 32 B k-code in; compressed words out
+        cols = (n // 8) * (n // 8)
+        per_column = (leaf and args.z_slices == 1 and 2 * cols <= n_leaves <= 8 * cols
+                      and os.environ.get("CPVS_LEAF_COLUMNS", "1") != "0") or os.environ.get("CPVS_LEAF_COLUMNS") == "2"
+        leaves_bytes = (4.0 * n * n + cols * 12.0 + n_leaves * (4.0 + 32 + 2)) if per_column else (4.0 * n * n + n_leaves * (8.0 + 32 + 8 + 2))
         kernels = {
             "pyramid_base": ((4.0 + 8.0 * (1 / 4 + 1 / 16 + 1 / 64 + 1 / 256 + 1 / 1024)) * n * n, pyr_base),
-            "leaves": (4.0 * n * n + n_leaves * (8.0 + 32 + 8 + 2), main_phase["leaves"]),
-            "leaf_insert": (n_leaves * (8.0 + 32 + 4) + (n_leaves - u_leaves) * 32.0, main_phase["leaf_insert"]),
+            "leaves": (leaves_bytes, main_phase["leaves"]),
+            "leaf_insert": (n_leaves * ((0.0 if per_column else 8.0) + 32 + 4) + (n_leaves - u_leaves) * 32.0, main_phase["leaf_insert"]),
             "emit_leaves": (u_leaves * (4.0 + 4 + 2 + 32) + 4.0 * int(info0.dag_words[2] if leaf else 0), main_phase["emit_leaves"]),
         }
         dom = max(kernels, key=lambda k: kernels[k][1])
@@ -475,7 +481,7 @@ def run_own(args):
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "top_kernel_traffic.json")
         if os.path.exists(tpath) and n == 16384 and args.kind == "terrain" and world == 1:
-            names = {"leaves": "buildLeavesKernel", "leaf_insert": "insertLeavesKernel", "emit_leaves": "emitLeavesKernel",
+            names = {"leaves": "buildLeafColumnsKernel" if per_column else "buildLeavesKernel", "leaf_insert": "insertLeavesKernel", "emit_leaves": "emitLeavesKernel",
                      "pyramid_base": "pyramidBaseKernel<0>"}
             with open(tpath) as f:
                 traffic = json.load(f)["dram_bytes_per_launch"].get(names[dom])

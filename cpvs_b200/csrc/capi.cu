@@ -88,7 +88,7 @@ struct cpvs_ctx {
 	// which therefore run next to the following levels' inserts.
 	cudaStream_t aux2, aux3;  // the ranks of different levels are independent: alternate between the two
 	cudaEvent_t evRankStart, evRankStop, evJoin3, evClear, evCols;
-	bool leafColumns;  // leaves built per column (CPVS_LEAF_COLUMNS=0: per leaf, the older kernel, kept for comparison)
+	int leafColumns;  // leaves built per column: 1 = where it pays (default), 0 = never, 2 = always (CPVS_LEAF_COLUMNS; tests)
 };
 
 struct cpvs_minmax {
@@ -237,7 +237,7 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 	ctx->evRankStart = ctx->evRankStop = ctx->evJoin3 = ctx->evClear = ctx->evCols = nullptr;
 	{
 		const char* v = std::getenv("CPVS_LEAF_COLUMNS");
-		ctx->leafColumns = !(v && v[0] == '0');
+		ctx->leafColumns = (v && v[0] >= '0' && v[0] <= '2') ? v[0] - '0' : 1;
 	}
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux2, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux3, cudaStreamNonBlocking);
@@ -644,7 +644,13 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	u32* dSketch = nullptr;
 	const bool needSketch = useLeaf && lv[2].n > 0, haveLeaves = useLeaf && lv[2].n > 1;
 	// leaves per column: one more scan (over the columns = texels of pyramid level 3)
-	const bool leafColumns = needSketch && ctx->leafColumns;
+	// Where it pays: whole-volume builds with 2..8 leaves per column (terrain-like surfaces; measured at 16K^2: terrain 0.42 ms
+	// against 0.50 ms per leaf). A z-slice of a tall grid leaves most columns empty; box edges make columns of hundreds of
+	// leaves that a four-lane group walks alone (16K^2 city: 6.1 ms against 2.9 ms); a gentle plane has one leaf per column
+	// and nothing to share (0.30 ms against 0.27 ms): those keep the per-leaf kernel.
+	const u64 allCols = ((u64)mm->n >> 3) * ((u64)mm->n >> 3);
+	const bool leafColumns = needSketch && (ctx->leafColumns == 2 || (ctx->leafColumns == 1 && zTileNum == 1 && lv[2].n >= 2 * allCols &&
+																   lv[2].n <= 8 * allCols));
 	const u64 numCols = leafColumns ? ((u64)mm->n >> 3) * ((u64)mm->n >> 3) : 0;
 	u32* dColBias = nullptr;
 	if (leafColumns) {
@@ -679,7 +685,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 			if (l < smallLow) a.sizeOf = ar.take<unsigned char>(a.n + 4);
 			if (useLeaf && l == 2) {
 				a.leafCodes = ar.take<u32>(a.n * 8);
-				a.leafHash = ar.take<u64>(a.n);
+				if (!leafColumns) a.leafHash = ar.take<u64>(a.n);
 			} else {
 				a.firstChild = ar.take<u32>(a.n);
 			}
@@ -780,8 +786,8 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	}
 	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAVES], st));
 	if (leafColumns)  // constructLastLevels (src/CompressedShadow.cpp:171-190)
-		ctx->launches += launchBuildLeafColumns(pyr, zTileIndex, zTileNum, dColBias, lv[2].leafAt, (u32)lv[2].n, lv[2].leafCodes, lv[2].leafHash,
-				lv[2].masks, dSketch, st);
+		ctx->launches += launchBuildLeafColumns(pyr, zTileIndex, zTileNum, dColBias, lv[2].leafAt, (u32)lv[2].n, lv[2].leafCodes, lv[2].masks,
+				dSketch, st);
 	else if (useLeaf && lv[2].n)
 		ctx->launches += launchBuildLeaves(pyr, zTileNum, lv[2].coords, lv[2].n, lv[2].leafCodes, lv[2].leafHash, lv[2].masks,
 				dSketch, st);

@@ -74,8 +74,9 @@ int launchBuildLeaves(const PyramidView& pyr, u32 zTileNum, const u64* coords, u
 // z-block of c; one look-back scan over pyramid level 3. leafAt[colBias[c] + zb] = index of leaf (c, zb) in the
 // level, written by the expansion of level 3.
 int launchColumnBias(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, u32* colBias, ScanLaunch scan, cudaStream_t stream);
+// (No hash array: the insert derives its hash from the code when MergeLevelArgs::leafHash is NULL.)
 int launchBuildLeafColumns(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, const u32* colBias, const u32* leafAt, u32 numLeaves, u32* codes,
-		u64* hashes, u16* masks, u32* sketch, cudaStream_t stream);
+		u16* masks, u32* sketch, cudaStream_t stream);
 int launchSketchPopcount(const u32* sketch, u64* setBits, cudaStream_t stream);
 
 // ---- merge.cu: mergeCommonSubtrees (reference src/CompressedShadow.cpp:215-304, Util.h:154-182) ----
@@ -85,7 +86,7 @@ struct MergeLevelArgs {
 	u64 n;                 // nodes in this level
 	int leaf;              // 1: level of leafmask nodes
 	const u32* leafCodes;  // leaf: k-code, 8 words per node
-	const u64* leafHash;   // leaf: content hash per node
+	const u64* leafHash;   // leaf: content hash per node, or NULL (then computed from the code)
 	const u16* masks;      // inner: childmask per node
 	const u32* firstChild; // inner: index of first child in the level below
 	const u32* childUid;   // inner: unique id of every node of the level below

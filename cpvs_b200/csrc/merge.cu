@@ -85,7 +85,17 @@ __global__ void __launch_bounds__(256) insertLeavesKernel(const u32* __restrict_
 	// own code and hash are fetched up front so that their latency overlaps the first table probe
 	const uint4* mine = reinterpret_cast<const uint4*>(codes + j * 8);
 	const uint4 a0 = __ldcs(mine), a1 = __ldcs(mine + 1);
-	const u64 hash = __ldcs(hashes + j);
+	u64 hash;
+	if (hashes) {
+		hash = __ldcs(hashes + j);
+	} else {
+		u64 h = 0x9E3779B97F4A7C15ull;
+		h = (h ^ (((u64)a0.y << 32) | a0.x)) * 0xFF51AFD7ED558CCDull;
+		h = (h ^ (h >> 32) ^ (((u64)a0.w << 32) | a0.z)) * 0xC4CEB9FE1A85EC53ull;
+		h = (h ^ (h >> 32) ^ (((u64)a1.y << 32) | a1.x)) * 0xFF51AFD7ED558CCDull;
+		h = (h ^ (h >> 32) ^ (((u64)a1.w << 32) | a1.z)) * 0xC4CEB9FE1A85EC53ull;
+		hash = mix64(h);
+	}
 	slotOf[j] = findGroupSlot(table, tableMask, hash, (u32)j, errorFlag, [&](u32 other) {
 		const uint4* theirs = reinterpret_cast<const uint4*>(codes + (u64)other * 8);
 		const uint4 b0 = theirs[0], b1 = theirs[1];

@@ -8,6 +8,8 @@
 // child counts across the whole level in the same pass (decoupled look-back) and writes the next
 // level's coordinate list in the reference's order: parent order, then child index x | y<<1 | z<<2.
 // Leaves (level 2) are built by eight lanes per node straight from the depth map.
+#include <cuda_fp16.h>
+
 #include "kernels.h"
 
 namespace cpvs {
@@ -80,13 +82,28 @@ __global__ void __launch_bounds__(256) countNodesKernel(CountLevels p, u64* __re
 	const u64 numTexels = p.numTexels[level];
 	const float heightF = p.heightF[level], zLoF = p.zLoF[level], zHiF = p.zHiF[level];
 	u64 local = 0;
-	for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < numTexels; i += (u64)gridDim.x * blockDim.x) {
-		const float2 t = texels[i];
-		const float a = __fmul_rn(t.x, heightF), b = __fmul_rn(t.y, heightF);
+	// two texels per 128-bit load (every counted level has an even number of texels), two loads in flight per thread
+	const float4* __restrict__ pairs = reinterpret_cast<const float4*>(texels);
+	const u64 numPairs = numTexels >> 1, stride = (u64)gridDim.x * blockDim.x;
+	auto add = [&](float mn, float mx) {
+		const float a = __fmul_rn(mn, heightF), b = __fmul_rn(mx, heightF);
 		// fmaxf/fminf drop a NaN operand: a NaN bound makes every z of the tile PARTIAL, as in the reference
 		const float lo = fmaxf(floorf(a), zLoF);
 		const float hi = fminf(__fadd_rn(ceilf(b), -1.0f), zHiF);
 		if (hi >= lo) local += (u64)(hi - lo) + 1ull;
+	};
+	u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	for (; i + stride < numPairs; i += 2 * stride) {
+		const float4 t = pairs[i], u = pairs[i + stride];
+		add(t.x, t.y);
+		add(t.z, t.w);
+		add(u.x, u.y);
+		add(u.z, u.w);
+	}
+	if (i < numPairs) {
+		const float4 t = pairs[i];
+		add(t.x, t.y);
+		add(t.z, t.w);
 	}
 #pragma unroll
 	for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, d);
@@ -360,91 +377,206 @@ __global__ void __launch_bounds__(kScanThreads) columnBiasKernel(const float2* _
 	}
 }
 
-// litCountBits with q = depth * H0 already formed and nzc8 = -(z0 - 0.5) / 8.
-__device__ __forceinline__ u32 litCountBitsQ(float q, float nzc8) {
-	float s;
-	asm("fma.rm.sat.f32 %0, %1, 0f3E000000, %2;" : "=f"(s) : "f"(q), "f"(nzc8));
-	return (u32)__float_as_int(__fmaf_rd(s, 8.0f, 8388608.0f));  // 0x4B000000 + k
+// Lit slices of a texel, counted from slice 0 of the whole volume: slice z is lit iff z + 0.5 <= q with q = fl(depth * H0)
+// (absoluteVisible), so T = floor(q + 0.5) of them are -- the sum rounded toward -inf never crosses an integer, and NaN
+// ends up as 0 (never lit, as midZ <= NaN is false). A leaf at z-block zb then has k = clamp(T - 8 zb, 0, 8).
+__device__ __forceinline__ float litSlicesBelow(float q) { return floorf(__fadd_rd(q, 0.5f)); }
+
+// Four lanes per column, lane `sub` owns depth rows 2*sub and 2*sub+1. Per texel the lane keeps
+// R = clamp(T - 8 * (first z-block of the chunk), 0, 2040) as an fp16 integer, two texels (x, x+4) per half2 register; a
+// leaf's nibbles are then k = 8 * sat(R / 8 - i) for its block i inside the chunk -- two HFMA2 per texel pair, all exact
+// (multiples of 1/8 below 256) -- and adding 1024 leaves k in the low bits of each half, so three shift-adds pack a row
+// word. Chunks are 252 z-blocks (8 * 252 + 8 <= 2040); taller columns (box edges) re-base R per chunk.
+// The column's leaves are walked in batches of four: every lane stores its two row words of each leaf (4 lanes x 8 bytes =
+// the leaf's 32-byte k-code), the 64-bit content hash is a sum of per-lane products folded by two shuffles, and lane j
+// finishes the j-th leaf of the batch (hash, 1x1x8 mask, sketch bit).
+constexpr int kColumnsPerCta = 64;
+constexpr u32 kChunkBlocks = 252;
+constexpr u32 kNoLeaf = 0xFFFFFFFFu;
+
+struct LeafColumn {  // per lane
+	float lo;        // first z-block of the column
+	u32 cnt;         // z-blocks (leaves) of the column
+	u32 first;       // column-order position of the column's first leaf
+	float tMin, tMax;
+};
+struct LeafSink {
+	const u32* __restrict__ leafAt;
+	u32 numLeaves;
+	u32* __restrict__ codes;
+	u16* __restrict__ masks;
+	u32* __restrict__ bitmap;
+	u32 bitmapWordMask;
+};
+// Distinct-count sketch update whose read is in flight: the bit is tested (and set if need be) when the next leaf of the
+// lane comes along, so nobody waits for the random read. (Read first: on repetitive maps nearly every leaf finds its bit
+// already set, and the atomics of a popular hash would otherwise serialise on one address.)
+struct PendingSketch {
+	u32* word = nullptr;
+	u32 bit = 0, seen = 0;
+	__device__ __forceinline__ void flush() {
+		if (word && !(seen & bit)) atomicOr(word, bit);
+		word = nullptr;
+	}
+	__device__ __forceinline__ void post(u32* w, u32 b) {
+		flush();
+		word = w;
+		bit = b;
+		seen = __ldcg(w);
+	}
+};
+
+// R of the lane's two rows for the chunk starting at z-block `zb0`: clamp(floor(q + 0.5) - 8 zb0, 0, 2040). The sum
+// q + (0.5 - 8 zb0) is rounded toward -inf (the addend is exact: 8 zb0 < 2^23), which never crosses an integer, so the floor is
+// that of the exact value; the clamps run on the packed halves (below 2048 the conversion is exact, above it stays above 2040,
+// NaN is dropped by max(.,0): never lit, as midZ <= NaN is false).
+__device__ __forceinline__ void rowsToR(const Float8& a, const Float8& b, float heightF, float zb0, __half2 (&r0)[4], __half2 (&r1)[4]) {
+	const float shift = __fsub_rn(0.5f, __fmul_rn(zb0, 8.0f));
+	const __half2 zero2 = __float2half2_rn(0.f), cap2 = __float2half2_rn(2040.f);
+#pragma unroll
+	for (int p = 0; p < 4; ++p) {
+		const float x0 = floorf(__fadd_rd(__fmul_rn(a.v[p], heightF), shift)), x1 = floorf(__fadd_rd(__fmul_rn(a.v[p + 4], heightF), shift));
+		const float y0 = floorf(__fadd_rd(__fmul_rn(b.v[p], heightF), shift)), y1 = floorf(__fadd_rd(__fmul_rn(b.v[p + 4], heightF), shift));
+		r0[p] = __hmin2(__hmax2(__floats2half2_rn(x0, x1), zero2), cap2);
+		r1[p] = __hmin2(__hmax2(__floats2half2_rn(y0, y1), zero2), cap2);
+	}
 }
 
-// Four lanes per column, lane `sub` owns depth rows 2*sub and 2*sub+1 (two 256-bit loads; a warp instruction
-// covers eight x-adjacent columns = four rows of 256 contiguous bytes). The column's leaves are walked in
-// batches of four: every lane forms its two row words of each leaf and stores them (8 lanes-bytes x 4 = the
-// leaf's 32-byte k-code), the 64-bit content hash is a sum of per-lane products folded by two shuffles, and
-// lane j finishes the j-th leaf of the batch (hash, 1x1x8 mask, sketch bit).
-constexpr int kColumnsPerCta = 64;
-__global__ void __launch_bounds__(256) buildLeafColumnsKernel(const float* __restrict__ depth, u32 n, u32 colShift, float heightF,
-		float height3F, float zLoF, float zHiF, const float2* __restrict__ level3, u32 numCols, const u32* __restrict__ colBias,
-		const u32* __restrict__ leafAt, u32 numLeaves, u32* __restrict__ codes, u64* __restrict__ hashes, u16* __restrict__ masks,
-		u32* __restrict__ bitmap, u32 bitmapWordMask) {
-	const u32 lane = threadIdx.x & 31u, sub = lane & 3u;
-	const u32 col = blockIdx.x * kColumnsPerCta + (threadIdx.x >> 2);
-	float lo = 0.f;
-	u32 cnt = 0;
-	float2 mm = make_float2(0.f, 0.f);
-	if (col < numCols) {
-		mm = level3[col];
-		columnRange(mm, height3F, zLoF, zHiF, lo, cnt);
-	}
-	const u32 maxCnt = __reduce_max_sync(0xFFFFFFFFu, cnt);
-	if (maxCnt == 0) return;
-	float q0[8], q1[8];
-	u32 first = 0;  // column-order position of the column's first leaf
-	if (cnt) {
-		const u32 cx = col & ((1u << colShift) - 1u), cy = col >> colShift;
-		const float* p = depth + (size_t)(cy * 8u + sub * 2u) * n + cx * 8u;
-		const Float8 a = ldSector256(p), b = ldSector256(p + n);
-		first = colBias[col] + (u32)lo;
-#pragma unroll
-		for (int t = 0; t < 8; ++t) {
-			q0[t] = __fmul_rn(a.v[t], heightF);
-			q1[t] = __fmul_rn(b.v[t], heightF);
+__constant__ u64 kLaneHashMul[4] = {0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull, 0xD6E8FEB86659FD93ull};
+
+// The leaves chunk..chunkEnd-1 (warp-uniform bounds) of the eight columns of a warp. firstIdx: leafAt of the lane's leaf of
+// the very first batch if the caller fetched it ahead (only looked at for chunk == 0).
+__device__ __forceinline__ void emitColumnLeaves(const LeafColumn& c, const __half2 (&r0)[4], const __half2 (&r1)[4], u32 chunk, u32 chunkEnd,
+		u32 firstIdx, bool haveFirstIdx, const LeafSink& out, PendingSketch& pending) {
+	const u32 lane = threadIdx.x & 31u, sub = lane & 3u, groupLane = lane & ~3u;
+	const u64 mulK = kLaneHashMul[sub];
+	const __half2 eighth2 = __float2half2_rn(0.125f), eight2 = __float2half2_rn(8.0f), bias2 = __float2half2_rn(1024.0f),
+				  one2 = __float2half2_rn(1.0f);
+	constexpr u32 kStrip = 0x64006400u * 0x1111u;  // the fp16 bits of 1024 under all eight nibbles of a row word
+	__half2 negI2 = __float2half2_rn(0.f);         // -(block index inside the chunk)
+	for (u32 m = chunk; m < chunkEnd; m += 4) {
+		u32 mineIdx = kNoLeaf;
+		if (haveFirstIdx && m == 0) {
+			mineIdx = firstIdx;
+		} else if (m + sub < c.cnt && c.first + m + sub < out.numLeaves) {
+			mineIdx = out.leafAt[c.first + m + sub];
 		}
-	} else {
-#pragma unroll
-		for (int t = 0; t < 8; ++t) q0[t] = q1[t] = 0.f;
-	}
-	const float qMin = __fmul_rn(mm.x, heightF), qMax = __fmul_rn(mm.y, heightF);
-	const u64 mulK = mix64(0x9E3779B97F4A7C15ull * (sub + 1u)) | 1ull, xorK = mix64(0xD6E8FEB86659FD93ull + sub);
-	const u32 groupLane = lane & ~3u;
-	for (u32 m = 0; m < maxCnt; m += 4) {
-		u32 mineIdx = 0xFFFFFFFFu;
-		if (m + sub < cnt && first + m + sub < numLeaves) {
-			mineIdx = leafAt[first + m + sub];
-			if (mineIdx >= numLeaves) mineIdx = 0xFFFFFFFFu;  // cannot happen on an ordered pyramid (see the expansion)
-		}
-		u64 keep = 0;
+		if (mineIdx >= out.numLeaves) mineIdx = kNoLeaf;  // cannot happen on an ordered pyramid (see the expansion)
+		u64 hp[4] = {0, 0, 0, 0};
 #pragma unroll
 		for (u32 j = 0; j < 4; ++j) {
+			if (m + j >= chunkEnd) break;  // warp-uniform
 			const u32 leaf = __shfl_sync(0xFFFFFFFFu, mineIdx, groupLane + j);
-			const float nzc8 = __fsub_rn(0.0625f, __fadd_rn(lo, __uint2float_rn(m + j)));  // -(8 zb - 0.5) / 8, exact
 			u32 w0 = 0, w1 = 0;
 #pragma unroll
-			for (int t = 7; t >= 0; --t) {
-				w0 = w0 * 16u + litCountBitsQ(q0[t], nzc8);
-				w1 = w1 * 16u + litCountBitsQ(q1[t], nzc8);
+			for (int p = 3; p >= 0; --p) {
+				const __half2 y0 = __hfma2(__hfma2_sat(r0[p], eighth2, negI2), eight2, bias2);
+				const __half2 y1 = __hfma2(__hfma2_sat(r1[p], eighth2, negI2), eight2, bias2);
+				w0 = w0 * 16u + *reinterpret_cast<const u32*>(&y0);
+				w1 = w1 * 16u + *reinterpret_cast<const u32*>(&y1);
 			}
-			w0 -= 0x4B000000u * 0x11111111u;  // strips the float exponent bits of all eight terms
-			w1 -= 0x4B000000u * 0x11111111u;
-			if (leaf != 0xFFFFFFFFu) *reinterpret_cast<uint2*>(codes + (u64)leaf * 8u + sub * 2u) = make_uint2(w0, w1);
-			u64 hp = (((((u64)w1) << 32) | w0) ^ xorK) * mulK;
-			hp += __shfl_xor_sync(0xFFFFFFFFu, hp, 1);
-			hp += __shfl_xor_sync(0xFFFFFFFFu, hp, 2);
-			if (j == sub) keep = hp;
+			w0 -= kStrip;
+			w1 -= kStrip;
+			negI2 = __hsub2(negI2, one2);
+			if (leaf != kNoLeaf) *reinterpret_cast<uint2*>(out.codes + (u64)leaf * 8u + sub * 2u) = make_uint2(w0, w1);
+			hp[j] = ((((u64)w1) << 32) | w0) * mulK;
 		}
-		if (mineIdx != 0xFFFFFFFFu) {
+		// lane `sub` ends up with the sum over the four lanes of hp[sub]: a 4 x 4 reduce-scatter in two exchanges
+		const bool hi = (sub & 2u) != 0, odd = (sub & 1u) != 0;
+		const u64 k0 = (hi ? hp[2] : hp[0]) + __shfl_xor_sync(0xFFFFFFFFu, hi ? hp[0] : hp[2], 2);
+		const u64 k1 = (hi ? hp[3] : hp[1]) + __shfl_xor_sync(0xFFFFFFFFu, hi ? hp[1] : hp[3], 2);
+		const u64 keep = (odd ? k1 : k0) + __shfl_xor_sync(0xFFFFFFFFu, odd ? k0 : k1, 1);
+		if (mineIdx != kNoLeaf) {
 			const u64 h = mix64(keep);
-			const float nzc8 = __fsub_rn(0.0625f, __fadd_rn(lo, __uint2float_rn(m + sub)));
-			const u32 kmin = litCountBitsQ(qMin, nzc8) & 15u, kmax = litCountBitsQ(qMax, nzc8) & 15u;
+			const float z8 = __fmul_rn(__fadd_rn(c.lo, __uint2float_rn(m + sub)), 8.0f);
+			const u32 kmin = (u32)fminf(fmaxf(__fsub_rn(c.tMin, z8), 0.f), 8.f), kmax = (u32)fminf(fmaxf(__fsub_rn(c.tMax, z8), 0.f), 8.f);
 			// slices below kmin are lit (01), slices from kmax up are shadowed (00), the rest PARTIAL (10)
 			const u32 below = (1u << (2u * kmin)) - 1u;
-			masks[mineIdx] = (u16)((0x5555u & below) | (0xAAAAu & ((1u << (2u * kmax)) - 1u) & ~below));
-			hashes[mineIdx] = h;
+			out.masks[mineIdx] = (u16)((0x5555u & below) | (0xAAAAu & ((1u << (2u * kmax)) - 1u) & ~below));
+			// the hash only feeds the sketch here: the insert recomputes its own from the code it reads anyway, which is
+			// cheaper than 8-byte stores scattered over the level (partial sectors: a fill and a write-back each)
 			const u32 bit = (u32)(h >> 20);
-			u32* word = bitmap + ((bit >> 5) & bitmapWordMask);
-			if (!(__ldcg(word) & (1u << (bit & 31u)))) atomicOr(word, 1u << (bit & 31u));
+			pending.post(out.bitmap + ((bit >> 5) & out.bitmapWordMask), 1u << (bit & 31u));
 		}
 	}
+}
+
+// Persistent warps, each walking groups of eight x-adjacent columns (two 256-bit loads per lane; a warp instruction covers
+// four rows of 256 contiguous bytes), software-pipelined in registers so that no load is waited for: a group's level-3
+// texel and colBias are fetched two groups ahead; its depth rows and the leafAt of its first batch one group ahead, and only
+// if the column has leaves (most columns of a z-slice of a tall grid have none). Warps never synchronise with each other.
+__global__ void __launch_bounds__(256, 3) buildLeafColumnsKernel(const float* __restrict__ depth, u32 n, u32 colShift, float heightF,
+		float height3F, float zLoF, float zHiF, const float2* __restrict__ level3, u32 numCols, const u32* __restrict__ colBias, LeafSink out) {
+	const u32 lane = threadIdx.x & 31u, sub = lane & 3u;
+	const u32 numWarps = gridDim.x * (blockDim.x >> 5), numGroups = (numCols + 7u) >> 3;
+	u32 group = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	PendingSketch pending;
+
+	// stage 2 (two groups ahead): level-3 texel and bias
+	float2 mm2 = make_float2(0.f, 0.f);
+	u32 bias2 = 0;
+	auto fetchTexel = [&](u32 g) {
+		const u32 col = g * 8u + (lane >> 2);
+		mm2 = make_float2(0.f, 0.f);  // an empty column (lo > hi)
+		bias2 = 0;
+		if (g < numGroups && col < numCols) {
+			mm2 = level3[col];
+			bias2 = colBias[col];
+		}
+	};
+	// stage 1 (one group ahead): column range, depth rows, first leafAt batch
+	LeafColumn c1;
+	float2 mm1 = make_float2(0.f, 0.f);
+	Float8 a1, b1;
+	u32 idx1 = kNoLeaf;
+	auto fetchRows = [&](u32 g) {  // consumes stage 2
+		mm1 = mm2;
+		c1.lo = 0.f;
+		c1.cnt = 0;
+		const u32 col = g * 8u + (lane >> 2);
+		if (g < numGroups && col < numCols) columnRange(mm1, height3F, zLoF, zHiF, c1.lo, c1.cnt);
+		c1.first = bias2 + (u32)c1.lo;
+		idx1 = kNoLeaf;
+		if (c1.cnt) {
+			const u32 cx = col & ((1u << colShift) - 1u), cy = col >> colShift;
+			const float* p = depth + (size_t)(cy * 8u + sub * 2u) * n + cx * 8u;
+			a1 = ldSector256(p);
+			b1 = ldSector256(p + n);
+			if (sub < c1.cnt && c1.first + sub < out.numLeaves) idx1 = out.leafAt[c1.first + sub];
+		}
+	};
+	fetchTexel(group);
+	fetchRows(group);
+	fetchTexel(group + numWarps);
+	for (; group < numGroups; group += numWarps) {
+		// stage 0: this group. Its rows become R right away so that the row registers can take the next group's loads.
+		LeafColumn c = c1;
+		c.tMin = litSlicesBelow(__fmul_rn(mm1.x, heightF));
+		c.tMax = litSlicesBelow(__fmul_rn(mm1.y, heightF));
+		const u32 firstIdx = idx1;
+		const u32 maxCnt = __reduce_max_sync(0xFFFFFFFFu, c.cnt);
+		__half2 r0[4], r1[4];
+		if (c.cnt) {
+			rowsToR(a1, b1, heightF, c.lo, r0, r1);
+		} else {
+#pragma unroll
+			for (int p = 0; p < 4; ++p) r0[p] = r1[p] = __float2half2_rn(0.f);
+		}
+		fetchRows(group + numWarps);
+		fetchTexel(group + 2u * numWarps);
+		if (maxCnt == 0) continue;
+		emitColumnLeaves(c, r0, r1, 0, min(maxCnt, kChunkBlocks), firstIdx, true, out, pending);
+		for (u32 chunk = kChunkBlocks; chunk < maxCnt; chunk += kChunkBlocks) {  // tall columns (box edges): re-read the rows
+			if (c.cnt) {
+				const u32 col = group * 8u + (lane >> 2);
+				const u32 cx = col & ((1u << colShift) - 1u), cy = col >> colShift;
+				const float* p = depth + (size_t)(cy * 8u + sub * 2u) * n + cx * 8u;
+				rowsToR(ldSector256(p), ldSector256(p + n), heightF, __fadd_rn(c.lo, __uint2float_rn(chunk)), r0, r1);
+			}
+			emitColumnLeaves(c, r0, r1, chunk, min(maxCnt, chunk + kChunkBlocks), kNoLeaf, false, out, pending);
+		}
+	}
+	pending.flush();
 }
 
 // Number of set bits of the sketch -> *setBits (zeroed beforehand).
@@ -552,13 +684,17 @@ int launchColumnBias(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, u32* 
 }
 
 int launchBuildLeafColumns(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, const u32* colBias, const u32* leafAt, u32 numLeaves, u32* codes,
-		u64* hashes, u16* masks, u32* sketch, cudaStream_t stream) {
+		u16* masks, u32* sketch, cudaStream_t stream) {
 	const u32 side3 = (u32)pyr.n >> 3, numCols = side3 * side3;
 	u32 colShift = 0;
 	while ((1u << colShift) < side3) ++colShift;
-	buildLeafColumnsKernel<<<(numCols + kColumnsPerCta - 1) / kColumnsPerCta, 256, 0, stream>>>(pyr.level[0], (u32)pyr.n, colShift,
-			(float)((u32)pyr.n * zTileNum), (float)(side3 * zTileNum), (float)(zTileIndex * side3), (float)(zTileIndex * side3 + side3 - 1),
-			reinterpret_cast<const float2*>(pyr.level[3]), numCols, colBias, leafAt, numLeaves, codes, hashes, masks, sketch, kSketchWords - 1);
+	const float heightF = (float)((u32)pyr.n * zTileNum), height3F = (float)(side3 * zTileNum);
+	const float zLoF = (float)(zTileIndex * side3), zHiF = (float)(zTileIndex * side3 + side3 - 1);
+	const float2* level3 = reinterpret_cast<const float2*>(pyr.level[3]);
+	LeafSink out{leafAt, numLeaves, codes, masks, sketch, kSketchWords - 1};
+	const u32 wanted = (numCols + kColumnsPerCta - 1) / kColumnsPerCta;  // 8 warps of 8 columns per CTA
+	buildLeafColumnsKernel<<<wanted < 148u * 3u ? wanted : 148u * 3u, 256, 0, stream>>>(pyr.level[0], (u32)pyr.n, colShift, heightF, height3F,
+			zLoF, zHiF, level3, numCols, colBias, out);
 	return 1;
 }
 

@@ -7,6 +7,7 @@ from cpvs_b200 import synth
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 mode = sys.argv[2] if len(sys.argv) > 2 else "own"
+kind = sys.argv[3] if len(sys.argv) > 3 else "terrain"
 if mode == "own":
     ctx = cpvs_b200.Context(0)
 elif mode == "legacy":
@@ -16,7 +17,7 @@ else:
     torch.cuda.set_stream(s)
     ctx = cpvs_b200.Context(0, stream=s.cuda_stream)
 print("mode", mode, "stream", torch.cuda.current_stream().cuda_stream, file=sys.stderr)
-d = torch.from_numpy(synth.depth_map("terrain", n)).cuda()
+d = torch.from_numpy(synth.depth_map(kind, n)).cuda()
 torch.cuda.synchronize()
 for i in range(4):
     print("--- step", i, file=sys.stderr)

@@ -520,3 +520,29 @@ def test_reserve_and_kept_dags(gpu_ctx, oracle):
         kept.append((g, oracle.Shadow(oracle.MinMax(d))))
     for g, o in kept:
         _assert_same_dag(g, o, "kept")
+
+
+# ---- leaves built per column (svo.cu buildLeafColumnsKernel) -------------------------------------------
+
+@pytest.mark.parametrize("mode", ["0", "2"])
+def test_leaf_kernels_forced(oracle, mode, monkeypatch):
+    """Both leaf builders on everything: CPVS_LEAF_COLUMNS=2 forces the per-column kernel onto the cases the default
+    heuristic keeps away from it (columns of hundreds of leaves that cross the 252-block chunks, z-slices with mostly empty
+    columns, a 2x2-column map), =0 forces the per-leaf kernel onto smooth surfaces. Same words either way."""
+    monkeypatch.setenv("CPVS_LEAF_COLUMNS", mode)
+    ctx = cpvs_b200.Context(0)  # the switch is read when the context is created
+    rng = np.random.default_rng(5)
+    cases = [("terrain", synth.depth_map("terrain", 512), 0, 1), ("plane", synth.depth_map("plane", 256), 0, 1),
+             ("city", synth.depth_map("city", 1024), 0, 1), ("city z1/2", synth.depth_map("city", 512), 1, 2),
+             ("terrain z2/4", synth.depth_map("terrain", 256), 2, 4), ("random 16", rng.random((16, 16), dtype=np.float32), 0, 1),
+             ("random 128", rng.random((128, 128), dtype=np.float32), 0, 1)]
+    wall = np.full((4096, 4096), 0.97, np.float32)  # a cliff: columns of ~450 leaves, in x- and in y-direction
+    wall[:, 2001:] = 0.05
+    wall[3000:, :] = 0.5
+    wall += (rng.random((4096, 4096), dtype=np.float32) * np.float32(1e-3))
+    cases.append(("cliff", wall, 0, 1))
+    for tag, d, zt, zn in cases:
+        mm = cpvs_b200.MinMaxHierarchy(d, ctx)
+        g = cpvs_b200.CompressedShadow.create(mm, zt, zn)
+        o = oracle.Shadow(oracle.MinMax(d), zt, zn)
+        _assert_same_dag(g, o, (mode, tag))
