@@ -207,16 +207,31 @@ __global__ void __launch_bounds__(kScanThreads, 8) rankCountKernel(const u64* __
 	}
 }
 
-// Exclusive prefix sums of the tile totals, in place; one CTA.
-__global__ void __launch_bounds__(1024) rankScanTilesKernel(ScanTileState* __restrict__ tiles, u32 numTiles, u64* __restrict__ uniqueCount,
+// Exclusive prefix sums of the tile totals, in place; one CTA. Every thread owns a contiguous chunk of tiles and fetches it
+// whole before anything is added up, so the kernel pays one memory round trip however many tiles there are (a loop of
+// 1024-tile rounds paid one per round: 54 us for the 13.6 K tiles of the 16K^2 terrain's leaf level).
+constexpr int kScanChunk = 16, kScanTilesThreads = 512;  // 8 K tiles per pass
+__global__ void __launch_bounds__(kScanTilesThreads) rankScanTilesKernel(ScanTileState* __restrict__ tiles, u32 numTiles, u64* __restrict__ uniqueCount,
 		u64* __restrict__ wordCount) {
 	__shared__ u64 sA[32], sB[32];
 	const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	u64 carryA = 0, carryB = 0;
-	for (u32 base = 0; base < numTiles; base += 1024) {
-		const u32 t = base + threadIdx.x;
-		const u64 a = t < numTiles ? tiles[t].a : 0, b = t < numTiles ? tiles[t].b : 0;
-		u64 ia = a, ib = b;
+	for (u32 base = 0; base < numTiles; base += (u32)kScanTilesThreads * kScanChunk) {
+		const u32 first = base + threadIdx.x * kScanChunk;
+		u64 a[kScanChunk], b[kScanChunk];
+#pragma unroll
+		for (int i = 0; i < kScanChunk; ++i) {
+			const bool live = first + i < numTiles;
+			a[i] = live ? tiles[first + i].a : 0;
+			b[i] = live ? tiles[first + i].b : 0;
+		}
+		u64 sumA = 0, sumB = 0;
+#pragma unroll
+		for (int i = 0; i < kScanChunk; ++i) {
+			sumA += a[i];
+			sumB += b[i];
+		}
+		u64 ia = sumA, ib = sumB;
 #pragma unroll
 		for (int d = 1; d < 32; d <<= 1) {
 			const u64 ua = __shfl_up_sync(0xFFFFFFFFu, ia, d), ub = __shfl_up_sync(0xFFFFFFFFu, ib, d);
@@ -232,7 +247,7 @@ __global__ void __launch_bounds__(1024) rankScanTilesKernel(ScanTileState* __res
 		__syncthreads();
 		u64 offA = 0, offB = 0, totA = 0, totB = 0;
 #pragma unroll
-		for (u32 w = 0; w < 32; ++w) {
+		for (u32 w = 0; w < kScanTilesThreads / 32; ++w) {
 			if (w < warp) {
 				offA += sA[w];
 				offB += sB[w];
@@ -241,9 +256,15 @@ __global__ void __launch_bounds__(1024) rankScanTilesKernel(ScanTileState* __res
 			totB += sB[w];
 		}
 		__syncthreads();
-		if (t < numTiles) {
-			tiles[t].a = carryA + offA + ia - a;
-			tiles[t].b = carryB + offB + ib - b;
+		u64 runA = carryA + offA + ia - sumA, runB = carryB + offB + ib - sumB;
+#pragma unroll
+		for (int i = 0; i < kScanChunk; ++i) {
+			if (first + i < numTiles) {
+				tiles[first + i].a = runA;
+				tiles[first + i].b = runB;
+			}
+			runA += a[i];
+			runB += b[i];
 		}
 		carryA += totA;
 		carryB += totB;
@@ -417,7 +438,7 @@ int launchRankLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaStream_t strea
 	if (a.n == 1) return 0;  // done by launchInsertLevel
 	const u32 tiles = (u32)((a.n + kScanTile - 1) / kScanTile);
 	rankCountKernel<<<tiles, kScanThreads, 0, stream>>>(a.table, a.masks, a.leaf, a.n, a.uid, a.sizeOf, scan.tiles);
-	rankScanTilesKernel<<<1, 1024, 0, stream>>>(scan.tiles, tiles, a.uniqueCount, a.wordCount);
+	rankScanTilesKernel<<<1, kScanTilesThreads, 0, stream>>>(scan.tiles, tiles, a.uniqueCount, a.wordCount);
 	rankWriteKernel<<<tiles, kScanThreads, 0, stream>>>(a.sizeOf, a.uid, a.n, scan.tiles, a.firstList, a.wordOffset, a.slotOffset);
 	return 3;
 }

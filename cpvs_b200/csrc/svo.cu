@@ -56,8 +56,10 @@ struct CountLevels {
 	int minLevel;
 	int topCounted;  // level of the root's children
 	u32 rootZ;       // z of the root's first child slab (2 * zTileIndex)
+	u32 blockStart[kMaxLevels + 1];  // [minLevel + i] = first block of level minLevel + i; blocks per level follow its size
 };
-// blockIdx.y picks the node level; all levels are counted by one launch.
+// All levels are counted by one launch; a level owns the blocks blockStart[level] .. blockStart[level + 1] - 1 (a grid of
+// levels x the widest level's blocks spent more time dispatching the empty blocks of the small levels than counting).
 __global__ void __launch_bounds__(256) countNodesKernel(CountLevels p, u64* __restrict__ counts) {
 	// A z-slice that misses the surface has no node below the root (most slices of a tall tile grid): every
 	// CTA sees that from the four texels under the root and leaves. CTA (0,0) also reports the root's mask,
@@ -73,18 +75,20 @@ __global__ void __launch_bounds__(256) countNodesKernel(CountLevels p, u64* __re
 			const float hi = fminf(__fadd_rn(ceilf(__fmul_rn(t.y, h)), -1.0f), zHi);
 			any |= hi >= lo;
 		}
-		if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+		if (blockIdx.x == 0 && threadIdx.x == 0)
 			counts[kRootMaskScalar] = (1ull << 32) | childmaskInner(under, 2u, h, 0u, 0u, p.rootZ);
 		if (!any) return;
 	}
-	const int level = p.minLevel + blockIdx.y;
+	int level = p.minLevel;
+	while (level < p.topCounted && blockIdx.x >= p.blockStart[level + 1]) ++level;
+	const u32 block = blockIdx.x - p.blockStart[level], blocks = p.blockStart[level + 1] - p.blockStart[level];
 	const float2* __restrict__ texels = p.texels[level];
 	const u64 numTexels = p.numTexels[level];
 	const float heightF = p.heightF[level], zLoF = p.zLoF[level], zHiF = p.zHiF[level];
 	u64 local = 0;
 	// two texels per 128-bit load (every counted level has an even number of texels), two loads in flight per thread
 	const float4* __restrict__ pairs = reinterpret_cast<const float4*>(texels);
-	const u64 numPairs = numTexels >> 1, stride = (u64)gridDim.x * blockDim.x;
+	const u64 numPairs = numTexels >> 1, stride = (u64)blocks * blockDim.x;
 	auto add = [&](float mn, float mx) {
 		const float a = __fmul_rn(mn, heightF), b = __fmul_rn(mx, heightF);
 		// fmaxf/fminf drop a NaN operand: a NaN bound makes every z of the tile PARTIAL, as in the reference
@@ -92,7 +96,7 @@ __global__ void __launch_bounds__(256) countNodesKernel(CountLevels p, u64* __re
 		const float hi = fminf(__fadd_rn(ceilf(b), -1.0f), zHiF);
 		if (hi >= lo) local += (u64)(hi - lo) + 1ull;
 	};
-	u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	u64 i = (u64)block * blockDim.x + threadIdx.x;
 	for (; i + stride < numPairs; i += 2 * stride) {
 		const float4 t = pairs[i], u = pairs[i + stride];
 		add(t.x, t.y);
@@ -635,7 +639,7 @@ int launchCountNodes(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, int m
 	p.minLevel = minLevel;
 	p.topCounted = pyr.numLevels - 3;
 	p.rootZ = zTileIndex * 2;
-	u64 maxTexels = 0;
+	u32 totalBlocks = 0;
 	for (int level = minLevel; level <= pyr.numLevels - 3; ++level) {
 		const u32 side = (u32)pyr.n >> (level + 1);
 		p.texels[level] = reinterpret_cast<const float2*>(pyr.level[level + 1]);
@@ -643,12 +647,13 @@ int launchCountNodes(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, int m
 		p.heightF[level] = (float)(side * zTileNum);
 		p.zLoF[level] = (float)(zTileIndex * side);
 		p.zHiF[level] = (float)(zTileIndex * side + side - 1);
-		if (p.numTexels[level] > maxTexels) maxTexels = p.numTexels[level];
+		u64 blocks = (p.numTexels[level] + 256 * 8 - 1) / (256 * 8);  // two passes of two 2-texel loads per thread
+		if (blocks > 148 * 8) blocks = 148 * 8;
+		p.blockStart[level] = totalBlocks;
+		totalBlocks += (u32)blocks;
 	}
-	u64 blocks = (maxTexels + 256 * 8 - 1) / (256 * 8);
-	if (blocks > 148 * 8) blocks = 148 * 8;
-	if (blocks < 1) blocks = 1;
-	countNodesKernel<<<dim3((unsigned)blocks, (unsigned)numCounted), 256, 0, stream>>>(p, counts);
+	p.blockStart[pyr.numLevels - 2] = totalBlocks;
+	countNodesKernel<<<totalBlocks, 256, 0, stream>>>(p, counts);
 	return 1;
 }
 

@@ -86,5 +86,8 @@ if rep:
         return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
     traffic = {k: to_bytes(*e["dram__bytes_read.sum"]) + to_bytes(*e["dram__bytes_write.sum"]) for k, e in summary.items()
                if "dram__bytes_read.sum" in e}
-    json.dump({"tag": tag, "dram_bytes_per_launch": traffic}, open(os.path.join(out_dir, "top_kernel_traffic.json"), "w"), indent=1)
+    tpath = os.path.join(out_dir, "top_kernel_traffic.json")
+    merged = json.load(open(tpath))["dram_bytes_per_launch"] if os.path.exists(tpath) else {}
+    merged.update(traffic)  # kernels not in this capture keep their earlier figures
+    json.dump({"tag": tag, "dram_bytes_per_launch": merged}, open(tpath, "w"), indent=1)
 print("wrote profiles for", tag)
