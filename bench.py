@@ -458,7 +458,7 @@ def run_own(args):
         u_leaves = int(info0.dag_nodes[2]) if leaf else 0
         # algorithmic (compulsory HBM) bytes per launch of the single-kernel phases -- DESIGN.md "Kernels":
         #   pyramid_base  depth read once + levels 1..5 written
-        #   leaves        per column (whole-volume builds with 2..8 leaves per column, the library's own rule): depth read once
+        #   leaves        per column (whole-volume builds of maps >= 8192^2 with 2..8 leaves per column, the library's own rule): depth read once
         #                 + per column 8 B level-3 texel and 4 B bias in + per leaf 4 B index in, 32 B k-code and 2 B mask out;
         #                 per leaf (otherwise): depth read once (L2 serves the z-block re-reads) + per leaf 8 B coordinate in,
         #                 32 B k-code, 8 B hash, 2 B mask out
@@ -466,7 +466,7 @@ def run_own(args):
         #                 representative k-code (the table itself is sized to stay in L2)
         #   emit_leaves   per unique leaf: 4 B index + 4 B offset + 2 B mask + 32 B k-code in; compressed words out
         cols = (n // 8) * (n // 8)
-        per_column = (leaf and args.z_slices == 1 and 2 * cols <= n_leaves <= 8 * cols
+        per_column = (leaf and args.z_slices == 1 and n >= 8192 and 2 * cols <= n_leaves <= 8 * cols
                       and os.environ.get("CPVS_LEAF_COLUMNS", "1") != "0") or os.environ.get("CPVS_LEAF_COLUMNS") == "2"
         leaves_bytes = (4.0 * n * n + cols * 12.0 + n_leaves * (4.0 + 32 + 2)) if per_column else (4.0 * n * n + n_leaves * (8.0 + 32 + 8 + 2))
         kernels = {

@@ -644,13 +644,14 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	u32* dSketch = nullptr;
 	const bool needSketch = useLeaf && lv[2].n > 0, haveLeaves = useLeaf && lv[2].n > 1;
 	// leaves per column: one more scan (over the columns = texels of pyramid level 3)
-	// Where it pays: whole-volume builds with 2..8 leaves per column (terrain-like surfaces; measured at 16K^2: terrain 0.42 ms
-	// against 0.50 ms per leaf). A z-slice of a tall grid leaves most columns empty; box edges make columns of hundreds of
-	// leaves that a four-lane group walks alone (16K^2 city: 6.1 ms against 2.9 ms); a gentle plane has one leaf per column
-	// and nothing to share (0.30 ms against 0.27 ms): those keep the per-leaf kernel.
+	// Where it pays: whole-volume builds with 2..8 leaves per column of a depth map that does not fit in L2 (terrain-like
+	// surfaces; measured at 16K^2: 0.42 ms against 0.50 ms per leaf, at 8192^2 0.121 against 0.137, at 4096^2 -- 64 MiB, L2
+	// serves the re-reads -- 0.046 against 0.045). A z-slice of a tall grid leaves most columns empty; box edges make columns
+	// of hundreds of leaves that a four-lane group walks alone (16K^2 city: 6.1 ms against 2.9 ms); a gentle plane has one
+	// leaf per column and nothing to share (0.30 ms against 0.27 ms): those keep the per-leaf kernel.
 	const u64 allCols = ((u64)mm->n >> 3) * ((u64)mm->n >> 3);
-	const bool leafColumns = needSketch && (ctx->leafColumns == 2 || (ctx->leafColumns == 1 && zTileNum == 1 && lv[2].n >= 2 * allCols &&
-																   lv[2].n <= 8 * allCols));
+	const bool leafColumns = needSketch && (ctx->leafColumns == 2 || (ctx->leafColumns == 1 && zTileNum == 1 && mm->n >= 8192 &&
+																   lv[2].n >= 2 * allCols && lv[2].n <= 8 * allCols));
 	const u64 numCols = leafColumns ? ((u64)mm->n >> 3) * ((u64)mm->n >> 3) : 0;
 	u32* dColBias = nullptr;
 	if (leafColumns) {
