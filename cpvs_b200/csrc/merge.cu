@@ -409,10 +409,13 @@ __global__ void singleNodeKernel(const u16* __restrict__ masks, int leaf, u32* g
 int launchMergeSmallLevels(const SmallMergeArgs& a, cudaStream_t stream) {
 	if (a.count <= 0) return 0;
 	constexpr size_t kBytes = 2 * kSmallMaxNodes * sizeof(u64);
-	static bool configured = false;  // > 48 KiB of dynamic shared memory needs the opt-in, once per process
-	if (!configured) {
+	// > 48 KiB of dynamic shared memory needs the opt-in, once per device (a process may hold one context per GPU)
+	static bool configured[64] = {false};
+	int device = 0;
+	cudaGetDevice(&device);
+	if (device < 0 || device >= 64 || !configured[device]) {
 		cudaFuncSetAttribute(mergeSmallLevelsKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBytes);
-		configured = true;
+		if (device >= 0 && device < 64) configured[device] = true;
 	}
 	mergeSmallLevelsKernel<<<1, kSmallThreads, kBytes, stream>>>(a);
 	return 1;
