@@ -38,15 +38,9 @@ __device__ __forceinline__ u32 classifyPoint(float minZ, float maxZ, float depth
 __device__ __forceinline__ float stdMin(float a, float b) { return (b < a) ? b : a; }
 __device__ __forceinline__ float stdMax(float a, float b) { return (a < b) ? b : a; }
 
-// 128-bit read-only load that asks L2 to fetch the whole 128-byte line on a miss. Used where a warp
-// touches isolated 32-byte sectors whose neighbours are needed by nearby work items moments later:
-// DRAM then sees full-line bursts instead of scattered sectors.
-__device__ __forceinline__ float4 ldLine128(const float* p) {
-	float4 v;
-	asm volatile("ld.global.nc.L2::128B.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-	return v;
-}
-// Same, 256 bits per lane (LDG.E.256, new with sm_100): one lane fetches a whole 32-byte sector.
+// 256-bit read-only load (LDG.E.256, new with sm_100: one lane fetches a whole 32-byte sector) that does not allocate in
+// L1 and asks L2 to fetch the whole 128-byte line on a miss. Used where a warp touches isolated 32-byte sectors whose
+// neighbours are needed by nearby work items moments later: DRAM then sees full-line bursts instead of scattered sectors.
 struct Float8 {
 	float v[8];
 };
