@@ -64,7 +64,7 @@ __device__ __forceinline__ u32 findGroupSlot(u64* __restrict__ table, u64 tableM
 // up to a power of two with >= 1.5x headroom, then cleared. The result does not depend on the capacity,
 // only the speed does: a table sized for the distinct leaves (not for all leaves) stays in L2.
 __global__ void __launch_bounds__(256) sizeAndClearLeafTableKernel(u64* __restrict__ table, u64 maxSlots, const u64* __restrict__ setBits,
-		u64* __restrict__ tableMaskDev) {
+		u64* __restrict__ tableMaskDev, u32* __restrict__ minIndex) {
 	const float m = (float)kSketchWords * 32.0f;
 	const float frac = fminf((float)*setBits / m, 0.999f);
 	const float distinct = -m * log1pf(-frac);
@@ -75,6 +75,11 @@ __global__ void __launch_bounds__(256) sizeAndClearLeafTableKernel(u64* __restri
 	if (blockIdx.x == 0 && threadIdx.x == 0) *tableMaskDev = cap - 1;
 	ulonglong2* t2 = reinterpret_cast<ulonglong2*>(table);
 	for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap / 2; i += (u64)gridDim.x * blockDim.x) t2[i] = make_ulonglong2(kEmpty, kEmpty);
+	if (minIndex) {  // leaves stored by position: first occurrences are tracked beside the table (insertLeavesByPositionKernel)
+		uint4* m4 = reinterpret_cast<uint4*>(minIndex);
+		for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap / 4; i += (u64)gridDim.x * blockDim.x)
+			m4[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+	}
 }
 
 __global__ void __launch_bounds__(256) insertLeavesKernel(const u32* __restrict__ codes, const u64* __restrict__ hashes, u64 n, u64* __restrict__ table,
@@ -101,6 +106,36 @@ __global__ void __launch_bounds__(256) insertLeavesKernel(const u32* __restrict_
 		const uint4 b0 = theirs[0], b1 = theirs[1];
 		return a0.x == b0.x && a0.y == b0.y && a0.z == b0.z && a0.w == b0.w && a1.x == b1.x && a1.y == b1.y && a1.z == b1.z && a1.w == b1.w;
 	});
+}
+
+// Leaves stored by column-order position (launchBuildLeafColumns with leafAt == NULL): thread p handles the leaf whose code sits
+// at position p and whose index in the level is j = leafAt[p]. The table groups by position (slot = fingerprint | smallest
+// position: any member serves as the witness a newcomer compares against); which member comes first in the level -- what the
+// reference's layout needs -- is kept beside it as minIndex[slot] = smallest j, read before the atomic so that the members of
+// a popular group do not queue up on one address. A node is a candidate for "first occurrence" iff it lowered minIndex.
+// The group id goes to slotOf[j]: 4-byte stores scattered over the level instead of the builder's 32-byte ones.
+__global__ void __launch_bounds__(256) insertLeavesByPositionKernel(const u32* __restrict__ codes, const u32* __restrict__ leafAt, u64 n,
+		u64* __restrict__ table, const u64* __restrict__ tableMaskDev, u32* __restrict__ minIndex, u32* __restrict__ slotOf, u32* errorFlag) {
+	const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= n) return;
+	const u64 tableMask = *tableMaskDev;
+	const uint4* mine = reinterpret_cast<const uint4*>(codes + p * 8);
+	const uint4 a0 = __ldcs(mine), a1 = __ldcs(mine + 1);
+	const u32 j = __ldcs(leafAt + p);
+	u64 h = 0x9E3779B97F4A7C15ull;
+	h = (h ^ (((u64)a0.y << 32) | a0.x)) * 0xFF51AFD7ED558CCDull;
+	h = (h ^ (h >> 32) ^ (((u64)a0.w << 32) | a0.z)) * 0xC4CEB9FE1A85EC53ull;
+	h = (h ^ (h >> 32) ^ (((u64)a1.y << 32) | a1.x)) * 0xFF51AFD7ED558CCDull;
+	h = (h ^ (h >> 32) ^ (((u64)a1.w << 32) | a1.z)) * 0xC4CEB9FE1A85EC53ull;
+	const u32 slot = findGroupSlot(table, tableMask, mix64(h), (u32)p, errorFlag, [&](u32 other) {
+		const uint4* theirs = reinterpret_cast<const uint4*>(codes + (u64)other * 8);
+		const uint4 b0 = theirs[0], b1 = theirs[1];
+		return a0.x == b0.x && a0.y == b0.y && a0.z == b0.z && a0.w == b0.w && a1.x == b1.x && a1.y == b1.y && a1.z == b1.z && a1.w == b1.w;
+	}) & kGidMask;
+	if (j >= n) return;  // cannot happen on an ordered pyramid (see the expansion); the count check reports such maps
+	u32 candidate = 0;
+	if (ldRelaxed32(minIndex + slot) > j) candidate = atomicMin(minIndex + slot, j) > j ? kCandidateFlag : 0u;
+	slotOf[j] = slot | candidate;
 }
 
 template <bool kShared = false>
@@ -175,8 +210,11 @@ __global__ void __launch_bounds__(256) insertInnerKernel(const u16* __restrict__
 // (the only part with random accesses) and leave each node's compressed size in a byte plus the tile's
 // totals; (2) one CTA prefix-sums the tile totals; (3) per tile, a block scan of the bytes and the writes.
 // No CTA ever waits for another one, which matters more here than the extra byte per node of traffic.
+// kByPosition (leaves stored by column-order position): first occurrence <=> minIndex[slot] == j; the node's mask is read
+// at the group's witness position, the low word of the slot (equal codes have equal masks).
+template <bool kByPosition>
 __global__ void __launch_bounds__(kScanThreads, 8) rankCountKernel(const u64* __restrict__ table, const u16* __restrict__ masks, int leaf, u64 n,
-		const u32* __restrict__ gid, unsigned char* __restrict__ sizeOf, ScanTileState* __restrict__ tiles) {
+		const u32* __restrict__ gid, unsigned char* __restrict__ sizeOf, ScanTileState* __restrict__ tiles, const u32* __restrict__ minIndex) {
 	const u64 base = (u64)blockIdx.x * kScanTile + (u64)threadIdx.x * kScanItems;
 	u32 words[kScanItems];
 	u64 cnt = 0, wsum = 0;
@@ -185,8 +223,16 @@ __global__ void __launch_bounds__(kScanThreads, 8) rankCountKernel(const u64* __
 		words[i] = 0;
 		if (base + i < n) {
 			const u32 g = gid[base + i];
-			if ((g & kCandidateFlag) && (u32)table[g & kGidMask] == (u32)(base + i)) {
-				const u32 k = __popc(masks[base + i] & 0xAAAAu);
+			bool first;
+			u32 maskAt = (u32)(base + i);
+			if constexpr (kByPosition) {
+				first = (g & kCandidateFlag) && minIndex[g & kGidMask] == (u32)(base + i);
+				if (first) maskAt = (u32)table[g & kGidMask];
+			} else {
+				first = (g & kCandidateFlag) && (u32)table[g & kGidMask] == (u32)(base + i);
+			}
+			if (first) {
+				const u32 k = __popc(masks[maskAt] & 0xAAAAu);
 				words[i] = 1 + (leaf ? 2 * k : k);
 				cnt += 1;
 				wsum += words[i];
@@ -277,8 +323,12 @@ __global__ void __launch_bounds__(kScanTilesThreads) rankScanTilesKernel(ScanTil
 	}
 }
 
+// kByPosition: firstList[] receives the witness position of the group (where the emission finds the code and the mask)
+// instead of the node's index.
+template <bool kByPosition>
 __global__ void __launch_bounds__(kScanThreads, 8) rankWriteKernel(const unsigned char* __restrict__ sizeOf, const u32* __restrict__ gid, u64 n,
-		const ScanTileState* __restrict__ tiles, u32* __restrict__ firstList, u32* __restrict__ wordOffset, u32* __restrict__ slotOffset) {
+		const ScanTileState* __restrict__ tiles, u32* __restrict__ firstList, u32* __restrict__ wordOffset, u32* __restrict__ slotOffset,
+		const u64* __restrict__ table) {
 	const u64 base = (u64)blockIdx.x * kScanTile + (u64)threadIdx.x * kScanItems;
 	u32 words[kScanItems] = {0, 0, 0, 0};
 	if (base + kScanItems <= n) {
@@ -304,9 +354,13 @@ __global__ void __launch_bounds__(kScanThreads, 8) rankWriteKernel(const unsigne
 #pragma unroll
 	for (int i = 0; i < kScanItems; ++i) {
 		if (words[i]) {
-			firstList[rank] = (u32)(base + i);
+			const u32 slot = gid[base + i] & kGidMask;
+			if constexpr (kByPosition)
+				firstList[rank] = (u32)table[slot];
+			else
+				firstList[rank] = (u32)(base + i);
 			wordOffset[rank] = (u32)woff;
-			slotOffset[gid[base + i] & kGidMask] = (u32)woff;
+			slotOffset[slot] = (u32)woff;
 			++rank;
 			woff += words[i];
 		}
@@ -421,8 +475,8 @@ int launchMergeSmallLevels(const SmallMergeArgs& a, cudaStream_t stream) {
 	return 1;
 }
 
-int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* tableMaskDev, cudaStream_t stream) {
-	sizeAndClearLeafTableKernel<<<148 * 8, 256, 0, stream>>>(table, maxSlots, setBits, tableMaskDev);
+int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* tableMaskDev, u32* minIndex, cudaStream_t stream) {
+	sizeAndClearLeafTableKernel<<<148 * 8, 256, 0, stream>>>(table, maxSlots, setBits, tableMaskDev, minIndex);
 	return 1;
 }
 
@@ -432,7 +486,9 @@ int launchInsertLevel(const MergeLevelArgs& a, cudaStream_t stream) {
 		return 1;
 	}
 	const unsigned blocks = (unsigned)((a.n + 255) / 256);
-	if (a.leaf)
+	if (a.leaf && a.leafAt)
+		insertLeavesByPositionKernel<<<blocks, 256, 0, stream>>>(a.leafCodes, a.leafAt, a.n, a.table, a.tableMaskDev, a.minIndex, a.uid, a.errorFlag);
+	else if (a.leaf)
 		insertLeavesKernel<<<blocks, 256, 0, stream>>>(a.leafCodes, a.leafHash, a.n, a.table, a.tableMaskDev, a.uid, a.errorFlag);
 	else
 		insertInnerKernel<<<blocks, 256, 0, stream>>>(a.masks, a.firstChild, a.childUid, a.n, a.table, a.tableSize - 1, a.uid, a.errorFlag);
@@ -442,9 +498,17 @@ int launchInsertLevel(const MergeLevelArgs& a, cudaStream_t stream) {
 int launchRankLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaStream_t stream) {
 	if (a.n == 1) return 0;  // done by launchInsertLevel
 	const u32 tiles = (u32)((a.n + kScanTile - 1) / kScanTile);
-	rankCountKernel<<<tiles, kScanThreads, 0, stream>>>(a.table, a.masks, a.leaf, a.n, a.uid, a.sizeOf, scan.tiles);
+	const bool byPosition = a.leaf && a.leafAt;
+	if (byPosition)
+		rankCountKernel<true><<<tiles, kScanThreads, 0, stream>>>(a.table, a.masks, a.leaf, a.n, a.uid, a.sizeOf, scan.tiles, a.minIndex);
+	else
+		rankCountKernel<false><<<tiles, kScanThreads, 0, stream>>>(a.table, a.masks, a.leaf, a.n, a.uid, a.sizeOf, scan.tiles, nullptr);
 	rankScanTilesKernel<<<1, kScanTilesThreads, 0, stream>>>(scan.tiles, tiles, a.uniqueCount, a.wordCount);
-	rankWriteKernel<<<tiles, kScanThreads, 0, stream>>>(a.sizeOf, a.uid, a.n, scan.tiles, a.firstList, a.wordOffset, a.slotOffset);
+	// (minIndex may alias slotOffset: the count kernel above is the last reader of the former, the write kernel the first writer of the latter)
+	if (byPosition)
+		rankWriteKernel<true><<<tiles, kScanThreads, 0, stream>>>(a.sizeOf, a.uid, a.n, scan.tiles, a.firstList, a.wordOffset, a.slotOffset, a.table);
+	else
+		rankWriteKernel<false><<<tiles, kScanThreads, 0, stream>>>(a.sizeOf, a.uid, a.n, scan.tiles, a.firstList, a.wordOffset, a.slotOffset, nullptr);
 	return 3;
 }
 

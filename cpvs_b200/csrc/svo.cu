@@ -450,6 +450,9 @@ __constant__ u64 kLaneHashMul[4] = {0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full
 
 // The leaves chunk..chunkEnd-1 (warp-uniform bounds) of the eight columns of a warp. firstIdx: leafAt of the lane's leaf of
 // the very first batch if the caller fetched it ahead (only looked at for chunk == 0).
+// kByPosition: a leaf is stored at its column-order position (colBias[column] + z-block) instead of its breadth-first index,
+// so nothing here depends on the expansion (see launchBuildLeafColumns).
+template <bool kByPosition>
 __device__ __forceinline__ void emitColumnLeaves(const LeafColumn& c, const __half2 (&r0)[4], const __half2 (&r1)[4], u32 chunk, u32 chunkEnd,
 		u32 firstIdx, bool haveFirstIdx, const LeafSink& out, PendingSketch& pending) {
 	const u32 lane = threadIdx.x & 31u, sub = lane & 3u, groupLane = lane & ~3u;
@@ -460,7 +463,9 @@ __device__ __forceinline__ void emitColumnLeaves(const LeafColumn& c, const __ha
 	__half2 negI2 = __float2half2_rn(0.f);         // -(block index inside the chunk)
 	for (u32 m = chunk; m < chunkEnd; m += 4) {
 		u32 mineIdx = kNoLeaf;
-		if (haveFirstIdx && m == 0) {
+		if constexpr (kByPosition) {
+			if (m + sub < c.cnt) mineIdx = c.first + m + sub;
+		} else if (haveFirstIdx && m == 0) {
 			mineIdx = firstIdx;
 		} else if (m + sub < c.cnt && c.first + m + sub < out.numLeaves) {
 			mineIdx = out.leafAt[c.first + m + sub];
@@ -509,6 +514,7 @@ __device__ __forceinline__ void emitColumnLeaves(const LeafColumn& c, const __ha
 // four rows of 256 contiguous bytes), software-pipelined in registers so that no load is waited for: a group's level-3
 // texel and colBias are fetched two groups ahead; its depth rows and the leafAt of its first batch one group ahead, and only
 // if the column has leaves (most columns of a z-slice of a tall grid have none). Warps never synchronise with each other.
+template <bool kByPosition>
 __global__ void __launch_bounds__(256, 3) buildLeafColumnsKernel(const float* __restrict__ depth, u32 n, u32 colShift, float heightF,
 		float height3F, float zLoF, float zHiF, const float2* __restrict__ level3, u32 numCols, const u32* __restrict__ colBias, LeafSink out) {
 	const u32 lane = threadIdx.x & 31u, sub = lane & 3u;
@@ -546,7 +552,8 @@ __global__ void __launch_bounds__(256, 3) buildLeafColumnsKernel(const float* __
 			const float* p = depth + (size_t)(cy * 8u + sub * 2u) * n + cx * 8u;
 			a1 = ldSector256(p);
 			b1 = ldSector256(p + n);
-			if (sub < c1.cnt && c1.first + sub < out.numLeaves) idx1 = out.leafAt[c1.first + sub];
+			if constexpr (!kByPosition)
+				if (sub < c1.cnt && c1.first + sub < out.numLeaves) idx1 = out.leafAt[c1.first + sub];
 		}
 	};
 	fetchTexel(group);
@@ -569,7 +576,7 @@ __global__ void __launch_bounds__(256, 3) buildLeafColumnsKernel(const float* __
 		fetchRows(group + numWarps);
 		fetchTexel(group + 2u * numWarps);
 		if (maxCnt == 0) continue;
-		emitColumnLeaves(c, r0, r1, 0, min(maxCnt, kChunkBlocks), firstIdx, true, out, pending);
+		emitColumnLeaves<kByPosition>(c, r0, r1, 0, min(maxCnt, kChunkBlocks), firstIdx, true, out, pending);
 		for (u32 chunk = kChunkBlocks; chunk < maxCnt; chunk += kChunkBlocks) {  // tall columns (box edges): re-read the rows
 			if (c.cnt) {
 				const u32 col = group * 8u + (lane >> 2);
@@ -577,7 +584,7 @@ __global__ void __launch_bounds__(256, 3) buildLeafColumnsKernel(const float* __
 				const float* p = depth + (size_t)(cy * 8u + sub * 2u) * n + cx * 8u;
 				rowsToR(ldSector256(p), ldSector256(p + n), heightF, __fadd_rn(c.lo, __uint2float_rn(chunk)), r0, r1);
 			}
-			emitColumnLeaves(c, r0, r1, chunk, min(maxCnt, chunk + kChunkBlocks), kNoLeaf, false, out, pending);
+			emitColumnLeaves<kByPosition>(c, r0, r1, chunk, min(maxCnt, chunk + kChunkBlocks), kNoLeaf, false, out, pending);
 		}
 	}
 	pending.flush();
@@ -689,7 +696,7 @@ int launchColumnBias(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, u32* 
 }
 
 int launchBuildLeafColumns(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, const u32* colBias, const u32* leafAt, u32 numLeaves, u32* codes,
-		u16* masks, u32* sketch, cudaStream_t stream) {
+		u16* masks, u32* sketch, u32 ctasPerSm, cudaStream_t stream) {
 	const u32 side3 = (u32)pyr.n >> 3, numCols = side3 * side3;
 	u32 colShift = 0;
 	while ((1u << colShift) < side3) ++colShift;
@@ -698,8 +705,14 @@ int launchBuildLeafColumns(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum,
 	const float2* level3 = reinterpret_cast<const float2*>(pyr.level[3]);
 	LeafSink out{leafAt, numLeaves, codes, masks, sketch, kSketchWords - 1};
 	const u32 wanted = (numCols + kColumnsPerCta - 1) / kColumnsPerCta;  // 8 warps of 8 columns per CTA
-	buildLeafColumnsKernel<<<wanted < 148u * 3u ? wanted : 148u * 3u, 256, 0, stream>>>(pyr.level[0], (u32)pyr.n, colShift, heightF, height3F,
-			zLoF, zHiF, level3, numCols, colBias, out);
+	const u32 resident = 148u * (ctasPerSm >= 1u && ctasPerSm <= 3u ? ctasPerSm : 3u);  // persistent CTAs (launch bounds: 3 per SM)
+	const u32 grid = wanted < resident ? wanted : resident;
+	if (leafAt)
+		buildLeafColumnsKernel<false><<<grid, 256, 0, stream>>>(pyr.level[0], (u32)pyr.n, colShift, heightF, height3F, zLoF, zHiF, level3, numCols,
+				colBias, out);
+	else
+		buildLeafColumnsKernel<true><<<grid, 256, 0, stream>>>(pyr.level[0], (u32)pyr.n, colShift, heightF, height3F, zLoF, zHiF, level3, numCols,
+				colBias, out);
 	return 1;
 }
 
