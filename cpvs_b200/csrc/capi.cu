@@ -95,6 +95,7 @@ struct cpvs_ctx {
 	// (default 3; 2 when it runs beside the expansion, whose CTAs need registers of their own).
 	int leafByPosition;
 	int leafCtas;
+	int emitPlanes;  // experimental (CPVS_EMIT_PLANES=1): leaf emission through bit planes (emit.cu emitLeavesPlanesKernel)
 	cudaEvent_t evLeafStart, evLeafStop;
 };
 
@@ -250,6 +251,8 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 	{
 		const char* v = std::getenv("CPVS_LEAF_ORDER");
 		ctx->leafByPosition = (v && v[0] == '1') ? 1 : 0;
+		const char* pl = std::getenv("CPVS_EMIT_PLANES");
+		ctx->emitPlanes = (pl && pl[0] == '1') ? 1 : 0;
 		const char* c = std::getenv("CPVS_LEAF_CTAS");
 		ctx->leafCtas = (c && c[0] >= '1' && c[0] <= '3') ? c[0] - '0' : (ctx->leafByPosition ? 2 : 3);
 	}
@@ -966,6 +969,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		EmitLevelArgs em;
 		em.n = hScalars[32 + l];  // unique nodes of the level (read back with the sizes): exact grid
 		em.leaf = isLeaf ? 1 : 0;
+		em.planes = ctx->emitPlanes;
 		em.uniqueCount = dUnique + l;
 		em.wordCount = dWords + l;
 		em.firstList = a.firstList;

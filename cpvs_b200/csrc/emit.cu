@@ -6,6 +6,7 @@
 // mask + (lo32, hi32) per PARTIAL slice. The per-level word offsets were prefix-summed while
 // merging; here level bases are chained top-down and every unique node is written exactly once.
 #include "kernels.h"
+#include "leafbits.cuh"
 
 namespace cpvs {
 
@@ -68,13 +69,7 @@ __global__ void __launch_bounds__(kEmitThreads) emitInnerLevelsKernel(EmitMultiA
 
 // Leaves: expands the k-code (nibble x of word y = lit slices of texel (x,y)) into the 64-bit masks of
 // the PARTIAL slices, bit x + 8y = lit (createLeafmask, src/CompressedShadowUtil.cpp:59-78).
-__device__ __forceinline__ u32 rowBits(u32 code, u32 slice) {
-	// nibble k > slice  <=>  bit 3 of (k + 7 - slice); nibbles are <= 8 so nothing carries
-	u32 y = ((code + (7u - slice) * 0x11111111u) >> 3) & 0x11111111u;
-	y = (y | (y >> 3)) & 0x03030303u;
-	y = (y | (y >> 6)) & 0x000F000Fu;
-	return (y | (y >> 12)) & 0xFFu;
-}
+// (rowBits: leafbits.cuh)
 
 __global__ void __launch_bounds__(kEmitThreads) emitLeavesKernel(EmitLevelArgs a) {
 	__shared__ u32 sOut[kEmitThreads * 17];
@@ -102,6 +97,42 @@ __global__ void __launch_bounds__(kEmitThreads) emitLeavesKernel(EmitLevelArgs a
 	emitRun(a, sOut, runStart, runEnd - runStart);
 }
 
+// The same through bit planes (leafbits.cuh): the code is transposed once, every slice is then a couple of logic
+// instructions, and the loop over the slices is unrolled with predicated stores -- about a quarter of the instructions
+// when most slices of a leaf are PARTIAL (terrain-like surfaces). Experimental, CPVS_EMIT_PLANES=1.
+__global__ void __launch_bounds__(kEmitThreads) emitLeavesPlanesKernel(EmitLevelArgs a) {
+	__shared__ u32 sOut[kEmitThreads * 17];
+	const u64 unique = *a.uniqueCount;
+	const u64 r0 = (u64)blockIdx.x * kEmitThreads;
+	if (r0 >= unique) return;
+	const u64 r = r0 + threadIdx.x;
+	const u32 runStart = a.wordOffset[r0];
+	const u32 runEnd = (r0 + kEmitThreads < unique) ? a.wordOffset[r0 + kEmitThreads] : (u32)*a.wordCount;
+	if (r < unique) {
+		const u32 j = a.firstList[r];
+		const u32 mask = a.masks[j];
+		u32* out = sOut + (a.wordOffset[r] - runStart);
+		*out++ = mask;
+		const uint4* src = reinterpret_cast<const uint4*>(a.leafCodes + (u64)j * 8);
+		const uint4 c0 = src[0], c1 = src[1];
+		if (mask & 0xAAAAu) {
+			const u32 code[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+			u32 lo[4], hi[4];
+			codeToPlanes(code, lo, hi);
+#pragma unroll
+			for (u32 slice = 0; slice < 8; ++slice) {
+				if (mask & (2u << (2u * slice))) {  // PARTIAL slices only, lowest first
+					out[0] = sliceFromPlanes(lo, slice);
+					out[1] = sliceFromPlanes(hi, slice);
+					out += 2;
+				}
+			}
+		}
+	}
+	__syncthreads();
+	emitRun(a, sOut, runStart, runEnd - runStart);
+}
+
 }  // namespace
 
 int launchLevelBases(const u64* words, u64* bases, int topLevel, int minLevel, u64* totalWords, cudaStream_t stream) {
@@ -123,7 +154,9 @@ int launchEmitInnerLevels(EmitMultiArgs& m, cudaStream_t stream) {
 
 int launchEmitLevel(const EmitLevelArgs& a, cudaStream_t stream) {
 	const unsigned blocks = (unsigned)((a.n + 255) / 256);
-	if (a.leaf)
+	if (a.leaf && a.planes)
+		emitLeavesPlanesKernel<<<blocks, 256, 0, stream>>>(a);
+	else if (a.leaf)
 		emitLeavesKernel<<<blocks, 256, 0, stream>>>(a);
 	else
 		emitInnerKernel<<<blocks, 256, 0, stream>>>(a);

@@ -142,6 +142,7 @@ int launchRankLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaStream_t strea
 struct EmitLevelArgs {
 	u64 n;                    // unique nodes of the level (or any upper bound: sizes the grid)
 	int leaf;
+	int planes;               // leaf: expand the k-code through bit planes (leafbits.cuh; experimental, CPVS_EMIT_PLANES=1)
 	const u64* uniqueCount;   // device: unique nodes of this level
 	const u32* firstList;
 	const u32* wordOffset;
