@@ -63,6 +63,7 @@ __device__ __forceinline__ u32 findGroupSlot(u64* __restrict__ table, u64 tableM
 // Leaf table capacity from the distinct-count sketch (linear counting: u ~ -m ln(zero fraction)), rounded
 // up to a power of two with >= 1.5x headroom, then cleared. The result does not depend on the capacity,
 // only the speed does: a table sized for the distinct leaves (not for all leaves) stays in L2.
+template <bool kWithMinIndex>
 __global__ void __launch_bounds__(256) sizeAndClearLeafTableKernel(u64* __restrict__ table, u64 maxSlots, const u64* __restrict__ setBits,
 		u64* __restrict__ tableMaskDev, u32* __restrict__ minIndex) {
 	const float m = (float)kSketchWords * 32.0f;
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(256) sizeAndClearLeafTableKernel(u64* __restri
 	if (blockIdx.x == 0 && threadIdx.x == 0) *tableMaskDev = cap - 1;
 	ulonglong2* t2 = reinterpret_cast<ulonglong2*>(table);
 	for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap / 2; i += (u64)gridDim.x * blockDim.x) t2[i] = make_ulonglong2(kEmpty, kEmpty);
-	if (minIndex) {  // leaves stored by position: first occurrences are tracked beside the table (insertLeavesByPositionKernel)
+	if constexpr (kWithMinIndex) {  // leaves stored by position: first occurrences are tracked beside the table (insertLeavesByPositionKernel)
 		uint4* m4 = reinterpret_cast<uint4*>(minIndex);
 		for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap / 4; i += (u64)gridDim.x * blockDim.x)
 			m4[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
@@ -223,16 +224,15 @@ __global__ void __launch_bounds__(kScanThreads, 8) rankCountKernel(const u64* __
 		words[i] = 0;
 		if (base + i < n) {
 			const u32 g = gid[base + i];
-			bool first;
-			u32 maskAt = (u32)(base + i);
 			if constexpr (kByPosition) {
-				first = (g & kCandidateFlag) && minIndex[g & kGidMask] == (u32)(base + i);
-				if (first) maskAt = (u32)table[g & kGidMask];
-			} else {
-				first = (g & kCandidateFlag) && (u32)table[g & kGidMask] == (u32)(base + i);
-			}
-			if (first) {
-				const u32 k = __popc(masks[maskAt] & 0xAAAAu);
+				if ((g & kCandidateFlag) && minIndex[g & kGidMask] == (u32)(base + i)) {
+					const u32 k = __popc(masks[(u32)table[g & kGidMask]] & 0xAAAAu);
+					words[i] = 1 + (leaf ? 2 * k : k);
+					cnt += 1;
+					wsum += words[i];
+				}
+			} else if ((g & kCandidateFlag) && (u32)table[g & kGidMask] == (u32)(base + i)) {
+				const u32 k = __popc(masks[base + i] & 0xAAAAu);
 				words[i] = 1 + (leaf ? 2 * k : k);
 				cnt += 1;
 				wsum += words[i];
@@ -476,7 +476,10 @@ int launchMergeSmallLevels(const SmallMergeArgs& a, cudaStream_t stream) {
 }
 
 int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* tableMaskDev, u32* minIndex, cudaStream_t stream) {
-	sizeAndClearLeafTableKernel<<<148 * 8, 256, 0, stream>>>(table, maxSlots, setBits, tableMaskDev, minIndex);
+	if (minIndex)
+		sizeAndClearLeafTableKernel<true><<<148 * 8, 256, 0, stream>>>(table, maxSlots, setBits, tableMaskDev, minIndex);
+	else
+		sizeAndClearLeafTableKernel<false><<<148 * 8, 256, 0, stream>>>(table, maxSlots, setBits, tableMaskDev, nullptr);
 	return 1;
 }
 
