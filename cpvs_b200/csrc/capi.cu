@@ -229,6 +229,7 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 	ctx->arena = nullptr;
 	ctx->arenaBytes = 0;
 	ctx->scalars = nullptr;
+	ctx->own = nullptr;
 	cudaError_t e = cudaStreamCreateWithFlags(&ctx->own, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->scalars), 192 * sizeof(u64));
 	ctx->hostScalars = nullptr;
@@ -265,11 +266,11 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evCols, cudaEventDisableTiming);
 	if (e == cudaSuccess) e = cudaEventCreate(&ctx->evRankStart);
 	if (e == cudaSuccess) e = cudaEventCreate(&ctx->evRankStop);
+	ctx->stream = ctx->own;
 	if (e != cudaSuccess) {
-		delete ctx;
+		cpvs_ctx_destroy(ctx);  // releases whatever was created before the failure
 		return fail(CPVS_ECUDA, "cpvs_ctx_create: %s", cudaGetErrorString(e));
 	}
-	ctx->stream = ctx->own;
 	*out = ctx;
 	return CPVS_OK;
 }
@@ -295,7 +296,7 @@ int cpvs_ctx_destroy(cpvs_ctx* ctx) {
 	if (ctx->evRankStop) cudaEventDestroy(ctx->evRankStop);
 	if (ctx->evLeafStart) cudaEventDestroy(ctx->evLeafStart);
 	if (ctx->evLeafStop) cudaEventDestroy(ctx->evLeafStop);
-	cudaStreamDestroy(ctx->own);
+	if (ctx->own) cudaStreamDestroy(ctx->own);
 	delete ctx;
 	return CPVS_OK;
 }
