@@ -95,6 +95,7 @@ struct cpvs_ctx {
 	// (default 3; 2 when it runs beside the expansion, whose CTAs need registers of their own).
 	int leafByPosition;
 	int leafCtas;
+	int insertHints;  // experimental (CPVS_INSERT_HINTS=1): L2 eviction priorities in the leaf insert (merge.cu)
 	int emitPlanes;  // experimental (CPVS_EMIT_PLANES=1): leaf emission through bit planes (emit.cu emitLeavesPlanesKernel)
 	cudaEvent_t evLeafStart, evLeafStop;
 };
@@ -252,6 +253,8 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 	{
 		const char* v = std::getenv("CPVS_LEAF_ORDER");
 		ctx->leafByPosition = (v && v[0] == '1') ? 1 : 0;
+		const char* ih = std::getenv("CPVS_INSERT_HINTS");
+		ctx->insertHints = (ih && ih[0] == '1') ? 1 : 0;
 		const char* pl = std::getenv("CPVS_EMIT_PLANES");
 		ctx->emitPlanes = (pl && pl[0] == '1') ? 1 : 0;
 		const char* c = std::getenv("CPVS_LEAF_CTAS");
@@ -855,6 +858,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		m.leaf = leafLevel ? 1 : 0;
 		m.leafCodes = a.leafCodes;
 		m.leafHash = a.leafHash;
+		m.hints = ctx->insertHints;
 		m.leafAt = (leafLevel && leafByPosition) ? a.leafAt : nullptr;
 		m.minIndex = (leafLevel && leafByPosition) ? a.slotOffset : nullptr;
 		m.masks = a.masks;

@@ -30,13 +30,20 @@ static_assert(kDirectSlots == 256, "one direct slot per thread of the insert CTA
 constexpr u32 kCandidateFlag = 0x80000000u, kGidMask = 0x7FFFFFFFu;
 
 // kShared: the table lives in shared memory (single-CTA kernels for the small levels).
-template <bool kShared = false, typename Equal>
+// kKeep: probes mark the table's lines evict-last in L2 (leaf level, CPVS_INSERT_HINTS=1).
+template <bool kShared = false, bool kKeep = false, typename Equal>
 __device__ __forceinline__ u32 findGroupSlot(u64* __restrict__ table, u64 tableMask, u64 hash, u32 self, u32* errorFlag, Equal sameTuple) {
 	const u64 fp = hash >> 32;
 	const u64 key = (fp << 32) | self;
 	u64 slot = hash & tableMask;
+	u64 keepPolicy = 0;
+	if constexpr (kKeep) keepPolicy = l2KeepPolicy();
 	for (u64 probes = 0; probes <= tableMask; ++probes) {
-		u64 v = kShared ? *reinterpret_cast<volatile u64*>(table + slot) : ldRelaxed64(table + slot);
+		u64 v;
+		if constexpr (kKeep)
+			v = ldRelaxed64Keep(table + slot, keepPolicy);
+		else
+			v = kShared ? *reinterpret_cast<volatile u64*>(table + slot) : ldRelaxed64(table + slot);
 		if (v == kEmpty) {
 			const u64 old = atomicCAS(reinterpret_cast<unsigned long long*>(table + slot), (unsigned long long)kEmpty, (unsigned long long)key);
 			if (old == kEmpty) return (u32)slot | kCandidateFlag;
@@ -83,14 +90,45 @@ __global__ void __launch_bounds__(256) sizeAndClearLeafTableKernel(u64* __restri
 	}
 }
 
+// kHints (experimental, CPVS_INSERT_HINTS=1): L2 eviction priorities. The kernel streams every code once (447 MB at 16K^2
+// terrain) while it keeps returning, at random, to the table (32 MiB) and to the codes of the groups' witnesses (~80 MB of
+// scattered 32-byte sectors); the profile shows 40 % L2 hits and 0.3 GB of DRAM reads beyond the stream, i.e. the stream
+// evicts the witnesses. With the switch the own code is one 256-bit evict-first load, witness codes and table probes are
+// evict-last.
+template <bool kHints>
+__device__ __forceinline__ void loadOwnCode(const u32* __restrict__ codes, u64 at, uint4& a0, uint4& a1) {
+	if constexpr (kHints) {
+		const Uint8 c = ldStream256(codes + at * 8);
+		a0 = make_uint4(c.v[0], c.v[1], c.v[2], c.v[3]);
+		a1 = make_uint4(c.v[4], c.v[5], c.v[6], c.v[7]);
+	} else {
+		const uint4* mine = reinterpret_cast<const uint4*>(codes + at * 8);
+		a0 = __ldcs(mine);
+		a1 = __ldcs(mine + 1);
+	}
+}
+template <bool kHints>
+__device__ __forceinline__ bool sameCode(const u32* __restrict__ codes, u32 other, const uint4& a0, const uint4& a1) {
+	if constexpr (kHints) {
+		const Uint8 b = ldKeep256(codes + (u64)other * 8);
+		return a0.x == b.v[0] && a0.y == b.v[1] && a0.z == b.v[2] && a0.w == b.v[3] && a1.x == b.v[4] && a1.y == b.v[5] && a1.z == b.v[6] &&
+			   a1.w == b.v[7];
+	} else {
+		const uint4* theirs = reinterpret_cast<const uint4*>(codes + (u64)other * 8);
+		const uint4 b0 = theirs[0], b1 = theirs[1];
+		return a0.x == b0.x && a0.y == b0.y && a0.z == b0.z && a0.w == b0.w && a1.x == b1.x && a1.y == b1.y && a1.z == b1.z && a1.w == b1.w;
+	}
+}
+
+template <bool kHints>
 __global__ void __launch_bounds__(256) insertLeavesKernel(const u32* __restrict__ codes, const u64* __restrict__ hashes, u64 n, u64* __restrict__ table,
 		const u64* __restrict__ tableMaskDev, u32* __restrict__ slotOf, u32* errorFlag) {
 	const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= n) return;
 	const u64 tableMask = *tableMaskDev;
 	// own code and hash are fetched up front so that their latency overlaps the first table probe
-	const uint4* mine = reinterpret_cast<const uint4*>(codes + j * 8);
-	const uint4 a0 = __ldcs(mine), a1 = __ldcs(mine + 1);
+	uint4 a0, a1;
+	loadOwnCode<kHints>(codes, j, a0, a1);
 	u64 hash;
 	if (hashes) {
 		hash = __ldcs(hashes + j);
@@ -102,11 +140,7 @@ __global__ void __launch_bounds__(256) insertLeavesKernel(const u32* __restrict_
 		h = (h ^ (h >> 32) ^ (((u64)a1.w << 32) | a1.z)) * 0xC4CEB9FE1A85EC53ull;
 		hash = mix64(h);
 	}
-	slotOf[j] = findGroupSlot(table, tableMask, hash, (u32)j, errorFlag, [&](u32 other) {
-		const uint4* theirs = reinterpret_cast<const uint4*>(codes + (u64)other * 8);
-		const uint4 b0 = theirs[0], b1 = theirs[1];
-		return a0.x == b0.x && a0.y == b0.y && a0.z == b0.z && a0.w == b0.w && a1.x == b1.x && a1.y == b1.y && a1.z == b1.z && a1.w == b1.w;
-	});
+	slotOf[j] = findGroupSlot<false, kHints>(table, tableMask, hash, (u32)j, errorFlag, [&](u32 other) { return sameCode<kHints>(codes, other, a0, a1); });
 }
 
 // Leaves stored by column-order position (launchBuildLeafColumns with leafAt == NULL): thread p handles the leaf whose code sits
@@ -115,24 +149,23 @@ __global__ void __launch_bounds__(256) insertLeavesKernel(const u32* __restrict_
 // reference's layout needs -- is kept beside it as minIndex[slot] = smallest j, read before the atomic so that the members of
 // a popular group do not queue up on one address. A node is a candidate for "first occurrence" iff it lowered minIndex.
 // The group id goes to slotOf[j]: 4-byte stores scattered over the level instead of the builder's 32-byte ones.
+template <bool kHints>
 __global__ void __launch_bounds__(256) insertLeavesByPositionKernel(const u32* __restrict__ codes, const u32* __restrict__ leafAt, u64 n,
 		u64* __restrict__ table, const u64* __restrict__ tableMaskDev, u32* __restrict__ minIndex, u32* __restrict__ slotOf, u32* errorFlag) {
 	const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	if (p >= n) return;
 	const u64 tableMask = *tableMaskDev;
-	const uint4* mine = reinterpret_cast<const uint4*>(codes + p * 8);
-	const uint4 a0 = __ldcs(mine), a1 = __ldcs(mine + 1);
+	uint4 a0, a1;
+	loadOwnCode<kHints>(codes, p, a0, a1);
 	const u32 j = __ldcs(leafAt + p);
 	u64 h = 0x9E3779B97F4A7C15ull;
 	h = (h ^ (((u64)a0.y << 32) | a0.x)) * 0xFF51AFD7ED558CCDull;
 	h = (h ^ (h >> 32) ^ (((u64)a0.w << 32) | a0.z)) * 0xC4CEB9FE1A85EC53ull;
 	h = (h ^ (h >> 32) ^ (((u64)a1.y << 32) | a1.x)) * 0xFF51AFD7ED558CCDull;
 	h = (h ^ (h >> 32) ^ (((u64)a1.w << 32) | a1.z)) * 0xC4CEB9FE1A85EC53ull;
-	const u32 slot = findGroupSlot(table, tableMask, mix64(h), (u32)p, errorFlag, [&](u32 other) {
-		const uint4* theirs = reinterpret_cast<const uint4*>(codes + (u64)other * 8);
-		const uint4 b0 = theirs[0], b1 = theirs[1];
-		return a0.x == b0.x && a0.y == b0.y && a0.z == b0.z && a0.w == b0.w && a1.x == b1.x && a1.y == b1.y && a1.z == b1.z && a1.w == b1.w;
-	}) & kGidMask;
+	const u32 slot =
+			findGroupSlot<false, kHints>(table, tableMask, mix64(h), (u32)p, errorFlag, [&](u32 other) { return sameCode<kHints>(codes, other, a0, a1); }) &
+			kGidMask;
 	if (j >= n) return;  // cannot happen on an ordered pyramid (see the expansion); the count check reports such maps
 	u32 candidate = 0;
 	if (ldRelaxed32(minIndex + slot) > j) candidate = atomicMin(minIndex + slot, j) > j ? kCandidateFlag : 0u;
@@ -489,10 +522,14 @@ int launchInsertLevel(const MergeLevelArgs& a, cudaStream_t stream) {
 		return 1;
 	}
 	const unsigned blocks = (unsigned)((a.n + 255) / 256);
-	if (a.leaf && a.leafAt)
-		insertLeavesByPositionKernel<<<blocks, 256, 0, stream>>>(a.leafCodes, a.leafAt, a.n, a.table, a.tableMaskDev, a.minIndex, a.uid, a.errorFlag);
+	if (a.leaf && a.leafAt && a.hints)
+		insertLeavesByPositionKernel<true><<<blocks, 256, 0, stream>>>(a.leafCodes, a.leafAt, a.n, a.table, a.tableMaskDev, a.minIndex, a.uid, a.errorFlag);
+	else if (a.leaf && a.leafAt)
+		insertLeavesByPositionKernel<false><<<blocks, 256, 0, stream>>>(a.leafCodes, a.leafAt, a.n, a.table, a.tableMaskDev, a.minIndex, a.uid, a.errorFlag);
+	else if (a.leaf && a.hints)
+		insertLeavesKernel<true><<<blocks, 256, 0, stream>>>(a.leafCodes, a.leafHash, a.n, a.table, a.tableMaskDev, a.uid, a.errorFlag);
 	else if (a.leaf)
-		insertLeavesKernel<<<blocks, 256, 0, stream>>>(a.leafCodes, a.leafHash, a.n, a.table, a.tableMaskDev, a.uid, a.errorFlag);
+		insertLeavesKernel<false><<<blocks, 256, 0, stream>>>(a.leafCodes, a.leafHash, a.n, a.table, a.tableMaskDev, a.uid, a.errorFlag);
 	else
 		insertInnerKernel<<<blocks, 256, 0, stream>>>(a.masks, a.firstChild, a.childUid, a.n, a.table, a.tableSize - 1, a.uid, a.errorFlag);
 	return 1;
