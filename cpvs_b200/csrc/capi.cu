@@ -91,10 +91,11 @@ struct cpvs_ctx {
 	int leafColumns;  // leaves built per column: 1 = where it pays (default), 0 = never, 2 = always (CPVS_LEAF_COLUMNS; tests)
 	// Experimental (CPVS_LEAF_ORDER=1, off by default; only with the per-column builder): leaf codes and masks are stored by
 	// column-order position, so the leaf builder needs nothing from the expansion and runs beside it on a side stream; the
-	// merge maps positions to level indices. leafCtas (CPVS_LEAF_CTAS=1..3): resident CTAs per SM of the persistent builder
+	// merge maps positions to level indices. leafCtas (CPVS_LEAF_CTAS=1..4): resident CTAs per SM of the persistent builder
 	// (default 3; 2 when it runs beside the expansion, whose CTAs need registers of their own).
 	int leafByPosition;
 	int leafCtas;
+	int expandBlocks;  // experimental (CPVS_EXPAND_BLOCKS=12): expansion kernel held to 40 registers, 12 CTAs per SM
 	int insertHints;  // experimental (CPVS_INSERT_HINTS=1): L2 eviction priorities in the leaf insert (merge.cu)
 	int emitPlanes;  // experimental (CPVS_EMIT_PLANES=1): leaf emission through bit planes (emit.cu emitLeavesPlanesKernel)
 	cudaEvent_t evLeafStart, evLeafStop;
@@ -258,7 +259,9 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 		const char* pl = std::getenv("CPVS_EMIT_PLANES");
 		ctx->emitPlanes = (pl && pl[0] == '1') ? 1 : 0;
 		const char* c = std::getenv("CPVS_LEAF_CTAS");
-		ctx->leafCtas = (c && c[0] >= '1' && c[0] <= '3') ? c[0] - '0' : (ctx->leafByPosition ? 2 : 3);
+		ctx->leafCtas = (c && c[0] >= '1' && c[0] <= '4') ? c[0] - '0' : (ctx->leafByPosition ? 2 : 3);
+		const char* xb = std::getenv("CPVS_EXPAND_BLOCKS");
+		ctx->expandBlocks = (xb && std::atoi(xb) == 12) ? 12 : 1;
 	}
 	if (e == cudaSuccess) e = cudaEventCreate(&ctx->evLeafStart);
 	if (e == cudaSuccess) e = cudaEventCreate(&ctx->evLeafStop);
@@ -816,7 +819,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		const bool toColumns = leafColumns && l == 3;
 		if (toColumns) CPVS_CUDA(cudaStreamWaitEvent(st, ctx->evCols, 0));
 		ctx->launches += launchExpandLevel(pyr, l, zTileNum, lv[l].coords, lv[l].n, lv[l].masks, lv[l].firstChild, childCoords,
-				dChildTotal + l, nextScan(lv[l].n, kExpandTileNodes), toColumns ? dColBias : nullptr, toColumns ? lv[2].leafAt : nullptr, (u32)lv[2].n, st);
+				dChildTotal + l, nextScan(lv[l].n, kExpandTileNodes), toColumns ? dColBias : nullptr, toColumns ? lv[2].leafAt : nullptr, (u32)lv[2].n, ctx->expandBlocks, st);
 	}
 	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAVES], st));
 	if (leafByPosition)  // already running on the side stream; the merge below waits for it

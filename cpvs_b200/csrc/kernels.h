@@ -37,7 +37,8 @@ constexpr u64 kExpandTileNodes = 128 * kScanItems;  // nodes per look-back tile 
 // With leafAt != NULL the children are leaves built per column (launchBuildLeafColumns): instead of their
 // coordinates, each child's index is stored at its column-order position leafAt[colBias[column] + z].
 int launchExpandLevel(const PyramidView& pyr, int level, u32 zTileNum, const u64* coords, u64 n, u16* masks,
-		u32* firstChild, u64* childCoords, u64* childTotal, ScanLaunch scan, const u32* colBias, u32* leafAt, u32 numLeaves, cudaStream_t stream);
+		u32* firstChild, u64* childCoords, u64* childTotal, ScanLaunch scan, const u32* colBias, u32* leafAt, u32 numLeaves, int minBlocks,
+		cudaStream_t stream);  // minBlocks: 12 selects the 40-register instantiation (experimental), anything else the default
 
 // The small top levels (<= kSmallMaxNodes nodes each, root first) expanded by a single CTA.
 constexpr int kSmallThreads = 1024;
@@ -77,7 +78,8 @@ int launchColumnBias(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, u32* 
 // (No hash array: the insert derives its hash from the code when MergeLevelArgs::leafHash is NULL.)
 // leafAt == NULL: codes[] and masks[] are stored by column-order position instead of by index in the level. The builder then
 // needs nothing from the expansion and may run beside it; the merge maps positions to indices (MergeLevelArgs::leafAt).
-// ctasPerSm (1..3): resident CTAs per SM of the persistent kernel; fewer leave room for kernels running beside it.
+// ctasPerSm (1..4): resident CTAs per SM of the persistent kernel; fewer leave room for kernels running beside it, 4 selects
+// an instantiation held to 64 registers.
 int launchBuildLeafColumns(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, const u32* colBias, const u32* leafAt, u32 numLeaves, u32* codes,
 		u16* masks, u32* sketch, u32 ctasPerSm, cudaStream_t stream);
 int launchSketchPopcount(const u32* sketch, u64* setBits, cudaStream_t stream);

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) countNodesKernel(CountLevels p, u64* __re
 // chain better than 256-thread ones.)
 constexpr int kExpandThreads = 128;
 constexpr int kExpandTile = kExpandThreads * kScanItems;
-__global__ void __launch_bounds__(kExpandThreads) expandLevelKernel(const float* __restrict__ tex, u32 side, float heightF, int level0,
+__device__ __forceinline__ void expandLevelBody(const float* __restrict__ tex, u32 side, float heightF, int level0,
 		const u64* __restrict__ coords, u64 n, u16* __restrict__ masks, u32* __restrict__ firstChild, u64* __restrict__ childCoords,
 		u64* __restrict__ childTotal, ScanLaunch scan, u32 numTiles, const u32* __restrict__ colBias, u32* __restrict__ leafAt, u32 numLeaves) {
 	const u32 tile = scanAcquireTile(scan);
@@ -180,6 +180,18 @@ __global__ void __launch_bounds__(kExpandThreads) expandLevelKernel(const float*
 			}
 		}
 	}
+}
+
+__global__ void __launch_bounds__(kExpandThreads) expandLevelKernel(const float* __restrict__ tex, u32 side, float heightF, int level0,
+		const u64* __restrict__ coords, u64 n, u16* __restrict__ masks, u32* __restrict__ firstChild, u64* __restrict__ childCoords,
+		u64* __restrict__ childTotal, ScanLaunch scan, u32 numTiles, const u32* __restrict__ colBias, u32* __restrict__ leafAt, u32 numLeaves) {
+	expandLevelBody(tex, side, heightF, level0, coords, n, masks, firstChild, childCoords, childTotal, scan, numTiles, colBias, leafAt, numLeaves);
+}
+// The same, held to 40 registers so that 12 CTAs instead of 10 fit an SM (no spills). Experimental, CPVS_EXPAND_BLOCKS=12.
+__global__ void __launch_bounds__(kExpandThreads, 12) expandLevelDenseKernel(const float* __restrict__ tex, u32 side, float heightF, int level0,
+		const u64* __restrict__ coords, u64 n, u16* __restrict__ masks, u32* __restrict__ firstChild, u64* __restrict__ childCoords,
+		u64* __restrict__ childTotal, ScanLaunch scan, u32 numTiles, const u32* __restrict__ colBias, u32* __restrict__ leafAt, u32 numLeaves) {
+	expandLevelBody(tex, side, heightF, level0, coords, n, masks, firstChild, childCoords, childTotal, scan, numTiles, colBias, leafAt, numLeaves);
 }
 
 // The top of the octree: levels of at most kSmallMaxNodes nodes are a chain of tiny dependent steps.
@@ -514,8 +526,9 @@ __device__ __forceinline__ void emitColumnLeaves(const LeafColumn& c, const __ha
 // four rows of 256 contiguous bytes), software-pipelined in registers so that no load is waited for: a group's level-3
 // texel and colBias are fetched two groups ahead; its depth rows and the leafAt of its first batch one group ahead, and only
 // if the column has leaves (most columns of a z-slice of a tall grid have none). Warps never synchronise with each other.
-template <bool kByPosition>
-__global__ void __launch_bounds__(256, 3) buildLeafColumnsKernel(const float* __restrict__ depth, u32 n, u32 colShift, float heightF,
+// kMinBlocks: 3 (78 registers), or 4 (64 registers with 64 bytes of spills; experimental, CPVS_LEAF_CTAS=4).
+template <bool kByPosition, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks) buildLeafColumnsKernel(const float* __restrict__ depth, u32 n, u32 colShift, float heightF,
 		float height3F, float zLoF, float zHiF, const float2* __restrict__ level3, u32 numCols, const u32* __restrict__ colBias, LeafSink out) {
 	const u32 lane = threadIdx.x & 31u, sub = lane & 3u;
 	const u32 numWarps = gridDim.x * (blockDim.x >> 5), numGroups = (numCols + 7u) >> 3;
@@ -671,12 +684,16 @@ int launchExpandSmallLevels(const SmallExpandArgs& a, cudaStream_t stream) {
 }
 
 int launchExpandLevel(const PyramidView& pyr, int level, u32 zTileNum, const u64* coords, u64 n, u16* masks, u32* firstChild,
-		u64* childCoords, u64* childTotal, ScanLaunch scan, const u32* colBias, u32* leafAt, u32 numLeaves, cudaStream_t stream) {
+		u64* childCoords, u64* childTotal, ScanLaunch scan, const u32* colBias, u32* leafAt, u32 numLeaves, int minBlocks, cudaStream_t stream) {
 	const u32 side = (u32)pyr.n >> level;
 	const float heightF = (float)(side * zTileNum);
 	const u32 tiles = (u32)((n + kExpandTile - 1) / kExpandTile);
-	expandLevelKernel<<<tiles, kExpandThreads, 0, stream>>>(pyr.level[level], side, heightF, level == 0 ? 1 : 0, coords, n, masks, firstChild,
-			childCoords, childTotal, scan, tiles, colBias, leafAt, numLeaves);
+	if (minBlocks == 12)
+		expandLevelDenseKernel<<<tiles, kExpandThreads, 0, stream>>>(pyr.level[level], side, heightF, level == 0 ? 1 : 0, coords, n, masks, firstChild,
+				childCoords, childTotal, scan, tiles, colBias, leafAt, numLeaves);
+	else
+		expandLevelKernel<<<tiles, kExpandThreads, 0, stream>>>(pyr.level[level], side, heightF, level == 0 ? 1 : 0, coords, n, masks, firstChild,
+				childCoords, childTotal, scan, tiles, colBias, leafAt, numLeaves);
 	return 1;
 }
 
@@ -705,14 +722,22 @@ int launchBuildLeafColumns(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum,
 	const float2* level3 = reinterpret_cast<const float2*>(pyr.level[3]);
 	LeafSink out{leafAt, numLeaves, codes, masks, sketch, kSketchWords - 1};
 	const u32 wanted = (numCols + kColumnsPerCta - 1) / kColumnsPerCta;  // 8 warps of 8 columns per CTA
-	const u32 resident = 148u * (ctasPerSm >= 1u && ctasPerSm <= 3u ? ctasPerSm : 3u);  // persistent CTAs (launch bounds: 3 per SM)
+	const u32 resident = 148u * (ctasPerSm >= 1u && ctasPerSm <= 4u ? ctasPerSm : 3u);  // persistent CTAs
 	const u32 grid = wanted < resident ? wanted : resident;
-	if (leafAt)
-		buildLeafColumnsKernel<false><<<grid, 256, 0, stream>>>(pyr.level[0], (u32)pyr.n, colShift, heightF, height3F, zLoF, zHiF, level3, numCols,
-				colBias, out);
-	else
-		buildLeafColumnsKernel<true><<<grid, 256, 0, stream>>>(pyr.level[0], (u32)pyr.n, colShift, heightF, height3F, zLoF, zHiF, level3, numCols,
-				colBias, out);
+#define CPVS_LAUNCH_COLUMNS(BYPOS, BLOCKS)                                                                                                      \
+	buildLeafColumnsKernel<BYPOS, BLOCKS><<<grid, 256, 0, stream>>>(pyr.level[0], (u32)pyr.n, colShift, heightF, height3F, zLoF, zHiF, level3, numCols, \
+			colBias, out)
+	if (ctasPerSm == 4u) {  // the instantiation whose register allocation allows four CTAs per SM
+		if (leafAt)
+			CPVS_LAUNCH_COLUMNS(false, 4);
+		else
+			CPVS_LAUNCH_COLUMNS(true, 4);
+	} else if (leafAt) {
+		CPVS_LAUNCH_COLUMNS(false, 3);
+	} else {
+		CPVS_LAUNCH_COLUMNS(true, 3);
+	}
+#undef CPVS_LAUNCH_COLUMNS
 	return 1;
 }
 
