@@ -96,6 +96,7 @@ struct cpvs_ctx {
 	int leafByPosition;
 	int leafCtas;
 	int expandBlocks;  // experimental (CPVS_EXPAND_BLOCKS=12): expansion kernel held to 40 registers, 12 CTAs per SM
+	int innerDense;   // experimental (CPVS_INNER_BLOCKS=8): inner insert held to 32 registers, 8 CTAs per SM
 	int insertHints;  // experimental (CPVS_INSERT_HINTS=1): L2 eviction priorities in the leaf insert (merge.cu)
 	int emitPlanes;  // experimental (CPVS_EMIT_PLANES=1): leaf emission through bit planes (emit.cu emitLeavesPlanesKernel)
 	cudaEvent_t evLeafStart, evLeafStop;
@@ -260,6 +261,8 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 		ctx->emitPlanes = (pl && pl[0] == '1') ? 1 : 0;
 		const char* c = std::getenv("CPVS_LEAF_CTAS");
 		ctx->leafCtas = (c && c[0] >= '1' && c[0] <= '4') ? c[0] - '0' : (ctx->leafByPosition ? 2 : 3);
+		const char* ib = std::getenv("CPVS_INNER_BLOCKS");
+		ctx->innerDense = (ib && std::atoi(ib) == 8) ? 1 : 0;
 		const char* xb = std::getenv("CPVS_EXPAND_BLOCKS");
 		ctx->expandBlocks = (xb && std::atoi(xb) == 12) ? 12 : 1;
 	}
@@ -862,6 +865,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		m.leafCodes = a.leafCodes;
 		m.leafHash = a.leafHash;
 		m.hints = ctx->insertHints;
+		m.dense = ctx->innerDense;
 		m.leafAt = (leafLevel && leafByPosition) ? a.leafAt : nullptr;
 		m.minIndex = (leafLevel && leafByPosition) ? a.slotOffset : nullptr;
 		m.masks = a.masks;

@@ -93,6 +93,7 @@ struct MergeLevelArgs {
 	const u32* leafCodes;  // leaf: k-code, 8 words per node
 	const u64* leafHash;   // leaf: content hash per node, or NULL (then computed from the code)
 	const u32* leafAt;     // leaf: NULL, or leafCodes/masks are stored by column-order position p and leafAt[p] is the node's index
+	int dense;             // inner: the instantiation held to 32 registers (experimental, CPVS_INNER_BLOCKS=8)
 	int hints;             // leaf: L2 eviction priorities in the insert (experimental, CPVS_INSERT_HINTS=1; see merge.cu)
 	u32* minIndex;         // leaf, with leafAt: per table slot, the smallest node index of the group (set to ~0 by the sizing kernel)
 	const u16* masks;      // inner: childmask per node

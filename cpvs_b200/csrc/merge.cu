@@ -211,7 +211,7 @@ __device__ __forceinline__ u32 compactLitBits(u32 mask) {
 	return (x | (x >> 4)) & 0x00FFu;
 }
 
-__global__ void __launch_bounds__(256) insertInnerKernel(const u16* __restrict__ masks, const u32* __restrict__ firstChild,
+__device__ __forceinline__ void insertInnerBody(const u16* __restrict__ masks, const u32* __restrict__ firstChild,
 		const u32* __restrict__ childUid, u64 n, u64* __restrict__ table, u64 tableMask, u32* __restrict__ slotOf, u32* errorFlag) {
 	__shared__ u32 sFirst[kDirectSlots];
 	const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -234,6 +234,15 @@ __global__ void __launch_bounds__(256) insertInnerKernel(const u16* __restrict__
 		slotOf[j] = (u32)(tableMask + 1 + c) | (sFirst[c] == (u32)j ? kCandidateFlag : 0u);
 	else if (live)
 		slotOf[j] = insertInnerNode((u32)j, masks, firstChild, childUid, table, tableMask, errorFlag);
+}
+__global__ void __launch_bounds__(256) insertInnerKernel(const u16* __restrict__ masks, const u32* __restrict__ firstChild,
+		const u32* __restrict__ childUid, u64 n, u64* __restrict__ table, u64 tableMask, u32* __restrict__ slotOf, u32* errorFlag) {
+	insertInnerBody(masks, firstChild, childUid, n, table, tableMask, slotOf, errorFlag);
+}
+// The same, held to 32 registers (8 instead of 6 CTAs per SM, one 4-byte spill). Experimental, CPVS_INNER_BLOCKS=8.
+__global__ void __launch_bounds__(256, 8) insertInnerDenseKernel(const u16* __restrict__ masks, const u32* __restrict__ firstChild,
+		const u32* __restrict__ childUid, u64 n, u64* __restrict__ table, u64 tableMask, u32* __restrict__ slotOf, u32* errorFlag) {
+	insertInnerBody(masks, firstChild, childUid, n, table, tableMask, slotOf, errorFlag);
 }
 
 // gid[j] = slot of node j's group. Ranks the first occurrences (slot's final index == j) in order,
@@ -530,6 +539,8 @@ int launchInsertLevel(const MergeLevelArgs& a, cudaStream_t stream) {
 		insertLeavesKernel<true><<<blocks, 256, 0, stream>>>(a.leafCodes, a.leafHash, a.n, a.table, a.tableMaskDev, a.uid, a.errorFlag);
 	else if (a.leaf)
 		insertLeavesKernel<false><<<blocks, 256, 0, stream>>>(a.leafCodes, a.leafHash, a.n, a.table, a.tableMaskDev, a.uid, a.errorFlag);
+	else if (a.dense)
+		insertInnerDenseKernel<<<blocks, 256, 0, stream>>>(a.masks, a.firstChild, a.childUid, a.n, a.table, a.tableSize - 1, a.uid, a.errorFlag);
 	else
 		insertInnerKernel<<<blocks, 256, 0, stream>>>(a.masks, a.firstChild, a.childUid, a.n, a.table, a.tableSize - 1, a.uid, a.errorFlag);
 	return 1;

@@ -13,7 +13,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SETTINGS = [{}, {"CPVS_EMIT_PLANES": "1"}, {"CPVS_LEAF_ORDER": "1", "CPVS_LEAF_CTAS": "2"}, {"CPVS_LEAF_ORDER": "1", "CPVS_LEAF_CTAS": "3"},
-            {"CPVS_LEAF_ORDER": "1", "CPVS_LEAF_CTAS": "1"}, {"CPVS_LEAF_CTAS": "2"}, {"CPVS_LEAF_CTAS": "4"}, {"CPVS_LEAF_ORDER": "1", "CPVS_LEAF_CTAS": "4"}, {"CPVS_EXPAND_BLOCKS": "12"},
+            {"CPVS_LEAF_ORDER": "1", "CPVS_LEAF_CTAS": "1"}, {"CPVS_LEAF_CTAS": "2"}, {"CPVS_LEAF_CTAS": "4"}, {"CPVS_LEAF_ORDER": "1", "CPVS_LEAF_CTAS": "4"}, {"CPVS_EXPAND_BLOCKS": "12"}, {"CPVS_INNER_BLOCKS": "8"},
             {"CPVS_INSERT_HINTS": "1"},
             {"CPVS_LEAF_ORDER": "1", "CPVS_EMIT_PLANES": "1", "CPVS_INSERT_HINTS": "1"}]
 

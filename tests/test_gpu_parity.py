@@ -558,7 +558,7 @@ _experimental = pytest.mark.skipif(os.environ.get("CPVS_TEST_EXPERIMENTAL") != "
 
 @_experimental
 @pytest.mark.parametrize("env", [{"CPVS_LEAF_ORDER": "1"}, {"CPVS_LEAF_ORDER": "1", "CPVS_LEAF_CTAS": "3"},
-                                 {"CPVS_EMIT_PLANES": "1"}, {"CPVS_INSERT_HINTS": "1"}, {"CPVS_EXPAND_BLOCKS": "12"}, {"CPVS_LEAF_CTAS": "4"},
+                                 {"CPVS_EMIT_PLANES": "1"}, {"CPVS_INSERT_HINTS": "1"}, {"CPVS_EXPAND_BLOCKS": "12"}, {"CPVS_INNER_BLOCKS": "8"}, {"CPVS_LEAF_CTAS": "4"},
                                  {"CPVS_LEAF_ORDER": "1", "CPVS_LEAF_CTAS": "4"},
                                  {"CPVS_LEAF_ORDER": "1", "CPVS_EMIT_PLANES": "1", "CPVS_INSERT_HINTS": "1"}],
                          ids=lambda e: ",".join("%s=%s" % kv for kv in sorted(e.items())))
@@ -566,7 +566,7 @@ def test_experimental_switches_keep_the_words(oracle, env, monkeypatch):
     """Every experimental switch (README "Environment switches") must leave the DAG words untouched: leaves stored by
     column position and built beside the expansion (CPVS_LEAF_ORDER=1, needs the per-column builder, hence
     CPVS_LEAF_COLUMNS=2 here), the bit-plane leaf emission (CPVS_EMIT_PLANES=1), L2 eviction priorities in the leaf insert
-    (CPVS_INSERT_HINTS=1), the denser register allocations (CPVS_EXPAND_BLOCKS=12, CPVS_LEAF_CTAS=4)."""
+    (CPVS_INSERT_HINTS=1), the denser register allocations (CPVS_EXPAND_BLOCKS=12, CPVS_INNER_BLOCKS=8, CPVS_LEAF_CTAS=4)."""
     monkeypatch.setenv("CPVS_LEAF_COLUMNS", "2")
     for k, v in env.items():
         monkeypatch.setenv(k, v)
