@@ -89,17 +89,6 @@ struct cpvs_ctx {
 	cudaStream_t aux2, aux3;  // the ranks of different levels are independent: alternate between the two
 	cudaEvent_t evRankStart, evRankStop, evJoin3, evClear, evCols;
 	int leafColumns;  // leaves built per column: 1 = where it pays (default), 0 = never, 2 = always (CPVS_LEAF_COLUMNS; tests)
-	// Experimental (CPVS_LEAF_ORDER=1, off by default; only with the per-column builder): leaf codes and masks are stored by
-	// column-order position, so the leaf builder needs nothing from the expansion and runs beside it on a side stream; the
-	// merge maps positions to level indices. leafCtas (CPVS_LEAF_CTAS=1..4): resident CTAs per SM of the persistent builder
-	// (default 3; 2 when it runs beside the expansion, whose CTAs need registers of their own).
-	int leafByPosition;
-	int leafCtas;
-	int expandBlocks;  // experimental (CPVS_EXPAND_BLOCKS=12): expansion kernel held to 40 registers, 12 CTAs per SM
-	int innerDense;   // experimental (CPVS_INNER_BLOCKS=8): inner insert held to 32 registers, 8 CTAs per SM
-	int insertHints;  // experimental (CPVS_INSERT_HINTS=1): L2 eviction priorities in the leaf insert (merge.cu)
-	int emitPlanes;  // experimental (CPVS_EMIT_PLANES=1): leaf emission through bit planes (emit.cu emitLeavesPlanesKernel)
-	cudaEvent_t evLeafStart, evLeafStop;
 };
 
 struct cpvs_minmax {
@@ -251,23 +240,6 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 		const char* v = std::getenv("CPVS_LEAF_COLUMNS");
 		ctx->leafColumns = (v && v[0] >= '0' && v[0] <= '2') ? v[0] - '0' : 1;
 	}
-	ctx->evLeafStart = ctx->evLeafStop = nullptr;
-	{
-		const char* v = std::getenv("CPVS_LEAF_ORDER");
-		ctx->leafByPosition = (v && v[0] == '1') ? 1 : 0;
-		const char* ih = std::getenv("CPVS_INSERT_HINTS");
-		ctx->insertHints = (ih && ih[0] == '1') ? 1 : 0;
-		const char* pl = std::getenv("CPVS_EMIT_PLANES");
-		ctx->emitPlanes = (pl && pl[0] == '1') ? 1 : 0;
-		const char* c = std::getenv("CPVS_LEAF_CTAS");
-		ctx->leafCtas = (c && c[0] >= '1' && c[0] <= '4') ? c[0] - '0' : (ctx->leafByPosition ? 2 : 3);
-		const char* ib = std::getenv("CPVS_INNER_BLOCKS");
-		ctx->innerDense = (ib && std::atoi(ib) == 8) ? 1 : 0;
-		const char* xb = std::getenv("CPVS_EXPAND_BLOCKS");
-		ctx->expandBlocks = (xb && std::atoi(xb) == 12) ? 12 : 1;
-	}
-	if (e == cudaSuccess) e = cudaEventCreate(&ctx->evLeafStart);
-	if (e == cudaSuccess) e = cudaEventCreate(&ctx->evLeafStop);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux2, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux3, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evJoin3, cudaEventDisableTiming);
@@ -303,8 +275,6 @@ int cpvs_ctx_destroy(cpvs_ctx* ctx) {
 	if (ctx->evCols) cudaEventDestroy(ctx->evCols);
 	if (ctx->evRankStart) cudaEventDestroy(ctx->evRankStart);
 	if (ctx->evRankStop) cudaEventDestroy(ctx->evRankStop);
-	if (ctx->evLeafStart) cudaEventDestroy(ctx->evLeafStart);
-	if (ctx->evLeafStop) cudaEventDestroy(ctx->evLeafStop);
 	if (ctx->own) cudaStreamDestroy(ctx->own);
 	delete ctx;
 	return CPVS_OK;
@@ -684,8 +654,6 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	const bool leafColumns = needSketch && (ctx->leafColumns == 2 || (ctx->leafColumns == 1 && zTileNum == 1 && mm->n >= 8192 &&
 																   lv[2].n >= 2 * allCols && lv[2].n <= 8 * allCols));
 	const u64 numCols = leafColumns ? ((u64)mm->n >> 3) * ((u64)mm->n >> 3) : 0;
-	// experimental: leaves stored by column-order position, built beside the expansion (see cpvs_ctx::leafByPosition)
-	const bool leafByPosition = leafColumns && haveLeaves && ctx->leafByPosition;
 	u32* dColBias = nullptr;
 	if (leafColumns) {
 		scanTiles += (numCols + kScanTile - 1) / kScanTile;
@@ -758,12 +726,6 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		ScanLaunch colScan{dTickets + scanLaunches - 1, dTiles + scanTiles - (numCols + kScanTile - 1) / kScanTile};
 		ctx->launches += launchColumnBias(pyr, zTileIndex, zTileNum, dColBias, colScan, ctx->aux2);
 		CPVS_CUDA(cudaEventRecord(ctx->evCols, ctx->aux2));
-		if (leafByPosition) {  // constructLastLevels (src/CompressedShadow.cpp:171-190), beside the expansion below
-			CPVS_CUDA(cudaEventRecord(ctx->evLeafStart, ctx->aux2));
-			ctx->launches += launchBuildLeafColumns(pyr, zTileIndex, zTileNum, dColBias, nullptr, (u32)lv[2].n, lv[2].leafCodes, lv[2].masks, dSketch,
-					(u32)ctx->leafCtas, ctx->aux2);
-			CPVS_CUDA(cudaEventRecord(ctx->evLeafStop, ctx->aux2));
-		}
 	}
 	bool tablesClearing = false;
 	for (int l = minLevel; l < smallLow; ++l)
@@ -822,14 +784,12 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		const bool toColumns = leafColumns && l == 3;
 		if (toColumns) CPVS_CUDA(cudaStreamWaitEvent(st, ctx->evCols, 0));
 		ctx->launches += launchExpandLevel(pyr, l, zTileNum, lv[l].coords, lv[l].n, lv[l].masks, lv[l].firstChild, childCoords,
-				dChildTotal + l, nextScan(lv[l].n, kExpandTileNodes), toColumns ? dColBias : nullptr, toColumns ? lv[2].leafAt : nullptr, (u32)lv[2].n, ctx->expandBlocks, st);
+				dChildTotal + l, nextScan(lv[l].n, kExpandTileNodes), toColumns ? dColBias : nullptr, toColumns ? lv[2].leafAt : nullptr, (u32)lv[2].n, st);
 	}
 	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAVES], st));
-	if (leafByPosition)  // already running on the side stream; the merge below waits for it
-		CPVS_CUDA(cudaStreamWaitEvent(st, ctx->evLeafStop, 0));
-	else if (leafColumns)  // constructLastLevels (src/CompressedShadow.cpp:171-190)
+	if (leafColumns)  // constructLastLevels (src/CompressedShadow.cpp:171-190)
 		ctx->launches += launchBuildLeafColumns(pyr, zTileIndex, zTileNum, dColBias, lv[2].leafAt, (u32)lv[2].n, lv[2].leafCodes, lv[2].masks,
-				dSketch, (u32)ctx->leafCtas, st);
+				dSketch, st);
 	else if (useLeaf && lv[2].n)
 		ctx->launches += launchBuildLeaves(pyr, zTileNum, lv[2].coords, lv[2].n, lv[2].leafCodes, lv[2].leafHash, lv[2].masks,
 				dSketch, st);
@@ -843,9 +803,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAF_TABLE], mergeStream));
 	if (haveLeaves) {
 		ctx->launches += launchSketchPopcount(dSketch, dSketchBits, mergeStream);
-		// (by position: the per-slot smallest index lives in the level's slotOffset array until the rank's last kernel overwrites it)
-		ctx->launches += launchSizeLeafTable(lv[2].table, lv[2].tableSlots, dSketchBits, dLeafTableMask, leafByPosition ? lv[2].slotOffset : nullptr,
-				mergeStream);
+		ctx->launches += launchSizeLeafTable(lv[2].table, lv[2].tableSlots, dSketchBits, dLeafTableMask, mergeStream);
 	}
 	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAF_INSERT], mergeStream));
 	if (!(useLeaf && lv[2].n)) {
@@ -864,10 +822,6 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		m.leaf = leafLevel ? 1 : 0;
 		m.leafCodes = a.leafCodes;
 		m.leafHash = a.leafHash;
-		m.hints = ctx->insertHints;
-		m.dense = ctx->innerDense;
-		m.leafAt = (leafLevel && leafByPosition) ? a.leafAt : nullptr;
-		m.minIndex = (leafLevel && leafByPosition) ? a.slotOffset : nullptr;
 		m.masks = a.masks;
 		m.firstChild = a.firstChild;
 		m.childUid = l > minLevel ? lv[l - 1].uid : nullptr;
@@ -981,7 +935,6 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		EmitLevelArgs em;
 		em.n = hScalars[32 + l];  // unique nodes of the level (read back with the sizes): exact grid
 		em.leaf = isLeaf ? 1 : 0;
-		em.planes = ctx->emitPlanes;
 		em.uniqueCount = dUnique + l;
 		em.wordCount = dWords + l;
 		em.firstList = a.firstList;
@@ -1021,7 +974,6 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	if (e == cudaSuccess) e = cudaEventElapsedTime(&phaseMs[CPVS_PHASE_EMIT_INNER], phases.ev[CPVS_PHASE_EMIT_INNER], phases.ev[CPVS_NUM_PHASES]);
 	if (e == cudaSuccess && leafEmit) e = cudaEventElapsedTime(&phaseMs[CPVS_PHASE_EMIT_LEAVES], ctx->evAuxStart, phases.ev[CPVS_PHASE_EMIT_LEAVES]);
 	if (e == cudaSuccess && haveLeaves) e = cudaEventElapsedTime(&phaseMs[CPVS_PHASE_LEAF_RESOLVE], ctx->evRankStart, ctx->evRankStop);
-	if (e == cudaSuccess && leafByPosition) e = cudaEventElapsedTime(&phaseMs[CPVS_PHASE_LEAVES], ctx->evLeafStart, ctx->evLeafStop);
 	if (e != cudaSuccess) {
 		cudaFreeAsync(s->dag, st);
 		delete s;

@@ -52,33 +52,6 @@ __device__ __forceinline__ Float8 ldSector256(const float* p) {
 	return r;
 }
 
-// 256-bit loads with an L2 eviction priority (sm_100: the priority qualifiers exist for 256-bit loads only). "Keep" marks the
-// line evict-last -- for the few lines a kernel returns to at random while it streams hundreds of MB past them; "stream"
-// marks the passing data evict-first and keeps it out of L1.
-struct Uint8 {
-	u32 v[8];
-};
-__device__ __forceinline__ Uint8 ldKeep256(const u32* p) {
-	Uint8 r;
-	asm volatile("ld.global.L2::evict_last.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-				 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
-				 : "l"(p));
-	return r;
-}
-__device__ __forceinline__ Uint8 ldStream256(const u32* p) {
-	Uint8 r;
-	asm volatile("ld.global.L1::no_allocate.L2::evict_first.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-				 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
-				 : "l"(p));
-	return r;
-}
-// L2 cache policy "evict last" for loads that take a policy operand (narrower than 256 bits).
-__device__ __forceinline__ u64 l2KeepPolicy() {
-	u64 policy;
-	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
-	return policy;
-}
-
 __device__ __forceinline__ u64 mix64(u64 h) {
 	h ^= h >> 33;
 	h *= 0xFF51AFD7ED558CCDull;
@@ -116,11 +89,6 @@ __device__ __forceinline__ void stRelaxed32(u32* p, u32 v) {
 __device__ __forceinline__ u64 ldRelaxed64(const u64* p) {
 	u64 v;
 	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-	return v;
-}
-__device__ __forceinline__ u64 ldRelaxed64Keep(const u64* p, u64 policy) {
-	u64 v;
-	asm volatile("ld.relaxed.gpu.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(policy) : "memory");
 	return v;
 }
 __device__ __forceinline__ void stRelaxed64(u64* p, u64 v) {

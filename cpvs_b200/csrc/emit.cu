@@ -68,39 +68,12 @@ __global__ void __launch_bounds__(kEmitThreads) emitInnerLevelsKernel(EmitMultiA
 }
 
 // Leaves: expands the k-code (nibble x of word y = lit slices of texel (x,y)) into the 64-bit masks of
-// the PARTIAL slices, bit x + 8y = lit (createLeafmask, src/CompressedShadowUtil.cpp:59-78).
-// (rowBits: leafbits.cuh)
+// the PARTIAL slices, bit x + 8y = lit (createLeafmask, src/CompressedShadowUtil.cpp:59-78) -- through bit planes
+// (leafbits.cuh): the code is transposed once, every slice is then one or two logic instructions per half, and the loop over
+// the slices is unrolled with predicated stores. About 330 executed instructions per terrain leaf (nearly all of its slices
+// PARTIAL) against 850 for row-by-row nibble compares: 0.200 -> 0.174 ms at 16K^2 terrain (profiles/r1_switch_probe.txt).
 
 __global__ void __launch_bounds__(kEmitThreads) emitLeavesKernel(EmitLevelArgs a) {
-	__shared__ u32 sOut[kEmitThreads * 17];
-	const u64 unique = *a.uniqueCount;
-	const u64 r0 = (u64)blockIdx.x * kEmitThreads;
-	if (r0 >= unique) return;
-	const u64 r = r0 + threadIdx.x;
-	const u32 runStart = a.wordOffset[r0];
-	const u32 runEnd = (r0 + kEmitThreads < unique) ? a.wordOffset[r0 + kEmitThreads] : (u32)*a.wordCount;
-	if (r < unique) {
-		const u32 j = a.firstList[r];
-		const u32 mask = a.masks[j];
-		u32* out = sOut + (a.wordOffset[r] - runStart);
-		*out++ = mask;
-		const uint4* src = reinterpret_cast<const uint4*>(a.leafCodes + (u64)j * 8);
-		const uint4 c0 = src[0], c1 = src[1];
-		// only the PARTIAL slices, lowest first: the warp iterates as often as its busiest leaf has such slices
-		for (u32 part = mask & 0xAAAAu; part; part &= part - 1u) {
-			const u32 slice = (u32)(__ffs((int)part) - 1) >> 1;
-			*out++ = rowBits(c0.x, slice) | (rowBits(c0.y, slice) << 8) | (rowBits(c0.z, slice) << 16) | (rowBits(c0.w, slice) << 24);
-			*out++ = rowBits(c1.x, slice) | (rowBits(c1.y, slice) << 8) | (rowBits(c1.z, slice) << 16) | (rowBits(c1.w, slice) << 24);
-		}
-	}
-	__syncthreads();
-	emitRun(a, sOut, runStart, runEnd - runStart);
-}
-
-// The same through bit planes (leafbits.cuh): the code is transposed once, every slice is then a couple of logic
-// instructions, and the loop over the slices is unrolled with predicated stores -- about a quarter of the instructions
-// when most slices of a leaf are PARTIAL (terrain-like surfaces). Experimental, CPVS_EMIT_PLANES=1.
-__global__ void __launch_bounds__(kEmitThreads) emitLeavesPlanesKernel(EmitLevelArgs a) {
 	__shared__ u32 sOut[kEmitThreads * 17];
 	const u64 unique = *a.uniqueCount;
 	const u64 r0 = (u64)blockIdx.x * kEmitThreads;
@@ -154,9 +127,7 @@ int launchEmitInnerLevels(EmitMultiArgs& m, cudaStream_t stream) {
 
 int launchEmitLevel(const EmitLevelArgs& a, cudaStream_t stream) {
 	const unsigned blocks = (unsigned)((a.n + 255) / 256);
-	if (a.leaf && a.planes)
-		emitLeavesPlanesKernel<<<blocks, 256, 0, stream>>>(a);
-	else if (a.leaf)
+	if (a.leaf)
 		emitLeavesKernel<<<blocks, 256, 0, stream>>>(a);
 	else
 		emitInnerKernel<<<blocks, 256, 0, stream>>>(a);

@@ -37,8 +37,7 @@ constexpr u64 kExpandTileNodes = 128 * kScanItems;  // nodes per look-back tile 
 // With leafAt != NULL the children are leaves built per column (launchBuildLeafColumns): instead of their
 // coordinates, each child's index is stored at its column-order position leafAt[colBias[column] + z].
 int launchExpandLevel(const PyramidView& pyr, int level, u32 zTileNum, const u64* coords, u64 n, u16* masks,
-		u32* firstChild, u64* childCoords, u64* childTotal, ScanLaunch scan, const u32* colBias, u32* leafAt, u32 numLeaves, int minBlocks,
-		cudaStream_t stream);  // minBlocks: 12 selects the 40-register instantiation (experimental), anything else the default
+		u32* firstChild, u64* childCoords, u64* childTotal, ScanLaunch scan, const u32* colBias, u32* leafAt, u32 numLeaves, cudaStream_t stream);
 
 // The small top levels (<= kSmallMaxNodes nodes each, root first) expanded by a single CTA.
 constexpr int kSmallThreads = 1024;
@@ -76,12 +75,8 @@ int launchBuildLeaves(const PyramidView& pyr, u32 zTileNum, const u64* coords, u
 // level, written by the expansion of level 3.
 int launchColumnBias(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, u32* colBias, ScanLaunch scan, cudaStream_t stream);
 // (No hash array: the insert derives its hash from the code when MergeLevelArgs::leafHash is NULL.)
-// leafAt == NULL: codes[] and masks[] are stored by column-order position instead of by index in the level. The builder then
-// needs nothing from the expansion and may run beside it; the merge maps positions to indices (MergeLevelArgs::leafAt).
-// ctasPerSm (1..4): resident CTAs per SM of the persistent kernel; fewer leave room for kernels running beside it, 4 selects
-// an instantiation held to 64 registers.
 int launchBuildLeafColumns(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, const u32* colBias, const u32* leafAt, u32 numLeaves, u32* codes,
-		u16* masks, u32* sketch, u32 ctasPerSm, cudaStream_t stream);
+		u16* masks, u32* sketch, cudaStream_t stream);
 int launchSketchPopcount(const u32* sketch, u64* setBits, cudaStream_t stream);
 
 // ---- merge.cu: mergeCommonSubtrees (reference src/CompressedShadow.cpp:215-304, Util.h:154-182) ----
@@ -92,10 +87,6 @@ struct MergeLevelArgs {
 	int leaf;              // 1: level of leafmask nodes
 	const u32* leafCodes;  // leaf: k-code, 8 words per node
 	const u64* leafHash;   // leaf: content hash per node, or NULL (then computed from the code)
-	const u32* leafAt;     // leaf: NULL, or leafCodes/masks are stored by column-order position p and leafAt[p] is the node's index
-	int dense;             // inner: the instantiation held to 32 registers (experimental, CPVS_INNER_BLOCKS=8)
-	int hints;             // leaf: L2 eviction priorities in the insert (experimental, CPVS_INSERT_HINTS=1; see merge.cu)
-	u32* minIndex;         // leaf, with leafAt: per table slot, the smallest node index of the group (set to ~0 by the sizing kernel)
 	const u16* masks;      // inner: childmask per node
 	const u32* firstChild; // inner: index of first child in the level below
 	const u32* childUid;   // inner: unique id of every node of the level below
@@ -134,9 +125,8 @@ struct SmallMergeArgs {
 };
 int launchMergeSmallLevels(const SmallMergeArgs& a, cudaStream_t stream);
 
-// Leaf level only: picks the table capacity from the sketch's set-bit count and clears that many slots
-// (and as many entries of minIndex, if given).
-int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* tableMaskDev, u32* minIndex, cudaStream_t stream);
+// Leaf level only: picks the table capacity from the sketch's set-bit count and clears that many slots.
+int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* tableMaskDev, cudaStream_t stream);
 // Insert assigns group ids (all the parent level needs); rank orders the unique nodes and may run
 // concurrently with the next level's insert as long as this level's table is left alone.
 int launchInsertLevel(const MergeLevelArgs& a, cudaStream_t stream);
@@ -146,7 +136,6 @@ int launchRankLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaStream_t strea
 struct EmitLevelArgs {
 	u64 n;                    // unique nodes of the level (or any upper bound: sizes the grid)
 	int leaf;
-	int planes;               // leaf: expand the k-code through bit planes (leafbits.cuh; experimental, CPVS_EMIT_PLANES=1)
 	const u64* uniqueCount;   // device: unique nodes of this level
 	const u32* firstList;
 	const u32* wordOffset;

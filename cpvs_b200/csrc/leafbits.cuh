@@ -19,8 +19,8 @@
 
 namespace cpvs {
 
-// The direct way (the default emission): one row of one slice. nibble k > slice <=> bit 3 of (k + 7 - slice); nibbles are
-// <= 8 so nothing carries.
+// The direct way (what the emission did before the planes; kept as the second opinion of tests/test_leaf_bits.py): one row of
+// one slice. nibble k > slice <=> bit 3 of (k + 7 - slice); nibbles are <= 8 so nothing carries.
 CPVS_HD uint32_t rowBits(uint32_t code, uint32_t slice) {
 	uint32_t y = ((code + (7u - slice) * 0x11111111u) >> 3) & 0x11111111u;
 	y = (y | (y >> 3)) & 0x03030303u;

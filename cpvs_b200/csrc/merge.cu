@@ -30,20 +30,13 @@ static_assert(kDirectSlots == 256, "one direct slot per thread of the insert CTA
 constexpr u32 kCandidateFlag = 0x80000000u, kGidMask = 0x7FFFFFFFu;
 
 // kShared: the table lives in shared memory (single-CTA kernels for the small levels).
-// kKeep: probes mark the table's lines evict-last in L2 (leaf level, CPVS_INSERT_HINTS=1).
-template <bool kShared = false, bool kKeep = false, typename Equal>
+template <bool kShared = false, typename Equal>
 __device__ __forceinline__ u32 findGroupSlot(u64* __restrict__ table, u64 tableMask, u64 hash, u32 self, u32* errorFlag, Equal sameTuple) {
 	const u64 fp = hash >> 32;
 	const u64 key = (fp << 32) | self;
 	u64 slot = hash & tableMask;
-	u64 keepPolicy = 0;
-	if constexpr (kKeep) keepPolicy = l2KeepPolicy();
 	for (u64 probes = 0; probes <= tableMask; ++probes) {
-		u64 v;
-		if constexpr (kKeep)
-			v = ldRelaxed64Keep(table + slot, keepPolicy);
-		else
-			v = kShared ? *reinterpret_cast<volatile u64*>(table + slot) : ldRelaxed64(table + slot);
+		u64 v = kShared ? *reinterpret_cast<volatile u64*>(table + slot) : ldRelaxed64(table + slot);
 		if (v == kEmpty) {
 			const u64 old = atomicCAS(reinterpret_cast<unsigned long long*>(table + slot), (unsigned long long)kEmpty, (unsigned long long)key);
 			if (old == kEmpty) return (u32)slot | kCandidateFlag;
@@ -70,9 +63,8 @@ __device__ __forceinline__ u32 findGroupSlot(u64* __restrict__ table, u64 tableM
 // Leaf table capacity from the distinct-count sketch (linear counting: u ~ -m ln(zero fraction)), rounded
 // up to a power of two with >= 1.5x headroom, then cleared. The result does not depend on the capacity,
 // only the speed does: a table sized for the distinct leaves (not for all leaves) stays in L2.
-template <bool kWithMinIndex>
 __global__ void __launch_bounds__(256) sizeAndClearLeafTableKernel(u64* __restrict__ table, u64 maxSlots, const u64* __restrict__ setBits,
-		u64* __restrict__ tableMaskDev, u32* __restrict__ minIndex) {
+		u64* __restrict__ tableMaskDev) {
 	const float m = (float)kSketchWords * 32.0f;
 	const float frac = fminf((float)*setBits / m, 0.999f);
 	const float distinct = -m * log1pf(-frac);
@@ -83,52 +75,16 @@ __global__ void __launch_bounds__(256) sizeAndClearLeafTableKernel(u64* __restri
 	if (blockIdx.x == 0 && threadIdx.x == 0) *tableMaskDev = cap - 1;
 	ulonglong2* t2 = reinterpret_cast<ulonglong2*>(table);
 	for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap / 2; i += (u64)gridDim.x * blockDim.x) t2[i] = make_ulonglong2(kEmpty, kEmpty);
-	if constexpr (kWithMinIndex) {  // leaves stored by position: first occurrences are tracked beside the table (insertLeavesByPositionKernel)
-		uint4* m4 = reinterpret_cast<uint4*>(minIndex);
-		for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap / 4; i += (u64)gridDim.x * blockDim.x)
-			m4[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-	}
 }
 
-// kHints (experimental, CPVS_INSERT_HINTS=1): L2 eviction priorities. The kernel streams every code once (447 MB at 16K^2
-// terrain) while it keeps returning, at random, to the table (32 MiB) and to the codes of the groups' witnesses (~80 MB of
-// scattered 32-byte sectors); the profile shows 40 % L2 hits and 0.3 GB of DRAM reads beyond the stream, i.e. the stream
-// evicts the witnesses. With the switch the own code is one 256-bit evict-first load, witness codes and table probes are
-// evict-last.
-template <bool kHints>
-__device__ __forceinline__ void loadOwnCode(const u32* __restrict__ codes, u64 at, uint4& a0, uint4& a1) {
-	if constexpr (kHints) {
-		const Uint8 c = ldStream256(codes + at * 8);
-		a0 = make_uint4(c.v[0], c.v[1], c.v[2], c.v[3]);
-		a1 = make_uint4(c.v[4], c.v[5], c.v[6], c.v[7]);
-	} else {
-		const uint4* mine = reinterpret_cast<const uint4*>(codes + at * 8);
-		a0 = __ldcs(mine);
-		a1 = __ldcs(mine + 1);
-	}
-}
-template <bool kHints>
-__device__ __forceinline__ bool sameCode(const u32* __restrict__ codes, u32 other, const uint4& a0, const uint4& a1) {
-	if constexpr (kHints) {
-		const Uint8 b = ldKeep256(codes + (u64)other * 8);
-		return a0.x == b.v[0] && a0.y == b.v[1] && a0.z == b.v[2] && a0.w == b.v[3] && a1.x == b.v[4] && a1.y == b.v[5] && a1.z == b.v[6] &&
-			   a1.w == b.v[7];
-	} else {
-		const uint4* theirs = reinterpret_cast<const uint4*>(codes + (u64)other * 8);
-		const uint4 b0 = theirs[0], b1 = theirs[1];
-		return a0.x == b0.x && a0.y == b0.y && a0.z == b0.z && a0.w == b0.w && a1.x == b1.x && a1.y == b1.y && a1.z == b1.z && a1.w == b1.w;
-	}
-}
-
-template <bool kHints>
 __global__ void __launch_bounds__(256) insertLeavesKernel(const u32* __restrict__ codes, const u64* __restrict__ hashes, u64 n, u64* __restrict__ table,
 		const u64* __restrict__ tableMaskDev, u32* __restrict__ slotOf, u32* errorFlag) {
 	const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	if (j >= n) return;
 	const u64 tableMask = *tableMaskDev;
 	// own code and hash are fetched up front so that their latency overlaps the first table probe
-	uint4 a0, a1;
-	loadOwnCode<kHints>(codes, j, a0, a1);
+	const uint4* mine = reinterpret_cast<const uint4*>(codes + j * 8);
+	const uint4 a0 = __ldcs(mine), a1 = __ldcs(mine + 1);
 	u64 hash;
 	if (hashes) {
 		hash = __ldcs(hashes + j);
@@ -140,36 +96,11 @@ __global__ void __launch_bounds__(256) insertLeavesKernel(const u32* __restrict_
 		h = (h ^ (h >> 32) ^ (((u64)a1.w << 32) | a1.z)) * 0xC4CEB9FE1A85EC53ull;
 		hash = mix64(h);
 	}
-	slotOf[j] = findGroupSlot<false, kHints>(table, tableMask, hash, (u32)j, errorFlag, [&](u32 other) { return sameCode<kHints>(codes, other, a0, a1); });
-}
-
-// Leaves stored by column-order position (launchBuildLeafColumns with leafAt == NULL): thread p handles the leaf whose code sits
-// at position p and whose index in the level is j = leafAt[p]. The table groups by position (slot = fingerprint | smallest
-// position: any member serves as the witness a newcomer compares against); which member comes first in the level -- what the
-// reference's layout needs -- is kept beside it as minIndex[slot] = smallest j, read before the atomic so that the members of
-// a popular group do not queue up on one address. A node is a candidate for "first occurrence" iff it lowered minIndex.
-// The group id goes to slotOf[j]: 4-byte stores scattered over the level instead of the builder's 32-byte ones.
-template <bool kHints>
-__global__ void __launch_bounds__(256) insertLeavesByPositionKernel(const u32* __restrict__ codes, const u32* __restrict__ leafAt, u64 n,
-		u64* __restrict__ table, const u64* __restrict__ tableMaskDev, u32* __restrict__ minIndex, u32* __restrict__ slotOf, u32* errorFlag) {
-	const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-	if (p >= n) return;
-	const u64 tableMask = *tableMaskDev;
-	uint4 a0, a1;
-	loadOwnCode<kHints>(codes, p, a0, a1);
-	const u32 j = __ldcs(leafAt + p);
-	u64 h = 0x9E3779B97F4A7C15ull;
-	h = (h ^ (((u64)a0.y << 32) | a0.x)) * 0xFF51AFD7ED558CCDull;
-	h = (h ^ (h >> 32) ^ (((u64)a0.w << 32) | a0.z)) * 0xC4CEB9FE1A85EC53ull;
-	h = (h ^ (h >> 32) ^ (((u64)a1.y << 32) | a1.x)) * 0xFF51AFD7ED558CCDull;
-	h = (h ^ (h >> 32) ^ (((u64)a1.w << 32) | a1.z)) * 0xC4CEB9FE1A85EC53ull;
-	const u32 slot =
-			findGroupSlot<false, kHints>(table, tableMask, mix64(h), (u32)p, errorFlag, [&](u32 other) { return sameCode<kHints>(codes, other, a0, a1); }) &
-			kGidMask;
-	if (j >= n) return;  // cannot happen on an ordered pyramid (see the expansion); the count check reports such maps
-	u32 candidate = 0;
-	if (ldRelaxed32(minIndex + slot) > j) candidate = atomicMin(minIndex + slot, j) > j ? kCandidateFlag : 0u;
-	slotOf[j] = slot | candidate;
+	slotOf[j] = findGroupSlot(table, tableMask, hash, (u32)j, errorFlag, [&](u32 other) {
+		const uint4* theirs = reinterpret_cast<const uint4*>(codes + (u64)other * 8);
+		const uint4 b0 = theirs[0], b1 = theirs[1];
+		return a0.x == b0.x && a0.y == b0.y && a0.z == b0.z && a0.w == b0.w && a1.x == b1.x && a1.y == b1.y && a1.z == b1.z && a1.w == b1.w;
+	});
 }
 
 template <bool kShared = false>
@@ -211,7 +142,10 @@ __device__ __forceinline__ u32 compactLitBits(u32 mask) {
 	return (x | (x >> 4)) & 0x00FFu;
 }
 
-__device__ __forceinline__ void insertInnerBody(const u16* __restrict__ masks, const u32* __restrict__ firstChild,
+// Held to 32 registers (8 instead of 6 CTAs of 256 threads per SM, one 4-byte spill): the kernel waits on dependent loads 62 % of
+// the time, and the two extra CTAs are worth 0.03 ms on the 16K^2 terrain (inner merge 0.436 -> 0.409 ms, the leaf rank running
+// beside it 0.375 -> 0.348 ms; profiles/r1_switch_probe.txt).
+__global__ void __launch_bounds__(256, 8) insertInnerKernel(const u16* __restrict__ masks, const u32* __restrict__ firstChild,
 		const u32* __restrict__ childUid, u64 n, u64* __restrict__ table, u64 tableMask, u32* __restrict__ slotOf, u32* errorFlag) {
 	__shared__ u32 sFirst[kDirectSlots];
 	const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -235,15 +169,6 @@ __device__ __forceinline__ void insertInnerBody(const u16* __restrict__ masks, c
 	else if (live)
 		slotOf[j] = insertInnerNode((u32)j, masks, firstChild, childUid, table, tableMask, errorFlag);
 }
-__global__ void __launch_bounds__(256) insertInnerKernel(const u16* __restrict__ masks, const u32* __restrict__ firstChild,
-		const u32* __restrict__ childUid, u64 n, u64* __restrict__ table, u64 tableMask, u32* __restrict__ slotOf, u32* errorFlag) {
-	insertInnerBody(masks, firstChild, childUid, n, table, tableMask, slotOf, errorFlag);
-}
-// The same, held to 32 registers (8 instead of 6 CTAs per SM, one 4-byte spill). Experimental, CPVS_INNER_BLOCKS=8.
-__global__ void __launch_bounds__(256, 8) insertInnerDenseKernel(const u16* __restrict__ masks, const u32* __restrict__ firstChild,
-		const u32* __restrict__ childUid, u64 n, u64* __restrict__ table, u64 tableMask, u32* __restrict__ slotOf, u32* errorFlag) {
-	insertInnerBody(masks, firstChild, childUid, n, table, tableMask, slotOf, errorFlag);
-}
 
 // gid[j] = slot of node j's group. Ranks the first occurrences (slot's final index == j) in order,
 // prefix-sums their compressed sizes, and records firstList[rank], wordOffset[rank] and, per group,
@@ -253,11 +178,8 @@ __global__ void __launch_bounds__(256, 8) insertInnerDenseKernel(const u16* __re
 // (the only part with random accesses) and leave each node's compressed size in a byte plus the tile's
 // totals; (2) one CTA prefix-sums the tile totals; (3) per tile, a block scan of the bytes and the writes.
 // No CTA ever waits for another one, which matters more here than the extra byte per node of traffic.
-// kByPosition (leaves stored by column-order position): first occurrence <=> minIndex[slot] == j; the node's mask is read
-// at the group's witness position, the low word of the slot (equal codes have equal masks).
-template <bool kByPosition>
 __global__ void __launch_bounds__(kScanThreads, 8) rankCountKernel(const u64* __restrict__ table, const u16* __restrict__ masks, int leaf, u64 n,
-		const u32* __restrict__ gid, unsigned char* __restrict__ sizeOf, ScanTileState* __restrict__ tiles, const u32* __restrict__ minIndex) {
+		const u32* __restrict__ gid, unsigned char* __restrict__ sizeOf, ScanTileState* __restrict__ tiles) {
 	const u64 base = (u64)blockIdx.x * kScanTile + (u64)threadIdx.x * kScanItems;
 	u32 words[kScanItems];
 	u64 cnt = 0, wsum = 0;
@@ -266,14 +188,7 @@ __global__ void __launch_bounds__(kScanThreads, 8) rankCountKernel(const u64* __
 		words[i] = 0;
 		if (base + i < n) {
 			const u32 g = gid[base + i];
-			if constexpr (kByPosition) {
-				if ((g & kCandidateFlag) && minIndex[g & kGidMask] == (u32)(base + i)) {
-					const u32 k = __popc(masks[(u32)table[g & kGidMask]] & 0xAAAAu);
-					words[i] = 1 + (leaf ? 2 * k : k);
-					cnt += 1;
-					wsum += words[i];
-				}
-			} else if ((g & kCandidateFlag) && (u32)table[g & kGidMask] == (u32)(base + i)) {
+			if ((g & kCandidateFlag) && (u32)table[g & kGidMask] == (u32)(base + i)) {
 				const u32 k = __popc(masks[base + i] & 0xAAAAu);
 				words[i] = 1 + (leaf ? 2 * k : k);
 				cnt += 1;
@@ -365,12 +280,8 @@ __global__ void __launch_bounds__(kScanTilesThreads) rankScanTilesKernel(ScanTil
 	}
 }
 
-// kByPosition: firstList[] receives the witness position of the group (where the emission finds the code and the mask)
-// instead of the node's index.
-template <bool kByPosition>
 __global__ void __launch_bounds__(kScanThreads, 8) rankWriteKernel(const unsigned char* __restrict__ sizeOf, const u32* __restrict__ gid, u64 n,
-		const ScanTileState* __restrict__ tiles, u32* __restrict__ firstList, u32* __restrict__ wordOffset, u32* __restrict__ slotOffset,
-		const u64* __restrict__ table) {
+		const ScanTileState* __restrict__ tiles, u32* __restrict__ firstList, u32* __restrict__ wordOffset, u32* __restrict__ slotOffset) {
 	const u64 base = (u64)blockIdx.x * kScanTile + (u64)threadIdx.x * kScanItems;
 	u32 words[kScanItems] = {0, 0, 0, 0};
 	if (base + kScanItems <= n) {
@@ -396,13 +307,9 @@ __global__ void __launch_bounds__(kScanThreads, 8) rankWriteKernel(const unsigne
 #pragma unroll
 	for (int i = 0; i < kScanItems; ++i) {
 		if (words[i]) {
-			const u32 slot = gid[base + i] & kGidMask;
-			if constexpr (kByPosition)
-				firstList[rank] = (u32)table[slot];
-			else
-				firstList[rank] = (u32)(base + i);
+			firstList[rank] = (u32)(base + i);
 			wordOffset[rank] = (u32)woff;
-			slotOffset[slot] = (u32)woff;
+			slotOffset[gid[base + i] & kGidMask] = (u32)woff;
 			++rank;
 			woff += words[i];
 		}
@@ -517,11 +424,8 @@ int launchMergeSmallLevels(const SmallMergeArgs& a, cudaStream_t stream) {
 	return 1;
 }
 
-int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* tableMaskDev, u32* minIndex, cudaStream_t stream) {
-	if (minIndex)
-		sizeAndClearLeafTableKernel<true><<<148 * 8, 256, 0, stream>>>(table, maxSlots, setBits, tableMaskDev, minIndex);
-	else
-		sizeAndClearLeafTableKernel<false><<<148 * 8, 256, 0, stream>>>(table, maxSlots, setBits, tableMaskDev, nullptr);
+int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* tableMaskDev, cudaStream_t stream) {
+	sizeAndClearLeafTableKernel<<<148 * 8, 256, 0, stream>>>(table, maxSlots, setBits, tableMaskDev);
 	return 1;
 }
 
@@ -531,16 +435,8 @@ int launchInsertLevel(const MergeLevelArgs& a, cudaStream_t stream) {
 		return 1;
 	}
 	const unsigned blocks = (unsigned)((a.n + 255) / 256);
-	if (a.leaf && a.leafAt && a.hints)
-		insertLeavesByPositionKernel<true><<<blocks, 256, 0, stream>>>(a.leafCodes, a.leafAt, a.n, a.table, a.tableMaskDev, a.minIndex, a.uid, a.errorFlag);
-	else if (a.leaf && a.leafAt)
-		insertLeavesByPositionKernel<false><<<blocks, 256, 0, stream>>>(a.leafCodes, a.leafAt, a.n, a.table, a.tableMaskDev, a.minIndex, a.uid, a.errorFlag);
-	else if (a.leaf && a.hints)
-		insertLeavesKernel<true><<<blocks, 256, 0, stream>>>(a.leafCodes, a.leafHash, a.n, a.table, a.tableMaskDev, a.uid, a.errorFlag);
-	else if (a.leaf)
-		insertLeavesKernel<false><<<blocks, 256, 0, stream>>>(a.leafCodes, a.leafHash, a.n, a.table, a.tableMaskDev, a.uid, a.errorFlag);
-	else if (a.dense)
-		insertInnerDenseKernel<<<blocks, 256, 0, stream>>>(a.masks, a.firstChild, a.childUid, a.n, a.table, a.tableSize - 1, a.uid, a.errorFlag);
+	if (a.leaf)
+		insertLeavesKernel<<<blocks, 256, 0, stream>>>(a.leafCodes, a.leafHash, a.n, a.table, a.tableMaskDev, a.uid, a.errorFlag);
 	else
 		insertInnerKernel<<<blocks, 256, 0, stream>>>(a.masks, a.firstChild, a.childUid, a.n, a.table, a.tableSize - 1, a.uid, a.errorFlag);
 	return 1;
@@ -549,17 +445,9 @@ int launchInsertLevel(const MergeLevelArgs& a, cudaStream_t stream) {
 int launchRankLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaStream_t stream) {
 	if (a.n == 1) return 0;  // done by launchInsertLevel
 	const u32 tiles = (u32)((a.n + kScanTile - 1) / kScanTile);
-	const bool byPosition = a.leaf && a.leafAt;
-	if (byPosition)
-		rankCountKernel<true><<<tiles, kScanThreads, 0, stream>>>(a.table, a.masks, a.leaf, a.n, a.uid, a.sizeOf, scan.tiles, a.minIndex);
-	else
-		rankCountKernel<false><<<tiles, kScanThreads, 0, stream>>>(a.table, a.masks, a.leaf, a.n, a.uid, a.sizeOf, scan.tiles, nullptr);
+	rankCountKernel<<<tiles, kScanThreads, 0, stream>>>(a.table, a.masks, a.leaf, a.n, a.uid, a.sizeOf, scan.tiles);
 	rankScanTilesKernel<<<1, kScanTilesThreads, 0, stream>>>(scan.tiles, tiles, a.uniqueCount, a.wordCount);
-	// (minIndex may alias slotOffset: the count kernel above is the last reader of the former, the write kernel the first writer of the latter)
-	if (byPosition)
-		rankWriteKernel<true><<<tiles, kScanThreads, 0, stream>>>(a.sizeOf, a.uid, a.n, scan.tiles, a.firstList, a.wordOffset, a.slotOffset, a.table);
-	else
-		rankWriteKernel<false><<<tiles, kScanThreads, 0, stream>>>(a.sizeOf, a.uid, a.n, scan.tiles, a.firstList, a.wordOffset, a.slotOffset, nullptr);
+	rankWriteKernel<<<tiles, kScanThreads, 0, stream>>>(a.sizeOf, a.uid, a.n, scan.tiles, a.firstList, a.wordOffset, a.slotOffset);
 	return 3;
 }
 

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) countNodesKernel(CountLevels p, u64* __re
 // chain better than 256-thread ones.)
 constexpr int kExpandThreads = 128;
 constexpr int kExpandTile = kExpandThreads * kScanItems;
-__device__ __forceinline__ void expandLevelBody(const float* __restrict__ tex, u32 side, float heightF, int level0,
+__global__ void __launch_bounds__(kExpandThreads) expandLevelKernel(const float* __restrict__ tex, u32 side, float heightF, int level0,
 		const u64* __restrict__ coords, u64 n, u16* __restrict__ masks, u32* __restrict__ firstChild, u64* __restrict__ childCoords,
 		u64* __restrict__ childTotal, ScanLaunch scan, u32 numTiles, const u32* __restrict__ colBias, u32* __restrict__ leafAt, u32 numLeaves) {
 	const u32 tile = scanAcquireTile(scan);
@@ -180,18 +180,6 @@ __device__ __forceinline__ void expandLevelBody(const float* __restrict__ tex, u
 			}
 		}
 	}
-}
-
-__global__ void __launch_bounds__(kExpandThreads) expandLevelKernel(const float* __restrict__ tex, u32 side, float heightF, int level0,
-		const u64* __restrict__ coords, u64 n, u16* __restrict__ masks, u32* __restrict__ firstChild, u64* __restrict__ childCoords,
-		u64* __restrict__ childTotal, ScanLaunch scan, u32 numTiles, const u32* __restrict__ colBias, u32* __restrict__ leafAt, u32 numLeaves) {
-	expandLevelBody(tex, side, heightF, level0, coords, n, masks, firstChild, childCoords, childTotal, scan, numTiles, colBias, leafAt, numLeaves);
-}
-// The same, held to 40 registers so that 12 CTAs instead of 10 fit an SM (no spills). Experimental, CPVS_EXPAND_BLOCKS=12.
-__global__ void __launch_bounds__(kExpandThreads, 12) expandLevelDenseKernel(const float* __restrict__ tex, u32 side, float heightF, int level0,
-		const u64* __restrict__ coords, u64 n, u16* __restrict__ masks, u32* __restrict__ firstChild, u64* __restrict__ childCoords,
-		u64* __restrict__ childTotal, ScanLaunch scan, u32 numTiles, const u32* __restrict__ colBias, u32* __restrict__ leafAt, u32 numLeaves) {
-	expandLevelBody(tex, side, heightF, level0, coords, n, masks, firstChild, childCoords, childTotal, scan, numTiles, colBias, leafAt, numLeaves);
 }
 
 // The top of the octree: levels of at most kSmallMaxNodes nodes are a chain of tiny dependent steps.
@@ -462,9 +450,6 @@ __constant__ u64 kLaneHashMul[4] = {0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full
 
 // The leaves chunk..chunkEnd-1 (warp-uniform bounds) of the eight columns of a warp. firstIdx: leafAt of the lane's leaf of
 // the very first batch if the caller fetched it ahead (only looked at for chunk == 0).
-// kByPosition: a leaf is stored at its column-order position (colBias[column] + z-block) instead of its breadth-first index,
-// so nothing here depends on the expansion (see launchBuildLeafColumns).
-template <bool kByPosition>
 __device__ __forceinline__ void emitColumnLeaves(const LeafColumn& c, const __half2 (&r0)[4], const __half2 (&r1)[4], u32 chunk, u32 chunkEnd,
 		u32 firstIdx, bool haveFirstIdx, const LeafSink& out, PendingSketch& pending) {
 	const u32 lane = threadIdx.x & 31u, sub = lane & 3u, groupLane = lane & ~3u;
@@ -475,9 +460,7 @@ __device__ __forceinline__ void emitColumnLeaves(const LeafColumn& c, const __ha
 	__half2 negI2 = __float2half2_rn(0.f);         // -(block index inside the chunk)
 	for (u32 m = chunk; m < chunkEnd; m += 4) {
 		u32 mineIdx = kNoLeaf;
-		if constexpr (kByPosition) {
-			if (m + sub < c.cnt) mineIdx = c.first + m + sub;
-		} else if (haveFirstIdx && m == 0) {
+		if (haveFirstIdx && m == 0) {
 			mineIdx = firstIdx;
 		} else if (m + sub < c.cnt && c.first + m + sub < out.numLeaves) {
 			mineIdx = out.leafAt[c.first + m + sub];
@@ -526,9 +509,7 @@ __device__ __forceinline__ void emitColumnLeaves(const LeafColumn& c, const __ha
 // four rows of 256 contiguous bytes), software-pipelined in registers so that no load is waited for: a group's level-3
 // texel and colBias are fetched two groups ahead; its depth rows and the leafAt of its first batch one group ahead, and only
 // if the column has leaves (most columns of a z-slice of a tall grid have none). Warps never synchronise with each other.
-// kMinBlocks: 3 (78 registers), or 4 (64 registers with 64 bytes of spills; experimental, CPVS_LEAF_CTAS=4).
-template <bool kByPosition, int kMinBlocks>
-__global__ void __launch_bounds__(256, kMinBlocks) buildLeafColumnsKernel(const float* __restrict__ depth, u32 n, u32 colShift, float heightF,
+__global__ void __launch_bounds__(256, 3) buildLeafColumnsKernel(const float* __restrict__ depth, u32 n, u32 colShift, float heightF,
 		float height3F, float zLoF, float zHiF, const float2* __restrict__ level3, u32 numCols, const u32* __restrict__ colBias, LeafSink out) {
 	const u32 lane = threadIdx.x & 31u, sub = lane & 3u;
 	const u32 numWarps = gridDim.x * (blockDim.x >> 5), numGroups = (numCols + 7u) >> 3;
@@ -565,8 +546,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) buildLeafColumnsKernel(const 
 			const float* p = depth + (size_t)(cy * 8u + sub * 2u) * n + cx * 8u;
 			a1 = ldSector256(p);
 			b1 = ldSector256(p + n);
-			if constexpr (!kByPosition)
-				if (sub < c1.cnt && c1.first + sub < out.numLeaves) idx1 = out.leafAt[c1.first + sub];
+			if (sub < c1.cnt && c1.first + sub < out.numLeaves) idx1 = out.leafAt[c1.first + sub];
 		}
 	};
 	fetchTexel(group);
@@ -589,7 +569,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) buildLeafColumnsKernel(const 
 		fetchRows(group + numWarps);
 		fetchTexel(group + 2u * numWarps);
 		if (maxCnt == 0) continue;
-		emitColumnLeaves<kByPosition>(c, r0, r1, 0, min(maxCnt, kChunkBlocks), firstIdx, true, out, pending);
+		emitColumnLeaves(c, r0, r1, 0, min(maxCnt, kChunkBlocks), firstIdx, true, out, pending);
 		for (u32 chunk = kChunkBlocks; chunk < maxCnt; chunk += kChunkBlocks) {  // tall columns (box edges): re-read the rows
 			if (c.cnt) {
 				const u32 col = group * 8u + (lane >> 2);
@@ -597,7 +577,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) buildLeafColumnsKernel(const 
 				const float* p = depth + (size_t)(cy * 8u + sub * 2u) * n + cx * 8u;
 				rowsToR(ldSector256(p), ldSector256(p + n), heightF, __fadd_rn(c.lo, __uint2float_rn(chunk)), r0, r1);
 			}
-			emitColumnLeaves<kByPosition>(c, r0, r1, chunk, min(maxCnt, chunk + kChunkBlocks), kNoLeaf, false, out, pending);
+			emitColumnLeaves(c, r0, r1, chunk, min(maxCnt, chunk + kChunkBlocks), kNoLeaf, false, out, pending);
 		}
 	}
 	pending.flush();
@@ -684,16 +664,12 @@ int launchExpandSmallLevels(const SmallExpandArgs& a, cudaStream_t stream) {
 }
 
 int launchExpandLevel(const PyramidView& pyr, int level, u32 zTileNum, const u64* coords, u64 n, u16* masks, u32* firstChild,
-		u64* childCoords, u64* childTotal, ScanLaunch scan, const u32* colBias, u32* leafAt, u32 numLeaves, int minBlocks, cudaStream_t stream) {
+		u64* childCoords, u64* childTotal, ScanLaunch scan, const u32* colBias, u32* leafAt, u32 numLeaves, cudaStream_t stream) {
 	const u32 side = (u32)pyr.n >> level;
 	const float heightF = (float)(side * zTileNum);
 	const u32 tiles = (u32)((n + kExpandTile - 1) / kExpandTile);
-	if (minBlocks == 12)
-		expandLevelDenseKernel<<<tiles, kExpandThreads, 0, stream>>>(pyr.level[level], side, heightF, level == 0 ? 1 : 0, coords, n, masks, firstChild,
-				childCoords, childTotal, scan, tiles, colBias, leafAt, numLeaves);
-	else
-		expandLevelKernel<<<tiles, kExpandThreads, 0, stream>>>(pyr.level[level], side, heightF, level == 0 ? 1 : 0, coords, n, masks, firstChild,
-				childCoords, childTotal, scan, tiles, colBias, leafAt, numLeaves);
+	expandLevelKernel<<<tiles, kExpandThreads, 0, stream>>>(pyr.level[level], side, heightF, level == 0 ? 1 : 0, coords, n, masks, firstChild,
+			childCoords, childTotal, scan, tiles, colBias, leafAt, numLeaves);
 	return 1;
 }
 
@@ -713,7 +689,7 @@ int launchColumnBias(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, u32* 
 }
 
 int launchBuildLeafColumns(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, const u32* colBias, const u32* leafAt, u32 numLeaves, u32* codes,
-		u16* masks, u32* sketch, u32 ctasPerSm, cudaStream_t stream) {
+		u16* masks, u32* sketch, cudaStream_t stream) {
 	const u32 side3 = (u32)pyr.n >> 3, numCols = side3 * side3;
 	u32 colShift = 0;
 	while ((1u << colShift) < side3) ++colShift;
@@ -722,22 +698,8 @@ int launchBuildLeafColumns(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum,
 	const float2* level3 = reinterpret_cast<const float2*>(pyr.level[3]);
 	LeafSink out{leafAt, numLeaves, codes, masks, sketch, kSketchWords - 1};
 	const u32 wanted = (numCols + kColumnsPerCta - 1) / kColumnsPerCta;  // 8 warps of 8 columns per CTA
-	const u32 resident = 148u * (ctasPerSm >= 1u && ctasPerSm <= 4u ? ctasPerSm : 3u);  // persistent CTAs
-	const u32 grid = wanted < resident ? wanted : resident;
-#define CPVS_LAUNCH_COLUMNS(BYPOS, BLOCKS)                                                                                                      \
-	buildLeafColumnsKernel<BYPOS, BLOCKS><<<grid, 256, 0, stream>>>(pyr.level[0], (u32)pyr.n, colShift, heightF, height3F, zLoF, zHiF, level3, numCols, \
-			colBias, out)
-	if (ctasPerSm == 4u) {  // the instantiation whose register allocation allows four CTAs per SM
-		if (leafAt)
-			CPVS_LAUNCH_COLUMNS(false, 4);
-		else
-			CPVS_LAUNCH_COLUMNS(true, 4);
-	} else if (leafAt) {
-		CPVS_LAUNCH_COLUMNS(false, 3);
-	} else {
-		CPVS_LAUNCH_COLUMNS(true, 3);
-	}
-#undef CPVS_LAUNCH_COLUMNS
+	buildLeafColumnsKernel<<<wanted < 148u * 3u ? wanted : 148u * 3u, 256, 0, stream>>>(pyr.level[0], (u32)pyr.n, colShift, heightF, height3F,
+			zLoF, zHiF, level3, numCols, colBias, out);
 	return 1;
 }
 

@@ -1,8 +1,6 @@
 """GPU suite (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle and the
 committed golden vectors. Bit-exact throughout: pyramid floats, DAG words, per-level node counts,
 lookup results. Nothing here reads /root/reference."""
-import os
-
 import numpy as np
 import pytest
 
@@ -548,40 +546,3 @@ def test_leaf_kernels_forced(oracle, mode, monkeypatch):
         g = cpvs_b200.CompressedShadow.create(mm, zt, zn)
         o = oracle.Shadow(oracle.MinMax(d), zt, zn)
         _assert_same_dag(g, o, (mode, tag))
-
-
-# ---- experimental switches: not measured yet, off by default, and not part of the default GPU run ------------------------
-
-_experimental = pytest.mark.skipif(os.environ.get("CPVS_TEST_EXPERIMENTAL") != "1",
-                                   reason="experimental library switches: set CPVS_TEST_EXPERIMENTAL=1 to run")
-
-
-@_experimental
-@pytest.mark.parametrize("env", [{"CPVS_LEAF_ORDER": "1"}, {"CPVS_LEAF_ORDER": "1", "CPVS_LEAF_CTAS": "3"},
-                                 {"CPVS_EMIT_PLANES": "1"}, {"CPVS_INSERT_HINTS": "1"}, {"CPVS_EXPAND_BLOCKS": "12"}, {"CPVS_INNER_BLOCKS": "8"}, {"CPVS_LEAF_CTAS": "4"},
-                                 {"CPVS_LEAF_ORDER": "1", "CPVS_LEAF_CTAS": "4"},
-                                 {"CPVS_LEAF_ORDER": "1", "CPVS_EMIT_PLANES": "1", "CPVS_INSERT_HINTS": "1"}],
-                         ids=lambda e: ",".join("%s=%s" % kv for kv in sorted(e.items())))
-def test_experimental_switches_keep_the_words(oracle, env, monkeypatch):
-    """Every experimental switch (README "Environment switches") must leave the DAG words untouched: leaves stored by
-    column position and built beside the expansion (CPVS_LEAF_ORDER=1, needs the per-column builder, hence
-    CPVS_LEAF_COLUMNS=2 here), the bit-plane leaf emission (CPVS_EMIT_PLANES=1), L2 eviction priorities in the leaf insert
-    (CPVS_INSERT_HINTS=1), the denser register allocations (CPVS_EXPAND_BLOCKS=12, CPVS_INNER_BLOCKS=8, CPVS_LEAF_CTAS=4)."""
-    monkeypatch.setenv("CPVS_LEAF_COLUMNS", "2")
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
-    ctx = cpvs_b200.Context(0)
-    rng = np.random.default_rng(11)
-    cases = [("terrain", synth.depth_map("terrain", 1024), 0, 1), ("plane", synth.depth_map("plane", 256), 0, 1),
-             ("city", synth.depth_map("city", 1024), 0, 1), ("city z1/2", synth.depth_map("city", 512), 1, 2),
-             ("terrain z2/4", synth.depth_map("terrain", 256), 2, 4), ("random 16", rng.random((16, 16), dtype=np.float32), 0, 1),
-             ("random 128", rng.random((128, 128), dtype=np.float32), 0, 1), ("terrain 2048", synth.depth_map("terrain", 2048), 0, 1)]
-    pts = synth.lookups(50000)
-    for tag, d, zt, zn in cases:
-        for rep in range(2):  # the second build reuses the arena the first one left behind
-            mm = cpvs_b200.MinMaxHierarchy(d, ctx)
-            g = cpvs_b200.CompressedShadow.create(mm, zt, zn)
-            o = oracle.Shadow(oracle.MinMax(d), zt, zn)
-            _assert_same_dag(g, o, (env, tag, rep))
-        if zn == 1:
-            assert np.array_equal(g.traverse(pts), o.traverse(pts)), (env, tag)

@@ -1,8 +1,8 @@
 """CPU checks of the integer bit manipulation the leaf emission runs on the device (cpvs_b200/csrc/leafbits.cuh): the header
 is plain integer logic marked __host__ __device__, so it is compiled here with g++ and compared with the definition of a
 leafmask -- slice s of a leaf has bit x + 8y set iff texel (x, y) has more than s lit slices (createLeafmask, reference
-src/CompressedShadowUtil.cpp:59-78). Covers the shipped per-row expansion (rowBits) and the bit-plane one
-(CPVS_EMIT_PLANES=1)."""
+src/CompressedShadowUtil.cpp:59-78). Covers the bit-plane expansion the emission kernel runs (codeToPlanes /
+sliceFromPlanes) and the direct per-row one it replaced (rowBits, kept in the header as the second opinion)."""
 import ctypes
 import os
 import subprocess
