@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(kEmitThreads) emitInnerLevelsKernel(EmitMultiA
 // the PARTIAL slices, bit x + 8y = lit (createLeafmask, src/CompressedShadowUtil.cpp:59-78) -- through bit planes
 // (leafbits.cuh): the code is transposed once, every slice is then one or two logic instructions per half, and the loop over
 // the slices is unrolled with predicated stores. About 330 executed instructions per terrain leaf (nearly all of its slices
-// PARTIAL) against 850 for row-by-row nibble compares: 0.200 -> 0.174 ms at 16K^2 terrain (profiles/r1_switch_probe.txt).
+// PARTIAL) against 850 for row-by-row nibble compares: 0.200 -> 0.174 ms at 16K^2 terrain (profiles/r1_switch_probe.md).
 
 __global__ void __launch_bounds__(kEmitThreads) emitLeavesKernel(EmitLevelArgs a) {
 	__shared__ u32 sOut[kEmitThreads * 17];

@@ -144,7 +144,7 @@ __device__ __forceinline__ u32 compactLitBits(u32 mask) {
 
 // Held to 32 registers (8 instead of 6 CTAs of 256 threads per SM, one 4-byte spill): the kernel waits on dependent loads 62 % of
 // the time, and the two extra CTAs are worth 0.03 ms on the 16K^2 terrain (inner merge 0.436 -> 0.409 ms, the leaf rank running
-// beside it 0.375 -> 0.348 ms; profiles/r1_switch_probe.txt).
+// beside it 0.375 -> 0.348 ms; profiles/r1_switch_probe.md).
 __global__ void __launch_bounds__(256, 8) insertInnerKernel(const u16* __restrict__ masks, const u32* __restrict__ firstChild,
 		const u32* __restrict__ childUid, u64 n, u64* __restrict__ table, u64 tableMask, u32* __restrict__ slotOf, u32* errorFlag) {
 	__shared__ u32 sFirst[kDirectSlots];
