@@ -89,6 +89,7 @@ struct cpvs_ctx {
 	cudaStream_t aux2, aux3;  // the ranks of different levels are independent: alternate between the two
 	cudaEvent_t evRankStart, evRankStop, evJoin3, evClear, evCols;
 	int leafColumns;  // leaves built per column: 1 = where it pays (default), 0 = never, 2 = always (CPVS_LEAF_COLUMNS; tests)
+	unsigned experiments;  // kExperiment* bits (CPVS_EXPERIMENTS): unmeasured kernel variants, off by default
 };
 
 struct cpvs_minmax {
@@ -239,6 +240,13 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 	{
 		const char* v = std::getenv("CPVS_LEAF_COLUMNS");
 		ctx->leafColumns = (v && v[0] >= '0' && v[0] <= '2') ? v[0] - '0' : 1;
+		const char* x = std::getenv("CPVS_EXPERIMENTS");
+		ctx->experiments = 0;
+		if (x) {
+			if (std::strstr(x, "expand-preload")) ctx->experiments |= kExperimentExpandPreload;
+			if (std::strstr(x, "emit-gather")) ctx->experiments |= kExperimentEmitGather;
+			if (std::strstr(x, "rank-preload")) ctx->experiments |= kExperimentRankPreload;
+		}
 	}
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux2, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux3, cudaStreamNonBlocking);
@@ -784,7 +792,8 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		const bool toColumns = leafColumns && l == 3;
 		if (toColumns) CPVS_CUDA(cudaStreamWaitEvent(st, ctx->evCols, 0));
 		ctx->launches += launchExpandLevel(pyr, l, zTileNum, lv[l].coords, lv[l].n, lv[l].masks, lv[l].firstChild, childCoords,
-				dChildTotal + l, nextScan(lv[l].n, kExpandTileNodes), toColumns ? dColBias : nullptr, toColumns ? lv[2].leafAt : nullptr, (u32)lv[2].n, st);
+				dChildTotal + l, nextScan(lv[l].n, kExpandTileNodes), toColumns ? dColBias : nullptr, toColumns ? lv[2].leafAt : nullptr, (u32)lv[2].n,
+				(ctx->experiments & kExperimentExpandPreload) ? 1 : 0, st);
 	}
 	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAVES], st));
 	if (leafColumns)  // constructLastLevels (src/CompressedShadow.cpp:171-190)
@@ -837,6 +846,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		m.sizeOf = a.sizeOf;
 		m.uniqueCount = dUnique + l;
 		m.wordCount = dWords + l;
+		m.rankPreload = (ctx->experiments & kExperimentRankPreload) ? 1 : 0;
 		if (!leafLevel && tablesClearing) {
 			CPVS_CUDA(cudaStreamWaitEvent(mergeStream, ctx->evClear, 0));
 			tablesClearing = false;
@@ -928,6 +938,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	}
 	EmitMultiArgs inner;
 	inner.count = 0;
+	inner.gather = (ctx->experiments & kExperimentEmitGather) ? 1 : 0;
 	for (int l = minLevel; l <= top; ++l) {
 		const LevelArrays& a = lv[l];
 		if (!a.n) continue;

@@ -31,6 +31,10 @@ __device__ __forceinline__ void emitRun(const EmitLevelArgs& a, const u32* sOut,
 	for (u32 i = threadIdx.x; i < runWords; i += kEmitThreads) out[i] = sOut[i];
 }
 
+// kGather (experimental, CPVS_EXPERIMENTS=emit-gather): the plain loop over the k PARTIAL children loads a child's group id,
+// waits, loads that group's word offset, waits, stores, and only then turns to the next child -- 2k dependent round trips.
+// The variant issues the (up to) eight id loads together, then the eight offset loads, then the stores: two round trips.
+template <bool kGather>
 __device__ __forceinline__ void emitInnerBlock(const EmitLevelArgs& a, u32 block, u32* sOut) {
 	const u64 unique = *a.uniqueCount;
 	const u64 r0 = (u64)block * kEmitThreads;
@@ -47,7 +51,18 @@ __device__ __forceinline__ void emitInnerBlock(const EmitLevelArgs& a, u32 block
 		if (k) {
 			const u32* kids = a.childUid + a.firstChild[j];
 			const u32 childBase = (u32)*a.childLevelBase;
-			for (u32 c = 0; c < k; ++c) out[1 + c] = childBase + a.childSlotOffset[kids[c] & 0x7FFFFFFFu];
+			if constexpr (kGather) {
+				u32 kid[8], off[8];
+#pragma unroll
+				for (u32 c = 0; c < 8; ++c) kid[c] = c < k ? kids[c] & 0x7FFFFFFFu : 0u;
+#pragma unroll
+				for (u32 c = 0; c < 8; ++c) off[c] = c < k ? a.childSlotOffset[kid[c]] : 0u;
+#pragma unroll
+				for (u32 c = 0; c < 8; ++c)
+					if (c < k) out[1 + c] = childBase + off[c];
+			} else {
+				for (u32 c = 0; c < k; ++c) out[1 + c] = childBase + a.childSlotOffset[kids[c] & 0x7FFFFFFFu];
+			}
 		}
 	}
 	__syncthreads();
@@ -56,15 +71,16 @@ __device__ __forceinline__ void emitInnerBlock(const EmitLevelArgs& a, u32 block
 
 __global__ void __launch_bounds__(kEmitThreads) emitInnerKernel(EmitLevelArgs a) {
 	__shared__ u32 sOut[kEmitThreads * 9];
-	emitInnerBlock(a, blockIdx.x, sOut);
+	emitInnerBlock<false>(a, blockIdx.x, sOut);
 }
 
 // All inner levels in one launch: blockStart[] maps a block to its level.
+template <bool kGather>
 __global__ void __launch_bounds__(kEmitThreads) emitInnerLevelsKernel(EmitMultiArgs m) {
 	__shared__ u32 sOut[kEmitThreads * 9];
 	int s = 0;
 	while (s + 1 < m.count && blockIdx.x >= m.blockStart[s + 1]) ++s;
-	emitInnerBlock(m.lv[s], blockIdx.x - m.blockStart[s], sOut);
+	emitInnerBlock<kGather>(m.lv[s], blockIdx.x - m.blockStart[s], sOut);
 }
 
 // Leaves: expands the k-code (nibble x of word y = lit slices of texel (x,y)) into the 64-bit masks of
@@ -121,7 +137,10 @@ int launchEmitInnerLevels(EmitMultiArgs& m, cudaStream_t stream) {
 		blocks += (u32)((m.lv[s].n + kEmitThreads - 1) / kEmitThreads);
 	}
 	m.blockStart[m.count] = blocks;
-	emitInnerLevelsKernel<<<blocks, kEmitThreads, 0, stream>>>(m);
+	if (m.gather)
+		emitInnerLevelsKernel<true><<<blocks, kEmitThreads, 0, stream>>>(m);
+	else
+		emitInnerLevelsKernel<false><<<blocks, kEmitThreads, 0, stream>>>(m);
 	return 1;
 }
 

@@ -37,7 +37,14 @@ constexpr u64 kExpandTileNodes = 128 * kScanItems;  // nodes per look-back tile 
 // With leafAt != NULL the children are leaves built per column (launchBuildLeafColumns): instead of their
 // coordinates, each child's index is stored at its column-order position leafAt[colBias[column] + z].
 int launchExpandLevel(const PyramidView& pyr, int level, u32 zTileNum, const u64* coords, u64 n, u16* masks,
-		u32* firstChild, u64* childCoords, u64* childTotal, ScanLaunch scan, const u32* colBias, u32* leafAt, u32 numLeaves, cudaStream_t stream);
+		u32* firstChild, u64* childCoords, u64* childTotal, ScanLaunch scan, const u32* colBias, u32* leafAt, u32 numLeaves, int preloadBias,
+		cudaStream_t stream);  // preloadBias: experimental variant of the leaf-column scatter (kExperimentExpandPreload)
+
+// Experimental kernel variants, off by default, selected per context by CPVS_EXPERIMENTS (comma-separated names); the default
+// kernels stay instruction-identical (scripts/sass_diff.py) and results never depend on them.
+constexpr unsigned kExperimentExpandPreload = 1u;  // "expand-preload": svo.cu expandLevelPreloadKernel
+constexpr unsigned kExperimentEmitGather = 2u;     // "emit-gather":    emit.cu emitInnerLevelsKernel<true>
+constexpr unsigned kExperimentRankPreload = 4u;    // "rank-preload":   merge.cu rankWriteKernel<true>
 
 // The small top levels (<= kSmallMaxNodes nodes each, root first) expanded by a single CTA.
 constexpr int kSmallThreads = 1024;
@@ -103,6 +110,7 @@ struct MergeLevelArgs {
 	unsigned char* sizeOf; // scratch (rank): compressed size of node j if it is a first occurrence, else 0
 	u64* uniqueCount;      // out: number of unique nodes
 	u64* wordCount;        // out: compressed words of the level
+	int rankPreload;       // experimental variant of the rank's last kernel (kExperimentRankPreload)
 };
 // The small top levels merged bottom-up by a single CTA (same result as launchMergeLevel per level).
 struct SmallMergeLevel {
@@ -156,6 +164,7 @@ struct EmitMultiArgs {
 	EmitLevelArgs lv[kMaxEmitLevels];
 	u32 blockStart[kMaxEmitLevels + 1];
 	int count;
+	int gather;  // experimental variant of the pointer gather (kExperimentEmitGather)
 };
 int launchEmitInnerLevels(EmitMultiArgs& a, cudaStream_t stream);
 // bases[l] for l = top..minLevel from words[l]; total -> *totalWords. One thread.

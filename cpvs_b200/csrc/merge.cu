@@ -280,9 +280,27 @@ __global__ void __launch_bounds__(kScanTilesThreads) rankScanTilesKernel(ScanTil
 	}
 }
 
+// kPreload (experimental, CPVS_EXPERIMENTS=rank-preload): the group ids of the thread's four nodes are fetched with one 128-bit
+// load next to the size bytes, instead of one dependent load per unique node after the scan (a round trip off the chain at the
+// price of reading the ids of the nodes that turn out not to be unique).
+template <bool kPreload>
 __global__ void __launch_bounds__(kScanThreads, 8) rankWriteKernel(const unsigned char* __restrict__ sizeOf, const u32* __restrict__ gid, u64 n,
 		const ScanTileState* __restrict__ tiles, u32* __restrict__ firstList, u32* __restrict__ wordOffset, u32* __restrict__ slotOffset) {
 	const u64 base = (u64)blockIdx.x * kScanTile + (u64)threadIdx.x * kScanItems;
+	u32 g[kScanItems] = {0, 0, 0, 0};
+	if constexpr (kPreload) {
+		if (base + kScanItems <= n) {
+			const uint4 v = *reinterpret_cast<const uint4*>(gid + base);
+			g[0] = v.x;
+			g[1] = v.y;
+			g[2] = v.z;
+			g[3] = v.w;
+		} else {
+#pragma unroll
+			for (int i = 0; i < kScanItems; ++i)
+				if (base + i < n) g[i] = gid[base + i];
+		}
+	}
 	u32 words[kScanItems] = {0, 0, 0, 0};
 	if (base + kScanItems <= n) {
 		const u32 packed = *reinterpret_cast<const u32*>(sizeOf + base);
@@ -309,7 +327,10 @@ __global__ void __launch_bounds__(kScanThreads, 8) rankWriteKernel(const unsigne
 		if (words[i]) {
 			firstList[rank] = (u32)(base + i);
 			wordOffset[rank] = (u32)woff;
-			slotOffset[gid[base + i] & kGidMask] = (u32)woff;
+			if constexpr (kPreload)
+				slotOffset[g[i] & kGidMask] = (u32)woff;
+			else
+				slotOffset[gid[base + i] & kGidMask] = (u32)woff;
 			++rank;
 			woff += words[i];
 		}
@@ -447,7 +468,10 @@ int launchRankLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaStream_t strea
 	const u32 tiles = (u32)((a.n + kScanTile - 1) / kScanTile);
 	rankCountKernel<<<tiles, kScanThreads, 0, stream>>>(a.table, a.masks, a.leaf, a.n, a.uid, a.sizeOf, scan.tiles);
 	rankScanTilesKernel<<<1, kScanTilesThreads, 0, stream>>>(scan.tiles, tiles, a.uniqueCount, a.wordCount);
-	rankWriteKernel<<<tiles, kScanThreads, 0, stream>>>(a.sizeOf, a.uid, a.n, scan.tiles, a.firstList, a.wordOffset, a.slotOffset);
+	if (a.rankPreload)
+		rankWriteKernel<true><<<tiles, kScanThreads, 0, stream>>>(a.sizeOf, a.uid, a.n, scan.tiles, a.firstList, a.wordOffset, a.slotOffset);
+	else
+		rankWriteKernel<false><<<tiles, kScanThreads, 0, stream>>>(a.sizeOf, a.uid, a.n, scan.tiles, a.firstList, a.wordOffset, a.slotOffset);
 	return 3;
 }
 

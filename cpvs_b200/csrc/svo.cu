@@ -126,7 +126,13 @@ __global__ void __launch_bounds__(256) countNodesKernel(CountLevels p, u64* __re
 // chain better than 256-thread ones.)
 constexpr int kExpandThreads = 128;
 constexpr int kExpandTile = kExpandThreads * kScanItems;
-__global__ void __launch_bounds__(kExpandThreads) expandLevelKernel(const float* __restrict__ tex, u32 side, float heightF, int level0,
+// kPreloadBias (experimental, CPVS_EXPERIMENTS=expand-preload): when the children are leaves built per column, the plain
+// loop below reads colBias for one child, waits, stores, and only then reads it for the next -- up to 4 x 8 dependent
+// round trips per thread. The children of a node sit in just four columns, (x, y) .. (x+1, y+1) with x even, so two 8-byte
+// loads per node fetch every bias it needs; the variant issues them for the thread's four nodes back to back before the
+// first store.
+template <bool kPreloadBias>
+__device__ __forceinline__ void expandLevelBody(const float* __restrict__ tex, u32 side, float heightF, int level0,
 		const u64* __restrict__ coords, u64 n, u16* __restrict__ masks, u32* __restrict__ firstChild, u64* __restrict__ childCoords,
 		u64* __restrict__ childTotal, ScanLaunch scan, u32 numTiles, const u32* __restrict__ colBias, u32* __restrict__ leafAt, u32 numLeaves) {
 	const u32 tile = scanAcquireTile(scan);
@@ -153,6 +159,40 @@ __global__ void __launch_bounds__(kExpandThreads) expandLevelKernel(const float*
 	scanLookback2(scan, tile, tot, 0, tilePre, tilePreB);
 	if (tile == numTiles - 1 && threadIdx.x == 0) *childTotal = tilePre + tot;
 	u64 pos = tilePre + pre;
+	if constexpr (kPreloadBias) {
+		if (leafAt) {
+			uint2 row0[kScanItems], row1[kScanItems];  // colBias of columns (x, y), (x+1, y) and (x, y+1), (x+1, y+1)
+#pragma unroll
+			for (int i = 0; i < kScanItems; ++i) {
+				row0[i] = row1[i] = make_uint2(0u, 0u);
+				if (base + i < n && (m[i] & 0xAAAAu)) {
+					u32 x, y, z;
+					unpackCoord(c[i], x, y, z);  // x is even (child coordinates are doubled) and so is side: 8-byte aligned
+					row0[i] = *reinterpret_cast<const uint2*>(colBias + (size_t)y * side + x);
+					row1[i] = *reinterpret_cast<const uint2*>(colBias + (size_t)(y + 1) * side + x);
+				}
+			}
+#pragma unroll
+			for (int i = 0; i < kScanItems; ++i) {
+				if (base + i >= n) break;
+				masks[base + i] = (u16)m[i];
+				firstChild[base + i] = (u32)pos;
+				u32 partial = m[i] & 0xAAAAu;
+				if (partial) {
+					const u32 z = (u32)(c[i] >> 40);
+					while (partial) {
+						const u32 child = (__ffs(partial) - 1) >> 1;
+						partial &= partial - 1;
+						const uint2 row = (child & 2u) ? row1[i] : row0[i];
+						const u32 at = ((child & 1u) ? row.y : row.x) + z + (child >> 2);
+						if (at < numLeaves) leafAt[at] = (u32)pos;
+						++pos;
+					}
+				}
+			}
+			return;
+		}
+	}
 #pragma unroll
 	for (int i = 0; i < kScanItems; ++i) {
 		if (base + i >= n) break;
@@ -180,6 +220,17 @@ __global__ void __launch_bounds__(kExpandThreads) expandLevelKernel(const float*
 			}
 		}
 	}
+}
+
+__global__ void __launch_bounds__(kExpandThreads) expandLevelKernel(const float* __restrict__ tex, u32 side, float heightF, int level0,
+		const u64* __restrict__ coords, u64 n, u16* __restrict__ masks, u32* __restrict__ firstChild, u64* __restrict__ childCoords,
+		u64* __restrict__ childTotal, ScanLaunch scan, u32 numTiles, const u32* __restrict__ colBias, u32* __restrict__ leafAt, u32 numLeaves) {
+	expandLevelBody<false>(tex, side, heightF, level0, coords, n, masks, firstChild, childCoords, childTotal, scan, numTiles, colBias, leafAt, numLeaves);
+}
+__global__ void __launch_bounds__(kExpandThreads) expandLevelPreloadKernel(const float* __restrict__ tex, u32 side, float heightF, int level0,
+		const u64* __restrict__ coords, u64 n, u16* __restrict__ masks, u32* __restrict__ firstChild, u64* __restrict__ childCoords,
+		u64* __restrict__ childTotal, ScanLaunch scan, u32 numTiles, const u32* __restrict__ colBias, u32* __restrict__ leafAt, u32 numLeaves) {
+	expandLevelBody<true>(tex, side, heightF, level0, coords, n, masks, firstChild, childCoords, childTotal, scan, numTiles, colBias, leafAt, numLeaves);
 }
 
 // The top of the octree: levels of at most kSmallMaxNodes nodes are a chain of tiny dependent steps.
@@ -664,12 +715,16 @@ int launchExpandSmallLevels(const SmallExpandArgs& a, cudaStream_t stream) {
 }
 
 int launchExpandLevel(const PyramidView& pyr, int level, u32 zTileNum, const u64* coords, u64 n, u16* masks, u32* firstChild,
-		u64* childCoords, u64* childTotal, ScanLaunch scan, const u32* colBias, u32* leafAt, u32 numLeaves, cudaStream_t stream) {
+		u64* childCoords, u64* childTotal, ScanLaunch scan, const u32* colBias, u32* leafAt, u32 numLeaves, int preloadBias, cudaStream_t stream) {
 	const u32 side = (u32)pyr.n >> level;
 	const float heightF = (float)(side * zTileNum);
 	const u32 tiles = (u32)((n + kExpandTile - 1) / kExpandTile);
-	expandLevelKernel<<<tiles, kExpandThreads, 0, stream>>>(pyr.level[level], side, heightF, level == 0 ? 1 : 0, coords, n, masks, firstChild,
-			childCoords, childTotal, scan, tiles, colBias, leafAt, numLeaves);
+	if (preloadBias && leafAt)
+		expandLevelPreloadKernel<<<tiles, kExpandThreads, 0, stream>>>(pyr.level[level], side, heightF, level == 0 ? 1 : 0, coords, n, masks,
+				firstChild, childCoords, childTotal, scan, tiles, colBias, leafAt, numLeaves);
+	else
+		expandLevelKernel<<<tiles, kExpandThreads, 0, stream>>>(pyr.level[level], side, heightF, level == 0 ? 1 : 0, coords, n, masks, firstChild,
+				childCoords, childTotal, scan, tiles, colBias, leafAt, numLeaves);
 	return 1;
 }
 
