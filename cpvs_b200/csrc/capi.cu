@@ -246,6 +246,7 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 			if (std::strstr(x, "expand-preload")) ctx->experiments |= kExperimentExpandPreload;
 			if (std::strstr(x, "emit-gather")) ctx->experiments |= kExperimentEmitGather;
 			if (std::strstr(x, "rank-preload")) ctx->experiments |= kExperimentRankPreload;
+			if (std::strstr(x, "insert-witness")) ctx->experiments |= kExperimentInsertWitness;
 		}
 	}
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux2, cudaStreamNonBlocking);
@@ -847,6 +848,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		m.uniqueCount = dUnique + l;
 		m.wordCount = dWords + l;
 		m.rankPreload = (ctx->experiments & kExperimentRankPreload) ? 1 : 0;
+		m.parallelWitness = (ctx->experiments & kExperimentInsertWitness) ? 1 : 0;
 		if (!leafLevel && tablesClearing) {
 			CPVS_CUDA(cudaStreamWaitEvent(mergeStream, ctx->evClear, 0));
 			tablesClearing = false;

@@ -44,7 +44,8 @@ int launchExpandLevel(const PyramidView& pyr, int level, u32 zTileNum, const u64
 // kernels stay instruction-identical (scripts/sass_diff.py) and results never depend on them.
 constexpr unsigned kExperimentExpandPreload = 1u;  // "expand-preload": svo.cu expandLevelPreloadKernel
 constexpr unsigned kExperimentEmitGather = 2u;     // "emit-gather":    emit.cu emitInnerLevelsKernel<true>
-constexpr unsigned kExperimentRankPreload = 4u;    // "rank-preload":   merge.cu rankWriteKernel<true>
+constexpr unsigned kExperimentRankPreload = 4u;    // "rank-preload":   merge.cu rankCountKernel<true>, rankWriteKernel<true>
+constexpr unsigned kExperimentInsertWitness = 8u;  // "insert-witness": merge.cu insertInnerWitnessKernel
 
 // The small top levels (<= kSmallMaxNodes nodes each, root first) expanded by a single CTA.
 constexpr int kSmallThreads = 1024;
@@ -110,7 +111,8 @@ struct MergeLevelArgs {
 	unsigned char* sizeOf; // scratch (rank): compressed size of node j if it is a first occurrence, else 0
 	u64* uniqueCount;      // out: number of unique nodes
 	u64* wordCount;        // out: compressed words of the level
-	int rankPreload;       // experimental variant of the rank's last kernel (kExperimentRankPreload)
+	int rankPreload;       // experimental variants of the rank's first and last kernel (kExperimentRankPreload)
+	int parallelWitness;   // experimental variant of the inner insert (kExperimentInsertWitness)
 };
 // The small top levels merged bottom-up by a single CTA (same result as launchMergeLevel per level).
 struct SmallMergeLevel {

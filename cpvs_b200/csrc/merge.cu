@@ -103,7 +103,9 @@ __global__ void __launch_bounds__(256) insertLeavesKernel(const u32* __restrict_
 	});
 }
 
-template <bool kShared = false>
+// kParallelWitness (experimental, CPVS_EXPERIMENTS=insert-witness): the witness's mask and first-child index are loaded together
+// (the fingerprint already matched, so the mask almost always does too) instead of the index only after the mask compared equal.
+template <bool kShared = false, bool kParallelWitness = false>
 __device__ __forceinline__ u32 insertInnerNode(u32 j, const u16* __restrict__ masks, const u32* __restrict__ firstChild,
 		const u32* __restrict__ childUid, u64* __restrict__ table, u64 tableMask, u32* errorFlag) {
 	const u32 mask = masks[j];
@@ -120,8 +122,15 @@ __device__ __forceinline__ u32 insertInnerNode(u32 j, const u16* __restrict__ ma
 		}
 	}
 	return findGroupSlot<kShared>(table, tableMask, h, j, errorFlag, [&](u32 other) {
-		if (masks[other] != mask) return false;
-		const u32* theirs = childUid + firstChild[other];
+		const u32* theirs;
+		if constexpr (kParallelWitness) {
+			const u32 theirMask = masks[other], theirFirst = firstChild[other];
+			if (theirMask != mask) return false;
+			theirs = childUid + theirFirst;
+		} else {
+			if (masks[other] != mask) return false;
+			theirs = childUid + firstChild[other];
+		}
 		bool same = true;
 #pragma unroll
 		for (u32 c = 0; c < 8; ++c)
@@ -145,7 +154,8 @@ __device__ __forceinline__ u32 compactLitBits(u32 mask) {
 // Held to 32 registers (8 instead of 6 CTAs of 256 threads per SM, one 4-byte spill): the kernel waits on dependent loads 62 % of
 // the time, and the two extra CTAs are worth 0.03 ms on the 16K^2 terrain (inner merge 0.436 -> 0.409 ms, the leaf rank running
 // beside it 0.375 -> 0.348 ms; profiles/r1_switch_probe.md).
-__global__ void __launch_bounds__(256, 8) insertInnerKernel(const u16* __restrict__ masks, const u32* __restrict__ firstChild,
+template <bool kParallelWitness>
+__device__ __forceinline__ void insertInnerBody(const u16* __restrict__ masks, const u32* __restrict__ firstChild,
 		const u32* __restrict__ childUid, u64 n, u64* __restrict__ table, u64 tableMask, u32* __restrict__ slotOf, u32* errorFlag) {
 	__shared__ u32 sFirst[kDirectSlots];
 	const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -167,7 +177,15 @@ __global__ void __launch_bounds__(256, 8) insertInnerKernel(const u16* __restric
 	if (direct)
 		slotOf[j] = (u32)(tableMask + 1 + c) | (sFirst[c] == (u32)j ? kCandidateFlag : 0u);
 	else if (live)
-		slotOf[j] = insertInnerNode((u32)j, masks, firstChild, childUid, table, tableMask, errorFlag);
+		slotOf[j] = insertInnerNode<false, kParallelWitness>((u32)j, masks, firstChild, childUid, table, tableMask, errorFlag);
+}
+__global__ void __launch_bounds__(256, 8) insertInnerKernel(const u16* __restrict__ masks, const u32* __restrict__ firstChild,
+		const u32* __restrict__ childUid, u64 n, u64* __restrict__ table, u64 tableMask, u32* __restrict__ slotOf, u32* errorFlag) {
+	insertInnerBody<false>(masks, firstChild, childUid, n, table, tableMask, slotOf, errorFlag);
+}
+__global__ void __launch_bounds__(256, 8) insertInnerWitnessKernel(const u16* __restrict__ masks, const u32* __restrict__ firstChild,
+		const u32* __restrict__ childUid, u64 n, u64* __restrict__ table, u64 tableMask, u32* __restrict__ slotOf, u32* errorFlag) {
+	insertInnerBody<true>(masks, firstChild, childUid, n, table, tableMask, slotOf, errorFlag);
 }
 
 // gid[j] = slot of node j's group. Ranks the first occurrences (slot's final index == j) in order,
@@ -178,9 +196,26 @@ __global__ void __launch_bounds__(256, 8) insertInnerKernel(const u16* __restric
 // (the only part with random accesses) and leave each node's compressed size in a byte plus the tile's
 // totals; (2) one CTA prefix-sums the tile totals; (3) per tile, a block scan of the bytes and the writes.
 // No CTA ever waits for another one, which matters more here than the extra byte per node of traffic.
+// kPreload (experimental, CPVS_EXPERIMENTS=rank-preload): the four masks of the thread are fetched with one 8-byte load up front
+// instead of one dependent load per first occurrence behind the table look-up.
+template <bool kPreload>
 __global__ void __launch_bounds__(kScanThreads, 8) rankCountKernel(const u64* __restrict__ table, const u16* __restrict__ masks, int leaf, u64 n,
 		const u32* __restrict__ gid, unsigned char* __restrict__ sizeOf, ScanTileState* __restrict__ tiles) {
 	const u64 base = (u64)blockIdx.x * kScanTile + (u64)threadIdx.x * kScanItems;
+	u32 myMask[kScanItems] = {0, 0, 0, 0};
+	if constexpr (kPreload) {
+		if (base + kScanItems <= n) {
+			const uint2 v = *reinterpret_cast<const uint2*>(masks + base);
+			myMask[0] = v.x & 0xFFFFu;
+			myMask[1] = v.x >> 16;
+			myMask[2] = v.y & 0xFFFFu;
+			myMask[3] = v.y >> 16;
+		} else {
+#pragma unroll
+			for (int i = 0; i < kScanItems; ++i)
+				if (base + i < n) myMask[i] = masks[base + i];
+		}
+	}
 	u32 words[kScanItems];
 	u64 cnt = 0, wsum = 0;
 #pragma unroll
@@ -189,7 +224,11 @@ __global__ void __launch_bounds__(kScanThreads, 8) rankCountKernel(const u64* __
 		if (base + i < n) {
 			const u32 g = gid[base + i];
 			if ((g & kCandidateFlag) && (u32)table[g & kGidMask] == (u32)(base + i)) {
-				const u32 k = __popc(masks[base + i] & 0xAAAAu);
+				u32 k;
+				if constexpr (kPreload)
+					k = __popc(myMask[i] & 0xAAAAu);
+				else
+					k = __popc(masks[base + i] & 0xAAAAu);
 				words[i] = 1 + (leaf ? 2 * k : k);
 				cnt += 1;
 				wsum += words[i];
@@ -458,6 +497,8 @@ int launchInsertLevel(const MergeLevelArgs& a, cudaStream_t stream) {
 	const unsigned blocks = (unsigned)((a.n + 255) / 256);
 	if (a.leaf)
 		insertLeavesKernel<<<blocks, 256, 0, stream>>>(a.leafCodes, a.leafHash, a.n, a.table, a.tableMaskDev, a.uid, a.errorFlag);
+	else if (a.parallelWitness)
+		insertInnerWitnessKernel<<<blocks, 256, 0, stream>>>(a.masks, a.firstChild, a.childUid, a.n, a.table, a.tableSize - 1, a.uid, a.errorFlag);
 	else
 		insertInnerKernel<<<blocks, 256, 0, stream>>>(a.masks, a.firstChild, a.childUid, a.n, a.table, a.tableSize - 1, a.uid, a.errorFlag);
 	return 1;
@@ -466,7 +507,10 @@ int launchInsertLevel(const MergeLevelArgs& a, cudaStream_t stream) {
 int launchRankLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaStream_t stream) {
 	if (a.n == 1) return 0;  // done by launchInsertLevel
 	const u32 tiles = (u32)((a.n + kScanTile - 1) / kScanTile);
-	rankCountKernel<<<tiles, kScanThreads, 0, stream>>>(a.table, a.masks, a.leaf, a.n, a.uid, a.sizeOf, scan.tiles);
+	if (a.rankPreload)
+		rankCountKernel<true><<<tiles, kScanThreads, 0, stream>>>(a.table, a.masks, a.leaf, a.n, a.uid, a.sizeOf, scan.tiles);
+	else
+		rankCountKernel<false><<<tiles, kScanThreads, 0, stream>>>(a.table, a.masks, a.leaf, a.n, a.uid, a.sizeOf, scan.tiles);
 	rankScanTilesKernel<<<1, kScanTilesThreads, 0, stream>>>(scan.tiles, tiles, a.uniqueCount, a.wordCount);
 	if (a.rankPreload)
 		rankWriteKernel<true><<<tiles, kScanThreads, 0, stream>>>(a.sizeOf, a.uid, a.n, scan.tiles, a.firstList, a.wordOffset, a.slotOffset);
