@@ -90,6 +90,10 @@ struct cpvs_ctx {
 	cudaEvent_t evRankStart, evRankStop, evJoin3, evClear, evCols;
 	int leafColumns;  // leaves built per column: 1 = where it pays (default), 0 = never, 2 = always (CPVS_LEAF_COLUMNS; tests)
 	unsigned experiments;  // kExperiment* bits (CPVS_EXPERIMENTS): unmeasured kernel variants, off by default
+	// "early-bases" (experimental): the bottom level's rank runs on a stream of its own, and the level bases, the size
+	// read-back and the DAG allocation only wait for its first two kernels (the sizes), not for the third (the writes).
+	cudaStream_t aux4;
+	cudaEvent_t evBottomSized, evBottomRanked;
 };
 
 struct cpvs_minmax {
@@ -247,10 +251,16 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 			if (std::strstr(x, "emit-gather")) ctx->experiments |= kExperimentEmitGather;
 			if (std::strstr(x, "rank-preload")) ctx->experiments |= kExperimentRankPreload;
 			if (std::strstr(x, "insert-witness")) ctx->experiments |= kExperimentInsertWitness;
+			if (std::strstr(x, "early-bases")) ctx->experiments |= kExperimentEarlyBases;
 		}
 	}
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux2, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux3, cudaStreamNonBlocking);
+	ctx->aux4 = nullptr;
+	ctx->evBottomSized = ctx->evBottomRanked = nullptr;
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux4, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evBottomSized, cudaEventDisableTiming);
+	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evBottomRanked, cudaEventDisableTiming);
 	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evJoin3, cudaEventDisableTiming);
 	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evClear, cudaEventDisableTiming);
 	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evCols, cudaEventDisableTiming);
@@ -279,6 +289,9 @@ int cpvs_ctx_destroy(cpvs_ctx* ctx) {
 	if (ctx->evAuxStart) cudaEventDestroy(ctx->evAuxStart);
 	if (ctx->aux2) cudaStreamDestroy(ctx->aux2);
 	if (ctx->aux3) cudaStreamDestroy(ctx->aux3);
+	if (ctx->aux4) cudaStreamDestroy(ctx->aux4);
+	if (ctx->evBottomSized) cudaEventDestroy(ctx->evBottomSized);
+	if (ctx->evBottomRanked) cudaEventDestroy(ctx->evBottomRanked);
 	if (ctx->evJoin3) cudaEventDestroy(ctx->evJoin3);
 	if (ctx->evClear) cudaEventDestroy(ctx->evClear);
 	if (ctx->evCols) cudaEventDestroy(ctx->evCols);
@@ -823,6 +836,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	// Per level: insert on the main stream (gives every node its group id, all the next level needs),
 	// rank on the side stream (orders the unique nodes; only the emission needs it).
 	bool ranksPending = false;
+	bool bottomRankSplit = false;  // early-bases: the bottom level's rank is on aux4, its write kernel not joined before the bases
 	for (int l = minLevel; l < smallLow; ++l) {
 		LevelArrays& a = lv[l];
 		if (!a.n) continue;
@@ -859,12 +873,17 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 			CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_INNER_MERGE], mergeStream));
 		}
 		if (a.n > 1) {
-			cudaStream_t rs = (l & 1) ? ctx->aux3 : ctx->aux2;
+			const bool split = (ctx->experiments & kExperimentEarlyBases) && l == minLevel;
+			cudaStream_t rs = split ? ctx->aux4 : ((l & 1) ? ctx->aux3 : ctx->aux2);
 			CPVS_CUDA(cudaEventRecord(ctx->evFork, mergeStream));
 			CPVS_CUDA(cudaStreamWaitEvent(rs, ctx->evFork, 0));
 			if (leafLevel) CPVS_CUDA(cudaEventRecord(ctx->evRankStart, rs));
-			ctx->launches += launchRankLevel(m, nextScan(a.n), rs);
+			ctx->launches += launchRankLevel(m, nextScan(a.n), rs, split ? ctx->evBottomSized : nullptr);
 			if (leafLevel) CPVS_CUDA(cudaEventRecord(ctx->evRankStop, rs));
+			if (split) {
+				CPVS_CUDA(cudaEventRecord(ctx->evBottomRanked, rs));
+				bottomRankSplit = true;
+			}
 			ranksPending = true;
 		}
 	}
@@ -894,6 +913,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		CPVS_CUDA(cudaStreamWaitEvent(mergeStream, ctx->evJoin, 0));
 		CPVS_CUDA(cudaEventRecord(ctx->evJoin3, ctx->aux3));
 		CPVS_CUDA(cudaStreamWaitEvent(mergeStream, ctx->evJoin3, 0));
+		if (bottomRankSplit) CPVS_CUDA(cudaStreamWaitEvent(mergeStream, ctx->evBottomSized, 0));  // its sizes, not its writes
 	}
 	CPVS_CUDA(cudaEventRecord(ctx->evJoin, mergeStream));
 	CPVS_CUDA(cudaStreamWaitEvent(st, ctx->evJoin, 0));
@@ -932,6 +952,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	// now; the leaf level (most of the words) stays on the main stream, the chain of inner levels runs on
 	// the high-priority side stream next to it.
 	// phase EMIT_INNER: fork .. join on the main stream; phase EMIT_LEAVES: the leaf kernel alone (they overlap).
+	if (bottomRankSplit) cudaStreamWaitEvent(st, ctx->evBottomRanked, 0);  // the emission reads what the rank's last kernel wrote
 	cudaEventRecord(phases.ev[CPVS_PHASE_EMIT_INNER], st);
 	const bool leafEmit = useLeaf && lv[2].n;
 	if (leafEmit) {

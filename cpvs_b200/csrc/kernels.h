@@ -46,6 +46,7 @@ constexpr unsigned kExperimentExpandPreload = 1u;  // "expand-preload": svo.cu e
 constexpr unsigned kExperimentEmitGather = 2u;     // "emit-gather":    emit.cu emitInnerLevelsKernel<true>
 constexpr unsigned kExperimentRankPreload = 4u;    // "rank-preload":   merge.cu rankCountKernel<true>, rankWriteKernel<true>
 constexpr unsigned kExperimentInsertWitness = 8u;  // "insert-witness": merge.cu insertInnerWitnessKernel
+constexpr unsigned kExperimentEarlyBases = 16u;    // "early-bases":    capi.cu, streams only (see cpvs_ctx::aux4)
 
 // The small top levels (<= kSmallMaxNodes nodes each, root first) expanded by a single CTA.
 constexpr int kSmallThreads = 1024;
@@ -140,7 +141,8 @@ int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* table
 // Insert assigns group ids (all the parent level needs); rank orders the unique nodes and may run
 // concurrently with the next level's insert as long as this level's table is left alone.
 int launchInsertLevel(const MergeLevelArgs& a, cudaStream_t stream);
-int launchRankLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaStream_t stream);
+// afterSizes (optional) is recorded once uniqueCount / wordCount are final, ahead of the kernel that writes the lists.
+int launchRankLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaStream_t stream, cudaEvent_t afterSizes = nullptr);
 
 // ---- emit.cu: compress (reference src/CompressedShadow.cpp:326-392) ----
 struct EmitLevelArgs {

@@ -504,7 +504,7 @@ int launchInsertLevel(const MergeLevelArgs& a, cudaStream_t stream) {
 	return 1;
 }
 
-int launchRankLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaStream_t stream) {
+int launchRankLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaStream_t stream, cudaEvent_t afterSizes) {
 	if (a.n == 1) return 0;  // done by launchInsertLevel
 	const u32 tiles = (u32)((a.n + kScanTile - 1) / kScanTile);
 	if (a.rankPreload)
@@ -512,6 +512,7 @@ int launchRankLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaStream_t strea
 	else
 		rankCountKernel<false><<<tiles, kScanThreads, 0, stream>>>(a.table, a.masks, a.leaf, a.n, a.uid, a.sizeOf, scan.tiles);
 	rankScanTilesKernel<<<1, kScanTilesThreads, 0, stream>>>(scan.tiles, tiles, a.uniqueCount, a.wordCount);
+	if (afterSizes) cudaEventRecord(afterSizes, stream);
 	if (a.rankPreload)
 		rankWriteKernel<true><<<tiles, kScanThreads, 0, stream>>>(a.sizeOf, a.uid, a.n, scan.tiles, a.firstList, a.wordOffset, a.slotOffset);
 	else
