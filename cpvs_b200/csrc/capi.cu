@@ -94,6 +94,11 @@ struct cpvs_ctx {
 	// read-back and the DAG allocation only wait for its first two kernels (the sizes), not for the third (the writes).
 	cudaStream_t aux4;
 	cudaEvent_t evBottomSized, evBottomRanked;
+	// "leaf-fp64" (experimental): the leaf groups found by fingerprint are verified on this stream, beside the inner inserts;
+	// forceExact is set while a build whose verification failed is redone with the exact insert.
+	cudaStream_t aux5;
+	cudaEvent_t evVerified;
+	bool forceExact;
 };
 
 struct cpvs_minmax {
@@ -252,12 +257,17 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 			if (std::strstr(x, "rank-preload")) ctx->experiments |= kExperimentRankPreload;
 			if (std::strstr(x, "insert-witness")) ctx->experiments |= kExperimentInsertWitness;
 			if (std::strstr(x, "early-bases")) ctx->experiments |= kExperimentEarlyBases;
+			if (std::strstr(x, "leaf-fp64")) ctx->experiments |= kExperimentLeafFp64;
+			if (std::strstr(x, "leaf-fp64-weak")) ctx->experiments |= kExperimentLeafFpWeak;
 		}
 	}
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux2, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux3, cudaStreamNonBlocking);
-	ctx->aux4 = nullptr;
-	ctx->evBottomSized = ctx->evBottomRanked = nullptr;
+	ctx->aux4 = ctx->aux5 = nullptr;
+	ctx->evBottomSized = ctx->evBottomRanked = ctx->evVerified = nullptr;
+	ctx->forceExact = false;
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux5, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evVerified, cudaEventDisableTiming);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux4, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evBottomSized, cudaEventDisableTiming);
 	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evBottomRanked, cudaEventDisableTiming);
@@ -290,6 +300,8 @@ int cpvs_ctx_destroy(cpvs_ctx* ctx) {
 	if (ctx->aux2) cudaStreamDestroy(ctx->aux2);
 	if (ctx->aux3) cudaStreamDestroy(ctx->aux3);
 	if (ctx->aux4) cudaStreamDestroy(ctx->aux4);
+	if (ctx->aux5) cudaStreamDestroy(ctx->aux5);
+	if (ctx->evVerified) cudaEventDestroy(ctx->evVerified);
 	if (ctx->evBottomSized) cudaEventDestroy(ctx->evBottomSized);
 	if (ctx->evBottomRanked) cudaEventDestroy(ctx->evBottomRanked);
 	if (ctx->evJoin3) cudaEventDestroy(ctx->evJoin3);
@@ -569,7 +581,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	for (cudaEvent_t& e : phases.ev) CPVS_CUDA(cudaEventCreate(&e));
 	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_COUNT], st));
 
-	std::lock_guard<std::mutex> buildGuard(ctx->buildLock);
+	std::unique_lock<std::mutex> buildGuard(ctx->buildLock);
 	PyramidView pyr;
 	pyr.n = mm->n;
 	pyr.numLevels = L;
@@ -762,6 +774,9 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	if (tablesClearing) CPVS_CUDA(cudaEventRecord(ctx->evClear, ctx->aux3));
 	u64 *dSketchBits = dScalars + 161, *dLeafTableMask = dScalars + 162;
 	u32* dErrorFlag = reinterpret_cast<u32*>(dScalars + 163);
+	u32* dMismatchFlag = reinterpret_cast<u32*>(dScalars + 164);  // leaf-fp64: a fingerprint group held two different leaves
+	const bool leafFingerprint = haveLeaves && (ctx->experiments & kExperimentLeafFp64) && !ctx->forceExact;
+	bool verifyPending = false;
 	u64 tileCursor = 0, launchCursor = 0;
 	auto nextScan = [&](u64 n, u64 tileNodes = kScanTile) {
 		ScanLaunch s{dTickets + launchCursor, dTiles + tileCursor};
@@ -826,7 +841,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAF_TABLE], mergeStream));
 	if (haveLeaves) {
 		ctx->launches += launchSketchPopcount(dSketch, dSketchBits, mergeStream);
-		ctx->launches += launchSizeLeafTable(lv[2].table, lv[2].tableSlots, dSketchBits, dLeafTableMask, mergeStream);
+		ctx->launches += launchSizeLeafTable(lv[2].table, lv[2].tableSlots, dSketchBits, dLeafTableMask, leafFingerprint ? 1 : 0, mergeStream);
 	}
 	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAF_INSERT], mergeStream));
 	if (!(useLeaf && lv[2].n)) {
@@ -863,6 +878,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		m.wordCount = dWords + l;
 		m.rankPreload = (ctx->experiments & kExperimentRankPreload) ? 1 : 0;
 		m.parallelWitness = (ctx->experiments & kExperimentInsertWitness) ? 1 : 0;
+		m.fingerprint = (leafLevel && leafFingerprint) ? ((ctx->experiments & kExperimentLeafFpWeak) ? 2 : 1) : 0;
 		if (!leafLevel && tablesClearing) {
 			CPVS_CUDA(cudaStreamWaitEvent(mergeStream, ctx->evClear, 0));
 			tablesClearing = false;
@@ -871,6 +887,13 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		if (leafLevel) {
 			CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAF_RESOLVE], mergeStream));
 			CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_INNER_MERGE], mergeStream));
+			if (m.fingerprint) {  // the exact compare, off the critical path
+				CPVS_CUDA(cudaEventRecord(ctx->evFork, mergeStream));
+				CPVS_CUDA(cudaStreamWaitEvent(ctx->aux5, ctx->evFork, 0));
+				ctx->launches += launchVerifyLeafGroups(m, dMismatchFlag, ctx->aux5);
+				CPVS_CUDA(cudaEventRecord(ctx->evVerified, ctx->aux5));
+				verifyPending = true;
+			}
 		}
 		if (a.n > 1) {
 			const bool split = (ctx->experiments & kExperimentEarlyBases) && l == minLevel;
@@ -915,6 +938,7 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 		CPVS_CUDA(cudaStreamWaitEvent(mergeStream, ctx->evJoin3, 0));
 		if (bottomRankSplit) CPVS_CUDA(cudaStreamWaitEvent(mergeStream, ctx->evBottomSized, 0));  // its sizes, not its writes
 	}
+	if (verifyPending) CPVS_CUDA(cudaStreamWaitEvent(mergeStream, ctx->evVerified, 0));  // its verdict is read back with the sizes
 	CPVS_CUDA(cudaEventRecord(ctx->evJoin, mergeStream));
 	CPVS_CUDA(cudaStreamWaitEvent(st, ctx->evJoin, 0));
 	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_BASES], st));
@@ -931,6 +955,15 @@ int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex
 			return fail(CPVS_EINTERNAL, "level %d: expansion produced %llu nodes, count pass predicted %llu", l - 1,
 					(unsigned long long)hScalars[128 + l], (unsigned long long)lv[l - 1].n);
 	if (hScalars[163] != 0) return fail(CPVS_EINTERNAL, "merge table overflow (leaf table mask %llu)", (unsigned long long)hScalars[162]);
+	if (verifyPending && (u32)hScalars[164] != 0) {
+		// two different leaves shared a 64-bit fingerprint: nothing has been emitted yet -- once more, with the exact insert
+		if (bottomRankSplit) CPVS_CUDA(cudaStreamSynchronize(ctx->aux4));  // the rank's last kernel still uses the arena
+		ctx->forceExact = true;
+		buildGuard.unlock();
+		const int rc = cpvs_shadow_create(ctx, mm, zTileIndex, zTileNum, leafmasks, out);
+		ctx->forceExact = false;
+		return rc;
+	}
 	const u64 totalWords = hScalars[160];
 	if (totalWords > (1ull << 32)) return fail(CPVS_EOVERFLOW, "DAG needs %llu words; offsets are 32-bit", (unsigned long long)totalWords);
 

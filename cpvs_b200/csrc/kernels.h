@@ -47,6 +47,8 @@ constexpr unsigned kExperimentEmitGather = 2u;     // "emit-gather":    emit.cu 
 constexpr unsigned kExperimentRankPreload = 4u;    // "rank-preload":   merge.cu rankCountKernel<true>, rankWriteKernel<true>
 constexpr unsigned kExperimentInsertWitness = 8u;  // "insert-witness": merge.cu insertInnerWitnessKernel
 constexpr unsigned kExperimentEarlyBases = 16u;    // "early-bases":    capi.cu, streams only (see cpvs_ctx::aux4)
+constexpr unsigned kExperimentLeafFp64 = 32u;      // "leaf-fp64":      merge.cu insertLeavesFingerprintKernel + verifyLeafGroupsKernel
+constexpr unsigned kExperimentLeafFpWeak = 64u;    // "leaf-fp64-weak": the same with a 12-bit fingerprint (tests of the fallback only)
 
 // The small top levels (<= kSmallMaxNodes nodes each, root first) expanded by a single CTA.
 constexpr int kSmallThreads = 1024;
@@ -114,6 +116,8 @@ struct MergeLevelArgs {
 	u64* wordCount;        // out: compressed words of the level
 	int rankPreload;       // experimental variants of the rank's first and last kernel (kExperimentRankPreload)
 	int parallelWitness;   // experimental variant of the inner insert (kExperimentInsertWitness)
+	int fingerprint;       // leaf: 16-byte slots grouped by 64-bit fingerprint, verified later (kExperimentLeafFp64);
+	                       // 2: a 12-bit fingerprint, to drive tests through the failed-verification path
 };
 // The small top levels merged bottom-up by a single CTA (same result as launchMergeLevel per level).
 struct SmallMergeLevel {
@@ -137,7 +141,10 @@ struct SmallMergeArgs {
 int launchMergeSmallLevels(const SmallMergeArgs& a, cudaStream_t stream);
 
 // Leaf level only: picks the table capacity from the sketch's set-bit count and clears that many slots.
-int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* tableMaskDev, cudaStream_t stream);
+// wideSlots: 16-byte slots (kExperimentLeafFp64); maxSlots still counts the 8-byte words behind `table`.
+int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* tableMaskDev, int wideSlots, cudaStream_t stream);
+// kExperimentLeafFp64: every leaf that is not its group's first is compared with the first; *mismatchFlag = 1 on a difference.
+int launchVerifyLeafGroups(const MergeLevelArgs& a, u32* mismatchFlag, cudaStream_t stream);
 // Insert assigns group ids (all the parent level needs); rank orders the unique nodes and may run
 // concurrently with the next level's insert as long as this level's table is left alone.
 int launchInsertLevel(const MergeLevelArgs& a, cudaStream_t stream);

@@ -63,6 +63,8 @@ __device__ __forceinline__ u32 findGroupSlot(u64* __restrict__ table, u64 tableM
 // Leaf table capacity from the distinct-count sketch (linear counting: u ~ -m ln(zero fraction)), rounded
 // up to a power of two with >= 1.5x headroom, then cleared. The result does not depend on the capacity,
 // only the speed does: a table sized for the distinct leaves (not for all leaves) stays in L2.
+// kWide (experimental, leaf-fp64): 16-byte slots (64-bit fingerprint, smallest node index), maxSlots counts such slots.
+template <bool kWide>
 __global__ void __launch_bounds__(256) sizeAndClearLeafTableKernel(u64* __restrict__ table, u64 maxSlots, const u64* __restrict__ setBits,
 		u64* __restrict__ tableMaskDev) {
 	const float m = (float)kSketchWords * 32.0f;
@@ -74,7 +76,8 @@ __global__ void __launch_bounds__(256) sizeAndClearLeafTableKernel(u64* __restri
 	if (cap > maxSlots) cap = maxSlots;
 	if (blockIdx.x == 0 && threadIdx.x == 0) *tableMaskDev = cap - 1;
 	ulonglong2* t2 = reinterpret_cast<ulonglong2*>(table);
-	for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap / 2; i += (u64)gridDim.x * blockDim.x) t2[i] = make_ulonglong2(kEmpty, kEmpty);
+	const u64 pairs = kWide ? cap : cap / 2;
+	for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += (u64)gridDim.x * blockDim.x) t2[i] = make_ulonglong2(kEmpty, kEmpty);
 }
 
 __global__ void __launch_bounds__(256) insertLeavesKernel(const u32* __restrict__ codes, const u64* __restrict__ hashes, u64 n, u64* __restrict__ table,
@@ -101,6 +104,62 @@ __global__ void __launch_bounds__(256) insertLeavesKernel(const u32* __restrict_
 		const uint4 b0 = theirs[0], b1 = theirs[1];
 		return a0.x == b0.x && a0.y == b0.y && a0.z == b0.z && a0.w == b0.w && a1.x == b1.x && a1.y == b1.y && a1.z == b1.z && a1.w == b1.w;
 	});
+}
+
+// ---- experimental: leaf-fp64 ------------------------------------------------------------------------------------------------
+// The exact insert above pays a DRAM round trip per duplicate leaf for the witness's code (L2 allocates 128-byte lines, a witness
+// is one 32-byte sector of an otherwise idle line: 2.5 M witnesses want 320 MB of L2). Here the grouping that the parent level
+// waits for trusts a 64-bit fingerprint -- 16-byte slots (fingerprint, smallest node index), one probe, no witness read -- and
+// the exact compare moves off the critical path: verifyLeafGroupsKernel, on a side stream beside the inner inserts, compares
+// every leaf that is not its group's first with the first. A mismatch raises a flag and the build is redone with the exact
+// insert, so the words never depend on the hash.
+__global__ void __launch_bounds__(256) insertLeavesFingerprintKernel(const u32* __restrict__ codes, u64 n, u64* __restrict__ table,
+		const u64* __restrict__ tableMaskDev, u64 fingerprintMask, u32* __restrict__ slotOf, u32* errorFlag) {
+	const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	const u64 tableMask = *tableMaskDev;
+	const uint4* mine = reinterpret_cast<const uint4*>(codes + j * 8);
+	const uint4 a0 = __ldcs(mine), a1 = __ldcs(mine + 1);
+	u64 h = 0x9E3779B97F4A7C15ull;
+	h = (h ^ (((u64)a0.y << 32) | a0.x)) * 0xFF51AFD7ED558CCDull;
+	h = (h ^ (h >> 32) ^ (((u64)a0.w << 32) | a0.z)) * 0xC4CEB9FE1A85EC53ull;
+	h = (h ^ (h >> 32) ^ (((u64)a1.y << 32) | a1.x)) * 0xFF51AFD7ED558CCDull;
+	h = (h ^ (h >> 32) ^ (((u64)a1.w << 32) | a1.z)) * 0xC4CEB9FE1A85EC53ull;
+	h = mix64(h);
+	u64 slot = (h >> 20) & tableMask;  // (the low bits would do as well; these are the ones the sketch looked at)
+	h &= fingerprintMask;              // all ones, except in the test mode that provokes collisions (leaf-fp64-weak)
+	if (h == kEmpty) h = 0;            // the empty marker is not a fingerprint
+	for (u64 probes = 0; probes <= tableMask; ++probes) {
+		u64* entry = table + 2 * slot;
+		u64 fp = ldRelaxed64(entry);
+		if (fp == kEmpty) {
+			const u64 old = atomicCAS(reinterpret_cast<unsigned long long*>(entry), (unsigned long long)kEmpty, (unsigned long long)h);
+			fp = old == kEmpty ? h : old;
+		}
+		if (fp == h) {
+			// smallest index of the group: read first, the members of a popular group must not queue up on one address
+			u32 lowered = 0;
+			if (ldRelaxed64(entry + 1) > j) lowered = atomicMin(reinterpret_cast<unsigned long long*>(entry + 1), (unsigned long long)j) > j ? kCandidateFlag : 0u;
+			slotOf[j] = (u32)slot | lowered;
+			return;
+		}
+		slot = (slot + 1) & tableMask;
+	}
+	atomicExch(errorFlag, 1u);
+	slotOf[j] = 0u;
+}
+
+__global__ void __launch_bounds__(256) verifyLeafGroupsKernel(const u32* __restrict__ codes, u64 n, const u64* __restrict__ table,
+		const u32* __restrict__ slotOf, u32* mismatchFlag) {
+	const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	const u32 first = (u32)table[2 * (u64)(slotOf[j] & kGidMask) + 1];
+	if (first == (u32)j) return;
+	const uint4* mine = reinterpret_cast<const uint4*>(codes + j * 8);
+	const uint4* theirs = reinterpret_cast<const uint4*>(codes + (u64)first * 8);
+	const uint4 a0 = __ldcs(mine), a1 = __ldcs(mine + 1), b0 = theirs[0], b1 = theirs[1];
+	const bool same = a0.x == b0.x && a0.y == b0.y && a0.z == b0.z && a0.w == b0.w && a1.x == b1.x && a1.y == b1.y && a1.z == b1.z && a1.w == b1.w;
+	if (!same) atomicExch(mismatchFlag, 1u);
 }
 
 // kParallelWitness (experimental, CPVS_EXPERIMENTS=insert-witness): the witness's mask and first-child index are loaded together
@@ -198,7 +257,8 @@ __global__ void __launch_bounds__(256, 8) insertInnerWitnessKernel(const u16* __
 // No CTA ever waits for another one, which matters more here than the extra byte per node of traffic.
 // kPreload (experimental, CPVS_EXPERIMENTS=rank-preload): the four masks of the thread are fetched with one 8-byte load up front
 // instead of one dependent load per first occurrence behind the table look-up.
-template <bool kPreload>
+// kWide (experimental, leaf-fp64): 16-byte slots, the group's smallest index is the second word.
+template <bool kPreload, bool kWide = false>
 __global__ void __launch_bounds__(kScanThreads, 8) rankCountKernel(const u64* __restrict__ table, const u16* __restrict__ masks, int leaf, u64 n,
 		const u32* __restrict__ gid, unsigned char* __restrict__ sizeOf, ScanTileState* __restrict__ tiles) {
 	const u64 base = (u64)blockIdx.x * kScanTile + (u64)threadIdx.x * kScanItems;
@@ -223,7 +283,7 @@ __global__ void __launch_bounds__(kScanThreads, 8) rankCountKernel(const u64* __
 		words[i] = 0;
 		if (base + i < n) {
 			const u32 g = gid[base + i];
-			if ((g & kCandidateFlag) && (u32)table[g & kGidMask] == (u32)(base + i)) {
+			if ((g & kCandidateFlag) && (u32)table[kWide ? 2 * (u64)(g & kGidMask) + 1 : (u64)(g & kGidMask)] == (u32)(base + i)) {
 				u32 k;
 				if constexpr (kPreload)
 					k = __popc(myMask[i] & 0xAAAAu);
@@ -484,8 +544,16 @@ int launchMergeSmallLevels(const SmallMergeArgs& a, cudaStream_t stream) {
 	return 1;
 }
 
-int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* tableMaskDev, cudaStream_t stream) {
-	sizeAndClearLeafTableKernel<<<148 * 8, 256, 0, stream>>>(table, maxSlots, setBits, tableMaskDev);
+int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* tableMaskDev, int wideSlots, cudaStream_t stream) {
+	if (wideSlots)
+		sizeAndClearLeafTableKernel<true><<<148 * 8, 256, 0, stream>>>(table, maxSlots / 2, setBits, tableMaskDev);
+	else
+		sizeAndClearLeafTableKernel<false><<<148 * 8, 256, 0, stream>>>(table, maxSlots, setBits, tableMaskDev);
+	return 1;
+}
+
+int launchVerifyLeafGroups(const MergeLevelArgs& a, u32* mismatchFlag, cudaStream_t stream) {
+	verifyLeafGroupsKernel<<<(unsigned)((a.n + 255) / 256), 256, 0, stream>>>(a.leafCodes, a.n, a.table, a.uid, mismatchFlag);
 	return 1;
 }
 
@@ -495,7 +563,10 @@ int launchInsertLevel(const MergeLevelArgs& a, cudaStream_t stream) {
 		return 1;
 	}
 	const unsigned blocks = (unsigned)((a.n + 255) / 256);
-	if (a.leaf)
+	if (a.leaf && a.fingerprint)
+		insertLeavesFingerprintKernel<<<blocks, 256, 0, stream>>>(a.leafCodes, a.n, a.table, a.tableMaskDev, a.fingerprint == 2 ? 0xFFFull : ~0ull,
+				a.uid, a.errorFlag);
+	else if (a.leaf)
 		insertLeavesKernel<<<blocks, 256, 0, stream>>>(a.leafCodes, a.leafHash, a.n, a.table, a.tableMaskDev, a.uid, a.errorFlag);
 	else if (a.parallelWitness)
 		insertInnerWitnessKernel<<<blocks, 256, 0, stream>>>(a.masks, a.firstChild, a.childUid, a.n, a.table, a.tableSize - 1, a.uid, a.errorFlag);
@@ -507,7 +578,9 @@ int launchInsertLevel(const MergeLevelArgs& a, cudaStream_t stream) {
 int launchRankLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaStream_t stream, cudaEvent_t afterSizes) {
 	if (a.n == 1) return 0;  // done by launchInsertLevel
 	const u32 tiles = (u32)((a.n + kScanTile - 1) / kScanTile);
-	if (a.rankPreload)
+	if (a.leaf && a.fingerprint)
+		rankCountKernel<false, true><<<tiles, kScanThreads, 0, stream>>>(a.table, a.masks, a.leaf, a.n, a.uid, a.sizeOf, scan.tiles);
+	else if (a.rankPreload)
 		rankCountKernel<true><<<tiles, kScanThreads, 0, stream>>>(a.table, a.masks, a.leaf, a.n, a.uid, a.sizeOf, scan.tiles);
 	else
 		rankCountKernel<false><<<tiles, kScanThreads, 0, stream>>>(a.table, a.masks, a.leaf, a.n, a.uid, a.sizeOf, scan.tiles);

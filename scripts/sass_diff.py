@@ -47,7 +47,7 @@ def main():
             old, new = kernels(cub["old"]), kernels(cub["new"])
             for name in sorted(set(old) | set(new)):
                 # a kernel that became a template keeps its default behaviour in the <false> instantiation
-                twin = next((t for t in (name, name + "<false>", name + "<false, 3>") if t in new), name)
+                twin = next((t for t in (name, name + "<false>", name + "<false, false>") if t in new), name)
                 if name not in old:
                     print("%-9s %-50s new kernel (%d instructions)" % (f, name[:50], len(new[name])))
                 elif twin not in new:

@@ -20,7 +20,7 @@ import cpvs_b200  # noqa: E402
 from cpvs_b200 import synth  # noqa: E402
 
 KEYS = ["CPVS_EXPERIMENTS", "CPVS_LEAF_COLUMNS"]
-NAMES = ["expand-preload", "emit-gather", "rank-preload", "insert-witness", "early-bases"]
+NAMES = ["expand-preload", "emit-gather", "rank-preload", "insert-witness", "early-bases", "leaf-fp64"]
 SETTINGS = [{}] + [{"CPVS_EXPERIMENTS": name} for name in NAMES] + [{"CPVS_EXPERIMENTS": ",".join(NAMES)}, {}]
 
 

@@ -553,8 +553,8 @@ def test_leaf_kernels_forced(oracle, mode, monkeypatch):
 # ---- experimental kernel variants: not measured yet, off by default, and not part of the default GPU run ----------------
 
 @pytest.mark.skipif(os.environ.get("CPVS_TEST_EXPERIMENTAL") != "1", reason="unmeasured kernel variants: set CPVS_TEST_EXPERIMENTAL=1 to run")
-@pytest.mark.parametrize("names", ["expand-preload", "emit-gather", "rank-preload", "insert-witness", "early-bases",
-                                   "expand-preload,emit-gather,rank-preload,insert-witness,early-bases"])
+@pytest.mark.parametrize("names", ["expand-preload", "emit-gather", "rank-preload", "insert-witness", "early-bases", "leaf-fp64", "leaf-fp64-weak",
+                                   "expand-preload,emit-gather,rank-preload,insert-witness,early-bases,leaf-fp64"])
 def test_experimental_variants_keep_the_words(oracle, names, monkeypatch):
     """CPVS_EXPERIMENTS picks kernel variants written without GPU time to measure them; whatever they
     do to the speed, the words must not move. The per-column leaf builder is forced so that the column scatter of the
