@@ -189,6 +189,13 @@ def run_reference(args):
 
 
 def workload_config(args, n_gpus):
+    cfg = _workload_config(args, n_gpus)
+    if os.environ.get("CPVS_EXPERIMENTS"):  # unmeasured kernel variants switched on for this run
+        cfg["experiments"] = os.environ["CPVS_EXPERIMENTS"]
+    return cfg
+
+
+def _workload_config(args, n_gpus):
     if n_gpus == 1:
         return {"workload": "configs[1]: %dx%d synthetic %s depth map, leafmasks on, single DAG (MinMaxHierarchy + CompressedShadow::create) "
                             "+ %d random NDC lookups" % (args.size, args.size, args.kind, args.lookups),
