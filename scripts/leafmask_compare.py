@@ -1,5 +1,7 @@
 """BASELINE configs[3], second half: the same surface-hugging G-buffer lookups with leafmasks on vs off.
-Leafmask-less octrees descend three more levels of 9-word nodes, so they are built at 4096^2 here."""
+Leafmask-less octrees descend three more levels of 9-word nodes, so they are built at 4096^2 here.
+Appends what it prints to gpurun_out/leafmask_compare.txt (copy it under profiles/ for the record)."""
+import os
 import sys
 import time
 sys.path.insert(0, ".")
@@ -26,6 +28,16 @@ frames = [torch.from_numpy(pos_np).cuda() for _ in range(4)]
 vis = torch.zeros((gh, gw), dtype=torch.uint8, device="cuda")
 ident = np.eye(4, dtype=np.float32)
 results = {}
+os.makedirs("gpurun_out", exist_ok=True)
+record = open(os.path.join("gpurun_out", "leafmask_compare.txt"), "a")
+
+
+def say(text):
+    print(text)
+    record.write(text + "\n")
+    record.flush()
+
+
 for leaf in (True, False):
     mm = cpvs_b200.MinMaxHierarchy(d, ctx, n=n)
     sh = cpvs_b200.CompressedShadow.create(mm, leafmasks=leaf)
@@ -41,6 +53,6 @@ for leaf in (True, False):
     dt = (time.perf_counter() - t) / 20
     results[leaf] = vis.cpu().numpy().copy()
     svo, dagn, _ = sh.level_counts()
-    print("n=%d leafmasks=%s: build %.2f ms, %d words (%.1f MB), svo nodes %d, lookups %.3f ms = %.1f G/s"
+    say("n=%d leafmasks=%s: build %.2f ms, %d words (%.1f MB), svo nodes %d, lookups %.3f ms = %.1f G/s"
           % (n, leaf, sh.info.build_ms, sh.info.words, sh.info.words * 4 / 1e6, int(svo.sum()), dt * 1e3, gw * gh / dt / 1e9))
-print("identical visibility with and without leafmasks:", bool(np.array_equal(results[True], results[False])))
+say("identical visibility with and without leafmasks: %s" % bool(np.array_equal(results[True], results[False])))
