@@ -33,9 +33,14 @@ class CpvsError(RuntimeError):
         self.code = code
 
 
+class CtxStats(ctypes.Structure):
+    _fields_ = [("predicted_builds", ctypes.c_uint64), ("exact_builds", ctypes.c_uint64), ("overflow_rebuilds", ctypes.c_uint64),
+                ("reemissions", ctypes.c_uint64)]
+
+
 class ShadowInfo(ctypes.Structure):
     _fields_ = [("num_levels", ctypes.c_uint32), ("leafmasks", ctypes.c_uint32), ("total_visibility", ctypes.c_uint32),
-                ("reserved", ctypes.c_uint32), ("words", ctypes.c_uint64), ("svo_nodes", ctypes.c_uint64 * MAX_LEVELS),
+                ("predicted", ctypes.c_uint32), ("words", ctypes.c_uint64), ("svo_nodes", ctypes.c_uint64 * MAX_LEVELS),
                 ("dag_nodes", ctypes.c_uint64 * MAX_LEVELS), ("dag_words", ctypes.c_uint64 * MAX_LEVELS),
                 ("build_ms", ctypes.c_float), ("phase_ms", ctypes.c_float * NUM_PHASES)]
 
@@ -51,6 +56,8 @@ SIGNATURES = {
     "cpvs_ctx_reserve": (_I, [_VP, _U64]),
     "cpvs_ctx_synchronize": (_I, [_VP]),
     "cpvs_ctx_launch_count": (_U64, [_VP]),
+    "cpvs_ctx_set_prediction": (_I, [_VP, _I, _U32]),
+    "cpvs_ctx_get_stats": (_I, [_VP, _VP]),
     "cpvs_last_error": (ctypes.c_char_p, []),
     "cpvs_version": (ctypes.c_char_p, []),
     "cpvs_minmax_build": (_I, [_VP, _VP, _I, _I, _PP]),
@@ -62,6 +69,8 @@ SIGNATURES = {
     "cpvs_minmax_childmask": (_I, [_VP, _U32, _U32, _U32, _U32, _U32, ctypes.POINTER(_U32)]),
     "cpvs_minmax_timing": (_I, [_VP, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
     "cpvs_shadow_create": (_I, [_VP, _VP, _U32, _U32, _I, _PP]),
+    "cpvs_shadow_create_async": (_I, [_VP, _VP, _U32, _U32, _I, _PP]),
+    "cpvs_shadow_wait": (_I, [_VP]),
     "cpvs_shadow_create_from_depth": (_I, [_VP, _VP, _I, _I, _U32, _U32, _I, _PP]),
     "cpvs_shadow_destroy": (_I, [_VP]),
     "cpvs_shadow_info_get": (_I, [_VP, ctypes.POINTER(ShadowInfo)]),
@@ -144,6 +153,15 @@ class Context:
     def launch_count(self):
         return int(self._lib.cpvs_ctx_launch_count(self.handle))
 
+    def set_prediction(self, enabled=True, headroom_shift=3):
+        """Sizing of builds from the previous build of the same shape (see cpvs_ctx_set_prediction)."""
+        _check(self._lib.cpvs_ctx_set_prediction(self.handle, int(bool(enabled)), int(headroom_shift)))
+
+    def stats(self):
+        st = CtxStats()
+        _check(self._lib.cpvs_ctx_get_stats(self.handle, ctypes.byref(st)))
+        return {name: int(getattr(st, name)) for name, _ in CtxStats._fields_}
+
     def close(self):
         if self.handle:
             self._lib.cpvs_ctx_destroy(self.handle)
@@ -159,7 +177,7 @@ class Context:
 _default_ctx = {}
 
 
-SCENES = {"plane": 0, "city": 2}  # CPVS_SCENE_*: the scenes with a device generator
+SCENES = {"plane": 0, "city": 2, "terrain_dev": 3}  # CPVS_SCENE_*: the scenes with a device generator
 
 
 def generate_depth(kind, n, out, tile=(0, 0), tiles_per_side=1, ctx=None):
@@ -246,20 +264,37 @@ class CompressedShadow:
 
     SHADOW, VISIBLE, PARTIAL = SHADOW, VISIBLE, PARTIAL
 
-    def __init__(self, ctx, handle):
+    def __init__(self, ctx, handle, wait=True, keep=None):
         self.ctx = ctx
         self._lib = ctx._lib
         self.handle = handle
-        self.info = ShadowInfo()
-        _check(self._lib.cpvs_shadow_info_get(handle, ctypes.byref(self.info)))
+        self._info = None
+        self._keep = keep  # the hierarchy of a build in flight
+        if wait:
+            self.wait()
 
     @classmethod
-    def create(cls, minmax, zTileIndex=0, zTileNum=1, leafmasks=True, ctx=None):
-        """``CompressedShadow::create(minMax, zTileIndex, zTileNum)`` (src/CompressedShadow.cpp:49-59)."""
+    def create(cls, minmax, zTileIndex=0, zTileNum=1, leafmasks=True, ctx=None, wait=True):
+        """``CompressedShadow::create(minMax, zTileIndex, zTileNum)`` (src/CompressedShadow.cpp:49-59).
+        ``wait=False``: return while the build is in flight (``cpvs_shadow_create_async``); ``wait()`` or any accessor finishes it."""
         ctx = ctx or minmax.ctx
         h = ctypes.c_void_p()
-        _check(ctx._lib.cpvs_shadow_create(ctx.handle, minmax.handle, zTileIndex, zTileNum, int(leafmasks), ctypes.byref(h)))
-        return cls(ctx, h)
+        fn = ctx._lib.cpvs_shadow_create if wait else ctx._lib.cpvs_shadow_create_async
+        _check(fn(ctx.handle, minmax.handle, zTileIndex, zTileNum, int(leafmasks), ctypes.byref(h)))
+        return cls(ctx, h, wait, None if wait else minmax)
+
+    def wait(self):
+        if self._info is None:
+            _check(self._lib.cpvs_shadow_wait(self.handle))
+            info = ShadowInfo()
+            _check(self._lib.cpvs_shadow_info_get(self.handle, ctypes.byref(info)))
+            self._info = info
+            self._keep = None
+        return self
+
+    @property
+    def info(self):
+        return self.wait()._info
 
     def getNumLevels(self):
         return int(self.info.num_levels)

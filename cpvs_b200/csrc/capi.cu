@@ -2,27 +2,20 @@
 // device pipeline  depth -> pyramid -> SVO levels -> bottom-up merge -> compressed DAG -> lookups.
 //
 // No CPU fallback lives here: every entry point either drives the CUDA kernels or returns an error.
-#include "../../include/cpvs_b200.h"
-
-#include <chrono>
-#include <cstdarg>
-#include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
 #include <new>
-#include <string>
-#include <vector>
 
 #include "../synth/scene.h"
-#include "kernels.h"
+#include "handles.h"
 
 using namespace cpvs;
 
 namespace {
-
 thread_local std::string gLastError;
+}  // namespace
 
+namespace cpvs {
 int fail(int code, const char* fmt, ...) {
 	char buf[512];
 	va_list ap;
@@ -32,125 +25,7 @@ int fail(int code, const char* fmt, ...) {
 	gLastError = buf;
 	return code;
 }
-
-#define CPVS_CUDA(expr)                                                                                      \
-	do {                                                                                                     \
-		cudaError_t _e = (expr);                                                                             \
-		if (_e != cudaSuccess)                                                                               \
-			return fail(_e == cudaErrorMemoryAllocation ? CPVS_ENOMEM : CPVS_ECUDA, "%s: %s (%s:%d)", #expr, \
-					cudaGetErrorString(_e), __FILE__, __LINE__);                                             \
-	} while (0)
-
-inline bool isPow2(u64 v) { return v && !(v & (v - 1)); }
-inline u64 pow2AtLeast(u64 v) {
-	u64 p = 1;
-	while (p < v) p <<= 1;
-	return p;
-}
-
-__global__ void storeU64Kernel(u64* dst, u64 value) { *dst = value; }
-__global__ void storeU32Kernel(u32* dst, u32 value) { *dst = value; }
-
-// CPVS_TRACE=1: host wall-clock between orchestration steps, to stderr.
-struct HostTrace {
-	bool on;
-	std::chrono::steady_clock::time_point last;
-	HostTrace() : on(std::getenv("CPVS_TRACE") != nullptr), last(std::chrono::steady_clock::now()) {}
-	void mark(const char* what) {
-		if (!on) return;
-		const auto now = std::chrono::steady_clock::now();
-		fprintf(stderr, "[cpvs trace] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
-		last = now;
-	}
-};
-
-}  // namespace
-
-struct cpvs_ctx {
-	int device;
-	cudaStream_t own;
-	cudaStream_t stream;
-	u64 launches;
-	// Scratch arena for cpvs_shadow_create: one device allocation, grown when a build needs more and
-	// kept between calls, carved by bump pointer -- no allocator traffic in steady state. Builds on one
-	// context are serialised by `buildLock` (use one context per host thread for concurrent builds).
-	std::mutex buildLock;
-	char* arena;
-	size_t arenaBytes;
-	u64* scalars;  // 192 device words: per-level counters of the build in flight
-	u64* hostScalars;  // pinned mirror for the two read-backs of a build (pageable copies are staged)
-	// High-priority side stream for a short chain of small kernels that is independent of a bulk kernel
-	// on the main stream (the inner levels' emission next to the leaf level's): its CTAs are scheduled
-	// ahead of the bulk kernel's queued ones. Fork/join through the two events.
-	cudaStream_t aux;
-	cudaEvent_t evFork, evJoin, evAuxStart;
-	// Normal-priority side stream for the per-level rank scans, which only the final emission needs and
-	// which therefore run next to the following levels' inserts.
-	cudaStream_t aux2, aux3;  // the ranks of different levels are independent: alternate between the two
-	cudaEvent_t evRankStart, evRankStop, evJoin3, evClear, evCols;
-	int leafColumns;  // leaves built per column: 1 = where it pays (default), 0 = never, 2 = always (CPVS_LEAF_COLUMNS; tests)
-	unsigned experiments;  // kExperiment* bits (CPVS_EXPERIMENTS): unmeasured kernel variants, off by default
-	// "early-bases" (experimental): the bottom level's rank runs on a stream of its own, and the level bases, the size
-	// read-back and the DAG allocation only wait for its first two kernels (the sizes), not for the third (the writes).
-	cudaStream_t aux4;
-	cudaEvent_t evBottomSized, evBottomRanked;
-	// "leaf-fp64" (experimental): the leaf groups found by fingerprint are verified on this stream, beside the inner inserts;
-	// forceExact is set while a build whose verification failed is redone with the exact insert.
-	cudaStream_t aux5;
-	cudaEvent_t evVerified;
-	bool forceExact;
-};
-
-struct cpvs_minmax {
-	cpvs_ctx* ctx;
-	int n;
-	int numLevels;
-	float* ownedDepth;   // device copy when built from host memory
-	float* levelStorage; // levels 1.. in one allocation
-	const float* level[kMaxLevels];
-	cudaEvent_t evStart, evBase, evStop;
-	// Levels 1 and 2 are not needed by the leafmask builder and are only produced on first use.
-	std::mutex lowLock;
-	bool lowLevelsBuilt;
-	// Roots of all z-slices of the column for the zTileNum last asked for (createShadowTiles builds them all
-	// from this one pyramid): slices that miss the surface are answered from here without a device round trip.
-	u32 columnSlices;
-	std::vector<u64> columnRoots;  // [z] = hasNodes << 32 | root mask
-};
-
-struct cpvs_shadow {
-	cpvs_ctx* ctx;
-	u32* dag;
-	cpvs_shadow_info info;
-	// lookup shortcut over the top levels, built on the first lookup (see LookupDag::skip)
-	std::mutex skipLock;
-	u32* skip;
-	u32 skipLevels;
-};
-
-struct ContainerCell {
-	u32* words = nullptr;  // device copy owned by the container
-	u64 count = 0;
-	u32 numLevels = 0;
-	int leafmasks = 0;
-	u32 rootMask = 0;
-	bool set = false;
-};
-
-struct cpvs_container {
-	cpvs_ctx* ctx;
-	u32 length;
-	u32 filterSize;
-	std::vector<ContainerCell> cells;
-	u32* dag = nullptr;
-	u32* grid = nullptr;
-	u32* skip = nullptr;  // lookup shortcut over the top levels of every cell (see LookupDag::skip)
-	u32 skipLevels = 0;
-	u64 dagWords = 0;
-	u32 dagLevels = 0, gridLevels = 0;
-	int leafmasks = 0;
-	bool finalized = false;
-};
+}  // namespace cpvs
 
 namespace {
 
@@ -170,37 +45,6 @@ struct Scratch {
 		*out = static_cast<T*>(p);
 		return e;
 	}
-};
-
-// Bump-pointer carving of the context arena; run once with base == nullptr to size it.
-struct ArenaCarver {
-	char* base;
-	size_t offset = 0;
-	explicit ArenaCarver(char* b) : base(b) {}
-	template <typename T>
-	T* take(u64 count) {
-		offset = (offset + 255) & ~size_t(255);
-		T* p = base ? reinterpret_cast<T*>(base + offset) : nullptr;
-		offset += (count ? count : 1) * sizeof(T);
-		return p;
-	}
-};
-
-struct LevelArrays {
-	u64 n = 0;
-	u64* coords = nullptr;
-	u16* masks = nullptr;
-	u32* firstChild = nullptr;
-	u32* uid = nullptr;
-	u32* firstList = nullptr;
-	u32* wordOffset = nullptr;
-	u32* leafCodes = nullptr;
-	u64* leafHash = nullptr;
-	u32* leafAt = nullptr;  // leaf level, built per column: node index by column-order position
-	u64* table = nullptr;      // merge table of this level (large levels own one; small levels share)
-	u64 tableSlots = 0;
-	u32* slotOffset = nullptr; // per table slot: word offset of the group's node
-	unsigned char* sizeOf = nullptr;  // rank scratch, one byte per node (large levels)
 };
 
 }  // namespace
@@ -231,51 +75,38 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 	ctx->arena = nullptr;
 	ctx->arenaBytes = 0;
 	ctx->scalars = nullptr;
-	ctx->own = nullptr;
-	cudaError_t e = cudaStreamCreateWithFlags(&ctx->own, cudaStreamNonBlocking);
-	if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->scalars), 192 * sizeof(u64));
-	ctx->hostScalars = nullptr;
-	if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&ctx->hostScalars), 192 * sizeof(u64));
-	ctx->aux = nullptr;
-	ctx->evFork = ctx->evJoin = ctx->evAuxStart = nullptr;
-	int prioLeast = 0, prioGreatest = 0;
-	if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prioLeast, &prioGreatest);
-	if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, prioGreatest);
-	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming);
-	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming);
-	if (e == cudaSuccess) e = cudaEventCreate(&ctx->evAuxStart);
-	ctx->aux2 = ctx->aux3 = nullptr;
-	ctx->evRankStart = ctx->evRankStop = ctx->evJoin3 = ctx->evClear = ctx->evCols = nullptr;
+	ctx->own = ctx->aux = ctx->aux2 = ctx->aux3 = ctx->aux4 = nullptr;
+	ctx->predictedBuilds = ctx->exactBuilds = ctx->overflowRebuilds = ctx->reemissions = 0;
+	cudaEvent_t* plain[] = {&ctx->evFork, &ctx->evJoin, &ctx->evJoin3, &ctx->evClear, &ctx->evCols, &ctx->evLeafRanked, &ctx->evLeafEmitted};
+	for (cudaEvent_t* e : plain) *e = nullptr;
+	ctx->buildSerial = 0;
 	{
 		const char* v = std::getenv("CPVS_LEAF_COLUMNS");
 		ctx->leafColumns = (v && v[0] >= '0' && v[0] <= '2') ? v[0] - '0' : 1;
-		const char* x = std::getenv("CPVS_EXPERIMENTS");
-		ctx->experiments = 0;
-		if (x) {
-			if (std::strstr(x, "expand-preload")) ctx->experiments |= kExperimentExpandPreload;
-			if (std::strstr(x, "emit-gather")) ctx->experiments |= kExperimentEmitGather;
-			if (std::strstr(x, "rank-preload")) ctx->experiments |= kExperimentRankPreload;
-			if (std::strstr(x, "insert-witness")) ctx->experiments |= kExperimentInsertWitness;
-			if (std::strstr(x, "early-bases")) ctx->experiments |= kExperimentEarlyBases;
-			if (std::strstr(x, "leaf-fp64")) ctx->experiments |= kExperimentLeafFp64;
-			if (std::strstr(x, "leaf-fp64-weak")) ctx->experiments |= kExperimentLeafFpWeak;
+		const char* p = std::getenv("CPVS_PREDICT");
+		ctx->predictSizes = (p && p[0] == '0') ? 0 : 1;
+		const char* h = std::getenv("CPVS_HEADROOM_SHIFT");  // capacity = predicted + (predicted >> shift); tests use 30 to provoke overflows
+		ctx->headroomShift = (h && h[0] >= '0' && h[0] <= '9') ? (unsigned)std::atoi(h) : 3u;
+		if (ctx->headroomShift > 40) ctx->headroomShift = 40;
+	}
+	cudaError_t e = cudaStreamCreateWithFlags(&ctx->own, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->scalars), kNumScalars * sizeof(u64));
+	for (int i = 0; i < 4 && e == cudaSuccess; ++i) {
+		u64* slot = nullptr;
+		e = cudaMallocHost(reinterpret_cast<void**>(&slot), kNumScalars * sizeof(u64));
+		if (e == cudaSuccess) {
+			ctx->readbackAll.push_back(slot);
+			ctx->readbackFree.push_back(slot);
 		}
 	}
+	int prioLeast = 0, prioGreatest = 0;
+	if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prioLeast, &prioGreatest);
+	if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, prioGreatest);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux2, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux3, cudaStreamNonBlocking);
-	ctx->aux4 = ctx->aux5 = nullptr;
-	ctx->evBottomSized = ctx->evBottomRanked = ctx->evVerified = nullptr;
-	ctx->forceExact = false;
-	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux5, cudaStreamNonBlocking);
-	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evVerified, cudaEventDisableTiming);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux4, cudaStreamNonBlocking);
-	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evBottomSized, cudaEventDisableTiming);
-	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evBottomRanked, cudaEventDisableTiming);
-	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evJoin3, cudaEventDisableTiming);
-	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evClear, cudaEventDisableTiming);
-	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->evCols, cudaEventDisableTiming);
-	if (e == cudaSuccess) e = cudaEventCreate(&ctx->evRankStart);
-	if (e == cudaSuccess) e = cudaEventCreate(&ctx->evRankStop);
+	for (cudaEvent_t* ev : plain)
+		if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
 	ctx->stream = ctx->own;
 	if (e != cudaSuccess) {
 		cpvs_ctx_destroy(ctx);  // releases whatever was created before the failure
@@ -292,24 +123,11 @@ int cpvs_ctx_destroy(cpvs_ctx* ctx) {
 	if (ctx->arena) cudaFreeAsync(ctx->arena, ctx->stream);
 	cudaStreamSynchronize(ctx->stream);
 	if (ctx->scalars) cudaFree(ctx->scalars);
-	if (ctx->hostScalars) cudaFreeHost(ctx->hostScalars);
-	if (ctx->aux) cudaStreamDestroy(ctx->aux);
-	if (ctx->evFork) cudaEventDestroy(ctx->evFork);
-	if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
-	if (ctx->evAuxStart) cudaEventDestroy(ctx->evAuxStart);
-	if (ctx->aux2) cudaStreamDestroy(ctx->aux2);
-	if (ctx->aux3) cudaStreamDestroy(ctx->aux3);
-	if (ctx->aux4) cudaStreamDestroy(ctx->aux4);
-	if (ctx->aux5) cudaStreamDestroy(ctx->aux5);
-	if (ctx->evVerified) cudaEventDestroy(ctx->evVerified);
-	if (ctx->evBottomSized) cudaEventDestroy(ctx->evBottomSized);
-	if (ctx->evBottomRanked) cudaEventDestroy(ctx->evBottomRanked);
-	if (ctx->evJoin3) cudaEventDestroy(ctx->evJoin3);
-	if (ctx->evClear) cudaEventDestroy(ctx->evClear);
-	if (ctx->evCols) cudaEventDestroy(ctx->evCols);
-	if (ctx->evRankStart) cudaEventDestroy(ctx->evRankStart);
-	if (ctx->evRankStop) cudaEventDestroy(ctx->evRankStop);
-	if (ctx->own) cudaStreamDestroy(ctx->own);
+	for (u64* slot : ctx->readbackAll) cudaFreeHost(slot);
+	for (cudaStream_t st : {ctx->aux, ctx->aux2, ctx->aux3, ctx->aux4, ctx->own})
+		if (st) cudaStreamDestroy(st);
+	for (cudaEvent_t ev : {ctx->evFork, ctx->evJoin, ctx->evJoin3, ctx->evClear, ctx->evCols, ctx->evLeafRanked, ctx->evLeafEmitted})
+		if (ev) cudaEventDestroy(ev);
 	delete ctx;
 	return CPVS_OK;
 }
@@ -342,6 +160,23 @@ int cpvs_ctx_reserve(cpvs_ctx* ctx, uint64_t bytes) {
 }
 
 uint64_t cpvs_ctx_launch_count(const cpvs_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int cpvs_ctx_set_prediction(cpvs_ctx* ctx, int enabled, uint32_t headroomShift) {
+	if (!ctx) return fail(CPVS_EINVAL, "cpvs_ctx_set_prediction: NULL context");
+	std::lock_guard<std::mutex> guard(ctx->buildLock);
+	ctx->predictSizes = enabled ? 1 : 0;
+	ctx->headroomShift = headroomShift > 40 ? 40 : headroomShift;
+	return CPVS_OK;
+}
+
+int cpvs_ctx_get_stats(const cpvs_ctx* ctx, cpvs_ctx_stats* out) {
+	if (!ctx || !out) return fail(CPVS_EINVAL, "cpvs_ctx_get_stats: NULL argument");
+	out->predicted_builds = ctx->predictedBuilds;
+	out->exact_builds = ctx->exactBuilds;
+	out->overflow_rebuilds = ctx->overflowRebuilds;
+	out->reemissions = ctx->reemissions;
+	return CPVS_OK;
+}
 
 /* ---- MinMaxHierarchy ------------------------------------------------------------------------ */
 
@@ -392,6 +227,7 @@ int cpvs_minmax_build(cpvs_ctx* ctx, const float* depth, int n, int mem, cpvs_mi
 	cudaEventCreate(&mm->evStop);
 	cudaEventRecord(mm->evStart, ctx->stream);
 	mm->columnSlices = 0;
+	mm->columnMinLevel = -1;
 	mm->lowLevelsBuilt = n < 128;  // small maps take the generic path, which writes every level
 	ctx->launches += launchPyramid(mm->level[0], n, lv, levels, false, mm->evBase, ctx->stream);
 	cudaEventRecord(mm->evStop, ctx->stream);
@@ -420,7 +256,7 @@ int cpvs_minmax_destroy(cpvs_minmax* mm) {
 
 }  // extern "C"
 
-namespace {
+namespace cpvs {
 // Levels 1 and 2 on demand (accessors, cs::createChildmask, leafmask-less builds).
 int ensureLowLevels(const cpvs_minmax* cmm, int level) {
 	cpvs_minmax* mm = const_cast<cpvs_minmax*>(cmm);
@@ -436,26 +272,7 @@ int ensureLowLevels(const cpvs_minmax* cmm, int level) {
 	mm->lowLevelsBuilt = true;
 	return CPVS_OK;
 }
-
-// hasNodes << 32 | root mask of slice zTileIndex, computing the whole column on first use (one launch, one read-back).
-int columnRoot(cpvs_ctx* ctx, const cpvs_minmax* cmm, const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, u64* root) {
-	cpvs_minmax* mm = const_cast<cpvs_minmax*>(cmm);
-	std::lock_guard<std::mutex> guard(mm->lowLock);
-	if (mm->columnSlices != zTileNum) {
-		u64* dRoots = nullptr;
-		CPVS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dRoots), zTileNum * sizeof(u64), ctx->stream));
-		ctx->launches += launchColumnRoots(pyr, zTileNum, dRoots, ctx->stream);
-		mm->columnRoots.assign(zTileNum, 0);
-		cudaError_t e = cudaMemcpyAsync(mm->columnRoots.data(), dRoots, zTileNum * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream);
-		if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-		cudaFreeAsync(dRoots, ctx->stream);
-		if (e != cudaSuccess) return fail(CPVS_ECUDA, "column roots: %s", cudaGetErrorString(e));
-		mm->columnSlices = zTileNum;
-	}
-	*root = mm->columnRoots[zTileIndex];
-	return CPVS_OK;
-}
-}  // namespace
+}  // namespace cpvs
 
 extern "C" {
 
@@ -498,603 +315,42 @@ int cpvs_minmax_childmask(const cpvs_minmax* mm, uint32_t level, uint32_t x, uin
 	CPVS_CUDA(cudaSetDevice(ctx->device));
 	if (int rc = ensureLowLevels(mm, (int)level)) return rc;
 	std::lock_guard<std::mutex> guard(ctx->buildLock);
-	PyramidView pyr;
-	pyr.n = mm->n;
-	pyr.numLevels = mm->numLevels;
-	for (int k = 0; k < kMaxLevels; ++k) pyr.level[k] = k < mm->numLevels ? mm->level[k] : nullptr;
-	u32* dOut = reinterpret_cast<u32*>(ctx->scalars + 191);
+	const PyramidView pyr = pyramidView(mm);
+	u32* dOut = reinterpret_cast<u32*>(ctx->scalars + kNumScalars - 1);
 	ctx->launches += launchChildmask(pyr, (int)level, zTileNum, x, y, z, dOut, ctx->stream);
 	CPVS_CUDA(cudaMemcpyAsync(out, dOut, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
 	CPVS_CUDA(cudaStreamSynchronize(ctx->stream));
 	return CPVS_OK;
 }
 
-/* ---- CompressedShadow::create ------------------------------------------------------------------ */
+/* ---- CompressedShadow (cpvs_shadow_create lives in build.cu) ------------------------------------- */
 
-int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex, uint32_t zTileNum, int leafmasks, cpvs_shadow** out) {
-	if (!ctx || !mm || !out) return fail(CPVS_EINVAL, "cpvs_shadow_create: NULL argument");
-	*out = nullptr;
-	if (mm->ctx->device != ctx->device) return fail(CPVS_EINVAL, "cpvs_shadow_create: hierarchy lives on device %d, context on %d", mm->ctx->device, ctx->device);
-	const int L = mm->numLevels;
-	if (L <= 3) return fail(CPVS_EINVAL, "cpvs_shadow_create: needs more than 3 levels (side >= 8), got %d", L);  // src/CompressedShadow.cpp:46
-	if (zTileNum == 0 || zTileIndex >= zTileNum) return fail(CPVS_EINVAL, "cpvs_shadow_create: z tile %u of %u", zTileIndex, zTileNum);
-	if ((u64)mm->n * zTileNum > (1ull << 23))
-		return fail(CPVS_EINVAL, "cpvs_shadow_create: side * zTileNum = %llu exceeds 2^23 (depth slices must stay exact in fp32)",
-				(unsigned long long)((u64)mm->n * zTileNum));
-	CPVS_CUDA(cudaSetDevice(ctx->device));
-	cudaStream_t st = ctx->stream;
-	// a hierarchy built by another context (createShadowTiles: one pyramid, one builder per z-slice) may
-	// still be in flight on that context's stream
-	if (mm->ctx != ctx && mm->evStop) CPVS_CUDA(cudaStreamWaitEvent(st, mm->evStop, 0));
-
-	const int top = L - 2;
-	const bool useLeaf = leafmasks && (L - 3) >= 2;  // src/CompressedShadow.cpp:20-27
-	const int minLevel = useLeaf ? 2 : 0;            // src/CompressedShadow.cpp:30-32
-	const int lastInner = useLeaf ? 3 : 0;
-	if (!useLeaf)
-		if (int rc = ensureLowLevels(mm, 1)) return rc;  // the leafmask-less octree descends through levels 2 and 1
-
-	// One slice of a column (createShadowTiles, reference src/DeferredRenderer.cpp:150-163): most slices of a tall
-	// grid miss the surface; their DAG is the root's mask word, known for the whole column after one launch.
-	if (zTileNum > 1 && top - 1 >= minLevel) {
-		PyramidView pyrTop;
-		pyrTop.n = mm->n;
-		pyrTop.numLevels = L;
-		for (int k = 0; k < kMaxLevels; ++k) pyrTop.level[k] = k < L ? mm->level[k] : nullptr;
-		u64 root = 0;
-		if (int rc = columnRoot(ctx, mm, pyrTop, zTileIndex, zTileNum, &root)) return rc;
-		if (!(root >> 32)) {
-			cpvs_shadow* s = new (std::nothrow) cpvs_shadow();
-			if (!s) return fail(CPVS_ENOMEM, "cpvs_shadow_create: host allocation");
-			std::memset(&s->info, 0, sizeof(s->info));
-			s->skip = nullptr;
-			s->skipLevels = 0;
-			s->ctx = ctx;
-			s->dag = nullptr;
-			const u32 rootMask = (u32)root;
-			cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&s->dag), sizeof(u32), st);
-			if (e != cudaSuccess) {
-				delete s;
-				return fail(e == cudaErrorMemoryAllocation ? CPVS_ENOMEM : CPVS_ECUDA, "cpvs_shadow_create: %s", cudaGetErrorString(e));
-			}
-			storeU32Kernel<<<1, 1, 0, st>>>(s->dag, rootMask);
-			++ctx->launches;
-			s->info.num_levels = (u32)L;
-			s->info.leafmasks = useLeaf ? 1 : 0;
-			s->info.total_visibility = rootMask == 0x5555u ? CPVS_VISIBLE : (rootMask == 0u ? CPVS_SHADOW : CPVS_PARTIAL);
-			s->info.words = 1;
-			s->info.svo_nodes[top] = s->info.dag_nodes[top] = s->info.dag_words[top] = 1;
-			*out = s;
-			return CPVS_OK;
-		}
-	}
-
-	// ev[i] opens phase i (CPVS_PHASE_*), ev[CPVS_NUM_PHASES] closes the last one
-	struct PhaseEvents {
-		cudaEvent_t ev[CPVS_NUM_PHASES + 1];
-		PhaseEvents() { std::memset(ev, 0, sizeof(ev)); }
-		~PhaseEvents() {
-			for (cudaEvent_t e : ev)
-				if (e) cudaEventDestroy(e);
-		}
-	} phases;
-	for (cudaEvent_t& e : phases.ev) CPVS_CUDA(cudaEventCreate(&e));
-	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_COUNT], st));
-
-	std::unique_lock<std::mutex> buildGuard(ctx->buildLock);
-	PyramidView pyr;
-	pyr.n = mm->n;
-	pyr.numLevels = L;
-	for (int k = 0; k < kMaxLevels; ++k) pyr.level[k] = k < L ? mm->level[k] : nullptr;
-
-	// device scalars: [0..31] SVO counts, [32..63] unique, [64..95] words, [96..127] bases, [128..159] child totals, [160] total words
-	u64* dScalars = ctx->scalars;
-	CPVS_CUDA(cudaMemsetAsync(dScalars, 0, 192 * sizeof(u64), st));
-	u64 *dCounts = dScalars, *dUnique = dScalars + 32, *dWords = dScalars + 64, *dBases = dScalars + 96, *dChildTotal = dScalars + 128,
-		*dTotal = dScalars + 160;
-
-	HostTrace trace;
-	trace.mark("setup");
-	// 1. exact node counts of every level (closed form), so all buffers can be sized up front
-	ctx->launches += launchCountNodes(pyr, zTileIndex, zTileNum, minLevel, dCounts, st);
-	u64* hScalars = ctx->hostScalars;
-	CPVS_CUDA(cudaMemcpyAsync(hScalars, dCounts, 32 * sizeof(u64), cudaMemcpyDeviceToHost, st));
-	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_NUM_PHASES], st));  // end of a slice that stops here; re-recorded at the end otherwise
-	CPVS_CUDA(cudaStreamSynchronize(st));
-	trace.mark("count kernels + sync");
-	LevelArrays lv[kMaxLevels];
-	lv[top].n = 1;
-	for (int l = top - 1; l >= minLevel; --l) lv[l].n = lv[l + 1].n ? hScalars[l] : 0;
-	for (int l = minLevel; l <= top; ++l)
-		if (lv[l].n >= (1ull << 30)) return fail(CPVS_EOVERFLOW, "level %d has %llu nodes (limit 2^30)", l, (unsigned long long)lv[l].n);
-
-	// A z-slice that misses the surface altogether (most slices of a tall tile grid): the root has no PARTIAL
-	// child, the DAG is its one mask word (0x5555 lit / 0x0000 shadow). One tiny kernel instead of the pipeline.
-	if (top - 1 >= minLevel && lv[top - 1].n == 0) {
-		cpvs_shadow* s = new (std::nothrow) cpvs_shadow();
-		if (!s) return fail(CPVS_ENOMEM, "cpvs_shadow_create: host allocation");
-		std::memset(&s->info, 0, sizeof(s->info));
-		s->skip = nullptr;
-		s->skipLevels = 0;
-		s->ctx = ctx;
-		s->dag = nullptr;
-		// The count launch already reported the root's mask (kRootMaskScalar) and its read-back is complete: store
-		// the word and return without another round trip. build_ms ends at the read-back.
-		cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&s->dag), sizeof(u32), st);
-		u32 rootMask = 0;
-		u32* hMask = &rootMask;
-		float ms = 0.f;
-		if (e == cudaSuccess && (hScalars[kRootMaskScalar] >> 32) == 1ull) {
-			rootMask = (u32)hScalars[kRootMaskScalar];
-			storeU32Kernel<<<1, 1, 0, st>>>(s->dag, rootMask);
-			++ctx->launches;
-			e = cudaEventElapsedTime(&ms, phases.ev[CPVS_PHASE_COUNT], phases.ev[CPVS_NUM_PHASES]);
-		} else if (e == cudaSuccess) {  // no level was counted (tiny maps): ask for the mask
-			ctx->launches += launchChildmask(pyr, top, zTileNum, 0, 0, zTileIndex * 2, s->dag, st);
-			e = cudaMemcpyAsync(hScalars + 190, s->dag, sizeof(u32), cudaMemcpyDeviceToHost, st);
-			if (e == cudaSuccess) e = cudaEventRecord(phases.ev[CPVS_NUM_PHASES], st);
-			if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-			rootMask = *reinterpret_cast<u32*>(hScalars + 190);
-			if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, phases.ev[CPVS_PHASE_COUNT], phases.ev[CPVS_NUM_PHASES]);
-		}
-		if (e != cudaSuccess) {
-			if (s->dag) cudaFreeAsync(s->dag, st);
-			delete s;
-			return fail(CPVS_ECUDA, "cpvs_shadow_create: %s", cudaGetErrorString(e));
-		}
-		s->info.num_levels = (u32)L;
-		s->info.leafmasks = useLeaf ? 1 : 0;
-		s->info.total_visibility = *hMask == 0x5555u ? CPVS_VISIBLE : (*hMask == 0u ? CPVS_SHADOW : CPVS_PARTIAL);
-		s->info.words = 1;
-		s->info.svo_nodes[top] = s->info.dag_nodes[top] = s->info.dag_words[top] = 1;
-		s->info.build_ms = ms;
-		s->info.phase_ms[CPVS_PHASE_COUNT] = ms;
-		*out = s;
-		return CPVS_OK;
-	}
-
-	// The top levels up to kSmallMaxNodes nodes each ("small": smallLow..top) are handled by single-CTA
-	// kernels, one launch per phase instead of one or more per level.
-	int smallLow = top + 1;
-	for (int l = top; l >= lastInner && lv[l].n && lv[l].n <= kSmallMaxNodes; --l) smallLow = l;
-
-	// 2. per-level arrays, carved out of the context arena
-	u64 scanTiles = 0, scanLaunches = 0;
-	const u64 maxTable = 2 * kSmallMaxNodes;  // shared by the small levels; large levels own their tables
-	for (int l = top; l >= minLevel; --l) {
-		const u64 n = lv[l].n;
-		if (!n || l >= smallLow) continue;
-		if (!(useLeaf && l == 2)) {
-			scanTiles += (n + kExpandTileNodes - 1) / kExpandTileNodes;
-			++scanLaunches;
-		}
-		if (n > 1) {
-			scanTiles += (n + kScanTile - 1) / kScanTile;
-			++scanLaunches;
-		}
-	}
-	ScanTileState* dTiles = nullptr;
-	u32* dTickets = nullptr;
-	u64* dTable = nullptr;
-	u32* dSketch = nullptr;
-	const bool needSketch = useLeaf && lv[2].n > 0, haveLeaves = useLeaf && lv[2].n > 1;
-	// leaves per column: one more scan (over the columns = texels of pyramid level 3)
-	// Where it pays: whole-volume builds with 2..8 leaves per column of a depth map that does not fit in L2 (terrain-like
-	// surfaces; measured at 16K^2: 0.42 ms against 0.50 ms per leaf, at 8192^2 0.121 against 0.137, at 4096^2 -- 64 MiB, L2
-	// serves the re-reads -- 0.046 against 0.045). A z-slice of a tall grid leaves most columns empty; box edges make columns
-	// of hundreds of leaves that a four-lane group walks alone (16K^2 city: 6.1 ms against 2.9 ms); a gentle plane has one
-	// leaf per column and nothing to share (0.30 ms against 0.27 ms): those keep the per-leaf kernel.
-	const u64 allCols = ((u64)mm->n >> 3) * ((u64)mm->n >> 3);
-	const bool leafColumns = needSketch && (ctx->leafColumns == 2 || (ctx->leafColumns == 1 && zTileNum == 1 && mm->n >= 8192 &&
-																   lv[2].n >= 2 * allCols && lv[2].n <= 8 * allCols));
-	const u64 numCols = leafColumns ? ((u64)mm->n >> 3) * ((u64)mm->n >> 3) : 0;
-	u32* dColBias = nullptr;
-	if (leafColumns) {
-		scanTiles += (numCols + kScanTile - 1) / kScanTile;
-		++scanLaunches;
-	}
-	auto carve = [&](ArenaCarver& ar) {
-		dTiles = ar.take<ScanTileState>(scanTiles);
-		dTickets = ar.take<u32>(scanLaunches);
-		dSketch = ar.take<u32>(needSketch ? kSketchWords : 0);
-		dTable = ar.take<u64>(maxTable);
-		dColBias = ar.take<u32>(numCols);
-		for (int l = top; l >= minLevel; --l) {
-			LevelArrays& a = lv[l];
-			if (!a.n) continue;
-			if (leafColumns && l == 2)
-				a.leafAt = ar.take<u32>(a.n);
-			else
-				a.coords = ar.take<u64>(a.n);
-			a.masks = ar.take<u16>(a.n);
-			a.uid = ar.take<u32>(a.n);
-			a.firstList = ar.take<u32>(a.n);
-			a.wordOffset = ar.take<u32>(a.n);
-			if (l >= smallLow) {
-				a.table = dTable;
-				a.tableSlots = 2 * kSmallMaxNodes;
-			} else {
-				a.tableSlots = pow2AtLeast(a.n * 2 < 1024 ? 1024 : a.n * 2);
-				a.table = ar.take<u64>(a.tableSlots + kDirectSlots);
-			}
-			a.slotOffset = ar.take<u32>(a.tableSlots + kDirectSlots);
-			if (l < smallLow) a.sizeOf = ar.take<unsigned char>(a.n + 4);
-			if (useLeaf && l == 2) {
-				a.leafCodes = ar.take<u32>(a.n * 8);
-				if (!leafColumns) a.leafHash = ar.take<u64>(a.n);
-			} else {
-				a.firstChild = ar.take<u32>(a.n);
-			}
-		}
-	};
-	ArenaCarver sizing(nullptr);
-	carve(sizing);
-	if (sizing.offset > ctx->arenaBytes) {
-		// Grow geometrically (a tile grid feeds builds of slowly increasing size) and from the stream-ordered
-		// pool: a regrowth served from memory the pool already holds (cpvs_ctx_reserve, earlier frees) costs
-		// microseconds, where cudaFree + cudaMalloc synchronise the device and, with peer access enabled by a
-		// communication library, remap on every GPU (100+ ms). The previous build has completed on all streams.
-		const size_t doubled = ctx->arenaBytes * 2;
-		if (ctx->arena) CPVS_CUDA(cudaFreeAsync(ctx->arena, st));
-		ctx->arena = nullptr;
-		ctx->arenaBytes = 0;
-		size_t want = sizing.offset + sizing.offset / 4;
-		if (want < doubled) want = doubled;
-		size_t freeBytes = 0, totalBytes = 0;
-		if (cudaMemGetInfo(&freeBytes, &totalBytes) == cudaSuccess && want > freeBytes / 2) want = sizing.offset + sizing.offset / 8;
-		cudaError_t ae = cudaMallocAsync(reinterpret_cast<void**>(&ctx->arena), want, st);
-		if (ae != cudaSuccess) return fail(CPVS_ENOMEM, "scratch arena of %zu bytes: %s", want, cudaGetErrorString(ae));
-		ctx->arenaBytes = want;
-	}
-	ArenaCarver real(ctx->arena);
-	carve(real);
-	trace.mark("arena carve");
-	// tile states, tickets and the leaf sketch sit at the front of the arena: one memset clears them all
-	CPVS_CUDA(cudaMemsetAsync(ctx->arena, 0, reinterpret_cast<char*>(dTable) - ctx->arena, st));
-	// the large inner levels' tables are cleared up front (the leaf level sizes and clears its table on
-	// the device, once the sketch is filled; the small levels clear theirs inside their kernel)
-	// -- on a side stream, next to the expansion; the first inner insert waits for it.
-	if (leafColumns) {
-		CPVS_CUDA(cudaEventRecord(ctx->evFork, st));
-		CPVS_CUDA(cudaStreamWaitEvent(ctx->aux2, ctx->evFork, 0));
-		ScanLaunch colScan{dTickets + scanLaunches - 1, dTiles + scanTiles - (numCols + kScanTile - 1) / kScanTile};
-		ctx->launches += launchColumnBias(pyr, zTileIndex, zTileNum, dColBias, colScan, ctx->aux2);
-		CPVS_CUDA(cudaEventRecord(ctx->evCols, ctx->aux2));
-	}
-	bool tablesClearing = false;
-	for (int l = minLevel; l < smallLow; ++l)
-		if (lv[l].n > 1 && !(useLeaf && l == 2)) {
-			if (!tablesClearing) {
-				CPVS_CUDA(cudaEventRecord(ctx->evFork, st));  // the arena may still be in use by the previous build
-				CPVS_CUDA(cudaStreamWaitEvent(ctx->aux3, ctx->evFork, 0));
-				tablesClearing = true;
-			}
-			CPVS_CUDA(cudaMemsetAsync(lv[l].table, 0xFF, (lv[l].tableSlots + kDirectSlots) * sizeof(u64), ctx->aux3));
-		}
-	if (tablesClearing) CPVS_CUDA(cudaEventRecord(ctx->evClear, ctx->aux3));
-	u64 *dSketchBits = dScalars + 161, *dLeafTableMask = dScalars + 162;
-	u32* dErrorFlag = reinterpret_cast<u32*>(dScalars + 163);
-	u32* dMismatchFlag = reinterpret_cast<u32*>(dScalars + 164);  // leaf-fp64: a fingerprint group held two different leaves
-	const bool leafFingerprint = haveLeaves && (ctx->experiments & kExperimentLeafFp64) && !ctx->forceExact;
-	bool verifyPending = false;
-	u64 tileCursor = 0, launchCursor = 0;
-	auto nextScan = [&](u64 n, u64 tileNodes = kScanTile) {
-		ScanLaunch s{dTickets + launchCursor, dTiles + tileCursor};
-		++launchCursor;
-		tileCursor += (n + tileNodes - 1) / tileNodes;
-		return s;
-	};
-
-	trace.mark("memsets");
-	// 3. breadth-first construction, top level first (src/CompressedShadow.cpp:87-169)
-	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_EXPAND], st));
-	storeU64Kernel<<<1, 1, 0, st>>>(lv[top].coords, packCoord(0, 0, zTileIndex * 2));
-	++ctx->launches;
-	{
-		SmallExpandArgs sx;
-		sx.count = 0;
-		for (int l = top; l >= smallLow; --l) {
-			SmallExpandLevel& e = sx.lv[sx.count++];
-			e.side = (u32)mm->n >> l;
-			e.tex = pyr.level[l];
-			e.heightF = (float)(e.side * zTileNum);
-			e.level0 = l == 0 ? 1 : 0;
-			e.coords = lv[l].coords;
-			e.masks = lv[l].masks;
-			e.firstChild = lv[l].firstChild;
-			e.childCoords = (l > minLevel && lv[l - 1].n) ? lv[l - 1].coords : nullptr;
-			e.childTotal = dChildTotal + l;
-			e.colBias = nullptr;
-			e.leafAt = nullptr;
-			e.numLeaves = 0;
-			if (leafColumns && l == 3) {
-				e.numLeaves = (u32)lv[2].n;
-				e.colBias = dColBias;
-				e.leafAt = lv[2].leafAt;
-				CPVS_CUDA(cudaStreamWaitEvent(st, ctx->evCols, 0));
-			}
-		}
-		ctx->launches += launchExpandSmallLevels(sx, st);
-	}
-	for (int l = smallLow - 1; l >= lastInner && lv[l].n; --l) {
-		u64* childCoords = (l > minLevel && lv[l - 1].n) ? lv[l - 1].coords : nullptr;
-		const bool toColumns = leafColumns && l == 3;
-		if (toColumns) CPVS_CUDA(cudaStreamWaitEvent(st, ctx->evCols, 0));
-		ctx->launches += launchExpandLevel(pyr, l, zTileNum, lv[l].coords, lv[l].n, lv[l].masks, lv[l].firstChild, childCoords,
-				dChildTotal + l, nextScan(lv[l].n, kExpandTileNodes), toColumns ? dColBias : nullptr, toColumns ? lv[2].leafAt : nullptr, (u32)lv[2].n,
-				(ctx->experiments & kExperimentExpandPreload) ? 1 : 0, st);
-	}
-	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAVES], st));
-	if (leafColumns)  // constructLastLevels (src/CompressedShadow.cpp:171-190)
-		ctx->launches += launchBuildLeafColumns(pyr, zTileIndex, zTileNum, dColBias, lv[2].leafAt, (u32)lv[2].n, lv[2].leafCodes, lv[2].masks,
-				dSketch, st);
-	else if (useLeaf && lv[2].n)
-		ctx->launches += launchBuildLeaves(pyr, zTileNum, lv[2].coords, lv[2].n, lv[2].leafCodes, lv[2].leafHash, lv[2].masks,
-				dSketch, st);
-
-	// 4. bottom-up merge (src/CompressedShadow.cpp:215-241). The chain of inserts is the critical path and
-	// runs on the high-priority stream `ms`, so that its CTAs are dispatched ahead of the queued CTAs of
-	// the rank scans running beside it; the main stream rejoins before the bases.
-	cudaStream_t mergeStream = ctx->aux;
-	CPVS_CUDA(cudaEventRecord(ctx->evFork, st));
-	CPVS_CUDA(cudaStreamWaitEvent(mergeStream, ctx->evFork, 0));
-	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAF_TABLE], mergeStream));
-	if (haveLeaves) {
-		ctx->launches += launchSketchPopcount(dSketch, dSketchBits, mergeStream);
-		ctx->launches += launchSizeLeafTable(lv[2].table, lv[2].tableSlots, dSketchBits, dLeafTableMask, leafFingerprint ? 1 : 0, mergeStream);
-	}
-	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAF_INSERT], mergeStream));
-	if (!(useLeaf && lv[2].n)) {
-		CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAF_RESOLVE], mergeStream));
-		CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_INNER_MERGE], mergeStream));
-	}
-	// Per level: insert on the main stream (gives every node its group id, all the next level needs),
-	// rank on the side stream (orders the unique nodes; only the emission needs it).
-	bool ranksPending = false;
-	bool bottomRankSplit = false;  // early-bases: the bottom level's rank is on aux4, its write kernel not joined before the bases
-	for (int l = minLevel; l < smallLow; ++l) {
-		LevelArrays& a = lv[l];
-		if (!a.n) continue;
-		const bool leafLevel = useLeaf && l == 2;
-		MergeLevelArgs m;
-		m.n = a.n;
-		m.leaf = leafLevel ? 1 : 0;
-		m.leafCodes = a.leafCodes;
-		m.leafHash = a.leafHash;
-		m.masks = a.masks;
-		m.firstChild = a.firstChild;
-		m.childUid = l > minLevel ? lv[l - 1].uid : nullptr;
-		m.table = a.table;
-		m.tableSize = a.tableSlots;
-		m.sketchBits = dSketchBits;
-		m.tableMaskDev = dLeafTableMask;
-		m.errorFlag = dErrorFlag;
-		m.uid = a.uid;
-		m.firstList = a.firstList;
-		m.wordOffset = a.wordOffset;
-		m.slotOffset = a.slotOffset;
-		m.sizeOf = a.sizeOf;
-		m.uniqueCount = dUnique + l;
-		m.wordCount = dWords + l;
-		m.rankPreload = (ctx->experiments & kExperimentRankPreload) ? 1 : 0;
-		m.parallelWitness = (ctx->experiments & kExperimentInsertWitness) ? 1 : 0;
-		m.fingerprint = (leafLevel && leafFingerprint) ? ((ctx->experiments & kExperimentLeafFpWeak) ? 2 : 1) : 0;
-		if (!leafLevel && tablesClearing) {
-			CPVS_CUDA(cudaStreamWaitEvent(mergeStream, ctx->evClear, 0));
-			tablesClearing = false;
-		}
-		ctx->launches += launchInsertLevel(m, mergeStream);
-		if (leafLevel) {
-			CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_LEAF_RESOLVE], mergeStream));
-			CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_INNER_MERGE], mergeStream));
-			if (m.fingerprint) {  // the exact compare, off the critical path
-				CPVS_CUDA(cudaEventRecord(ctx->evFork, mergeStream));
-				CPVS_CUDA(cudaStreamWaitEvent(ctx->aux5, ctx->evFork, 0));
-				ctx->launches += launchVerifyLeafGroups(m, dMismatchFlag, ctx->aux5);
-				CPVS_CUDA(cudaEventRecord(ctx->evVerified, ctx->aux5));
-				verifyPending = true;
-			}
-		}
-		if (a.n > 1) {
-			const bool split = (ctx->experiments & kExperimentEarlyBases) && l == minLevel;
-			cudaStream_t rs = split ? ctx->aux4 : ((l & 1) ? ctx->aux3 : ctx->aux2);
-			CPVS_CUDA(cudaEventRecord(ctx->evFork, mergeStream));
-			CPVS_CUDA(cudaStreamWaitEvent(rs, ctx->evFork, 0));
-			if (leafLevel) CPVS_CUDA(cudaEventRecord(ctx->evRankStart, rs));
-			ctx->launches += launchRankLevel(m, nextScan(a.n), rs, split ? ctx->evBottomSized : nullptr);
-			if (leafLevel) CPVS_CUDA(cudaEventRecord(ctx->evRankStop, rs));
-			if (split) {
-				CPVS_CUDA(cudaEventRecord(ctx->evBottomRanked, rs));
-				bottomRankSplit = true;
-			}
-			ranksPending = true;
-		}
-	}
-	{
-		SmallMergeArgs sm;
-		sm.count = 0;
-		sm.table = dTable;
-		sm.errorFlag = dErrorFlag;
-		for (int l = smallLow; l <= top; ++l) {
-			if (!lv[l].n) continue;
-			SmallMergeLevel& m = sm.lv[sm.count++];
-			m.n = (u32)lv[l].n;
-			m.masks = lv[l].masks;
-			m.firstChild = lv[l].firstChild;
-			m.childUid = l > minLevel ? lv[l - 1].uid : nullptr;
-			m.uid = lv[l].uid;
-			m.firstList = lv[l].firstList;
-			m.wordOffset = lv[l].wordOffset;
-			m.slotOffset = lv[l].slotOffset;
-			m.uniqueCount = dUnique + l;
-			m.wordCount = dWords + l;
-		}
-		ctx->launches += launchMergeSmallLevels(sm, mergeStream);
-	}
-	if (ranksPending || tablesClearing) {  // join: the level sizes feed the bases
-		CPVS_CUDA(cudaEventRecord(ctx->evJoin, ctx->aux2));
-		CPVS_CUDA(cudaStreamWaitEvent(mergeStream, ctx->evJoin, 0));
-		CPVS_CUDA(cudaEventRecord(ctx->evJoin3, ctx->aux3));
-		CPVS_CUDA(cudaStreamWaitEvent(mergeStream, ctx->evJoin3, 0));
-		if (bottomRankSplit) CPVS_CUDA(cudaStreamWaitEvent(mergeStream, ctx->evBottomSized, 0));  // its sizes, not its writes
-	}
-	if (verifyPending) CPVS_CUDA(cudaStreamWaitEvent(mergeStream, ctx->evVerified, 0));  // its verdict is read back with the sizes
-	CPVS_CUDA(cudaEventRecord(ctx->evJoin, mergeStream));
-	CPVS_CUDA(cudaStreamWaitEvent(st, ctx->evJoin, 0));
-	CPVS_CUDA(cudaEventRecord(phases.ev[CPVS_PHASE_BASES], st));
-
-	// 5. level bases and the total size (src/CompressedShadow.cpp:326-392)
-	ctx->launches += launchLevelBases(dWords, dBases, top, minLevel, dTotal, st);
-	trace.mark("enqueue expand..bases");
-	CPVS_CUDA(cudaMemcpyAsync(hScalars, dScalars, 192 * sizeof(u64), cudaMemcpyDeviceToHost, st));
-	CPVS_CUDA(cudaStreamSynchronize(st));
-	trace.mark("sync after bases");
-	CPVS_CUDA(cudaGetLastError());
-	for (int l = top; l > minLevel; --l)
-		if (lv[l].n && l >= lastInner && hScalars[128 + l] != lv[l - 1].n)
-			return fail(CPVS_EINTERNAL, "level %d: expansion produced %llu nodes, count pass predicted %llu", l - 1,
-					(unsigned long long)hScalars[128 + l], (unsigned long long)lv[l - 1].n);
-	if (hScalars[163] != 0) return fail(CPVS_EINTERNAL, "merge table overflow (leaf table mask %llu)", (unsigned long long)hScalars[162]);
-	if (verifyPending && (u32)hScalars[164] != 0) {
-		// two different leaves shared a 64-bit fingerprint: nothing has been emitted yet -- once more, with the exact insert
-		if (bottomRankSplit) CPVS_CUDA(cudaStreamSynchronize(ctx->aux4));  // the rank's last kernel still uses the arena
-		ctx->forceExact = true;
-		buildGuard.unlock();
-		const int rc = cpvs_shadow_create(ctx, mm, zTileIndex, zTileNum, leafmasks, out);
-		ctx->forceExact = false;
-		return rc;
-	}
-	const u64 totalWords = hScalars[160];
-	if (totalWords > (1ull << 32)) return fail(CPVS_EOVERFLOW, "DAG needs %llu words; offsets are 32-bit", (unsigned long long)totalWords);
-
-	cpvs_shadow* s = new (std::nothrow) cpvs_shadow();
-	if (!s) return fail(CPVS_ENOMEM, "cpvs_shadow_create: host allocation");
-	std::memset(&s->info, 0, sizeof(s->info));
-	s->dag = nullptr;
-	s->skip = nullptr;
-	s->skipLevels = 0;
-	s->ctx = ctx;
-	cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&s->dag), totalWords * sizeof(u32), st);
-	if (e != cudaSuccess) {
-		delete s;
-		return fail(CPVS_ENOMEM, "DAG allocation of %llu words: %s", (unsigned long long)totalWords, cudaGetErrorString(e));
-	}
-
-	trace.mark("dag alloc");
-	// 6. write every unique node once, in its final place. The levels are independent of each other
-	// now; the leaf level (most of the words) stays on the main stream, the chain of inner levels runs on
-	// the high-priority side stream next to it.
-	// phase EMIT_INNER: fork .. join on the main stream; phase EMIT_LEAVES: the leaf kernel alone (they overlap).
-	if (bottomRankSplit) cudaStreamWaitEvent(st, ctx->evBottomRanked, 0);  // the emission reads what the rank's last kernel wrote
-	cudaEventRecord(phases.ev[CPVS_PHASE_EMIT_INNER], st);
-	const bool leafEmit = useLeaf && lv[2].n;
-	if (leafEmit) {
-		cudaEventRecord(ctx->evFork, st);
-		cudaStreamWaitEvent(ctx->aux, ctx->evFork, 0);
-	}
-	EmitMultiArgs inner;
-	inner.count = 0;
-	inner.gather = (ctx->experiments & kExperimentEmitGather) ? 1 : 0;
-	for (int l = minLevel; l <= top; ++l) {
-		const LevelArrays& a = lv[l];
-		if (!a.n) continue;
-		const bool isLeaf = useLeaf && l == 2;
-		EmitLevelArgs em;
-		em.n = hScalars[32 + l];  // unique nodes of the level (read back with the sizes): exact grid
-		em.leaf = isLeaf ? 1 : 0;
-		em.uniqueCount = dUnique + l;
-		em.wordCount = dWords + l;
-		em.firstList = a.firstList;
-		em.wordOffset = a.wordOffset;
-		em.levelBase = dBases + l;
-		em.leafCodes = a.leafCodes;
-		em.masks = a.masks;
-		em.firstChild = a.firstChild;
-		em.childUid = l > minLevel ? lv[l - 1].uid : nullptr;
-		em.childSlotOffset = l > minLevel ? lv[l - 1].slotOffset : nullptr;
-		em.childLevelBase = dBases + (l > minLevel ? l - 1 : l);
-		em.dag = s->dag;
-		if (isLeaf) {
-			cudaEventRecord(ctx->evAuxStart, st);
-			ctx->launches += launchEmitLevel(em, st);
-			cudaEventRecord(phases.ev[CPVS_PHASE_EMIT_LEAVES], st);  // closes the leaf kernel
-		} else if (inner.count < kMaxEmitLevels) {
-			inner.lv[inner.count++] = em;
-		}
-	}
-	ctx->launches += launchEmitInnerLevels(inner, leafEmit ? ctx->aux : st);
-	if (leafEmit) {
-		cudaEventRecord(ctx->evJoin, ctx->aux);
-		cudaStreamWaitEvent(st, ctx->evJoin, 0);
-	} else {
-		cudaEventRecord(phases.ev[CPVS_PHASE_EMIT_LEAVES], st);
-	}
-	u32 rootMask = 0;
-	e = cudaMemcpyAsync(&rootMask, s->dag, sizeof(u32), cudaMemcpyDeviceToHost, st);
-	if (e == cudaSuccess) e = cudaEventRecord(phases.ev[CPVS_NUM_PHASES], st);
-	if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-	if (e == cudaSuccess) e = cudaGetLastError();
-	trace.mark("emit + final sync");
-	float ms = 0.f, phaseMs[CPVS_NUM_PHASES] = {0};
-	if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, phases.ev[0], phases.ev[CPVS_NUM_PHASES]);
-	for (int i = 0; i < CPVS_PHASE_EMIT_INNER && e == cudaSuccess; ++i) e = cudaEventElapsedTime(&phaseMs[i], phases.ev[i], phases.ev[i + 1]);
-	if (e == cudaSuccess) e = cudaEventElapsedTime(&phaseMs[CPVS_PHASE_EMIT_INNER], phases.ev[CPVS_PHASE_EMIT_INNER], phases.ev[CPVS_NUM_PHASES]);
-	if (e == cudaSuccess && leafEmit) e = cudaEventElapsedTime(&phaseMs[CPVS_PHASE_EMIT_LEAVES], ctx->evAuxStart, phases.ev[CPVS_PHASE_EMIT_LEAVES]);
-	if (e == cudaSuccess && haveLeaves) e = cudaEventElapsedTime(&phaseMs[CPVS_PHASE_LEAF_RESOLVE], ctx->evRankStart, ctx->evRankStop);
-	if (e != cudaSuccess) {
-		cudaFreeAsync(s->dag, st);
-		delete s;
-		return fail(CPVS_ECUDA, "cpvs_shadow_create: %s", cudaGetErrorString(e));
-	}
-	s->info.num_levels = (u32)L;
-	s->info.leafmasks = useLeaf ? 1 : 0;
-	s->info.total_visibility = rootMask == 0x5555u ? CPVS_VISIBLE : (rootMask == 0u ? CPVS_SHADOW : CPVS_PARTIAL);
-	s->info.words = totalWords;
-	for (int l = minLevel; l <= top; ++l) {
-		s->info.svo_nodes[l] = lv[l].n;
-		s->info.dag_nodes[l] = hScalars[32 + l];
-		s->info.dag_words[l] = hScalars[64 + l];
-	}
-	s->info.build_ms = ms;
-	for (int i = 0; i < CPVS_NUM_PHASES; ++i) s->info.phase_ms[i] = phaseMs[i];
-	*out = s;
-	return CPVS_OK;
-}
-
-int cpvs_shadow_create_from_depth(cpvs_ctx* ctx, const float* depth, int n, int mem, uint32_t zTileIndex, uint32_t zTileNum, int leafmasks,
-		cpvs_shadow** out) {
-	cpvs_minmax* mm = nullptr;
-	int rc = cpvs_minmax_build(ctx, depth, n, mem, &mm);
-	if (rc != CPVS_OK) return rc;
-	rc = cpvs_shadow_create(ctx, mm, zTileIndex, zTileNum, leafmasks, out);
-	cpvs_minmax_destroy(mm);
-	return rc;
-}
-
-int cpvs_shadow_destroy(cpvs_shadow* s) {
-	if (!s) return CPVS_OK;
-	cudaSetDevice(s->ctx->device);
-	if (s->dag) cudaFreeAsync(s->dag, s->ctx->stream);
-	if (s->skip) cudaFreeAsync(s->skip, s->ctx->stream);
-	delete s;
-	return CPVS_OK;
-}
+// Accessors of a shadow created asynchronously wait for the build first.
+#define CPVS_READY(s)                                                        \
+	do {                                                                     \
+		if (int _rc = cpvs_shadow_wait(const_cast<cpvs_shadow*>(s))) return _rc; \
+	} while (0)
 
 int cpvs_shadow_info_get(const cpvs_shadow* s, cpvs_shadow_info* info) {
 	if (!s || !info) return fail(CPVS_EINVAL, "cpvs_shadow_info_get: NULL argument");
+	CPVS_READY(s);
 	*info = s->info;
 	return CPVS_OK;
 }
 
 int cpvs_shadow_copy_dag(const cpvs_shadow* s, uint32_t* out_host) {
 	if (!s || !out_host) return fail(CPVS_EINVAL, "cpvs_shadow_copy_dag: NULL argument");
+	CPVS_READY(s);
 	CPVS_CUDA(cudaSetDevice(s->ctx->device));
 	CPVS_CUDA(cudaMemcpyAsync(out_host, s->dag, s->info.words * sizeof(u32), cudaMemcpyDeviceToHost, s->ctx->stream));
 	CPVS_CUDA(cudaStreamSynchronize(s->ctx->stream));
 	return CPVS_OK;
 }
 
-const uint32_t* cpvs_shadow_dag_device(const cpvs_shadow* s) { return s ? s->dag : nullptr; }
+const uint32_t* cpvs_shadow_dag_device(const cpvs_shadow* s) {
+	if (!s || cpvs_shadow_wait(const_cast<cpvs_shadow*>(s)) != CPVS_OK) return nullptr;
+	return s->dag;
+}
 
 }  // extern "C"
 
@@ -1130,12 +386,16 @@ int cpvs_shadow_lookup_ndc(const cpvs_shadow* s, const float* ndc, int64_t count
 	if (!s || (count > 0 && (!ndc || !out))) return fail(CPVS_EINVAL, "cpvs_shadow_lookup_ndc: NULL argument");
 	if (count < 0) return fail(CPVS_EINVAL, "cpvs_shadow_lookup_ndc: count %lld", (long long)count);
 	if (count == 0) return CPVS_OK;
-	if (tryLeafmasks && !s->info.leafmasks)
-		return fail(CPVS_EINVAL, "cpvs_shadow_lookup_ndc: tryLeafmasks on a DAG built without leafmasks (SURVEY.md T2)");
+	CPVS_READY(s);
+	// The descent must match the layout: following a leafmask DAG below level 3 reads leaf words as pointers, and the other
+	// way round -- undefined in the reference, an error here.
+	if ((tryLeafmasks != 0) != (s->info.leafmasks != 0))
+		return fail(CPVS_EINVAL, "cpvs_shadow_lookup_ndc: tryLeafmasks=%d on a DAG built %s leafmasks (SURVEY.md T2)", tryLeafmasks ? 1 : 0,
+				s->info.leafmasks ? "with" : "without");
 	CPVS_CUDA(cudaSetDevice(s->ctx->device));
 	cudaStream_t st = s->ctx->stream;
 	LookupDag d{s->dag, nullptr, s->info.num_levels, 0, tryLeafmasks ? 1 : 0, nullptr, 0};
-	if ((tryLeafmasks != 0) == (s->info.leafmasks != 0)) {  // shortcut grid, built once
+	{  // shortcut grid, built once
 		cpvs_shadow* ms = const_cast<cpvs_shadow*>(s);
 		std::lock_guard<std::mutex> guard(ms->skipLock);
 		if (!ms->skip) {
@@ -1194,6 +454,7 @@ int cpvs_container_set_dag(cpvs_container* c, const uint32_t* words, uint64_t co
 	if (!c || !words || !count) return fail(CPVS_EINVAL, "cpvs_container_set_dag: NULL or empty DAG");
 	if (x >= c->length || y >= c->length || z >= c->length)  // assert of src/CompressedShadowContainer.h:35
 		return fail(CPVS_EINVAL, "cpvs_container_set_dag: cell (%u,%u,%u) outside length %u", x, y, z, c->length);
+	if (c->loaded) return fail(CPVS_EINVAL, "cpvs_container_set_dag: a container loaded from a file cannot be modified");
 	CPVS_CUDA(cudaSetDevice(c->ctx->device));
 	cudaStream_t st = c->ctx->stream;
 	ContainerCell& cell = c->cells[((size_t)z * c->length + y) * c->length + x];  // src/CompressedShadowContainer.h:37-38
@@ -1213,12 +474,16 @@ int cpvs_container_set_dag(cpvs_container* c, const uint32_t* words, uint64_t co
 
 int cpvs_container_set(cpvs_container* c, const cpvs_shadow* s, uint32_t x, uint32_t y, uint32_t z) {
 	if (!c || !s) return fail(CPVS_EINVAL, "cpvs_container_set: NULL argument");
+	CPVS_READY(s);
 	if (s->ctx->device != c->ctx->device) return fail(CPVS_EINVAL, "cpvs_container_set: shadow lives on another device; use cpvs_container_set_dag");
+	// a one-word DAG is stored without synchronising its builder's stream: order this stream behind that store
+	if (s->ready) CPVS_CUDA(cudaStreamWaitEvent(c->ctx->stream, s->ready, 0));
 	return cpvs_container_set_dag(c, s->dag, s->info.words, CPVS_MEM_DEVICE, s->info.num_levels, (int)s->info.leafmasks, x, y, z);
 }
 
 int cpvs_container_finalize(cpvs_container* c) {
 	if (!c) return fail(CPVS_EINVAL, "cpvs_container_finalize: NULL argument");
+	if (c->loaded) return CPVS_OK;  // a loaded container is final
 	CPVS_CUDA(cudaSetDevice(c->ctx->device));
 	cudaStream_t st = c->ctx->stream;
 	u64 total = 0;
@@ -1309,32 +574,45 @@ struct ContainerFileHeader {
 	u64 pad;
 };
 static_assert(sizeof(ContainerFileHeader) == 64, "on-disk header is 64 bytes");
-u64 fnv64Words(const u32* w, u64 n) {
-	u64 h = 14695981039346656037ull;
+u64 fnv64Words(u64 h, const u32* w, u64 n) {
 	for (u64 i = 0; i < n; ++i) {
 		h ^= w[i];
 		h *= 1099511628211ull;
 	}
 	return h;
 }
+// Checksum over everything the lookup trusts: the header fields, the grid and the DAG words.
+u64 containerChecksum(const ContainerFileHeader& h, const u32* grid, const u32* dag) {
+	const u32 fields[] = {h.version, h.length, h.dagLevels, h.gridLevels, h.leafmasks, (u32)h.dagWords, (u32)(h.dagWords >> 32),
+			(u32)h.gridCells, (u32)(h.gridCells >> 32)};
+	u64 sum = fnv64Words(14695981039346656037ull, fields, sizeof(fields) / sizeof(fields[0]));
+	sum = fnv64Words(sum, grid, h.gridCells);
+	return fnv64Words(sum, dag, h.dagWords);
+}
 }  // namespace
 
 int cpvs_container_save(const cpvs_container* c, const char* path) {
 	if (!c || !c->finalized || !path) return fail(CPVS_EINVAL, "cpvs_container_save: container not finalized or NULL path");
-	std::vector<u32> dag(c->dagWords), grid(c->cells.size());
+	std::vector<u32> dag, grid;
+	try {
+		dag.resize(c->dagWords);
+		grid.resize(c->cells.size());
+	} catch (const std::bad_alloc&) {
+		return fail(CPVS_ENOMEM, "cpvs_container_save: host staging of %llu words", (unsigned long long)c->dagWords);
+	}
 	int rc = cpvs_container_copy(c, dag.data(), grid.data());
 	if (rc != CPVS_OK) return rc;
 	ContainerFileHeader h;
 	std::memset(&h, 0, sizeof(h));
-	std::memcpy(h.magic, "CPVSDAG1", 8);
-	h.version = 1;
+	std::memcpy(h.magic, "CPVSDAG2", 8);
+	h.version = 2;
 	h.length = c->length;
 	h.dagLevels = c->dagLevels;
 	h.gridLevels = c->gridLevels;
 	h.leafmasks = (u32)c->leafmasks;
 	h.dagWords = c->dagWords;
 	h.gridCells = grid.size();
-	h.fnv64 = fnv64Words(dag.data(), dag.size());
+	h.fnv64 = containerChecksum(h, grid.data(), dag.data());
 	FILE* f = std::fopen(path, "wb");
 	if (!f) return fail(CPVS_EINVAL, "cpvs_container_save: cannot open %s", path);
 	const bool ok = std::fwrite(&h, sizeof(h), 1, f) == 1 && std::fwrite(grid.data(), sizeof(u32), grid.size(), f) == grid.size() &&
@@ -1350,20 +628,36 @@ int cpvs_container_load(cpvs_ctx* ctx, const char* path, cpvs_container** out) {
 	if (!f) return fail(CPVS_EINVAL, "cpvs_container_load: cannot open %s", path);
 	ContainerFileHeader h;
 	std::vector<u32> dag, grid;
-	bool ok = std::fread(&h, sizeof(h), 1, f) == 1 && std::memcmp(h.magic, "CPVSDAG1", 8) == 0 && h.version == 1 && isPow2(h.length) &&
+	// Every header field the lookup indexes with is validated against the others and against the file's size before
+	// anything is allocated; grid entries are checked against the DAG's extent afterwards.
+	bool ok = std::fread(&h, sizeof(h), 1, f) == 1 && std::memcmp(h.magic, "CPVSDAG2", 8) == 0 && h.version == 2 && isPow2(h.length) &&
 			  h.length <= 64 && h.gridCells == (u64)h.length * h.length * h.length && h.dagWords > 0 && h.dagWords <= (1ull << 32) &&
-			  h.dagLevels > 3 && h.dagLevels < kMaxLevels;
+			  h.dagLevels > 3 && h.dagLevels < (u32)kMaxLevels && h.leafmasks <= 1 && (1u << h.gridLevels) == h.length &&
+			  (!h.leafmasks || h.dagLevels >= 5);
 	if (ok) {
-		grid.resize(h.gridCells);
-		dag.resize(h.dagWords);
+		ok = std::fseek(f, 0, SEEK_END) == 0;
+		const long long size = ok ? (long long)std::ftell(f) : -1;
+		ok = ok && size == (long long)(sizeof(h) + (h.gridCells + h.dagWords) * sizeof(u32)) && std::fseek(f, (long)sizeof(h), SEEK_SET) == 0;
+	}
+	if (ok) {
+		try {
+			grid.resize(h.gridCells);
+			dag.resize(h.dagWords);
+		} catch (const std::bad_alloc&) {
+			std::fclose(f);
+			return fail(CPVS_ENOMEM, "cpvs_container_load: host staging of %llu words", (unsigned long long)h.dagWords);
+		}
 		ok = std::fread(grid.data(), sizeof(u32), grid.size(), f) == grid.size() && std::fread(dag.data(), sizeof(u32), dag.size(), f) == dag.size() &&
-			 fnv64Words(dag.data(), dag.size()) == h.fnv64;
+			 containerChecksum(h, grid.data(), dag.data()) == h.fnv64;
+		for (size_t i = 0; ok && i < grid.size(); ++i)
+			ok = grid[i] == CPVS_GRID_CELL_SHADOWED || grid[i] == CPVS_GRID_CELL_VISIBLE || grid[i] < h.dagWords;
 	}
 	std::fclose(f);
-	if (!ok) return fail(CPVS_EINVAL, "cpvs_container_load: %s is not a valid container file (header, size or checksum)", path);
+	if (!ok) return fail(CPVS_EINVAL, "cpvs_container_load: %s is not a valid container file (header, size, checksum or grid)", path);
 	cpvs_container* c = nullptr;
 	int rc = cpvs_container_create(ctx, h.length, &c);
 	if (rc != CPVS_OK) return rc;
+	c->loaded = true;
 	cudaStream_t st = ctx->stream;
 	cudaError_t e = cudaSetDevice(ctx->device);
 	if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(&c->dag), dag.size() * sizeof(u32), st);
@@ -1409,6 +703,8 @@ int cpvs_depth_generate(cpvs_ctx* ctx, int kind, int n, int tileX, int tileY, in
 	CPVS_CUDA(cudaSetDevice(ctx->device));
 	if (kind == CPVS_SCENE_PLANE) {
 		ctx->launches += launchPlaneDepth(depthDevice, n, gx0, gy0, gn, ctx->stream);
+	} else if (kind == CPVS_SCENE_TERRAIN_DEV) {
+		ctx->launches += launchTerrainDevDepth(depthDevice, n, gx0, gy0, gn, ctx->stream);
 	} else if (kind == CPVS_SCENE_CITY) {
 		std::vector<CityBoxDev> boxes;
 		cpvs_synth::forEachCityBox(gn, gx0, gy0, n, [&](const cpvs_synth::CityBox& b) { boxes.push_back(CityBoxDev{b.x0, b.y0, b.x1, b.y1, b.z}); });

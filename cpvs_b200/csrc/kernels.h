@@ -23,32 +23,25 @@ struct PyramidView {
 // cs::createChildmask for one node (known-answer tests): *out = 16-bit mask of the node at `level`.
 int launchChildmask(const PyramidView& pyr, int level, u32 zTileNum, u32 x, u32 y, u32 z, u32* out, cudaStream_t stream);
 
-// counts[l] += number of SVO nodes at level l, for l in [minLevel, numLevels-3]; counts must be zeroed.
-// All z-slices of a column at once: out[z] = (slice z has nodes below the root) << 32 | the root's child mask.
-int launchColumnRoots(const PyramidView& pyr, u32 zTileNum, u64* out, cudaStream_t stream);
-// counts[kRootMaskScalar] = 1<<32 | the root's child mask, written by every launch (a slice without nodes below
-// the root is that one word).
+// Closed-form node counts of every level for ALL z-slices of the column at once (createShadowTiles builds them from one
+// pyramid): counts[z * kMaxLevels + l] += number of SVO nodes at level l of slice z, for l in [minLevel, numLevels-3];
+// counts[z * kMaxLevels + kRootMaskScalar] = 1<<32 | the root's child mask of slice z (a slice without nodes below the
+// root is that one word). counts must be zeroed (zTileNum * kMaxLevels words).
 constexpr int kRootMaskScalar = 31;
-int launchCountNodes(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, int minLevel, u64* counts, cudaStream_t stream);
+int launchColumnCounts(const PyramidView& pyr, u32 zTileNum, int minLevel, u64* counts, cudaStream_t stream);
 
 constexpr u64 kExpandTileNodes = 128 * kScanItems;  // nodes per look-back tile of launchExpandLevel
-// One breadth-first step: masks of the n nodes of `level`, index of each node's first child in the
-// next level, and the next level's coordinate list. childTotal receives the next level's node count.
+// One breadth-first step: masks of the *nDev nodes of `level`, index of each node's first child in the
+// next level, and the next level's coordinate list. *childN receives the next level's node count.
+// Every size is read on the device: `cap` (>= *nDev) only sizes the grid, `childCap` bounds the writes into the next
+// level's arrays -- if the level turns out larger, *childN is clamped to childCap and bit 0 of *overflow is set (the
+// host then rebuilds with exact counts).
 // With leafAt != NULL the children are leaves built per column (launchBuildLeafColumns): instead of their
 // coordinates, each child's index is stored at its column-order position leafAt[colBias[column] + z].
-int launchExpandLevel(const PyramidView& pyr, int level, u32 zTileNum, const u64* coords, u64 n, u16* masks,
-		u32* firstChild, u64* childCoords, u64* childTotal, ScanLaunch scan, const u32* colBias, u32* leafAt, u32 numLeaves, int preloadBias,
-		cudaStream_t stream);  // preloadBias: experimental variant of the leaf-column scatter (kExperimentExpandPreload)
-
-// Experimental kernel variants, off by default, selected per context by CPVS_EXPERIMENTS (comma-separated names); the default
-// kernels stay instruction-identical (scripts/sass_diff.py) and results never depend on them.
-constexpr unsigned kExperimentExpandPreload = 1u;  // "expand-preload": svo.cu expandLevelPreloadKernel
-constexpr unsigned kExperimentEmitGather = 2u;     // "emit-gather":    emit.cu emitInnerLevelsKernel<true>
-constexpr unsigned kExperimentRankPreload = 4u;    // "rank-preload":   merge.cu rankCountKernel<true>, rankWriteKernel<true>
-constexpr unsigned kExperimentInsertWitness = 8u;  // "insert-witness": merge.cu insertInnerWitnessKernel
-constexpr unsigned kExperimentEarlyBases = 16u;    // "early-bases":    capi.cu, streams only (see cpvs_ctx::aux4)
-constexpr unsigned kExperimentLeafFp64 = 32u;      // "leaf-fp64":      merge.cu insertLeavesFingerprintKernel + verifyLeafGroupsKernel
-constexpr unsigned kExperimentLeafFpWeak = 64u;    // "leaf-fp64-weak": the same with a 12-bit fingerprint (tests of the fallback only)
+constexpr u32 kOverflowNodes = 1u, kOverflowWords = 2u;  // bits of the build's overflow word
+int launchExpandLevel(const PyramidView& pyr, int level, u32 zTileNum, const u64* coords, const u64* nDev, u64 cap, u16* masks,
+		u32* firstChild, u64* childCoords, u64 childCap, u64* childN, u32* overflow, ScanLaunch scan, const u32* colBias, u32* leafAt,
+		cudaStream_t stream);
 
 // The small top levels (<= kSmallMaxNodes nodes each, root first) expanded by a single CTA.
 constexpr int kSmallThreads = 1024;
@@ -62,14 +55,16 @@ struct SmallExpandLevel {
 	u16* masks;
 	u32* firstChild;
 	u64* childCoords;  // next level's coordinate list (may be null when no child can exist)
-	u64* childTotal;
+	u64* childN;       // out: the next level's node count, clamped to childCap
+	u32 childCap;      // capacity of the next level's arrays
 	const u32* colBias;  // with leafAt: the children are leaves built per column (see launchExpandLevel)
 	u32* leafAt;
-	u32 numLeaves;
 };
 struct SmallExpandArgs {
 	SmallExpandLevel lv[kMaxLevels];
 	int count;
+	u64* rootN;     // out: node count of the first level (1)
+	u32* overflow;  // see launchExpandLevel
 };
 int launchExpandSmallLevels(const SmallExpandArgs& a, cudaStream_t stream);
 
@@ -78,8 +73,8 @@ int launchExpandSmallLevels(const SmallExpandArgs& a, cudaStream_t stream);
 // Also sets one bit per leaf hash in `sketch` (kSketchWords zeroed words): a linear-counting estimate of
 // the number of distinct leaves, used to size the merge table so that it stays resident in L2.
 constexpr u32 kSketchWords = 1u << 22;  // 2^27 bits, 16 MiB
-int launchBuildLeaves(const PyramidView& pyr, u32 zTileNum, const u64* coords, u64 n, u32* codes, u64* hashes, u16* masks, u32* sketch,
-		cudaStream_t stream);
+int launchBuildLeaves(const PyramidView& pyr, u32 zTileNum, const u64* coords, const u64* nDev, u64 cap, u32* codes, u64* hashes, u16* masks,
+		u32* sketch, cudaStream_t stream);
 // The same, one column of leaves (all z-blocks over an 8x8 texel block) at a time: every depth row is read once.
 // launchColumnBias: colBias[c] = (leaves in the columns in front of c, row-major over the (n/8)^2 columns) - first
 // z-block of c; one look-back scan over pyramid level 3. leafAt[colBias[c] + zb] = index of leaf (c, zb) in the
@@ -94,7 +89,8 @@ int launchSketchPopcount(const u32* sketch, u64* setBits, cudaStream_t stream);
 // Inner-level tables carry kDirectSlots extra slots behind the tableSize hashed ones (merge.cu).
 constexpr u32 kDirectSlots = 256;
 struct MergeLevelArgs {
-	u64 n;                 // nodes in this level
+	const u64* nDev;       // device: nodes in this level
+	u64 cap;               // host: upper bound of *nDev (sizes the grids)
 	int leaf;              // 1: level of leafmask nodes
 	const u32* leafCodes;  // leaf: k-code, 8 words per node
 	const u64* leafHash;   // leaf: content hash per node, or NULL (then computed from the code)
@@ -107,6 +103,7 @@ struct MergeLevelArgs {
 	const u64* sketchBits; // leaf level: set bits of the distinct-count sketch (device)
 	u64* tableMaskDev;     // leaf level: (chosen capacity - 1), written by the sizing kernel (device)
 	u32* errorFlag;        // device: set if a probe sequence wraps the whole table
+	const u32* overflow;   // device: kOverflowNodes set by the expansion = the level arrays are incomplete; merge nothing
 	u32* uid;              // out (insert): group id per node = its group's table slot
 	u32* firstList;        // out (rank): node index of the r-th unique node
 	u32* wordOffset;       // out (rank): compressed word offset (inside the level) of the r-th unique node
@@ -114,14 +111,10 @@ struct MergeLevelArgs {
 	unsigned char* sizeOf; // scratch (rank): compressed size of node j if it is a first occurrence, else 0
 	u64* uniqueCount;      // out: number of unique nodes
 	u64* wordCount;        // out: compressed words of the level
-	int rankPreload;       // experimental variants of the rank's first and last kernel (kExperimentRankPreload)
-	int parallelWitness;   // experimental variant of the inner insert (kExperimentInsertWitness)
-	int fingerprint;       // leaf: 16-byte slots grouped by 64-bit fingerprint, verified later (kExperimentLeafFp64);
-	                       // 2: a 12-bit fingerprint, to drive tests through the failed-verification path
 };
 // The small top levels merged bottom-up by a single CTA (same result as launchMergeLevel per level).
 struct SmallMergeLevel {
-	u32 n;
+	const u64* nDev;  // device: nodes in this level (<= kSmallMaxNodes)
 	const u16* masks;
 	const u32* firstChild;
 	const u32* childUid;
@@ -137,36 +130,41 @@ struct SmallMergeArgs {
 	int count;
 	u64* table;  // >= 2 * kSmallMaxNodes slots
 	u32* errorFlag;
+	const u32* overflow;  // see MergeLevelArgs
 };
 int launchMergeSmallLevels(const SmallMergeArgs& a, cudaStream_t stream);
 
 // Leaf level only: picks the table capacity from the sketch's set-bit count and clears that many slots.
-// wideSlots: 16-byte slots (kExperimentLeafFp64); maxSlots still counts the 8-byte words behind `table`.
-int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* tableMaskDev, int wideSlots, cudaStream_t stream);
-// kExperimentLeafFp64: every leaf that is not its group's first is compared with the first; *mismatchFlag = 1 on a difference.
-int launchVerifyLeafGroups(const MergeLevelArgs& a, u32* mismatchFlag, cudaStream_t stream);
+int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* tableMaskDev, cudaStream_t stream);
 // Insert assigns group ids (all the parent level needs); rank orders the unique nodes and may run
 // concurrently with the next level's insert as long as this level's table is left alone.
 int launchInsertLevel(const MergeLevelArgs& a, cudaStream_t stream);
-// afterSizes (optional) is recorded once uniqueCount / wordCount are final, ahead of the kernel that writes the lists.
-int launchRankLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaStream_t stream, cudaEvent_t afterSizes = nullptr);
+int launchRankLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaStream_t stream);
 
 // ---- emit.cu: compress (reference src/CompressedShadow.cpp:326-392) ----
+// The DAG is written at the END of an allocation of `capacity` words (the capacity may be a prediction made before the
+// sizes were known): its first word is dagAlloc[capacity - *totalWords]. The leaf level ends the DAG, so it can be
+// written as soon as it is ranked (fromEnd: level start = capacity - *wordCount), next to the merge of the inner levels.
+// Nothing is written when the words do not fit (launchLevelBases reports that).
 struct EmitLevelArgs {
-	u64 n;                    // unique nodes of the level (or any upper bound: sizes the grid)
+	u64 n;                    // expected unique nodes of the level (sizes the grid; any value is correct)
 	int leaf;
+	int fromEnd;              // the level is the DAG's last: place it from the end of the allocation, totalWords not needed
 	const u64* uniqueCount;   // device: unique nodes of this level
 	const u32* firstList;
 	const u32* wordOffset;
 	const u64* wordCount;     // device: compressed words of this level
 	const u64* levelBase;     // device: word offset of this level in the DAG
+	const u64* totalWords;    // device: words of the whole DAG
 	const u32* leafCodes;
 	const u16* masks;
 	const u32* firstChild;
 	const u32* childUid;        // group ids (table slots) of the level below
 	const u32* childSlotOffset; // word offset per slot of the level below
 	const u64* childLevelBase;  // device: word offset of the level below in the DAG
-	u32* dag;
+	u32* dagAlloc;
+	u64 capacity;
+	const u32* overflow;  // device: kOverflowNodes set = the level arrays are incomplete; write nothing
 };
 int launchEmitLevel(const EmitLevelArgs& a, cudaStream_t stream);
 // Several inner levels in one launch (block ranges per level).
@@ -175,11 +173,12 @@ struct EmitMultiArgs {
 	EmitLevelArgs lv[kMaxEmitLevels];
 	u32 blockStart[kMaxEmitLevels + 1];
 	int count;
-	int gather;  // experimental variant of the pointer gather (kExperimentEmitGather)
 };
 int launchEmitInnerLevels(EmitMultiArgs& a, cudaStream_t stream);
-// bases[l] for l = top..minLevel from words[l]; total -> *totalWords. One thread.
-int launchLevelBases(const u64* words, u64* bases, int topLevel, int minLevel, u64* totalWords, cudaStream_t stream);
+// bases[l] for l = top..minLevel from words[l]; total -> *totalWords; sets kOverflowWords in *overflow if the total
+// exceeds `capacity`; *rootWord = the root's mask (the DAG's first word). One thread.
+int launchLevelBases(const u64* words, u64* bases, int topLevel, int minLevel, u64* totalWords, u64 capacity, u32* overflow, const u16* rootMask,
+		u32* rootWord, cudaStream_t stream);
 
 // ---- lookup.cu: traverse (reference src/CompressedShadow.cpp:404-463, shader/traverse.cs) ----
 struct LookupDag {
@@ -216,6 +215,7 @@ struct CityBoxDev {
 	float z;
 };
 int launchPlaneDepth(float* out, int n, long long gx0, long long gy0, long long gn, cudaStream_t stream);
+int launchTerrainDevDepth(float* out, int n, long long gx0, long long gy0, long long gn, cudaStream_t stream);
 int launchCityDepth(float* out, int n, const CityBoxDev* boxes, int numBoxes, float farPlane, cudaStream_t stream);
 
 }  // namespace cpvs

@@ -18,6 +18,8 @@
 //                that are their own representative are the unique nodes. One look-back scan ranks them
 //                (first-occurrence order = the reference's layout), prefix-sums their compressed sizes
 //                and leaves each group's word offset next to its slot for the parents' pointers.
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace cpvs {
@@ -63,8 +65,6 @@ __device__ __forceinline__ u32 findGroupSlot(u64* __restrict__ table, u64 tableM
 // Leaf table capacity from the distinct-count sketch (linear counting: u ~ -m ln(zero fraction)), rounded
 // up to a power of two with >= 1.5x headroom, then cleared. The result does not depend on the capacity,
 // only the speed does: a table sized for the distinct leaves (not for all leaves) stays in L2.
-// kWide (experimental, leaf-fp64): 16-byte slots (64-bit fingerprint, smallest node index), maxSlots counts such slots.
-template <bool kWide>
 __global__ void __launch_bounds__(256) sizeAndClearLeafTableKernel(u64* __restrict__ table, u64 maxSlots, const u64* __restrict__ setBits,
 		u64* __restrict__ tableMaskDev) {
 	const float m = (float)kSketchWords * 32.0f;
@@ -76,29 +76,36 @@ __global__ void __launch_bounds__(256) sizeAndClearLeafTableKernel(u64* __restri
 	if (cap > maxSlots) cap = maxSlots;
 	if (blockIdx.x == 0 && threadIdx.x == 0) *tableMaskDev = cap - 1;
 	ulonglong2* t2 = reinterpret_cast<ulonglong2*>(table);
-	const u64 pairs = kWide ? cap : cap / 2;
+	const u64 pairs = cap / 2;
 	for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += (u64)gridDim.x * blockDim.x) t2[i] = make_ulonglong2(kEmpty, kEmpty);
 }
 
-__global__ void __launch_bounds__(256) insertLeavesKernel(const u32* __restrict__ codes, const u64* __restrict__ hashes, u64 n, u64* __restrict__ table,
-		const u64* __restrict__ tableMaskDev, u32* __restrict__ slotOf, u32* errorFlag) {
+// Leaf insert. The chain per leaf is own code -> hash -> table probe -> witness code -> compare -> atomicMin: three to four
+// dependent memory round trips, and with one leaf per thread the kernel sat at 76 % long-scoreboard stalls with DRAM a
+// third busy (profiles/r1_stall_sites.md). Here a CTA stages the codes of 1024 consecutive leaves in shared memory with
+// cp.async (no registers, fully coalesced), every thread owns four of them, and each step of the chain is issued for all
+// four before any result is looked at -- probes, then CAS for the empty slots, then witness codes, then atomicMin --
+// in rounds until every leaf has found its group (linear probing: the rare leaf that must move on takes another round).
+// Same table, same keys, same first-occurrence rule as findGroupSlot.
+
+__device__ __forceinline__ u64 hashLeafCode(const uint4& a0, const uint4& a1) {
+	u64 h = 0x9E3779B97F4A7C15ull;
+	h = (h ^ (((u64)a0.y << 32) | a0.x)) * 0xFF51AFD7ED558CCDull;
+	h = (h ^ (h >> 32) ^ (((u64)a0.w << 32) | a0.z)) * 0xC4CEB9FE1A85EC53ull;
+	h = (h ^ (h >> 32) ^ (((u64)a1.y << 32) | a1.x)) * 0xFF51AFD7ED558CCDull;
+	h = (h ^ (h >> 32) ^ (((u64)a1.w << 32) | a1.z)) * 0xC4CEB9FE1A85EC53ull;
+	return mix64(h);
+}
+
+__global__ void __launch_bounds__(256) insertLeavesKernel(const u32* __restrict__ codes, const u64* __restrict__ hashes, const u64* __restrict__ nDev,
+		u64* __restrict__ table, const u64* __restrict__ tableMaskDev, u32* __restrict__ slotOf, u32* errorFlag, const u32* __restrict__ overflow) {
 	const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= n) return;
+	if (j >= *nDev || (*overflow & kOverflowNodes)) return;
 	const u64 tableMask = *tableMaskDev;
 	// own code and hash are fetched up front so that their latency overlaps the first table probe
 	const uint4* mine = reinterpret_cast<const uint4*>(codes + j * 8);
 	const uint4 a0 = __ldcs(mine), a1 = __ldcs(mine + 1);
-	u64 hash;
-	if (hashes) {
-		hash = __ldcs(hashes + j);
-	} else {
-		u64 h = 0x9E3779B97F4A7C15ull;
-		h = (h ^ (((u64)a0.y << 32) | a0.x)) * 0xFF51AFD7ED558CCDull;
-		h = (h ^ (h >> 32) ^ (((u64)a0.w << 32) | a0.z)) * 0xC4CEB9FE1A85EC53ull;
-		h = (h ^ (h >> 32) ^ (((u64)a1.y << 32) | a1.x)) * 0xFF51AFD7ED558CCDull;
-		h = (h ^ (h >> 32) ^ (((u64)a1.w << 32) | a1.z)) * 0xC4CEB9FE1A85EC53ull;
-		hash = mix64(h);
-	}
+	const u64 hash = hashes ? __ldcs(hashes + j) : hashLeafCode(a0, a1);
 	slotOf[j] = findGroupSlot(table, tableMask, hash, (u32)j, errorFlag, [&](u32 other) {
 		const uint4* theirs = reinterpret_cast<const uint4*>(codes + (u64)other * 8);
 		const uint4 b0 = theirs[0], b1 = theirs[1];
@@ -106,65 +113,136 @@ __global__ void __launch_bounds__(256) insertLeavesKernel(const u32* __restrict_
 	});
 }
 
-// ---- experimental: leaf-fp64 ------------------------------------------------------------------------------------------------
-// The exact insert above pays a DRAM round trip per duplicate leaf for the witness's code (L2 allocates 128-byte lines, a witness
-// is one 32-byte sector of an otherwise idle line: 2.5 M witnesses want 320 MB of L2). Here the grouping that the parent level
-// waits for trusts a 64-bit fingerprint -- 16-byte slots (fingerprint, smallest node index), one probe, no witness read -- and
-// the exact compare moves off the critical path: verifyLeafGroupsKernel, on a side stream beside the inner inserts, compares
-// every leaf that is not its group's first with the first. A mismatch raises a flag and the build is redone with the exact
-// insert, so the words never depend on the hash.
-__global__ void __launch_bounds__(256) insertLeavesFingerprintKernel(const u32* __restrict__ codes, u64 n, u64* __restrict__ table,
-		const u64* __restrict__ tableMaskDev, u64 fingerprintMask, u32* __restrict__ slotOf, u32* errorFlag) {
-	const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= n) return;
-	const u64 tableMask = *tableMaskDev;
-	const uint4* mine = reinterpret_cast<const uint4*>(codes + j * 8);
-	const uint4 a0 = __ldcs(mine), a1 = __ldcs(mine + 1);
-	u64 h = 0x9E3779B97F4A7C15ull;
-	h = (h ^ (((u64)a0.y << 32) | a0.x)) * 0xFF51AFD7ED558CCDull;
-	h = (h ^ (h >> 32) ^ (((u64)a0.w << 32) | a0.z)) * 0xC4CEB9FE1A85EC53ull;
-	h = (h ^ (h >> 32) ^ (((u64)a1.y << 32) | a1.x)) * 0xFF51AFD7ED558CCDull;
-	h = (h ^ (h >> 32) ^ (((u64)a1.w << 32) | a1.z)) * 0xC4CEB9FE1A85EC53ull;
-	h = mix64(h);
-	u64 slot = (h >> 20) & tableMask;  // (the low bits would do as well; these are the ones the sketch looked at)
-	h &= fingerprintMask;              // all ones, except in the test mode that provokes collisions (leaf-fp64-weak)
-	if (h == kEmpty) h = 0;            // the empty marker is not a fingerprint
-	for (u64 probes = 0; probes <= tableMask; ++probes) {
-		u64* entry = table + 2 * slot;
-		u64 fp = ldRelaxed64(entry);
-		if (fp == kEmpty) {
-			const u64 old = atomicCAS(reinterpret_cast<unsigned long long*>(entry), (unsigned long long)kEmpty, (unsigned long long)h);
-			fp = old == kEmpty ? h : old;
+template <int kLeafBatch>
+__global__ void __launch_bounds__(256) insertLeavesBatchKernel(const u32* __restrict__ codes, const u64* __restrict__ hashes, const u64* __restrict__ nDev,
+		u64* __restrict__ table, const u64* __restrict__ tableMaskDev, u32* __restrict__ slotOf, u32* errorFlag, const u32* __restrict__ overflow) {
+	constexpr int kInsertLeaves = 256 * kLeafBatch;
+	__shared__ __align__(16) uint4 sCode[kInsertLeaves * 2];
+	const u64 n = *nDev;
+	const u64 ctaBase = (u64)blockIdx.x * kInsertLeaves;
+	if (ctaBase >= n || (*overflow & kOverflowNodes)) return;  // the grid is sized for the level's capacity
+	const u32 tableMask = (u32)*tableMaskDev;
+	const u32 live = (u32)(n - ctaBase < (u64)kInsertLeaves ? n - ctaBase : (u64)kInsertLeaves);
+	{
+		const uint4* src = reinterpret_cast<const uint4*>(codes + ctaBase * 8);
+#pragma unroll
+		for (int i = 0; i < 2 * kLeafBatch; ++i) {
+			const u32 piece = threadIdx.x + 256u * i;
+			if (piece < live * 2u) {
+				const u32 dst = (u32)__cvta_generic_to_shared(&sCode[piece]);
+				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + piece) : "memory");
+			}
 		}
-		if (fp == h) {
-			// smallest index of the group: read first, the members of a popular group must not queue up on one address
-			u32 lowered = 0;
-			if (ldRelaxed64(entry + 1) > j) lowered = atomicMin(reinterpret_cast<unsigned long long*>(entry + 1), (unsigned long long)j) > j ? kCandidateFlag : 0u;
-			slotOf[j] = (u32)slot | lowered;
-			return;
-		}
-		slot = (slot + 1) & tableMask;
+		asm volatile("cp.async.commit_group;" ::: "memory");
 	}
-	atomicExch(errorFlag, 1u);
-	slotOf[j] = 0u;
+	u64 preHash[kLeafBatch];
+	if (hashes) {  // (per-leaf builder: the hash was stored next to the code)
+#pragma unroll
+		for (int i = 0; i < kLeafBatch; ++i) {
+			const u32 q = threadIdx.x + 256u * i;
+			preHash[i] = q < live ? __ldcs(hashes + ctaBase + q) : 0;
+		}
+	}
+	asm volatile("cp.async.wait_group 0;" ::: "memory");
+	__syncthreads();
+
+	u32 slot[kLeafBatch], fp[kLeafBatch], res[kLeafBatch];
+	u32 pending = 0;
+#pragma unroll
+	for (int i = 0; i < kLeafBatch; ++i) {
+		const u32 q = threadIdx.x + 256u * i;
+		res[i] = 0;
+		slot[i] = fp[i] = 0;
+		if (q < live) {
+			const u64 h = hashes ? preHash[i] : hashLeafCode(sCode[2 * q], sCode[2 * q + 1]);
+			fp[i] = (u32)(h >> 32);
+			slot[i] = (u32)h & tableMask;
+			pending |= 1u << i;
+		}
+	}
+	for (u32 round = 0; pending; ++round) {
+		if (round > tableMask) {  // table full: cannot happen with a sane size estimate; reported to the host
+			atomicExch(errorFlag, 1u);
+			break;
+		}
+		u64 v[kLeafBatch];
+#pragma unroll
+		for (int i = 0; i < kLeafBatch; ++i)
+			if (pending & (1u << i)) v[i] = ldRelaxed64(table + slot[i]);
+		// empty slots: claim them (all CAS in flight together)
+		u64 cur[kLeafBatch];
+#pragma unroll
+		for (int i = 0; i < kLeafBatch; ++i) {
+			cur[i] = 0;
+			if (pending & (1u << i)) {
+				const u64 key = ((u64)fp[i] << 32) | (u32)(ctaBase + threadIdx.x + 256u * i);
+				cur[i] = v[i] == kEmpty ? atomicCAS(reinterpret_cast<unsigned long long*>(table + slot[i]), (unsigned long long)kEmpty, (unsigned long long)key)
+										: v[i];
+			}
+		}
+		u32 want = 0;
+#pragma unroll
+		for (int i = 0; i < kLeafBatch; ++i) {
+			if (!(pending & (1u << i))) continue;
+			if (v[i] == kEmpty && cur[i] == kEmpty) {  // ours now: the first of its group so far
+				res[i] = slot[i] | kCandidateFlag;
+				pending &= ~(1u << i);
+			} else if ((u32)(cur[i] >> 32) == fp[i]) {
+				want |= 1u << i;
+			}
+		}
+		// same fingerprint: compare with a member of the group (all witness codes in flight together)
+		uint4 w0[kLeafBatch], w1[kLeafBatch];
+#pragma unroll
+		for (int i = 0; i < kLeafBatch; ++i)
+			if (want & (1u << i)) {
+				const uint4* theirs = reinterpret_cast<const uint4*>(codes + (u64)(u32)cur[i] * 8);
+				w0[i] = theirs[0];
+				w1[i] = theirs[1];
+			}
+		u32 same = 0;
+#pragma unroll
+		for (int i = 0; i < kLeafBatch; ++i)
+			if (want & (1u << i)) {
+				const u32 q = threadIdx.x + 256u * i;
+				const uint4 a0 = sCode[2 * q], a1 = sCode[2 * q + 1];
+				if (a0.x == w0[i].x && a0.y == w0[i].y && a0.z == w0[i].z && a0.w == w0[i].w && a1.x == w1[i].x && a1.y == w1[i].y && a1.z == w1[i].z &&
+						a1.w == w1[i].w)
+					same |= 1u << i;
+			}
+		// the slot only ever decreases: nothing to do if an earlier node already holds it. A node that never lowered its
+		// slot cannot be the first occurrence; the ones that did are marked as candidates for the rank scan.
+		u64 before[kLeafBatch];
+#pragma unroll
+		for (int i = 0; i < kLeafBatch; ++i) {
+			before[i] = 0;
+			const u32 self = (u32)(ctaBase + threadIdx.x + 256u * i);
+			if ((same & (1u << i)) && (u32)cur[i] > self) {
+				const u64 key = ((u64)fp[i] << 32) | self;
+				before[i] = atomicMin(reinterpret_cast<unsigned long long*>(table + slot[i]), (unsigned long long)key);
+			}
+		}
+#pragma unroll
+		for (int i = 0; i < kLeafBatch; ++i) {
+			if (!(pending & (1u << i))) continue;
+			const u32 self = (u32)(ctaBase + threadIdx.x + 256u * i);
+			if (same & (1u << i)) {
+				const u64 key = ((u64)fp[i] << 32) | self;
+				res[i] = slot[i] | (((u32)cur[i] > self && before[i] > key) ? kCandidateFlag : 0u);
+				pending &= ~(1u << i);
+			} else {
+				slot[i] = (slot[i] + 1u) & tableMask;
+			}
+		}
+	}
+#pragma unroll
+	for (int i = 0; i < kLeafBatch; ++i) {
+		const u32 q = threadIdx.x + 256u * i;
+		if (q < live) slotOf[ctaBase + q] = res[i];
+	}
 }
 
-__global__ void __launch_bounds__(256) verifyLeafGroupsKernel(const u32* __restrict__ codes, u64 n, const u64* __restrict__ table,
-		const u32* __restrict__ slotOf, u32* mismatchFlag) {
-	const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= n) return;
-	const u32 first = (u32)table[2 * (u64)(slotOf[j] & kGidMask) + 1];
-	if (first == (u32)j) return;
-	const uint4* mine = reinterpret_cast<const uint4*>(codes + j * 8);
-	const uint4* theirs = reinterpret_cast<const uint4*>(codes + (u64)first * 8);
-	const uint4 a0 = __ldcs(mine), a1 = __ldcs(mine + 1), b0 = theirs[0], b1 = theirs[1];
-	const bool same = a0.x == b0.x && a0.y == b0.y && a0.z == b0.z && a0.w == b0.w && a1.x == b1.x && a1.y == b1.y && a1.z == b1.z && a1.w == b1.w;
-	if (!same) atomicExch(mismatchFlag, 1u);
-}
-
-// kParallelWitness (experimental, CPVS_EXPERIMENTS=insert-witness): the witness's mask and first-child index are loaded together
-// (the fingerprint already matched, so the mask almost always does too) instead of the index only after the mask compared equal.
-template <bool kShared = false, bool kParallelWitness = false>
+template <bool kShared = false>
 __device__ __forceinline__ u32 insertInnerNode(u32 j, const u16* __restrict__ masks, const u32* __restrict__ firstChild,
 		const u32* __restrict__ childUid, u64* __restrict__ table, u64 tableMask, u32* errorFlag) {
 	const u32 mask = masks[j];
@@ -181,15 +259,8 @@ __device__ __forceinline__ u32 insertInnerNode(u32 j, const u16* __restrict__ ma
 		}
 	}
 	return findGroupSlot<kShared>(table, tableMask, h, j, errorFlag, [&](u32 other) {
-		const u32* theirs;
-		if constexpr (kParallelWitness) {
-			const u32 theirMask = masks[other], theirFirst = firstChild[other];
-			if (theirMask != mask) return false;
-			theirs = childUid + theirFirst;
-		} else {
-			if (masks[other] != mask) return false;
-			theirs = childUid + firstChild[other];
-		}
+		if (masks[other] != mask) return false;
+		const u32* theirs = childUid + firstChild[other];
 		bool same = true;
 #pragma unroll
 		for (u32 c = 0; c < 8; ++c)
@@ -213,10 +284,14 @@ __device__ __forceinline__ u32 compactLitBits(u32 mask) {
 // Held to 32 registers (8 instead of 6 CTAs of 256 threads per SM, one 4-byte spill): the kernel waits on dependent loads 62 % of
 // the time, and the two extra CTAs are worth 0.03 ms on the 16K^2 terrain (inner merge 0.436 -> 0.409 ms, the leaf rank running
 // beside it 0.375 -> 0.348 ms; profiles/r1_switch_probe.md).
-template <bool kParallelWitness>
-__device__ __forceinline__ void insertInnerBody(const u16* __restrict__ masks, const u32* __restrict__ firstChild,
-		const u32* __restrict__ childUid, u64 n, u64* __restrict__ table, u64 tableMask, u32* __restrict__ slotOf, u32* errorFlag) {
+__global__ void __launch_bounds__(256, 8) insertInnerKernel(const u16* __restrict__ masks, const u32* __restrict__ firstChild,
+		const u32* __restrict__ childUid, const u64* __restrict__ nDev, u64* __restrict__ table, u64 tableMask, u32* __restrict__ slotOf,
+		u32* errorFlag, const u32* __restrict__ overflow) {
 	__shared__ u32 sFirst[kDirectSlots];
+	const u64 n = *nDev;
+	// the grid is sized for the level's capacity; a level cut short by a capacity (the child lists of its last nodes are
+	// incomplete) is not merged at all -- the host rebuilds with exact counts
+	if ((u64)blockIdx.x * blockDim.x >= n || (*overflow & kOverflowNodes)) return;
 	const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	sFirst[threadIdx.x] = 0xFFFFFFFFu;
 	__syncthreads();
@@ -236,15 +311,7 @@ __device__ __forceinline__ void insertInnerBody(const u16* __restrict__ masks, c
 	if (direct)
 		slotOf[j] = (u32)(tableMask + 1 + c) | (sFirst[c] == (u32)j ? kCandidateFlag : 0u);
 	else if (live)
-		slotOf[j] = insertInnerNode<false, kParallelWitness>((u32)j, masks, firstChild, childUid, table, tableMask, errorFlag);
-}
-__global__ void __launch_bounds__(256, 8) insertInnerKernel(const u16* __restrict__ masks, const u32* __restrict__ firstChild,
-		const u32* __restrict__ childUid, u64 n, u64* __restrict__ table, u64 tableMask, u32* __restrict__ slotOf, u32* errorFlag) {
-	insertInnerBody<false>(masks, firstChild, childUid, n, table, tableMask, slotOf, errorFlag);
-}
-__global__ void __launch_bounds__(256, 8) insertInnerWitnessKernel(const u16* __restrict__ masks, const u32* __restrict__ firstChild,
-		const u32* __restrict__ childUid, u64 n, u64* __restrict__ table, u64 tableMask, u32* __restrict__ slotOf, u32* errorFlag) {
-	insertInnerBody<true>(masks, firstChild, childUid, n, table, tableMask, slotOf, errorFlag);
+		slotOf[j] = insertInnerNode<false>((u32)j, masks, firstChild, childUid, table, tableMask, errorFlag);
 }
 
 // gid[j] = slot of node j's group. Ranks the first occurrences (slot's final index == j) in order,
@@ -255,44 +322,44 @@ __global__ void __launch_bounds__(256, 8) insertInnerWitnessKernel(const u16* __
 // (the only part with random accesses) and leave each node's compressed size in a byte plus the tile's
 // totals; (2) one CTA prefix-sums the tile totals; (3) per tile, a block scan of the bytes and the writes.
 // No CTA ever waits for another one, which matters more here than the extra byte per node of traffic.
-// kPreload (experimental, CPVS_EXPERIMENTS=rank-preload): the four masks of the thread are fetched with one 8-byte load up front
-// instead of one dependent load per first occurrence behind the table look-up.
-// kWide (experimental, leaf-fp64): 16-byte slots, the group's smallest index is the second word.
-template <bool kPreload, bool kWide = false>
-__global__ void __launch_bounds__(kScanThreads, 8) rankCountKernel(const u64* __restrict__ table, const u16* __restrict__ masks, int leaf, u64 n,
-		const u32* __restrict__ gid, unsigned char* __restrict__ sizeOf, ScanTileState* __restrict__ tiles) {
+// The four masks and group ids of a thread are fetched with one 8-byte / 16-byte load up front instead of one dependent load per
+// first occurrence behind the table look-up (measured: 0.015 ms of the 16K^2 terrain build, profiles/r2_switch_probe.md).
+__global__ void __launch_bounds__(kScanThreads, 8) rankCountKernel(const u64* __restrict__ table, const u16* __restrict__ masks, int leaf,
+		const u64* __restrict__ nDev, const u32* __restrict__ gid, unsigned char* __restrict__ sizeOf, ScanTileState* __restrict__ tiles,
+		const u32* __restrict__ overflow) {
+	const u64 n = (*overflow & kOverflowNodes) ? 0 : *nDev;
 	const u64 base = (u64)blockIdx.x * kScanTile + (u64)threadIdx.x * kScanItems;
-	u32 myMask[kScanItems] = {0, 0, 0, 0};
-	if constexpr (kPreload) {
-		if (base + kScanItems <= n) {
-			const uint2 v = *reinterpret_cast<const uint2*>(masks + base);
-			myMask[0] = v.x & 0xFFFFu;
-			myMask[1] = v.x >> 16;
-			myMask[2] = v.y & 0xFFFFu;
-			myMask[3] = v.y >> 16;
-		} else {
+	if ((u64)blockIdx.x * kScanTile >= n) return;  // the grid is sized for the level's capacity
+	u32 myMask[kScanItems] = {0, 0, 0, 0}, g[kScanItems] = {0, 0, 0, 0};
+	if (base + kScanItems <= n) {
+		const uint2 v = *reinterpret_cast<const uint2*>(masks + base);
+		myMask[0] = v.x & 0xFFFFu;
+		myMask[1] = v.x >> 16;
+		myMask[2] = v.y & 0xFFFFu;
+		myMask[3] = v.y >> 16;
+		const uint4 w = *reinterpret_cast<const uint4*>(gid + base);
+		g[0] = w.x;
+		g[1] = w.y;
+		g[2] = w.z;
+		g[3] = w.w;
+	} else {
 #pragma unroll
-			for (int i = 0; i < kScanItems; ++i)
-				if (base + i < n) myMask[i] = masks[base + i];
-		}
+		for (int i = 0; i < kScanItems; ++i)
+			if (base + i < n) {
+				myMask[i] = masks[base + i];
+				g[i] = gid[base + i];
+			}
 	}
 	u32 words[kScanItems];
 	u64 cnt = 0, wsum = 0;
 #pragma unroll
 	for (int i = 0; i < kScanItems; ++i) {
 		words[i] = 0;
-		if (base + i < n) {
-			const u32 g = gid[base + i];
-			if ((g & kCandidateFlag) && (u32)table[kWide ? 2 * (u64)(g & kGidMask) + 1 : (u64)(g & kGidMask)] == (u32)(base + i)) {
-				u32 k;
-				if constexpr (kPreload)
-					k = __popc(myMask[i] & 0xAAAAu);
-				else
-					k = __popc(masks[base + i] & 0xAAAAu);
-				words[i] = 1 + (leaf ? 2 * k : k);
-				cnt += 1;
-				wsum += words[i];
-			}
+		if (base + i < n && (g[i] & kCandidateFlag) && (u32)table[(u64)(g[i] & kGidMask)] == (u32)(base + i)) {
+			const u32 k = __popc(myMask[i] & 0xAAAAu);
+			words[i] = 1 + (leaf ? 2 * k : k);
+			cnt += 1;
+			wsum += words[i];
 		}
 	}
 	if (base + kScanItems <= n) {
@@ -315,8 +382,9 @@ __global__ void __launch_bounds__(kScanThreads, 8) rankCountKernel(const u64* __
 // whole before anything is added up, so the kernel pays one memory round trip however many tiles there are (a loop of
 // 1024-tile rounds paid one per round: 54 us for the 13.6 K tiles of the 16K^2 terrain's leaf level).
 constexpr int kScanChunk = 16, kScanTilesThreads = 512;  // 8 K tiles per pass
-__global__ void __launch_bounds__(kScanTilesThreads) rankScanTilesKernel(ScanTileState* __restrict__ tiles, u32 numTiles, u64* __restrict__ uniqueCount,
-		u64* __restrict__ wordCount) {
+__global__ void __launch_bounds__(kScanTilesThreads) rankScanTilesKernel(ScanTileState* __restrict__ tiles, const u64* __restrict__ nDev,
+		u64* __restrict__ uniqueCount, u64* __restrict__ wordCount, const u32* __restrict__ overflow) {
+	const u32 numTiles = (*overflow & kOverflowNodes) ? 0u : (u32)((*nDev + kScanTile - 1) / kScanTile);
 	__shared__ u64 sA[32], sB[32];
 	const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	u64 carryA = 0, carryB = 0;
@@ -379,29 +447,20 @@ __global__ void __launch_bounds__(kScanTilesThreads) rankScanTilesKernel(ScanTil
 	}
 }
 
-// kPreload (experimental, CPVS_EXPERIMENTS=rank-preload): the group ids of the thread's four nodes are fetched with one 128-bit
-// load next to the size bytes, instead of one dependent load per unique node after the scan (a round trip off the chain at the
-// price of reading the ids of the nodes that turn out not to be unique).
-template <bool kPreload>
-__global__ void __launch_bounds__(kScanThreads, 8) rankWriteKernel(const unsigned char* __restrict__ sizeOf, const u32* __restrict__ gid, u64 n,
-		const ScanTileState* __restrict__ tiles, u32* __restrict__ firstList, u32* __restrict__ wordOffset, u32* __restrict__ slotOffset) {
+__global__ void __launch_bounds__(kScanThreads, 8) rankWriteKernel(const unsigned char* __restrict__ sizeOf, const u32* __restrict__ gid,
+		const u64* __restrict__ nDev, const ScanTileState* __restrict__ tiles, u32* __restrict__ firstList, u32* __restrict__ wordOffset,
+		u32* __restrict__ slotOffset, const u32* __restrict__ overflow) {
+	const u64 n = (*overflow & kOverflowNodes) ? 0 : *nDev;
 	const u64 base = (u64)blockIdx.x * kScanTile + (u64)threadIdx.x * kScanItems;
+	if ((u64)blockIdx.x * kScanTile >= n) return;  // the grid is sized for the level's capacity
 	u32 g[kScanItems] = {0, 0, 0, 0};
-	if constexpr (kPreload) {
-		if (base + kScanItems <= n) {
-			const uint4 v = *reinterpret_cast<const uint4*>(gid + base);
-			g[0] = v.x;
-			g[1] = v.y;
-			g[2] = v.z;
-			g[3] = v.w;
-		} else {
-#pragma unroll
-			for (int i = 0; i < kScanItems; ++i)
-				if (base + i < n) g[i] = gid[base + i];
-		}
-	}
 	u32 words[kScanItems] = {0, 0, 0, 0};
 	if (base + kScanItems <= n) {
+		const uint4 v = *reinterpret_cast<const uint4*>(gid + base);
+		g[0] = v.x;
+		g[1] = v.y;
+		g[2] = v.z;
+		g[3] = v.w;
 		const u32 packed = *reinterpret_cast<const u32*>(sizeOf + base);
 		words[0] = packed & 0xFFu;
 		words[1] = (packed >> 8) & 0xFFu;
@@ -410,7 +469,10 @@ __global__ void __launch_bounds__(kScanThreads, 8) rankWriteKernel(const unsigne
 	} else {
 #pragma unroll
 		for (int i = 0; i < kScanItems; ++i)
-			if (base + i < n) words[i] = sizeOf[base + i];
+			if (base + i < n) {
+				g[i] = gid[base + i];
+				words[i] = sizeOf[base + i];
+			}
 	}
 	u64 cnt = 0, wsum = 0;
 #pragma unroll
@@ -426,10 +488,7 @@ __global__ void __launch_bounds__(kScanThreads, 8) rankWriteKernel(const unsigne
 		if (words[i]) {
 			firstList[rank] = (u32)(base + i);
 			wordOffset[rank] = (u32)woff;
-			if constexpr (kPreload)
-				slotOffset[g[i] & kGidMask] = (u32)woff;
-			else
-				slotOffset[gid[base + i] & kGidMask] = (u32)woff;
+			slotOffset[g[i] & kGidMask] = (u32)woff;
 			++rank;
 			woff += words[i];
 		}
@@ -443,8 +502,16 @@ __global__ void __launch_bounds__(kSmallThreads) mergeSmallLevelsKernel(SmallMer
 	extern __shared__ __align__(16) u64 sTable[];  // 2 * kSmallMaxNodes slots: probes and atomics stay on chip
 	const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	for (int s = 0; s < a.count; ++s) {
-		const SmallMergeLevel& L = a.lv[s];
-		if (L.n == 1) {
+		SmallMergeLevel L = a.lv[s];
+		const u32 n = (*a.overflow & kOverflowNodes) ? 0u : (u32)*L.nDev;
+		if (n == 0) {
+			if (threadIdx.x == 0) {
+				*L.uniqueCount = 0;
+				*L.wordCount = 0;
+			}
+			continue;
+		}
+		if (n == 1) {
 			if (threadIdx.x == 0) {
 				L.uid[0] = 0;
 				L.slotOffset[0] = 0;
@@ -458,17 +525,17 @@ __global__ void __launch_bounds__(kSmallThreads) mergeSmallLevelsKernel(SmallMer
 		}
 		// table sized to the level (power of two >= 2n), cleared and probed in shared memory
 		u32 slots = 64;
-		while (slots < 2 * L.n) slots <<= 1;
+		while (slots < 2 * n) slots <<= 1;
 		for (u32 i = threadIdx.x; i < slots; i += kSmallThreads) sTable[i] = kEmpty;
 		__syncthreads();
-		for (u32 j = threadIdx.x; j < L.n; j += kSmallThreads)
+		for (u32 j = threadIdx.x; j < n; j += kSmallThreads)
 			L.uid[j] = insertInnerNode<true>(j, L.masks, L.firstChild, L.childUid, sTable, slots - 1, a.errorFlag);
 		__syncthreads();
 		u32 carryC = 0, carryW = 0;
-		for (u32 base = 0; base < L.n; base += kSmallThreads) {
+		for (u32 base = 0; base < n; base += kSmallThreads) {
 			const u32 j = base + threadIdx.x;
 			u32 slot = 0, words = 0;
-			if (j < L.n) {
+			if (j < n) {
 				slot = L.uid[j] & kGidMask;
 				if ((u32)sTable[slot] == j) words = 1 + __popc(L.masks[j] & 0xAAAAu);
 			}
@@ -498,7 +565,7 @@ __global__ void __launch_bounds__(kSmallThreads) mergeSmallLevelsKernel(SmallMer
 				totW += v;
 			}
 			__syncthreads();
-			if (j < L.n && words) {
+			if (j < n && words) {
 				const u32 rank = carryC + beforeC + inclC - 1, woff = carryW + beforeW + inclW - words;
 				L.firstList[rank] = j;
 				L.wordOffset[rank] = woff;
@@ -513,18 +580,6 @@ __global__ void __launch_bounds__(kSmallThreads) mergeSmallLevelsKernel(SmallMer
 		}
 		__syncthreads();
 	}
-}
-
-// A level with a single node (the root, which the reference never merges).
-__global__ void singleNodeKernel(const u16* __restrict__ masks, int leaf, u32* gid, u32* firstList, u32* wordOffset, u32* slotOffset,
-		u64* uniqueCount, u64* wordCount) {
-	const u32 k = __popc(masks[0] & 0xAAAAu);
-	gid[0] = 0;
-	slotOffset[0] = 0;
-	firstList[0] = 0;
-	wordOffset[0] = 0;
-	*uniqueCount = 1;
-	*wordCount = 1 + (leaf ? 2 * k : k);
 }
 
 }  // namespace
@@ -544,52 +599,34 @@ int launchMergeSmallLevels(const SmallMergeArgs& a, cudaStream_t stream) {
 	return 1;
 }
 
-int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* tableMaskDev, int wideSlots, cudaStream_t stream) {
-	if (wideSlots)
-		sizeAndClearLeafTableKernel<true><<<148 * 8, 256, 0, stream>>>(table, maxSlots / 2, setBits, tableMaskDev);
-	else
-		sizeAndClearLeafTableKernel<false><<<148 * 8, 256, 0, stream>>>(table, maxSlots, setBits, tableMaskDev);
-	return 1;
-}
-
-int launchVerifyLeafGroups(const MergeLevelArgs& a, u32* mismatchFlag, cudaStream_t stream) {
-	verifyLeafGroupsKernel<<<(unsigned)((a.n + 255) / 256), 256, 0, stream>>>(a.leafCodes, a.n, a.table, a.uid, mismatchFlag);
+int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* tableMaskDev, cudaStream_t stream) {
+	sizeAndClearLeafTableKernel<<<148 * 8, 256, 0, stream>>>(table, maxSlots, setBits, tableMaskDev);
 	return 1;
 }
 
 int launchInsertLevel(const MergeLevelArgs& a, cudaStream_t stream) {
-	if (a.n == 1) {
-		singleNodeKernel<<<1, 1, 0, stream>>>(a.masks, a.leaf, a.uid, a.firstList, a.wordOffset, a.slotOffset, a.uniqueCount, a.wordCount);
-		return 1;
-	}
-	const unsigned blocks = (unsigned)((a.n + 255) / 256);
-	if (a.leaf && a.fingerprint)
-		insertLeavesFingerprintKernel<<<blocks, 256, 0, stream>>>(a.leafCodes, a.n, a.table, a.tableMaskDev, a.fingerprint == 2 ? 0xFFFull : ~0ull,
-				a.uid, a.errorFlag);
+	if (!a.cap) return 0;
+	const unsigned blocks = (unsigned)((a.cap + 255) / 256);
+	static const int batch = std::getenv("CPVS_LEAF_BATCH") ? std::atoi(std::getenv("CPVS_LEAF_BATCH")) : 0;  // dev switch
+	if (a.leaf && batch == 4)
+		insertLeavesBatchKernel<4><<<(unsigned)((a.cap + 1023) / 1024), 256, 0, stream>>>(a.leafCodes, a.leafHash, a.nDev, a.table, a.tableMaskDev, a.uid, a.errorFlag, a.overflow);
+	else if (a.leaf && batch == 2)
+		insertLeavesBatchKernel<2><<<(unsigned)((a.cap + 511) / 512), 256, 0, stream>>>(a.leafCodes, a.leafHash, a.nDev, a.table, a.tableMaskDev, a.uid, a.errorFlag, a.overflow);
+	else if (a.leaf && batch == 1)
+		insertLeavesBatchKernel<1><<<(unsigned)((a.cap + 255) / 256), 256, 0, stream>>>(a.leafCodes, a.leafHash, a.nDev, a.table, a.tableMaskDev, a.uid, a.errorFlag, a.overflow);
 	else if (a.leaf)
-		insertLeavesKernel<<<blocks, 256, 0, stream>>>(a.leafCodes, a.leafHash, a.n, a.table, a.tableMaskDev, a.uid, a.errorFlag);
-	else if (a.parallelWitness)
-		insertInnerWitnessKernel<<<blocks, 256, 0, stream>>>(a.masks, a.firstChild, a.childUid, a.n, a.table, a.tableSize - 1, a.uid, a.errorFlag);
+		insertLeavesKernel<<<blocks, 256, 0, stream>>>(a.leafCodes, a.leafHash, a.nDev, a.table, a.tableMaskDev, a.uid, a.errorFlag, a.overflow);
 	else
-		insertInnerKernel<<<blocks, 256, 0, stream>>>(a.masks, a.firstChild, a.childUid, a.n, a.table, a.tableSize - 1, a.uid, a.errorFlag);
+		insertInnerKernel<<<blocks, 256, 0, stream>>>(a.masks, a.firstChild, a.childUid, a.nDev, a.table, a.tableSize - 1, a.uid, a.errorFlag, a.overflow);
 	return 1;
 }
 
-int launchRankLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaStream_t stream, cudaEvent_t afterSizes) {
-	if (a.n == 1) return 0;  // done by launchInsertLevel
-	const u32 tiles = (u32)((a.n + kScanTile - 1) / kScanTile);
-	if (a.leaf && a.fingerprint)
-		rankCountKernel<false, true><<<tiles, kScanThreads, 0, stream>>>(a.table, a.masks, a.leaf, a.n, a.uid, a.sizeOf, scan.tiles);
-	else if (a.rankPreload)
-		rankCountKernel<true><<<tiles, kScanThreads, 0, stream>>>(a.table, a.masks, a.leaf, a.n, a.uid, a.sizeOf, scan.tiles);
-	else
-		rankCountKernel<false><<<tiles, kScanThreads, 0, stream>>>(a.table, a.masks, a.leaf, a.n, a.uid, a.sizeOf, scan.tiles);
-	rankScanTilesKernel<<<1, kScanTilesThreads, 0, stream>>>(scan.tiles, tiles, a.uniqueCount, a.wordCount);
-	if (afterSizes) cudaEventRecord(afterSizes, stream);
-	if (a.rankPreload)
-		rankWriteKernel<true><<<tiles, kScanThreads, 0, stream>>>(a.sizeOf, a.uid, a.n, scan.tiles, a.firstList, a.wordOffset, a.slotOffset);
-	else
-		rankWriteKernel<false><<<tiles, kScanThreads, 0, stream>>>(a.sizeOf, a.uid, a.n, scan.tiles, a.firstList, a.wordOffset, a.slotOffset);
+int launchRankLevel(const MergeLevelArgs& a, ScanLaunch scan, cudaStream_t stream) {
+	if (!a.cap) return 0;
+	const u32 tiles = (u32)((a.cap + kScanTile - 1) / kScanTile);
+	rankCountKernel<<<tiles, kScanThreads, 0, stream>>>(a.table, a.masks, a.leaf, a.nDev, a.uid, a.sizeOf, scan.tiles, a.overflow);
+	rankScanTilesKernel<<<1, kScanTilesThreads, 0, stream>>>(scan.tiles, a.nDev, a.uniqueCount, a.wordCount, a.overflow);
+	rankWriteKernel<<<tiles, kScanThreads, 0, stream>>>(a.sizeOf, a.uid, a.nDev, scan.tiles, a.firstList, a.wordOffset, a.slotOffset, a.overflow);
 	return 3;
 }
 

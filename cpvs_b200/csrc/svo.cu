@@ -48,53 +48,64 @@ __device__ __forceinline__ u32 childmaskLevel0(const float* __restrict__ depth, 
 
 // ---- node counts per level, for exact allocation (closed form of the classification) ------------
 // A level-l node exists for every voxel (x,y,z) of pyramid level l+1 that classifies PARTIAL:
-// !(z+1 <= min*H) && !(z >= max*H)  <=>  floor(min*H) <= z <= ceil(max*H)-1, inside the z-tile.
+// !(z+1 <= min*H) && !(z >= max*H)  <=>  floor(min*H) <= z <= ceil(max*H)-1. Slice s of the column owns the voxels
+// s*side .. s*side+side-1 (side = that level's width), so one pass over the pyramid counts every slice at once.
 struct CountLevels {
 	const float2* texels[kMaxLevels];  // pyramid level l+1 for node level l
 	u64 numTexels[kMaxLevels];
-	float heightF[kMaxLevels], zLoF[kMaxLevels], zHiF[kMaxLevels];
+	float heightF[kMaxLevels];  // side * zTileNum
+	u32 sideShift[kMaxLevels];  // log2(side)
 	int minLevel;
 	int topCounted;  // level of the root's children
-	u32 rootZ;       // z of the root's first child slab (2 * zTileIndex)
+	u32 zTileNum;
 	u32 blockStart[kMaxLevels + 1];  // [minLevel + i] = first block of level minLevel + i; blocks per level follow its size
 };
+constexpr u32 kCountSharedSlices = 2048;
 // All levels are counted by one launch; a level owns the blocks blockStart[level] .. blockStart[level + 1] - 1 (a grid of
 // levels x the widest level's blocks spent more time dispatching the empty blocks of the small levels than counting).
 __global__ void __launch_bounds__(256) countNodesKernel(CountLevels p, u64* __restrict__ counts) {
-	// A z-slice that misses the surface has no node below the root (most slices of a tall tile grid): every
-	// CTA sees that from the four texels under the root and leaves. CTA (0,0) also reports the root's mask,
-	// which is the whole DAG of such a slice.
-	{
+	__shared__ u32 sSlice[kCountSharedSlices];
+	__shared__ u64 sWarp[8];
+	// CTA 0 also reports every slice's root mask, which is the whole DAG of a slice that misses the surface.
+	if (blockIdx.x == 0) {
 		const float2* __restrict__ under = p.texels[p.topCounted];
-		const float h = p.heightF[p.topCounted], zLo = p.zLoF[p.topCounted], zHi = p.zHiF[p.topCounted];
-		bool any = false;
-#pragma unroll
-		for (int i = 0; i < 4; ++i) {
-			const float2 t = under[i];
-			const float lo = fmaxf(floorf(__fmul_rn(t.x, h)), zLo);
-			const float hi = fminf(__fadd_rn(ceilf(__fmul_rn(t.y, h)), -1.0f), zHi);
-			any |= hi >= lo;
-		}
-		if (blockIdx.x == 0 && threadIdx.x == 0)
-			counts[kRootMaskScalar] = (1ull << 32) | childmaskInner(under, 2u, h, 0u, 0u, p.rootZ);
-		if (!any) return;
+		for (u32 z = threadIdx.x; z < p.zTileNum; z += blockDim.x)
+			counts[(u64)z * kMaxLevels + kRootMaskScalar] = (1ull << 32) | childmaskInner(under, 2u, p.heightF[p.topCounted], 0u, 0u, z * 2u);
 	}
 	int level = p.minLevel;
 	while (level < p.topCounted && blockIdx.x >= p.blockStart[level + 1]) ++level;
 	const u32 block = blockIdx.x - p.blockStart[level], blocks = p.blockStart[level + 1] - p.blockStart[level];
 	const float2* __restrict__ texels = p.texels[level];
 	const u64 numTexels = p.numTexels[level];
-	const float heightF = p.heightF[level], zLoF = p.zLoF[level], zHiF = p.zHiF[level];
+	const float heightF = p.heightF[level], topF = __fadd_rn(heightF, -1.0f);
+	const u32 shift = p.sideShift[level], side = 1u << shift;
+	const bool single = p.zTileNum == 1, shared = p.zTileNum <= kCountSharedSlices;
+	if (!single && shared) {
+		for (u32 i = threadIdx.x; i < p.zTileNum; i += blockDim.x) sSlice[i] = 0;
+		__syncthreads();
+	}
 	u64 local = 0;
 	// two texels per 128-bit load (every counted level has an even number of texels), two loads in flight per thread
 	const float4* __restrict__ pairs = reinterpret_cast<const float4*>(texels);
 	const u64 numPairs = numTexels >> 1, stride = (u64)blocks * blockDim.x;
 	auto add = [&](float mn, float mx) {
 		const float a = __fmul_rn(mn, heightF), b = __fmul_rn(mx, heightF);
-		// fmaxf/fminf drop a NaN operand: a NaN bound makes every z of the tile PARTIAL, as in the reference
-		const float lo = fmaxf(floorf(a), zLoF);
-		const float hi = fminf(__fadd_rn(ceilf(b), -1.0f), zHiF);
-		if (hi >= lo) local += (u64)(hi - lo) + 1ull;
+		// fmaxf/fminf drop a NaN operand: a NaN bound makes every z of the column PARTIAL, as in the reference
+		const float lo = fmaxf(floorf(a), 0.0f);
+		const float hi = fminf(__fadd_rn(ceilf(b), -1.0f), topF);
+		if (!(hi >= lo)) return;
+		if (single) {
+			local += (u64)(hi - lo) + 1ull;
+			return;
+		}
+		const u32 zl = (u32)lo, zh = (u32)hi;
+		for (u32 s = zl >> shift; s <= (zh >> shift); ++s) {  // one or two slices for a surface, many across a box edge
+			const u32 from = max(zl, s << shift), to = min(zh, (s << shift) + side - 1u);
+			if (shared)
+				atomicAdd(&sSlice[s], to - from + 1u);
+			else
+				atomicAdd(reinterpret_cast<unsigned long long*>(counts + (u64)s * kMaxLevels + level), (unsigned long long)(to - from + 1u));
+		}
 	};
 	u64 i = (u64)block * blockDim.x + threadIdx.x;
 	for (; i + stride < numPairs; i += 2 * stride) {
@@ -109,15 +120,20 @@ __global__ void __launch_bounds__(256) countNodesKernel(CountLevels p, u64* __re
 		add(t.x, t.y);
 		add(t.z, t.w);
 	}
+	if (single) {
 #pragma unroll
-	for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, d);
-	__shared__ u64 sWarp[8];
-	if ((threadIdx.x & 31) == 0) sWarp[threadIdx.x >> 5] = local;
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		u64 total = 0;
-		for (int w = 0; w < (int)(blockDim.x >> 5); ++w) total += sWarp[w];
-		if (total) atomicAdd(reinterpret_cast<unsigned long long*>(counts + level), (unsigned long long)total);
+		for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, d);
+		if ((threadIdx.x & 31) == 0) sWarp[threadIdx.x >> 5] = local;
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			u64 total = 0;
+			for (int w = 0; w < (int)(blockDim.x >> 5); ++w) total += sWarp[w];
+			if (total) atomicAdd(reinterpret_cast<unsigned long long*>(counts + level), (unsigned long long)total);
+		}
+	} else if (shared) {
+		__syncthreads();
+		for (u32 s = threadIdx.x; s < p.zTileNum; s += blockDim.x)
+			if (sSlice[s]) atomicAdd(reinterpret_cast<unsigned long long*>(counts + (u64)s * kMaxLevels + level), (unsigned long long)sSlice[s]);
 	}
 }
 
@@ -126,16 +142,14 @@ __global__ void __launch_bounds__(256) countNodesKernel(CountLevels p, u64* __re
 // chain better than 256-thread ones.)
 constexpr int kExpandThreads = 128;
 constexpr int kExpandTile = kExpandThreads * kScanItems;
-// kPreloadBias (experimental, CPVS_EXPERIMENTS=expand-preload): when the children are leaves built per column, the plain
-// loop below reads colBias for one child, waits, stores, and only then reads it for the next -- up to 4 x 8 dependent
-// round trips per thread. The children of a node sit in just four columns, (x, y) .. (x+1, y+1) with x even, so two 8-byte
-// loads per node fetch every bias it needs; the variant issues them for the thread's four nodes back to back before the
-// first store.
-template <bool kPreloadBias>
-__device__ __forceinline__ void expandLevelBody(const float* __restrict__ tex, u32 side, float heightF, int level0,
-		const u64* __restrict__ coords, u64 n, u16* __restrict__ masks, u32* __restrict__ firstChild, u64* __restrict__ childCoords,
-		u64* __restrict__ childTotal, ScanLaunch scan, u32 numTiles, const u32* __restrict__ colBias, u32* __restrict__ leafAt, u32 numLeaves) {
+__global__ void __launch_bounds__(kExpandThreads) expandLevelKernel(const float* __restrict__ tex, u32 side, float heightF, int level0,
+		const u64* __restrict__ coords, const u64* __restrict__ nDev, u16* __restrict__ masks, u32* __restrict__ firstChild,
+		u64* __restrict__ childCoords, u64 childCap, u64* __restrict__ childN, u32* __restrict__ overflow, ScanLaunch scan,
+		const u32* __restrict__ colBias, u32* __restrict__ leafAt) {
+	const u64 n = *nDev;
+	const u32 numTiles = (u32)((n + kExpandTile - 1) / kExpandTile);
 	const u32 tile = scanAcquireTile(scan);
+	if (tile >= numTiles) return;  // the grid is sized for the level's capacity
 	const u64 base = (u64)tile * kExpandTile + (u64)threadIdx.x * kScanItems;
 	u64 c[kScanItems];
 	u32 m[kScanItems];
@@ -157,42 +171,12 @@ __device__ __forceinline__ void expandLevelBody(const float* __restrict__ tex, u
 	blockExclusiveScan2<kExpandThreads>(pre, dummy, tot, totDummy);
 	u64 tilePre, tilePreB;
 	scanLookback2(scan, tile, tot, 0, tilePre, tilePreB);
-	if (tile == numTiles - 1 && threadIdx.x == 0) *childTotal = tilePre + tot;
-	u64 pos = tilePre + pre;
-	if constexpr (kPreloadBias) {
-		if (leafAt) {
-			uint2 row0[kScanItems], row1[kScanItems];  // colBias of columns (x, y), (x+1, y) and (x, y+1), (x+1, y+1)
-#pragma unroll
-			for (int i = 0; i < kScanItems; ++i) {
-				row0[i] = row1[i] = make_uint2(0u, 0u);
-				if (base + i < n && (m[i] & 0xAAAAu)) {
-					u32 x, y, z;
-					unpackCoord(c[i], x, y, z);  // x is even (child coordinates are doubled) and so is side: 8-byte aligned
-					row0[i] = *reinterpret_cast<const uint2*>(colBias + (size_t)y * side + x);
-					row1[i] = *reinterpret_cast<const uint2*>(colBias + (size_t)(y + 1) * side + x);
-				}
-			}
-#pragma unroll
-			for (int i = 0; i < kScanItems; ++i) {
-				if (base + i >= n) break;
-				masks[base + i] = (u16)m[i];
-				firstChild[base + i] = (u32)pos;
-				u32 partial = m[i] & 0xAAAAu;
-				if (partial) {
-					const u32 z = (u32)(c[i] >> 40);
-					while (partial) {
-						const u32 child = (__ffs(partial) - 1) >> 1;
-						partial &= partial - 1;
-						const uint2 row = (child & 2u) ? row1[i] : row0[i];
-						const u32 at = ((child & 1u) ? row.y : row.x) + z + (child >> 2);
-						if (at < numLeaves) leafAt[at] = (u32)pos;
-						++pos;
-					}
-				}
-			}
-			return;
-		}
+	if (tile == numTiles - 1 && threadIdx.x == 0) {
+		const u64 total = tilePre + tot;
+		*childN = total < childCap ? total : childCap;
+		if (total > childCap) atomicOr(overflow, kOverflowNodes);
 	}
+	u64 pos = tilePre + pre;
 #pragma unroll
 	for (int i = 0; i < kScanItems; ++i) {
 		if (base + i >= n) break;
@@ -208,7 +192,7 @@ __device__ __forceinline__ void expandLevelBody(const float* __restrict__ tex, u
 					partial &= partial - 1;
 					// (positions are in range whenever the pyramid is ordered; a NaN-ridden map fails the count check instead)
 					const u32 at = colBias[(size_t)(y + ((child >> 1) & 1u)) * side + x + (child & 1u)] + z + (child >> 2);
-					if (at < numLeaves) leafAt[at] = (u32)pos;
+					if (at < childCap && pos < childCap) leafAt[at] = (u32)pos;
 					++pos;
 				}
 				continue;
@@ -216,21 +200,11 @@ __device__ __forceinline__ void expandLevelBody(const float* __restrict__ tex, u
 			while (partial) {  // ascending child index (cs::getChildCoordinates, Util.cpp:101-117)
 				const u32 child = (__ffs(partial) - 1) >> 1;
 				partial &= partial - 1;
-				childCoords[pos++] = packCoord((x + (child & 1u)) * 2u, (y + ((child >> 1) & 1u)) * 2u, (z + (child >> 2)) * 2u);
+				if (pos < childCap) childCoords[pos] = packCoord((x + (child & 1u)) * 2u, (y + ((child >> 1) & 1u)) * 2u, (z + (child >> 2)) * 2u);
+				++pos;
 			}
 		}
 	}
-}
-
-__global__ void __launch_bounds__(kExpandThreads) expandLevelKernel(const float* __restrict__ tex, u32 side, float heightF, int level0,
-		const u64* __restrict__ coords, u64 n, u16* __restrict__ masks, u32* __restrict__ firstChild, u64* __restrict__ childCoords,
-		u64* __restrict__ childTotal, ScanLaunch scan, u32 numTiles, const u32* __restrict__ colBias, u32* __restrict__ leafAt, u32 numLeaves) {
-	expandLevelBody<false>(tex, side, heightF, level0, coords, n, masks, firstChild, childCoords, childTotal, scan, numTiles, colBias, leafAt, numLeaves);
-}
-__global__ void __launch_bounds__(kExpandThreads) expandLevelPreloadKernel(const float* __restrict__ tex, u32 side, float heightF, int level0,
-		const u64* __restrict__ coords, u64 n, u16* __restrict__ masks, u32* __restrict__ firstChild, u64* __restrict__ childCoords,
-		u64* __restrict__ childTotal, ScanLaunch scan, u32 numTiles, const u32* __restrict__ colBias, u32* __restrict__ leafAt, u32 numLeaves) {
-	expandLevelBody<true>(tex, side, heightF, level0, coords, n, masks, firstChild, childCoords, childTotal, scan, numTiles, colBias, leafAt, numLeaves);
 }
 
 // The top of the octree: levels of at most kSmallMaxNodes nodes are a chain of tiny dependent steps.
@@ -239,6 +213,7 @@ __global__ void __launch_bounds__(kSmallThreads) expandSmallLevelsKernel(SmallEx
 	__shared__ u32 sWarp[kSmallThreads / 32];
 	const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	u32 n = 1;  // the first level is the root
+	if (threadIdx.x == 0) *a.rootN = 1;
 	for (int s = 0; s < a.count; ++s) {
 		const SmallExpandLevel& L = a.lv[s];
 		u32 carry = 0;
@@ -283,16 +258,21 @@ __global__ void __launch_bounds__(kSmallThreads) expandSmallLevelsKernel(SmallEx
 						partial &= partial - 1;
 						if (L.leafAt) {
 							const u32 at = L.colBias[(size_t)(y + ((child >> 1) & 1u)) * L.side + x + (child & 1u)] + z + (child >> 2);
-							if (at < L.numLeaves) L.leafAt[at] = pos;
-							++pos;
-						} else
-							L.childCoords[pos++] = packCoord((x + (child & 1u)) * 2u, (y + ((child >> 1) & 1u)) * 2u, (z + (child >> 2)) * 2u);
+							if (at < L.childCap && pos < L.childCap) L.leafAt[at] = pos;
+						} else if (pos < L.childCap) {
+							L.childCoords[pos] = packCoord((x + (child & 1u)) * 2u, (y + ((child >> 1) & 1u)) * 2u, (z + (child >> 2)) * 2u);
+						}
+						++pos;
 					}
 				}
 			}
 			carry += total;
 		}
-		if (threadIdx.x == 0) *L.childTotal = carry;
+		if (carry > L.childCap) {
+			if (threadIdx.x == 0) atomicOr(a.overflow, kOverflowNodes);
+			carry = L.childCap;
+		}
+		if (threadIdx.x == 0) *L.childN = carry;
 		n = carry;
 		__syncthreads();  // the next level reads the coordinates written above
 	}
@@ -330,11 +310,13 @@ __device__ __forceinline__ u32 litCountBits(float depth, float heightF, float zc
 constexpr int kLeavesPerCta = 256;
 
 __global__ void __launch_bounds__(256, 8) buildLeavesKernel(const float* __restrict__ depth, u32 n, float heightF, const float2* __restrict__ level3,
-		const u64* __restrict__ coords, u64 numLeaves, u32* __restrict__ codes, u64* __restrict__ hashes, u16* __restrict__ masks,
+		const u64* __restrict__ coords, const u64* __restrict__ nDev, u32* __restrict__ codes, u64* __restrict__ hashes, u16* __restrict__ masks,
 		u32* __restrict__ bitmap, u32 bitmapWordMask) {
 	__shared__ __align__(16) u32 sCode[kLeavesPerCta][8];
 	__shared__ u64 sCoord[kLeavesPerCta];
+	const u64 numLeaves = *nDev;
 	const u64 ctaBase = (u64)blockIdx.x * kLeavesPerCta;
+	if (ctaBase >= numLeaves) return;  // the grid is sized for the level's capacity
 	const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	const u32 row = lane & 7u, which = lane >> 3;
 	sCoord[threadIdx.x] = coords[min(ctaBase + threadIdx.x, numLeaves - 1)];
@@ -658,46 +640,21 @@ int launchChildmask(const PyramidView& pyr, int level, u32 zTileNum, u32 x, u32 
 	return 1;
 }
 
-namespace {
-// One thread per z-slice of the column: does the slice reach below the root, and the root's mask.
-__global__ void columnRootsKernel(const float2* __restrict__ under, float heightF, u32 zTileNum, u64* __restrict__ out) {
-	const u32 z = blockIdx.x * blockDim.x + threadIdx.x;
-	if (z >= zTileNum) return;
-	const float zLo = (float)(z * 2u), zHi = (float)(z * 2u + 1u);
-	bool any = false;
-#pragma unroll
-	for (int i = 0; i < 4; ++i) {
-		const float2 t = under[i];
-		const float lo = fmaxf(floorf(__fmul_rn(t.x, heightF)), zLo);
-		const float hi = fminf(__fadd_rn(ceilf(__fmul_rn(t.y, heightF)), -1.0f), zHi);
-		any |= hi >= lo;
-	}
-	out[z] = ((u64)(any ? 1u : 0u) << 32) | childmaskInner(under, 2u, heightF, 0u, 0u, z * 2u);
-}
-
-}  // namespace
-
-int launchColumnRoots(const PyramidView& pyr, u32 zTileNum, u64* out, cudaStream_t stream) {
-	const int top = pyr.numLevels - 2;  // 2 x 2 texels under the root
-	columnRootsKernel<<<(zTileNum + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const float2*>(pyr.level[top]), (float)(2u * zTileNum), zTileNum, out);
-	return 1;
-}
-
-int launchCountNodes(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, int minLevel, u64* counts, cudaStream_t stream) {
+int launchColumnCounts(const PyramidView& pyr, u32 zTileNum, int minLevel, u64* counts, cudaStream_t stream) {
 	const int numCounted = pyr.numLevels - 2 - minLevel;  // levels minLevel .. numLevels-3
 	if (numCounted <= 0) return 0;
 	CountLevels p;
 	p.minLevel = minLevel;
 	p.topCounted = pyr.numLevels - 3;
-	p.rootZ = zTileIndex * 2;
+	p.zTileNum = zTileNum;
 	u32 totalBlocks = 0;
 	for (int level = minLevel; level <= pyr.numLevels - 3; ++level) {
 		const u32 side = (u32)pyr.n >> (level + 1);
 		p.texels[level] = reinterpret_cast<const float2*>(pyr.level[level + 1]);
 		p.numTexels[level] = (u64)side * side;
 		p.heightF[level] = (float)(side * zTileNum);
-		p.zLoF[level] = (float)(zTileIndex * side);
-		p.zHiF[level] = (float)(zTileIndex * side + side - 1);
+		p.sideShift[level] = 0;
+		while ((1u << p.sideShift[level]) < side) ++p.sideShift[level];
 		u64 blocks = (p.numTexels[level] + 256 * 8 - 1) / (256 * 8);  // two passes of two 2-texel loads per thread
 		if (blocks > 148 * 8) blocks = 148 * 8;
 		p.blockStart[level] = totalBlocks;
@@ -714,25 +671,23 @@ int launchExpandSmallLevels(const SmallExpandArgs& a, cudaStream_t stream) {
 	return 1;
 }
 
-int launchExpandLevel(const PyramidView& pyr, int level, u32 zTileNum, const u64* coords, u64 n, u16* masks, u32* firstChild,
-		u64* childCoords, u64* childTotal, ScanLaunch scan, const u32* colBias, u32* leafAt, u32 numLeaves, int preloadBias, cudaStream_t stream) {
+int launchExpandLevel(const PyramidView& pyr, int level, u32 zTileNum, const u64* coords, const u64* nDev, u64 cap, u16* masks, u32* firstChild,
+		u64* childCoords, u64 childCap, u64* childN, u32* overflow, ScanLaunch scan, const u32* colBias, u32* leafAt, cudaStream_t stream) {
 	const u32 side = (u32)pyr.n >> level;
 	const float heightF = (float)(side * zTileNum);
-	const u32 tiles = (u32)((n + kExpandTile - 1) / kExpandTile);
-	if (preloadBias && leafAt)
-		expandLevelPreloadKernel<<<tiles, kExpandThreads, 0, stream>>>(pyr.level[level], side, heightF, level == 0 ? 1 : 0, coords, n, masks,
-				firstChild, childCoords, childTotal, scan, tiles, colBias, leafAt, numLeaves);
-	else
-		expandLevelKernel<<<tiles, kExpandThreads, 0, stream>>>(pyr.level[level], side, heightF, level == 0 ? 1 : 0, coords, n, masks, firstChild,
-				childCoords, childTotal, scan, tiles, colBias, leafAt, numLeaves);
+	const u32 tiles = (u32)((cap + kExpandTile - 1) / kExpandTile);
+	if (!tiles) return 0;
+	expandLevelKernel<<<tiles, kExpandThreads, 0, stream>>>(pyr.level[level], side, heightF, level == 0 ? 1 : 0, coords, nDev, masks, firstChild,
+			childCoords, childCap, childN, overflow, scan, colBias, leafAt);
 	return 1;
 }
 
-int launchBuildLeaves(const PyramidView& pyr, u32 zTileNum, const u64* coords, u64 n, u32* codes, u64* hashes, u16* masks, u32* sketch,
-		cudaStream_t stream) {
+int launchBuildLeaves(const PyramidView& pyr, u32 zTileNum, const u64* coords, const u64* nDev, u64 cap, u32* codes, u64* hashes, u16* masks,
+		u32* sketch, cudaStream_t stream) {
 	const float heightF = (float)((u32)pyr.n * zTileNum);
-	buildLeavesKernel<<<(unsigned)((n + kLeavesPerCta - 1) / kLeavesPerCta), 256, 0, stream>>>(pyr.level[0], (u32)pyr.n, heightF,
-			reinterpret_cast<const float2*>(pyr.level[3]), coords, n, codes, hashes, masks, sketch, kSketchWords - 1);
+	if (!cap) return 0;
+	buildLeavesKernel<<<(unsigned)((cap + kLeavesPerCta - 1) / kLeavesPerCta), 256, 0, stream>>>(pyr.level[0], (u32)pyr.n, heightF,
+			reinterpret_cast<const float2*>(pyr.level[3]), coords, nDev, codes, hashes, masks, sketch, kSketchWords - 1);
 	return 1;
 }
 

@@ -2,7 +2,9 @@
 // render + read-back of the reference (src/ShadowMap.cpp:23-30, src/DeferredRenderer.cpp:173-177) so a
 // tile-grid build never leaves the GPU. The scenes are defined once in synth/scene.h; the bytes
 // written here equal the host generator's (plane: IEEE mul/div/add in the same order, no FMA; city:
-// a min over the same box list). The terrain scene uses the host libm and has no device twin.
+// a min over the same box list; terrain_dev: synth/scene.h's terrainDevDepth compiled for both sides). SURVEY.md's own
+// terrain uses the host libm and has no device twin.
+#include "../synth/scene.h"
 #include "kernels.h"
 
 namespace cpvs {
@@ -26,6 +28,24 @@ __global__ void __launch_bounds__(kGenThreads) planeDepthKernel(float* __restric
 		v.z = __fadd_rn(__fadd_rn(0.3f, __fdiv_rn(__fmul_rn(0.4f, (float)(gx0 + x + 2)), fN)), fy);
 		v.w = __fadd_rn(__fadd_rn(0.3f, __fdiv_rn(__fmul_rn(0.4f, (float)(gx0 + x + 3)), fN)), fy);
 		__stcs(reinterpret_cast<float4*>(out + (size_t)y * n + x), v);
+	}
+}
+
+__global__ void __launch_bounds__(kGenThreads) terrainDevDepthKernel(float* __restrict__ out, int n, long long gx0, long long gy0, float fN) {
+	const int x = (blockIdx.x * kGenTileW) + (threadIdx.x & 31) * 4;
+	const int yBase = blockIdx.y * kGenTileH + (threadIdx.x >> 5) * 4;
+	if (x >= n) return;
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		const int y = yBase + j;
+		if (y >= n) break;
+		const float v = __fdiv_rn((float)(gy0 + y), fN);
+		float4 d;
+		d.x = cpvs_synth::terrainDevDepth(__fdiv_rn((float)(gx0 + x + 0), fN), v);
+		d.y = cpvs_synth::terrainDevDepth(__fdiv_rn((float)(gx0 + x + 1), fN), v);
+		d.z = cpvs_synth::terrainDevDepth(__fdiv_rn((float)(gx0 + x + 2), fN), v);
+		d.w = cpvs_synth::terrainDevDepth(__fdiv_rn((float)(gx0 + x + 3), fN), v);
+		__stcs(reinterpret_cast<float4*>(out + (size_t)y * n + x), d);
 	}
 }
 
@@ -97,6 +117,12 @@ __global__ void __launch_bounds__(kGenThreads) cityDepthKernel(float* __restrict
 int launchPlaneDepth(float* out, int n, long long gx0, long long gy0, long long gn, cudaStream_t stream) {
 	const dim3 grid((n + kGenTileW - 1) / kGenTileW, (n + kGenTileH - 1) / kGenTileH);
 	planeDepthKernel<<<grid, kGenThreads, 0, stream>>>(out, n, gx0, gy0, (float)gn);
+	return 1;
+}
+
+int launchTerrainDevDepth(float* out, int n, long long gx0, long long gy0, long long gn, cudaStream_t stream) {
+	const dim3 grid((n + kGenTileW - 1) / kGenTileW, (n + kGenTileH - 1) / kGenTileH);
+	terrainDevDepthKernel<<<grid, kGenThreads, 0, stream>>>(out, n, gx0, gy0, (float)gn);
 	return 1;
 }
 

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libcpvs_synth.so")
 _lib = None
 
-KINDS = {"plane": 0, "terrain": 1, "city": 2}
+KINDS = {"plane": 0, "terrain": 1, "city": 2, "terrain_dev": 3}
 
 
 def build(force=False):

@@ -4,11 +4,48 @@
  */
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
+
+#if defined(__CUDACC__)
+#define CPVS_SYNTH_HD __host__ __device__
+#else
+#define CPVS_SYNTH_HD
+#endif
 
 namespace cpvs_synth {
 
-enum { kPlane = 0, kTerrain = 1, kCity = 2 };
+/* kTerrain is SURVEY.md 8d's height field verbatim (sinf/cosf of the host libm: host generator only, its digests are tied
+ * to the build container's glibc). kTerrainDev is the same formula on sinDet/cosDet below -- plain IEEE float arithmetic in
+ * a fixed order, no FMA -- so the host generator (g++ -ffp-contract=off) and the CUDA generator (--fmad=false) write
+ * the same bytes and a tile grid never has to be copied to the device. */
+enum { kPlane = 0, kTerrain = 1, kCity = 2, kTerrainDev = 3 };
+
+/* sin and cos for |x| < 2^15: Cody-Waite reduction by pi/2 split into three floats (the first with 8 significant bits, so
+ * k * kPiHalf1 is exact), then the cephes single-precision polynomials on [-pi/4, pi/4]. Accurate to a few ulp, which is
+ * all a synthetic scene needs; what matters is that every operation is a single correctly rounded IEEE one. */
+CPVS_SYNTH_HD inline void sinCosDet(float x, float* s, float* c) {
+	const float kf = floorf(x * 0.636619772f + 0.5f);
+	float r = x - kf * 1.5703125f;
+	r = r - kf * 4.837512969970703125e-4f;
+	r = r - kf * 7.54978995489188216e-8f;
+	const float z = r * r;
+	const float sp = r + r * z * (-1.6666654611e-1f + z * (8.3321608736e-3f + z * -1.9515295891e-4f));
+	const float cp = (1.0f - 0.5f * z) + z * z * (4.166664568298827e-2f + z * (-1.388731625493765e-3f + z * 2.443315711809948e-5f));
+	const int q = static_cast<int>(kf) & 3;
+	*s = q == 0 ? sp : (q == 1 ? cp : (q == 2 ? -sp : -cp));
+	*c = q == 0 ? cp : (q == 1 ? -sp : (q == 2 ? -cp : sp));
+}
+
+/* Depth of the device-generatable terrain at (u, v) in [0,1)^2 of the virtual map. */
+CPVS_SYNTH_HD inline float terrainDevDepth(float u, float v) {
+	float s1, c1, s2, c2, s3, c3, s4, c4;
+	sinCosDet(9.1f * u, &s1, &c1);
+	sinCosDet(7.3f * v, &s2, &c2);
+	sinCosDet(41.f * u + 3.f * v, &s3, &c3);
+	sinCosDet(97.f * v - 11.f * u, &s4, &c4);
+	return 0.5f + 0.15f * s1 * c2 + 0.05f * s3 + 0.02f * c4;
+}
 constexpr uint32_t kMapSeed = 12345u;
 constexpr float kCityFarPlane = 0.9f;
 

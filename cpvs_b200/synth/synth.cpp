@@ -7,6 +7,7 @@
  *
  *   plane   - tilted ground as seen from the default light direction (reference src/main.cpp:35)
  *   terrain - smooth height field with three octaves (sinf/cosf: results depend on the host libm)
+ *   terrain_dev - the same height field on the deterministic sin/cos of scene.h: byte-identical to the CUDA generator
  *   city    - far plane at 0.9 with N/8 random axis-aligned boxes (xorshift32, seed 12345; libm-free)
  *
  * A tile (tx,ty) of a tilesPerSide x tilesPerSide virtual map samples the same function at the
@@ -46,7 +47,12 @@ void parallelRows(int n, int threads, F rowFn) {
 
 extern "C" {
 
-enum { CPVS_SYNTH_PLANE = cpvs_synth::kPlane, CPVS_SYNTH_TERRAIN = cpvs_synth::kTerrain, CPVS_SYNTH_CITY = cpvs_synth::kCity };
+enum {
+	CPVS_SYNTH_PLANE = cpvs_synth::kPlane,
+	CPVS_SYNTH_TERRAIN = cpvs_synth::kTerrain,
+	CPVS_SYNTH_CITY = cpvs_synth::kCity,
+	CPVS_SYNTH_TERRAIN_DEV = cpvs_synth::kTerrainDev
+};
 
 /* out: n*n floats. (tx,ty,tilesPerSide) select a window of the virtual map; (0,0,1) is the whole map. */
 int cpvs_synth_depth(int kind, int n, int tx, int ty, int tilesPerSide, int threads, float* out) {
@@ -72,6 +78,14 @@ int cpvs_synth_depth(int kind, int n, int tx, int ty, int tilesPerSide, int thre
 				row[x] = 0.5f + 0.15f * sinf(9.1f * u) * cosf(7.3f * v) + 0.05f * sinf(41.f * u + 3.f * v) +
 						 0.02f * cosf(97.f * v - 11.f * u);
 			}
+		});
+		return 0;
+	}
+	if (kind == CPVS_SYNTH_TERRAIN_DEV) {
+		parallelRows(n, threads, [=](int y) {
+			float* row = out + static_cast<size_t>(y) * n;
+			const float v = (float)(gy0 + y) / fN;
+			for (int x = 0; x < n; ++x) row[x] = cpvs_synth::terrainDevDepth((float)(gx0 + x) / fN, v);
 		});
 		return 0;
 	}

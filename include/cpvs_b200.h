@@ -53,16 +53,16 @@ extern "C" {
 
 /* Phases of cpvs_shadow_create timed with CUDA events on the context's stream (cpvs_shadow_info.phase_ms).
  * Phases marked (1 kernel) bracket exactly one kernel launch. */
-#define CPVS_PHASE_COUNT 0        /* closed-form node counts per level + host read-back */
+#define CPVS_PHASE_COUNT 0        /* closed-form node counts of the column + host read-back (absent when sizes are predicted or cached) */
 #define CPVS_PHASE_EXPAND 1       /* breadth-first expansion of all inner levels */
 #define CPVS_PHASE_LEAVES 2       /* leaf build (1 kernel) */
 #define CPVS_PHASE_LEAF_TABLE 3   /* leaf level: distinct-count sketch read-out, table sizing + clear */
 #define CPVS_PHASE_LEAF_INSERT 4  /* leaf level: hash-table insert (1 kernel) */
 #define CPVS_PHASE_LEAF_RESOLVE 5 /* leaf level: rank scan (1 kernel) on a side stream, concurrent with phase 6 */
 #define CPVS_PHASE_INNER_MERGE 6  /* inner levels: inserts on the main stream (rank scans beside them), join */
-#define CPVS_PHASE_BASES 7        /* level bases + host read-back of sizes */
-#define CPVS_PHASE_EMIT_INNER 8   /* whole emission: inner levels on the main stream, leaves on a side stream */
-#define CPVS_PHASE_EMIT_LEAVES 9  /* compressed leaves (1 kernel); runs concurrently, inside phase 8 */
+#define CPVS_PHASE_BASES 7        /* level bases (+ host read-back of sizes when the DAG's allocation was not predicted) */
+#define CPVS_PHASE_EMIT_INNER 8   /* emission after the bases: inner levels (and the leaves, unless they were written during the merge) */
+#define CPVS_PHASE_EMIT_LEAVES 9  /* compressed leaves (1 kernel); concurrent with phase 6 (predicted allocation) or inside phase 8 */
 #define CPVS_NUM_PHASES 10
 
 /* Grid sentinels written by CompressedShadowContainer::createTopLevelGrid
@@ -91,6 +91,19 @@ CPVS_API uint64_t cpvs_ctx_launch_count(const cpvs_ctx* ctx);
  * paying a fresh device allocation inside the build. Optional; HBM is 180 GB, a 4x4x4 grid of 16K^2 terrain
  * tiles keeps 3.8 GB of DAG words. */
 CPVS_API int cpvs_ctx_reserve(cpvs_ctx* ctx, uint64_t bytes);
+/* cpvs_shadow_create sizes a build from the previous build of the same shape (side, z tile, leafmasks) on this context:
+ * scratch, grids and the DAG's allocation come from those numbers plus head room (predicted + predicted >> headroom_shift),
+ * so the build runs without asking the device for sizes first. Every kernel stays inside its capacities; a build that
+ * outgrows them is redone with exact counts, so results never depend on the prediction. enabled = 0 always counts first.
+ * Defaults: enabled, headroom_shift 3 (CPVS_PREDICT / CPVS_HEADROOM_SHIFT in the environment override them at creation). */
+CPVS_API int cpvs_ctx_set_prediction(cpvs_ctx* ctx, int enabled, uint32_t headroom_shift);
+typedef struct cpvs_ctx_stats {
+	uint64_t predicted_builds;  /* builds started on predicted sizes */
+	uint64_t exact_builds;      /* builds that counted first (incl. the rebuilds below) */
+	uint64_t overflow_rebuilds; /* predicted builds that outgrew a node capacity and were redone */
+	uint64_t reemissions;       /* builds whose predicted DAG allocation was too small: emitted again into an exact one */
+} cpvs_ctx_stats;
+CPVS_API int cpvs_ctx_get_stats(const cpvs_ctx* ctx, cpvs_ctx_stats* out);
 /* Message for the last non-OK status on the calling thread. */
 CPVS_API const char* cpvs_last_error(void);
 CPVS_API const char* cpvs_version(void);
@@ -126,7 +139,7 @@ typedef struct cpvs_shadow_info {
 	uint32_t num_levels;       /* getNumLevels() (src/CompressedShadow.h:71) */
 	uint32_t leafmasks;        /* 1 if level 2 holds 64-bit leafmasks (src/CompressedShadow.cpp:20-27) */
 	uint32_t total_visibility; /* getTotalVisibility() (src/CompressedShadow.cpp:66-72) */
-	uint32_t reserved;
+	uint32_t predicted;        /* 1: the build ran on sizes predicted from the previous build of the same shape (no count pass) */
 	uint64_t words;                      /* getDAG().size() */
 	uint64_t svo_nodes[CPVS_MAX_LEVELS]; /* nodes per level before merging, index = level */
 	uint64_t dag_nodes[CPVS_MAX_LEVELS]; /* nodes per level after merging, index = level */
@@ -143,6 +156,15 @@ typedef struct cpvs_shadow_info {
  * z_tile_num is passed by value (the reference keeps it in a file-static). */
 CPVS_API int cpvs_shadow_create(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t z_tile_index, uint32_t z_tile_num,
 		int leafmasks, cpvs_shadow** out);
+/* The same build without waiting for it: when the sizes can be predicted (cpvs_ctx_set_prediction; whole-volume builds
+ * of a shape this context has built before) the call returns as soon as the kernels are enqueued, so a caller can
+ * keep several builds in flight -- the next frame's on this context, or others on other contexts of the same GPU,
+ * whose kernels then fill the gaps of this one's latency-bound phases. Otherwise it behaves like cpvs_shadow_create.
+ * Every other call on the handle waits for the build first; cpvs_shadow_wait does only that and returns the build's
+ * status. `mm` (and a borrowed device depth map) must stay alive until then. */
+CPVS_API int cpvs_shadow_create_async(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t z_tile_index, uint32_t z_tile_num,
+		int leafmasks, cpvs_shadow** out);
+CPVS_API int cpvs_shadow_wait(cpvs_shadow* s);
 /* CompressedShadow::create(const ShadowMap*, ...) (src/CompressedShadow.cpp:61-64): temporary hierarchy. */
 CPVS_API int cpvs_shadow_create_from_depth(cpvs_ctx* ctx, const float* depth, int n, int mem, uint32_t z_tile_index,
 		uint32_t z_tile_num, int leafmasks, cpvs_shadow** out);
@@ -153,7 +175,8 @@ CPVS_API int cpvs_shadow_copy_dag(const cpvs_shadow* s, uint32_t* out_host);
 CPVS_API const uint32_t* cpvs_shadow_dag_device(const cpvs_shadow* s);
 /* CompressedShadow::traverse(vec3 ndc, bool tryLeafmasks) (src/CompressedShadow.cpp:404-463) for
  * `count` points: ndc = count x (x,y,z) floats in [-1,1]^3, out = count NodeVisibility bytes. Points
- * outside the cube are clamped to it. */
+ * outside the cube are clamped to it. try_leafmasks must match how the DAG was built
+ * (info.leafmasks): the mismatch is undefined behaviour in the reference and CPVS_EINVAL here. */
 CPVS_API int cpvs_shadow_lookup_ndc(const cpvs_shadow* s, const float* ndc, int64_t count, int mem, int try_leafmasks,
 		uint8_t* out);
 
@@ -184,9 +207,10 @@ CPVS_API int cpvs_container_lookup_ndc(const cpvs_container* c, const float* ndc
 CPVS_API int cpvs_container_evaluate(const cpvs_container* c, const float* positions, uint32_t width, uint32_t height, int mem,
 		const float light_view_proj[16], uint8_t* visibilities);
 /* On-disk container (the reference has no serialisation and rebuilds on every launch).
- * File = 64-byte header {"CPVSDAG1", version, length, dag_levels, grid_levels, leafmasks, dag_words,
- * grid_cells, fnv64 of the DAG words} + grid words + DAG words, little endian. A loaded container is
- * finalized and ready for lookups; its cells cannot be re-set. */
+ * File = 64-byte header {"CPVSDAG2", version, length, dag_levels, grid_levels, leafmasks, dag_words,
+ * grid_cells, fnv64 over header fields + grid + DAG words} + grid words + DAG words, little endian. Loading validates
+ * the header fields against each other and the file size, the checksum, and every grid entry against the DAG's extent.
+ * A loaded container is finalized and ready for lookups; its cells cannot be re-set (CPVS_EINVAL). */
 CPVS_API int cpvs_container_save(const cpvs_container* c, const char* path);
 CPVS_API int cpvs_container_load(cpvs_ctx* ctx, const char* path, cpvs_container** out);
 /* setFilterSize (src/CompressedShadowContainer.h:71-73): stored, unused -- as in the reference
@@ -197,10 +221,12 @@ CPVS_API int cpvs_container_set_filter_size(cpvs_container* c, uint32_t size);
  * Replaces the reference's render + glGetTexImage read-back of one light-frustum tile
  * (src/ShadowMap.cpp:23-30, src/DeferredRenderer.cpp:173-177) for the synthetic scenes of SURVEY.md 8d:
  * writes the n x n window (tile_x, tile_y) of the (n * tiles_per_side)^2 virtual map into device memory on
- * the context's stream, byte-identical to the host generator (cpvs_b200/synth). kind: CPVS_SCENE_PLANE or
- * CPVS_SCENE_CITY (the terrain scene depends on the host libm: CPVS_EINVAL). n: multiple of 4. */
+ * the context's stream, byte-identical to the host generator (cpvs_b200/synth). kind: CPVS_SCENE_PLANE,
+ * CPVS_SCENE_CITY or CPVS_SCENE_TERRAIN_DEV (SURVEY.md's terrain on a deterministic sin/cos shared by host and device;
+ * the libm terrain itself, scene 1, has no device twin: CPVS_EINVAL). n: multiple of 4. */
 #define CPVS_SCENE_PLANE 0
 #define CPVS_SCENE_CITY 2
+#define CPVS_SCENE_TERRAIN_DEV 3
 CPVS_API int cpvs_depth_generate(cpvs_ctx* ctx, int kind, int n, int tile_x, int tile_y, int tiles_per_side, float* depth_device);
 
 #ifdef __cplusplus

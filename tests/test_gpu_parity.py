@@ -391,12 +391,35 @@ def test_container_file_round_trip(gpu_ctx, tmp_path):
     assert np.array_equal(dag, dag2) and np.array_equal(grid, grid2)
     pts = synth.lookups(50000, seed=4)
     assert np.array_equal(cont.lookup_ndc(pts), back.lookup_ndc(pts))
-    raw = bytearray(open(path, "rb").read())
-    raw[-5] ^= 0x40
+    good = open(path, "rb").read()
     bad = str(tmp_path / "bad.cpvs")
-    open(bad, "wb").write(raw)
-    with pytest.raises(cpvs_b200.CpvsError):
-        cpvs_b200.CompressedShadowContainer.load(bad, gpu_ctx)
+
+    def rejected(raw):
+        open(bad, "wb").write(bytes(raw))
+        with pytest.raises(cpvs_b200.CpvsError) as e:
+            cpvs_b200.CompressedShadowContainer.load(bad, gpu_ctx)
+        return e.value.code == cpvs_b200.EINVAL
+
+    raw = bytearray(good)
+    raw[-5] ^= 0x40  # a DAG word
+    assert rejected(raw)
+    raw = bytearray(good)
+    raw[64 + 2] ^= 0x01  # a grid word: covered by the checksum too
+    assert rejected(raw)
+    raw = bytearray(good)
+    raw[20] = 5  # gridLevels no longer log2(length): lookups would index past the grid
+    assert rejected(raw)
+    raw = bytearray(good)
+    raw[24] = 7  # leafmasks must be 0 or 1
+    assert rejected(raw)
+    assert rejected(good[:-8])  # truncated: the size is checked against the header before anything is allocated
+    raw = bytearray(good)
+    raw[32:40] = (1 << 31).to_bytes(8, "little")  # dagWords far beyond the file
+    assert rejected(raw)
+    with pytest.raises(cpvs_b200.CpvsError):  # a loaded container is final
+        mm = cpvs_b200.MinMaxHierarchy(synth.depth_map("city", n, (0, 0), length), gpu_ctx)
+        back.set(cpvs_b200.CompressedShadow.create(mm, 0, length), 0, 0, 0)
+    assert np.array_equal(cont.lookup_ndc(pts), back.lookup_ndc(pts))
 
 
 def test_config2_tile_grid_4x4x4(gpu_ctx, oracle):
@@ -432,7 +455,8 @@ def test_config2_tile_grid_4x4x4(gpu_ctx, oracle):
 # ---- device-resident depth source ----------------------------------------------------
 
 @pytest.mark.parametrize("kind,n,tiles", [("plane", 1024, 1), ("plane", 512, 4), ("city", 1024, 1), ("city", 512, 4),
-                                          ("city", 256, 64), ("city", 16, 2)])
+                                          ("city", 256, 64), ("city", 16, 2), ("terrain_dev", 1024, 1), ("terrain_dev", 512, 4),
+                                          ("terrain_dev", 256, 64), ("terrain_dev", 2048, 8)])
 def test_device_generated_tiles_equal_host_bytes(gpu_ctx, kind, n, tiles):
     """The CUDA generator must write the same bytes as the host generator the oracle is fed with. 64 tiles per
     side of 256 texels = a 16K^2 city with 2048 boxes of up to 1032 texels: most of them cover whole 128x32
@@ -550,26 +574,117 @@ def test_leaf_kernels_forced(oracle, mode, monkeypatch):
         _assert_same_dag(g, o, (mode, tag))
 
 
-# ---- experimental kernel variants: not measured yet, off by default, and not part of the default GPU run ----------------
+# ---- builds sized from the previous build of the same shape (cpvs_ctx_set_prediction) ---------------------------------------
 
-@pytest.mark.skipif(os.environ.get("CPVS_TEST_EXPERIMENTAL") != "1", reason="unmeasured kernel variants: set CPVS_TEST_EXPERIMENTAL=1 to run")
-@pytest.mark.parametrize("names", ["expand-preload", "emit-gather", "rank-preload", "insert-witness", "early-bases", "leaf-fp64", "leaf-fp64-weak",
-                                   "expand-preload,emit-gather,rank-preload,insert-witness,early-bases,leaf-fp64"])
-def test_experimental_variants_keep_the_words(oracle, names, monkeypatch):
-    """CPVS_EXPERIMENTS picks kernel variants written without GPU time to measure them; whatever they
-    do to the speed, the words must not move. The per-column leaf builder is forced so that the column scatter of the
-    expansion runs on small maps too."""
-    monkeypatch.setenv("CPVS_EXPERIMENTS", names)
-    monkeypatch.setenv("CPVS_LEAF_COLUMNS", "2")
+def _terrain_like(n, seed, amp):
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:n, 0:n].astype(np.float32) / np.float32(n)
+    d = 0.5 + amp * np.sin(9.1 * x) * np.cos(7.3 * y) + 0.05 * np.sin(41.0 * x + 3.0 * y)
+    return (d + rng.random((n, n)) * 1e-3).astype(np.float32)
+
+
+@pytest.mark.parametrize("columns", ["1", "2"])
+def test_predicted_builds_keep_the_words(oracle, columns, monkeypatch):
+    """The second build of a shape runs on predicted sizes (no count pass, the DAG allocated up front, leaves emitted during the
+    merge); the words must be those of the exact build and of the oracle -- also when the map changed in between."""
+    monkeypatch.setenv("CPVS_LEAF_COLUMNS", columns)
     ctx = cpvs_b200.Context(0)
-    rng = np.random.default_rng(11)
-    cases = [("terrain", synth.depth_map("terrain", 1024), 0, 1, True), ("plane", synth.depth_map("plane", 256), 0, 1, True),
-             ("city", synth.depth_map("city", 1024), 0, 1, True), ("city z1/2", synth.depth_map("city", 512), 1, 2, True),
-             ("terrain z2/4", synth.depth_map("terrain", 256), 2, 4, True), ("random 128", rng.random((128, 128), dtype=np.float32), 0, 1, True),
-             ("terrain 2048", synth.depth_map("terrain", 2048), 0, 1, True), ("terrain no leafmasks", synth.depth_map("terrain", 256), 0, 1, False)]
-    for tag, d, zt, zn, leaf in cases:
-        for rep in range(2):  # the second build reuses the arena the first one left behind
+    maps = [_terrain_like(1024, 1, 0.15), _terrain_like(1024, 2, 0.16), _terrain_like(1024, 3, 0.14), synth.depth_map("terrain", 1024)]
+    for i, d in enumerate(maps):
+        mm = cpvs_b200.MinMaxHierarchy(d, ctx)
+        g = cpvs_b200.CompressedShadow.create(mm)
+        if i < 3:  # (the last map may outgrow what its noisy predecessors predicted: rebuilt exactly, same words)
+            assert bool(g.info.predicted) == (i > 0), i
+        _assert_same_dag(g, oracle.Shadow(oracle.MinMax(d)), ("predicted", columns, i))
+        pts = synth.lookups(5000, seed=i + 1)
+        assert np.array_equal(g.traverse(pts), oracle.Shadow(oracle.MinMax(d)).traverse(pts))
+    st = ctx.stats()
+    assert st["predicted_builds"] == 3 and st["overflow_rebuilds"] <= 1, st
+    for leaf in (True, False):  # leafmask-less builds keep their own memo
+        for rep in range(2):
+            d = synth.depth_map("city", 256)
             mm = cpvs_b200.MinMaxHierarchy(d, ctx)
-            g = cpvs_b200.CompressedShadow.create(mm, zt, zn, leaf)
-            o = oracle.Shadow(oracle.MinMax(d), zt, zn, leaf)
-            _assert_same_dag(g, o, (names, tag, rep))
+            g = cpvs_b200.CompressedShadow.create(mm, leafmasks=leaf)
+            _assert_same_dag(g, oracle.Shadow(oracle.MinMax(d), 0, 1, leaf), ("predicted city", leaf, rep))
+
+
+def test_prediction_overflow_falls_back_to_exact(oracle):
+    """A map that outgrows the capacities predicted from its predecessor is rebuilt with exact counts; one that only outgrows
+    the predicted DAG allocation is emitted again. Either way the words are the oracle's."""
+    ctx = cpvs_b200.Context(0)
+    small, big = synth.depth_map("plane", 512), synth.depth_map("terrain", 512)
+    for d in (small, big, small, big):
+        mm = cpvs_b200.MinMaxHierarchy(d, ctx)
+        _assert_same_dag(cpvs_b200.CompressedShadow.create(mm), oracle.Shadow(oracle.MinMax(d)), "overflow")
+    st = ctx.stats()
+    assert st["overflow_rebuilds"] >= 1, st
+    # no head room at all: the slightest growth overflows -- nodes (rebuild) or only words (re-emission)
+    ctx2 = cpvs_b200.Context(0)
+    ctx2.set_prediction(True, 40)
+    rng = np.random.default_rng(3)
+    base = synth.depth_map("plane", 512)  # nearly all of its leaves are duplicates: every disturbed texel adds a distinct one
+    for i in range(6):
+        d = base.copy()
+        ys, xs = rng.integers(0, 512, 1500 * i), rng.integers(0, 512, 1500 * i)
+        d[ys, xs] += np.float32(0.0005)  # a quarter of a slice: more distinct leaves (words), hardly any more nodes
+        mm = cpvs_b200.MinMaxHierarchy(d, ctx2)
+        _assert_same_dag(cpvs_b200.CompressedShadow.create(mm), oracle.Shadow(oracle.MinMax(d)), ("tight words", i))
+    st2 = ctx2.stats()
+    assert st2["overflow_rebuilds"] + st2["reemissions"] >= 1, st2
+    for i in range(4):
+        d = base.copy()
+        ys, xs = rng.integers(0, 512, 3000 * i), rng.integers(0, 512, 3000 * i)
+        d[ys, xs] += np.float32(0.05)  # spikes: more nodes on every level
+        mm = cpvs_b200.MinMaxHierarchy(d, ctx2)
+        _assert_same_dag(cpvs_b200.CompressedShadow.create(mm), oracle.Shadow(oracle.MinMax(d)), ("tight nodes", i))
+    st3 = ctx2.stats()
+    assert st3["overflow_rebuilds"] > st2["overflow_rebuilds"], (st2, st3)
+    # prediction switched off: every build counts first
+    ctx3 = cpvs_b200.Context(0)
+    ctx3.set_prediction(False)
+    for _ in range(2):
+        mm = cpvs_b200.MinMaxHierarchy(big, ctx3)
+        g = cpvs_b200.CompressedShadow.create(mm)
+        assert not g.info.predicted
+        _assert_same_dag(g, oracle.Shadow(oracle.MinMax(big)), "unpredicted")
+    assert ctx3.stats()["predicted_builds"] == 0
+
+
+def test_lookup_leafmask_mismatch_is_an_error(gpu_ctx):
+    """traverse(..., tryLeafmasks=False) on a leafmask DAG walked leaf words as pointers."""
+    _, with_leaf = _build(gpu_ctx, synth.depth_map("terrain", 64))
+    _, without = _build(gpu_ctx, synth.depth_map("terrain", 64), leaf=False)
+    pts = synth.lookups(100)
+    with pytest.raises(cpvs_b200.CpvsError) as e:
+        with_leaf.traverse(pts, False)
+    assert e.value.code == cpvs_b200.EINVAL
+    with pytest.raises(cpvs_b200.CpvsError):
+        without.traverse(pts, True)
+    assert np.array_equal(with_leaf.traverse(pts, True), without.traverse(pts, False))
+
+
+def test_async_builds_in_flight(oracle):
+    """cpvs_shadow_create_async: several builds in flight on one context and on two contexts of the same GPU; every handle
+    ends up with the oracle's words, also when a prediction fails while later builds are already enqueued."""
+    ctxs = [cpvs_b200.Context(0), cpvs_b200.Context(0)]
+    maps = [_terrain_like(512, s, 0.15) for s in (1, 2, 3, 4)]
+    spiky = maps[0].copy()
+    spiky[::7, ::5] += np.float32(0.07)  # outgrows whatever the smooth maps predicted
+    want = [oracle.Shadow(oracle.MinMax(d)).dag() for d in maps + [spiky]]
+    for ctx in ctxs:  # first build of the shape: exact, fills the memo
+        mm = cpvs_b200.MinMaxHierarchy(maps[0], ctx)
+        assert np.array_equal(cpvs_b200.CompressedShadow.create(mm).getDAG(), want[0])
+    order = [0, 1, 2, 4, 3, 0, 4, 1]
+    flying = []
+    for k, idx in enumerate(order):
+        ctx = ctxs[k % 2]
+        d = spiky if idx == 4 else maps[idx]
+        mm = cpvs_b200.MinMaxHierarchy(d, ctx)
+        flying.append((idx, mm, cpvs_b200.CompressedShadow.create(mm, wait=False)))
+    for idx, mm, sh in reversed(flying):  # finished out of order
+        assert np.array_equal(sh.getDAG(), want[idx]), idx
+    stats = [c.stats() for c in ctxs]
+    assert sum(s["overflow_rebuilds"] for s in stats) >= 1, stats
+    pts = synth.lookups(2000)
+    idx, mm, sh = flying[0]
+    assert np.array_equal(sh.traverse(pts), oracle.Shadow(oracle.MinMax(maps[idx])).traverse(pts))
