@@ -61,6 +61,7 @@ SIGNATURES = {
     "cpvs_last_error": (ctypes.c_char_p, []),
     "cpvs_version": (ctypes.c_char_p, []),
     "cpvs_minmax_build": (_I, [_VP, _VP, _I, _I, _PP]),
+    "cpvs_minmax_build_tiled": (_I, [_VP, _VP, _I, _I, _U32, _PP]),
     "cpvs_minmax_destroy": (_I, [_VP]),
     "cpvs_minmax_num_levels": (_I, [_VP]),
     "cpvs_minmax_size": (_I, [_VP]),
@@ -90,6 +91,21 @@ SIGNATURES = {
     "cpvs_container_save": (_I, [_VP, ctypes.c_char_p]),
     "cpvs_container_load": (_I, [_VP, ctypes.c_char_p, _PP]),
     "cpvs_depth_generate": (_I, [_VP, _I, _I, _I, _I, _I, _VP]),
+    "cpvs_container_assemble": (_I, [_VP, _U32, _U32, _I, _VP, _PP]),
+    "cpvs_grid_worker_create": (_I, [_VP, _VP, _PP]),
+    "cpvs_grid_worker_destroy": (_I, [_VP]),
+    "cpvs_grid_worker_estimate": (_I, [_VP, _VP, _I, _VP]),
+    "cpvs_grid_worker_release": (_I, [_VP, _VP, _I]),
+    "cpvs_grid_worker_build": (_I, [_VP, _VP, _I]),
+    "cpvs_grid_worker_num_cells": (_I, [_VP]),
+    "cpvs_grid_worker_cells": (_I, [_VP, _VP, _I]),
+    "cpvs_grid_worker_device_ms": (ctypes.c_float, [_VP]),
+    "cpvs_grid_assign": (_I, [_VP, _I, _I, _VP, _VP]),
+    "cpvs_grid_build": (_I, [_VP, _I, _VP, _I, _PP]),
+    "cpvs_grid_destroy": (_I, [_VP]),
+    "cpvs_grid_stats_get": (_I, [_VP, _VP]),
+    "cpvs_grid_container": (_VP, [_VP, _I]),
+    "cpvs_grid_lookup_ndc": (_I, [_VP, _VP, _I64, _VP]),
 }
 
 _lib = None
@@ -201,7 +217,8 @@ def default_context(device=0):
 class MinMaxHierarchy:
     """Reference ``MinMaxHierarchy`` (src/MinMaxHierarchy.h:23-72), built on the GPU."""
 
-    def __init__(self, depth, ctx=None, n=None):
+    def __init__(self, depth, ctx=None, n=None, zTileNum=1):
+        """``zTileNum``: the slicing the hierarchy's builds will use (a speed hint, see cpvs_minmax_build_tiled)."""
         self.ctx = ctx or default_context()
         self._lib = self.ctx._lib
         if isinstance(depth, np.ndarray):
@@ -214,7 +231,7 @@ class MinMaxHierarchy:
         self._keepalive = depth
         ptr, mem = _as_ptr(depth)
         h = ctypes.c_void_p()
-        _check(self._lib.cpvs_minmax_build(self.ctx.handle, ctypes.c_void_p(ptr), n, mem, ctypes.byref(h)))
+        _check(self._lib.cpvs_minmax_build_tiled(self.ctx.handle, ctypes.c_void_p(ptr), n, mem, zTileNum, ctypes.byref(h)))
         self.handle = h
         self.n = n
 

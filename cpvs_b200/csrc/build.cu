@@ -14,6 +14,7 @@
 //             exact numbers, so results never depend on the prediction
 //
 // Every kernel reads the sizes it needs on the device; the host only supplies capacities.
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -85,6 +86,7 @@ enum : int {
 	kSlotTableError = 163,  // u32: a probe sequence wrapped a merge table
 	kSlotOverflow = 164,    // u32: kOverflowNodes | kOverflowWords
 	kSlotRootMask = 165,    // u32: first word of the DAG (the root's mask)
+	kSlotTallColumns = 166, // u32: the residue leaf builder met columns it leaves to the depth-based one
 };
 
 struct PhaseEvents {
@@ -111,6 +113,7 @@ struct Build {
 	int smallLow = 0;  // levels smallLow..top are walked by the single-CTA kernels
 	bool leafColumns = false, haveLeaves = false;
 	u64 numCols = 0;
+	u64 expectedDistinctLeaves = 0;  // > 0: the leaf table is sized from the memo, no distinct-count sketch is taken
 
 	u64* dScalars = nullptr;
 	ScanTileState* dTiles = nullptr;
@@ -271,6 +274,9 @@ void planLevels(Build& b, const u64* exactCounts, const SizeMemo* memo) {
 	b.smallLow = b.top + 1;
 	for (int l = b.top; l >= b.lastInner && b.lv[l].cap && b.lv[l].cap <= kSmallMaxNodes; --l) b.smallLow = l;
 	b.haveLeaves = b.useLeaf && b.lv[2].cap > 0;
+	// (the sizing kernel adds half again and rounds up to a power of two: no further head room here, or the table doubles
+	// and drops out of L2; a build with many more distinct leaves than this is redone)
+	if (b.haveLeaves && !exactCounts && memo->unique[2]) b.expectedDistinctLeaves = memo->unique[2];
 	// Leaves per column -- where it pays: whole-volume builds with 2..8 leaves per column of a depth map that does not fit in L2 (terrain-like
 	// surfaces; measured at 16K^2: 0.42 ms against 0.50 ms per leaf, at 8192^2 0.121 against 0.137, at 4096^2 -- 64 MiB, L2
 	// serves the re-reads -- 0.046 against 0.045). A z-slice of a tall grid leaves most columns empty; box edges make columns
@@ -280,6 +286,12 @@ void planLevels(Build& b, const u64* exactCounts, const SizeMemo* memo) {
 	b.leafColumns = b.haveLeaves && (ctx->leafColumns == 2 || (ctx->leafColumns == 1 && b.zTileNum == 1 && b.mm->n >= 8192 &&
 																 expect[2] >= 2 * allCols && expect[2] <= 8 * allCols));
 	b.numCols = b.leafColumns ? allCols : 0;
+	// remember for the hierarchies to come whether maps of this side take the per-column builder (cpvs_minmax_build)
+	if (b.haveLeaves && b.zTileNum == 1) {
+		std::vector<int>& no = ctx->noColumnSides;
+		no.erase(std::remove(no.begin(), no.end(), b.mm->n), no.end());
+		if (!b.leafColumns) no.push_back(b.mm->n);
+	}
 }
 
 // ---- carve ---------------------------------------------------------------------------------------------------------------
@@ -304,7 +316,7 @@ int carveArena(Build& b) {
 	auto carve = [&](ArenaCarver& ar) {
 		b.dTiles = ar.take<ScanTileState>(b.scanTiles);
 		b.dTickets = ar.take<u32>(b.scanLaunches);
-		b.dSketch = ar.take<u32>(b.haveLeaves ? kSketchWords : 0);
+		b.dSketch = ar.take<u32>(b.haveLeaves && !b.expectedDistinctLeaves ? kSketchWords : 0);
 		b.dTable = ar.take<u64>(maxTable);
 		b.dColBias = ar.take<u32>(b.numCols);
 		for (int l = b.top; l >= b.minLevel; --l) {
@@ -430,10 +442,11 @@ int stageExpand(Build& b, bool& tablesClearing) {
 	CPVS_CUDA(cudaEventRecord(b.phases.ev[CPVS_PHASE_LEAVES], st));
 	if (b.leafColumns)  // constructLastLevels (src/CompressedShadow.cpp:171-190)
 		ctx->launches += launchBuildLeafColumns(b.pyr, b.zTileIndex, b.zTileNum, b.dColBias, b.lv[2].leafAt, (u32)b.lv[2].cap, b.lv[2].leafCodes,
-				b.lv[2].masks, b.dSketch, st);
+				b.lv[2].masks, b.expectedDistinctLeaves ? nullptr : b.dSketch, (b.mm->residue && b.mm->residueTiles == b.zTileNum) ? b.mm->residue : nullptr,
+				reinterpret_cast<u32*>(b.dScalars + kSlotTallColumns), st);
 	else if (b.haveLeaves)
 		ctx->launches += launchBuildLeaves(b.pyr, b.zTileNum, b.lv[2].coords, b.dNodes() + 2, b.lv[2].cap, b.lv[2].leafCodes, b.lv[2].leafHash,
-				b.lv[2].masks, b.dSketch, st);
+				b.lv[2].masks, b.expectedDistinctLeaves ? nullptr : b.dSketch, st);
 	return CPVS_OK;
 }
 
@@ -472,8 +485,8 @@ int stageMerge(Build& b, bool tablesClearing) {
 	CPVS_CUDA(cudaStreamWaitEvent(mergeStream, ctx->evFork, 0));
 	CPVS_CUDA(cudaEventRecord(b.phases.ev[CPVS_PHASE_LEAF_TABLE], mergeStream));
 	if (b.haveLeaves) {
-		ctx->launches += launchSketchPopcount(b.dSketch, dSketchBits, mergeStream);
-		ctx->launches += launchSizeLeafTable(b.lv[2].table, b.lv[2].tableSlots, dSketchBits, dLeafTableMask, mergeStream);
+		if (!b.expectedDistinctLeaves) ctx->launches += launchSketchPopcount(b.dSketch, dSketchBits, mergeStream);
+		ctx->launches += launchSizeLeafTable(b.lv[2].table, b.lv[2].tableSlots, dSketchBits, dLeafTableMask, b.expectedDistinctLeaves, mergeStream);
 	}
 	CPVS_CUDA(cudaEventRecord(b.phases.ev[CPVS_PHASE_LEAF_INSERT], mergeStream));
 	if (!b.haveLeaves) {
@@ -702,7 +715,13 @@ int finishBuild(Build& b, cpvs_shadow* s, bool arenaIntact, bool* redo) {
 		if (e == cudaSuccess) e = cudaGetLastError();
 		if (e != cudaSuccess) return fail(CPVS_ECUDA, "cpvs_shadow_create: %s", cudaGetErrorString(e));
 		b.trace.mark("emit + final sync");
-		if ((u32)h[kSlotTableError]) return fail(CPVS_EINTERNAL, "merge table overflow (leaf table mask %llu)", (unsigned long long)h[kSlotLeafTableMask]);
+		if ((u32)h[kSlotTableError]) {
+			if (b.predicted) {  // far more distinct leaves than the memo promised: the table was too small
+				*redo = true;
+				return CPVS_OK;
+			}
+			return fail(CPVS_EINTERNAL, "merge table overflow (leaf table mask %llu)", (unsigned long long)h[kSlotLeafTableMask]);
+		}
 		const u32 overflow = (u32)h[kSlotOverflow];
 		if (overflow & kOverflowNodes) {
 			if (b.predicted) {
@@ -819,6 +838,10 @@ int buildExact(cpvs_ctx* ctx, const cpvs_minmax* mm, u32 zTileIndex, u32 zTileNu
 }  // namespace
 
 namespace cpvs {
+int columnCountsOf(cpvs_ctx* ctx, const cpvs_minmax* mm, u32 zTileNum, int minLevel, const u64** counts) {
+	CPVS_CUDA(cudaSetDevice(ctx->device));
+	return columnCounts(ctx, mm, pyramidView(mm), zTileNum, minLevel, counts);
+}
 PyramidView pyramidView(const cpvs_minmax* mm) {
 	PyramidView pyr;
 	pyr.n = mm->n;

@@ -181,7 +181,12 @@ int cpvs_ctx_get_stats(const cpvs_ctx* ctx, cpvs_ctx_stats* out) {
 /* ---- MinMaxHierarchy ------------------------------------------------------------------------ */
 
 int cpvs_minmax_build(cpvs_ctx* ctx, const float* depth, int n, int mem, cpvs_minmax** out) {
+	return cpvs_minmax_build_tiled(ctx, depth, n, mem, 1, out);
+}
+
+int cpvs_minmax_build_tiled(cpvs_ctx* ctx, const float* depth, int n, int mem, uint32_t zTileNum, cpvs_minmax** out) {
 	if (!ctx || !depth || !out) return fail(CPVS_EINVAL, "cpvs_minmax_build: NULL argument");
+	if (zTileNum == 0 || (u64)(n > 0 ? n : 0) * zTileNum > (1ull << 23)) return fail(CPVS_EINVAL, "cpvs_minmax_build_tiled: %u z-slices of side %d", zTileNum, n);
 	*out = nullptr;
 	if (n < 2 || !isPow2((u64)n) || n > (1 << 19)) return fail(CPVS_EINVAL, "cpvs_minmax_build: side %d is not a power of two in [2, 2^19]", n);
 	if (mem != CPVS_MEM_HOST && mem != CPVS_MEM_DEVICE) return fail(CPVS_EINVAL, "cpvs_minmax_build: mem %d", mem);
@@ -190,6 +195,8 @@ int cpvs_minmax_build(cpvs_ctx* ctx, const float* depth, int n, int mem, cpvs_mi
 	if (!mm) return fail(CPVS_ENOMEM, "cpvs_minmax_build: host allocation");
 	mm->ownedDepth = nullptr;
 	mm->levelStorage = nullptr;
+	mm->residue = nullptr;
+	mm->residueTiles = 0;
 	mm->evStart = mm->evBase = mm->evStop = nullptr;
 	for (int k = 0; k < kMaxLevels; ++k) mm->level[k] = nullptr;
 	mm->ctx = ctx;
@@ -204,13 +211,26 @@ int cpvs_minmax_build(cpvs_ctx* ctx, const float* depth, int n, int mem, cpvs_mi
 		const u64 side = (u64)n >> k;
 		total += (side * side * 2 + 63) & ~63ull;  // floats, each level 256-byte aligned
 	}
+	// Column residues for the per-column leaf builder: where that builder is used (maps >= 8192^2 whose last build on this
+	// context took it, or always when it is forced), one byte per texel written by the base kernel saves it the second pass
+	// over the 4-byte depths.
+	bool wantResidue = n >= 128 && (ctx->leafColumns == 2 || (ctx->leafColumns == 1 && n >= 8192));
+	if (wantResidue && ctx->leafColumns == 1) {
+		std::lock_guard<std::mutex> guard(ctx->buildLock);
+		for (int side : ctx->noColumnSides) wantResidue = wantResidue && side != n;
+	}
 	cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&mm->levelStorage), total * sizeof(float), ctx->stream);
+	if (e == cudaSuccess && wantResidue) {
+		e = cudaMallocAsync(reinterpret_cast<void**>(&mm->residue), (u64)n * n, ctx->stream);
+		mm->residueTiles = zTileNum;
+	}
 	if (e == cudaSuccess && mem == CPVS_MEM_HOST) {
 		e = cudaMallocAsync(reinterpret_cast<void**>(&mm->ownedDepth), (u64)n * n * sizeof(float), ctx->stream);
 		if (e == cudaSuccess) e = cudaMemcpyAsync(mm->ownedDepth, depth, (u64)n * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
 	}
 	if (e != cudaSuccess) {
 		if (mm->levelStorage) cudaFreeAsync(mm->levelStorage, ctx->stream);
+		if (mm->residue) cudaFreeAsync(mm->residue, ctx->stream);
 		if (mm->ownedDepth) cudaFreeAsync(mm->ownedDepth, ctx->stream);
 		delete mm;
 		return fail(e == cudaErrorMemoryAllocation ? CPVS_ENOMEM : CPVS_ECUDA, "cpvs_minmax_build: %s", cudaGetErrorString(e));
@@ -229,7 +249,7 @@ int cpvs_minmax_build(cpvs_ctx* ctx, const float* depth, int n, int mem, cpvs_mi
 	mm->columnSlices = 0;
 	mm->columnMinLevel = -1;
 	mm->lowLevelsBuilt = n < 128;  // small maps take the generic path, which writes every level
-	ctx->launches += launchPyramid(mm->level[0], n, lv, levels, false, mm->evBase, ctx->stream);
+	ctx->launches += launchPyramid(mm->level[0], n, lv, levels, false, mm->residue, mm->residueTiles, mm->evBase, ctx->stream);
 	cudaEventRecord(mm->evStop, ctx->stream);
 	e = cudaGetLastError();
 	if (e != cudaSuccess) {
@@ -244,6 +264,7 @@ int cpvs_minmax_destroy(cpvs_minmax* mm) {
 	if (!mm) return CPVS_OK;
 	cudaSetDevice(mm->ctx->device);
 	if (mm->levelStorage) cudaFreeAsync(mm->levelStorage, mm->ctx->stream);
+	if (mm->residue) cudaFreeAsync(mm->residue, mm->ctx->stream);
 	if (mm->ownedDepth) cudaFreeAsync(mm->ownedDepth, mm->ctx->stream);
 	if (mm->evStart) {
 		cudaEventDestroy(mm->evStart);
@@ -522,6 +543,98 @@ int cpvs_container_finalize(cpvs_container* c) {
 	}
 	c->finalized = true;
 	return CPVS_OK;
+}
+
+}  // extern "C"
+
+namespace {
+struct WordPatch {
+	u64 offset;
+	u32 value;
+};
+__global__ void patchWordsKernel(u32* __restrict__ dag, const WordPatch* __restrict__ patches, u32 count) {
+	const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < count) dag[patches[i].offset] = patches[i].value;
+}
+}  // namespace
+
+namespace cpvs {
+// combineDAGs + createTopLevelGrid from cells resident on any GPU of the box.
+int containerFromParts(cpvs_ctx* ctx, u32 length, u32 numLevels, int leafmasks, const cpvs_cell_part* parts, cpvs_container** out) {
+	*out = nullptr;
+	cpvs_container* c = nullptr;
+	if (int rc = cpvs_container_create(ctx, length, &c)) return rc;
+	c->loaded = true;  // no per-cell copies: the cells cannot be re-set
+	CPVS_CUDA(cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	const size_t numCells = c->cells.size();
+	u64 total = 0;
+	for (size_t i = 0; i < numCells; ++i) total += parts[i].words;
+	if (total == 0 || total > (1ull << 32)) {
+		cpvs_container_destroy(c);
+		return fail(CPVS_EOVERFLOW, "combined DAG needs %llu words; offsets are 32-bit", (unsigned long long)total);
+	}
+	std::vector<u32> grid(numCells);
+	std::vector<WordPatch> patches;
+	cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&c->dag), total * sizeof(u32), st);
+	if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(&c->grid), numCells * sizeof(u32), st);
+	u64 offset = 0;
+	for (size_t i = 0; i < numCells && e == cudaSuccess; ++i) {
+		const cpvs_cell_part& p = parts[i];
+		grid[i] = p.root_mask == 0u ? CPVS_GRID_CELL_SHADOWED : (p.root_mask == 0x5555u ? CPVS_GRID_CELL_VISIBLE : (u32)offset);
+		if (p.words == 1 && (!p.words_device || p.root_mask == 0u || p.root_mask == 0x5555u))
+			patches.push_back(WordPatch{offset, p.root_mask});  // (thousands of one-word cells in a tall grid: one kernel stores them all)
+		else if (!p.words_device)
+			e = cudaErrorInvalidValue;
+		else if (p.device == ctx->device)
+			e = cudaMemcpyAsync(c->dag + offset, p.words_device, p.words * sizeof(u32), cudaMemcpyDeviceToDevice, st);
+		else
+			e = cudaMemcpyPeerAsync(c->dag + offset, ctx->device, p.words_device, p.device, p.words * sizeof(u32), st);
+		offset += p.words;
+	}
+	WordPatch* dPatches = nullptr;
+	if (e == cudaSuccess && !patches.empty()) {
+		e = cudaMallocAsync(reinterpret_cast<void**>(&dPatches), patches.size() * sizeof(WordPatch), st);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(dPatches, patches.data(), patches.size() * sizeof(WordPatch), cudaMemcpyHostToDevice, st);
+		if (e == cudaSuccess) {
+			patchWordsKernel<<<(unsigned)((patches.size() + 255) / 256), 256, 0, st>>>(c->dag, dPatches, (u32)patches.size());
+			++ctx->launches;
+			e = cudaGetLastError();
+		}
+	}
+	if (e == cudaSuccess) e = cudaMemcpyAsync(c->grid, grid.data(), numCells * sizeof(u32), cudaMemcpyHostToDevice, st);
+	c->dagWords = total;
+	c->dagLevels = numLevels;
+	c->gridLevels = 0;
+	while ((1u << c->gridLevels) < length) ++c->gridLevels;
+	c->leafmasks = leafmasks;
+	c->skipLevels = skipLevelsFor(c->dagLevels, c->leafmasks, c->gridLevels);
+	if (e == cudaSuccess && c->skipLevels) {
+		e = cudaMallocAsync(reinterpret_cast<void**>(&c->skip), sizeof(u32) << (3 * (c->gridLevels + c->skipLevels)), st);
+		if (e == cudaSuccess) {
+			LookupDag d{c->dag, c->grid, c->dagLevels, c->gridLevels, c->leafmasks, nullptr, c->skipLevels};
+			ctx->launches += launchBuildSkipGrid(d, c->skip, st);
+			e = cudaGetLastError();
+		}
+	}
+	if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // host staging goes away; the sources may be released by the caller
+	if (dPatches) cudaFreeAsync(dPatches, st);
+	if (e != cudaSuccess) {
+		cpvs_container_destroy(c);
+		return fail(CPVS_ECUDA, "cpvs_container_assemble: %s", cudaGetErrorString(e));
+	}
+	c->finalized = true;
+	*out = c;
+	return CPVS_OK;
+}
+}  // namespace cpvs
+
+extern "C" {
+
+int cpvs_container_assemble(cpvs_ctx* ctx, uint32_t length, uint32_t numLevels, int leafmasks, const cpvs_cell_part* cells, cpvs_container** out) {
+	if (!ctx || !cells || !out) return fail(CPVS_EINVAL, "cpvs_container_assemble: NULL argument");
+	if (numLevels <= 3 || numLevels >= (u32)kMaxLevels) return fail(CPVS_EINVAL, "cpvs_container_assemble: %u levels", numLevels);
+	return containerFromParts(ctx, length, numLevels, leafmasks ? 1 : 0, cells, out);
 }
 
 int cpvs_container_info(const cpvs_container* c, uint64_t* dagWords, uint32_t* gridCells, uint32_t* dagLevels, uint32_t* gridLevels) {

@@ -1,0 +1,479 @@
+// Tile-grid driver in C++: the caller contract of the reference's DeferredRenderer::renderWithTiles / createShadowTiles /
+// precomputeShadows (reference src/DeferredRenderer.cpp:150-235) spread over the GPUs of one box.
+//
+// The virtual shadow map is a length x length grid of depth tiles; every xy tile yields `length` z-slice DAGs from one
+// pyramid, and the cells are independent. A *worker* (one per GPU, one host thread each) produces the depth
+// tiles it owns in device memory, builds their pyramids and cells, and keeps the finished DAGs in its GPU's memory. Nothing
+// crosses GPUs while building: the host gathers (words, root mask) per cell, runs createTopLevelGrid's exclusive scan
+// (reference src/CompressedShadowContainer.cpp:71-91), and the words are then replicated with cudaMemcpyPeerAsync into one
+// container per GPU for the lookups, whose batches are split by rows. No NCCL anywhere.
+//
+// Ownership follows the cost of the tiles, not their position: with few tiles per GPU (configs[2]: 16 tiles on 8 GPUs) every
+// worker first builds the pyramids of a round-robin share and counts their nodes (closed form, one launch per tile), the host
+// assigns tiles longest-first to the least loaded worker, and a tile that changes hands is produced again by its new
+// owner; with many tiles per GPU (configs[4]: 256 tiles) the workers simply pull the next tile from a shared queue.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstring>
+#include <new>
+#include <thread>
+
+#include "handles.h"
+
+using namespace cpvs;
+
+namespace cpvs {
+int columnCountsOf(cpvs_ctx* ctx, const cpvs_minmax* mm, u32 zTileNum, int minLevel, const u64** counts);  // build.cu
+int containerFromParts(cpvs_ctx* ctx, u32 length, u32 numLevels, int leafmasks, const cpvs_cell_part* parts, cpvs_container** out);  // capi.cu
+}  // namespace cpvs
+
+namespace {
+struct WorkerTile {
+	u32 x = 0, y = 0;
+	float* depth = nullptr;  // device, owned; released once the tile is built
+	cpvs_minmax* mm = nullptr;
+	u64 cost = 0;
+	bool built = false;
+	std::vector<cpvs_shadow*> cells;  // z = 0 .. length-1
+};
+double nowMs() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+}  // namespace
+
+struct cpvs_grid_worker {
+	cpvs_ctx* ctx = nullptr;
+	cpvs_grid_desc desc{};
+	std::vector<WorkerTile> tiles;
+	float* hostStage = nullptr;  // pinned, one tile (fetch callback)
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	float deviceMs = 0.f;  // device time of everything the worker enqueued for estimates and builds
+	u32 built = 0;
+	int status = CPVS_OK;
+	std::string error;
+};
+
+namespace {
+
+WorkerTile* findTile(cpvs_grid_worker* w, u32 x, u32 y) {
+	for (WorkerTile& t : w->tiles)
+		if (t.x == x && t.y == y) return &t;
+	return nullptr;
+}
+
+void releaseInputs(cpvs_grid_worker* w, WorkerTile& t) {
+	if (t.mm) cpvs_minmax_destroy(t.mm);
+	t.mm = nullptr;
+	if (t.depth) cudaFreeAsync(t.depth, w->ctx->stream);
+	t.depth = nullptr;
+}
+
+// Depth tile in device memory + its pyramid, prepared for `length` z-slices.
+int produceTile(cpvs_grid_worker* w, WorkerTile& t) {
+	if (t.mm) return CPVS_OK;
+	cpvs_ctx* ctx = w->ctx;
+	const cpvs_grid_desc& d = w->desc;
+	const size_t texels = (size_t)d.tile * d.tile;
+	CPVS_CUDA(cudaSetDevice(ctx->device));
+	CPVS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&t.depth), texels * sizeof(float), ctx->stream));
+	if (d.scene >= 0) {
+		if (int rc = cpvs_depth_generate(ctx, d.scene, d.tile, (int)t.x, (int)t.y, (int)d.length, t.depth)) return rc;
+	} else {
+		if (!d.fetch) return fail(CPVS_EINVAL, "cpvs_grid: neither a scene nor a fetch callback");
+		if (!w->hostStage) CPVS_CUDA(cudaMallocHost(reinterpret_cast<void**>(&w->hostStage), texels * sizeof(float)));
+		CPVS_CUDA(cudaStreamSynchronize(ctx->stream));  // the previous tile's copy out of the staging buffer
+		if (d.fetch(d.user, t.x, t.y, w->hostStage) != 0) return fail(CPVS_EINVAL, "cpvs_grid: fetch callback failed for tile (%u,%u)", t.x, t.y);
+		CPVS_CUDA(cudaMemcpyAsync(t.depth, w->hostStage, texels * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+	}
+	return cpvs_minmax_build_tiled(ctx, t.depth, d.tile, CPVS_MEM_DEVICE, d.length, &t.mm);
+}
+
+struct DeviceTimer {  // accumulates device time between construction and destruction into the worker
+	cpvs_grid_worker* w;
+	explicit DeviceTimer(cpvs_grid_worker* worker) : w(worker) { cudaEventRecord(w->ev0, w->ctx->stream); }
+	~DeviceTimer() {
+		cudaEventRecord(w->ev1, w->ctx->stream);
+		float ms = 0.f;
+		if (cudaEventSynchronize(w->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, w->ev0, w->ev1) == cudaSuccess) w->deviceMs += ms;
+	}
+};
+
+}  // namespace
+
+extern "C" {
+
+int cpvs_grid_worker_create(cpvs_ctx* ctx, const cpvs_grid_desc* desc, cpvs_grid_worker** out) {
+	if (!ctx || !desc || !out) return fail(CPVS_EINVAL, "cpvs_grid_worker_create: NULL argument");
+	*out = nullptr;
+	if (!isPow2(desc->length) || desc->length > 64) return fail(CPVS_EINVAL, "cpvs_grid: length %u must be a power of two <= 64", desc->length);
+	if (desc->tile < 16 || !isPow2((u64)desc->tile) || (u64)desc->tile * desc->length > (1ull << 23))
+		return fail(CPVS_EINVAL, "cpvs_grid: tile side %d with %u slices", desc->tile, desc->length);
+	cpvs_grid_worker* w = new (std::nothrow) cpvs_grid_worker();
+	if (!w) return fail(CPVS_ENOMEM, "cpvs_grid_worker_create: host allocation");
+	w->ctx = ctx;
+	w->desc = *desc;
+	cudaSetDevice(ctx->device);
+	if (cudaEventCreate(&w->ev0) != cudaSuccess || cudaEventCreate(&w->ev1) != cudaSuccess) {
+		cpvs_grid_worker_destroy(w);
+		return fail(CPVS_ECUDA, "cpvs_grid_worker_create: events");
+	}
+	*out = w;
+	return CPVS_OK;
+}
+
+int cpvs_grid_worker_destroy(cpvs_grid_worker* w) {
+	if (!w) return CPVS_OK;
+	cudaSetDevice(w->ctx->device);
+	for (WorkerTile& t : w->tiles) {
+		releaseInputs(w, t);
+		for (cpvs_shadow* s : t.cells) cpvs_shadow_destroy(s);
+	}
+	if (w->hostStage) cudaFreeHost(w->hostStage);
+	if (w->ev0) cudaEventDestroy(w->ev0);
+	if (w->ev1) cudaEventDestroy(w->ev1);
+	delete w;
+	return CPVS_OK;
+}
+
+// Cost of tiles = SVO nodes of all their z-slices (closed form: one launch and one read-back per tile); the depth tile and
+// its pyramid stay resident for the build. xy: count pairs (x, y).
+int cpvs_grid_worker_estimate(cpvs_grid_worker* w, const uint32_t* xy, int count, uint64_t* costOut) {
+	if (!w || (count > 0 && (!xy || !costOut))) return fail(CPVS_EINVAL, "cpvs_grid_worker_estimate: NULL argument");
+	DeviceTimer timer(w);
+	const int L = [&] {
+		int levels = 1;
+		while ((1 << (levels - 1)) < w->desc.tile) ++levels;
+		return levels;
+	}();
+	const bool useLeaf = w->desc.leafmasks && (L - 3) >= 2;
+	const int minLevel = useLeaf ? 2 : 0;
+	for (int i = 0; i < count; ++i) {
+		WorkerTile* t = findTile(w, xy[2 * i], xy[2 * i + 1]);
+		if (!t) {
+			w->tiles.emplace_back();
+			t = &w->tiles.back();
+			t->x = xy[2 * i];
+			t->y = xy[2 * i + 1];
+		}
+		if (int rc = produceTile(w, *t)) return rc;
+		if (!useLeaf)
+			if (int rc = ensureLowLevels(t->mm, 1)) return rc;
+		const u64* counts = nullptr;
+		if (int rc = columnCountsOf(w->ctx, t->mm, w->desc.length, minLevel, &counts)) return rc;
+		u64 cost = 0;
+		for (u32 z = 0; z < w->desc.length; ++z) {
+			const u64* c = counts + (size_t)z * kMaxLevels;
+			if (c[L - 3] == 0) {  // a one-word cell
+				cost += 1;
+				continue;
+			}
+			for (int l = minLevel; l <= L - 3; ++l) cost += c[l] * (useLeaf && l == 2 ? 3u : 2u);  // leaves weigh more: built, hashed, expanded
+		}
+		t->cost = cost + ((u64)w->desc.tile * w->desc.tile >> 4);  // + the pyramid pass over the tile
+		costOut[i] = t->cost;
+	}
+	return CPVS_OK;
+}
+
+// Drops tiles that were estimated here but went to another worker.
+int cpvs_grid_worker_release(cpvs_grid_worker* w, const uint32_t* xy, int count) {
+	if (!w) return fail(CPVS_EINVAL, "cpvs_grid_worker_release: NULL argument");
+	cudaSetDevice(w->ctx->device);
+	for (int i = 0; i < count; ++i) {
+		WorkerTile* t = findTile(w, xy[2 * i], xy[2 * i + 1]);
+		if (t && !t->built) {
+			releaseInputs(w, *t);
+			w->tiles.erase(w->tiles.begin() + (t - w->tiles.data()));
+		}
+	}
+	return CPVS_OK;
+}
+
+// createShadowTiles for the given xy tiles: depth tile (unless still resident from the estimate), pyramid, one DAG per z-slice.
+int cpvs_grid_worker_build(cpvs_grid_worker* w, const uint32_t* xy, int count) {
+	if (!w || (count > 0 && !xy)) return fail(CPVS_EINVAL, "cpvs_grid_worker_build: NULL argument");
+	DeviceTimer timer(w);
+	for (int i = 0; i < count; ++i) {
+		WorkerTile* t = findTile(w, xy[2 * i], xy[2 * i + 1]);
+		if (!t) {
+			w->tiles.emplace_back();
+			t = &w->tiles.back();
+			t->x = xy[2 * i];
+			t->y = xy[2 * i + 1];
+		}
+		if (t->built) continue;
+		if (int rc = produceTile(w, *t)) return rc;
+		t->cells.assign(w->desc.length, nullptr);
+		for (u32 z = 0; z < w->desc.length; ++z)
+			if (int rc = cpvs_shadow_create(w->ctx, t->mm, z, w->desc.length, w->desc.leafmasks, &t->cells[z])) return rc;
+		releaseInputs(w, *t);
+		t->built = true;
+		++w->built;
+	}
+	return CPVS_OK;
+}
+
+int cpvs_grid_worker_num_cells(const cpvs_grid_worker* w) { return w ? (int)(w->built * w->desc.length) : 0; }
+
+// The finished cells of this worker: index = cell index in the container ((z * length + y) * length + x).
+int cpvs_grid_worker_cells(const cpvs_grid_worker* w, cpvs_grid_cell* out, int capacity) {
+	if (!w || !out) return fail(CPVS_EINVAL, "cpvs_grid_worker_cells: NULL argument");
+	int n = 0;
+	const u32 len = w->desc.length;
+	for (const WorkerTile& t : w->tiles) {
+		if (!t.built) continue;
+		for (u32 z = 0; z < len; ++z) {
+			if (n >= capacity) return fail(CPVS_EINVAL, "cpvs_grid_worker_cells: capacity %d", capacity);
+			const cpvs_shadow* s = t.cells[z];
+			cpvs_grid_cell& c = out[n++];
+			c.index = (z * len + t.y) * len + t.x;
+			c.words = s->info.words;
+			c.num_levels = s->info.num_levels;
+			c.root_mask = s->info.total_visibility == CPVS_SHADOW ? 0u : (s->info.total_visibility == CPVS_VISIBLE ? 0x5555u : 0xAAAAu);
+			c.device = w->ctx->device;
+			c.words_device = s->dag;
+			c.svo_nodes = c.dag_nodes = 0;
+			for (int l = 0; l < CPVS_MAX_LEVELS; ++l) {
+				c.svo_nodes += s->info.svo_nodes[l];
+				c.dag_nodes += s->info.dag_nodes[l];
+			}
+		}
+	}
+	return n;
+}
+
+float cpvs_grid_worker_device_ms(const cpvs_grid_worker* w) { return w ? w->deviceMs : 0.f; }
+
+// Longest-processing-time-first: tiles in order of falling cost, each to the least loaded worker; among equally loaded
+// workers the one that already holds the tile (its pyramid is resident there). owner_in may be NULL.
+int cpvs_grid_assign(const uint64_t* cost, int numTiles, int numWorkers, const int* ownerIn, int* ownerOut) {
+	if (!cost || !ownerOut || numTiles < 0 || numWorkers < 1) return fail(CPVS_EINVAL, "cpvs_grid_assign: bad arguments");
+	std::vector<int> order(numTiles);
+	for (int i = 0; i < numTiles; ++i) order[i] = i;
+	std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+	std::vector<u64> load(numWorkers, 0);
+	for (int t : order) {
+		int best = 0;
+		for (int wk = 1; wk < numWorkers; ++wk)
+			if (load[wk] < load[best]) best = wk;
+		if (ownerIn && ownerIn[t] >= 0 && ownerIn[t] < numWorkers && load[ownerIn[t]] == load[best]) best = ownerIn[t];
+		ownerOut[t] = best;
+		load[best] += cost[t];
+	}
+	return CPVS_OK;
+}
+
+}  // extern "C"
+
+// ---- the whole grid on several GPUs of one process ----------------------------------------------------------------------
+
+struct cpvs_grid {
+	cpvs_grid_desc desc{};
+	std::vector<int> devices;
+	std::vector<cpvs_ctx*> ctxs;
+	std::vector<cpvs_container*> containers;  // one per device (replicated) or only [0]
+	cpvs_grid_stats stats{};
+};
+
+namespace {
+
+int initialOwner(u32 x, u32 y, u32 length, int workers) { return (int)((y * length + (x + y) % length) % (u32)workers); }
+
+template <typename F>
+int runOnWorkers(std::vector<cpvs_grid_worker*>& workers, F fn) {
+	std::vector<std::thread> threads;
+	for (size_t i = 0; i < workers.size(); ++i)
+		threads.emplace_back([&, i]() {
+			cpvs_grid_worker* w = workers[i];
+			if (w->status != CPVS_OK) return;
+			const int rc = fn((int)i, w);
+			if (rc != CPVS_OK) {
+				w->status = rc;
+				w->error = cpvs_last_error();
+			}
+		});
+	for (std::thread& t : threads) t.join();
+	for (cpvs_grid_worker* w : workers)
+		if (w->status != CPVS_OK) return fail(w->status, "cpvs_grid_build (device %d): %s", w->ctx->device, w->error.c_str());
+	return CPVS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cpvs_grid_destroy(cpvs_grid* g) {
+	if (!g) return CPVS_OK;
+	for (cpvs_container* c : g->containers) cpvs_container_destroy(c);
+	for (cpvs_ctx* c : g->ctxs) cpvs_ctx_destroy(c);
+	delete g;
+	return CPVS_OK;
+}
+
+int cpvs_grid_build(const int* devices, int numDevices, const cpvs_grid_desc* desc, int replicate, cpvs_grid** out) {
+	if (!devices || numDevices < 1 || numDevices > CPVS_GRID_MAX_DEVICES || !desc || !out)
+		return fail(CPVS_EINVAL, "cpvs_grid_build: bad arguments (1..%d devices)", CPVS_GRID_MAX_DEVICES);
+	*out = nullptr;
+	cpvs_grid* g = new (std::nothrow) cpvs_grid();
+	if (!g) return fail(CPVS_ENOMEM, "cpvs_grid_build: host allocation");
+	g->desc = *desc;
+	g->devices.assign(devices, devices + numDevices);
+	std::vector<cpvs_grid_worker*> workers;
+	auto cleanup = [&](int rc) {
+		for (cpvs_grid_worker* w : workers) cpvs_grid_worker_destroy(w);
+		cpvs_grid_destroy(g);
+		return rc;
+	};
+	for (int d = 0; d < numDevices; ++d) {
+		cpvs_ctx* ctx = nullptr;
+		if (int rc = cpvs_ctx_create(devices[d], &ctx)) return cleanup(rc);
+		g->ctxs.push_back(ctx);
+		cpvs_grid_worker* w = nullptr;
+		if (int rc = cpvs_grid_worker_create(ctx, desc, &w)) return cleanup(rc);
+		workers.push_back(w);
+	}
+	// peer access for the replication (best effort: cudaMemcpyPeerAsync stages through the host without it)
+	for (int a = 0; a < numDevices; ++a)
+		for (int b = 0; b < numDevices; ++b)
+			if (a != b) {
+				int can = 0;
+				if (cudaDeviceCanAccessPeer(&can, devices[a], devices[b]) == cudaSuccess && can) {
+					cudaSetDevice(devices[a]);
+					if (cudaDeviceEnablePeerAccess(devices[b], 0) == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+				}
+			}
+	const u32 len = desc->length;
+	const int numTiles = (int)(len * len);
+	const double wall0 = nowMs();
+	std::vector<uint32_t> xy(2 * (size_t)numTiles);
+	std::vector<int> owner(numTiles);
+	for (u32 y = 0; y < len; ++y)
+		for (u32 x = 0; x < len; ++x) {
+			const int t = (int)(y * len + x);  // the reference's loop order: y outer, x inner (src/DeferredRenderer.cpp:170-171)
+			xy[2 * t] = x;
+			xy[2 * t + 1] = y;
+			owner[t] = initialOwner(x, y, len, numDevices);
+		}
+	cpvs_grid_stats& st = g->stats;
+	st.devices = (uint32_t)numDevices;
+	const bool costAware = numDevices > 1 && numTiles <= 4 * numDevices;
+	if (costAware) {
+		std::vector<uint64_t> cost(numTiles, 0);
+		int rc = runOnWorkers(workers, [&](int i, cpvs_grid_worker* w) {
+			for (int t = 0; t < numTiles; ++t)
+				if (owner[t] == i)
+					if (int e = cpvs_grid_worker_estimate(w, &xy[2 * t], 1, &cost[t])) return e;
+			return (int)CPVS_OK;
+		});
+		if (rc) return cleanup(rc);
+		std::vector<int> assigned(numTiles);
+		if (int e = cpvs_grid_assign(cost.data(), numTiles, numDevices, owner.data(), assigned.data())) return cleanup(e);
+		for (int t = 0; t < numTiles; ++t)
+			if (assigned[t] != owner[t]) {
+				++st.moved_tiles;
+				cpvs_grid_worker_release(workers[owner[t]], &xy[2 * t], 1);
+			}
+		owner = assigned;
+		rc = runOnWorkers(workers, [&](int i, cpvs_grid_worker* w) {
+			for (int t = 0; t < numTiles; ++t)
+				if (owner[t] == i)
+					if (int e = cpvs_grid_worker_build(w, &xy[2 * t], 1)) return e;
+			return (int)CPVS_OK;
+		});
+		if (rc) return cleanup(rc);
+	} else {
+		std::atomic<int> next(0);
+		const int rc = runOnWorkers(workers, [&](int i, cpvs_grid_worker* w) {
+			for (;;) {
+				const int t = next.fetch_add(1);
+				if (t >= numTiles) return (int)CPVS_OK;
+				owner[t] = i;
+				if (int e = cpvs_grid_worker_build(w, &xy[2 * t], 1)) return e;
+			}
+		});
+		if (rc) return cleanup(rc);
+	}
+	st.build_wall_ms = (float)(nowMs() - wall0);
+
+	// host-side gather of sizes: the only cross-GPU step of the build
+	const double gather0 = nowMs();
+	std::vector<cpvs_cell_part> parts((size_t)len * len * len);
+	std::vector<bool> have(parts.size(), false);
+	u32 numLevels = 0;
+	for (int d = 0; d < numDevices; ++d) {
+		std::vector<cpvs_grid_cell> cells((size_t)cpvs_grid_worker_num_cells(workers[d]) + 1);
+		const int n = cpvs_grid_worker_cells(workers[d], cells.data(), (int)cells.size());
+		if (n < 0) return cleanup(CPVS_EINTERNAL);
+		st.tiles[d] = workers[d]->built;
+		st.build_ms[d] = workers[d]->deviceMs;
+		st.build_ms_max = std::max(st.build_ms_max, workers[d]->deviceMs);
+		st.launches += cpvs_ctx_launch_count(workers[d]->ctx);
+		for (int i = 0; i < n; ++i) {
+			const cpvs_grid_cell& c = cells[i];
+			parts[c.index] = cpvs_cell_part{c.words, c.root_mask, c.device, c.words_device};
+			have[c.index] = true;
+			numLevels = c.num_levels;
+			st.svo_nodes += c.svo_nodes;
+			st.dag_nodes += c.dag_nodes;
+			st.dag_words += c.words;
+			if (c.words == 1) ++st.one_word_cells;
+		}
+	}
+	for (size_t i = 0; i < have.size(); ++i)
+		if (!have[i]) return cleanup(fail(CPVS_EINTERNAL, "cpvs_grid_build: cell %zu was never built", i));
+	st.cells = (uint32_t)parts.size();
+	st.gather_ms = (float)(nowMs() - gather0);
+
+	// replication for the lookups: one container per GPU (or only on the first), filled with peer copies
+	const double rep0 = nowMs();
+	const int copies = replicate ? numDevices : 1;
+	g->containers.assign(copies, nullptr);
+	{
+		std::vector<std::thread> threads;
+		std::vector<int> rcs(copies, CPVS_OK);
+		std::vector<std::string> errs(copies);
+		const bool useLeaf = desc->leafmasks && numLevels >= 5;
+		for (int d = 0; d < copies; ++d)
+			threads.emplace_back([&, d]() {
+				rcs[d] = containerFromParts(g->ctxs[d], len, numLevels, useLeaf ? 1 : 0, parts.data(), &g->containers[d]);
+				if (rcs[d] != CPVS_OK) errs[d] = cpvs_last_error();
+			});
+		for (std::thread& t : threads) t.join();
+		for (int d = 0; d < copies; ++d)
+			if (rcs[d] != CPVS_OK) return cleanup(fail(rcs[d], "cpvs_grid_build (replicate to device %d): %s", devices[d], errs[d].c_str()));
+	}
+	st.replicate_ms = (float)(nowMs() - rep0);
+	st.wall_ms = (float)(nowMs() - wall0);
+	for (cpvs_grid_worker* w : workers) cpvs_grid_worker_destroy(w);  // the cells now live in the containers
+	workers.clear();
+	*out = g;
+	return CPVS_OK;
+}
+
+int cpvs_grid_stats_get(const cpvs_grid* g, cpvs_grid_stats* out) {
+	if (!g || !out) return fail(CPVS_EINVAL, "cpvs_grid_stats_get: NULL argument");
+	*out = g->stats;
+	return CPVS_OK;
+}
+
+cpvs_container* cpvs_grid_container(const cpvs_grid* g, int index) {
+	return (g && index >= 0 && index < (int)g->containers.size()) ? g->containers[index] : nullptr;
+}
+
+// traverse.cs over the whole grid: the batch is split by rows over the GPUs that hold a replica.
+int cpvs_grid_lookup_ndc(const cpvs_grid* g, const float* ndcHost, int64_t count, uint8_t* outHost) {
+	if (!g || g->containers.empty() || count < 0 || (count > 0 && (!ndcHost || !outHost))) return fail(CPVS_EINVAL, "cpvs_grid_lookup_ndc: bad arguments");
+	const int parts = (int)g->containers.size();
+	std::vector<std::thread> threads;
+	std::vector<int> rcs(parts, CPVS_OK);
+	for (int d = 0; d < parts; ++d)
+		threads.emplace_back([&, d]() {
+			const int64_t lo = count * d / parts, hi = count * (d + 1) / parts;
+			rcs[d] = cpvs_container_lookup_ndc(g->containers[d], ndcHost + 3 * lo, hi - lo, CPVS_MEM_HOST, outHost + lo);
+		});
+	for (std::thread& t : threads) t.join();
+	for (int rc : rcs)
+		if (rc != CPVS_OK) return fail(rc, "cpvs_grid_lookup_ndc: a device failed");
+	return CPVS_OK;
+}
+
+}  // extern "C"

@@ -78,6 +78,9 @@ struct cpvs_ctx {
 	unsigned headroomShift;  // capacities = predicted + (predicted >> headroomShift) + slack
 	std::vector<cpvs::SizeMemo> memos;
 	cpvs::u64 predictedBuilds, exactBuilds, overflowRebuilds, reemissions;  // statistics (cpvs_ctx_stats)
+	// Sides of the depth maps whose last build did NOT use the per-column leaf builder (cities, planes): hierarchies of
+	// that side skip the column residues, which only that builder reads.
+	std::vector<int> noColumnSides;
 	cpvs::u64 buildSerial;  // builds enqueued so far: a pending build whose serial is the latest still owns the arena's contents
 };
 
@@ -87,6 +90,10 @@ struct cpvs_minmax {
 	int numLevels;
 	float* ownedDepth;    // device copy when built from host memory
 	float* levelStorage;  // levels 1.. in one allocation
+	// The depth map re-encoded per 8x8 column for the per-column leaf builder (pyramid.cu), valid for builds with
+	// `residueTiles` z-slices; NULL when it was not produced.
+	unsigned char* residue;
+	cpvs::u32 residueTiles;
 	const float* level[cpvs::kMaxLevels];
 	cudaEvent_t evStart, evBase, evStop;
 	// Levels 1 and 2 are not needed by the leafmask builder and are only produced on first use.

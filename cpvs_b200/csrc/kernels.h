@@ -9,8 +9,10 @@ namespace cpvs {
 // levels[k] (k >= 1) points at (n>>k)^2 float2 (min,max); levels[0] = depth.
 // afterBase (optional) is recorded right after the fused base kernel. With writeLowLevels == false (and
 // n >= 128) levels 1 and 2 are left unwritten; launchPyramidLowLevels produces them later if needed.
-int launchPyramid(const float* depth, int n, float* const* levels, int numLevels, bool writeLowLevels, cudaEvent_t afterBase,
-		cudaStream_t stream);
+// residue (optional, n >= 128): n * n bytes, the depth map re-encoded per 8x8 column for the per-column leaf builder of
+// builds with `residueTiles` z-slices (see pyramid.cu).
+int launchPyramid(const float* depth, int n, float* const* levels, int numLevels, bool writeLowLevels, unsigned char* residue, unsigned residueTiles,
+		cudaEvent_t afterBase, cudaStream_t stream);
 int launchPyramidLowLevels(const float* depth, int n, float* const* levels, cudaStream_t stream);
 
 // ---- svo.cu: constructSvo (reference src/CompressedShadow.cpp:87-190) ----
@@ -70,7 +72,7 @@ int launchExpandSmallLevels(const SmallExpandArgs& a, cudaStream_t stream);
 
 // Level-2 nodes: the leaf's k-code (codes[leaf*8 + row], nibble x = lit slices of texel (x,row)), a
 // 64-bit hash of it and the 16-bit 1x1x8 childmask (2 bits per slice).
-// Also sets one bit per leaf hash in `sketch` (kSketchWords zeroed words): a linear-counting estimate of
+// Also sets one bit per leaf hash in `sketch` (kSketchWords zeroed words; NULL: skipped): a linear-counting estimate of
 // the number of distinct leaves, used to size the merge table so that it stays resident in L2.
 constexpr u32 kSketchWords = 1u << 22;  // 2^27 bits, 16 MiB
 int launchBuildLeaves(const PyramidView& pyr, u32 zTileNum, const u64* coords, const u64* nDev, u64 cap, u32* codes, u64* hashes, u16* masks,
@@ -81,8 +83,10 @@ int launchBuildLeaves(const PyramidView& pyr, u32 zTileNum, const u64* coords, c
 // level, written by the expansion of level 3.
 int launchColumnBias(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, u32* colBias, ScanLaunch scan, cudaStream_t stream);
 // (No hash array: the insert derives its hash from the code when MergeLevelArgs::leafHash is NULL.)
+// residue: the hierarchy's re-encoded depth map for this zTileNum, or NULL (then, and for columns taller than 31 z-blocks,
+// the depth map itself is read). tallFlag: one zeroed device word of scratch.
 int launchBuildLeafColumns(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, const u32* colBias, const u32* leafAt, u32 numLeaves, u32* codes,
-		u16* masks, u32* sketch, cudaStream_t stream);
+		u16* masks, u32* sketch, const unsigned char* residue, u32* tallFlag, cudaStream_t stream);
 int launchSketchPopcount(const u32* sketch, u64* setBits, cudaStream_t stream);
 
 // ---- merge.cu: mergeCommonSubtrees (reference src/CompressedShadow.cpp:215-304, Util.h:154-182) ----
@@ -134,8 +138,9 @@ struct SmallMergeArgs {
 };
 int launchMergeSmallLevels(const SmallMergeArgs& a, cudaStream_t stream);
 
-// Leaf level only: picks the table capacity from the sketch's set-bit count and clears that many slots.
-int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* tableMaskDev, cudaStream_t stream);
+// Leaf level only: picks the table capacity from the sketch's set-bit count -- or from expectedDistinct (> 0: the previous
+// build's count of distinct leaves plus head room; no sketch then) -- and clears that many slots.
+int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* tableMaskDev, u64 expectedDistinct, cudaStream_t stream);
 // Insert assigns group ids (all the parent level needs); rank orders the unique nodes and may run
 // concurrently with the next level's insert as long as this level's table is left alone.
 int launchInsertLevel(const MergeLevelArgs& a, cudaStream_t stream);

@@ -27,6 +27,7 @@ namespace cpvs {
 namespace {
 
 constexpr u64 kEmpty = ~0ull;
+constexpr u64 kMaxProbes = 4096;
 static_assert(kDirectSlots == 256, "one direct slot per thread of the insert CTA");
 // gid = table slot (< 2^31) | kCandidateFlag; consumers of the group id strip the flag (kGidMask).
 constexpr u32 kCandidateFlag = 0x80000000u, kGidMask = 0x7FFFFFFFu;
@@ -37,7 +38,10 @@ __device__ __forceinline__ u32 findGroupSlot(u64* __restrict__ table, u64 tableM
 	const u64 fp = hash >> 32;
 	const u64 key = (fp << 32) | self;
 	u64 slot = hash & tableMask;
-	for (u64 probes = 0; probes <= tableMask; ++probes) {
+	// (a probe sequence this long means the table was sized for far fewer groups than there are -- a prediction that failed:
+	// give up at once, the host rebuilds with a table sized from the data)
+	for (u64 probes = 0; probes <= tableMask && probes < kMaxProbes; ++probes) {
+		if ((probes & 63u) == 63u && ldRelaxed32(errorFlag)) return 0u;  // somebody already found the table too small
 		u64 v = kShared ? *reinterpret_cast<volatile u64*>(table + slot) : ldRelaxed64(table + slot);
 		if (v == kEmpty) {
 			const u64 old = atomicCAS(reinterpret_cast<unsigned long long*>(table + slot), (unsigned long long)kEmpty, (unsigned long long)key);
@@ -66,10 +70,10 @@ __device__ __forceinline__ u32 findGroupSlot(u64* __restrict__ table, u64 tableM
 // up to a power of two with >= 1.5x headroom, then cleared. The result does not depend on the capacity,
 // only the speed does: a table sized for the distinct leaves (not for all leaves) stays in L2.
 __global__ void __launch_bounds__(256) sizeAndClearLeafTableKernel(u64* __restrict__ table, u64 maxSlots, const u64* __restrict__ setBits,
-		u64* __restrict__ tableMaskDev) {
+		u64* __restrict__ tableMaskDev, float expectedDistinct) {
 	const float m = (float)kSketchWords * 32.0f;
 	const float frac = fminf((float)*setBits / m, 0.999f);
-	const float distinct = -m * log1pf(-frac);
+	const float distinct = expectedDistinct > 0.f ? expectedDistinct : -m * log1pf(-frac);
 	u64 want = (u64)(distinct * 1.5f) + 4096u;
 	u64 cap = 4096;
 	while (cap < want && cap < maxSlots) cap <<= 1;
@@ -161,7 +165,7 @@ __global__ void __launch_bounds__(256) insertLeavesBatchKernel(const u32* __rest
 		}
 	}
 	for (u32 round = 0; pending; ++round) {
-		if (round > tableMask) {  // table full: cannot happen with a sane size estimate; reported to the host
+		if (round > tableMask || round >= kMaxProbes) {  // table full: cannot happen with a sane size estimate; reported to the host
 			atomicExch(errorFlag, 1u);
 			break;
 		}
@@ -599,8 +603,8 @@ int launchMergeSmallLevels(const SmallMergeArgs& a, cudaStream_t stream) {
 	return 1;
 }
 
-int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* tableMaskDev, cudaStream_t stream) {
-	sizeAndClearLeafTableKernel<<<148 * 8, 256, 0, stream>>>(table, maxSlots, setBits, tableMaskDev);
+int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* tableMaskDev, u64 expectedDistinct, cudaStream_t stream) {
+	sizeAndClearLeafTableKernel<<<148 * 8, 256, 0, stream>>>(table, maxSlots, setBits, tableMaskDev, (float)expectedDistinct);
 	return 1;
 }
 

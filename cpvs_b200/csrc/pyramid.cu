@@ -22,9 +22,15 @@ __device__ __forceinline__ float2 reduce4(float2 a, float2 b, float2 c, float2 d
 // kWriteLow = false skips the stores of levels 1 and 2: the leafmask builder never reads them (it
 // classifies against levels >= 3 and builds leaves from level 0), and they are 37% of this kernel's
 // traffic. They are produced on demand (launchPyramidLowLevels) for accessors and the leafmask-less mode.
-template <bool kWriteLow>
+// kResidue: also writes the depth map re-encoded for the per-column leaf builder (svo.cu buildLeafColumnsResidueKernel): per
+// 8x8-texel column 64 bytes, 8 per row in the order x = 0 4 1 5 2 6 3 7, byte = clamp(T - 8*lo, 0, 255), where T = floor(fl(depth * H) + 0.5) is the number of
+// lit slices below the texel (H = n * zTileNum) and lo the column's first z-block, floor(fl(min * H/8)) of its level-3 texel.
+// A leaf's k-code is min(residue - 8 * block, 8) per texel, so the builder reads 1 byte per texel instead of 4 and
+// needs no float arithmetic; columns taller than 31 z-blocks (box edges) do not fit a byte and keep the depth path.
+template <bool kWriteLow, bool kResidue>
 __global__ void __launch_bounds__(256) pyramidBaseKernel(const float* __restrict__ depth, int n, float2* __restrict__ l1,
-		float2* __restrict__ l2, float2* __restrict__ l3, float2* __restrict__ l4, float2* __restrict__ l5) {
+		float2* __restrict__ l2, float2* __restrict__ l3, float2* __restrict__ l4, float2* __restrict__ l5, unsigned char* __restrict__ residue,
+		float heightF, float height3F) {
 	__shared__ float2 s2[8][32];
 	__shared__ float2 s3[4][16];
 	__shared__ float2 s4[2][8];
@@ -64,6 +70,30 @@ __global__ void __launch_bounds__(256) pyramidBaseKernel(const float* __restrict
 		s3[y][x] = v;
 	}
 	__syncthreads();
+	if (kResidue) {
+		// the thread's 4 x 4 texels are rows (warp & 1) * 4 .. + 3, bytes (lane & 1) * 4 .. + 3 of column (lane >> 1, warp >> 1)
+		const float lo3 = fmaxf(floorf(__fmul_rn(s3[warp >> 1][lane >> 1].x, height3F)), 0.0f);  // NaN: 0, as columnRange
+		const float shift = __fsub_rn(0.5f, __fmul_rn(lo3, 8.0f));                             // exact
+		unsigned char* col = residue + ((size_t)(by3 + (warp >> 1)) * n3 + bx3 + (lane >> 1)) * 64 + (warp & 1) * 32 + (lane & 1) * 4;
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			const float d[4] = {r[i].x, r[i].y, r[i].z, r[i].w};
+			unsigned int b[4];
+#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				// floor of the exact sum (rounded toward -inf, which never crosses an integer), clamped; the second sum parks the
+				// integer in the low mantissa bits. NaN is dropped by fmaxf: residue 0 = never lit, as midZ <= NaN is false.
+				float x = __fadd_rd(__fmul_rn(d[k], heightF), shift);
+				x = fminf(fmaxf(x, 0.0f), 255.0f);
+				b[k] = __float_as_uint(__fadd_rd(x, 8388608.0f));
+			}
+			const unsigned int lo = __byte_perm(b[0], b[1], 0x0040), hi = __byte_perm(b[2], b[3], 0x0040);
+			// A row is stored with texels x and x + 4 next to each other (bytes 0 4 1 5 | 2 6 3 7): the builder works on such
+			// pairs. The even lane holds texels 0..3 of the row, its odd neighbour 4..7; each writes one of the two words.
+			const unsigned int mine = __byte_perm(lo, hi, 0x5410), other = __shfl_xor_sync(0xFFFFFFFFu, mine, 1);
+			*reinterpret_cast<unsigned int*>(col + i * 8) = (lane & 1) ? __byte_perm(mine, other, 0x3726) : __byte_perm(mine, other, 0x5140);
+		}
+	}
 	if (threadIdx.x < 16) {
 		const int x = threadIdx.x & 7, y = threadIdx.x >> 3;
 		const float2 v = reduce4(s3[2 * y][2 * x], s3[2 * y][2 * x + 1], s3[2 * y + 1][2 * x], s3[2 * y + 1][2 * x + 1]);
@@ -140,17 +170,23 @@ int launchPyramidLowLevels(const float* depth, int n, float* const* levels, cuda
 	return 2;
 }
 
-int launchPyramid(const float* depth, int n, float* const* levels, int numLevels, bool writeLowLevels, cudaEvent_t afterBase, cudaStream_t stream) {
+int launchPyramid(const float* depth, int n, float* const* levels, int numLevels, bool writeLowLevels, unsigned char* residue, unsigned residueTiles,
+		cudaEvent_t afterBase, cudaStream_t stream) {
 	int launches = 0;
 	int next = 1;
 	if (n >= 128) {
 		dim3 grid(n / 128, n / 32);
 		float2 *l1 = reinterpret_cast<float2*>(levels[1]), *l2 = reinterpret_cast<float2*>(levels[2]), *l3 = reinterpret_cast<float2*>(levels[3]),
 			   *l4 = reinterpret_cast<float2*>(levels[4]), *l5 = reinterpret_cast<float2*>(levels[5]);
-		if (writeLowLevels)
-			pyramidBaseKernel<true><<<grid, 256, 0, stream>>>(depth, n, l1, l2, l3, l4, l5);
+		const float heightF = (float)((unsigned)n * residueTiles), height3F = (float)(((unsigned)n >> 3) * residueTiles);
+		if (writeLowLevels && residue)
+			pyramidBaseKernel<true, true><<<grid, 256, 0, stream>>>(depth, n, l1, l2, l3, l4, l5, residue, heightF, height3F);
+		else if (writeLowLevels)
+			pyramidBaseKernel<true, false><<<grid, 256, 0, stream>>>(depth, n, l1, l2, l3, l4, l5, nullptr, 0.f, 0.f);
+		else if (residue)
+			pyramidBaseKernel<false, true><<<grid, 256, 0, stream>>>(depth, n, l1, l2, l3, l4, l5, residue, heightF, height3F);
 		else
-			pyramidBaseKernel<false><<<grid, 256, 0, stream>>>(depth, n, l1, l2, l3, l4, l5);
+			pyramidBaseKernel<false, false><<<grid, 256, 0, stream>>>(depth, n, l1, l2, l3, l4, l5, nullptr, 0.f, 0.f);
 		++launches;
 		next = 6;
 	}

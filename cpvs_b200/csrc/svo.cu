@@ -369,9 +369,11 @@ __global__ void __launch_bounds__(256, 8) buildLeavesKernel(const float* __restr
 	// distinct-count sketch (linear counting): one bit per hash value, read back by sizeLeafTable
 	// (read first: on repetitive maps nearly every leaf finds its bit already set, and the atomics of a
 	// popular hash would otherwise serialise on one address)
-	const u32 bit = (u32)(h >> 20);
-	u32* word = bitmap + ((bit >> 5) & bitmapWordMask);
-	if (!(__ldcg(word) & (1u << (bit & 31u)))) atomicOr(word, 1u << (bit & 31u));
+	if (bitmap) {
+		const u32 bit = (u32)(h >> 20);
+		u32* word = bitmap + ((bit >> 5) & bitmapWordMask);
+		if (!(__ldcg(word) & (1u << (bit & 31u)))) atomicOr(word, 1u << (bit & 31u));
+	}
 }
 
 // ---- leaf columns ---------------------------------------------------------------------------------
@@ -483,6 +485,9 @@ __constant__ u64 kLaneHashMul[4] = {0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full
 
 // The leaves chunk..chunkEnd-1 (warp-uniform bounds) of the eight columns of a warp. firstIdx: leafAt of the lane's leaf of
 // the very first batch if the caller fetched it ahead (only looked at for chunk == 0).
+// kSketch = false: the leaf table will be sized from the previous build's count of distinct leaves, so neither the hash nor
+// the sketch is needed (a third of the instructions of a batch).
+template <bool kSketch>
 __device__ __forceinline__ void emitColumnLeaves(const LeafColumn& c, const __half2 (&r0)[4], const __half2 (&r1)[4], u32 chunk, u32 chunkEnd,
 		u32 firstIdx, bool haveFirstIdx, const LeafSink& out, PendingSketch& pending) {
 	const u32 lane = threadIdx.x & 31u, sub = lane & 3u, groupLane = lane & ~3u;
@@ -516,15 +521,17 @@ __device__ __forceinline__ void emitColumnLeaves(const LeafColumn& c, const __ha
 			w1 -= kStrip;
 			negI2 = __hsub2(negI2, one2);
 			if (leaf != kNoLeaf) *reinterpret_cast<uint2*>(out.codes + (u64)leaf * 8u + sub * 2u) = make_uint2(w0, w1);
-			hp[j] = ((((u64)w1) << 32) | w0) * mulK;
+			if (kSketch) hp[j] = ((((u64)w1) << 32) | w0) * mulK;
 		}
-		// lane `sub` ends up with the sum over the four lanes of hp[sub]: a 4 x 4 reduce-scatter in two exchanges
-		const bool hi = (sub & 2u) != 0, odd = (sub & 1u) != 0;
-		const u64 k0 = (hi ? hp[2] : hp[0]) + __shfl_xor_sync(0xFFFFFFFFu, hi ? hp[0] : hp[2], 2);
-		const u64 k1 = (hi ? hp[3] : hp[1]) + __shfl_xor_sync(0xFFFFFFFFu, hi ? hp[1] : hp[3], 2);
-		const u64 keep = (odd ? k1 : k0) + __shfl_xor_sync(0xFFFFFFFFu, odd ? k0 : k1, 1);
+		u64 keep = 0;
+		if (kSketch) {
+			// lane `sub` ends up with the sum over the four lanes of hp[sub]: a 4 x 4 reduce-scatter in two exchanges
+			const bool hi = (sub & 2u) != 0, odd = (sub & 1u) != 0;
+			const u64 k0 = (hi ? hp[2] : hp[0]) + __shfl_xor_sync(0xFFFFFFFFu, hi ? hp[0] : hp[2], 2);
+			const u64 k1 = (hi ? hp[3] : hp[1]) + __shfl_xor_sync(0xFFFFFFFFu, hi ? hp[1] : hp[3], 2);
+			keep = (odd ? k1 : k0) + __shfl_xor_sync(0xFFFFFFFFu, odd ? k0 : k1, 1);
+		}
 		if (mineIdx != kNoLeaf) {
-			const u64 h = mix64(keep);
 			const float z8 = __fmul_rn(__fadd_rn(c.lo, __uint2float_rn(m + sub)), 8.0f);
 			const u32 kmin = (u32)fminf(fmaxf(__fsub_rn(c.tMin, z8), 0.f), 8.f), kmax = (u32)fminf(fmaxf(__fsub_rn(c.tMax, z8), 0.f), 8.f);
 			// slices below kmin are lit (01), slices from kmax up are shadowed (00), the rest PARTIAL (10)
@@ -532,8 +539,11 @@ __device__ __forceinline__ void emitColumnLeaves(const LeafColumn& c, const __ha
 			out.masks[mineIdx] = (u16)((0x5555u & below) | (0xAAAAu & ((1u << (2u * kmax)) - 1u) & ~below));
 			// the hash only feeds the sketch here: the insert recomputes its own from the code it reads anyway, which is
 			// cheaper than 8-byte stores scattered over the level (partial sectors: a fill and a write-back each)
-			const u32 bit = (u32)(h >> 20);
-			pending.post(out.bitmap + ((bit >> 5) & out.bitmapWordMask), 1u << (bit & 31u));
+			if (kSketch) {
+				const u64 h = mix64(keep);
+				const u32 bit = (u32)(h >> 20);
+				pending.post(out.bitmap + ((bit >> 5) & out.bitmapWordMask), 1u << (bit & 31u));
+			}
 		}
 	}
 }
@@ -542,8 +552,15 @@ __device__ __forceinline__ void emitColumnLeaves(const LeafColumn& c, const __ha
 // four rows of 256 contiguous bytes), software-pipelined in registers so that no load is waited for: a group's level-3
 // texel and colBias are fetched two groups ahead; its depth rows and the leafAt of its first batch one group ahead, and only
 // if the column has leaves (most columns of a z-slice of a tall grid have none). Warps never synchronise with each other.
+// tallOnly != NULL: the residue kernel below has built every column of at most kResidueBlocks z-blocks; this launch only
+// walks the taller ones (box edges), and not at all if *tallOnly says there are none.
+constexpr u32 kResidueBlocks = 31;
+template <bool kSketch>
 __global__ void __launch_bounds__(256, 3) buildLeafColumnsKernel(const float* __restrict__ depth, u32 n, u32 colShift, float heightF,
-		float height3F, float zLoF, float zHiF, const float2* __restrict__ level3, u32 numCols, const u32* __restrict__ colBias, LeafSink out) {
+		float height3F, float zLoF, float zHiF, const float2* __restrict__ level3, u32 numCols, const u32* __restrict__ colBias, LeafSink out,
+		const u32* __restrict__ tallOnly) {
+	if (tallOnly && *tallOnly == 0u) return;
+	const float topF = __fadd_rn(height3F, -1.0f);
 	const u32 lane = threadIdx.x & 31u, sub = lane & 3u;
 	const u32 numWarps = gridDim.x * (blockDim.x >> 5), numGroups = (numCols + 7u) >> 3;
 	u32 group = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -572,6 +589,12 @@ __global__ void __launch_bounds__(256, 3) buildLeafColumnsKernel(const float* __
 		c1.cnt = 0;
 		const u32 col = g * 8u + (lane >> 2);
 		if (g < numGroups && col < numCols) columnRange(mm1, height3F, zLoF, zHiF, c1.lo, c1.cnt);
+		if (tallOnly && c1.cnt) {  // (the residue kernel decides by the column's extent over all z-slices)
+			float loAll;
+			u32 cntAll;
+			columnRange(mm1, height3F, 0.0f, topF, loAll, cntAll);
+			if (cntAll <= kResidueBlocks) c1.cnt = 0;
+		}
 		c1.first = bias2 + (u32)c1.lo;
 		idx1 = kNoLeaf;
 		if (c1.cnt) {
@@ -602,7 +625,7 @@ __global__ void __launch_bounds__(256, 3) buildLeafColumnsKernel(const float* __
 		fetchRows(group + numWarps);
 		fetchTexel(group + 2u * numWarps);
 		if (maxCnt == 0) continue;
-		emitColumnLeaves(c, r0, r1, 0, min(maxCnt, kChunkBlocks), firstIdx, true, out, pending);
+		emitColumnLeaves<kSketch>(c, r0, r1, 0, min(maxCnt, kChunkBlocks), firstIdx, true, out, pending);
 		for (u32 chunk = kChunkBlocks; chunk < maxCnt; chunk += kChunkBlocks) {  // tall columns (box edges): re-read the rows
 			if (c.cnt) {
 				const u32 col = group * 8u + (lane >> 2);
@@ -610,10 +633,98 @@ __global__ void __launch_bounds__(256, 3) buildLeafColumnsKernel(const float* __
 				const float* p = depth + (size_t)(cy * 8u + sub * 2u) * n + cx * 8u;
 				rowsToR(ldSector256(p), ldSector256(p + n), heightF, __fadd_rn(c.lo, __uint2float_rn(chunk)), r0, r1);
 			}
-			emitColumnLeaves(c, r0, r1, chunk, min(maxCnt, chunk + kChunkBlocks), kNoLeaf, false, out, pending);
+			emitColumnLeaves<kSketch>(c, r0, r1, chunk, min(maxCnt, chunk + kChunkBlocks), kNoLeaf, false, out, pending);
 		}
 	}
 	pending.flush();
+}
+
+// ---- leaf columns from the hierarchy's residues -----------------------------------------------------------------------
+// The same leaves from the re-encoded depth map the pyramid's base kernel leaves behind (pyramid.cu): byte (row, x) of a
+// column = clamp(T - 8 * lo, 0, 255) with lo the column's first z-block over ALL z-slices -- the R of rowsToR above, already
+// computed. A lane owns rows 2*sub and 2*sub+1: one 16-byte load instead of two 32-byte ones, and a byte permute plus a
+// subtraction per texel pair instead of the float arithmetic (the bytes of a pair sit next to each other; 0x64 above a
+// byte is the fp16 1024 + byte). Columns taller than kResidueBlocks are left to buildLeafColumnsKernel.
+template <bool kSketch>
+__global__ void __launch_bounds__(256, 4) buildLeafColumnsResidueKernel(const uint4* __restrict__ residue, float heightF, float height3F,
+		float zLoF, float zHiF, const float2* __restrict__ level3, u32 numCols, const u32* __restrict__ colBias, LeafSink out, u32* __restrict__ tallFlag) {
+	const u32 lane = threadIdx.x & 31u, sub = lane & 3u;
+	const u32 numWarps = gridDim.x * (blockDim.x >> 5), numGroups = (numCols + 7u) >> 3;
+	const float topF = __fadd_rn(height3F, -1.0f);
+	u32 group = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	PendingSketch pending;
+	bool sawTall = false;
+
+	// stage 2 (two groups ahead): level-3 texel and bias
+	float2 mm2 = make_float2(0.f, 0.f);
+	u32 bias2 = 0;
+	auto fetchTexel = [&](u32 g) {
+		const u32 col = g * 8u + (lane >> 2);
+		mm2 = make_float2(0.f, 0.f);  // an empty column (lo > hi)
+		bias2 = 0;
+		if (g < numGroups && col < numCols) {
+			mm2 = level3[col];
+			bias2 = colBias[col];
+		}
+	};
+	// stage 1 (one group ahead): column range, residue rows, first leafAt batch
+	LeafColumn c1;
+	float delta1 = 0.f;
+	u32 idx1 = kNoLeaf;
+	uint4 r1 = make_uint4(0u, 0u, 0u, 0u);
+	auto fetchRows = [&](u32 g) {  // consumes stage 2
+		c1.lo = 0.f;
+		c1.cnt = 0;
+		delta1 = 0.f;
+		const u32 col = g * 8u + (lane >> 2);
+		if (g < numGroups && col < numCols) {
+			float loAll;
+			u32 cntAll;
+			columnRange(mm2, height3F, 0.0f, topF, loAll, cntAll);
+			columnRange(mm2, height3F, zLoF, zHiF, c1.lo, c1.cnt);
+			if (cntAll > kResidueBlocks) {  // does not fit a byte: the depth-based kernel builds this column
+				sawTall = sawTall || c1.cnt != 0;
+				c1.cnt = 0;
+			}
+			delta1 = __fmul_rn(__fsub_rn(c1.lo, loAll), 8.0f);  // slices between the column's first block and this z-slice's first block
+		}
+		c1.tMin = litSlicesBelow(__fmul_rn(mm2.x, heightF));
+		c1.tMax = litSlicesBelow(__fmul_rn(mm2.y, heightF));
+		c1.first = bias2 + (u32)c1.lo;
+		idx1 = kNoLeaf;
+		if (c1.cnt) {
+			r1 = residue[(size_t)col * 4u + sub];
+			if (sub < c1.cnt && c1.first + sub < out.numLeaves) idx1 = out.leafAt[c1.first + sub];
+		}
+	};
+	fetchTexel(group);
+	fetchRows(group);
+	fetchTexel(group + numWarps);
+	for (; group < numGroups; group += numWarps) {
+		// stage 0: this group. Its residues become R right away so that the registers can take the next group's loads.
+		const LeafColumn c = c1;
+		const u32 firstIdx = idx1;
+		const u32 maxCnt = __reduce_max_sync(0xFFFFFFFFu, c.cnt);
+		__half2 r0[4], r1h[4];
+		{
+			const u32 words[4] = {r1.x, r1.y, r1.z, r1.w};
+			// 1024 + byte as fp16, then minus (1024 + the slice's offset), clamped at 0 (whole-volume builds: offset 0)
+			const __half2 base2 = __float2half2_rn(__fadd_rn(1024.0f, fminf(delta1, 1016.0f))), zero2 = __float2half2_rn(0.f);
+#pragma unroll
+			for (int p = 0; p < 4; ++p) {
+				const u32 a = __byte_perm(words[p >> 1], 0x64646464u, (p & 1) ? 0x4342u : 0x4140u);
+				const u32 b = __byte_perm(words[2 + (p >> 1)], 0x64646464u, (p & 1) ? 0x4342u : 0x4140u);
+				r0[p] = __hmax2(__hsub2(*reinterpret_cast<const __half2*>(&a), base2), zero2);
+				r1h[p] = __hmax2(__hsub2(*reinterpret_cast<const __half2*>(&b), base2), zero2);
+			}
+		}
+		fetchRows(group + numWarps);
+		fetchTexel(group + 2u * numWarps);
+		if (maxCnt == 0) continue;
+		emitColumnLeaves<kSketch>(c, r0, r1h, 0, maxCnt, firstIdx, true, out, pending);
+	}
+	pending.flush();
+	if (__any_sync(0xFFFFFFFFu, sawTall) && lane == 0) atomicOr(tallFlag, 1u);
 }
 
 // Number of set bits of the sketch -> *setBits (zeroed beforehand).
@@ -699,7 +810,7 @@ int launchColumnBias(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, u32* 
 }
 
 int launchBuildLeafColumns(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum, const u32* colBias, const u32* leafAt, u32 numLeaves, u32* codes,
-		u16* masks, u32* sketch, cudaStream_t stream) {
+		u16* masks, u32* sketch, const unsigned char* residue, u32* tallFlag, cudaStream_t stream) {
 	const u32 side3 = (u32)pyr.n >> 3, numCols = side3 * side3;
 	u32 colShift = 0;
 	while ((1u << colShift) < side3) ++colShift;
@@ -708,9 +819,24 @@ int launchBuildLeafColumns(const PyramidView& pyr, u32 zTileIndex, u32 zTileNum,
 	const float2* level3 = reinterpret_cast<const float2*>(pyr.level[3]);
 	LeafSink out{leafAt, numLeaves, codes, masks, sketch, kSketchWords - 1};
 	const u32 wanted = (numCols + kColumnsPerCta - 1) / kColumnsPerCta;  // 8 warps of 8 columns per CTA
-	buildLeafColumnsKernel<<<wanted < 148u * 3u ? wanted : 148u * 3u, 256, 0, stream>>>(pyr.level[0], (u32)pyr.n, colShift, heightF, height3F,
-			zLoF, zHiF, level3, numCols, colBias, out);
-	return 1;
+	const u32 gridResidue = wanted < 148u * 4u ? wanted : 148u * 4u, gridDepth = wanted < 148u * 3u ? wanted : 148u * 3u;
+	const u32* tallOnly = residue ? tallFlag : nullptr;
+	int launches = 1;
+	if (residue) {
+		const uint4* res4 = reinterpret_cast<const uint4*>(residue);
+		if (sketch)
+			buildLeafColumnsResidueKernel<true><<<gridResidue, 256, 0, stream>>>(res4, heightF, height3F, zLoF, zHiF, level3, numCols, colBias, out, tallFlag);
+		else
+			buildLeafColumnsResidueKernel<false><<<gridResidue, 256, 0, stream>>>(res4, heightF, height3F, zLoF, zHiF, level3, numCols, colBias, out, tallFlag);
+		++launches;
+	}
+	if (sketch)
+		buildLeafColumnsKernel<true><<<gridDepth, 256, 0, stream>>>(pyr.level[0], (u32)pyr.n, colShift, heightF, height3F, zLoF, zHiF, level3, numCols, colBias,
+				out, tallOnly);
+	else
+		buildLeafColumnsKernel<false><<<gridDepth, 256, 0, stream>>>(pyr.level[0], (u32)pyr.n, colShift, heightF, height3F, zLoF, zHiF, level3, numCols, colBias,
+				out, tallOnly);
+	return launches;
 }
 
 int launchSketchPopcount(const u32* sketch, u64* setBits, cudaStream_t stream) {

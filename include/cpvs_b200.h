@@ -114,6 +114,11 @@ CPVS_API const char* cpvs_version(void);
  * n: side of the depth map (power of two, >= 2). A CPVS_MEM_DEVICE depth map is borrowed, not
  * copied: it must stay alive and unchanged for as long as the hierarchy is used. */
 CPVS_API int cpvs_minmax_build(cpvs_ctx* ctx, const float* depth, int n, int mem, cpvs_minmax** out);
+/* The same for a hierarchy whose builds will be cut into z_tile_num z-slices (createShadowTiles,
+ * src/DeferredRenderer.cpp:150-163): the construction pass also leaves the depth map re-encoded for the per-column leaf
+ * builder of exactly that slicing (1 byte per texel). Purely a speed hint: cpvs_shadow_create accepts any z_tile_num on
+ * any hierarchy and falls back to reading the depth map. cpvs_minmax_build is z_tile_num = 1. */
+CPVS_API int cpvs_minmax_build_tiled(cpvs_ctx* ctx, const float* depth, int n, int mem, uint32_t z_tile_num, cpvs_minmax** out);
 CPVS_API int cpvs_minmax_destroy(cpvs_minmax* mm);
 /* getNumLevels() (src/MinMaxHierarchy.h:60-62): log2(n) + 1. */
 CPVS_API int cpvs_minmax_num_levels(const cpvs_minmax* mm);
@@ -216,6 +221,84 @@ CPVS_API int cpvs_container_load(cpvs_ctx* ctx, const char* path, cpvs_container
 /* setFilterSize (src/CompressedShadowContainer.h:71-73): stored, unused -- as in the reference
  * (shader/traverse.cs:16-17). */
 CPVS_API int cpvs_container_set_filter_size(cpvs_container* c, uint32_t size);
+
+/* A container put together from cells that already sit in device memory -- possibly on other GPUs of the box (the words
+ * are fetched with cudaMemcpyPeerAsync): combineDAGs + createTopLevelGrid (src/CompressedShadowContainer.cpp:52-91) for a
+ * tile grid whose cells were built by several workers. cells: length^3 entries in container order
+ * ((z * length + y) * length + x); a cell of one word may leave words_device NULL (the word is its root mask). The result
+ * is finalized; its cells cannot be re-set. */
+typedef struct cpvs_cell_part {
+	uint64_t words;
+	uint32_t root_mask;           /* first word of the cell's DAG: 0x0000 all shadow, 0x5555 all lit, else partial */
+	int32_t device;               /* CUDA device of words_device */
+	const uint32_t* words_device;
+} cpvs_cell_part;
+CPVS_API int cpvs_container_assemble(cpvs_ctx* ctx, uint32_t length, uint32_t num_levels, int leafmasks, const cpvs_cell_part* cells,
+		cpvs_container** out);
+
+/* ---- tile grids over the GPUs of one box (src/DeferredRenderer.cpp:150-235) --------------------------
+ * renderWithTiles cuts the light frustum into length x length depth tiles, createShadowTiles builds `length` z-slice DAGs
+ * from each tile's hierarchy, precomputeShadows moves the container to the GPU. Here the xy tiles are sharded over GPUs:
+ * nothing crosses GPUs while building, the host gathers the cells' sizes and runs createTopLevelGrid's scan, and the
+ * finished words are replicated with peer copies for the lookups. No NCCL.
+ *
+ * cpvs_grid_build does all of it inside one process, one host thread per GPU. The worker calls underneath are exported
+ * for callers that run one process per GPU (torchrun): each process drives its own worker and exchanges the few bytes of
+ * costs and sizes through whatever host-side channel it has. */
+typedef struct cpvs_grid_desc {
+	uint32_t length;    /* cells per axis, a power of two: length^2 xy tiles, `length` z-slices each */
+	int32_t tile;       /* side of one depth tile (power of two) */
+	int32_t leafmasks;
+	int32_t scene;      /* CPVS_SCENE_*: tiles are generated on the owning GPU (cpvs_depth_generate); -1: fetch */
+	int (*fetch)(void* user, uint32_t x, uint32_t y, float* host_out); /* scene < 0: writes tile (x, y), tile*tile floats, returns 0 */
+	void* user;
+} cpvs_grid_desc;
+typedef struct cpvs_grid_cell {
+	uint32_t index;      /* cell index in the container: (z * length + y) * length + x */
+	uint32_t num_levels;
+	uint64_t words;
+	uint32_t root_mask;
+	int32_t device;
+	const uint32_t* words_device;
+	uint64_t svo_nodes, dag_nodes;
+} cpvs_grid_cell;
+typedef struct cpvs_grid_worker cpvs_grid_worker;
+CPVS_API int cpvs_grid_worker_create(cpvs_ctx* ctx, const cpvs_grid_desc* desc, cpvs_grid_worker** out);
+CPVS_API int cpvs_grid_worker_destroy(cpvs_grid_worker* w);
+/* Cost of `count` xy tiles (pairs x, y): the SVO nodes of all their cells, from the closed-form count over the tile's
+ * hierarchy. Depth tile and hierarchy stay resident for cpvs_grid_worker_build; _release drops tiles given to another worker. */
+CPVS_API int cpvs_grid_worker_estimate(cpvs_grid_worker* w, const uint32_t* xy, int count, uint64_t* cost_out);
+CPVS_API int cpvs_grid_worker_release(cpvs_grid_worker* w, const uint32_t* xy, int count);
+/* createShadowTiles (src/DeferredRenderer.cpp:150-163) for `count` xy tiles: hierarchy + one DAG per z-slice, kept on the GPU. */
+CPVS_API int cpvs_grid_worker_build(cpvs_grid_worker* w, const uint32_t* xy, int count);
+CPVS_API int cpvs_grid_worker_num_cells(const cpvs_grid_worker* w);
+/* The finished cells (returns their number, < 0 on error). */
+CPVS_API int cpvs_grid_worker_cells(const cpvs_grid_worker* w, cpvs_grid_cell* out, int capacity);
+/* Device time (CUDA events on the worker's stream) of everything _estimate and _build enqueued so far. */
+CPVS_API float cpvs_grid_worker_device_ms(const cpvs_grid_worker* w);
+/* Ownership by cost, longest tile first to the least loaded worker; owner_in (may be NULL) breaks ties in favour of the
+ * worker that already holds the tile's hierarchy. Pure host code. */
+CPVS_API int cpvs_grid_assign(const uint64_t* cost, int num_tiles, int num_workers, const int* owner_in, int* owner_out);
+
+#define CPVS_GRID_MAX_DEVICES 16
+typedef struct cpvs_grid_stats {
+	uint32_t devices, cells, one_word_cells, moved_tiles;
+	uint64_t dag_words, svo_nodes, dag_nodes, launches;
+	float build_ms_max;                       /* device time of the slowest GPU (estimates + builds) */
+	float build_ms[CPVS_GRID_MAX_DEVICES];    /* per GPU */
+	uint32_t tiles[CPVS_GRID_MAX_DEVICES];    /* xy tiles built per GPU */
+	float build_wall_ms, gather_ms, replicate_ms, wall_ms; /* host clock: builds on all GPUs; gather of sizes; replication; all */
+} cpvs_grid_stats;
+typedef struct cpvs_grid cpvs_grid;
+/* The whole grid on `devices` (1..16 GPUs of this box). replicate != 0: every GPU gets a copy of the container for the
+ * lookups, else only devices[0]. */
+CPVS_API int cpvs_grid_build(const int* devices, int num_devices, const cpvs_grid_desc* desc, int replicate, cpvs_grid** out);
+CPVS_API int cpvs_grid_destroy(cpvs_grid* g);
+CPVS_API int cpvs_grid_stats_get(const cpvs_grid* g, cpvs_grid_stats* out);
+/* The container on devices[index] (borrowed; index 0 always exists). */
+CPVS_API cpvs_container* cpvs_grid_container(const cpvs_grid* g, int index);
+/* traverse.cs over the grid for host points: the batch is split by rows over the GPUs holding a replica. */
+CPVS_API int cpvs_grid_lookup_ndc(const cpvs_grid* g, const float* ndc_host, int64_t count, uint8_t* out_host);
 
 /* ---- device-resident depth source ---------------------------------------------------------
  * Replaces the reference's render + glGetTexImage read-back of one light-frustum tile

@@ -75,3 +75,19 @@ def test_product_does_not_reference_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "include")):
         for f in files:
             assert "oracle" not in open(os.path.join(dirpath, f)).read().lower(), f
+
+
+def test_grid_assign_is_longest_first(lib_path):
+    """cpvs_grid_assign (pure host code): tiles by falling cost to the least loaded worker; ties keep a tile where it is."""
+    from cpvs_b200 import grid
+    costs = [10, 9, 8, 7, 6, 5, 4, 3]
+    owners = grid.assign(costs, 2)
+    loads = [sum(c for c, o in zip(costs, owners) if o == w) for w in range(2)]
+    assert sorted(loads) == [26, 26]
+    # equal costs: nothing moves away from a balanced round-robin
+    start = [0, 1, 2, 3, 0, 1, 2, 3]
+    assert grid.assign([5] * 8, 4, start) == start
+    # one heavy tile: it gets a worker of its own
+    owners = grid.assign([100, 1, 1, 1, 1, 1], 2)
+    assert owners[0] != owners[1] and len(set(owners[1:])) == 1
+    assert grid.assign([], 3) == []

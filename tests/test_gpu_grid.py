@@ -1,0 +1,98 @@
+"""GPU suite (-m gpu): the C++ tile-grid driver (cpvs_grid_* of include/cpvs_b200.h) -- against the CPU oracle's container at
+small sizes, and a C++ program (tests/cpp/grid_test.cpp) that builds grids on one and on several workers."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cpvs_b200
+from cpvs_b200 import grid as cgrid, synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _oracle_container(oracle, kind, tile, length):
+    cont = oracle.Container(length)
+    keep = []
+    for y in range(length):
+        for x in range(length):
+            mm = oracle.MinMax(synth.depth_map(kind, tile, (x, y), length))
+            for z in range(length):
+                sh = oracle.Shadow(mm, z, length)
+                keep.append((mm, sh))
+                cont.set(sh, x, y, z)
+    cont.finalize()
+    return cont, keep
+
+
+@pytest.mark.parametrize("kind,tile,length,workers", [("terrain_dev", 128, 4, 1), ("terrain_dev", 128, 4, 3), ("city", 256, 4, 2), ("plane", 64, 8, 2),
+                                                     ("city", 64, 16, 3)])
+def test_grid_build_equals_oracle_container(gpu_ctx, oracle, kind, tile, length, workers):
+    """combineDAGs + createTopLevelGrid over cells built by several workers (contexts of GPU 0 when the box has one GPU):
+    the container's words and grid are the oracle's, whoever built which tile."""
+    import torch
+    devices = [d % torch.cuda.device_count() for d in range(workers)]
+    g = cgrid.Grid.build(devices, length, tile, kind)
+    st = g.stats()
+    assert st["cells"] == length ** 3 and sum(st["tiles"]) == length * length
+    want, keep = _oracle_container(oracle, kind, tile, length)
+    wdag, wgrid = want.dag_and_grid()
+    pts = synth.lookups(100000, seed=5)
+    for i in range(len(devices)):
+        dag, grid = g.container(i).dag_and_grid()
+        assert np.array_equal(dag, wdag) and np.array_equal(grid, wgrid), (kind, i)
+    assert np.array_equal(g.lookup_ndc(pts), want.lookup_ndc(pts))
+    assert st["dag_words"] == wdag.size
+    g.close()
+
+
+def test_grid_fetch_callback_and_assemble(gpu_ctx, oracle):
+    """Depth tiles handed over by a host callback (the reference reads them back from GL, src/ShadowMap.cpp:23-30), and
+    cpvs_container_assemble on cells collected from two workers by hand (the one-process-per-GPU path)."""
+    tile, length = 128, 2
+    maps = {(x, y): synth.depth_map("terrain", tile, (x, y), length) for x in range(length) for y in range(length)}
+
+    def fetch(x, y, out):
+        out[...] = maps[x, y]
+
+    g = cgrid.Grid.build([0, 0], length, tile, fetch=fetch)
+    want, keep = _oracle_container(oracle, "terrain", tile, length)
+    wdag, wgrid = want.dag_and_grid()
+    dag, grid = g.container(0).dag_and_grid()
+    assert np.array_equal(dag, wdag) and np.array_equal(grid, wgrid)
+    g.close()
+
+    ctxs = [cpvs_b200.Context(0), cpvs_b200.Context(0)]
+    workers = [cgrid.GridWorker(c, length, tile, fetch=fetch) for c in ctxs]
+    tiles = [(x, y) for y in range(length) for x in range(length)]
+    costs = [workers[i % 2].estimate([t])[0] for i, t in enumerate(tiles)]
+    owners = cgrid.assign(costs, 2, [i % 2 for i in range(len(tiles))])
+    for i, t in enumerate(tiles):
+        if owners[i] != i % 2:
+            workers[i % 2].release([t])
+    for w, worker in enumerate(workers):
+        worker.build([t for i, t in enumerate(tiles) if owners[i] == w])
+    cells = {c.index: c for worker in workers for c in worker.cells()}
+    assert sorted(cells) == list(range(length ** 3))
+    parts = [(cells[i].words, cells[i].root_mask, cells[i].device, cells[i].words_device) for i in range(length ** 3)]
+    cont = cgrid.assemble(ctxs[0], length, cells[0].num_levels, True, parts)
+    dag, grid = cont.dag_and_grid()
+    assert np.array_equal(dag, wdag) and np.array_equal(grid, wgrid)
+    for worker in workers:
+        worker.close()
+
+
+def test_cpp_caller_builds_grids_on_several_workers(tmp_path):
+    """tests/cpp/grid_test.cpp: a plain C++ program against include/cpvs_b200.h + libcpvs_b200.so."""
+    import torch
+    from cpvs_b200 import build
+    lib = build.build()
+    exe = str(tmp_path / "grid_test")
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "grid_test.cpp"),
+                           "-o", exe, "-L", os.path.dirname(lib), "-lcpvs_b200", "-Wl,-rpath," + os.path.dirname(lib)])
+    count = torch.cuda.device_count()
+    devices = [str(d) for d in range(min(count, 4))] if count > 1 else ["0", "0", "0"]
+    out = subprocess.run([exe, "256", "4"] + devices, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "grid_test ok" in out.stdout, out.stdout + out.stderr

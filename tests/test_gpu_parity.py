@@ -567,11 +567,19 @@ def test_leaf_kernels_forced(oracle, mode, monkeypatch):
     wall[3000:, :] = 0.5
     wall += (rng.random((4096, 4096), dtype=np.float32) * np.float32(1e-3))
     cases.append(("cliff", wall, 0, 1))
+    steps = synth.depth_map("terrain", 512).copy()  # terraces: residues that sit exactly on block boundaries, and NaN-free extremes
+    steps = np.round(steps * np.float32(64)) / np.float32(64)
+    steps[:64, :64] = 0.0
+    steps[-64:, -64:] = 1.0
+    cases += [("terraces", steps, 0, 1), ("terraces z1/3", steps, 1, 3), ("terrain z0/4", synth.depth_map("terrain", 1024), 0, 4),
+              ("terrain z3/4", synth.depth_map("terrain", 1024), 3, 4), ("city z5/16", synth.depth_map("city", 512), 5, 16)]
     for tag, d, zt, zn in cases:
-        mm = cpvs_b200.MinMaxHierarchy(d, ctx)
-        g = cpvs_b200.CompressedShadow.create(mm, zt, zn)
         o = oracle.Shadow(oracle.MinMax(d), zt, zn)
-        _assert_same_dag(g, o, (mode, tag))
+        # hierarchy prepared for whole-volume builds (its column residues do not fit a sliced build: depth path) and for this slicing
+        for tiles in sorted({1, zn}):
+            mm = cpvs_b200.MinMaxHierarchy(d, ctx, zTileNum=tiles)
+            g = cpvs_b200.CompressedShadow.create(mm, zt, zn)
+            _assert_same_dag(g, o, (mode, tag, tiles))
 
 
 # ---- builds sized from the previous build of the same shape (cpvs_ctx_set_prediction) ---------------------------------------
