@@ -47,6 +47,7 @@ struct cpvs_grid_worker {
 	float* hostStage = nullptr;  // pinned, one tile (fetch callback)
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	float deviceMs = 0.f;  // device time of everything the worker enqueued for estimates and builds
+	u32* exported = nullptr;  // cpvs_grid_worker_export: all cells in one cudaMalloc'ed block other processes can map
 	u32 built = 0;
 	int status = CPVS_OK;
 	std::string error;
@@ -128,6 +129,7 @@ int cpvs_grid_worker_destroy(cpvs_grid_worker* w) {
 		for (cpvs_shadow* s : t.cells) cpvs_shadow_destroy(s);
 	}
 	if (w->hostStage) cudaFreeHost(w->hostStage);
+	if (w->exported) cudaFree(w->exported);
 	if (w->ev0) cudaEventDestroy(w->ev0);
 	if (w->ev1) cudaEventDestroy(w->ev1);
 	delete w;
@@ -242,6 +244,53 @@ int cpvs_grid_worker_cells(const cpvs_grid_worker* w, cpvs_grid_cell* out, int c
 }
 
 float cpvs_grid_worker_device_ms(const cpvs_grid_worker* w) { return w ? w->deviceMs : 0.f; }
+
+// One process per GPU: the finished cells are packed into one block of plain device memory (stream-ordered pool memory
+// cannot be shared) whose CUDA IPC handle another process opens with cpvs_ipc_open; offsets[i] = first word of the i-th cell
+// of cpvs_grid_worker_cells inside the block. The block lives until the worker is destroyed.
+int cpvs_grid_worker_export(cpvs_grid_worker* w, unsigned char handle[64], uint64_t* offsets, int capacity) {
+	if (!w || !handle || !offsets) return fail(CPVS_EINVAL, "cpvs_grid_worker_export: NULL argument");
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the handle travels as 64 bytes");
+	CPVS_CUDA(cudaSetDevice(w->ctx->device));
+	u64 total = 0;
+	int n = 0;
+	for (const WorkerTile& t : w->tiles)
+		if (t.built)
+			for (const cpvs_shadow* s : t.cells) {
+				if (n >= capacity) return fail(CPVS_EINVAL, "cpvs_grid_worker_export: capacity %d", capacity);
+				offsets[n++] = total;
+				total += s->info.words;
+			}
+	if (w->exported) CPVS_CUDA(cudaFree(w->exported));
+	w->exported = nullptr;
+	CPVS_CUDA(cudaMalloc(reinterpret_cast<void**>(&w->exported), (total ? total : 1) * sizeof(u32)));
+	n = 0;
+	for (const WorkerTile& t : w->tiles)
+		if (t.built)
+			for (const cpvs_shadow* s : t.cells)
+				CPVS_CUDA(cudaMemcpyAsync(w->exported + offsets[n++], s->dag, s->info.words * sizeof(u32), cudaMemcpyDeviceToDevice, w->ctx->stream));
+	CPVS_CUDA(cudaStreamSynchronize(w->ctx->stream));
+	cudaIpcMemHandle_t h;
+	CPVS_CUDA(cudaIpcGetMemHandle(&h, w->exported));
+	std::memcpy(handle, &h, 64);
+	return n;
+}
+
+int cpvs_ipc_open(const unsigned char handle[64], int device, void** out) {
+	if (!handle || !out) return fail(CPVS_EINVAL, "cpvs_ipc_open: NULL argument");
+	cudaIpcMemHandle_t h;
+	std::memcpy(&h, handle, 64);
+	CPVS_CUDA(cudaSetDevice(device));
+	CPVS_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+	return CPVS_OK;
+}
+
+int cpvs_ipc_close(int device, void* ptr) {
+	if (!ptr) return CPVS_OK;
+	CPVS_CUDA(cudaSetDevice(device));
+	CPVS_CUDA(cudaIpcCloseMemHandle(ptr));
+	return CPVS_OK;
+}
 
 // Longest-processing-time-first: tiles in order of falling cost, each to the least loaded worker; among equally loaded
 // workers the one that already holds the tile (its pyramid is resident there). owner_in may be NULL.

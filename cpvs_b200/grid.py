@@ -165,6 +165,16 @@ class GridWorker:
     def device_ms(self):
         return float(self._lib.cpvs_grid_worker_device_ms(self.handle))
 
+    def export(self):
+        """(64-byte CUDA IPC handle of a block holding all finished cells, first word of every cell in ``cells()`` order)."""
+        n = self._lib.cpvs_grid_worker_num_cells(self.handle)
+        handle = (ctypes.c_ubyte * 64)()
+        offsets = (ctypes.c_uint64 * max(1, n))()
+        got = self._lib.cpvs_grid_worker_export(self.handle, handle, offsets, max(1, n))
+        if got < 0:
+            _check(EINVAL)
+        return bytes(handle), [int(o) for o in offsets[:got]]
+
     def close(self):
         if getattr(self, "handle", None):
             self._lib.cpvs_grid_worker_destroy(self.handle)
@@ -199,3 +209,16 @@ def assemble(ctx, length, num_levels, leafmasks, parts):
     cont = CompressedShadowContainer.__new__(CompressedShadowContainer)
     cont.ctx, cont._lib, cont.handle, cont.length = ctx, lib, h, length
     return cont
+
+
+def ipc_open(handle, device):
+    """Maps another process's exported block (``GridWorker.export``) on ``device``; returns the device pointer."""
+    lib = load_library()
+    buf = (ctypes.c_ubyte * 64)(*handle)
+    ptr = ctypes.c_void_p()
+    _check(lib.cpvs_ipc_open(buf, device, ctypes.byref(ptr)))
+    return int(ptr.value)
+
+
+def ipc_close(device, ptr):
+    _check(load_library().cpvs_ipc_close(device, ctypes.c_void_p(ptr)))

@@ -276,6 +276,13 @@ CPVS_API int cpvs_grid_worker_num_cells(const cpvs_grid_worker* w);
 CPVS_API int cpvs_grid_worker_cells(const cpvs_grid_worker* w, cpvs_grid_cell* out, int capacity);
 /* Device time (CUDA events on the worker's stream) of everything _estimate and _build enqueued so far. */
 CPVS_API float cpvs_grid_worker_device_ms(const cpvs_grid_worker* w);
+/* One process per GPU: packs the finished cells into one block of plain device memory and returns its CUDA IPC handle
+ * (64 bytes) plus, per cell in the order of cpvs_grid_worker_cells, the first word inside the block (returns the number of
+ * cells, < 0 on error). Another process maps the block with cpvs_ipc_open (on its own device: the words are then fetched
+ * peer to peer) and feeds cpvs_container_assemble; the block lives until the worker is destroyed. */
+CPVS_API int cpvs_grid_worker_export(cpvs_grid_worker* w, unsigned char handle[64], uint64_t* offsets, int capacity);
+CPVS_API int cpvs_ipc_open(const unsigned char handle[64], int device, void** out);
+CPVS_API int cpvs_ipc_close(int device, void* ptr);
 /* Ownership by cost, longest tile first to the least loaded worker; owner_in (may be NULL) breaks ties in favour of the
  * worker that already holds the tile's hierarchy. Pure host code. */
 CPVS_API int cpvs_grid_assign(const uint64_t* cost, int num_tiles, int num_workers, const int* owner_in, int* owner_out);

@@ -515,23 +515,18 @@ def test_depth_generate_errors(gpu_ctx):
 
 # ---- whole tile grids (cpvs_b200.gridbuild: what bench.py --grid runs) -------------------------------
 
-@pytest.mark.parametrize("kind,tile,length", [("city", 256, 4), ("terrain", 128, 4), ("plane", 64, 8)])
+@pytest.mark.parametrize("kind,tile,length", [("city", 256, 4), ("terrain_dev", 128, 4), ("plane", 64, 8)])
 def test_gridbuild_small(kind, tile, length):
-    """The grid driver at a small size: every cell and every container lookup is checked against the depth
-    tiles inside run(); here the grid must also equal the oracle-free host scan and the counts must add up."""
-    import torch
+    """The one-process-per-GPU grid driver at a small size (a single rank here; tests/test_gpu_grid_ranks.py runs two): every
+    container lookup is checked against the depth tiles inside run(); the grid must equal the host scan."""
     from cpvs_b200 import gridbuild
-    stream = torch.cuda.Stream()
-    with torch.cuda.stream(stream):
-        ctx = cpvs_b200.Context(0, stream=stream.cuda_stream)
-        res = gridbuild.run(ctx, stream, tile, length, kind, lookups=3840 * 64, lookup_iters=2)
-        ctx.close()
-    assert res["cells"] == length ** 3 and res["verified"]["cell_lookups_vs_depth"] == length ** 3 * 65536
+    ctx = cpvs_b200.Context(0)
+    res = gridbuild.run(ctx, tile, length, kind, lookups=3840 * 64, lookup_iters=2)
+    ctx.close()
+    assert res["cells"] == length ** 3
     assert res["verified"]["container_lookups_vs_depth"] == res["lookups"] == 3840 * 64
     assert res["grid_cells_with_dag"] >= res["cells"] - res["one_word_cells"]  # one-word cells may still mix lit and shadow
-    top = str(int(np.log2(tile)) - 1)
-    assert res["dag_nodes_per_level"][top] == length ** 3  # one root per cell
-    assert 0 < res["lookups_lit"] < res["lookups"]
+    assert 0 < res["lookups_lit"] < res["lookups"] and res["dag_nodes"] >= length ** 3
 
 
 def test_reserve_and_kept_dags(gpu_ctx, oracle):
