@@ -326,8 +326,9 @@ int carveArena(Build& b) {
 				a.leafAt = ar.take<u32>(a.cap);
 			else
 				a.coords = ar.take<u64>(a.cap);
-			a.masks = ar.take<u16>(a.cap + 4);
-			a.uid = ar.take<u32>(a.cap + 4);
+			// (rounded up to whole rank tiles: the rank kernels fetch their vectors before they know the level's size)
+			a.masks = ar.take<u16>(((a.cap + kScanTile - 1) / kScanTile) * kScanTile + 4);
+			a.uid = ar.take<u32>(((a.cap + kScanTile - 1) / kScanTile) * kScanTile + 4);
 			a.firstList = ar.take<u32>(a.cap);
 			a.wordOffset = ar.take<u32>(a.cap);
 			if (l >= b.smallLow) {

@@ -101,15 +101,19 @@ __device__ __forceinline__ u64 hashLeafCode(const uint4& a0, const uint4& a1) {
 	return mix64(h);
 }
 
-__global__ void __launch_bounds__(256) insertLeavesKernel(const u32* __restrict__ codes, const u64* __restrict__ hashes, const u64* __restrict__ nDev,
-		u64* __restrict__ table, const u64* __restrict__ tableMaskDev, u32* __restrict__ slotOf, u32* errorFlag, const u32* __restrict__ overflow) {
+__global__ void __launch_bounds__(256, 8) insertLeavesKernel(const u32* __restrict__ codes, const u64* __restrict__ hashes, const u64* __restrict__ nDev,
+		u64 cap, u64* __restrict__ table, const u64* __restrict__ tableMaskDev, u32* __restrict__ slotOf, u32* errorFlag,
+		const u32* __restrict__ overflow) {
 	const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= *nDev || (*overflow & kOverflowNodes)) return;
-	const u64 tableMask = *tableMaskDev;
-	// own code and hash are fetched up front so that their latency overlaps the first table probe
+	if (j >= cap) return;
+	// own code (and hash) are fetched up front, together with the level's size: the arrays hold `cap` leaves, so the loads need not
+	// wait for the size that only the device knows -- one round trip less in front of a chain of three
 	const uint4* mine = reinterpret_cast<const uint4*>(codes + j * 8);
 	const uint4 a0 = __ldcs(mine), a1 = __ldcs(mine + 1);
-	const u64 hash = hashes ? __ldcs(hashes + j) : hashLeafCode(a0, a1);
+	u64 hash = hashes ? __ldcs(hashes + j) : 0;
+	const u64 tableMask = *tableMaskDev;
+	if (j >= *nDev || (*overflow & kOverflowNodes)) return;
+	if (!hashes) hash = hashLeafCode(a0, a1);
 	slotOf[j] = findGroupSlot(table, tableMask, hash, (u32)j, errorFlag, [&](u32 other) {
 		const uint4* theirs = reinterpret_cast<const uint4*>(codes + (u64)other * 8);
 		const uint4 b0 = theirs[0], b1 = theirs[1];
@@ -247,11 +251,10 @@ __global__ void __launch_bounds__(256) insertLeavesBatchKernel(const u32* __rest
 }
 
 template <bool kShared = false>
-__device__ __forceinline__ u32 insertInnerNode(u32 j, const u16* __restrict__ masks, const u32* __restrict__ firstChild,
+__device__ __forceinline__ u32 insertInnerNode(u32 j, u32 mask, u32 first, const u16* __restrict__ masks, const u32* __restrict__ firstChild,
 		const u32* __restrict__ childUid, u64* __restrict__ table, u64 tableMask, u32* errorFlag) {
-	const u32 mask = masks[j];
 	const u32 k = __popc(mask & 0xAAAAu);
-	const u32* kids = childUid + firstChild[j];
+	const u32* kids = childUid + first;
 	u32 uid[8];
 	u64 h = mix64(0x51ED270B6F2D4A6Bull ^ mask);
 #pragma unroll
@@ -289,18 +292,21 @@ __device__ __forceinline__ u32 compactLitBits(u32 mask) {
 // the time, and the two extra CTAs are worth 0.03 ms on the 16K^2 terrain (inner merge 0.436 -> 0.409 ms, the leaf rank running
 // beside it 0.375 -> 0.348 ms; profiles/r1_switch_probe.md).
 __global__ void __launch_bounds__(256, 8) insertInnerKernel(const u16* __restrict__ masks, const u32* __restrict__ firstChild,
-		const u32* __restrict__ childUid, const u64* __restrict__ nDev, u64* __restrict__ table, u64 tableMask, u32* __restrict__ slotOf,
+		const u32* __restrict__ childUid, const u64* __restrict__ nDev, u64 cap, u64* __restrict__ table, u64 tableMask, u32* __restrict__ slotOf,
 		u32* errorFlag, const u32* __restrict__ overflow) {
 	__shared__ u32 sFirst[kDirectSlots];
+	const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+	// (the mask is fetched together with the level's size: the arrays hold `cap` nodes)
+	const u32 maskSpec = j < cap ? masks[j] : 0xAAAAu;
+	const u32 firstSpec = j < cap ? firstChild[j] : 0u;
 	const u64 n = *nDev;
 	// the grid is sized for the level's capacity; a level cut short by a capacity (the child lists of its last nodes are
 	// incomplete) is not merged at all -- the host rebuilds with exact counts
 	if ((u64)blockIdx.x * blockDim.x >= n || (*overflow & kOverflowNodes)) return;
-	const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
 	sFirst[threadIdx.x] = 0xFFFFFFFFu;
 	__syncthreads();
 	const bool live = j < n;
-	const u32 mask = live ? masks[j] : 0xAAAAu;
+	const u32 mask = live ? maskSpec : 0xAAAAu;
 	const bool direct = live && (mask & 0xAAAAu) == 0;
 	const u32 c = compactLitBits(mask);
 	if (direct) atomicMin(&sFirst[c], (u32)j);
@@ -315,7 +321,7 @@ __global__ void __launch_bounds__(256, 8) insertInnerKernel(const u16* __restric
 	if (direct)
 		slotOf[j] = (u32)(tableMask + 1 + c) | (sFirst[c] == (u32)j ? kCandidateFlag : 0u);
 	else if (live)
-		slotOf[j] = insertInnerNode<false>((u32)j, masks, firstChild, childUid, table, tableMask, errorFlag);
+		slotOf[j] = insertInnerNode<false>((u32)j, mask, firstSpec, masks, firstChild, childUid, table, tableMask, errorFlag);
 }
 
 // gid[j] = slot of node j's group. Ranks the first occurrences (slot's final index == j) in order,
@@ -331,17 +337,18 @@ __global__ void __launch_bounds__(256, 8) insertInnerKernel(const u16* __restric
 __global__ void __launch_bounds__(kScanThreads, 8) rankCountKernel(const u64* __restrict__ table, const u16* __restrict__ masks, int leaf,
 		const u64* __restrict__ nDev, const u32* __restrict__ gid, unsigned char* __restrict__ sizeOf, ScanTileState* __restrict__ tiles,
 		const u32* __restrict__ overflow) {
-	const u64 n = (*overflow & kOverflowNodes) ? 0 : *nDev;
 	const u64 base = (u64)blockIdx.x * kScanTile + (u64)threadIdx.x * kScanItems;
+	// (the arrays hold at least the grid's worth of nodes, rounded up to whole vectors: these loads do not wait for the size)
+	const uint2 v = *reinterpret_cast<const uint2*>(masks + base);
+	const uint4 w = *reinterpret_cast<const uint4*>(gid + base);
+	const u64 n = (*overflow & kOverflowNodes) ? 0 : *nDev;
 	if ((u64)blockIdx.x * kScanTile >= n) return;  // the grid is sized for the level's capacity
 	u32 myMask[kScanItems] = {0, 0, 0, 0}, g[kScanItems] = {0, 0, 0, 0};
 	if (base + kScanItems <= n) {
-		const uint2 v = *reinterpret_cast<const uint2*>(masks + base);
 		myMask[0] = v.x & 0xFFFFu;
 		myMask[1] = v.x >> 16;
 		myMask[2] = v.y & 0xFFFFu;
 		myMask[3] = v.y >> 16;
-		const uint4 w = *reinterpret_cast<const uint4*>(gid + base);
 		g[0] = w.x;
 		g[1] = w.y;
 		g[2] = w.z;
@@ -533,7 +540,7 @@ __global__ void __launch_bounds__(kSmallThreads) mergeSmallLevelsKernel(SmallMer
 		for (u32 i = threadIdx.x; i < slots; i += kSmallThreads) sTable[i] = kEmpty;
 		__syncthreads();
 		for (u32 j = threadIdx.x; j < n; j += kSmallThreads)
-			L.uid[j] = insertInnerNode<true>(j, L.masks, L.firstChild, L.childUid, sTable, slots - 1, a.errorFlag);
+			L.uid[j] = insertInnerNode<true>(j, L.masks[j], L.firstChild[j], L.masks, L.firstChild, L.childUid, sTable, slots - 1, a.errorFlag);
 		__syncthreads();
 		u32 carryC = 0, carryW = 0;
 		for (u32 base = 0; base < n; base += kSmallThreads) {
@@ -619,9 +626,9 @@ int launchInsertLevel(const MergeLevelArgs& a, cudaStream_t stream) {
 	else if (a.leaf && batch == 1)
 		insertLeavesBatchKernel<1><<<(unsigned)((a.cap + 255) / 256), 256, 0, stream>>>(a.leafCodes, a.leafHash, a.nDev, a.table, a.tableMaskDev, a.uid, a.errorFlag, a.overflow);
 	else if (a.leaf)
-		insertLeavesKernel<<<blocks, 256, 0, stream>>>(a.leafCodes, a.leafHash, a.nDev, a.table, a.tableMaskDev, a.uid, a.errorFlag, a.overflow);
+		insertLeavesKernel<<<blocks, 256, 0, stream>>>(a.leafCodes, a.leafHash, a.nDev, a.cap, a.table, a.tableMaskDev, a.uid, a.errorFlag, a.overflow);
 	else
-		insertInnerKernel<<<blocks, 256, 0, stream>>>(a.masks, a.firstChild, a.childUid, a.nDev, a.table, a.tableSize - 1, a.uid, a.errorFlag, a.overflow);
+		insertInnerKernel<<<blocks, 256, 0, stream>>>(a.masks, a.firstChild, a.childUid, a.nDev, a.cap, a.table, a.tableSize - 1, a.uid, a.errorFlag, a.overflow);
 	return 1;
 }
 

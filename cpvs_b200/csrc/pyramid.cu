@@ -81,11 +81,11 @@ __global__ void __launch_bounds__(256) pyramidBaseKernel(const float* __restrict
 			unsigned int b[4];
 #pragma unroll
 			for (int k = 0; k < 4; ++k) {
-				// floor of the exact sum (rounded toward -inf, which never crosses an integer), clamped; the second sum parks the
-				// integer in the low mantissa bits. NaN is dropped by fmaxf: residue 0 = never lit, as midZ <= NaN is false.
-				float x = __fadd_rd(__fmul_rn(d[k], heightF), shift);
-				x = fminf(fmaxf(x, 0.0f), 255.0f);
-				b[k] = __float_as_uint(__fadd_rd(x, 8388608.0f));
+				// floor of the exact sum (rounded toward -inf, which never crosses an integer), clamped to a byte. NaN becomes
+				// residue 0 = never lit, as midZ <= NaN is false.
+				const float x = __fadd_rd(__fmul_rn(d[k], heightF), shift);
+				// (one conversion that floors and saturates to 0..255, NaN -> 0; it runs on the otherwise idle conversion pipe)
+				asm("cvt.rmi.sat.u8.f32 %0, %1;" : "=r"(b[k]) : "f"(x));
 			}
 			const unsigned int lo = __byte_perm(b[0], b[1], 0x0040), hi = __byte_perm(b[2], b[3], 0x0040);
 			// A row is stored with texels x and x + 4 next to each other (bytes 0 4 1 5 | 2 6 3 7): the builder works on such
