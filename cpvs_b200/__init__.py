@@ -88,6 +88,7 @@ SIGNATURES = {
     "cpvs_container_lookup_ndc": (_I, [_VP, _VP, _I64, _I, _VP]),
     "cpvs_container_evaluate": (_I, [_VP, _VP, _U32, _U32, _I, _VP, _VP]),
     "cpvs_container_set_filter_size": (_I, [_VP, _U32]),
+    "cpvs_container_evaluate_surface": (_I, [_VP, _U64, _U64, _U32, _U32, _VP]),
     "cpvs_container_save": (_I, [_VP, ctypes.c_char_p]),
     "cpvs_container_load": (_I, [_VP, ctypes.c_char_p, _PP]),
     "cpvs_depth_generate": (_I, [_VP, _I, _I, _I, _I, _I, _VP]),

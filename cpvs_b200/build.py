@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcpvs_b200.so")
-SOURCES = ["capi.cu", "build.cu", "grid.cu", "pyramid.cu", "svo.cu", "merge.cu", "emit.cu", "lookup.cu", "synthgen.cu"]
+SOURCES = ["capi.cu", "build.cu", "grid.cu", "pyramid.cu", "svo.cu", "merge.cu", "emit.cu", "lookup.cu", "lookup_index.cu", "synthgen.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--fmad=false",  # float products feeding comparisons must round like the reference's

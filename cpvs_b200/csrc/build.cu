@@ -977,6 +977,7 @@ int cpvs_shadow_destroy(cpvs_shadow* s) {
 	}
 	if (s->dagAlloc) cudaFreeAsync(s->dagAlloc, s->ctx->stream);
 	if (s->skip) cudaFreeAsync(s->skip, s->ctx->stream);
+	freeLookupIndex(s->ctx, &s->index);
 	if (s->ready) cudaEventDestroy(s->ready);
 	delete s;
 	return CPVS_OK;

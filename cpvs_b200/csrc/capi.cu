@@ -416,20 +416,30 @@ int cpvs_shadow_lookup_ndc(const cpvs_shadow* s, const float* ndc, int64_t count
 	CPVS_CUDA(cudaSetDevice(s->ctx->device));
 	cudaStream_t st = s->ctx->stream;
 	LookupDag d{s->dag, nullptr, s->info.num_levels, 0, tryLeafmasks ? 1 : 0, nullptr, 0};
-	{  // shortcut grid, built once
+	{  // the private lookup copy and the shortcut grid, built once
 		cpvs_shadow* ms = const_cast<cpvs_shadow*>(s);
 		std::lock_guard<std::mutex> guard(ms->skipLock);
-		if (!ms->skip) {
+		if (d.leafmasks && !ms->index.tried)
+			if (int rc = buildLookupIndex(s->ctx, s->dag, s->info.words, std::vector<u64>(1, 0), std::vector<u64>(1, s->info.words), std::vector<u32>(),
+						s->info.num_levels, 0, &ms->index))
+				return rc;
+		if (ms->index.valid) {
+			d.dag = ms->index.nodes;
+			d.leafCodes = ms->index.codes;
+		}
+		u32*& skip = ms->index.valid ? ms->index.skip : ms->skip;
+		u32& skipLevels = ms->index.valid ? ms->index.skipLevels : ms->skipLevels;
+		if (!skip) {
 			const u32 g = skipLevelsFor(d.dagLevels, d.leafmasks, 0);
 			if (g) {
-				CPVS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ms->skip), (sizeof(u32) << (3 * g)), st));
+				CPVS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&skip), (sizeof(u32) << (3 * g)), st));
 				d.skipLevels = g;
-				s->ctx->launches += launchBuildSkipGrid(d, ms->skip, st);
-				ms->skipLevels = g;
+				s->ctx->launches += launchBuildSkipGrid(d, skip, st);
+				skipLevels = g;
 			}
 		}
-		d.skip = ms->skip;
-		d.skipLevels = ms->skipLevels;
+		d.skip = skip;
+		d.skipLevels = skipLevels;
 	}
 	return runLookup(s->ctx, ndc, (u64)count * 3, mem, out, (u64)count,
 			[&](const float* in, unsigned char* o) { return launchLookupNdc(d, in, count, o, st); });
@@ -451,7 +461,53 @@ int cpvs_container_create(cpvs_ctx* ctx, uint32_t length, cpvs_container** out) 
 	return CPVS_OK;
 }
 
+}  // extern "C"
+
+namespace {
+// What the lookups of a finished container walk: the private lookup copy (lookup_index.cu) where it could be built, else the DAG
+// words themselves; either way with a shortcut grid over the top levels.
+// hostGrid: the cell table; cellWords: words per cell in container order.
+int prepareContainerLookups(cpvs_container* c, const std::vector<u32>& hostGrid, const std::vector<u64>& cellWords) {
+	cpvs_ctx* ctx = c->ctx;
+	cudaStream_t st = ctx->stream;
+	if (c->leafmasks) {
+		std::vector<u64> cellStart(cellWords.size());
+		u64 offset = 0;
+		for (size_t i = 0; i < cellWords.size(); ++i) {
+			cellStart[i] = offset;
+			offset += cellWords[i];
+		}
+		if (int rc = buildLookupIndex(ctx, c->dag, c->dagWords, cellStart, cellWords, hostGrid, c->dagLevels, c->gridLevels, &c->index)) return rc;
+	}
+	c->skipLevels = skipLevelsFor(c->dagLevels, c->leafmasks, c->gridLevels);
+	if (c->skipLevels) {
+		u32** skip = c->index.valid ? &c->index.skip : &c->skip;
+		CPVS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(skip), sizeof(u32) << (3 * (c->gridLevels + c->skipLevels)), st));
+		LookupDag d{c->index.valid ? c->index.nodes : c->dag, c->index.valid ? c->index.grid : c->grid, c->dagLevels, c->gridLevels, c->leafmasks, nullptr,
+				c->skipLevels};
+		if (c->index.valid) d.leafCodes = c->index.codes;
+		ctx->launches += launchBuildSkipGrid(d, *skip, st);
+		CPVS_CUDA(cudaGetLastError());
+		c->index.skipLevels = c->skipLevels;
+	}
+	return CPVS_OK;
+}
+
+LookupDag containerView(const cpvs_container* c) {
+	if (c->index.valid) {
+		LookupDag d{c->index.nodes, c->index.grid, c->dagLevels, c->gridLevels, c->leafmasks, c->index.skip, c->skipLevels};
+		d.leafCodes = c->index.codes;
+		return d;
+	}
+	return LookupDag{c->dag, c->grid, c->dagLevels, c->gridLevels, c->leafmasks, c->skip, c->skipLevels};
+}
+}  // namespace
+
+extern "C" {
+
 static void releaseContainerBuffers(cpvs_container* c) {
+	freeLookupIndex(c->ctx, &c->index);
+	c->index.tried = false;
 	if (c->dag) cudaFreeAsync(c->dag, c->ctx->stream);
 	if (c->grid) cudaFreeAsync(c->grid, c->ctx->stream);
 	if (c->skip) cudaFreeAsync(c->skip, c->ctx->stream);
@@ -534,13 +590,9 @@ int cpvs_container_finalize(cpvs_container* c) {
 	c->gridLevels = 0;                     // log8(#cells) (:42-43), exact here
 	while ((1u << c->gridLevels) < c->length) ++c->gridLevels;
 	c->leafmasks = c->cells[0].leafmasks;
-	c->skipLevels = skipLevelsFor(c->dagLevels, c->leafmasks, c->gridLevels);
-	if (c->skipLevels) {
-		CPVS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&c->skip), sizeof(u32) << (3 * (c->gridLevels + c->skipLevels)), st));
-		LookupDag d{c->dag, c->grid, c->dagLevels, c->gridLevels, c->leafmasks, nullptr, c->skipLevels};
-		c->ctx->launches += launchBuildSkipGrid(d, c->skip, st);
-		CPVS_CUDA(cudaGetLastError());
-	}
+	std::vector<u64> cellWords(c->cells.size());
+	for (size_t i = 0; i < c->cells.size(); ++i) cellWords[i] = c->cells[i].count;
+	if (int rc = prepareContainerLookups(c, grid, cellWords)) return rc;
 	c->finalized = true;
 	return CPVS_OK;
 }
@@ -608,20 +660,19 @@ int containerFromParts(cpvs_ctx* ctx, u32 length, u32 numLevels, int leafmasks, 
 	c->gridLevels = 0;
 	while ((1u << c->gridLevels) < length) ++c->gridLevels;
 	c->leafmasks = leafmasks;
-	c->skipLevels = skipLevelsFor(c->dagLevels, c->leafmasks, c->gridLevels);
-	if (e == cudaSuccess && c->skipLevels) {
-		e = cudaMallocAsync(reinterpret_cast<void**>(&c->skip), sizeof(u32) << (3 * (c->gridLevels + c->skipLevels)), st);
-		if (e == cudaSuccess) {
-			LookupDag d{c->dag, c->grid, c->dagLevels, c->gridLevels, c->leafmasks, nullptr, c->skipLevels};
-			ctx->launches += launchBuildSkipGrid(d, c->skip, st);
-			e = cudaGetLastError();
-		}
-	}
 	if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // host staging goes away; the sources may be released by the caller
 	if (dPatches) cudaFreeAsync(dPatches, st);
 	if (e != cudaSuccess) {
 		cpvs_container_destroy(c);
 		return fail(CPVS_ECUDA, "cpvs_container_assemble: %s", cudaGetErrorString(e));
+	}
+	{
+		std::vector<u64> cellWords(numCells);
+		for (size_t i = 0; i < numCells; ++i) cellWords[i] = parts[i].words;
+		if (int rc = prepareContainerLookups(c, grid, cellWords)) {
+			cpvs_container_destroy(c);
+			return rc;
+		}
 	}
 	c->finalized = true;
 	*out = c;
@@ -660,7 +711,7 @@ int cpvs_container_lookup_ndc(const cpvs_container* c, const float* ndc, int64_t
 	if (count < 0 || (count > 0 && (!ndc || !out))) return fail(CPVS_EINVAL, "cpvs_container_lookup_ndc: bad arguments");
 	if (count == 0) return CPVS_OK;
 	CPVS_CUDA(cudaSetDevice(c->ctx->device));
-	LookupDag d{c->dag, c->grid, c->dagLevels, c->gridLevels, c->leafmasks, c->skip, c->skipLevels};
+	const LookupDag d = containerView(c);
 	cudaStream_t st = c->ctx->stream;
 	return runLookup(c->ctx, ndc, (u64)count * 3, mem, out, (u64)count,
 			[&](const float* in, unsigned char* o) { return launchLookupNdc(d, in, count, o, st); });
@@ -673,11 +724,63 @@ int cpvs_container_evaluate(const cpvs_container* c, const float* positions, uin
 	const long long count = (long long)width * height;
 	if (count == 0) return CPVS_OK;
 	CPVS_CUDA(cudaSetDevice(c->ctx->device));
-	LookupDag d{c->dag, c->grid, c->dagLevels, c->gridLevels, c->leafmasks, c->skip, c->skipLevels};
+	const LookupDag d = containerView(c);
 	cudaStream_t st = c->ctx->stream;
 	return runLookup(c->ctx, positions, (u64)count * 4, mem, visibilities, (u64)count,
-			[&](const float* in, unsigned char* o) { return launchEvaluate(d, in, width, height, m, o, st); });
+			[&](const float* in, unsigned char* o) { return launchEvaluate(d, in, width, height, m, (int)c->filterSize, o, st); });
 }
+
+// evaluate() on the textures themselves (src/CompressedShadowContainer.cpp:100-107 binds image units 0 = rgba32f positions and
+// 1 = r8 visibilities): CUDA surface objects over the arrays behind them.
+int cpvs_container_evaluate_surface(const cpvs_container* c, unsigned long long positions, unsigned long long visibilities, uint32_t width,
+		uint32_t height, const float m[16]) {
+	if (!c || !c->finalized) return fail(CPVS_EINVAL, "cpvs_container_evaluate_surface: container not finalized");
+	if (!positions || !visibilities || !m) return fail(CPVS_EINVAL, "cpvs_container_evaluate_surface: NULL argument");
+	if (!width || !height) return CPVS_OK;
+	CPVS_CUDA(cudaSetDevice(c->ctx->device));
+	const LookupDag d = containerView(c);
+	c->ctx->launches += launchEvaluateSurface(d, positions, visibilities, width, height, m, (int)c->filterSize, c->ctx->stream);
+	CPVS_CUDA(cudaGetLastError());
+	return CPVS_OK;
+}
+
+#ifdef CPVS_WITH_GL
+}  // extern "C"
+// CUDA-GL interop for DeferredRenderer::doAllShading (src/DeferredRenderer.cpp:320-347): the G-buffer position texture
+// (rgba32f, :80) and the visibility texture (r8, :18) are registered once, mapped per frame, and evaluated in place of the
+// glDispatchCompute of CompressedShadowContainer::evaluate (src/CompressedShadowContainer.cpp:93-124). Needs GL headers and a
+// GL context current on the calling thread; not compiled in this repository's default build (no GL on the build machine).
+#include <cuda_gl_interop.h>
+extern "C" {
+int cpvs_container_evaluate_gl(const cpvs_container* c, unsigned int positionsTexture, unsigned int visibilitiesTexture, uint32_t width, uint32_t height,
+		const float m[16]) {
+	if (!c || !c->finalized) return fail(CPVS_EINVAL, "cpvs_container_evaluate_gl: container not finalized");
+	CPVS_CUDA(cudaSetDevice(c->ctx->device));
+	cudaStream_t st = c->ctx->stream;
+	cudaGraphicsResource_t res[2] = {nullptr, nullptr};
+	CPVS_CUDA(cudaGraphicsGLRegisterImage(&res[0], positionsTexture, 0x0DE1 /* GL_TEXTURE_2D */, cudaGraphicsRegisterFlagsReadOnly));
+	cudaError_t e = cudaGraphicsGLRegisterImage(&res[1], visibilitiesTexture, 0x0DE1, cudaGraphicsRegisterFlagsSurfaceLoadStore);
+	if (e == cudaSuccess) e = cudaGraphicsMapResources(2, res, st);
+	cudaSurfaceObject_t surf[2] = {0, 0};
+	for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+		cudaArray_t array = nullptr;
+		e = cudaGraphicsSubResourceGetMappedArray(&array, res[i], 0, 0);
+		cudaResourceDesc desc = {};
+		desc.resType = cudaResourceTypeArray;
+		desc.res.array.array = array;
+		if (e == cudaSuccess) e = cudaCreateSurfaceObject(&surf[i], &desc);
+	}
+	int rc = CPVS_OK;
+	if (e == cudaSuccess) rc = cpvs_container_evaluate_surface(c, surf[0], surf[1], width, height, m);
+	for (cudaSurfaceObject_t s : surf)
+		if (s) cudaDestroySurfaceObject(s);
+	if (res[0] && res[1]) cudaGraphicsUnmapResources(2, res, st);
+	for (cudaGraphicsResource_t r : res)
+		if (r) cudaGraphicsUnregisterResource(r);
+	if (e != cudaSuccess) return fail(CPVS_ECUDA, "cpvs_container_evaluate_gl: %s", cudaGetErrorString(e));
+	return rc;
+}
+#endif
 
 namespace {
 struct ContainerFileHeader {
@@ -781,19 +884,38 @@ int cpvs_container_load(cpvs_ctx* ctx, const char* path, cpvs_container** out) {
 	c->dagLevels = h.dagLevels;
 	c->gridLevels = h.gridLevels;
 	c->leafmasks = (int)h.leafmasks;
-	c->skipLevels = skipLevelsFor(c->dagLevels, c->leafmasks, c->gridLevels);
-	if (e == cudaSuccess && c->skipLevels) {
-		e = cudaMallocAsync(reinterpret_cast<void**>(&c->skip), sizeof(u32) << (3 * (c->gridLevels + c->skipLevels)), st);
-		if (e == cudaSuccess) {
-			LookupDag d{c->dag, c->grid, c->dagLevels, c->gridLevels, c->leafmasks, nullptr, c->skipLevels};
-			ctx->launches += launchBuildSkipGrid(d, c->skip, st);
-			e = cudaGetLastError();
-		}
-	}
 	if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the host staging buffers go away
 	if (e != cudaSuccess) {
 		cpvs_container_destroy(c);
 		return fail(CPVS_ECUDA, "cpvs_container_load: %s", cudaGetErrorString(e));
+	}
+	{
+		// words per cell from the cell table: a cell with a DAG starts at its grid entry, a uniform cell is one word
+		// (createTopLevelGrid advances the running offset for every cell, src/CompressedShadowContainer.cpp:88)
+		std::vector<u64> cellWords(grid.size(), 1);
+		size_t last = grid.size();
+		u64 end = h.dagWords;
+		for (size_t i = grid.size(); i-- > 0;) {
+			if (grid[i] == CPVS_GRID_CELL_SHADOWED || grid[i] == CPVS_GRID_CELL_VISIBLE) continue;
+			const u64 uniformBehind = (last == grid.size() ? grid.size() : last) - i - 1;
+			cellWords[i] = end - grid[i] - uniformBehind;
+			end = grid[i];
+			last = i;
+		}
+		bool consistent = true;
+		u64 sum = 0;
+		for (size_t i = 0; i < grid.size(); ++i) {
+			consistent = consistent && cellWords[i] >= 1 && cellWords[i] <= h.dagWords;
+			sum += cellWords[i];
+		}
+		if (!consistent || sum != h.dagWords) {
+			cpvs_container_destroy(c);
+			return fail(CPVS_EINVAL, "cpvs_container_load: %s: the cell table does not tile the DAG words", path);
+		}
+		if (int rc = prepareContainerLookups(c, grid, cellWords)) {
+			cpvs_container_destroy(c);
+			return rc;
+		}
 	}
 	c->finalized = true;
 	*out = c;
@@ -802,6 +924,7 @@ int cpvs_container_load(cpvs_ctx* ctx, const char* path, cpvs_container** out) {
 
 int cpvs_container_set_filter_size(cpvs_container* c, uint32_t size) {
 	if (!c) return fail(CPVS_EINVAL, "cpvs_container_set_filter_size: NULL argument");
+	if (size < 1 || size > 64) return fail(CPVS_EINVAL, "cpvs_container_set_filter_size: %u (1..64)", size);
 	c->filterSize = size;
 	return CPVS_OK;
 }

@@ -107,6 +107,22 @@ struct cpvs_minmax {
 	std::vector<cpvs::u64> columnCounts;  // [z * kMaxLevels + level]; [z * kMaxLevels + kRootMaskScalar] = 1 << 32 | root mask
 };
 
+namespace cpvs {
+// Private lookup-only copy of a DAG / container (lookup_index.cu): eight slots per inner node + one 32-byte k-code per leaf.
+struct LookupIndex {
+	u32* nodes = nullptr;  // 8 words per inner node: 0 shadow, 1 lit, 2 + id of the child node / leaf
+	u32* grid = nullptr;   // container: cell table with root node ids
+	u32* codes = nullptr;
+	u32* skip = nullptr;   // shortcut over the top levels (see LookupDag::skip), holding node ids
+	u32 skipLevels = 0;
+	u64 numNodes = 0, numLeaves = 0;
+	bool tried = false, valid = false;
+};
+void freeLookupIndex(cpvs_ctx* ctx, LookupIndex* ix);
+int buildLookupIndex(cpvs_ctx* ctx, const u32* dag, u64 dagWords, const std::vector<u64>& cellStart, const std::vector<u64>& cellWords,
+		const std::vector<u32>& hostGrid, u32 dagLevels, u32 gridLevels, LookupIndex* out);
+}  // namespace cpvs
+
 struct cpvs_pending_build;  // build.cu
 
 struct cpvs_shadow {
@@ -124,6 +140,7 @@ struct cpvs_shadow {
 	std::mutex skipLock;
 	cpvs::u32* skip;
 	cpvs::u32 skipLevels;
+	cpvs::LookupIndex index;  // built on the first lookup with leafmasks
 };
 
 struct ContainerCell {
@@ -149,6 +166,8 @@ struct cpvs_container {
 	int leafmasks = 0;
 	bool finalized = false;
 	bool loaded = false;  // came from cpvs_container_load: cells cannot be re-set
+	cpvs::LookupIndex index;  // built when the container is finalized
+	std::mutex indexLock;
 };
 
 namespace cpvs {

@@ -198,6 +198,10 @@ struct LookupDag {
 	// continue from. Private to the lookup; the DAG words themselves are untouched.
 	const u32* skip;
 	u32 skipLevels;
+	// Optional (lookup_index.cu): `dag` is the private lookup copy -- eight slots per inner node (0 shadow, 1 lit, 2 + id of the
+	// child), `grid` and `skip` hold node ids -- and leafCodes the 32-byte k-code per leaf id (nibble x of word y = lit slices of
+	// texel (x, y)).
+	const u32* leafCodes = nullptr;
 };
 constexpr u32 kSkipShadow = 0xFFFFFFFFu, kSkipVisible = 0xFFFFFFFEu;
 constexpr u32 kMaxSkipLevels = 6;
@@ -211,8 +215,12 @@ inline u32 skipLevelsFor(u32 dagLevels, int leafmasks, u32 gridLevels) {
 // Fills d.skip (writable here) for all cells; d.skipLevels must be set.
 int launchBuildSkipGrid(const LookupDag& d, u32* skip, cudaStream_t stream);
 int launchLookupNdc(const LookupDag& d, const float* ndc, long long count, unsigned char* out, cudaStream_t stream);
-int launchEvaluate(const LookupDag& d, const float* positions, unsigned width, unsigned height, const float* matrix, unsigned char* out,
+// filterSize: percentage-closer filter over filterSize^2 voxels of the pixel's depth slice (1 = one lookup, 0 / 255).
+int launchEvaluate(const LookupDag& d, const float* positions, unsigned width, unsigned height, const float* matrix, int filterSize, unsigned char* out,
 		cudaStream_t stream);
+// The same on CUDA surface objects: rgba32f positions, r8 visibilities (the renderer's G-buffer textures through CUDA-GL interop).
+int launchEvaluateSurface(const LookupDag& d, unsigned long long positions, unsigned long long visibilities, unsigned width, unsigned height,
+		const float* matrix, int filterSize, cudaStream_t stream);
 
 // ---- synthgen.cu: device-resident synthetic depth tiles (scene definition: ../synth/scene.h)
 struct CityBoxDev {

@@ -47,19 +47,35 @@ __device__ __forceinline__ u32 descend(const u32* __restrict__ dag, u32 offset, 
 	return (word >> (bit & 31)) & 1u;
 }
 
-__device__ __forceinline__ u32 lookupOne(const LookupDag& d, float x, float y, float z) {
-	const int resolution = (1 << (d.dagLevels + d.gridLevels - 1)) - 1;
-	const int px = pathCoord(x, resolution), py = pathCoord(y, resolution), pz = pathCoord(z, resolution);
+// The same descent on the private lookup copy (lookup_index.cu): one load per level at an address the path alone decides, one
+// load for the leaf -- lit <=> the slice lies below the texel's count of lit slices.
+__device__ __forceinline__ u32 descendSlots(const u32* __restrict__ nodes, const u32* __restrict__ codes, u32 node, int startLevel, int px, int py, int pz) {
+	for (int level = startLevel; level >= 3; --level) {
+		const u32 idx = ((px >> level) & 1) | (((py >> level) & 1) << 1) | (((pz >> level) & 1) << 2);
+		const u32 slot = __ldg(nodes + (size_t)node * 8u + idx);
+		if (slot < 2u) return slot;
+		node = slot - 2u;
+	}
+	const u32 row = __ldg(codes + (size_t)node * 8u + (u32)(py & 7));
+	return (u32)(pz & 7) < ((row >> (4 * (px & 7))) & 15u) ? 1u : 0u;
+}
+
+// The voxel (px, py, pz) of the whole virtual volume.
+__device__ __forceinline__ u32 lookupPath(const LookupDag& d, int px, int py, int pz) {
 	const u32* dag = d.dag;
+	u32 root = 0;  // lookup copy: the root's node id
 	if (d.grid) {  // traverse.cs:78-88
 		const u32 shift = d.dagLevels - 1, res = 1u << d.gridLevels;
 		const u32 cell = __ldg(d.grid + ((u32)(pz >> shift) * res + (u32)(py >> shift)) * res + (u32)(px >> shift));
 		if (cell == kCellShadowed) return 0u;
 		if (cell == kCellVisible) return 1u;
-		dag += cell;
+		if (d.leafCodes)
+			root = cell;
+		else
+			dag += cell;
 	}
 	int startLevel = (int)d.dagLevels - 2;
-	u32 offset = 0;
+	u32 offset = root;
 	if (d.skip) {  // the first skipLevels steps of the descent, precomputed per cell
 		const u32 shift = d.dagLevels - 1 - d.skipLevels, res = 1u << (d.gridLevels + d.skipLevels);
 		const u32 entry = __ldg(d.skip + ((u32)(pz >> shift) * res + (u32)(py >> shift)) * res + (u32)(px >> shift));
@@ -68,7 +84,13 @@ __device__ __forceinline__ u32 lookupOne(const LookupDag& d, float x, float y, f
 		offset = entry;
 		startLevel -= (int)d.skipLevels;
 	}
+	if (d.leafCodes) return descendSlots(dag, d.leafCodes, offset, startLevel, px, py, pz);
 	return descend(dag, offset, startLevel, d.leafmasks != 0, px, py, pz);
+}
+
+__device__ __forceinline__ u32 lookupOne(const LookupDag& d, float x, float y, float z) {
+	const int resolution = (1 << (d.dagLevels + d.gridLevels - 1)) - 1;
+	return lookupPath(d, pathCoord(x, resolution), pathCoord(y, resolution), pathCoord(z, resolution));
 }
 
 // One thread per shortcut cell: runs the first skipLevels steps of the descent for the cell's path prefix.
@@ -78,6 +100,7 @@ __global__ void __launch_bounds__(256) buildSkipGridKernel(LookupDag d, u32* __r
 	if (i >= res * res * res) return;
 	const u32 cx = i & (res - 1), cy = (i >> bits) & (res - 1), cz = i >> (2 * bits);
 	const u32* dag = d.dag;
+	u32 offset = 0;
 	if (d.grid) {
 		const u32 gres = 1u << d.gridLevels;
 		const u32 cell = d.grid[((cz >> d.skipLevels) * gres + (cy >> d.skipLevels)) * gres + (cx >> d.skipLevels)];
@@ -85,11 +108,22 @@ __global__ void __launch_bounds__(256) buildSkipGridKernel(LookupDag d, u32* __r
 			skip[i] = cell == kCellShadowed ? kSkipShadow : kSkipVisible;
 			return;
 		}
-		dag += cell;
+		if (d.leafCodes)
+			offset = cell;  // lookup copy: the root's node id
+		else
+			dag += cell;
 	}
-	u32 offset = 0;
 	for (int step = (int)d.skipLevels - 1; step >= 0; --step) {  // path bit dagLevels-2-k of the voxel = bit `step` of the cell
 		const u32 idx = ((cx >> step) & 1u) | (((cy >> step) & 1u) << 1) | (((cz >> step) & 1u) << 2);
+		if (d.leafCodes) {
+			const u32 slot = dag[(size_t)offset * 8u + idx];
+			if (slot < 2u) {
+				skip[i] = slot ? kSkipVisible : kSkipShadow;
+				return;
+			}
+			offset = slot - 2u;
+			continue;
+		}
 		const u32 mask = dag[offset];
 		const u32 vis = (mask >> (idx * 2)) & 3u;
 		if (vis != 2u) {
@@ -114,19 +148,50 @@ struct Mat4 {
 // traverse.cs main() (:135-149) with glm's evaluation order for mat4*vec4 and the divide by w.
 // 8x4-pixel warps (blockDim 8x32): neighbouring pixels share most of their path through the DAG, so a
 // compact footprint per warp means fewer distinct nodes per load instruction than a 32x1 strip.
-__global__ void __launch_bounds__(256) evaluateKernel(LookupDag d, const float4* __restrict__ pos, u32 width, u32 height, Mat4 mat,
-		unsigned char* __restrict__ out) {
+//
+// filterSize (setFilterSize, src/CompressedShadowContainer.h:71-73; `uniform int filterSize`, shader/traverse.cs:16-17 -- plumbed
+// through the reference but never used by its shader): percentage-closer filtering over filterSize x filterSize voxels of the
+// pixel's depth slice, centred on its voxel and clamped to the volume. 1 = the single lookup of the reference (0 / 255); larger
+// sizes write round(255 * lit taps / taps). The taps of a pixel share the upper part of their paths: their loads hit L1.
+struct PixelSource {  // linear rgba32f / r8 buffers, or CUDA surfaces (the G-buffer textures of the renderer mapped through CUDA-GL interop)
+	const float4* pos;
+	unsigned char* out;
+	cudaSurfaceObject_t posSurface, outSurface;
+};
+template <bool kSurface>
+__global__ void __launch_bounds__(256) evaluateKernel(LookupDag d, PixelSource io, u32 width, u32 height, Mat4 mat, int filterSize) {
 	const u32 x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
 	if (x >= width || y >= height) return;
 	const size_t i = (size_t)y * width + x;
-	const float4 p = pos[i];
+	float4 p;
+	if (kSurface)
+		p = surf2Dread<float4>(io.posSurface, (int)(x * sizeof(float4)), (int)y);
+	else
+		p = io.pos[i];
 	float v[4];
 #pragma unroll
 	for (int r = 0; r < 4; ++r)
 		v[r] = __fadd_rn(__fadd_rn(__fmul_rn(mat.m[r], p.x), __fmul_rn(mat.m[4 + r], p.y)),
 				__fadd_rn(__fmul_rn(mat.m[8 + r], p.z), mat.m[12 + r]));
-	const u32 vis = lookupOne(d, __fdiv_rn(v[0], v[3]), __fdiv_rn(v[1], v[3]), __fdiv_rn(v[2], v[3]));
-	out[i] = vis == 1u ? 255 : 0;
+	const int resolution = (1 << (d.dagLevels + d.gridLevels - 1)) - 1;
+	const int px = pathCoord(__fdiv_rn(v[0], v[3]), resolution), py = pathCoord(__fdiv_rn(v[1], v[3]), resolution),
+			  pz = pathCoord(__fdiv_rn(v[2], v[3]), resolution);
+	unsigned char result;
+	if (filterSize <= 1) {
+		result = lookupPath(d, px, py, pz) == 1u ? 255 : 0;
+	} else {
+		const int lo = -(filterSize / 2), hi = lo + filterSize;  // even sizes lean towards the lower texels
+		u32 lit = 0;
+		for (int dy = lo; dy < hi; ++dy)
+			for (int dx = lo; dx < hi; ++dx)
+				lit += lookupPath(d, min(max(px + dx, 0), resolution), min(max(py + dy, 0), resolution), pz) == 1u ? 1u : 0u;
+		const u32 taps = (u32)(filterSize * filterSize);
+		result = (unsigned char)((255u * lit + taps / 2u) / taps);
+	}
+	if (kSurface)
+		surf2Dwrite(result, io.outSurface, (int)x, (int)y);
+	else
+		io.out[i] = result;
 }
 
 }  // namespace
@@ -144,13 +209,25 @@ int launchLookupNdc(const LookupDag& d, const float* ndc, long long count, unsig
 	return 1;
 }
 
-int launchEvaluate(const LookupDag& d, const float* positions, unsigned width, unsigned height, const float* matrix, unsigned char* out,
+int launchEvaluate(const LookupDag& d, const float* positions, unsigned width, unsigned height, const float* matrix, int filterSize, unsigned char* out,
 		cudaStream_t stream) {
 	if (!width || !height) return 0;
 	Mat4 m;
 	for (int i = 0; i < 16; ++i) m.m[i] = matrix[i];
 	const dim3 block(8, 32), grid((width + 7) / 8, (height + 31) / 32);
-	evaluateKernel<<<grid, block, 0, stream>>>(d, reinterpret_cast<const float4*>(positions), width, height, m, out);
+	PixelSource io{reinterpret_cast<const float4*>(positions), out, 0, 0};
+	evaluateKernel<false><<<grid, block, 0, stream>>>(d, io, width, height, m, filterSize);
+	return 1;
+}
+
+int launchEvaluateSurface(const LookupDag& d, unsigned long long positions, unsigned long long visibilities, unsigned width, unsigned height,
+		const float* matrix, int filterSize, cudaStream_t stream) {
+	if (!width || !height) return 0;
+	Mat4 m;
+	for (int i = 0; i < 16; ++i) m.m[i] = matrix[i];
+	const dim3 block(8, 32), grid((width + 7) / 8, (height + 31) / 32);
+	PixelSource io{nullptr, nullptr, (cudaSurfaceObject_t)positions, (cudaSurfaceObject_t)visibilities};
+	evaluateKernel<true><<<grid, block, 0, stream>>>(d, io, width, height, m, filterSize);
 	return 1;
 }
 

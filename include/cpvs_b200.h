@@ -211,6 +211,20 @@ CPVS_API int cpvs_container_lookup_ndc(const cpvs_container* c, const float* ndc
  * column-major mat4 (glm::value_ptr order), visibilities = width*height r8 texels (0 or 255). */
 CPVS_API int cpvs_container_evaluate(const cpvs_container* c, const float* positions, uint32_t width, uint32_t height, int mem,
 		const float light_view_proj[16], uint8_t* visibilities);
+/* evaluate() on the textures themselves: CUDA surface objects (cudaSurfaceObject_t) over the arrays behind the rgba32f position
+ * texture and the r8 visibility texture the reference binds to image units 0 and 1 (src/CompressedShadowContainer.cpp:100-107).
+ * Asynchronous on the context's stream. With CUDA-GL interop the arrays are those of the renderer's own textures
+ * (cudaGraphicsGLRegisterImage + cudaGraphicsSubResourceGetMappedArray): cpvs_container_evaluate_gl below does exactly that
+ * and is compiled when the library is built with -DCPVS_WITH_GL (GL headers and a current GL context are needed). */
+CPVS_API int cpvs_container_evaluate_surface(const cpvs_container* c, unsigned long long positions_surface,
+		unsigned long long visibilities_surface, uint32_t width, uint32_t height, const float light_view_proj[16]);
+#ifdef CPVS_WITH_GL
+/* The drop-in for CompressedShadowContainer::evaluate(const Texture2D&, const mat4&, Texture2D*) in
+ * DeferredRenderer::doAllShading (src/DeferredRenderer.cpp:320-347): GL texture names of the G-buffer's position texture
+ * (rgba32f) and of the visibility texture (r8). */
+CPVS_API int cpvs_container_evaluate_gl(const cpvs_container* c, unsigned int positions_texture, unsigned int visibilities_texture,
+		uint32_t width, uint32_t height, const float light_view_proj[16]);
+#endif
 /* On-disk container (the reference has no serialisation and rebuilds on every launch).
  * File = 64-byte header {"CPVSDAG2", version, length, dag_levels, grid_levels, leafmasks, dag_words,
  * grid_cells, fnv64 over header fields + grid + DAG words} + grid words + DAG words, little endian. Loading validates
@@ -218,8 +232,10 @@ CPVS_API int cpvs_container_evaluate(const cpvs_container* c, const float* posit
  * A loaded container is finalized and ready for lookups; its cells cannot be re-set (CPVS_EINVAL). */
 CPVS_API int cpvs_container_save(const cpvs_container* c, const char* path);
 CPVS_API int cpvs_container_load(cpvs_ctx* ctx, const char* path, cpvs_container** out);
-/* setFilterSize (src/CompressedShadowContainer.h:71-73): stored, unused -- as in the reference
- * (shader/traverse.cs:16-17). */
+/* setFilterSize (src/CompressedShadowContainer.h:71-73). The reference plumbs the value into its shader
+ * (`uniform int filterSize`, shader/traverse.cs:16-17) and never uses it; here evaluate() filters: percentage-closer
+ * filtering over size x size voxels of the pixel's depth slice, centred on its voxel, clamped to the volume. 1 (the
+ * default) is the reference's single lookup and writes 0 / 255; larger sizes write round(255 * lit / taps). size <= 64. */
 CPVS_API int cpvs_container_set_filter_size(cpvs_container* c, uint32_t size);
 
 /* A container put together from cells that already sit in device memory -- possibly on other GPUs of the box (the words

@@ -18,6 +18,7 @@ def lib_path():
 
 def declared_symbols():
     text = open(os.path.join(ROOT, "include", "cpvs_b200.h")).read()
+    text = re.sub(r"#ifdef CPVS_WITH_GL.*?#endif", "", text, flags=re.S)  # GL interop glue: only in builds with GL headers
     return sorted(set(re.findall(r"CPVS_API[^;(]*?\b(cpvs_[a-z0-9_]+)\s*\(", text)))
 
 
