@@ -3,6 +3,7 @@
 #define CPVS_FACADE_COMPRESSED_SHADOW_H
 
 #include "MinMaxHierarchy.h"
+#include "ShadowMap.h"
 #include "cpvs.h"
 
 class CompressedShadow {
@@ -17,6 +18,15 @@ public:
 	static unique_ptr<CompressedShadow> create(const MinMaxHierarchy& minMax, uint zTileIndex = 0, uint zTileNum = 1, bool leafmasks = true) {
 		cpvs_shadow* h = nullptr;
 		cpvs_facade::check(cpvs_shadow_create(minMax.context(), minMax.handle(), zTileIndex, zTileNum, leafmasks ? 1 : 0, &h));
+		return unique_ptr<CompressedShadow>(new CompressedShadow(h));
+	}
+
+	// src/CompressedShadow.h:55-56 (src/CompressedShadow.cpp:61-64): the hierarchy is a temporary of the call.
+	static unique_ptr<CompressedShadow> create(const ShadowMap* shadowMap, uint zTileIndex = 0, uint zTileNum = 1, bool leafmasks = true,
+			cpvs_ctx* ctx = nullptr) {
+		cpvs_shadow* h = nullptr;
+		cpvs_facade::check(cpvs_shadow_create_from_depth(ctx ? ctx : cpvs_facade::defaultContext(), shadowMap->data(), (int)shadowMap->getSize(),
+				shadowMap->memoryKind(), zTileIndex, zTileNum, leafmasks ? 1 : 0, &h));
 		return unique_ptr<CompressedShadow>(new CompressedShadow(h));
 	}
 

@@ -1,6 +1,6 @@
 // CompressedShadowContainer with the reference's interface (src/CompressedShadowContainer.h:18-92).
-// evaluate() takes host or device arrays instead of GL textures (the CUDA-GL interop hook is the
-// "next" row of SURVEY.md 8f): positions = width*height rgba32f texels, visibilities = r8 texels.
+// evaluate() takes host or device arrays (positions = width*height rgba32f texels, visibilities = r8 texels) or CUDA surface
+// objects over the textures' arrays; with -DCPVS_WITH_GL also the GL texture names themselves (CUDA-GL interop).
 #ifndef CPVS_FACADE_COMPRESSED_SHADOW_CONTAINER_H
 #define CPVS_FACADE_COMPRESSED_SHADOW_CONTAINER_H
 
@@ -36,6 +36,18 @@ public:
 	void evaluate(const float* positionsWS, uint width, uint height, const mat4& lightViewProj, uint8_t* visibilities, int mem = CPVS_MEM_HOST) {
 		cpvs_facade::check(cpvs_container_evaluate(m_handle, positionsWS, width, height, mem, cpvs_facade::matrixData(lightViewProj), visibilities));
 	}
+	// the rgba32f position texture and the r8 visibility texture as cudaSurfaceObject_t (src/CompressedShadowContainer.cpp:100-107)
+	void evaluate(unsigned long long positionsSurface, unsigned long long visibilitiesSurface, uint width, uint height, const mat4& lightViewProj) {
+		cpvs_facade::check(cpvs_container_evaluate_surface(m_handle, positionsSurface, visibilitiesSurface, width, height,
+				cpvs_facade::matrixData(lightViewProj)));
+	}
+#ifdef CPVS_WITH_GL
+	// src/CompressedShadowContainer.h:59-60 with GL texture names (the reference passes Texture2D objects)
+	void evaluate(unsigned int positionsTexture, unsigned int visibilitiesTexture, uint width, uint height, const mat4& lightViewProj) {
+		cpvs_facade::check(cpvs_container_evaluate_gl(m_handle, positionsTexture, visibilitiesTexture, width, height,
+				cpvs_facade::matrixData(lightViewProj)));
+	}
+#endif
 	void lookupNdc(const float* ndcXyz, int64_t count, uint8_t* out, int mem = CPVS_MEM_HOST) {
 		cpvs_facade::check(cpvs_container_lookup_ndc(m_handle, ndcXyz, count, mem, out));
 	}

@@ -9,10 +9,11 @@
 
 class MinMaxHierarchy {
 public:
-	explicit MinMaxHierarchy(const ImageF& orig, cpvs_ctx* ctx = nullptr) : m_ctx(ctx ? ctx : cpvs_facade::defaultContext()) {
+	// zTileNum: the slicing the hierarchy's builds will use (createShadowTiles: one hierarchy, numSlices creates) -- a speed hint
+	explicit MinMaxHierarchy(const ImageF& orig, cpvs_ctx* ctx = nullptr, uint zTileNum = 1) : m_ctx(ctx ? ctx : cpvs_facade::defaultContext()) {
 		if (orig.getWidth() != orig.getHeight() || orig.getNumChannels() != 1)
 			throw cpvs_facade::Error(CPVS_EINVAL, "MinMaxHierarchy: the image must be square with one channel");
-		cpvs_facade::check(cpvs_minmax_build(m_ctx, orig.data(), (int)orig.getWidth(), CPVS_MEM_HOST, &m_handle));
+		cpvs_facade::check(cpvs_minmax_build_tiled(m_ctx, orig.data(), (int)orig.getWidth(), CPVS_MEM_HOST, zTileNum, &m_handle));
 		m_levels.resize(cpvs_minmax_num_levels(m_handle));
 	}
 	~MinMaxHierarchy() { cpvs_minmax_destroy(m_handle); }

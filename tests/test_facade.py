@@ -20,7 +20,16 @@ int main() {
     std::printf("words %zu levels %u vis %d\n", cs->getDAG().size(), cs->getNumLevels(), (int)cs->getTotalVisibility());
     if (cs->traverse(vec3(-1.f, -1.f, -1.f)) != CompressedShadow::VISIBLE) return 2;
     if (cs->traverse(vec3(1.f, 1.f, 1.f)) != CompressedShadow::SHADOW) return 3;
+    // create(const ShadowMap*, ...) (reference src/CompressedShadow.h:55-56): same words as through an explicit hierarchy
+    auto depth = std::make_shared<ImageF>(n, n, 1);
+    depth->setAll(img.data());
+    ShadowMap shadowMap(depth);
+    auto fromMap = CompressedShadow::create(&shadowMap);
+    if (fromMap->getDAG() != cs->getDAG()) return 5;
+    auto slice = CompressedShadow::create(&shadowMap, 1, 2);
+    if (slice->getDAG() != CompressedShadow::create(mm, 1, 2)->getDAG()) return 6;
     CompressedShadowContainer box(std::move(cs));
+    box.setFilterSize(1);
     box.moveToGPU();
     const float p[3] = {-1.f, -1.f, -1.f};
     uint8_t out = 9;
