@@ -218,7 +218,7 @@ GRIDS = {"64k": (2, 4, "terrain_dev"), "256k": (4, 16, "city")}  # name -> (BASE
 def grid_line(res, cfg_index):
     """The part of a grid result that goes into the bench line."""
     keep = ("virtual_side", "tile", "length", "kind", "n_gpus", "cells", "one_word_cells", "ownership", "moved_tiles", "build_ms_max_rank",
-            "build_ms_per_rank", "tiles_per_rank", "wall_ms_max_rank", "gather_sizes_ms", "replicate_and_finalize_ms", "dag_words", "dag_mbytes",
+            "build_ms_per_rank", "depth_ms_per_rank", "timing", "tiles_per_rank", "wall_ms_max_rank", "gather_sizes_ms", "replicate_and_finalize_ms", "dag_words", "dag_mbytes",
             "svo_nodes", "dag_nodes", "gpu_launches", "lookups", "lookups_g_per_s", "verified", "depth_source")
     out = {k: res[k] for k in keep if k in res}
     out["workload"] = ("configs[%d]: %dK^2 virtual %s shadow map as a %dx%dx%d CompressedShadowContainer of %dx%d depth tiles generated on the "

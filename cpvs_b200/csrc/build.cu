@@ -141,7 +141,7 @@ struct Build {
 			if (done) cudaEventSynchronize(done);  // an abandoned build may still be writing it
 			ctx->readbackFree.push_back(h);
 		}
-		if (dagAlloc) cudaFreeAsync(dagAlloc, st);
+		if (dagAlloc) ctxFree(ctx, dagAlloc);
 		for (cudaEvent_t e : {evRankStart, evRankStop, evLeafEmitStart, done})
 			if (e) cudaEventDestroy(e);
 	}
@@ -663,8 +663,14 @@ int enqueueBuild(Build& b, const u64* exactCounts, const SizeMemo* memo, cudaEve
 	// The DAG's allocation: with a memo of this shape its size is predicted and the leaf level can be written during the
 	// merge; otherwise it is made once the sizes are known.
 	if (memo && ctx->predictSizes) {
-		b.dagCapacity = memo->words + (memo->words >> ctx->headroomShift) + 1024;
-		cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&b.dagAlloc), b.dagCapacity * sizeof(u32), st);
+		u64 expectWords = memo->words;
+		if (exactCounts && memo->nodes[b.minLevel] && b.lv[b.minLevel].cap) {
+			// this build's node counts are known: the words follow the bottom level (same scene, another tile or slice)
+			const double ratio = (double)b.lv[b.minLevel].cap / (double)memo->nodes[b.minLevel];
+			expectWords = (u64)((double)memo->words * ratio) + 4096;
+		}
+		b.dagCapacity = expectWords + (expectWords >> ctx->headroomShift) + 1024;
+		cudaError_t e = ctxAlloc(ctx, reinterpret_cast<void**>(&b.dagAlloc), b.dagCapacity * sizeof(u32));
 		if (e != cudaSuccess) return fail(CPVS_ENOMEM, "DAG allocation of %llu words: %s", (unsigned long long)b.dagCapacity, cudaGetErrorString(e));
 	}
 	bool tablesClearing = false;
@@ -691,7 +697,7 @@ int enqueueBuild(Build& b, const u64* exactCounts, const SizeMemo* memo, cudaEve
 		if (!(u32)b.h[kSlotTableError] && !((u32)b.h[kSlotOverflow] & kOverflowNodes)) {  // (finishBuild reports those)
 			b.dagCapacity = b.h[kSlotTotal];
 			if (b.dagCapacity > (1ull << 32)) return fail(CPVS_EOVERFLOW, "DAG needs %llu words; offsets are 32-bit", (unsigned long long)b.dagCapacity);
-			cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&b.dagAlloc), b.dagCapacity * sizeof(u32), st);
+			cudaError_t e = ctxAlloc(ctx, reinterpret_cast<void**>(&b.dagAlloc), b.dagCapacity * sizeof(u32));
 			if (e != cudaSuccess) return fail(CPVS_ENOMEM, "DAG allocation of %llu words: %s", (unsigned long long)b.dagCapacity, cudaGetErrorString(e));
 			for (int l = b.minLevel; l <= b.top; ++l) b.lv[l].hint = b.h[kSlotUnique + l];
 		}
@@ -747,10 +753,10 @@ int finishBuild(Build& b, cpvs_shadow* s, bool arenaIntact, bool* redo) {
 			}
 			// The merge results are all still in the arena: emit again into an exact allocation.
 			++ctx->reemissions;
-			CPVS_CUDA(cudaFreeAsync(b.dagAlloc, st));
+			ctxFree(ctx, b.dagAlloc);
 			b.dagAlloc = nullptr;
 			b.dagCapacity = totalWords;
-			e = cudaMallocAsync(reinterpret_cast<void**>(&b.dagAlloc), b.dagCapacity * sizeof(u32), st);
+			e = ctxAlloc(ctx, reinterpret_cast<void**>(&b.dagAlloc), b.dagCapacity * sizeof(u32));
 			if (e != cudaSuccess) return fail(CPVS_ENOMEM, "DAG allocation of %llu words: %s", (unsigned long long)b.dagCapacity, cudaGetErrorString(e));
 			CPVS_CUDA(cudaMemsetAsync(b.dOverflow(), 0, sizeof(u32), st));
 			b.leavesEmitted = false;
@@ -797,7 +803,22 @@ int finishBuild(Build& b, cpvs_shadow* s, bool arenaIntact, bool* redo) {
 
 // The synchronous path with exact counts (first build of a shape, z-slices of a tile column, and every rebuild). The
 // column's counts are computed once per hierarchy; a slice that misses the surface is its root's mask word.
-int buildExact(cpvs_ctx* ctx, const cpvs_minmax* mm, u32 zTileIndex, u32 zTileNum, bool useLeaf, cpvs_shadow* s) {
+int buildExact(cpvs_ctx* ctx, const cpvs_minmax* mm, u32 zTileIndex, u32 zTileNum, bool useLeaf, cpvs_shadow* s, bool async);
+
+}  // namespace
+
+// A build in flight (cpvs_shadow_create_async): everything finishBuild needs, and what a rebuild would.
+struct cpvs_pending_build {
+	Build b;
+	const cpvs_minmax* mm;
+	u64 serial;  // the context's build counter when this one was enqueued
+};
+
+namespace {
+
+// async: with a memo of this shape the DAG's allocation is predicted, nothing is read back inside the build, and the call may
+// return with the build in flight (s->pending).
+int buildExact(cpvs_ctx* ctx, const cpvs_minmax* mm, u32 zTileIndex, u32 zTileNum, bool useLeaf, cpvs_shadow* s, bool async) {
 	const int L = mm->numLevels, top = L - 2, minLevel = useLeaf ? 2 : 0;
 	cudaStream_t st = ctx->stream;
 	const PyramidView pyr = pyramidView(mm);
@@ -807,6 +828,7 @@ int buildExact(cpvs_ctx* ctx, const cpvs_minmax* mm, u32 zTileIndex, u32 zTileNu
 		memoCopy = *memo;  // rememberSizes() may move the vector's storage
 		memo = &memoCopy;
 	}
+	async = async && memo && ctx->predictSizes;
 	struct EventGuard {
 		cudaEvent_t ev = nullptr;
 		~EventGuard() {
@@ -815,7 +837,7 @@ int buildExact(cpvs_ctx* ctx, const cpvs_minmax* mm, u32 zTileIndex, u32 zTileNu
 	} countStart;
 	u64 counts[kMaxLevels] = {0};
 	const bool cached = mm->columnSlices == zTileNum && mm->columnMinLevel == minLevel;
-	if (!cached) {
+	if (!cached && !async) {
 		CPVS_CUDA(cudaEventCreate(&countStart.ev));
 		CPVS_CUDA(cudaEventRecord(countStart.ev, st));
 	}
@@ -825,6 +847,20 @@ int buildExact(cpvs_ctx* ctx, const cpvs_minmax* mm, u32 zTileIndex, u32 zTileNu
 	for (int l = 0; l < kMaxLevels; ++l) counts[l] = mine[l];
 	if (counts[top - 1] == 0) return oneWordShadow(ctx, L, useLeaf, (u32)counts[kRootMaskScalar], s);
 	++ctx->exactBuilds;
+	++ctx->buildSerial;
+	if (async) {
+		cpvs_pending_build* p = new (std::nothrow) cpvs_pending_build();
+		if (!p) return fail(CPVS_ENOMEM, "cpvs_shadow_create: host allocation");
+		p->mm = mm;
+		p->b.ctx = ctx;
+		p->b.mm = mm;
+		p->b.zTileIndex = zTileIndex;
+		p->b.zTileNum = zTileNum;
+		p->b.useLeaf = useLeaf;
+		p->serial = ctx->buildSerial;
+		s->pending = p;
+		return enqueueBuild(p->b, counts, memo, nullptr);
+	}
 	Build b;
 	b.ctx = ctx;
 	b.mm = mm;
@@ -851,13 +887,6 @@ PyramidView pyramidView(const cpvs_minmax* mm) {
 	return pyr;
 }
 }  // namespace cpvs
-
-// A build in flight (cpvs_shadow_create_async): everything finishBuild needs, and what a rebuild would.
-struct cpvs_pending_build {
-	Build b;
-	const cpvs_minmax* mm;
-	u64 serial;  // the context's build counter when this one was enqueued
-};
 
 extern "C" {
 
@@ -912,8 +941,11 @@ static int createImpl(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex,
 		buildGuard.unlock();
 		if (rc == CPVS_OK) rc = cpvs_shadow_wait(s);
 	} else {
-		++ctx->buildSerial;
-		rc = buildExact(ctx, mm, zTileIndex, zTileNum, useLeaf, s);
+		rc = buildExact(ctx, mm, zTileIndex, zTileNum, useLeaf, s, async);
+		if (rc == CPVS_OK && s->pending) {  // in flight
+			*out = s;
+			return CPVS_OK;
+		}
 	}
 	if (rc != CPVS_OK) {
 		if (buildGuard.owns_lock()) buildGuard.unlock();
@@ -944,10 +976,10 @@ int cpvs_shadow_wait(cpvs_shadow* s) {
 	int rc = finishBuild(p->b, s, p->serial == ctx->buildSerial, &redo);
 	if (rc == CPVS_OK && redo) {  // a predicted capacity did not suffice: once more, with exact counts
 		++ctx->overflowRebuilds;
-		++ctx->buildSerial;
 		const cpvs_minmax* mm = p->mm;
 		const Build& b = p->b;
-		rc = buildExact(ctx, mm, b.zTileIndex, b.zTileNum, b.useLeaf, s);
+		s->pending = nullptr;
+		rc = buildExact(ctx, mm, b.zTileIndex, b.zTileNum, b.useLeaf, s, false);
 	}
 	s->pending = nullptr;
 	delete p;
@@ -975,7 +1007,7 @@ int cpvs_shadow_destroy(cpvs_shadow* s) {
 		s->pending = nullptr;
 		delete p;
 	}
-	if (s->dagAlloc) cudaFreeAsync(s->dagAlloc, s->ctx->stream);
+	ctxFree(s->ctx, s->dagAlloc);
 	if (s->skip) cudaFreeAsync(s->skip, s->ctx->stream);
 	freeLookupIndex(s->ctx, &s->index);
 	if (s->ready) cudaEventDestroy(s->ready);

@@ -16,6 +16,52 @@ thread_local std::string gLastError;
 }  // namespace
 
 namespace cpvs {
+constexpr size_t kCacheMinBytes = 4u << 20, kCacheMaxBytes = 24ull << 30, kCacheMaxBlocks = 24;
+
+cudaError_t ctxAlloc(cpvs_ctx* ctx, void** out, size_t bytes) {
+	*out = nullptr;
+	if (!bytes) bytes = 1;
+	if (bytes >= kCacheMinBytes) {
+		std::lock_guard<std::mutex> guard(ctx->cacheLock);
+		size_t best = ctx->freeBlocks.size();
+		for (size_t i = 0; i < ctx->freeBlocks.size(); ++i) {
+			const size_t have = ctx->freeBlocks[i].second;
+			if (have >= bytes && have - bytes <= bytes / 4 && (best == ctx->freeBlocks.size() || have < ctx->freeBlocks[best].second)) best = i;
+		}
+		if (best != ctx->freeBlocks.size()) {
+			*out = ctx->freeBlocks[best].first;
+			ctx->liveBlocks[*out] = ctx->freeBlocks[best].second;
+			ctx->cachedBytes -= ctx->freeBlocks[best].second;
+			ctx->freeBlocks.erase(ctx->freeBlocks.begin() + best);
+			return cudaSuccess;
+		}
+	}
+	const cudaError_t e = cudaMallocAsync(out, bytes, ctx->stream);
+	if (e == cudaSuccess && bytes >= kCacheMinBytes) {
+		std::lock_guard<std::mutex> guard(ctx->cacheLock);
+		ctx->liveBlocks[*out] = bytes;
+	}
+	return e;
+}
+
+void ctxFree(cpvs_ctx* ctx, void* p) {
+	if (!p) return;
+	std::lock_guard<std::mutex> guard(ctx->cacheLock);
+	const auto it = ctx->liveBlocks.find(p);
+	if (it == ctx->liveBlocks.end()) {
+		cudaFreeAsync(p, ctx->stream);
+		return;
+	}
+	ctx->freeBlocks.emplace_back(p, it->second);
+	ctx->cachedBytes += it->second;
+	ctx->liveBlocks.erase(it);
+	while (!ctx->freeBlocks.empty() && (ctx->cachedBytes > kCacheMaxBytes || ctx->freeBlocks.size() > kCacheMaxBlocks)) {
+		cudaFreeAsync(ctx->freeBlocks.front().first, ctx->stream);
+		ctx->cachedBytes -= ctx->freeBlocks.front().second;
+		ctx->freeBlocks.erase(ctx->freeBlocks.begin());
+	}
+}
+
 int fail(int code, const char* fmt, ...) {
 	char buf[512];
 	va_list ap;
@@ -76,6 +122,7 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 	ctx->arenaBytes = 0;
 	ctx->scalars = nullptr;
 	ctx->own = ctx->aux = ctx->aux2 = ctx->aux3 = ctx->aux4 = nullptr;
+	ctx->cachedBytes = 0;
 	ctx->predictedBuilds = ctx->exactBuilds = ctx->overflowRebuilds = ctx->reemissions = 0;
 	cudaEvent_t* plain[] = {&ctx->evFork, &ctx->evJoin, &ctx->evJoin3, &ctx->evClear, &ctx->evCols, &ctx->evLeafRanked, &ctx->evLeafEmitted};
 	for (cudaEvent_t* e : plain) *e = nullptr;
@@ -121,6 +168,8 @@ int cpvs_ctx_destroy(cpvs_ctx* ctx) {
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	if (ctx->arena) cudaFreeAsync(ctx->arena, ctx->stream);
+	for (auto& block : ctx->freeBlocks) cudaFreeAsync(block.first, ctx->stream);
+	ctx->freeBlocks.clear();
 	cudaStreamSynchronize(ctx->stream);
 	if (ctx->scalars) cudaFree(ctx->scalars);
 	for (u64* slot : ctx->readbackAll) cudaFreeHost(slot);
@@ -186,7 +235,7 @@ int cpvs_minmax_build(cpvs_ctx* ctx, const float* depth, int n, int mem, cpvs_mi
 
 int cpvs_minmax_build_tiled(cpvs_ctx* ctx, const float* depth, int n, int mem, uint32_t zTileNum, cpvs_minmax** out) {
 	if (!ctx || !depth || !out) return fail(CPVS_EINVAL, "cpvs_minmax_build: NULL argument");
-	if (zTileNum == 0 || (u64)(n > 0 ? n : 0) * zTileNum > (1ull << 23)) return fail(CPVS_EINVAL, "cpvs_minmax_build_tiled: %u z-slices of side %d", zTileNum, n);
+	if ((u64)(n > 0 ? n : 0) * zTileNum > (1ull << 23)) return fail(CPVS_EINVAL, "cpvs_minmax_build_tiled: %u z-slices of side %d", zTileNum, n);
 	*out = nullptr;
 	if (n < 2 || !isPow2((u64)n) || n > (1 << 19)) return fail(CPVS_EINVAL, "cpvs_minmax_build: side %d is not a power of two in [2, 2^19]", n);
 	if (mem != CPVS_MEM_HOST && mem != CPVS_MEM_DEVICE) return fail(CPVS_EINVAL, "cpvs_minmax_build: mem %d", mem);
@@ -214,24 +263,24 @@ int cpvs_minmax_build_tiled(cpvs_ctx* ctx, const float* depth, int n, int mem, u
 	// Column residues for the per-column leaf builder: where that builder is used (maps >= 8192^2 whose last build on this
 	// context took it, or always when it is forced), one byte per texel written by the base kernel saves it the second pass
 	// over the 4-byte depths.
-	bool wantResidue = n >= 128 && (ctx->leafColumns == 2 || (ctx->leafColumns == 1 && n >= 8192));
+	bool wantResidue = zTileNum > 0 && n >= 128 && (ctx->leafColumns == 2 || (ctx->leafColumns == 1 && n >= 8192));
 	if (wantResidue && ctx->leafColumns == 1) {
 		std::lock_guard<std::mutex> guard(ctx->buildLock);
 		for (int side : ctx->noColumnSides) wantResidue = wantResidue && side != n;
 	}
-	cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&mm->levelStorage), total * sizeof(float), ctx->stream);
+	cudaError_t e = ctxAlloc(ctx, reinterpret_cast<void**>(&mm->levelStorage), total * sizeof(float));
 	if (e == cudaSuccess && wantResidue) {
-		e = cudaMallocAsync(reinterpret_cast<void**>(&mm->residue), (u64)n * n, ctx->stream);
+		e = ctxAlloc(ctx, reinterpret_cast<void**>(&mm->residue), (u64)n * n);
 		mm->residueTiles = zTileNum;
 	}
 	if (e == cudaSuccess && mem == CPVS_MEM_HOST) {
-		e = cudaMallocAsync(reinterpret_cast<void**>(&mm->ownedDepth), (u64)n * n * sizeof(float), ctx->stream);
+		e = ctxAlloc(ctx, reinterpret_cast<void**>(&mm->ownedDepth), (u64)n * n * sizeof(float));
 		if (e == cudaSuccess) e = cudaMemcpyAsync(mm->ownedDepth, depth, (u64)n * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
 	}
 	if (e != cudaSuccess) {
-		if (mm->levelStorage) cudaFreeAsync(mm->levelStorage, ctx->stream);
-		if (mm->residue) cudaFreeAsync(mm->residue, ctx->stream);
-		if (mm->ownedDepth) cudaFreeAsync(mm->ownedDepth, ctx->stream);
+		ctxFree(ctx, mm->levelStorage);
+		ctxFree(ctx, mm->residue);
+		ctxFree(ctx, mm->ownedDepth);
 		delete mm;
 		return fail(e == cudaErrorMemoryAllocation ? CPVS_ENOMEM : CPVS_ECUDA, "cpvs_minmax_build: %s", cudaGetErrorString(e));
 	}
@@ -263,9 +312,9 @@ int cpvs_minmax_build_tiled(cpvs_ctx* ctx, const float* depth, int n, int mem, u
 int cpvs_minmax_destroy(cpvs_minmax* mm) {
 	if (!mm) return CPVS_OK;
 	cudaSetDevice(mm->ctx->device);
-	if (mm->levelStorage) cudaFreeAsync(mm->levelStorage, mm->ctx->stream);
-	if (mm->residue) cudaFreeAsync(mm->residue, mm->ctx->stream);
-	if (mm->ownedDepth) cudaFreeAsync(mm->ownedDepth, mm->ctx->stream);
+	ctxFree(mm->ctx, mm->levelStorage);
+	ctxFree(mm->ctx, mm->residue);
+	ctxFree(mm->ctx, mm->ownedDepth);
 	if (mm->evStart) {
 		cudaEventDestroy(mm->evStart);
 		cudaEventDestroy(mm->evBase);

@@ -42,6 +42,11 @@ double nowMs() { return std::chrono::duration<double, std::milli>(std::chrono::s
 
 struct cpvs_grid_worker {
 	cpvs_ctx* ctx = nullptr;
+	// A second context of the same GPU: the z-slices of a tile are independent builds from one hierarchy, so they alternate
+	// between the two contexts and run side by side (the kernels of one fill the latency-bound phases of the other).
+	cpvs_ctx* ctx2 = nullptr;
+	cudaEvent_t evJoin = nullptr;
+	float depthMs = 0.f;  // device time spent producing depth tiles (not part of the build metric: it starts from resident depth)
 	cpvs_grid_desc desc{};
 	std::vector<WorkerTile> tiles;
 	float* hostStage = nullptr;  // pinned, one tile (fetch callback)
@@ -64,28 +69,32 @@ WorkerTile* findTile(cpvs_grid_worker* w, u32 x, u32 y) {
 void releaseInputs(cpvs_grid_worker* w, WorkerTile& t) {
 	if (t.mm) cpvs_minmax_destroy(t.mm);
 	t.mm = nullptr;
-	if (t.depth) cudaFreeAsync(t.depth, w->ctx->stream);
+	ctxFree(w->ctx, t.depth);
 	t.depth = nullptr;
 }
 
-// Depth tile in device memory + its pyramid, prepared for `length` z-slices.
-int produceTile(cpvs_grid_worker* w, WorkerTile& t) {
-	if (t.mm) return CPVS_OK;
+// Depth tile in device memory (generated there, or fetched from the caller and copied).
+int produceDepth(cpvs_grid_worker* w, WorkerTile& t) {
+	if (t.depth) return CPVS_OK;
 	cpvs_ctx* ctx = w->ctx;
 	const cpvs_grid_desc& d = w->desc;
 	const size_t texels = (size_t)d.tile * d.tile;
 	CPVS_CUDA(cudaSetDevice(ctx->device));
-	CPVS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&t.depth), texels * sizeof(float), ctx->stream));
-	if (d.scene >= 0) {
-		if (int rc = cpvs_depth_generate(ctx, d.scene, d.tile, (int)t.x, (int)t.y, (int)d.length, t.depth)) return rc;
-	} else {
-		if (!d.fetch) return fail(CPVS_EINVAL, "cpvs_grid: neither a scene nor a fetch callback");
-		if (!w->hostStage) CPVS_CUDA(cudaMallocHost(reinterpret_cast<void**>(&w->hostStage), texels * sizeof(float)));
-		CPVS_CUDA(cudaStreamSynchronize(ctx->stream));  // the previous tile's copy out of the staging buffer
-		if (d.fetch(d.user, t.x, t.y, w->hostStage) != 0) return fail(CPVS_EINVAL, "cpvs_grid: fetch callback failed for tile (%u,%u)", t.x, t.y);
-		CPVS_CUDA(cudaMemcpyAsync(t.depth, w->hostStage, texels * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-	}
-	return cpvs_minmax_build_tiled(ctx, t.depth, d.tile, CPVS_MEM_DEVICE, d.length, &t.mm);
+	CPVS_CUDA(ctxAlloc(ctx, reinterpret_cast<void**>(&t.depth), texels * sizeof(float)));
+	if (d.scene >= 0) return cpvs_depth_generate(ctx, d.scene, d.tile, (int)t.x, (int)t.y, (int)d.length, t.depth);
+	if (!d.fetch) return fail(CPVS_EINVAL, "cpvs_grid: neither a scene nor a fetch callback");
+	if (!w->hostStage) CPVS_CUDA(cudaMallocHost(reinterpret_cast<void**>(&w->hostStage), texels * sizeof(float)));
+	CPVS_CUDA(cudaStreamSynchronize(ctx->stream));  // the previous tile's copy out of the staging buffer
+	if (d.fetch(d.user, t.x, t.y, w->hostStage) != 0) return fail(CPVS_EINVAL, "cpvs_grid: fetch callback failed for tile (%u,%u)", t.x, t.y);
+	CPVS_CUDA(cudaMemcpyAsync(t.depth, w->hostStage, texels * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+	return CPVS_OK;
+}
+
+// + its pyramid, prepared for `length` z-slices.
+int produceTile(cpvs_grid_worker* w, WorkerTile& t) {
+	if (t.mm) return CPVS_OK;
+	if (int rc = produceDepth(w, t)) return rc;
+	return cpvs_minmax_build_tiled(w->ctx, t.depth, w->desc.tile, CPVS_MEM_DEVICE, w->desc.length, &t.mm);
 }
 
 struct DeviceTimer {  // accumulates device time between construction and destruction into the worker
@@ -113,10 +122,16 @@ int cpvs_grid_worker_create(cpvs_ctx* ctx, const cpvs_grid_desc* desc, cpvs_grid
 	w->ctx = ctx;
 	w->desc = *desc;
 	cudaSetDevice(ctx->device);
-	if (cudaEventCreate(&w->ev0) != cudaSuccess || cudaEventCreate(&w->ev1) != cudaSuccess) {
+	if (cudaEventCreate(&w->ev0) != cudaSuccess || cudaEventCreate(&w->ev1) != cudaSuccess ||
+			cudaEventCreateWithFlags(&w->evJoin, cudaEventDisableTiming) != cudaSuccess) {
 		cpvs_grid_worker_destroy(w);
 		return fail(CPVS_ECUDA, "cpvs_grid_worker_create: events");
 	}
+	if (int rc = cpvs_ctx_create(ctx->device, &w->ctx2)) {
+		cpvs_grid_worker_destroy(w);
+		return rc;
+	}
+	cpvs_ctx_set_prediction(w->ctx2, ctx->predictSizes, ctx->headroomShift);
 	*out = w;
 	return CPVS_OK;
 }
@@ -130,50 +145,69 @@ int cpvs_grid_worker_destroy(cpvs_grid_worker* w) {
 	}
 	if (w->hostStage) cudaFreeHost(w->hostStage);
 	if (w->exported) cudaFree(w->exported);
+	if (w->evJoin) cudaEventDestroy(w->evJoin);
+	if (w->ctx2) cpvs_ctx_destroy(w->ctx2);
 	if (w->ev0) cudaEventDestroy(w->ev0);
 	if (w->ev1) cudaEventDestroy(w->ev1);
 	delete w;
 	return CPVS_OK;
 }
 
-// Cost of tiles = SVO nodes of all their z-slices (closed form: one launch and one read-back per tile); the depth tile and
-// its pyramid stay resident for the build. xy: count pairs (x, y).
+// Cost of tiles, for the ownership. Scenes generated on the device are sampled at an eighth of the tile's resolution (same
+// window, same slicing: its leaves are the tile's level-5 nodes) and the nodes of all z-slices of that small hierarchy are
+// counted -- a proxy that costs a few launches and keeps nothing resident. Tiles handed over by a callback cannot be
+// resampled: their own hierarchy is built and counted, and stays resident for cpvs_grid_worker_build. xy: count pairs (x, y).
 int cpvs_grid_worker_estimate(cpvs_grid_worker* w, const uint32_t* xy, int count, uint64_t* costOut) {
 	if (!w || (count > 0 && (!xy || !costOut))) return fail(CPVS_EINVAL, "cpvs_grid_worker_estimate: NULL argument");
 	DeviceTimer timer(w);
-	const int L = [&] {
-		int levels = 1;
-		while ((1 << (levels - 1)) < w->desc.tile) ++levels;
-		return levels;
-	}();
-	const bool useLeaf = w->desc.leafmasks && (L - 3) >= 2;
+	cpvs_ctx* ctx = w->ctx;
+	const cpvs_grid_desc& d = w->desc;
+	const bool proxy = d.scene >= 0 && d.tile >= 1024;
+	const int side = proxy ? d.tile / 8 : d.tile;
+	int L = 1;
+	while ((1 << (L - 1)) < side) ++L;
+	const bool useLeaf = d.leafmasks && (L - 3) >= 2;
 	const int minLevel = useLeaf ? 2 : 0;
-	for (int i = 0; i < count; ++i) {
-		WorkerTile* t = findTile(w, xy[2 * i], xy[2 * i + 1]);
-		if (!t) {
-			w->tiles.emplace_back();
-			t = &w->tiles.back();
-			t->x = xy[2 * i];
-			t->y = xy[2 * i + 1];
-		}
-		if (int rc = produceTile(w, *t)) return rc;
-		if (!useLeaf)
-			if (int rc = ensureLowLevels(t->mm, 1)) return rc;
-		const u64* counts = nullptr;
-		if (int rc = columnCountsOf(w->ctx, t->mm, w->desc.length, minLevel, &counts)) return rc;
-		u64 cost = 0;
-		for (u32 z = 0; z < w->desc.length; ++z) {
-			const u64* c = counts + (size_t)z * kMaxLevels;
-			if (c[L - 3] == 0) {  // a one-word cell
-				cost += 1;
-				continue;
+	float* small = nullptr;
+	if (proxy) CPVS_CUDA(ctxAlloc(ctx, reinterpret_cast<void**>(&small), (size_t)side * side * sizeof(float)));
+	int rc = CPVS_OK;
+	for (int i = 0; i < count && rc == CPVS_OK; ++i) {
+		cpvs_minmax* mm = nullptr;
+		WorkerTile* t = nullptr;
+		if (proxy) {
+			rc = cpvs_depth_generate(ctx, d.scene, side, (int)xy[2 * i], (int)xy[2 * i + 1], (int)d.length, small);
+			if (rc == CPVS_OK) rc = cpvs_minmax_build_tiled(ctx, small, side, CPVS_MEM_DEVICE, 0, &mm);
+		} else {
+			t = findTile(w, xy[2 * i], xy[2 * i + 1]);
+			if (!t) {
+				w->tiles.emplace_back();
+				t = &w->tiles.back();
+				t->x = xy[2 * i];
+				t->y = xy[2 * i + 1];
 			}
-			for (int l = minLevel; l <= L - 3; ++l) cost += c[l] * (useLeaf && l == 2 ? 3u : 2u);  // leaves weigh more: built, hashed, expanded
+			rc = produceTile(w, *t);
+			mm = t->mm;
 		}
-		t->cost = cost + ((u64)w->desc.tile * w->desc.tile >> 4);  // + the pyramid pass over the tile
-		costOut[i] = t->cost;
+		if (rc == CPVS_OK && !useLeaf) rc = ensureLowLevels(mm, 1);
+		const u64* counts = nullptr;
+		if (rc == CPVS_OK) rc = columnCountsOf(ctx, mm, d.length, minLevel, &counts);
+		if (rc == CPVS_OK) {
+			u64 cost = 0;
+			for (u32 z = 0; z < d.length; ++z) {
+				const u64* c = counts + (size_t)z * kMaxLevels;
+				if (c[L - 3] == 0) {  // a one-word cell
+					cost += 1;
+					continue;
+				}
+				for (int l = minLevel; l <= L - 3; ++l) cost += c[l] * (useLeaf && l == 2 ? 3u : 2u);  // leaves weigh more: built, hashed, expanded
+			}
+			costOut[i] = cost + ((u64)side * side >> 4);  // + the pyramid pass over the tile
+			if (t) t->cost = costOut[i];
+		}
+		if (proxy && mm) cpvs_minmax_destroy(mm);
 	}
-	return CPVS_OK;
+	if (small) ctxFree(ctx, small);
+	return rc;
 }
 
 // Drops tiles that were estimated here but went to another worker.
@@ -193,7 +227,8 @@ int cpvs_grid_worker_release(cpvs_grid_worker* w, const uint32_t* xy, int count)
 // createShadowTiles for the given xy tiles: depth tile (unless still resident from the estimate), pyramid, one DAG per z-slice.
 int cpvs_grid_worker_build(cpvs_grid_worker* w, const uint32_t* xy, int count) {
 	if (!w || (count > 0 && !xy)) return fail(CPVS_EINVAL, "cpvs_grid_worker_build: NULL argument");
-	DeviceTimer timer(w);
+	cpvs_ctx* ctx = w->ctx;
+	CPVS_CUDA(cudaSetDevice(ctx->device));
 	for (int i = 0; i < count; ++i) {
 		WorkerTile* t = findTile(w, xy[2 * i], xy[2 * i + 1]);
 		if (!t) {
@@ -203,10 +238,30 @@ int cpvs_grid_worker_build(cpvs_grid_worker* w, const uint32_t* xy, int count) {
 			t->y = xy[2 * i + 1];
 		}
 		if (t->built) continue;
+		// the depth tile first (its own clock: the build metric starts from depth resident in device memory)
+		if (!t->depth) {
+			CPVS_CUDA(cudaEventRecord(w->ev0, ctx->stream));
+			if (int rc = produceDepth(w, *t)) return rc;
+			CPVS_CUDA(cudaEventRecord(w->ev1, ctx->stream));
+			CPVS_CUDA(cudaEventSynchronize(w->ev1));
+			float ms = 0.f;
+			CPVS_CUDA(cudaEventElapsedTime(&ms, w->ev0, w->ev1));
+			w->depthMs += ms;
+		}
+		CPVS_CUDA(cudaEventRecord(w->ev0, ctx->stream));
 		if (int rc = produceTile(w, *t)) return rc;
 		t->cells.assign(w->desc.length, nullptr);
 		for (u32 z = 0; z < w->desc.length; ++z)
-			if (int rc = cpvs_shadow_create(w->ctx, t->mm, z, w->desc.length, w->desc.leafmasks, &t->cells[z])) return rc;
+			if (int rc = cpvs_shadow_create_async((z & 1u) ? w->ctx2 : ctx, t->mm, z, w->desc.length, w->desc.leafmasks, &t->cells[z])) return rc;
+		for (u32 z = 0; z < w->desc.length; ++z)
+			if (int rc = cpvs_shadow_wait(t->cells[z])) return rc;
+		CPVS_CUDA(cudaEventRecord(w->evJoin, w->ctx2->stream));
+		CPVS_CUDA(cudaStreamWaitEvent(ctx->stream, w->evJoin, 0));
+		CPVS_CUDA(cudaEventRecord(w->ev1, ctx->stream));
+		CPVS_CUDA(cudaEventSynchronize(w->ev1));
+		float ms = 0.f;
+		CPVS_CUDA(cudaEventElapsedTime(&ms, w->ev0, w->ev1));
+		w->deviceMs += ms;
 		releaseInputs(w, *t);
 		t->built = true;
 		++w->built;
@@ -244,6 +299,7 @@ int cpvs_grid_worker_cells(const cpvs_grid_worker* w, cpvs_grid_cell* out, int c
 }
 
 float cpvs_grid_worker_device_ms(const cpvs_grid_worker* w) { return w ? w->deviceMs : 0.f; }
+float cpvs_grid_worker_depth_ms(const cpvs_grid_worker* w) { return w ? w->depthMs : 0.f; }
 
 // One process per GPU: the finished cells are packed into one block of plain device memory (stream-ordered pool memory
 // cannot be shared) whose CUDA IPC handle another process opens with cpvs_ipc_open; offsets[i] = first word of the i-th cell
@@ -404,7 +460,7 @@ int cpvs_grid_build(const int* devices, int numDevices, const cpvs_grid_desc* de
 		}
 	cpvs_grid_stats& st = g->stats;
 	st.devices = (uint32_t)numDevices;
-	const bool costAware = numDevices > 1 && numTiles <= 4 * numDevices;
+	const bool costAware = numDevices > 1 && (desc->scene >= 0 || numTiles <= 16 * numDevices);  // (tiles from a callback stay resident once estimated: 2 GB each at 16K^2)
 	if (costAware) {
 		std::vector<uint64_t> cost(numTiles, 0);
 		int rc = runOnWorkers(workers, [&](int i, cpvs_grid_worker* w) {
@@ -455,7 +511,8 @@ int cpvs_grid_build(const int* devices, int numDevices, const cpvs_grid_desc* de
 		st.tiles[d] = workers[d]->built;
 		st.build_ms[d] = workers[d]->deviceMs;
 		st.build_ms_max = std::max(st.build_ms_max, workers[d]->deviceMs);
-		st.launches += cpvs_ctx_launch_count(workers[d]->ctx);
+		st.launches += cpvs_ctx_launch_count(workers[d]->ctx) + cpvs_ctx_launch_count(workers[d]->ctx2);
+		st.depth_ms[d] = workers[d]->depthMs;
 		for (int i = 0; i < n; ++i) {
 			const cpvs_grid_cell& c = cells[i];
 			parts[c.index] = cpvs_cell_part{c.words, c.root_mask, c.device, c.words_device};

@@ -9,6 +9,7 @@
 #include <initializer_list>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "kernels.h"
@@ -81,6 +82,13 @@ struct cpvs_ctx {
 	// Sides of the depth maps whose last build did NOT use the per-column leaf builder (cities, planes): hierarchies of
 	// that side skip the column residues, which only that builder reads.
 	std::vector<int> noColumnSides;
+	// Large per-build buffers (pyramid levels, residues, device copies of host depth maps, DAG allocations) are recycled inside
+	// the context: a build of a shape seen before then allocates nothing, whatever the driver's pool would have to do to serve
+	// several contexts and peers (with a communication library's peer mappings a fresh block costs milliseconds).
+	std::mutex cacheLock;
+	std::vector<std::pair<void*, size_t>> freeBlocks;  // oldest first
+	std::unordered_map<void*, size_t> liveBlocks;
+	size_t cachedBytes;
 	cpvs::u64 buildSerial;  // builds enqueued so far: a pending build whose serial is the latest still owns the arena's contents
 };
 
@@ -171,6 +179,9 @@ struct cpvs_container {
 };
 
 namespace cpvs {
+// capi.cu: stream-ordered blocks on the context's stream, recycled by size (see cpvs_ctx::freeBlocks).
+cudaError_t ctxAlloc(cpvs_ctx* ctx, void** out, size_t bytes);
+void ctxFree(cpvs_ctx* ctx, void* p);
 // capi.cu: levels 1 and 2 of a hierarchy on demand.
 int ensureLowLevels(const cpvs_minmax* mm, int level);
 // build.cu: a new shadow handle around `words` device words (NULL: allocate one word and store `rootMask` there).

@@ -32,7 +32,8 @@ class CellPart(ctypes.Structure):
 class GridStats(ctypes.Structure):
     _fields_ = [("devices", ctypes.c_uint32), ("cells", ctypes.c_uint32), ("one_word_cells", ctypes.c_uint32), ("moved_tiles", ctypes.c_uint32),
                 ("dag_words", ctypes.c_uint64), ("svo_nodes", ctypes.c_uint64), ("dag_nodes", ctypes.c_uint64), ("launches", ctypes.c_uint64),
-                ("build_ms_max", ctypes.c_float), ("build_ms", ctypes.c_float * MAX_DEVICES), ("tiles", ctypes.c_uint32 * MAX_DEVICES),
+                ("build_ms_max", ctypes.c_float), ("build_ms", ctypes.c_float * MAX_DEVICES), ("depth_ms", ctypes.c_float * MAX_DEVICES),
+                ("tiles", ctypes.c_uint32 * MAX_DEVICES),
                 ("build_wall_ms", ctypes.c_float), ("gather_ms", ctypes.c_float), ("replicate_ms", ctypes.c_float), ("wall_ms", ctypes.c_float)]
 
 
@@ -94,8 +95,9 @@ class Grid:
     def stats(self):
         st = GridStats()
         _check(self._lib.cpvs_grid_stats_get(self.handle, ctypes.byref(st)))
-        out = {name: getattr(st, name) for name, _ in GridStats._fields_ if name not in ("build_ms", "tiles")}
+        out = {name: getattr(st, name) for name, _ in GridStats._fields_ if name not in ("build_ms", "tiles", "depth_ms")}
         out["build_ms"] = [float(v) for v in st.build_ms[:st.devices]]
+        out["depth_ms"] = [float(v) for v in st.depth_ms[:st.devices]]
         out["tiles"] = [int(v) for v in st.tiles[:st.devices]]
         return out
 
@@ -164,6 +166,9 @@ class GridWorker:
 
     def device_ms(self):
         return float(self._lib.cpvs_grid_worker_device_ms(self.handle))
+
+    def depth_ms(self):
+        return float(self._lib.cpvs_grid_worker_depth_ms(self.handle))
 
     def export(self):
         """(64-byte CUDA IPC handle of a block holding all finished cells, first word of every cell in ``cells()`` order)."""

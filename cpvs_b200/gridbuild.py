@@ -69,7 +69,7 @@ def run(ctx, tile, length, kind, rank=0, world=1, group=None, lookups=3840 * 216
     wall0 = time.perf_counter()
 
     # 1. ownership
-    cost_aware = world > 1 and len(tiles) <= 4 * world
+    cost_aware = world > 1 and (fetch is None or len(tiles) <= 16 * world)  # (caller-provided tiles stay resident once estimated)
     owners, moved = start, 0
     if cost_aware:
         costs_mine = dict(zip(mine0, worker.estimate(mine0)))
@@ -85,6 +85,7 @@ def run(ctx, tile, length, kind, rank=0, world=1, group=None, lookups=3840 * 216
     # 2. build
     worker.build(mine)
     build_ms = worker.device_ms()
+    depth_ms = worker.depth_ms()
     wall_ms = (time.perf_counter() - wall0) * 1e3
     launches = ctx.launch_count - launches0
     if log:
@@ -94,7 +95,7 @@ def run(ctx, tile, length, kind, rank=0, world=1, group=None, lookups=3840 * 216
     t0 = time.perf_counter()
     cells = worker.cells()
     handle, offsets = worker.export() if (world > 1 and replicate) else (None, [0] * len(cells))
-    mine_info = {"rank": rank, "device": ctx.device, "handle": handle, "build_ms": build_ms, "wall_ms": wall_ms, "launches": launches,
+    mine_info = {"rank": rank, "device": ctx.device, "handle": handle, "build_ms": build_ms, "depth_ms": depth_ms, "wall_ms": wall_ms, "launches": launches,
                  "tiles": len(mine),
                  "cells": [(c.index, int(c.words), int(c.root_mask), int(c.num_levels), int(off), int(c.svo_nodes), int(c.dag_nodes))
                            for c, off in zip(cells, offsets)]}
@@ -114,6 +115,7 @@ def run(ctx, tile, length, kind, rank=0, world=1, group=None, lookups=3840 * 216
     cont = None
     if replicate:
         local = {c.index: c for c in cells}
+        t_open = time.perf_counter()
         for info in everyone:
             if info["rank"] != rank and info["handle"] is not None and info["cells"]:
                 opened[info["rank"]] = (cgrid.ipc_open(info["handle"], ctx.device), info["device"])
@@ -126,8 +128,11 @@ def run(ctx, tile, length, kind, rank=0, world=1, group=None, lookups=3840 * 216
             else:
                 base, dev = opened[owner]
                 parts.append((words, mask, dev, base + 4 * off))
+        ipc_open_ms = (time.perf_counter() - t_open) * 1e3
         cont = cgrid.assemble(ctx, length, ordered[0][2], leafmasks, parts)
         ctx.synchronize()
+        if log:
+            log("rank %d: ipc open %.1f ms, assemble (peer copies + lookup copy) %.1f ms" % (rank, ipc_open_ms, (time.perf_counter() - t_open) * 1e3 - ipc_open_ms))
         for (ptr, _dev) in opened.values():
             cgrid.ipc_close(ctx.device, ptr)
         _barrier(group, world)  # nobody frees its exported block while a peer still copies from it
@@ -139,6 +144,8 @@ def run(ctx, tile, length, kind, rank=0, world=1, group=None, lookups=3840 * 216
         "xy_tiles": length * length, "cells": length ** 3, "one_word_cells": sum(1 for c in ordered if c[0] == 1), "samples": res * res,
         "ownership": "cost-aware (closed-form node counts, longest first)" if cost_aware else "rotated round-robin", "moved_tiles": moved,
         "build_ms_max_rank": max(i["build_ms"] for i in everyone), "build_ms_per_rank": [i["build_ms"] for i in everyone],
+        "depth_ms_per_rank": [i["depth_ms"] for i in everyone], "timing": "device time from depth tiles resident in device memory (SURVEY.md 8d); "
+                                                                          "producing them is clocked separately (depth_ms_per_rank)",
         "tiles_per_rank": [i["tiles"] for i in everyone], "wall_ms_max_rank": max(i["wall_ms"] for i in everyone),
         "gather_sizes_ms": gather_ms, "replicate_and_finalize_ms": assemble_ms,
         "dag_words": int(total_words), "dag_mbytes": 4.0 * total_words / 1e6,

@@ -117,7 +117,7 @@ CPVS_API int cpvs_minmax_build(cpvs_ctx* ctx, const float* depth, int n, int mem
 /* The same for a hierarchy whose builds will be cut into z_tile_num z-slices (createShadowTiles,
  * src/DeferredRenderer.cpp:150-163): the construction pass also leaves the depth map re-encoded for the per-column leaf
  * builder of exactly that slicing (1 byte per texel). Purely a speed hint: cpvs_shadow_create accepts any z_tile_num on
- * any hierarchy and falls back to reading the depth map. cpvs_minmax_build is z_tile_num = 1. */
+ * any hierarchy and falls back to reading the depth map. cpvs_minmax_build is z_tile_num = 1; 0 prepares nothing. */
 CPVS_API int cpvs_minmax_build_tiled(cpvs_ctx* ctx, const float* depth, int n, int mem, uint32_t z_tile_num, cpvs_minmax** out);
 CPVS_API int cpvs_minmax_destroy(cpvs_minmax* mm);
 /* getNumLevels() (src/MinMaxHierarchy.h:60-62): log2(n) + 1. */
@@ -281,8 +281,10 @@ typedef struct cpvs_grid_cell {
 typedef struct cpvs_grid_worker cpvs_grid_worker;
 CPVS_API int cpvs_grid_worker_create(cpvs_ctx* ctx, const cpvs_grid_desc* desc, cpvs_grid_worker** out);
 CPVS_API int cpvs_grid_worker_destroy(cpvs_grid_worker* w);
-/* Cost of `count` xy tiles (pairs x, y): the SVO nodes of all their cells, from the closed-form count over the tile's
- * hierarchy. Depth tile and hierarchy stay resident for cpvs_grid_worker_build; _release drops tiles given to another worker. */
+/* Cost of `count` xy tiles (pairs x, y) for the ownership: the SVO nodes of all their cells from the closed-form count --
+ * over a hierarchy of the tile resampled at an eighth of its resolution when the scene is generated on the device (nothing
+ * stays resident), else over the tile's own hierarchy, which then stays resident for cpvs_grid_worker_build (_release
+ * drops tiles given to another worker). */
 CPVS_API int cpvs_grid_worker_estimate(cpvs_grid_worker* w, const uint32_t* xy, int count, uint64_t* cost_out);
 CPVS_API int cpvs_grid_worker_release(cpvs_grid_worker* w, const uint32_t* xy, int count);
 /* createShadowTiles (src/DeferredRenderer.cpp:150-163) for `count` xy tiles: hierarchy + one DAG per z-slice, kept on the GPU. */
@@ -290,8 +292,10 @@ CPVS_API int cpvs_grid_worker_build(cpvs_grid_worker* w, const uint32_t* xy, int
 CPVS_API int cpvs_grid_worker_num_cells(const cpvs_grid_worker* w);
 /* The finished cells (returns their number, < 0 on error). */
 CPVS_API int cpvs_grid_worker_cells(const cpvs_grid_worker* w, cpvs_grid_cell* out, int capacity);
-/* Device time (CUDA events on the worker's stream) of everything _estimate and _build enqueued so far. */
+/* Device time (CUDA events on the worker's stream) of everything _estimate and _build did so far, from depth tiles resident
+ * in device memory; producing the depth tiles (generator or callback + copy) is clocked separately. */
 CPVS_API float cpvs_grid_worker_device_ms(const cpvs_grid_worker* w);
+CPVS_API float cpvs_grid_worker_depth_ms(const cpvs_grid_worker* w);
 /* One process per GPU: packs the finished cells into one block of plain device memory and returns its CUDA IPC handle
  * (64 bytes) plus, per cell in the order of cpvs_grid_worker_cells, the first word inside the block (returns the number of
  * cells, < 0 on error). Another process maps the block with cpvs_ipc_open (on its own device: the words are then fetched
@@ -307,8 +311,9 @@ CPVS_API int cpvs_grid_assign(const uint64_t* cost, int num_tiles, int num_worke
 typedef struct cpvs_grid_stats {
 	uint32_t devices, cells, one_word_cells, moved_tiles;
 	uint64_t dag_words, svo_nodes, dag_nodes, launches;
-	float build_ms_max;                       /* device time of the slowest GPU (estimates + builds) */
+	float build_ms_max;                       /* device time of the slowest GPU (estimates + builds, from resident depth tiles) */
 	float build_ms[CPVS_GRID_MAX_DEVICES];    /* per GPU */
+	float depth_ms[CPVS_GRID_MAX_DEVICES];    /* per GPU: producing the depth tiles (not part of the build metric) */
 	uint32_t tiles[CPVS_GRID_MAX_DEVICES];    /* xy tiles built per GPU */
 	float build_wall_ms, gather_ms, replicate_ms, wall_ms; /* host clock: builds on all GPUs; gather of sizes; replication; all */
 } cpvs_grid_stats;

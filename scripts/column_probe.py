@@ -1,39 +1,53 @@
-"""Where the time of one tile column goes (a 16K^2 city tile of the 256K^2 map, 16 z-slices): per slice the
-device time between the first and last event of the build, the host wall time of the call, and the phases."""
+"""Dev probe (no torch): the z-slices of one tile of a tile grid -- per-slice device time and phases, repeated so that the
+later rounds run on warm memos.   python scripts/column_probe.py [kind] [length] [tile x] [tile y] [size]"""
 import os
 import sys
 import time
 
-import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import cpvs_b200  # noqa: E402
+from cpvs_b200 import synth  # noqa: E402
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-
-import cpvs_b200
-
-n, length = 16384, 16
-tile = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (5, 5)
-stream = torch.cuda.Stream()
-torch.cuda.set_stream(stream)
-ctx = cpvs_b200.Context(0, stream=stream.cuda_stream)
-depth = torch.empty((n, n), dtype=torch.float32, device="cuda")
-cpvs_b200.generate_depth("city", n, depth, tile, length, ctx)
+kind = sys.argv[1] if len(sys.argv) > 1 else "terrain_dev"
+length = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+tx, ty = (int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else (1, 2)
+n = int(sys.argv[5]) if len(sys.argv) > 5 else 16384
+lib = cpvs_b200.load_library()
+ctx = cpvs_b200.Context(0)
+mm0 = cpvs_b200.MinMaxHierarchy(synth.depth_map(kind, n, (tx, ty), length), ctx)
 ctx.synchronize()
-for rep in range(3):
+dptr = int(lib.cpvs_minmax_level_device(mm0.handle, 0))
+for rep in range(4):
     t0 = time.perf_counter()
-    mm = cpvs_b200.MinMaxHierarchy(depth, ctx, n=n)
-    ctx.synchronize()
-    t_mm = (time.perf_counter() - t0) * 1e3
+    mm = cpvs_b200.MinMaxHierarchy(dptr, ctx, n=n, zTileNum=length)
     rows = []
     for z in range(length):
-        t0 = time.perf_counter()
         sh = cpvs_b200.CompressedShadow.create(mm, z, length)
-        wall = (time.perf_counter() - t0) * 1e3
-        rows.append((z, int(sh.info.words), int(sum(sh.info.svo_nodes)), float(sh.info.build_ms), wall, sh.phase_ms()))
+        rows.append((z, int(sh.info.words), sh.info.build_ms, {k: round(v, 3) for k, v in sh.phase_ms().items() if v > 0.004}))
+        sh.close()
+    ctx.synchronize()
+    wall = (time.perf_counter() - t0) * 1e3
+    print("round %d: wall %.3f ms, pyramid %.3f, slices %.3f" % (rep, wall, mm.timing()[0], sum(r[2] for r in rows)))
+    if rep == 3:
+        for r in rows:
+            print("   z=%d words=%d build=%.3f %s" % r)
+    mm.close()
+
+# the same slices alternating between two contexts, all in flight (what the grid worker does)
+ctx2 = cpvs_b200.Context(0)
+for rep in range(4):
+    t0 = time.perf_counter()
+    mm = cpvs_b200.MinMaxHierarchy(dptr, ctx, n=n, zTileNum=length)
+    shs = [cpvs_b200.CompressedShadow.create(mm, z, length, ctx=(ctx2 if z & 1 else ctx), wait=False) for z in range(length)]
+    t1 = time.perf_counter()
+    for sh in shs:
+        sh.wait()
+    ctx.synchronize()
+    ctx2.synchronize()
+    wall = (time.perf_counter() - t0) * 1e3
+    print("two contexts, round %d: wall %.3f ms (enqueue %.3f ms), sum of builds %.3f, stats %s %s" % (
+        rep, wall, (t1 - t0) * 1e3, sum(sh.info.build_ms for sh in shs), ctx.stats(), ctx2.stats()))
+    for sh in shs:
         sh.close()
     mm.close()
-    if rep == 2:
-        print("pyramid wall %.3f ms" % t_mm)
-        for z, words, nodes, dev_ms, wall, ph in rows:
-            print("z=%2d words=%8d svo_nodes=%9d device %.3f ms wall %.3f ms %s" % (
-                z, words, nodes, dev_ms, wall, {k: round(v, 3) for k, v in ph.items() if v > 0.0005} if words > 1 else ""))
-        print("column: device %.3f ms, wall %.3f ms" % (sum(r[3] for r in rows), sum(r[4] for r in rows)))
