@@ -547,8 +547,17 @@ def run_own(args):
     if not args.no_grids:
         for name in ("64k", "256k"):
             cfg_index, length, kind = GRIDS[name]
-            g = gridbuild.run(ctx, args.grid_tile, length, kind, rank, world, gloo, lookups=3840 * 2160, lookup_iters=4, verify=True)
-            grids["configs%d" % cfg_index] = grid_line(g, cfg_index)
+            # the 64K^2 grid is a few milliseconds of work per GPU at N = 8: three repetitions, the median is reported and all
+            # three are listed (one descheduled host thread is a fifth of such a build)
+            reps = [gridbuild.run(ctx, args.grid_tile, length, kind, rank, world, gloo, lookups=3840 * 2160, lookup_iters=4, verify=(r == 0),
+                                  replicate=(r == 0)) for r in range(3 if name == "64k" else 1)]
+            by_time = sorted(reps, key=lambda g: g["build_ms_max_rank"])
+            g = dict(reps[0])
+            for key in ("build_ms_max_rank", "build_ms_per_rank", "depth_ms_per_rank", "tiles_per_rank", "wall_ms_max_rank", "build_msamples_per_s", "moved_tiles"):
+                g[key] = by_time[len(by_time) // 2][key]
+            entry = grid_line(g, cfg_index)
+            entry["repetitions_build_ms_max_rank"] = [r["build_ms_max_rank"] for r in reps]
+            grids["configs%d" % cfg_index] = entry
             barrier()
 
     if rank == 0:

@@ -103,6 +103,7 @@ SIGNATURES = {
     "cpvs_grid_worker_device_ms": (ctypes.c_float, [_VP]),
     "cpvs_grid_worker_depth_ms": (ctypes.c_float, [_VP]),
     "cpvs_grid_worker_export": (_I, [_VP, _VP, _VP, _I]),
+    "cpvs_grid_worker_copy_cells": (_I, [_VP, _VP, _U64, _VP, _I]),
     "cpvs_ipc_open": (_I, [_VP, _I, _PP]),
     "cpvs_ipc_close": (_I, [_I, _VP]),
     "cpvs_grid_assign": (_I, [_VP, _I, _I, _VP, _VP]),

@@ -62,6 +62,17 @@ void ctxFree(cpvs_ctx* ctx, void* p) {
 	}
 }
 
+cpvs_ctx* siblingContext(cpvs_ctx* ctx) {
+	std::lock_guard<std::mutex> guard(ctx->cacheLock);
+	if (!ctx->sibling) {
+		if (cpvs_ctx_create(ctx->device, &ctx->sibling) != CPVS_OK) return nullptr;
+		ctx->sibling->predictSizes = ctx->predictSizes;
+		ctx->sibling->headroomShift = ctx->headroomShift;
+		ctx->sibling->leafColumns = ctx->leafColumns;
+	}
+	return ctx->sibling;
+}
+
 int fail(int code, const char* fmt, ...) {
 	char buf[512];
 	va_list ap;
@@ -123,6 +134,7 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 	ctx->scalars = nullptr;
 	ctx->own = ctx->aux = ctx->aux2 = ctx->aux3 = ctx->aux4 = nullptr;
 	ctx->cachedBytes = 0;
+	ctx->sibling = nullptr;
 	ctx->predictedBuilds = ctx->exactBuilds = ctx->overflowRebuilds = ctx->reemissions = 0;
 	cudaEvent_t* plain[] = {&ctx->evFork, &ctx->evJoin, &ctx->evJoin3, &ctx->evClear, &ctx->evCols, &ctx->evLeafRanked, &ctx->evLeafEmitted};
 	for (cudaEvent_t* e : plain) *e = nullptr;
@@ -165,6 +177,8 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 
 int cpvs_ctx_destroy(cpvs_ctx* ctx) {
 	if (!ctx) return CPVS_OK;
+	if (ctx->sibling) cpvs_ctx_destroy(ctx->sibling);
+	ctx->sibling = nullptr;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	if (ctx->arena) cudaFreeAsync(ctx->arena, ctx->stream);
@@ -208,7 +222,7 @@ int cpvs_ctx_reserve(cpvs_ctx* ctx, uint64_t bytes) {
 	return CPVS_OK;
 }
 
-uint64_t cpvs_ctx_launch_count(const cpvs_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t cpvs_ctx_launch_count(const cpvs_ctx* ctx) { return ctx ? ctx->launches + (ctx->sibling ? ctx->sibling->launches : 0) : 0; }
 
 int cpvs_ctx_set_prediction(cpvs_ctx* ctx, int enabled, uint32_t headroomShift) {
 	if (!ctx) return fail(CPVS_EINVAL, "cpvs_ctx_set_prediction: NULL context");

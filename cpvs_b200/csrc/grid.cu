@@ -127,11 +127,11 @@ int cpvs_grid_worker_create(cpvs_ctx* ctx, const cpvs_grid_desc* desc, cpvs_grid
 		cpvs_grid_worker_destroy(w);
 		return fail(CPVS_ECUDA, "cpvs_grid_worker_create: events");
 	}
-	if (int rc = cpvs_ctx_create(ctx->device, &w->ctx2)) {
+	w->ctx2 = siblingContext(ctx);  // kept by the context: warm for the next worker
+	if (!w->ctx2) {
 		cpvs_grid_worker_destroy(w);
-		return rc;
+		return fail(CPVS_ECUDA, "cpvs_grid_worker_create: second context: %s", cpvs_last_error());
 	}
-	cpvs_ctx_set_prediction(w->ctx2, ctx->predictSizes, ctx->headroomShift);
 	*out = w;
 	return CPVS_OK;
 }
@@ -146,7 +146,6 @@ int cpvs_grid_worker_destroy(cpvs_grid_worker* w) {
 	if (w->hostStage) cudaFreeHost(w->hostStage);
 	if (w->exported) cudaFree(w->exported);
 	if (w->evJoin) cudaEventDestroy(w->evJoin);
-	if (w->ctx2) cpvs_ctx_destroy(w->ctx2);
 	if (w->ev0) cudaEventDestroy(w->ev0);
 	if (w->ev1) cudaEventDestroy(w->ev1);
 	delete w;
@@ -332,6 +331,32 @@ int cpvs_grid_worker_export(cpvs_grid_worker* w, unsigned char handle[64], uint6
 	return n;
 }
 
+// The finished cells copied to host memory, one after the other (offsets[i] = first word of the i-th cell of
+// cpvs_grid_worker_cells): the exchange medium of callers that run one process per GPU and share a host (a file in shared
+// memory), where mapping eight processes' device memory into each other costs seconds of peer-access set-up.
+int cpvs_grid_worker_copy_cells(const cpvs_grid_worker* w, uint32_t* outHost, uint64_t capacityWords, uint64_t* offsets, int capacity) {
+	if (!w || !offsets || (capacityWords && !outHost)) return fail(CPVS_EINVAL, "cpvs_grid_worker_copy_cells: NULL argument");
+	CPVS_CUDA(cudaSetDevice(w->ctx->device));
+	u64 total = 0;
+	int n = 0;
+	for (const WorkerTile& t : w->tiles)
+		if (t.built)
+			for (const cpvs_shadow* s : t.cells) {
+				if (n >= capacity) return fail(CPVS_EINVAL, "cpvs_grid_worker_copy_cells: capacity %d", capacity);
+				offsets[n++] = total;
+				total += s->info.words;
+			}
+	if (!outHost) return n;  // sizes only
+	if (total > capacityWords) return fail(CPVS_EINVAL, "cpvs_grid_worker_copy_cells: %llu words, room for %llu", (unsigned long long)total, (unsigned long long)capacityWords);
+	n = 0;
+	for (const WorkerTile& t : w->tiles)
+		if (t.built)
+			for (const cpvs_shadow* s : t.cells)
+				CPVS_CUDA(cudaMemcpyAsync(outHost + offsets[n++], s->dag, s->info.words * sizeof(u32), cudaMemcpyDeviceToHost, w->ctx->stream));
+	CPVS_CUDA(cudaStreamSynchronize(w->ctx->stream));
+	return n;
+}
+
 int cpvs_ipc_open(const unsigned char handle[64], int device, void** out) {
 	if (!handle || !out) return fail(CPVS_EINVAL, "cpvs_ipc_open: NULL argument");
 	cudaIpcMemHandle_t h;
@@ -435,6 +460,10 @@ int cpvs_grid_build(const int* devices, int numDevices, const cpvs_grid_desc* de
 		cpvs_grid_worker* w = nullptr;
 		if (int rc = cpvs_grid_worker_create(ctx, desc, &w)) return cleanup(rc);
 		workers.push_back(w);
+		// the kept DAGs and the scratch arenas come out of memory the pool already owns (see cpvs_ctx_reserve)
+		const double scale = ((double)desc->tile / 16384.0) * ((double)desc->tile / 16384.0);
+		const double share = (double)desc->length * desc->length / numDevices;
+		cpvs_ctx_reserve(ctx, (uint64_t)(std::min(share * 320e6 * scale, 8.0 * 1073741824.0) + 6e9 * scale));
 	}
 	// peer access for the replication (best effort: cudaMemcpyPeerAsync stages through the host without it)
 	for (int a = 0; a < numDevices; ++a)
@@ -460,42 +489,42 @@ int cpvs_grid_build(const int* devices, int numDevices, const cpvs_grid_desc* de
 		}
 	cpvs_grid_stats& st = g->stats;
 	st.devices = (uint32_t)numDevices;
-	const bool costAware = numDevices > 1 && (desc->scene >= 0 || numTiles <= 16 * numDevices);  // (tiles from a callback stay resident once estimated: 2 GB each at 16K^2)
+	// Few tiles per GPU: the tiles are first costed (each worker a round-robin share) and then handed out longest first -- but
+	// still from a shared queue, so that a worker whose tile turned out heavier than estimated simply comes back later and
+	// finds the lighter ones. Many tiles per GPU: the queue alone, in the reference's loop order.
+	const bool costAware = numDevices > 1 && numTiles <= 4 * numDevices;
+	std::vector<int> order(numTiles);
+	for (int t = 0; t < numTiles; ++t) order[t] = t;
 	if (costAware) {
 		std::vector<uint64_t> cost(numTiles, 0);
-		int rc = runOnWorkers(workers, [&](int i, cpvs_grid_worker* w) {
+		const int rc = runOnWorkers(workers, [&](int i, cpvs_grid_worker* w) {
 			for (int t = 0; t < numTiles; ++t)
 				if (owner[t] == i)
 					if (int e = cpvs_grid_worker_estimate(w, &xy[2 * t], 1, &cost[t])) return e;
 			return (int)CPVS_OK;
 		});
 		if (rc) return cleanup(rc);
-		std::vector<int> assigned(numTiles);
-		if (int e = cpvs_grid_assign(cost.data(), numTiles, numDevices, owner.data(), assigned.data())) return cleanup(e);
-		for (int t = 0; t < numTiles; ++t)
-			if (assigned[t] != owner[t]) {
-				++st.moved_tiles;
-				cpvs_grid_worker_release(workers[owner[t]], &xy[2 * t], 1);
-			}
-		owner = assigned;
-		rc = runOnWorkers(workers, [&](int i, cpvs_grid_worker* w) {
-			for (int t = 0; t < numTiles; ++t)
-				if (owner[t] == i)
-					if (int e = cpvs_grid_worker_build(w, &xy[2 * t], 1)) return e;
-			return (int)CPVS_OK;
-		});
-		if (rc) return cleanup(rc);
-	} else {
+		std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+	}
+	{
+		const std::vector<int> startOwner = owner;
 		std::atomic<int> next(0);
 		const int rc = runOnWorkers(workers, [&](int i, cpvs_grid_worker* w) {
 			for (;;) {
-				const int t = next.fetch_add(1);
-				if (t >= numTiles) return (int)CPVS_OK;
+				const int k = next.fetch_add(1);
+				if (k >= numTiles) return (int)CPVS_OK;
+				const int t = order[k];
 				owner[t] = i;
 				if (int e = cpvs_grid_worker_build(w, &xy[2 * t], 1)) return e;
 			}
 		});
 		if (rc) return cleanup(rc);
+		for (int t = 0; t < numTiles; ++t) {
+			if (owner[t] != startOwner[t]) {
+				++st.moved_tiles;
+				cpvs_grid_worker_release(workers[startOwner[t]], &xy[2 * t], 1);
+			}
+		}
 	}
 	st.build_wall_ms = (float)(nowMs() - wall0);
 
@@ -511,7 +540,7 @@ int cpvs_grid_build(const int* devices, int numDevices, const cpvs_grid_desc* de
 		st.tiles[d] = workers[d]->built;
 		st.build_ms[d] = workers[d]->deviceMs;
 		st.build_ms_max = std::max(st.build_ms_max, workers[d]->deviceMs);
-		st.launches += cpvs_ctx_launch_count(workers[d]->ctx) + cpvs_ctx_launch_count(workers[d]->ctx2);
+		st.launches += cpvs_ctx_launch_count(workers[d]->ctx);
 		st.depth_ms[d] = workers[d]->depthMs;
 		for (int i = 0; i < n; ++i) {
 			const cpvs_grid_cell& c = cells[i];

@@ -89,6 +89,9 @@ struct cpvs_ctx {
 	std::vector<std::pair<void*, size_t>> freeBlocks;  // oldest first
 	std::unordered_map<void*, size_t> liveBlocks;
 	size_t cachedBytes;
+	// A second context on the same GPU, created on demand and kept (cpvs::siblingContext): independent builds -- the z-slices
+	// of a tile -- alternate between the two so that their kernels run side by side.
+	cpvs_ctx* sibling;
 	cpvs::u64 buildSerial;  // builds enqueued so far: a pending build whose serial is the latest still owns the arena's contents
 };
 
@@ -182,6 +185,7 @@ namespace cpvs {
 // capi.cu: stream-ordered blocks on the context's stream, recycled by size (see cpvs_ctx::freeBlocks).
 cudaError_t ctxAlloc(cpvs_ctx* ctx, void** out, size_t bytes);
 void ctxFree(cpvs_ctx* ctx, void* p);
+cpvs_ctx* siblingContext(cpvs_ctx* ctx);  // NULL if it cannot be created
 // capi.cu: levels 1 and 2 of a hierarchy on demand.
 int ensureLowLevels(const cpvs_minmax* mm, int level);
 // build.cu: a new shadow handle around `words` device words (NULL: allocate one word and store `rootMask` there).

@@ -289,9 +289,9 @@ int buildLookupIndex(cpvs_ctx* ctx, const u32* dag, u64 dagWords, const std::vec
 	DeviceBuffer<u64> dCellStart(st), nodes(st);
 	DeviceBuffer<u32> nodeBits(st), leafBits(st), nodePrefix(st), leafPrefix(st), tileSum(st), counters(st);
 	const u32 tiles = (u32)((bitWords + kIndexTile - 1) / kIndexTile);
-	// a node with children is at least two words, the nodes above the leaves about five, a leaf more: a quarter of the words bounds
-	// the number of inner nodes in practice (a DAG that breaks the bound gets no index)
-	const u32 capacity = (u32)std::min<u64>(dagWords / 4 + roots.size() + 1024, 0xFFFFFFF0ull);
+	// the nodes above the leaves take about five words each and point to leaves of ten and more: an eighth of the words bounds the
+	// number of inner nodes in practice (a DAG that breaks the bound gets no index)
+	const u32 capacity = (u32)std::min<u64>(dagWords / 8 + roots.size() + 4096, 0xFFFFFFF0ull);
 	cudaError_t e = dCellStart.alloc(numCells);
 	if (e == cudaSuccess) e = nodes.alloc(capacity);
 	if (e == cudaSuccess) e = nodeBits.alloc(bitWords);

@@ -180,6 +180,18 @@ class GridWorker:
             _check(EINVAL)
         return bytes(handle), [int(o) for o in offsets[:got]]
 
+    def copy_cells(self, out=None):
+        """All finished cells copied into the uint32 numpy array ``out`` (host; None: sizes only).
+        Returns (first word of every cell in ``cells()`` order, total words)."""
+        n = self._lib.cpvs_grid_worker_num_cells(self.handle)
+        offsets = (ctypes.c_uint64 * max(1, n))()
+        ptr, cap = (out.ctypes.data, out.size) if out is not None else (None, 0)
+        got = self._lib.cpvs_grid_worker_copy_cells(self.handle, ptr, cap, offsets, max(1, n))
+        if got < 0:
+            _check(EINVAL)
+        offs = [int(o) for o in offsets[:got]]
+        return offs
+
     def close(self):
         if getattr(self, "handle", None):
             self._lib.cpvs_grid_worker_destroy(self.handle)

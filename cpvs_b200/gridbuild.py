@@ -7,18 +7,20 @@ MinMaxHierarchy and ``length`` z-slice DAGs from it, drop them into the cubic co
 by the C++ grid worker of the CUDA library (``cpvs_grid_worker_*``, csrc/grid.cu) -- the same one ``cpvs_grid_build`` runs on
 one host thread per GPU inside a single process; here every rank drives the worker of its own GPU:
 
-  1. cost of the xy tiles (closed-form node counts over each tile's hierarchy) for a rotated round-robin share; the few
-     integers are gathered on the host (gloo) and every rank runs the same longest-first assignment (``cpvs_grid_assign``).
-     With many tiles per GPU the round-robin share is kept as it is.
-  2. every rank builds the tiles it owns: depth tile generated on its GPU (or handed over by the caller), hierarchy, cells.
+  1. ownership. Few tiles per GPU: cost of the xy tiles (closed-form node counts over each tile resampled at 1/8 resolution)
+     for a rotated round-robin share, gathered on the host (gloo), then assigned longest first (``cpvs_grid_assign``). Many
+     tiles per GPU: every rank pulls its next tile from a shared counter on the rendezvous store.
+  2. every rank builds its tiles: depth tile generated on its GPU (or handed over by the caller), hierarchy, cells.
   3. host-side gather (gloo) of (words, root mask) per cell -- the only thing that crosses ranks for the build --, the
      exclusive scan of ``createTopLevelGrid`` (reference ``src/CompressedShadowContainer.cpp:71-91``) on the host.
-  4. for lookups every rank maps the other ranks' finished words through CUDA IPC and copies them peer to peer into its own
-     container (``cpvs_container_assemble``); the query batch is split by rows.
+  4. for lookups every rank writes its finished words to a file in the host's shared memory, reads the others', and puts its
+     own container together (``cpvs_container_assemble``); the query batch is split by rows. (The single-process driver
+     ``cpvs_grid_build`` replicates with cudaMemcpyPeerAsync instead.)
 
 No NCCL: ``group`` is any torch.distributed group with a CPU (gloo) backend, or None for a single process. Timing is on the
 device (CUDA events on the worker's stream); the figure of a multi-rank run is the maximum over ranks. No CPU fallback.
 """
+import os
 import time
 
 import numpy as np
@@ -34,6 +36,9 @@ def _gather(group, obj, world):
     out = [None] * world
     dist.all_gather_object(out, obj, group=group)
     return out
+
+
+_QUEUE_RUNS = {}  # (every rank calls run() the same number of times: the counters' names agree)
 
 
 def _barrier(group, world):
@@ -68,22 +73,39 @@ def run(ctx, tile, length, kind, rank=0, world=1, group=None, lookups=3840 * 216
     launches0 = ctx.launch_count
     wall0 = time.perf_counter()
 
-    # 1. ownership
-    cost_aware = world > 1 and (fetch is None or len(tiles) <= 16 * world)  # (caller-provided tiles stay resident once estimated)
-    owners, moved = start, 0
+    # 1. ownership + 2. build. With many tiles per GPU every rank pulls its next tile from a shared counter (an atomic add on the
+    # rendezvous store -- a host-side integer, nothing on the data path), which evens out tiles of very different cost (the
+    # 256K^2 city: box edges) without knowing the costs. With few tiles per GPU the tiles are costed first (each rank a
+    # round-robin share, gathered on the host) and assigned longest first.
+    cost_aware = world > 1 and len(tiles) <= 4 * world
+    moved = 0
     if cost_aware:
+        # few tiles per GPU: ownership by cost, longest first, decided before anybody builds (no traffic on the store while
+        # the few milliseconds of builds run)
         costs_mine = dict(zip(mine0, worker.estimate(mine0)))
         costs = {}
         for part in _gather(group, costs_mine, world):
             costs.update(part)
         owners = cgrid.assign([costs[t] for t in tiles], world, start)
-        gone = [t for t, o, s in zip(tiles, owners, start) if s == rank and o != rank]
-        worker.release(gone)
-        moved = sum(1 for o, s in zip(owners, start) if o != s)
-    mine = [t for t, o in zip(tiles, owners) if o == rank]
-
-    # 2. build
-    worker.build(mine)
+        mine = [t for t, o in zip(tiles, owners) if o == rank]
+        worker.release([t for t in mine0 if t not in mine])
+        worker.build(mine)
+    elif world > 1:
+        import torch.distributed as dist
+        store = dist.distributed_c10d._get_default_store()
+        key = "cpvs_grid_queue_%d_%d_%s" % (length, tile, kind)
+        _QUEUE_RUNS[key] = _QUEUE_RUNS.get(key, 0) + 1
+        key += "_%d" % _QUEUE_RUNS[key]
+        mine = []
+        while True:
+            k = store.add(key, 1) - 1
+            if k >= len(tiles):
+                break
+            mine.append(tiles[k])
+            worker.build([tiles[k]])
+    else:
+        mine = list(tiles)
+        worker.build(mine)
     build_ms = worker.device_ms()
     depth_ms = worker.depth_ms()
     wall_ms = (time.perf_counter() - wall0) * 1e3
@@ -94,12 +116,14 @@ def run(ctx, tile, length, kind, rank=0, world=1, group=None, lookups=3840 * 216
     # 3. host-side gather of sizes
     t0 = time.perf_counter()
     cells = worker.cells()
-    handle, offsets = worker.export() if (world > 1 and replicate) else (None, [0] * len(cells))
-    mine_info = {"rank": rank, "device": ctx.device, "handle": handle, "build_ms": build_ms, "depth_ms": depth_ms, "wall_ms": wall_ms, "launches": launches,
-                 "tiles": len(mine),
+    offsets = worker.copy_cells(None)
+    my_words = (offsets[-1] + int(cells[-1].words)) if cells else 0
+    mine_info = {"rank": rank, "device": ctx.device, "build_ms": build_ms, "depth_ms": depth_ms, "wall_ms": wall_ms, "launches": launches,
+                 "tiles": len(mine), "words": my_words, "moved": sum(1 for t in mine if t not in mine0),
                  "cells": [(c.index, int(c.words), int(c.root_mask), int(c.num_levels), int(off), int(c.svo_nodes), int(c.dag_nodes))
                            for c, off in zip(cells, offsets)]}
     everyone = _gather(group, mine_info, world)
+    moved = sum(i["moved"] for i in everyone)
     table = {}
     for info in everyone:
         for (index, words, mask, levels, off, svo, dagn) in info["cells"]:
@@ -109,16 +133,28 @@ def run(ctx, tile, length, kind, rank=0, world=1, group=None, lookups=3840 * 216
     grid_host, total_words = tiling.top_level_grid([(w, m) for (w, m, *_rest) in ordered], length)
     gather_ms = (time.perf_counter() - t0) * 1e3
 
-    # 4. replication for the lookups (after the build, not on its data path): peer copies through CUDA IPC
+    # 4. replication for the lookups (after the build, not on its data path). One process per GPU: the finished words go
+    # through files in the host's shared memory -- every rank writes its cells once and reads the others' -- because mapping
+    # eight processes' device memory into each other (CUDA IPC + peer access) costs seconds of set-up per process.
     t0 = time.perf_counter()
-    opened = {}
     cont = None
     if replicate:
+        import torch
         local = {c.index: c for c in cells}
-        t_open = time.perf_counter()
-        for info in everyone:
-            if info["rank"] != rank and info["handle"] is not None and info["cells"]:
-                opened[info["rank"]] = (cgrid.ipc_open(info["handle"], ctx.device), info["device"])
+        staged = {}
+        if world > 1:
+            tag = "/dev/shm/cpvs_grid_%s_%d" % (os.environ.get("MASTER_PORT", "0"), _QUEUE_RUNS.get("shm", 0))
+            _QUEUE_RUNS["shm"] = _QUEUE_RUNS.get("shm", 0) + 1
+            mine_file = np.lib.format.open_memmap("%s_%d.npy" % (tag, rank), mode="w+", dtype=np.uint32, shape=(max(1, my_words),))
+            worker.copy_cells(mine_file)
+            mine_file.flush()
+            _barrier(group, world)
+            dev = torch.device("cuda", ctx.device)
+            for info in everyone:
+                if info["rank"] != rank and info["words"]:
+                    words = np.load("%s_%d.npy" % (tag, info["rank"]), mmap_mode="r")
+                    staged[info["rank"]] = torch.from_numpy(np.ascontiguousarray(words).view(np.int32)).to(dev)
+            torch.cuda.synchronize(dev)
         parts = []
         for i, (words, mask, levels, off, owner, _svo, _dagn) in enumerate(ordered):
             if owner == rank:
@@ -126,23 +162,25 @@ def run(ctx, tile, length, kind, rank=0, world=1, group=None, lookups=3840 * 216
             elif words == 1 and mask in (0, 0x5555):
                 parts.append((words, mask, ctx.device, 0))
             else:
-                base, dev = opened[owner]
-                parts.append((words, mask, dev, base + 4 * off))
-        ipc_open_ms = (time.perf_counter() - t_open) * 1e3
+                parts.append((words, mask, ctx.device, staged[owner].data_ptr() + 4 * off))
         cont = cgrid.assemble(ctx, length, ordered[0][2], leafmasks, parts)
         ctx.synchronize()
-        if log:
-            log("rank %d: ipc open %.1f ms, assemble (peer copies + lookup copy) %.1f ms" % (rank, ipc_open_ms, (time.perf_counter() - t_open) * 1e3 - ipc_open_ms))
-        for (ptr, _dev) in opened.values():
-            cgrid.ipc_close(ctx.device, ptr)
-        _barrier(group, world)  # nobody frees its exported block while a peer still copies from it
+        staged.clear()
+        if world > 1:
+            _barrier(group, world)  # nobody removes its file while a peer still reads it
+            del mine_file
+            try:
+                os.remove("%s_%d.npy" % (tag, rank))
+            except OSError:
+                pass
     assemble_ms = (time.perf_counter() - t0) * 1e3
 
     result = {
         "virtual_side": res, "tile": n, "length": length, "kind": kind if fetch is None else "caller-provided tiles", "leafmasks": bool(leafmasks),
         "n_gpus": world, "depth_source": "device generator (cpvs_depth_generate)" if fetch is None else "host callback + H2D copy",
         "xy_tiles": length * length, "cells": length ** 3, "one_word_cells": sum(1 for c in ordered if c[0] == 1), "samples": res * res,
-        "ownership": "cost-aware (closed-form node counts, longest first)" if cost_aware else "rotated round-robin", "moved_tiles": moved,
+        "ownership": ("by cost (closed-form node counts of the tiles at 1/8 resolution), longest first" if cost_aware
+                      else "shared queue (atomic counter on the rendezvous store)" if world > 1 else "single GPU"), "moved_tiles": moved,
         "build_ms_max_rank": max(i["build_ms"] for i in everyone), "build_ms_per_rank": [i["build_ms"] for i in everyone],
         "depth_ms_per_rank": [i["depth_ms"] for i in everyone], "timing": "device time from depth tiles resident in device memory (SURVEY.md 8d); "
                                                                           "producing them is clocked separately (depth_ms_per_rank)",

@@ -302,6 +302,9 @@ CPVS_API float cpvs_grid_worker_depth_ms(const cpvs_grid_worker* w);
  * peer to peer) and feeds cpvs_container_assemble; the block lives until the worker is destroyed. */
 CPVS_API int cpvs_grid_worker_export(cpvs_grid_worker* w, unsigned char handle[64], uint64_t* offsets, int capacity);
 CPVS_API int cpvs_ipc_open(const unsigned char handle[64], int device, void** out);
+/* The same cells copied to host memory instead (out_host == NULL: only offsets and the count): the cheaper medium when
+ * eight processes would otherwise each have to set up peer access to seven others. Returns the number of cells. */
+CPVS_API int cpvs_grid_worker_copy_cells(const cpvs_grid_worker* w, uint32_t* out_host, uint64_t capacity_words, uint64_t* offsets, int capacity);
 CPVS_API int cpvs_ipc_close(int device, void* ptr);
 /* Ownership by cost, longest tile first to the least loaded worker; owner_in (may be NULL) breaks ties in favour of the
  * worker that already holds the tile's hierarchy. Pure host code. */
