@@ -603,7 +603,8 @@ def run_own(args):
             kname = {"leaves": "buildLeafColumnsResidueKernel" if per_column else "buildLeavesKernel", "leaf_insert": "insertLeavesKernel",
                      "emit_leaves": "emitLeavesKernel", "pyramid_base": "pyramidBaseKernel"}
             with open(tpath) as f:
-                traffic = json.load(f)["dram_bytes_per_launch"].get(kname[dom])
+                table = json.load(f)["dram_bytes_per_launch"]
+            traffic = next((v for k, v in table.items() if k == kname[dom] or k.startswith(kname[dom] + "<")), None)
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
         bbytes = build_bytes(n, info0, leaf)
         roof_ms = bbytes / (peak * 1e9) * 1e3
