@@ -53,6 +53,7 @@ def parse_args():
                     help="whole tile-grid build instead of the step bench: 64k = BASELINE configs[2] (4x4x4 cells of 16K^2 terrain "
                          "tiles), 256k = configs[4] (16x16x16 cells of 16K^2 city tiles); tiles are sharded over --gpus ranks")
     ap.add_argument("--grid-tile", type=int, default=16384, help="side of one depth tile of --grid (reduce for a quick run)")
+    ap.add_argument("--grid-passes", type=int, default=2, help="--grid builds the grid this many times and reports the last pass")
     ap.add_argument("--grid-length", type=int, default=None, help="override the grid length of --grid")
     ap.add_argument("--grid-kind", default=None, choices=["plane", "terrain_dev", "city"])
     ap.add_argument("--no-verify", action="store_true", help="--grid: skip the lookups-decode-to-depth checks")
@@ -260,8 +261,12 @@ def run_grid(args):
     sampler = ClockSampler(local)
     if not args.no_clocks:
         sampler.start()
-    res = gridbuild.run(ctx, args.grid_tile, length, kind, rank, world, group, verify=not args.no_verify,
-                        log=(lambda m: print(m, file=sys.stderr, flush=True)) if os.environ.get("CPVS_GRID_LOG") else None)
+    first = None
+    for r in range(max(1, args.grid_passes)):  # the last pass is reported; the first one warms the contexts up (see configs[2]/[4] below)
+        res = gridbuild.run(ctx, args.grid_tile, length, kind, rank, world, group, verify=not args.no_verify and r == 0,
+                            log=(lambda m: print(m, file=sys.stderr, flush=True)) if os.environ.get("CPVS_GRID_LOG") else None)
+        first = first or res
+    res["first_pass_build_ms_max_rank"] = first["build_ms_max_rank"]
     clocks = sampler.stop()
     if rank == 0:
         line = {"metric": METRIC, "value": res["build_msamples_per_s"], "unit": UNIT, "n_gpus": world, "higher_is_better": True,
@@ -547,16 +552,20 @@ def run_own(args):
     if not args.no_grids:
         for name in ("64k", "256k"):
             cfg_index, length, kind = GRIDS[name]
-            # the 64K^2 grid is a few milliseconds of work per GPU at N = 8: three repetitions, the median is reported and all
-            # three are listed (one descheduled host thread is a fifth of such a build)
+            # Like the steps of the headline, a grid is built again and again (every frame the light moves): the first pass is the
+            # warm-up -- the scratch arenas, staging buffers and size memos of every context grow to the grid's heaviest slice -- and
+            # is listed, not counted. The 64K^2 grid is a few milliseconds of work per GPU at N = 8: three timed passes, the median
+            # is reported and all are listed (one descheduled host thread is a fifth of such a build); the 256K^2 grid: two.
+            passes = 4 if name == "64k" else 3
             reps = [gridbuild.run(ctx, args.grid_tile, length, kind, rank, world, gloo, lookups=3840 * 2160, lookup_iters=4, verify=(r == 0),
-                                  replicate=(r == 0)) for r in range(3 if name == "64k" else 1)]
-            by_time = sorted(reps, key=lambda g: g["build_ms_max_rank"])
+                                  replicate=(r == 0)) for r in range(passes)]
+            by_time = sorted(reps[1:], key=lambda g: g["build_ms_max_rank"])
             g = dict(reps[0])
             for key in ("build_ms_max_rank", "build_ms_per_rank", "depth_ms_per_rank", "tiles_per_rank", "wall_ms_max_rank", "build_msamples_per_s", "moved_tiles"):
                 g[key] = by_time[len(by_time) // 2][key]
             entry = grid_line(g, cfg_index)
-            entry["repetitions_build_ms_max_rank"] = [r["build_ms_max_rank"] for r in reps]
+            entry["first_pass_build_ms_max_rank"] = reps[0]["build_ms_max_rank"]
+            entry["repetitions_build_ms_max_rank"] = [r["build_ms_max_rank"] for r in reps[1:]]
             grids["configs%d" % cfg_index] = entry
             barrier()
 

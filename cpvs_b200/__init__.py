@@ -14,6 +14,10 @@ import os
 
 import numpy as np
 
+# See capi.cu (moreHardwareQueues): the library's streams should not share hardware queues. Read by the driver when the
+# process's CUDA context is created, so it is set here, at import, and again when the library is loaded.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcpvs_b200.so")
 
@@ -98,6 +102,7 @@ SIGNATURES = {
     "cpvs_grid_worker_estimate": (_I, [_VP, _VP, _I, _VP]),
     "cpvs_grid_worker_release": (_I, [_VP, _VP, _I]),
     "cpvs_grid_worker_build": (_I, [_VP, _VP, _I]),
+    "cpvs_grid_worker_build_from": (_I, [_VP, _VP, _VP]),
     "cpvs_grid_worker_num_cells": (_I, [_VP]),
     "cpvs_grid_worker_cells": (_I, [_VP, _VP, _I]),
     "cpvs_grid_worker_device_ms": (ctypes.c_float, [_VP]),

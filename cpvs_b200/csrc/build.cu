@@ -33,7 +33,7 @@ __global__ void storeCoordKernel(u64* dst, u64 value) { *dst = value; }
 struct HostTrace {
 	bool on;
 	std::chrono::steady_clock::time_point last;
-	HostTrace() : on(std::getenv("CPVS_TRACE") != nullptr), last(std::chrono::steady_clock::now()) {}
+	HostTrace() : on(std::getenv("CPVS_TRACE") && std::getenv("CPVS_TRACE")[0] == '1'), last(std::chrono::steady_clock::now()) {}
 	void mark(const char* what) {
 		if (!on) return;
 		const auto now = std::chrono::steady_clock::now();
@@ -125,6 +125,10 @@ struct Build {
 
 	u32* dagAlloc = nullptr;  // capacity words; the DAG ends at its end (released here unless a shadow took it over)
 	u64 dagCapacity = 0;
+	// staged: dagAlloc is one of the context's staging buffers (stagingWords long), big enough for any DAG these node counts can
+	// give; the finished DAG is copied out of it into an allocation of its size.
+	bool staged = false;
+	u64 stagingWords = 0;
 	bool leavesEmitted = false;
 
 	PhaseEvents phases;
@@ -141,7 +145,12 @@ struct Build {
 			if (done) cudaEventSynchronize(done);  // an abandoned build may still be writing it
 			ctx->readbackFree.push_back(h);
 		}
-		if (dagAlloc) ctxFree(ctx, dagAlloc);
+		if (dagAlloc && staged) {
+			std::lock_guard<std::mutex> guard(ctx->cacheLock);
+			ctx->stagingFree.emplace_back(dagAlloc, stagingWords);
+		} else if (dagAlloc) {
+			ctxFree(ctx, dagAlloc);
+		}
 		for (cudaEvent_t e : {evRankStart, evRankStop, evLeafEmitStart, done})
 			if (e) cudaEventDestroy(e);
 	}
@@ -162,14 +171,30 @@ struct Build {
 	}
 };
 
-SizeMemo* findMemo(cpvs_ctx* ctx, int n, u32 zTileIndex, u32 zTileNum, int leafmasks) {
+SizeMemo* ownMemo(cpvs_ctx* ctx, int n, u32 zTileIndex, u32 zTileNum, int leafmasks) {
 	for (SizeMemo& m : ctx->memos)
 		if (m.n == n && m.zTileIndex == zTileIndex && m.zTileNum == zTileNum && m.leafmasks == leafmasks) return &m;
 	return nullptr;
 }
 
+// The sizes of the last build of this shape: the context's own, else what another context of its family (the contexts
+// cpvs::siblingContext chains on one GPU, which take turns on the same stream of builds) has seen.
+bool findMemo(cpvs_ctx* ctx, int n, u32 zTileIndex, u32 zTileNum, int leafmasks, SizeMemo* out) {
+	auto lookIn = [&](cpvs_ctx* c) {
+		std::lock_guard<std::mutex> guard(c->memoLock);
+		const SizeMemo* m = ownMemo(c, n, zTileIndex, zTileNum, leafmasks);
+		if (m) *out = *m;
+		return m != nullptr;
+	};
+	if (lookIn(ctx)) return true;
+	for (cpvs_ctx* c = ctx->family; c; c = c->sibling)
+		if (c != ctx && lookIn(c)) return true;
+	return false;
+}
+
 void rememberSizes(cpvs_ctx* ctx, const Build& b, const u64* h) {
-	SizeMemo* m = findMemo(ctx, b.mm->n, b.zTileIndex, b.zTileNum, b.useLeaf ? 1 : 0);
+	std::lock_guard<std::mutex> guard(ctx->memoLock);
+	SizeMemo* m = ownMemo(ctx, b.mm->n, b.zTileIndex, b.zTileNum, b.useLeaf ? 1 : 0);
 	if (!m) {
 		if (ctx->memos.size() >= 256) ctx->memos.erase(ctx->memos.begin());
 		ctx->memos.emplace_back();
@@ -196,6 +221,8 @@ cpvs_shadow* newShadow(cpvs_ctx* ctx) {
 	s->skip = nullptr;
 	s->skipLevels = 0;
 	s->pending = nullptr;
+	s->dagOnCopyStream = false;
+	s->copyInFlight = false;
 	s->pendingLeafmasks = 0;
 	s->status = CPVS_OK;
 	return s;
@@ -225,30 +252,119 @@ int oneWordShadow(cpvs_ctx* ctx, int L, bool useLeaf, u32 rootMask, cpvs_shadow*
 	return CPVS_OK;
 }
 
+}  // namespace
+namespace cpvs {
+void releaseCountsBuffer(cpvs_minmax* mm) {
+	if (!mm->countsPinned) return;
+	if (mm->countsPooled) {
+		std::lock_guard<std::mutex> poolGuard(mm->countsCtx->cacheLock);
+		mm->countsCtx->countBuffers.push_back(mm->countsPinned);
+	} else {
+		cudaFreeHost(mm->countsPinned);
+	}
+	mm->countsPinned = nullptr;
+}
+}  // namespace cpvs
+namespace {
+constexpr u32 kPooledCountSlices = 64;
+
 // Closed-form node counts of all z-slices of the hierarchy's column, computed once per (hierarchy, zTileNum, minLevel):
-// one launch and one read-back, shared by every slice built from this pyramid.
-int columnCounts(cpvs_ctx* ctx, const cpvs_minmax* cmm, const PyramidView& pyr, u32 zTileNum, int minLevel, const u64** counts) {
+// one launch and one read-back, shared by every slice built from this pyramid. columnCountsBegin enqueues the two (the
+// read-back into a pinned buffer of the context) and returns; columnCounts waits for them.
+int columnCountsBegin(cpvs_ctx* ctx, const cpvs_minmax* cmm, const PyramidView& pyr, u32 zTileNum, int minLevel) {
 	cpvs_minmax* mm = const_cast<cpvs_minmax*>(cmm);
 	std::lock_guard<std::mutex> guard(mm->lowLock);
-	if (mm->columnSlices != zTileNum || mm->columnMinLevel != minLevel) {
-		const size_t words = (size_t)zTileNum * kMaxLevels;
-		u64* dCounts = nullptr;
-		cudaStream_t st = ctx->stream;
-		CPVS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dCounts), words * sizeof(u64), st));
-		cudaError_t e = cudaMemsetAsync(dCounts, 0, words * sizeof(u64), st);
-		if (e == cudaSuccess) {
-			ctx->launches += launchColumnCounts(pyr, zTileNum, minLevel, dCounts, st);
-			mm->columnCounts.assign(words, 0);
-			e = cudaMemcpyAsync(mm->columnCounts.data(), dCounts, words * sizeof(u64), cudaMemcpyDeviceToHost, st);
+	if (mm->columnSlices == zTileNum && mm->columnMinLevel == minLevel) return CPVS_OK;
+	if (mm->countsPinned && mm->pendingSlices == zTileNum && mm->pendingMinLevel == minLevel) return CPVS_OK;
+	if (mm->countsPinned) CPVS_CUDA(cudaEventSynchronize(mm->evCounts));  // counts for another slicing in flight: superseded
+	const size_t words = (size_t)zTileNum * kMaxLevels;
+	if (mm->countsPinned && (!mm->countsPooled || zTileNum > kPooledCountSlices)) releaseCountsBuffer(mm);
+	if (!mm->countsPinned) {
+		if (zTileNum <= kPooledCountSlices) {
+			std::lock_guard<std::mutex> poolGuard(ctx->cacheLock);
+			if (ctx->countBuffers.empty()) {
+				u64* buf = nullptr;
+				CPVS_CUDA(cudaMallocHost(reinterpret_cast<void**>(&buf), (size_t)kPooledCountSlices * kMaxLevels * sizeof(u64)));
+				ctx->countBuffers.push_back(buf);
+			}
+			mm->countsPinned = ctx->countBuffers.back();
+			ctx->countBuffers.pop_back();
+			mm->countsPooled = true;
+		} else {
+			CPVS_CUDA(cudaMallocHost(reinterpret_cast<void**>(&mm->countsPinned), words * sizeof(u64)));
+			mm->countsPooled = false;
 		}
-		if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-		cudaFreeAsync(dCounts, st);
-		if (e != cudaSuccess) return fail(CPVS_ECUDA, "column counts: %s", cudaGetErrorString(e));
-		mm->columnSlices = zTileNum;
-		mm->columnMinLevel = minLevel;
+		mm->countsCtx = ctx;
+	}
+	if (!mm->evCounts) CPVS_CUDA(cudaEventCreateWithFlags(&mm->evCounts, cudaEventDisableTiming));
+	u64* dCounts = nullptr;
+	cudaStream_t st = ctx->stream;
+	CPVS_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dCounts), words * sizeof(u64), st));
+	cudaError_t e = cudaMemsetAsync(dCounts, 0, words * sizeof(u64), st);
+	if (e == cudaSuccess) {
+		ctx->launches += launchColumnCounts(pyr, zTileNum, minLevel, dCounts, st);
+		e = cudaMemcpyAsync(mm->countsPinned, dCounts, words * sizeof(u64), cudaMemcpyDeviceToHost, st);
+	}
+	if (e == cudaSuccess) e = cudaEventRecord(mm->evCounts, st);
+	cudaFreeAsync(dCounts, st);
+	if (e != cudaSuccess) return fail(CPVS_ECUDA, "column counts: %s", cudaGetErrorString(e));
+	mm->pendingSlices = zTileNum;
+	mm->pendingMinLevel = minLevel;
+	return CPVS_OK;
+}
+
+int columnCounts(cpvs_ctx* ctx, const cpvs_minmax* cmm, const PyramidView& pyr, u32 zTileNum, int minLevel, const u64** counts) {
+	cpvs_minmax* mm = const_cast<cpvs_minmax*>(cmm);
+	if (mm->columnSlices != zTileNum || mm->columnMinLevel != minLevel) {
+		if (int rc = columnCountsBegin(ctx, cmm, pyr, zTileNum, minLevel)) return rc;
+		std::lock_guard<std::mutex> guard(mm->lowLock);
+		if (mm->columnSlices != zTileNum || mm->columnMinLevel != minLevel) {
+			cudaError_t e = cudaEventSynchronize(mm->evCounts);
+			if (e != cudaSuccess) return fail(CPVS_ECUDA, "column counts: %s", cudaGetErrorString(e));
+			mm->columnCounts.assign(mm->countsPinned, mm->countsPinned + (size_t)zTileNum * kMaxLevels);
+			releaseCountsBuffer(mm);
+			mm->columnSlices = zTileNum;
+			mm->columnMinLevel = minLevel;
+		}
 	}
 	*counts = mm->columnCounts.data();
 	return CPVS_OK;
+}
+
+// No DAG of an octree with these node counts has more words: every node its mask, every node below the root one pointer in
+// its parent, every leaf two words per slice (emit.cu).
+u64 upperBoundWords(const u64* counts, int top, int minLevel, bool useLeaf) {
+	u64 words = 1;
+	for (int l = top - 1; l >= minLevel && counts[l]; --l) words += 2 * counts[l] + (useLeaf && l == 2 ? 16 * counts[l] : 0);
+	return words;
+}
+constexpr u64 kMaxStagingWords = 1ull << 29;  // 2 GiB: beyond that the DAG's size is predicted or waited for
+
+// A staging buffer of at least `words` words. All buffers of a context have one size, the largest bound seen so far plus a
+// quarter: once a grid's heaviest slice has been seen, nothing is allocated any more (buffers of an earlier, smaller size are
+// released as they turn up).
+cudaError_t takeStaging(cpvs_ctx* ctx, u64 words, u32** out, u64* have) {
+	std::vector<u32*> drop;
+	u64 size = 0;
+	*out = nullptr;
+	{
+		std::lock_guard<std::mutex> guard(ctx->cacheLock);
+		if (words > ctx->stagingWords) ctx->stagingWords = words + (words >> 2);
+		size = ctx->stagingWords;
+		while (!ctx->stagingFree.empty() && !*out) {
+			if (ctx->stagingFree.back().second >= size) {
+				*out = ctx->stagingFree.back().first;
+				*have = ctx->stagingFree.back().second;
+			} else {
+				drop.push_back(ctx->stagingFree.back().first);
+			}
+			ctx->stagingFree.pop_back();
+		}
+	}
+	for (u32* p : drop) cudaFreeAsync(p, ctx->stream);
+	if (*out) return cudaSuccess;
+	*have = size;
+	return cudaMallocAsync(reinterpret_cast<void**>(out), size * sizeof(u32), ctx->stream);
 }
 
 // ---- plan ----------------------------------------------------------------------------------------------------------------
@@ -662,14 +778,26 @@ int enqueueBuild(Build& b, const u64* exactCounts, const SizeMemo* memo, cudaEve
 
 	// The DAG's allocation: with a memo of this shape its size is predicted and the leaf level can be written during the
 	// merge; otherwise it is made once the sizes are known.
-	if (memo && ctx->predictSizes) {
+	if (exactCounts && ctx->predictSizes) {
+		const u64 bound = upperBoundWords(exactCounts, b.top, b.minLevel, b.useLeaf);
+		if (bound <= kMaxStagingWords) {
+			cudaError_t e = takeStaging(ctx, bound, &b.dagAlloc, &b.stagingWords);
+			if (e != cudaSuccess) return fail(CPVS_ENOMEM, "DAG staging buffer of %llu words: %s", (unsigned long long)bound, cudaGetErrorString(e));
+			b.staged = true;
+			b.dagCapacity = bound;
+		}
+	}
+	if (!b.dagAlloc && memo && ctx->predictSizes) {
 		u64 expectWords = memo->words;
 		if (exactCounts && memo->nodes[b.minLevel] && b.lv[b.minLevel].cap) {
 			// this build's node counts are known: the words follow the bottom level (same scene, another tile or slice)
 			const double ratio = (double)b.lv[b.minLevel].cap / (double)memo->nodes[b.minLevel];
 			expectWords = (u64)((double)memo->words * ratio) + 4096;
 		}
-		b.dagCapacity = expectWords + (expectWords >> ctx->headroomShift) + 1024;
+		// (scaled from another tile or slice: twice the head room -- a DAG that outgrows its allocation while later builds are
+		// already using the arena costs a whole rebuild)
+		const unsigned shift = exactCounts && ctx->headroomShift > 1 ? ctx->headroomShift - 1 : ctx->headroomShift;
+		b.dagCapacity = expectWords + (expectWords >> shift) + 1024;
 		cudaError_t e = ctxAlloc(ctx, reinterpret_cast<void**>(&b.dagAlloc), b.dagCapacity * sizeof(u32));
 		if (e != cudaSuccess) return fail(CPVS_ENOMEM, "DAG allocation of %llu words: %s", (unsigned long long)b.dagCapacity, cudaGetErrorString(e));
 	}
@@ -712,7 +840,7 @@ int enqueueBuild(Build& b, const u64* exactCounts, const SizeMemo* memo, cudaEve
 
 // arenaIntact: no later build has been enqueued on the context, so a DAG that outgrew its predicted allocation can be
 // emitted again from the merge results still in the arena; otherwise that, too, asks for a rebuild.
-int finishBuild(Build& b, cpvs_shadow* s, bool arenaIntact, bool* redo) {
+int finishBuild(Build& b, cpvs_shadow* s, bool arenaIntact, bool* redo, bool deferCopy = false) {
 	cpvs_ctx* ctx = b.ctx;
 	cudaStream_t st = b.st;
 	const u64* h = b.h;
@@ -744,6 +872,7 @@ int finishBuild(Build& b, cpvs_shadow* s, bool arenaIntact, bool* redo) {
 				if (b.lv[l].cap && l >= b.lastInner && h[kSlotNodes + l - 1] != b.lv[l - 1].cap)
 					return fail(CPVS_EINTERNAL, "level %d: expansion produced %llu nodes, count pass predicted %llu", l - 1,
 							(unsigned long long)h[kSlotNodes + l - 1], (unsigned long long)b.lv[l - 1].cap);
+		if ((overflow & kOverflowWords) && b.staged) return fail(CPVS_EINTERNAL, "DAG of %llu words exceeds the bound of its node counts", (unsigned long long)totalWords);
 		if (overflow & kOverflowWords) {
 			// The predicted allocation was too small.
 			if (attempt) return fail(CPVS_EINTERNAL, "DAG of %llu words did not fit an exact allocation", (unsigned long long)totalWords);
@@ -780,9 +909,31 @@ int finishBuild(Build& b, cpvs_shadow* s, bool arenaIntact, bool* redo) {
 		if (e == cudaSuccess && b.haveLeaves) e = cudaEventElapsedTime(&phaseMs[CPVS_PHASE_LEAF_RESOLVE], b.evRankStart, b.evRankStop);
 		if (e != cudaSuccess) return fail(CPVS_ECUDA, "cpvs_shadow_create: %s", cudaGetErrorString(e));
 
-		s->dagAlloc = b.dagAlloc;
-		s->dag = b.dagAlloc + (b.dagCapacity - totalWords);
-		b.dagAlloc = nullptr;  // owned by the shadow now
+		if (b.staged) {
+			// out of the staging buffer into an allocation of the DAG's size, on the context's copy stream: nothing that was
+			// enqueued on the build stream in the meantime (the next builds) is waited for
+			u32* exact = nullptr;
+			const u32* from = b.dagAlloc + (b.dagCapacity - totalWords);
+			const u64 shift = (reinterpret_cast<uintptr_t>(from) & 15u) >> 2;  // same alignment on both sides: 16-byte copies
+			e = cudaMallocAsync(reinterpret_cast<void**>(&exact), (totalWords + shift) * sizeof(u32), ctx->copyStream);
+			if (e != cudaSuccess) return fail(CPVS_ENOMEM, "DAG allocation of %llu words: %s", (unsigned long long)totalWords, cudaGetErrorString(e));
+			ctx->launches += launchCopyWords(exact + shift, from, totalWords, ctx->copyStream);
+			e = cudaGetLastError();
+			if (e == cudaSuccess && !deferCopy) e = cudaStreamSynchronize(ctx->copyStream);
+			s->copyInFlight = deferCopy;  // (the caller then keeps the Build, and with it the staging buffer, until the copy is done)
+			if (e != cudaSuccess) {
+				cudaFreeAsync(exact, ctx->copyStream);
+				return fail(CPVS_ECUDA, "cpvs_shadow_create: %s", cudaGetErrorString(e));
+			}
+			b.trace.mark("staged: allocation, copy, sync");
+			s->dagAlloc = exact;
+			s->dag = exact + shift;  // (the staging buffer goes back to the context with the Build)
+			s->dagOnCopyStream = true;
+		} else {
+			s->dagAlloc = b.dagAlloc;
+			s->dag = b.dagAlloc + (b.dagCapacity - totalWords);
+			b.dagAlloc = nullptr;  // owned by the shadow now
+		}
 		std::memset(&s->info, 0, sizeof(s->info));
 		s->info.num_levels = (u32)b.L;
 		s->info.leafmasks = b.useLeaf ? 1 : 0;
@@ -810,6 +961,7 @@ int buildExact(cpvs_ctx* ctx, const cpvs_minmax* mm, u32 zTileIndex, u32 zTileNu
 // A build in flight (cpvs_shadow_create_async): everything finishBuild needs, and what a rebuild would.
 struct cpvs_pending_build {
 	Build b;
+	bool finished = false;  // only the copy out of the staging buffer is still in flight (shadowWaitBegin)
 	const cpvs_minmax* mm;
 	u64 serial;  // the context's build counter when this one was enqueued
 };
@@ -822,13 +974,9 @@ int buildExact(cpvs_ctx* ctx, const cpvs_minmax* mm, u32 zTileIndex, u32 zTileNu
 	const int L = mm->numLevels, top = L - 2, minLevel = useLeaf ? 2 : 0;
 	cudaStream_t st = ctx->stream;
 	const PyramidView pyr = pyramidView(mm);
-	const SizeMemo* memo = findMemo(ctx, mm->n, zTileIndex, zTileNum, useLeaf ? 1 : 0);
 	SizeMemo memoCopy;
-	if (memo) {
-		memoCopy = *memo;  // rememberSizes() may move the vector's storage
-		memo = &memoCopy;
-	}
-	async = async && memo && ctx->predictSizes;
+	const SizeMemo* memo = findMemo(ctx, mm->n, zTileIndex, zTileNum, useLeaf ? 1 : 0, &memoCopy) ? &memoCopy : nullptr;
+	async = async && ctx->predictSizes;  // (whether anything stands in the way is known once the counts are)
 	struct EventGuard {
 		cudaEvent_t ev = nullptr;
 		~EventGuard() {
@@ -848,6 +996,7 @@ int buildExact(cpvs_ctx* ctx, const cpvs_minmax* mm, u32 zTileIndex, u32 zTileNu
 	if (counts[top - 1] == 0) return oneWordShadow(ctx, L, useLeaf, (u32)counts[kRootMaskScalar], s);
 	++ctx->exactBuilds;
 	++ctx->buildSerial;
+	async = async && (memo || upperBoundWords(counts, top, minLevel, useLeaf) <= kMaxStagingWords);
 	if (async) {
 		cpvs_pending_build* p = new (std::nothrow) cpvs_pending_build();
 		if (!p) return fail(CPVS_ENOMEM, "cpvs_shadow_create: host allocation");
@@ -875,6 +1024,10 @@ int buildExact(cpvs_ctx* ctx, const cpvs_minmax* mm, u32 zTileIndex, u32 zTileNu
 }  // namespace
 
 namespace cpvs {
+int columnCountsBegin(cpvs_ctx* ctx, const cpvs_minmax* mm, u32 zTileNum, int minLevel) {
+	CPVS_CUDA(cudaSetDevice(ctx->device));
+	return ::columnCountsBegin(ctx, mm, pyramidView(mm), zTileNum, minLevel);
+}
 int columnCountsOf(cpvs_ctx* ctx, const cpvs_minmax* mm, u32 zTileNum, int minLevel, const u64** counts) {
 	CPVS_CUDA(cudaSetDevice(ctx->device));
 	return columnCounts(ctx, mm, pyramidView(mm), zTileNum, minLevel, counts);
@@ -915,9 +1068,9 @@ static int createImpl(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTileIndex,
 	int rc = CPVS_OK;
 	// Whole-volume builds of a shape seen before run on predicted sizes. Slices of a tile column always take the column's
 	// exact counts: one launch and one read-back serve all of them, and most slices turn out to be a single word.
-	const SizeMemo* memo = findMemo(ctx, mm->n, zTileIndex, zTileNum, useLeaf ? 1 : 0);
+	SizeMemo memoCopy;
+	const bool memo = findMemo(ctx, mm->n, zTileIndex, zTileNum, useLeaf ? 1 : 0, &memoCopy);
 	if (memo && ctx->predictSizes && zTileNum == 1) {
-		const SizeMemo memoCopy = *memo;
 		++ctx->predictedBuilds;
 		cpvs_pending_build* p = new (std::nothrow) cpvs_pending_build();
 		if (!p) {
@@ -964,7 +1117,7 @@ int cpvs_shadow_create_async(cpvs_ctx* ctx, const cpvs_minmax* mm, uint32_t zTil
 	return createImpl(ctx, mm, zTileIndex, zTileNum, leafmasks, true, out);
 }
 
-int cpvs_shadow_wait(cpvs_shadow* s) {
+static int waitImpl(cpvs_shadow* s, bool deferCopy) {
 	if (!s) return fail(CPVS_EINVAL, "cpvs_shadow_wait: NULL argument");
 	if (!s->pending) return s->status;
 	cpvs_ctx* ctx = s->ctx;
@@ -972,21 +1125,45 @@ int cpvs_shadow_wait(cpvs_shadow* s) {
 	std::lock_guard<std::mutex> guard(ctx->buildLock);
 	cpvs_pending_build* p = s->pending;
 	if (!p) return s->status;
-	bool redo = false;
-	int rc = finishBuild(p->b, s, p->serial == ctx->buildSerial, &redo);
-	if (rc == CPVS_OK && redo) {  // a predicted capacity did not suffice: once more, with exact counts
-		++ctx->overflowRebuilds;
-		const cpvs_minmax* mm = p->mm;
-		const Build& b = p->b;
-		s->pending = nullptr;
-		rc = buildExact(ctx, mm, b.zTileIndex, b.zTileNum, b.useLeaf, s, false);
+	int rc = s->status;
+	if (!p->finished) {
+		bool redo = false;
+		rc = finishBuild(p->b, s, p->serial == ctx->buildSerial, &redo, deferCopy);
+		if (rc == CPVS_OK && redo) {  // a predicted capacity did not suffice: once more, with exact counts
+			++ctx->overflowRebuilds;
+			const cpvs_minmax* mm = p->mm;
+			const Build& b = p->b;
+			s->pending = nullptr;
+			rc = buildExact(ctx, mm, b.zTileIndex, b.zTileNum, b.useLeaf, s, false);
+		}
+		s->status = rc;
+		if (rc != CPVS_OK) s->statusText = cpvs_last_error();
+		if (rc == CPVS_OK && s->copyInFlight && deferCopy) {
+			p->finished = true;
+			s->pending = p;
+			return rc;
+		}
+	}
+	if (s->copyInFlight) {
+		s->copyInFlight = false;
+		const cudaError_t e = cudaStreamSynchronize(ctx->copyStream);
+		if (e != cudaSuccess) {
+			rc = s->status = fail(CPVS_ECUDA, "cpvs_shadow_create: %s", cudaGetErrorString(e));
+			s->statusText = cpvs_last_error();
+		}
 	}
 	s->pending = nullptr;
 	delete p;
-	s->status = rc;
-	if (rc != CPVS_OK) s->statusText = cpvs_last_error();
 	return rc;
 }
+
+int cpvs_shadow_wait(cpvs_shadow* s) { return waitImpl(s, false); }
+
+}  // extern "C"
+namespace cpvs {
+int shadowWaitBegin(cpvs_shadow* s) { return waitImpl(s, true); }
+}  // namespace cpvs
+extern "C" {
 
 int cpvs_shadow_create_from_depth(cpvs_ctx* ctx, const float* depth, int n, int mem, uint32_t zTileIndex, uint32_t zTileNum, int leafmasks,
 		cpvs_shadow** out) {
@@ -1007,7 +1184,16 @@ int cpvs_shadow_destroy(cpvs_shadow* s) {
 		s->pending = nullptr;
 		delete p;
 	}
-	ctxFree(s->ctx, s->dagAlloc);
+	if (s->copyInFlight) cudaStreamSynchronize(s->ctx->copyStream);
+	if (s->dagOnCopyStream) {
+		// allocated on the copy stream and given back there, so that the next such allocation finds it without depending on
+		// what the build stream still has queued -- behind the work enqueued on the build stream so far, like every release
+		cudaEventRecord(s->ctx->evCopyFree, s->ctx->stream);
+		cudaStreamWaitEvent(s->ctx->copyStream, s->ctx->evCopyFree, 0);
+		cudaFreeAsync(s->dagAlloc, s->ctx->copyStream);
+	} else {
+		ctxFree(s->ctx, s->dagAlloc);
+	}
 	if (s->skip) cudaFreeAsync(s->skip, s->ctx->stream);
 	freeLookupIndex(s->ctx, &s->index);
 	if (s->ready) cudaEventDestroy(s->ready);

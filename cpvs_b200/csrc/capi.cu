@@ -13,6 +13,13 @@ using namespace cpvs;
 
 namespace {
 thread_local std::string gLastError;
+
+// A context runs a build on five streams plus a copy stream, two or more contexts share a GPU, and the driver maps all
+// streams of a process onto CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8): streams that share a queue wait for each
+// other's kernels (measured: the copy of a finished DAG, on its own stream, waited 2.3 ms for the next tile's builds). The
+// variable is read when the process's CUDA context is created, so it is set when the library is loaded -- unless the process
+// has chosen a value itself; a process that has already initialised CUDA keeps what it had (slower, never wrong).
+__attribute__((constructor)) void moreHardwareQueues() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
 }  // namespace
 
 namespace cpvs {
@@ -44,6 +51,12 @@ cudaError_t ctxAlloc(cpvs_ctx* ctx, void** out, size_t bytes) {
 	return e;
 }
 
+void ctxAdopt(cpvs_ctx* ctx, void* p, size_t bytes) {
+	if (!p || bytes < kCacheMinBytes) return;
+	std::lock_guard<std::mutex> guard(ctx->cacheLock);
+	ctx->liveBlocks[p] = bytes;
+}
+
 void ctxFree(cpvs_ctx* ctx, void* p) {
 	if (!p) return;
 	std::lock_guard<std::mutex> guard(ctx->cacheLock);
@@ -66,6 +79,7 @@ cpvs_ctx* siblingContext(cpvs_ctx* ctx) {
 	std::lock_guard<std::mutex> guard(ctx->cacheLock);
 	if (!ctx->sibling) {
 		if (cpvs_ctx_create(ctx->device, &ctx->sibling) != CPVS_OK) return nullptr;
+		ctx->sibling->family = ctx->family;
 		ctx->sibling->predictSizes = ctx->predictSizes;
 		ctx->sibling->headroomShift = ctx->headroomShift;
 		ctx->sibling->leafColumns = ctx->leafColumns;
@@ -125,6 +139,10 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 	CPVS_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
 	unsigned long long keep = ~0ull;  // keep freed scratch cached in the pool between calls
 	CPVS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+	// An allocation never waits for a release that is still queued on another stream (a finished DAG's allocation on the copy
+	// stream would otherwise wait for the builds queued behind it); it takes memory that is free now, or new memory.
+	int off = 0;
+	CPVS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off));
 	cpvs_ctx* ctx = new (std::nothrow) cpvs_ctx;
 	if (!ctx) return fail(CPVS_ENOMEM, "cpvs_ctx_create: host allocation");
 	ctx->device = device;
@@ -132,11 +150,13 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 	ctx->arena = nullptr;
 	ctx->arenaBytes = 0;
 	ctx->scalars = nullptr;
-	ctx->own = ctx->aux = ctx->aux2 = ctx->aux3 = ctx->aux4 = nullptr;
+	ctx->own = ctx->aux = ctx->aux2 = ctx->aux3 = ctx->aux4 = ctx->copyStream = nullptr;
 	ctx->cachedBytes = 0;
+	ctx->stagingWords = 0;
 	ctx->sibling = nullptr;
+	ctx->family = ctx;
 	ctx->predictedBuilds = ctx->exactBuilds = ctx->overflowRebuilds = ctx->reemissions = 0;
-	cudaEvent_t* plain[] = {&ctx->evFork, &ctx->evJoin, &ctx->evJoin3, &ctx->evClear, &ctx->evCols, &ctx->evLeafRanked, &ctx->evLeafEmitted};
+	cudaEvent_t* plain[] = {&ctx->evFork, &ctx->evJoin, &ctx->evJoin3, &ctx->evClear, &ctx->evCols, &ctx->evLeafRanked, &ctx->evLeafEmitted, &ctx->evCopyFree};
 	for (cudaEvent_t* e : plain) *e = nullptr;
 	ctx->buildSerial = 0;
 	{
@@ -161,6 +181,7 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 	int prioLeast = 0, prioGreatest = 0;
 	if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prioLeast, &prioGreatest);
 	if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, prioGreatest);
+	if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->copyStream, cudaStreamNonBlocking, prioGreatest);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux2, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux3, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->aux4, cudaStreamNonBlocking);
@@ -187,9 +208,12 @@ int cpvs_ctx_destroy(cpvs_ctx* ctx) {
 	cudaStreamSynchronize(ctx->stream);
 	if (ctx->scalars) cudaFree(ctx->scalars);
 	for (u64* slot : ctx->readbackAll) cudaFreeHost(slot);
-	for (cudaStream_t st : {ctx->aux, ctx->aux2, ctx->aux3, ctx->aux4, ctx->own})
+	for (u64* buf : ctx->countBuffers) cudaFreeHost(buf);
+	for (auto& block : ctx->stagingFree) cudaFreeAsync(block.first, ctx->stream);
+	ctx->stagingFree.clear();
+	for (cudaStream_t st : {ctx->aux, ctx->aux2, ctx->aux3, ctx->aux4, ctx->copyStream, ctx->own})
 		if (st) cudaStreamDestroy(st);
-	for (cudaEvent_t ev : {ctx->evFork, ctx->evJoin, ctx->evJoin3, ctx->evClear, ctx->evCols, ctx->evLeafRanked, ctx->evLeafEmitted})
+	for (cudaEvent_t ev : {ctx->evFork, ctx->evJoin, ctx->evJoin3, ctx->evClear, ctx->evCols, ctx->evLeafRanked, ctx->evLeafEmitted, ctx->evCopyFree})
 		if (ev) cudaEventDestroy(ev);
 	delete ctx;
 	return CPVS_OK;
@@ -222,7 +246,7 @@ int cpvs_ctx_reserve(cpvs_ctx* ctx, uint64_t bytes) {
 	return CPVS_OK;
 }
 
-uint64_t cpvs_ctx_launch_count(const cpvs_ctx* ctx) { return ctx ? ctx->launches + (ctx->sibling ? ctx->sibling->launches : 0) : 0; }
+uint64_t cpvs_ctx_launch_count(const cpvs_ctx* ctx) { return ctx ? ctx->launches + cpvs_ctx_launch_count(ctx->sibling) : 0; }
 
 int cpvs_ctx_set_prediction(cpvs_ctx* ctx, int enabled, uint32_t headroomShift) {
 	if (!ctx) return fail(CPVS_EINVAL, "cpvs_ctx_set_prediction: NULL context");
@@ -234,10 +258,13 @@ int cpvs_ctx_set_prediction(cpvs_ctx* ctx, int enabled, uint32_t headroomShift) 
 
 int cpvs_ctx_get_stats(const cpvs_ctx* ctx, cpvs_ctx_stats* out) {
 	if (!ctx || !out) return fail(CPVS_EINVAL, "cpvs_ctx_get_stats: NULL argument");
-	out->predicted_builds = ctx->predictedBuilds;
-	out->exact_builds = ctx->exactBuilds;
-	out->overflow_rebuilds = ctx->overflowRebuilds;
-	out->reemissions = ctx->reemissions;
+	std::memset(out, 0, sizeof(*out));
+	for (const cpvs_ctx* c = ctx; c; c = c->sibling) {  // with the contexts chained to it (cpvs::siblingContext)
+		out->predicted_builds += c->predictedBuilds;
+		out->exact_builds += c->exactBuilds;
+		out->overflow_rebuilds += c->overflowRebuilds;
+		out->reemissions += c->reemissions;
+	}
 	return CPVS_OK;
 }
 
@@ -329,6 +356,11 @@ int cpvs_minmax_destroy(cpvs_minmax* mm) {
 	ctxFree(mm->ctx, mm->levelStorage);
 	ctxFree(mm->ctx, mm->residue);
 	ctxFree(mm->ctx, mm->ownedDepth);
+	if (mm->countsPinned) {  // counts that were begun and never used
+		cudaEventSynchronize(mm->evCounts);
+		releaseCountsBuffer(mm);
+	}
+	if (mm->evCounts) cudaEventDestroy(mm->evCounts);
 	if (mm->evStart) {
 		cudaEventDestroy(mm->evStart);
 		cudaEventDestroy(mm->evBase);

@@ -138,6 +138,34 @@ __global__ void __launch_bounds__(kEmitThreads) emitLeavesKernel(EmitLevelArgs a
 
 }  // namespace
 
+namespace {
+// A finished DAG out of its staging buffer: dst and src have the same alignment within 16 bytes (the caller offsets dst).
+__global__ void __launch_bounds__(256) copyWordsKernel(u32* __restrict__ dst, const u32* __restrict__ src, u64 words) {
+	const u64 head = ((16u - (reinterpret_cast<uintptr_t>(src) & 15u)) & 15u) >> 2;  // words before the first 16-byte boundary
+	const u64 tid = (u64)blockIdx.x * blockDim.x + threadIdx.x, threads = (u64)gridDim.x * blockDim.x;
+	if (words <= head) {
+		if (tid < words) dst[tid] = src[tid];
+		return;
+	}
+	const u64 quads = (words - head) >> 2;
+	const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
+	uint4* d4 = reinterpret_cast<uint4*>(dst + head);
+	for (u64 i = tid; i < quads; i += threads) d4[i] = __ldcs(s4 + i);
+	const u64 tail = head + (quads << 2);
+	if (tid < head) dst[tid] = src[tid];
+	if (tid < words - tail) dst[tail + tid] = src[tail + tid];
+}
+
+}  // namespace
+
+int launchCopyWords(u32* dst, const u32* src, u64 words, cudaStream_t stream) {
+	if (!words) return 0;
+	const u64 want = (words / 4 + 255) / 256;
+	const unsigned blocks = (unsigned)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+	copyWordsKernel<<<blocks, 256, 0, stream>>>(dst, src, words);
+	return 1;
+}
+
 int launchLevelBases(const u64* words, u64* bases, int topLevel, int minLevel, u64* totalWords, u64 capacity, u32* overflow, const u16* rootMask,
 		u32* rootWord, cudaStream_t stream) {
 	levelBasesKernel<<<1, 1, 0, stream>>>(words, bases, topLevel, minLevel, totalWords, capacity, overflow, rootMask, rootWord);

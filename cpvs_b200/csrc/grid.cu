@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cstdio>
 #include <cstring>
 #include <new>
 #include <thread>
@@ -24,7 +25,6 @@
 using namespace cpvs;
 
 namespace cpvs {
-int columnCountsOf(cpvs_ctx* ctx, const cpvs_minmax* mm, u32 zTileNum, int minLevel, const u64** counts);  // build.cu
 int containerFromParts(cpvs_ctx* ctx, u32 length, u32 numLevels, int leafmasks, const cpvs_cell_part* parts, cpvs_container** out);  // capi.cu
 }  // namespace cpvs
 
@@ -35,6 +35,7 @@ struct WorkerTile {
 	cpvs_minmax* mm = nullptr;
 	u64 cost = 0;
 	bool built = false;
+	cudaEvent_t evDepth0 = nullptr, evDepth1 = nullptr;  // around the production of the depth tile, which runs alone on the GPU
 	std::vector<cpvs_shadow*> cells;  // z = 0 .. length-1
 };
 double nowMs() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -42,11 +43,18 @@ double nowMs() { return std::chrono::duration<double, std::milli>(std::chrono::s
 
 struct cpvs_grid_worker {
 	cpvs_ctx* ctx = nullptr;
-	// A second context of the same GPU: the z-slices of a tile are independent builds from one hierarchy, so they alternate
-	// between the two contexts and run side by side (the kernels of one fill the latency-bound phases of the other).
-	cpvs_ctx* ctx2 = nullptr;
+	// More contexts of the same GPU: the z-slices of a tile are independent builds from one hierarchy, so those that are
+	// real builds take turns on the contexts and run side by side (the kernels of one fill the latency-bound phases of the
+	// others). lanes[0] == ctx.
+	std::vector<cpvs_ctx*> lanes;
+	std::vector<cudaEvent_t> evLane;  // [k]: the slices enqueued on lane k so far are done
+	std::vector<bool> laneUsed;
+	u32 nextLane = 0;
+	cudaEvent_t depthFence = nullptr;  // the latest depth tile is done (an evDepth1); the lanes wait for it before their slices
+	cudaEvent_t evStage = nullptr;     // the copy out of hostStage is done
 	cudaEvent_t evJoin = nullptr;
 	float depthMs = 0.f;  // device time spent producing depth tiles (not part of the build metric: it starts from resident depth)
+	float depthInSpanMs = 0.f;  // the part of it inside the build call in progress
 	cpvs_grid_desc desc{};
 	std::vector<WorkerTile> tiles;
 	float* hostStage = nullptr;  // pinned, one tile (fetch callback)
@@ -71,6 +79,12 @@ void releaseInputs(cpvs_grid_worker* w, WorkerTile& t) {
 	t.mm = nullptr;
 	ctxFree(w->ctx, t.depth);
 	t.depth = nullptr;
+	if (t.evDepth0) {
+		if (w->depthFence == t.evDepth1) w->depthFence = nullptr;
+		cudaEventDestroy(t.evDepth0);
+		cudaEventDestroy(t.evDepth1);
+		t.evDepth0 = t.evDepth1 = nullptr;
+	}
 }
 
 // Depth tile in device memory (generated there, or fetched from the caller and copied).
@@ -83,10 +97,15 @@ int produceDepth(cpvs_grid_worker* w, WorkerTile& t) {
 	CPVS_CUDA(ctxAlloc(ctx, reinterpret_cast<void**>(&t.depth), texels * sizeof(float)));
 	if (d.scene >= 0) return cpvs_depth_generate(ctx, d.scene, d.tile, (int)t.x, (int)t.y, (int)d.length, t.depth);
 	if (!d.fetch) return fail(CPVS_EINVAL, "cpvs_grid: neither a scene nor a fetch callback");
-	if (!w->hostStage) CPVS_CUDA(cudaMallocHost(reinterpret_cast<void**>(&w->hostStage), texels * sizeof(float)));
-	CPVS_CUDA(cudaStreamSynchronize(ctx->stream));  // the previous tile's copy out of the staging buffer
+	if (!w->hostStage) {
+		CPVS_CUDA(cudaMallocHost(reinterpret_cast<void**>(&w->hostStage), texels * sizeof(float)));
+		CPVS_CUDA(cudaEventCreateWithFlags(&w->evStage, cudaEventDisableTiming));
+	} else {
+		CPVS_CUDA(cudaEventSynchronize(w->evStage));  // the previous tile's copy out of the staging buffer
+	}
 	if (d.fetch(d.user, t.x, t.y, w->hostStage) != 0) return fail(CPVS_EINVAL, "cpvs_grid: fetch callback failed for tile (%u,%u)", t.x, t.y);
 	CPVS_CUDA(cudaMemcpyAsync(t.depth, w->hostStage, texels * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+	CPVS_CUDA(cudaEventRecord(w->evStage, ctx->stream));
 	return CPVS_OK;
 }
 
@@ -127,11 +146,26 @@ int cpvs_grid_worker_create(cpvs_ctx* ctx, const cpvs_grid_desc* desc, cpvs_grid
 		cpvs_grid_worker_destroy(w);
 		return fail(CPVS_ECUDA, "cpvs_grid_worker_create: events");
 	}
-	w->ctx2 = siblingContext(ctx);  // kept by the context: warm for the next worker
-	if (!w->ctx2) {
-		cpvs_grid_worker_destroy(w);
-		return fail(CPVS_ECUDA, "cpvs_grid_worker_create: second context: %s", cpvs_last_error());
+	// (measured on the 256K^2 city, 4096 cells, one B200: 505 ms with two lanes, 473 with three, 461 with four, 451 with six; the
+	// 64K^2 terrain, whose tiles have two real slices, does not care)
+	int numLanes = 4;
+	if (const char* e = getenv("CPVS_GRID_LANES")) numLanes = atoi(e) < 1 ? 1 : (atoi(e) > 8 ? 8 : atoi(e));
+	w->lanes.push_back(ctx);
+	while ((int)w->lanes.size() < numLanes) {
+		cpvs_ctx* next = siblingContext(w->lanes.back());  // kept by the context: warm for the next worker
+		if (!next) {
+			cpvs_grid_worker_destroy(w);
+			return fail(CPVS_ECUDA, "cpvs_grid_worker_create: context %d: %s", (int)w->lanes.size(), cpvs_last_error());
+		}
+		w->lanes.push_back(next);
 	}
+	w->evLane.assign(w->lanes.size(), nullptr);
+	w->laneUsed.assign(w->lanes.size(), false);
+	for (cudaEvent_t& e : w->evLane)
+		if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+			cpvs_grid_worker_destroy(w);
+			return fail(CPVS_ECUDA, "cpvs_grid_worker_create: events");
+		}
 	*out = w;
 	return CPVS_OK;
 }
@@ -146,6 +180,9 @@ int cpvs_grid_worker_destroy(cpvs_grid_worker* w) {
 	if (w->hostStage) cudaFreeHost(w->hostStage);
 	if (w->exported) cudaFree(w->exported);
 	if (w->evJoin) cudaEventDestroy(w->evJoin);
+	if (w->evStage) cudaEventDestroy(w->evStage);
+	for (cudaEvent_t e : w->evLane)
+		if (e) cudaEventDestroy(e);
 	if (w->ev0) cudaEventDestroy(w->ev0);
 	if (w->ev1) cudaEventDestroy(w->ev1);
 	delete w;
@@ -223,49 +260,159 @@ int cpvs_grid_worker_release(cpvs_grid_worker* w, const uint32_t* xy, int count)
 	return CPVS_OK;
 }
 
-// createShadowTiles for the given xy tiles: depth tile (unless still resident from the estimate), pyramid, one DAG per z-slice.
-int cpvs_grid_worker_build(cpvs_grid_worker* w, const uint32_t* xy, int count) {
-	if (!w || (count > 0 && !xy)) return fail(CPVS_EINVAL, "cpvs_grid_worker_build: NULL argument");
+}  // extern "C"
+
+namespace {
+
+int tileMinLevel(const cpvs_grid_worker* w) {
+	int L = 1;
+	while ((1 << (L - 1)) < w->desc.tile) ++L;
+	return w->desc.leafmasks && (L - 3) >= 2 ? 2 : 0;
+}
+
+size_t tileIndex(cpvs_grid_worker* w, u32 x, u32 y) {
+	if (WorkerTile* t = findTile(w, x, y)) return (size_t)(t - w->tiles.data());
+	w->tiles.emplace_back();
+	w->tiles.back().x = x;
+	w->tiles.back().y = y;
+	return w->tiles.size() - 1;
+}
+
+// Enqueues, on the worker's own stream, everything a tile's slices start from: the depth tile (alone on the GPU, between two
+// events: its time is not the build's), the pyramid, and the node counts of the tile's column with their read-back.
+int prepareTile(cpvs_grid_worker* w, WorkerTile& t) {
+	cpvs_ctx* ctx = w->ctx;
+	if (!t.depth) {
+		for (size_t k = 1; k < w->lanes.size(); ++k)
+			if (w->laneUsed[k]) CPVS_CUDA(cudaStreamWaitEvent(ctx->stream, w->evLane[k], 0));
+		CPVS_CUDA(cudaEventCreate(&t.evDepth0));
+		CPVS_CUDA(cudaEventCreate(&t.evDepth1));
+		CPVS_CUDA(cudaEventRecord(t.evDepth0, ctx->stream));
+		if (int rc = produceDepth(w, t)) return rc;
+		CPVS_CUDA(cudaEventRecord(t.evDepth1, ctx->stream));
+		w->depthFence = t.evDepth1;
+	}
+	if (int rc = produceTile(w, t)) return rc;
+	return columnCountsBegin(ctx, t.mm, w->desc.length, tileMinLevel(w));
+}
+
+// One DAG per z-slice; the slices that are real builds take turns on the lanes.
+int enqueueSlices(cpvs_grid_worker* w, WorkerTile& t) {
+	const u32 len = w->desc.length;
+	t.cells.assign(len, nullptr);
+	if (w->depthFence)
+		for (size_t k = 1; k < w->lanes.size(); ++k) CPVS_CUDA(cudaStreamWaitEvent(w->lanes[k]->stream, w->depthFence, 0));
+	for (u32 z = 0; z < len; ++z) {
+		if (int rc = cpvs_shadow_create_async(w->lanes[w->nextLane], t.mm, z, len, w->desc.leafmasks, &t.cells[z])) return rc;
+		if (t.cells[z]->pending) {  // (one-word slices cost nothing)
+			w->laneUsed[w->nextLane] = true;
+			w->nextLane = (w->nextLane + 1) % (u32)w->lanes.size();
+		}
+	}
+	for (size_t k = 1; k < w->lanes.size(); ++k)
+		if (w->laneUsed[k]) CPVS_CUDA(cudaEventRecord(w->evLane[k], w->lanes[k]->stream));
+	return CPVS_OK;
+}
+
+int finishTile(cpvs_grid_worker* w, WorkerTile& t) {
+	for (cpvs_shadow* s : t.cells)
+		if (int rc = shadowWaitBegin(s)) return rc;
+	for (cpvs_shadow* s : t.cells)
+		if (int rc = cpvs_shadow_wait(s)) return rc;
+	if (t.evDepth0) {
+		float ms = 0.f;
+		CPVS_CUDA(cudaEventSynchronize(t.evDepth1));
+		CPVS_CUDA(cudaEventElapsedTime(&ms, t.evDepth0, t.evDepth1));
+		w->depthMs += ms;
+		w->depthInSpanMs += ms;
+	}
+	releaseInputs(w, t);
+	t.built = true;
+	++w->built;
+	return CPVS_OK;
+}
+
+struct TileList {
+	const uint32_t* xy;
+	int count, at;
+};
+int nextFromList(void* user, uint32_t* x, uint32_t* y) {
+	TileList* l = static_cast<TileList*>(user);
+	if (l->at >= l->count) return 0;
+	*x = l->xy[2 * l->at];
+	*y = l->xy[2 * l->at + 1];
+	++l->at;
+	return 1;
+}
+
+}  // namespace
+
+extern "C" {
+
+// createShadowTiles for the xy tiles `next` hands out (returns 0 when there are no more): depth tile (unless still resident from
+// the estimate), pyramid, one DAG per z-slice. Two tiles are in flight: the next tile is asked for, and its depth, pyramid and
+// counts are enqueued, before the slices of the current one, so the host never waits for the counts and the GPU never for the host.
+int cpvs_grid_worker_build_from(cpvs_grid_worker* w, cpvs_next_tile_fn next, void* user) {
+	if (!w || !next) return fail(CPVS_EINVAL, "cpvs_grid_worker_build_from: NULL argument");
 	cpvs_ctx* ctx = w->ctx;
 	CPVS_CUDA(cudaSetDevice(ctx->device));
-	for (int i = 0; i < count; ++i) {
-		WorkerTile* t = findTile(w, xy[2 * i], xy[2 * i + 1]);
-		if (!t) {
-			w->tiles.emplace_back();
-			t = &w->tiles.back();
-			t->x = xy[2 * i];
-			t->y = xy[2 * i + 1];
+	const size_t none = ~(size_t)0;
+	auto take = [&](size_t* idx) {
+		*idx = none;
+		uint32_t x = 0, y = 0;
+		while (next(user, &x, &y)) {
+			if (x >= w->desc.length || y >= w->desc.length) return fail(CPVS_EINVAL, "cpvs_grid_worker_build: tile (%u,%u) of %u", x, y, w->desc.length);
+			const size_t i = tileIndex(w, x, y);
+			if (w->tiles[i].built) continue;
+			*idx = i;
+			break;
 		}
-		if (t->built) continue;
-		// the depth tile first (its own clock: the build metric starts from depth resident in device memory)
-		if (!t->depth) {
-			CPVS_CUDA(cudaEventRecord(w->ev0, ctx->stream));
-			if (int rc = produceDepth(w, *t)) return rc;
-			CPVS_CUDA(cudaEventRecord(w->ev1, ctx->stream));
-			CPVS_CUDA(cudaEventSynchronize(w->ev1));
-			float ms = 0.f;
-			CPVS_CUDA(cudaEventElapsedTime(&ms, w->ev0, w->ev1));
-			w->depthMs += ms;
-		}
-		CPVS_CUDA(cudaEventRecord(w->ev0, ctx->stream));
-		if (int rc = produceTile(w, *t)) return rc;
-		t->cells.assign(w->desc.length, nullptr);
-		for (u32 z = 0; z < w->desc.length; ++z)
-			if (int rc = cpvs_shadow_create_async((z & 1u) ? w->ctx2 : ctx, t->mm, z, w->desc.length, w->desc.leafmasks, &t->cells[z])) return rc;
-		for (u32 z = 0; z < w->desc.length; ++z)
-			if (int rc = cpvs_shadow_wait(t->cells[z])) return rc;
-		CPVS_CUDA(cudaEventRecord(w->evJoin, w->ctx2->stream));
-		CPVS_CUDA(cudaStreamWaitEvent(ctx->stream, w->evJoin, 0));
-		CPVS_CUDA(cudaEventRecord(w->ev1, ctx->stream));
-		CPVS_CUDA(cudaEventSynchronize(w->ev1));
-		float ms = 0.f;
-		CPVS_CUDA(cudaEventElapsedTime(&ms, w->ev0, w->ev1));
-		w->deviceMs += ms;
-		releaseInputs(w, *t);
-		t->built = true;
-		++w->built;
+		return (int)CPVS_OK;
+	};
+	size_t prev = none, cur = none, nxt = none;
+	if (int rc = take(&cur)) return rc;
+	if (cur == none) return CPVS_OK;
+	w->depthInSpanMs = 0.f;
+	const bool trace = getenv("CPVS_TRACE") != nullptr;  // host time per step of the loop
+	double tPrepare = 0, tEnqueue = 0, tFinish = 0, t0 = trace ? nowMs() : 0;
+	auto lap = [&](double& into) {
+		if (!trace) return;
+		const double t = nowMs();
+		into += t - t0;
+		t0 = t;
+	};
+	CPVS_CUDA(cudaEventRecord(w->ev0, ctx->stream));
+	if (int rc = prepareTile(w, w->tiles[cur])) return rc;
+	while (cur != none) {
+		if (int rc = take(&nxt)) return rc;
+		if (nxt != none)
+			if (int rc = prepareTile(w, w->tiles[nxt])) return rc;
+		lap(tPrepare);
+		if (int rc = enqueueSlices(w, w->tiles[cur])) return rc;
+		lap(tEnqueue);
+		if (prev != none)
+			if (int rc = finishTile(w, w->tiles[prev])) return rc;
+		lap(tFinish);
+		prev = cur;
+		cur = nxt;
 	}
+	if (int rc = finishTile(w, w->tiles[prev])) return rc;
+	lap(tFinish);
+	if (trace) fprintf(stderr, "[cpvs trace] grid worker: host %.2f ms preparing tiles, %.2f ms enqueueing slices, %.2f ms finishing tiles\n", tPrepare, tEnqueue, tFinish);
+	for (size_t k = 1; k < w->lanes.size(); ++k)
+		if (w->laneUsed[k]) CPVS_CUDA(cudaStreamWaitEvent(ctx->stream, w->evLane[k], 0));
+	CPVS_CUDA(cudaEventRecord(w->ev1, ctx->stream));
+	CPVS_CUDA(cudaEventSynchronize(w->ev1));
+	float ms = 0.f;
+	CPVS_CUDA(cudaEventElapsedTime(&ms, w->ev0, w->ev1));
+	w->deviceMs += ms - w->depthInSpanMs;
 	return CPVS_OK;
+}
+
+int cpvs_grid_worker_build(cpvs_grid_worker* w, const uint32_t* xy, int count) {
+	if (!w || (count > 0 && !xy)) return fail(CPVS_EINVAL, "cpvs_grid_worker_build: NULL argument");
+	TileList list{xy, count, 0};
+	return cpvs_grid_worker_build_from(w, nextFromList, &list);
 }
 
 int cpvs_grid_worker_num_cells(const cpvs_grid_worker* w) { return w ? (int)(w->built * w->desc.length) : 0; }
@@ -509,14 +656,25 @@ int cpvs_grid_build(const int* devices, int numDevices, const cpvs_grid_desc* de
 	{
 		const std::vector<int> startOwner = owner;
 		std::atomic<int> next(0);
+		struct Queue {
+			std::atomic<int>* next;
+			const std::vector<int>* order;
+			const std::vector<uint32_t>* xy;
+			std::vector<int>* owner;
+			int worker;
+		};
 		const int rc = runOnWorkers(workers, [&](int i, cpvs_grid_worker* w) {
-			for (;;) {
-				const int k = next.fetch_add(1);
-				if (k >= numTiles) return (int)CPVS_OK;
-				const int t = order[k];
-				owner[t] = i;
-				if (int e = cpvs_grid_worker_build(w, &xy[2 * t], 1)) return e;
-			}
+			Queue q{&next, &order, &xy, &owner, i};
+			return cpvs_grid_worker_build_from(w, [](void* user, uint32_t* x, uint32_t* y) {
+				Queue* q = static_cast<Queue*>(user);
+				const int k = q->next->fetch_add(1);
+				if (k >= (int)q->order->size()) return 0;
+				const int t = (*q->order)[k];
+				(*q->owner)[t] = q->worker;
+				*x = (*q->xy)[2 * t];
+				*y = (*q->xy)[2 * t + 1];
+				return 1;
+			}, &q);
 		});
 		if (rc) return cleanup(rc);
 		for (int t = 0; t < numTiles; ++t) {

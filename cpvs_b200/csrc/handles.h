@@ -65,6 +65,7 @@ struct cpvs_ctx {
 	// Pinned read-back buffers (kNumScalars words each), one per build in flight: taken when a build is enqueued, returned
 	// when it is finished; the pool grows when more builds are in flight than it has buffers.
 	std::vector<cpvs::u64*> readbackFree, readbackAll;
+	std::vector<cpvs::u64*> countBuffers;  // pinned, kPooledCountSlices * kMaxLevels words each (column counts in flight); under cacheLock
 	// High-priority side stream for the chain of inserts (the critical path of the merge): its CTAs are dispatched
 	// ahead of the queued CTAs of the rank scans and the leaf emission running beside it. Fork/join through events.
 	cudaStream_t aux;
@@ -78,6 +79,7 @@ struct cpvs_ctx {
 	int predictSizes; // 1 (default): size builds from the memo of the last build of the same shape; 0: always count first (CPVS_PREDICT=0; tests)
 	unsigned headroomShift;  // capacities = predicted + (predicted >> headroomShift) + slack
 	std::vector<cpvs::SizeMemo> memos;
+	std::mutex memoLock;  // memos are also read by the other contexts of the family
 	cpvs::u64 predictedBuilds, exactBuilds, overflowRebuilds, reemissions;  // statistics (cpvs_ctx_stats)
 	// Sides of the depth maps whose last build did NOT use the per-column leaf builder (cities, planes): hierarchies of
 	// that side skip the column residues, which only that builder reads.
@@ -89,9 +91,15 @@ struct cpvs_ctx {
 	std::vector<std::pair<void*, size_t>> freeBlocks;  // oldest first
 	std::unordered_map<void*, size_t> liveBlocks;
 	size_t cachedBytes;
+	// Staging buffers for DAGs whose size is only bounded when they are emitted (build.cu): (pointer, words), under cacheLock.
+	std::vector<std::pair<cpvs::u32*, cpvs::u64>> stagingFree;
+	cpvs::u64 stagingWords;  // the size new staging buffers get
+	cudaStream_t copyStream;  // copies finished DAGs out of them, behind nothing else; their final allocations are made and released on it
+	cudaEvent_t evCopyFree;
 	// A second context on the same GPU, created on demand and kept (cpvs::siblingContext): independent builds -- the z-slices
 	// of a tile -- alternate between the two so that their kernels run side by side.
 	cpvs_ctx* sibling;
+	cpvs_ctx* family;  // the first context of the chain of siblings this one belongs to (itself, if it was created by the caller)
 	cpvs::u64 buildSerial;  // builds enqueued so far: a pending build whose serial is the latest still owns the arena's contents
 };
 
@@ -116,6 +124,14 @@ struct cpvs_minmax {
 	cpvs::u32 columnSlices;
 	int columnMinLevel;
 	std::vector<cpvs::u64> columnCounts;  // [z * kMaxLevels + level]; [z * kMaxLevels + kRootMaskScalar] = 1 << 32 | root mask
+	// Counts in flight (columnCountsBegin): the pinned buffer they are read back into, taken from `countsCtx`'s pool when
+	// `countsPooled`, and the event that says they have arrived.
+	cpvs::u64* countsPinned = nullptr;
+	bool countsPooled = false;
+	cpvs_ctx* countsCtx = nullptr;
+	cudaEvent_t evCounts = nullptr;
+	cpvs::u32 pendingSlices = 0;
+	int pendingMinLevel = -1;
 };
 
 namespace cpvs {
@@ -145,6 +161,8 @@ struct cpvs_shadow {
 	std::string statusText;
 	cpvs::u32* dag;       // first word of the DAG
 	cpvs::u32* dagAlloc;  // the allocation it lives in (a predicted capacity; the DAG sits at its end)
+	bool copyInFlight;    // the DAG is still being copied out of its staging buffer (between shadowWaitBegin and cpvs_shadow_wait)
+	bool dagOnCopyStream; // dagAlloc was allocated on the context's copy stream (a staged build) and is released there
 	cudaEvent_t ready;    // recorded on the building stream once the words are written (consumers on other streams wait for it)
 	cpvs_shadow_info info;
 	// lookup shortcut over the top levels, built on the first lookup (see LookupDag::skip)
@@ -185,9 +203,18 @@ namespace cpvs {
 // capi.cu: stream-ordered blocks on the context's stream, recycled by size (see cpvs_ctx::freeBlocks).
 cudaError_t ctxAlloc(cpvs_ctx* ctx, void** out, size_t bytes);
 void ctxFree(cpvs_ctx* ctx, void* p);
+void ctxAdopt(cpvs_ctx* ctx, void* p, size_t bytes);  // a pool allocation made elsewhere becomes one ctxFree may recycle
 cpvs_ctx* siblingContext(cpvs_ctx* ctx);  // NULL if it cannot be created
 // capi.cu: levels 1 and 2 of a hierarchy on demand.
 int ensureLowLevels(const cpvs_minmax* mm, int level);
+// Node counts of all z-slices of the hierarchy's column (build.cu): Begin enqueues the launch and its read-back on the context's
+// stream, Of waits for them (and begins them if nobody has). counts: [z * kMaxLevels + level].
+int columnCountsBegin(cpvs_ctx* ctx, const cpvs_minmax* mm, u32 zTileNum, int minLevel);
+int columnCountsOf(cpvs_ctx* ctx, const cpvs_minmax* mm, u32 zTileNum, int minLevel, const u64** counts);
+void releaseCountsBuffer(cpvs_minmax* mm);
+// cpvs_shadow_wait in two halves, for callers that finish several builds at once: Begin does everything but wait for the copy of
+// a staged DAG into its final allocation; cpvs_shadow_wait afterwards waits for it (one wait serves all the copies of a context).
+int shadowWaitBegin(cpvs_shadow* s);
 // build.cu: a new shadow handle around `words` device words (NULL: allocate one word and store `rootMask` there).
 PyramidView pyramidView(const cpvs_minmax* mm);
 }  // namespace cpvs

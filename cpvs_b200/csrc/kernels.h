@@ -182,6 +182,8 @@ struct EmitMultiArgs {
 int launchEmitInnerLevels(EmitMultiArgs& a, cudaStream_t stream);
 // bases[l] for l = top..minLevel from words[l]; total -> *totalWords; sets kOverflowWords in *overflow if the total
 // exceeds `capacity`; *rootWord = the root's mask (the DAG's first word). One thread.
+// dst[0..words) = src[0..words); both pointers equally aligned within 16 bytes.
+int launchCopyWords(u32* dst, const u32* src, u64 words, cudaStream_t stream);
 int launchLevelBases(const u64* words, u64* bases, int topLevel, int minLevel, u64* totalWords, u64 capacity, u32* overflow, const u16* rootMask,
 		u32* rootWord, cudaStream_t stream);
 

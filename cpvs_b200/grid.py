@@ -13,6 +13,7 @@ from . import CpvsError, EINVAL, SCENES, _check, load_library, CompressedShadowC
 
 MAX_DEVICES = 16
 FETCH_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_float))
+NEXT_TILE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32))
 
 
 class GridDesc(ctypes.Structure):
@@ -155,6 +156,27 @@ class GridWorker:
     def build(self, tiles):
         arr, n = self._pairs(tiles)
         _check(self._lib.cpvs_grid_worker_build(self.handle, arr, n))
+
+    def build_from(self, next_tile):
+        """Builds the tiles ``next_tile()`` hands out -- (x, y), or None when there are no more (a shared queue). It is called one
+        tile ahead of the build (``cpvs_grid_worker_build_from``)."""
+        error = []
+
+        def pull(_user, x, y):
+            try:
+                t = next_tile()
+            except Exception as e:  # noqa: BLE001 -- must not unwind through the C frames
+                error.append(e)
+                return 0
+            if t is None:
+                return 0
+            x[0], y[0] = int(t[0]), int(t[1])
+            return 1
+
+        cb = NEXT_TILE_FN(pull)
+        _check(self._lib.cpvs_grid_worker_build_from(self.handle, cb, None))
+        if error:
+            raise error[0]
 
     def cells(self):
         n = self._lib.cpvs_grid_worker_num_cells(self.handle)

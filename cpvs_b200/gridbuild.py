@@ -97,12 +97,15 @@ def run(ctx, tile, length, kind, rank=0, world=1, group=None, lookups=3840 * 216
         _QUEUE_RUNS[key] = _QUEUE_RUNS.get(key, 0) + 1
         key += "_%d" % _QUEUE_RUNS[key]
         mine = []
-        while True:
+
+        def next_tile():
             k = store.add(key, 1) - 1
             if k >= len(tiles):
-                break
+                return None
             mine.append(tiles[k])
-            worker.build([tiles[k]])
+            return tiles[k]
+
+        worker.build_from(next_tile)
     else:
         mine = list(tiles)
         worker.build(mine)

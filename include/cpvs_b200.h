@@ -289,6 +289,11 @@ CPVS_API int cpvs_grid_worker_estimate(cpvs_grid_worker* w, const uint32_t* xy, 
 CPVS_API int cpvs_grid_worker_release(cpvs_grid_worker* w, const uint32_t* xy, int count);
 /* createShadowTiles (src/DeferredRenderer.cpp:150-163) for `count` xy tiles: hierarchy + one DAG per z-slice, kept on the GPU. */
 CPVS_API int cpvs_grid_worker_build(cpvs_grid_worker* w, const uint32_t* xy, int count);
+/* The same for tiles handed out one by one (a shared queue): `next` fills (x, y) and returns 1, or returns 0 when there are no
+ * more. It is called one tile ahead: the next tile's depth, pyramid and node counts are enqueued before the current tile's
+ * slices, so that the host never waits for the GPU between tiles. */
+typedef int (*cpvs_next_tile_fn)(void* user, uint32_t* x, uint32_t* y);
+CPVS_API int cpvs_grid_worker_build_from(cpvs_grid_worker* w, cpvs_next_tile_fn next, void* user);
 CPVS_API int cpvs_grid_worker_num_cells(const cpvs_grid_worker* w);
 /* The finished cells (returns their number, < 0 on error). */
 CPVS_API int cpvs_grid_worker_cells(const cpvs_grid_worker* w, cpvs_grid_cell* out, int capacity);

@@ -84,6 +84,62 @@ def test_grid_fetch_callback_and_assemble(gpu_ctx, oracle):
         worker.close()
 
 
+def _cells_by_index(worker):
+    cells = worker.cells()
+    offsets = worker.copy_cells(None)
+    total = (offsets[-1] + int(cells[-1].words)) if cells else 0
+    words = np.zeros(max(1, total), dtype=np.uint32)
+    worker.copy_cells(words)
+    return {int(c.index): words[o:o + int(c.words)].copy() for c, o in zip(cells, offsets)}
+
+
+@pytest.mark.parametrize("kind,length,tile", [("city", 4, 256), ("terrain_dev", 2, 512)])
+def test_worker_pulls_tiles_from_a_queue(kind, length, tile):
+    """cpvs_grid_worker_build_from: two workers of one GPU pull their tiles from one shared queue (each asks one tile ahead
+    of its build); the cells equal those of a worker that was handed the whole list."""
+    ctxs = [cpvs_b200.Context(0), cpvs_b200.Context(0)]
+    tiles = [(x, y) for y in range(length) for x in range(length)]
+    whole = cgrid.GridWorker(ctxs[0], length, tile, kind)
+    whole.build(tiles)
+    want = _cells_by_index(whole)
+    assert sorted(want) == list(range(length ** 3))
+
+    queue = list(tiles)
+    taken = [[], []]
+
+    def puller(i):
+        def next_tile():
+            if not queue:
+                return None
+            taken[i].append(queue.pop(0))
+            return taken[i][-1]
+        return next_tile
+
+    workers = [cgrid.GridWorker(c, length, tile, kind) for c in ctxs]
+    # alternate: a few tiles through worker 0, the rest through worker 1, then an empty pull
+    limited = iter(range(3))
+    workers[0].build_from(lambda: puller(0)() if next(limited, None) is not None else None)
+    workers[1].build_from(puller(1))
+    workers[0].build_from(puller(0))
+    assert len(taken[0]) == 3 and len(taken[0]) + len(taken[1]) == len(tiles)
+    got = {}
+    for worker in workers:
+        got.update(_cells_by_index(worker))
+    assert sorted(got) == sorted(want)
+    for i in want:
+        assert np.array_equal(got[i], want[i]), i
+    st = ctxs[0].stats()
+    assert st["overflow_rebuilds"] == 0 and st["reemissions"] == 0  # slices are emitted into staging buffers that cannot overflow
+
+    def failing():
+        raise RuntimeError("queue broke")
+
+    with pytest.raises(RuntimeError, match="queue broke"):
+        workers[1].build_from(failing)
+    for worker in workers + [whole]:
+        worker.close()
+
+
 def test_cpp_caller_builds_grids_on_several_workers(tmp_path):
     """tests/cpp/grid_test.cpp: a plain C++ program against include/cpvs_b200.h + libcpvs_b200.so."""
     import torch
