@@ -84,13 +84,11 @@ __global__ void __launch_bounds__(256) sizeAndClearLeafTableKernel(u64* __restri
 	for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += (u64)gridDim.x * blockDim.x) t2[i] = make_ulonglong2(kEmpty, kEmpty);
 }
 
-// Leaf insert. The chain per leaf is own code -> hash -> table probe -> witness code -> compare -> atomicMin: three to four
-// dependent memory round trips, and with one leaf per thread the kernel sat at 76 % long-scoreboard stalls with DRAM a
-// third busy (profiles/r1_stall_sites.md). Here a CTA stages the codes of 1024 consecutive leaves in shared memory with
-// cp.async (no registers, fully coalesced), every thread owns four of them, and each step of the chain is issued for all
-// four before any result is looked at -- probes, then CAS for the empty slots, then witness codes, then atomicMin --
-// in rounds until every leaf has found its group (linear probing: the rare leaf that must move on takes another round).
-// Same table, same keys, same first-occurrence rule as findGroupSlot.
+// Leaf insert, one leaf per thread. The chain per leaf is own code -> hash -> table probe -> witness code -> compare -> atomicMin:
+// three to four dependent memory round trips; the kernel runs at 32 registers and full occupancy, with the loads that do not
+// depend on the device-side size issued ahead of it. A staged variant (codes of 1024 leaves in shared memory through cp.async,
+// several leaves per thread, every step of the chain issued for all of them before any result is looked at) was measured and
+// removed: a warp then runs as many rounds as the longest probe chain among its leaves (profiles/r2_dropped.md).
 
 __device__ __forceinline__ u64 hashLeafCode(const uint4& a0, const uint4& a1) {
 	u64 h = 0x9E3779B97F4A7C15ull;
@@ -119,135 +117,6 @@ __global__ void __launch_bounds__(256, 8) insertLeavesKernel(const u32* __restri
 		const uint4 b0 = theirs[0], b1 = theirs[1];
 		return a0.x == b0.x && a0.y == b0.y && a0.z == b0.z && a0.w == b0.w && a1.x == b1.x && a1.y == b1.y && a1.z == b1.z && a1.w == b1.w;
 	});
-}
-
-template <int kLeafBatch>
-__global__ void __launch_bounds__(256) insertLeavesBatchKernel(const u32* __restrict__ codes, const u64* __restrict__ hashes, const u64* __restrict__ nDev,
-		u64* __restrict__ table, const u64* __restrict__ tableMaskDev, u32* __restrict__ slotOf, u32* errorFlag, const u32* __restrict__ overflow) {
-	constexpr int kInsertLeaves = 256 * kLeafBatch;
-	__shared__ __align__(16) uint4 sCode[kInsertLeaves * 2];
-	const u64 n = *nDev;
-	const u64 ctaBase = (u64)blockIdx.x * kInsertLeaves;
-	if (ctaBase >= n || (*overflow & kOverflowNodes)) return;  // the grid is sized for the level's capacity
-	const u32 tableMask = (u32)*tableMaskDev;
-	const u32 live = (u32)(n - ctaBase < (u64)kInsertLeaves ? n - ctaBase : (u64)kInsertLeaves);
-	{
-		const uint4* src = reinterpret_cast<const uint4*>(codes + ctaBase * 8);
-#pragma unroll
-		for (int i = 0; i < 2 * kLeafBatch; ++i) {
-			const u32 piece = threadIdx.x + 256u * i;
-			if (piece < live * 2u) {
-				const u32 dst = (u32)__cvta_generic_to_shared(&sCode[piece]);
-				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + piece) : "memory");
-			}
-		}
-		asm volatile("cp.async.commit_group;" ::: "memory");
-	}
-	u64 preHash[kLeafBatch];
-	if (hashes) {  // (per-leaf builder: the hash was stored next to the code)
-#pragma unroll
-		for (int i = 0; i < kLeafBatch; ++i) {
-			const u32 q = threadIdx.x + 256u * i;
-			preHash[i] = q < live ? __ldcs(hashes + ctaBase + q) : 0;
-		}
-	}
-	asm volatile("cp.async.wait_group 0;" ::: "memory");
-	__syncthreads();
-
-	u32 slot[kLeafBatch], fp[kLeafBatch], res[kLeafBatch];
-	u32 pending = 0;
-#pragma unroll
-	for (int i = 0; i < kLeafBatch; ++i) {
-		const u32 q = threadIdx.x + 256u * i;
-		res[i] = 0;
-		slot[i] = fp[i] = 0;
-		if (q < live) {
-			const u64 h = hashes ? preHash[i] : hashLeafCode(sCode[2 * q], sCode[2 * q + 1]);
-			fp[i] = (u32)(h >> 32);
-			slot[i] = (u32)h & tableMask;
-			pending |= 1u << i;
-		}
-	}
-	for (u32 round = 0; pending; ++round) {
-		if (round > tableMask || round >= kMaxProbes) {  // table full: cannot happen with a sane size estimate; reported to the host
-			atomicExch(errorFlag, 1u);
-			break;
-		}
-		u64 v[kLeafBatch];
-#pragma unroll
-		for (int i = 0; i < kLeafBatch; ++i)
-			if (pending & (1u << i)) v[i] = ldRelaxed64(table + slot[i]);
-		// empty slots: claim them (all CAS in flight together)
-		u64 cur[kLeafBatch];
-#pragma unroll
-		for (int i = 0; i < kLeafBatch; ++i) {
-			cur[i] = 0;
-			if (pending & (1u << i)) {
-				const u64 key = ((u64)fp[i] << 32) | (u32)(ctaBase + threadIdx.x + 256u * i);
-				cur[i] = v[i] == kEmpty ? atomicCAS(reinterpret_cast<unsigned long long*>(table + slot[i]), (unsigned long long)kEmpty, (unsigned long long)key)
-										: v[i];
-			}
-		}
-		u32 want = 0;
-#pragma unroll
-		for (int i = 0; i < kLeafBatch; ++i) {
-			if (!(pending & (1u << i))) continue;
-			if (v[i] == kEmpty && cur[i] == kEmpty) {  // ours now: the first of its group so far
-				res[i] = slot[i] | kCandidateFlag;
-				pending &= ~(1u << i);
-			} else if ((u32)(cur[i] >> 32) == fp[i]) {
-				want |= 1u << i;
-			}
-		}
-		// same fingerprint: compare with a member of the group (all witness codes in flight together)
-		uint4 w0[kLeafBatch], w1[kLeafBatch];
-#pragma unroll
-		for (int i = 0; i < kLeafBatch; ++i)
-			if (want & (1u << i)) {
-				const uint4* theirs = reinterpret_cast<const uint4*>(codes + (u64)(u32)cur[i] * 8);
-				w0[i] = theirs[0];
-				w1[i] = theirs[1];
-			}
-		u32 same = 0;
-#pragma unroll
-		for (int i = 0; i < kLeafBatch; ++i)
-			if (want & (1u << i)) {
-				const u32 q = threadIdx.x + 256u * i;
-				const uint4 a0 = sCode[2 * q], a1 = sCode[2 * q + 1];
-				if (a0.x == w0[i].x && a0.y == w0[i].y && a0.z == w0[i].z && a0.w == w0[i].w && a1.x == w1[i].x && a1.y == w1[i].y && a1.z == w1[i].z &&
-						a1.w == w1[i].w)
-					same |= 1u << i;
-			}
-		// the slot only ever decreases: nothing to do if an earlier node already holds it. A node that never lowered its
-		// slot cannot be the first occurrence; the ones that did are marked as candidates for the rank scan.
-		u64 before[kLeafBatch];
-#pragma unroll
-		for (int i = 0; i < kLeafBatch; ++i) {
-			before[i] = 0;
-			const u32 self = (u32)(ctaBase + threadIdx.x + 256u * i);
-			if ((same & (1u << i)) && (u32)cur[i] > self) {
-				const u64 key = ((u64)fp[i] << 32) | self;
-				before[i] = atomicMin(reinterpret_cast<unsigned long long*>(table + slot[i]), (unsigned long long)key);
-			}
-		}
-#pragma unroll
-		for (int i = 0; i < kLeafBatch; ++i) {
-			if (!(pending & (1u << i))) continue;
-			const u32 self = (u32)(ctaBase + threadIdx.x + 256u * i);
-			if (same & (1u << i)) {
-				const u64 key = ((u64)fp[i] << 32) | self;
-				res[i] = slot[i] | (((u32)cur[i] > self && before[i] > key) ? kCandidateFlag : 0u);
-				pending &= ~(1u << i);
-			} else {
-				slot[i] = (slot[i] + 1u) & tableMask;
-			}
-		}
-	}
-#pragma unroll
-	for (int i = 0; i < kLeafBatch; ++i) {
-		const u32 q = threadIdx.x + 256u * i;
-		if (q < live) slotOf[ctaBase + q] = res[i];
-	}
 }
 
 template <bool kShared = false>
@@ -618,14 +487,7 @@ int launchSizeLeafTable(u64* table, u64 maxSlots, const u64* setBits, u64* table
 int launchInsertLevel(const MergeLevelArgs& a, cudaStream_t stream) {
 	if (!a.cap) return 0;
 	const unsigned blocks = (unsigned)((a.cap + 255) / 256);
-	static const int batch = std::getenv("CPVS_LEAF_BATCH") ? std::atoi(std::getenv("CPVS_LEAF_BATCH")) : 0;  // dev switch
-	if (a.leaf && batch == 4)
-		insertLeavesBatchKernel<4><<<(unsigned)((a.cap + 1023) / 1024), 256, 0, stream>>>(a.leafCodes, a.leafHash, a.nDev, a.table, a.tableMaskDev, a.uid, a.errorFlag, a.overflow);
-	else if (a.leaf && batch == 2)
-		insertLeavesBatchKernel<2><<<(unsigned)((a.cap + 511) / 512), 256, 0, stream>>>(a.leafCodes, a.leafHash, a.nDev, a.table, a.tableMaskDev, a.uid, a.errorFlag, a.overflow);
-	else if (a.leaf && batch == 1)
-		insertLeavesBatchKernel<1><<<(unsigned)((a.cap + 255) / 256), 256, 0, stream>>>(a.leafCodes, a.leafHash, a.nDev, a.table, a.tableMaskDev, a.uid, a.errorFlag, a.overflow);
-	else if (a.leaf)
+	if (a.leaf)
 		insertLeavesKernel<<<blocks, 256, 0, stream>>>(a.leafCodes, a.leafHash, a.nDev, a.cap, a.table, a.tableMaskDev, a.uid, a.errorFlag, a.overflow);
 	else
 		insertInnerKernel<<<blocks, 256, 0, stream>>>(a.masks, a.firstChild, a.childUid, a.nDev, a.cap, a.table, a.tableSize - 1, a.uid, a.errorFlag, a.overflow);
