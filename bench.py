@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="do not run the nvidia-smi sampler (debugging)")
     ap.add_argument("--ref-sample", type=int, default=1024, help="side of one reference sample window")
+    ap.add_argument("--contexts", type=int, default=2, help="contexts of the GPU the timed loops alternate between")
     ap.add_argument("--in-flight", type=int, default=2,
                     help="builds in flight in the timed loops (cpvs_shadow_create_async on two contexts of the GPU); 0 = one synchronous build at a time")
     ap.add_argument("--no-configs3", action="store_true", help="skip the leafmasks on/off comparison (BASELINE configs[3])")
@@ -365,7 +366,7 @@ def run_own(args):
         dist.barrier()
     n, K, W = args.size, args.steps, args.warmup
     # two contexts on real (non-default) streams: the library enqueues on them and the CUDA events below are ordered against them
-    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    streams = [torch.cuda.Stream() for _ in range(max(1, args.contexts))]
     ctxs = [cpvs_b200.Context(local, stream=s.cuda_stream) for s in streams]
     clock = torch.cuda.Stream()
     torch.cuda.set_stream(streams[0])
