@@ -222,6 +222,7 @@ cpvs_shadow* newShadow(cpvs_ctx* ctx) {
 	s->skipLevels = 0;
 	s->pending = nullptr;
 	s->dagOnCopyStream = false;
+	s->dagAllocBytes = 0;
 	s->copyInFlight = false;
 	s->pendingLeafmasks = 0;
 	s->status = CPVS_OK;
@@ -338,6 +339,7 @@ u64 upperBoundWords(const u64* counts, int top, int minLevel, bool useLeaf) {
 	for (int l = top - 1; l >= minLevel && counts[l]; --l) words += 2 * counts[l] + (useLeaf && l == 2 ? 16 * counts[l] : 0);
 	return words;
 }
+constexpr size_t kDagKeepMinBytes = 1u << 20, kDagKeepMaxBytes = 16ull << 30, kDagKeepMaxBlocks = 256;  // cpvs_ctx::dagFree
 constexpr u64 kMaxStagingWords = 1ull << 29;  // 2 GiB: beyond that the DAG's size is predicted or waited for
 
 // A staging buffer of at least `words` words. All buffers of a context have one size, the largest bound seen so far plus a
@@ -915,8 +917,25 @@ int finishBuild(Build& b, cpvs_shadow* s, bool arenaIntact, bool* redo, bool def
 			u32* exact = nullptr;
 			const u32* from = b.dagAlloc + (b.dagCapacity - totalWords);
 			const u64 shift = (reinterpret_cast<uintptr_t>(from) & 15u) >> 2;  // same alignment on both sides: 16-byte copies
-			e = cudaMallocAsync(reinterpret_cast<void**>(&exact), (totalWords + shift) * sizeof(u32), ctx->copyStream);
+			size_t have = (totalWords + shift) * sizeof(u32);
+			{  // a released allocation of about this size, if there is one (under memory pressure the pool remaps pages: ~1 ms per 200 MB)
+				std::lock_guard<std::mutex> guard(ctx->cacheLock);
+				size_t best = ctx->dagFree.size();
+				for (size_t i = 0; i < ctx->dagFree.size(); ++i) {
+					const size_t bytes = ctx->dagFree[i].second;
+					if (bytes >= have && bytes - have <= have / 4 && (best == ctx->dagFree.size() || bytes < ctx->dagFree[best].second)) best = i;
+				}
+				if (best != ctx->dagFree.size()) {
+					exact = ctx->dagFree[best].first;
+					have = ctx->dagFree[best].second;
+					ctx->dagFreeBytes -= have;
+					ctx->dagFree.erase(ctx->dagFree.begin() + best);
+				}
+			}
+			e = exact ? cudaSuccess : cudaMallocAsync(reinterpret_cast<void**>(&exact), have, ctx->copyStream);
 			if (e != cudaSuccess) return fail(CPVS_ENOMEM, "DAG allocation of %llu words: %s", (unsigned long long)totalWords, cudaGetErrorString(e));
+			s->dagAllocBytes = have;
+			b.trace.mark("staged: allocation");
 			ctx->launches += launchCopyWords(exact + shift, from, totalWords, ctx->copyStream);
 			e = cudaGetLastError();
 			if (e == cudaSuccess && !deferCopy) e = cudaStreamSynchronize(ctx->copyStream);
@@ -925,7 +944,7 @@ int finishBuild(Build& b, cpvs_shadow* s, bool arenaIntact, bool* redo, bool def
 				cudaFreeAsync(exact, ctx->copyStream);
 				return fail(CPVS_ECUDA, "cpvs_shadow_create: %s", cudaGetErrorString(e));
 			}
-			b.trace.mark("staged: allocation, copy, sync");
+			b.trace.mark("staged: copy (+ wait)");
 			s->dagAlloc = exact;
 			s->dag = exact + shift;  // (the staging buffer goes back to the context with the Build)
 			s->dagOnCopyStream = true;
@@ -1188,9 +1207,25 @@ int cpvs_shadow_destroy(cpvs_shadow* s) {
 	if (s->dagOnCopyStream) {
 		// allocated on the copy stream and given back there, so that the next such allocation finds it without depending on
 		// what the build stream still has queued -- behind the work enqueued on the build stream so far, like every release
-		cudaEventRecord(s->ctx->evCopyFree, s->ctx->stream);
-		cudaStreamWaitEvent(s->ctx->copyStream, s->ctx->evCopyFree, 0);
-		cudaFreeAsync(s->dagAlloc, s->ctx->copyStream);
+		cpvs_ctx* ctx = s->ctx;
+		cudaEventRecord(ctx->evCopyFree, ctx->stream);
+		cudaStreamWaitEvent(ctx->copyStream, ctx->evCopyFree, 0);
+		std::vector<u32*> drop;
+		{
+			std::lock_guard<std::mutex> guard(ctx->cacheLock);
+			if (s->dagAllocBytes >= kDagKeepMinBytes) {
+				ctx->dagFree.emplace_back(s->dagAlloc, s->dagAllocBytes);
+				ctx->dagFreeBytes += s->dagAllocBytes;
+			} else {
+				drop.push_back(s->dagAlloc);
+			}
+			while (!ctx->dagFree.empty() && (ctx->dagFreeBytes > kDagKeepMaxBytes || ctx->dagFree.size() > kDagKeepMaxBlocks)) {
+				drop.push_back(ctx->dagFree.front().first);
+				ctx->dagFreeBytes -= ctx->dagFree.front().second;
+				ctx->dagFree.erase(ctx->dagFree.begin());
+			}
+		}
+		for (u32* p : drop) cudaFreeAsync(p, ctx->copyStream);
 	} else {
 		ctxFree(s->ctx, s->dagAlloc);
 	}

@@ -153,6 +153,7 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 	ctx->own = ctx->aux = ctx->aux2 = ctx->aux3 = ctx->aux4 = ctx->copyStream = nullptr;
 	ctx->cachedBytes = 0;
 	ctx->stagingWords = 0;
+	ctx->dagFreeBytes = 0;
 	ctx->sibling = nullptr;
 	ctx->family = ctx;
 	ctx->predictedBuilds = ctx->exactBuilds = ctx->overflowRebuilds = ctx->reemissions = 0;
@@ -211,6 +212,9 @@ int cpvs_ctx_destroy(cpvs_ctx* ctx) {
 	for (u64* buf : ctx->countBuffers) cudaFreeHost(buf);
 	for (auto& block : ctx->stagingFree) cudaFreeAsync(block.first, ctx->stream);
 	ctx->stagingFree.clear();
+	for (auto& block : ctx->dagFree) cudaFreeAsync(block.first, ctx->copyStream);
+	ctx->dagFree.clear();
+	if (ctx->copyStream) cudaStreamSynchronize(ctx->copyStream);
 	for (cudaStream_t st : {ctx->aux, ctx->aux2, ctx->aux3, ctx->aux4, ctx->copyStream, ctx->own})
 		if (st) cudaStreamDestroy(st);
 	for (cudaEvent_t ev : {ctx->evFork, ctx->evJoin, ctx->evJoin3, ctx->evClear, ctx->evCols, ctx->evLeafRanked, ctx->evLeafEmitted, ctx->evCopyFree})

@@ -94,6 +94,10 @@ struct cpvs_ctx {
 	// Staging buffers for DAGs whose size is only bounded when they are emitted (build.cu): (pointer, words), under cacheLock.
 	std::vector<std::pair<cpvs::u32*, cpvs::u64>> stagingFree;
 	cpvs::u64 stagingWords;  // the size new staging buffers get
+	// Allocations of finished staged DAGs (>= 1 MB) that were released, kept for the next DAG of about that size (the same
+	// grid built again asks for exactly these sizes): (pointer, bytes), oldest first, under cacheLock. They belong to the copy stream.
+	std::vector<std::pair<cpvs::u32*, size_t>> dagFree;
+	size_t dagFreeBytes;
 	cudaStream_t copyStream;  // copies finished DAGs out of them, behind nothing else; their final allocations are made and released on it
 	cudaEvent_t evCopyFree;
 	// A second context on the same GPU, created on demand and kept (cpvs::siblingContext): independent builds -- the z-slices
@@ -162,6 +166,7 @@ struct cpvs_shadow {
 	cpvs::u32* dag;       // first word of the DAG
 	cpvs::u32* dagAlloc;  // the allocation it lives in (a predicted capacity; the DAG sits at its end)
 	bool copyInFlight;    // the DAG is still being copied out of its staging buffer (between shadowWaitBegin and cpvs_shadow_wait)
+	size_t dagAllocBytes; // size of dagAlloc when dagOnCopyStream
 	bool dagOnCopyStream; // dagAlloc was allocated on the context's copy stream (a staged build) and is released there
 	cudaEvent_t ready;    // recorded on the building stream once the words are written (consumers on other streams wait for it)
 	cpvs_shadow_info info;
