@@ -556,8 +556,10 @@ def run_own(args):
             # Like the steps of the headline, a grid is built again and again (every frame the light moves): the first pass is the
             # warm-up -- the scratch arenas, staging buffers and size memos of every context grow to the grid's heaviest slice -- and
             # is listed, not counted. The 64K^2 grid is a few milliseconds of work per GPU at N = 8: three timed passes, the median
-            # is reported and all are listed (one descheduled host thread is a fifth of such a build); the 256K^2 grid: two.
-            passes = 4 if name == "64k" else 3
+            # is reported and all are listed (one descheduled host thread is a fifth of such a build). The 256K^2 grid hands its
+            # tiles out through the shared queue, so a rank meets other tiles in every pass: its second pass is still warming up
+            # (N = 8: 307, 97, 61 ms), hence three timed passes there too.
+            passes = 4
             reps = [gridbuild.run(ctx, args.grid_tile, length, kind, rank, world, gloo, lookups=3840 * 2160, lookup_iters=4, verify=(r == 0),
                                   replicate=(r == 0)) for r in range(passes)]
             by_time = sorted(reps[1:], key=lambda g: g["build_ms_max_rank"])
