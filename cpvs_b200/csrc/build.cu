@@ -350,9 +350,12 @@ cudaError_t takeStaging(cpvs_ctx* ctx, u64 words, u32** out, u64* have) {
 	u64 size = 0;
 	*out = nullptr;
 	{
+		{  // one size for the whole family: the lanes of a grid worker meet the same slices sooner or later
+			std::lock_guard<std::mutex> familyGuard(ctx->family->sizeLock);
+			if (words > ctx->family->stagingWords) ctx->family->stagingWords = words + (words >> 2);
+			size = ctx->family->stagingWords;
+		}
 		std::lock_guard<std::mutex> guard(ctx->cacheLock);
-		if (words > ctx->stagingWords) ctx->stagingWords = words + (words >> 2);
-		size = ctx->stagingWords;
 		while (!ctx->stagingFree.empty() && !*out) {
 			if (ctx->stagingFree.back().second >= size) {
 				*out = ctx->stagingFree.back().first;
@@ -479,11 +482,18 @@ int carveArena(Build& b) {
 		ctx->arenaBytes = 0;
 		size_t want = sizing.offset + sizing.offset / 4;
 		if (want < doubled) want = doubled;
+		{  // at least what another context of the family has already needed (the lanes of a grid worker take turns on the same slices)
+			std::lock_guard<std::mutex> familyGuard(ctx->family->sizeLock);
+			const size_t hint = ctx->family->familyArenaBytes < (8ull << 30) ? ctx->family->familyArenaBytes : (8ull << 30);  // (not a giant one-off build's)
+			if (want < hint) want = hint;
+		}
 		size_t freeBytes = 0, totalBytes = 0;
 		if (cudaMemGetInfo(&freeBytes, &totalBytes) == cudaSuccess && want > freeBytes / 2) want = sizing.offset + sizing.offset / 8;
 		cudaError_t ae = cudaMallocAsync(reinterpret_cast<void**>(&ctx->arena), want, b.st);
 		if (ae != cudaSuccess) return fail(CPVS_ENOMEM, "scratch arena of %zu bytes: %s", want, cudaGetErrorString(ae));
 		ctx->arenaBytes = want;
+		std::lock_guard<std::mutex> familyGuard(ctx->family->sizeLock);
+		if (ctx->family->familyArenaBytes < want) ctx->family->familyArenaBytes = want;
 	}
 	ArenaCarver real(ctx->arena);
 	carve(real);

@@ -153,6 +153,7 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 	ctx->own = ctx->aux = ctx->aux2 = ctx->aux3 = ctx->aux4 = ctx->copyStream = nullptr;
 	ctx->cachedBytes = 0;
 	ctx->stagingWords = 0;
+	ctx->familyArenaBytes = 0;
 	ctx->dagFreeBytes = 0;
 	ctx->sibling = nullptr;
 	ctx->family = ctx;

@@ -93,7 +93,9 @@ struct cpvs_ctx {
 	size_t cachedBytes;
 	// Staging buffers for DAGs whose size is only bounded when they are emitted (build.cu): (pointer, words), under cacheLock.
 	std::vector<std::pair<cpvs::u32*, cpvs::u64>> stagingFree;
-	cpvs::u64 stagingWords;  // the size new staging buffers get
+	cpvs::u64 stagingWords;  // the size new staging buffers get (kept in the family's first context, under sizeLock)
+	size_t familyArenaBytes; // the largest arena of the family so far (likewise)
+	std::mutex sizeLock;
 	// Allocations of finished staged DAGs (>= 1 MB) that were released, kept for the next DAG of about that size (the same
 	// grid built again asks for exactly these sizes): (pointer, bytes), oldest first, under cacheLock. They belong to the copy stream.
 	std::vector<std::pair<cpvs::u32*, size_t>> dagFree;
