@@ -340,7 +340,8 @@ u64 upperBoundWords(const u64* counts, int top, int minLevel, bool useLeaf) {
 	return words;
 }
 constexpr size_t kDagKeepMinBytes = 1u << 20, kDagKeepMaxBytes = 16ull << 30, kDagKeepMaxBlocks = 256;  // cpvs_ctx::dagFree
-constexpr u64 kMaxStagingWords = 1ull << 29;  // 2 GiB: beyond that the DAG's size is predicted or waited for
+// Bounds above cpvs_ctx::stagingMaxWords (2 GiB of words; CPVS_STAGING_MAX_WORDS for tests) are not staged: the DAG's size is
+// then predicted from the memo, or waited for.
 
 // A staging buffer of at least `words` words. All buffers of a context have one size, the largest bound seen so far plus a
 // quarter: once a grid's heaviest slice has been seen, nothing is allocated any more (buffers of an earlier, smaller size are
@@ -792,7 +793,7 @@ int enqueueBuild(Build& b, const u64* exactCounts, const SizeMemo* memo, cudaEve
 	// merge; otherwise it is made once the sizes are known.
 	if (exactCounts && ctx->predictSizes) {
 		const u64 bound = upperBoundWords(exactCounts, b.top, b.minLevel, b.useLeaf);
-		if (bound <= kMaxStagingWords) {
+		if (bound <= ctx->stagingMaxWords) {
 			cudaError_t e = takeStaging(ctx, bound, &b.dagAlloc, &b.stagingWords);
 			if (e != cudaSuccess) return fail(CPVS_ENOMEM, "DAG staging buffer of %llu words: %s", (unsigned long long)bound, cudaGetErrorString(e));
 			b.staged = true;
@@ -1025,7 +1026,7 @@ int buildExact(cpvs_ctx* ctx, const cpvs_minmax* mm, u32 zTileIndex, u32 zTileNu
 	if (counts[top - 1] == 0) return oneWordShadow(ctx, L, useLeaf, (u32)counts[kRootMaskScalar], s);
 	++ctx->exactBuilds;
 	++ctx->buildSerial;
-	async = async && (memo || upperBoundWords(counts, top, minLevel, useLeaf) <= kMaxStagingWords);
+	async = async && (memo || upperBoundWords(counts, top, minLevel, useLeaf) <= ctx->stagingMaxWords);
 	if (async) {
 		cpvs_pending_build* p = new (std::nothrow) cpvs_pending_build();
 		if (!p) return fail(CPVS_ENOMEM, "cpvs_shadow_create: host allocation");

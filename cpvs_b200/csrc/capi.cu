@@ -82,6 +82,7 @@ cpvs_ctx* siblingContext(cpvs_ctx* ctx) {
 		ctx->sibling->family = ctx->family;
 		ctx->sibling->predictSizes = ctx->predictSizes;
 		ctx->sibling->headroomShift = ctx->headroomShift;
+		ctx->sibling->stagingMaxWords = ctx->stagingMaxWords;
 		ctx->sibling->leafColumns = ctx->leafColumns;
 	}
 	return ctx->sibling;
@@ -169,6 +170,8 @@ int cpvs_ctx_create(int device, cpvs_ctx** out) {
 		const char* h = std::getenv("CPVS_HEADROOM_SHIFT");  // capacity = predicted + (predicted >> shift); tests use 30 to provoke overflows
 		ctx->headroomShift = (h && h[0] >= '0' && h[0] <= '9') ? (unsigned)std::atoi(h) : 3u;
 		if (ctx->headroomShift > 40) ctx->headroomShift = 40;
+		const char* m = std::getenv("CPVS_STAGING_MAX_WORDS");  // tests: 0 sends every build down the unstaged paths
+		ctx->stagingMaxWords = (m && m[0] >= '0' && m[0] <= '9') ? std::strtoull(m, nullptr, 10) : (1ull << 29);
 	}
 	cudaError_t e = cudaStreamCreateWithFlags(&ctx->own, cudaStreamNonBlocking);
 	if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&ctx->scalars), kNumScalars * sizeof(u64));

@@ -94,6 +94,7 @@ struct cpvs_ctx {
 	// Staging buffers for DAGs whose size is only bounded when they are emitted (build.cu): (pointer, words), under cacheLock.
 	std::vector<std::pair<cpvs::u32*, cpvs::u64>> stagingFree;
 	cpvs::u64 stagingWords;  // the size new staging buffers get (kept in the family's first context, under sizeLock)
+	cpvs::u64 stagingMaxWords;  // larger bounds are not staged
 	size_t familyArenaBytes; // the largest arena of the family so far (likewise)
 	std::mutex sizeLock;
 	// Allocations of finished staged DAGs (>= 1 MB) that were released, kept for the next DAG of about that size (the same

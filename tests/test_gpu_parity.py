@@ -611,6 +611,28 @@ def test_predicted_builds_keep_the_words(oracle, columns, monkeypatch):
             _assert_same_dag(g, oracle.Shadow(oracle.MinMax(d), 0, 1, leaf), ("predicted city", leaf, rep))
 
 
+@pytest.mark.parametrize("staging", ["default", "0"])
+def test_z_slices_in_flight_staged_and_unstaged(oracle, staging, monkeypatch):
+    """Builds with exact node counts (the z-slices of a tile) emit their DAG into a staging buffer bounded by those counts and
+    copy it into an allocation of its size; with staging switched off they take the older paths (capacity scaled from the memo
+    of another tile, re-emission or rebuild when it does not suffice; count-then-allocate without a memo). Several slices in
+    flight on two contexts, tiles of different weight one after the other: the words are the oracle's either way."""
+    if staging != "default":
+        monkeypatch.setenv("CPVS_STAGING_MAX_WORDS", staging)
+    ctxs = [cpvs_b200.Context(0), cpvs_b200.Context(0)]
+    n, zn = 512, 4
+    maps = [synth.depth_map("plane", n), synth.depth_map("terrain", n), synth.depth_map("city", n), synth.depth_map("terrain", n, (1, 0), 2)]
+    for i, d in enumerate(maps):
+        mm = cpvs_b200.MinMaxHierarchy(d, ctxs[0], zTileNum=zn)
+        om = oracle.MinMax(d)
+        flying = [cpvs_b200.CompressedShadow.create(mm, z, zn, ctx=ctxs[z & 1], wait=False) for z in range(zn)]
+        for z in reversed(range(zn)):  # finished out of order
+            _assert_same_dag(flying[z], oracle.Shadow(om, z, zn), ("slices", staging, i, z))
+    stats = [c.stats() for c in ctxs]
+    if staging == "default":
+        assert all(s["overflow_rebuilds"] == 0 and s["reemissions"] == 0 for s in stats), stats
+
+
 def test_prediction_overflow_falls_back_to_exact(oracle):
     """A map that outgrows the capacities predicted from its predecessor is rebuilt with exact counts; one that only outgrows
     the predicted DAG allocation is emitted again. Either way the words are the oracle's."""
