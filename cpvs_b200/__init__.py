@@ -58,6 +58,7 @@ SIGNATURES = {
     "cpvs_ctx_set_stream": (_I, [_VP, _VP]),
     "cpvs_ctx_get_stream": (_VP, [_VP]),
     "cpvs_ctx_reserve": (_I, [_VP, _U64]),
+    "cpvs_ctx_trim": (_I, [_VP]),
     "cpvs_ctx_synchronize": (_I, [_VP]),
     "cpvs_ctx_launch_count": (_U64, [_VP]),
     "cpvs_ctx_set_prediction": (_I, [_VP, _I, _U32]),
@@ -172,6 +173,10 @@ class Context:
     def reserve(self, nbytes):
         """Pre-grows the stream-ordered pool the finished DAGs are allocated from (see cpvs_ctx_reserve)."""
         _check(self._lib.cpvs_ctx_reserve(self.handle, int(nbytes)))
+
+    def trim(self):
+        """Releases the memory the context keeps for recycling (see cpvs_ctx_trim)."""
+        _check(self._lib.cpvs_ctx_trim(self.handle))
 
     def synchronize(self):
         _check(self._lib.cpvs_ctx_synchronize(self.handle))

@@ -43,7 +43,19 @@ cudaError_t ctxAlloc(cpvs_ctx* ctx, void** out, size_t bytes) {
 			return cudaSuccess;
 		}
 	}
-	const cudaError_t e = cudaMallocAsync(out, bytes, ctx->stream);
+	cudaError_t e = cudaMallocAsync(out, bytes, ctx->stream);
+	if (e == cudaErrorMemoryAllocation) {  // give back what this context keeps for recycling, then once more
+		cudaGetLastError();
+		std::vector<void*> drop;
+		{
+			std::lock_guard<std::mutex> guard(ctx->cacheLock);
+			for (auto& block : ctx->freeBlocks) drop.push_back(block.first);
+			ctx->freeBlocks.clear();
+			ctx->cachedBytes = 0;
+		}
+		for (void* p : drop) cudaFreeAsync(p, ctx->stream);
+		e = cudaMallocAsync(out, bytes, ctx->stream);
+	}
 	if (e == cudaSuccess && bytes >= kCacheMinBytes) {
 		std::lock_guard<std::mutex> guard(ctx->cacheLock);
 		ctx->liveBlocks[*out] = bytes;
@@ -251,6 +263,34 @@ int cpvs_ctx_reserve(cpvs_ctx* ctx, uint64_t bytes) {
 	CPVS_CUDA(cudaMallocAsync(&p, bytes, ctx->stream));
 	CPVS_CUDA(cudaFreeAsync(p, ctx->stream));  // stays cached: the pool's release threshold is unlimited
 	CPVS_CUDA(cudaStreamSynchronize(ctx->stream));
+	return CPVS_OK;
+}
+
+int cpvs_ctx_trim(cpvs_ctx* ctx) {
+	if (!ctx) return fail(CPVS_EINVAL, "cpvs_ctx_trim: NULL context");
+	CPVS_CUDA(cudaSetDevice(ctx->device));
+	for (cpvs_ctx* c = ctx; c; c = c->sibling) {
+		std::lock_guard<std::mutex> build(c->buildLock);  // no build is being enqueued on this context meanwhile
+		std::vector<void*> onBuild, onCopy;
+		{
+			std::lock_guard<std::mutex> guard(c->cacheLock);
+			for (auto& block : c->freeBlocks) onBuild.push_back(block.first);
+			c->freeBlocks.clear();
+			c->cachedBytes = 0;
+			for (auto& block : c->stagingFree) onBuild.push_back(block.first);
+			c->stagingFree.clear();
+			for (auto& block : c->dagFree) onCopy.push_back(block.first);
+			c->dagFree.clear();
+			c->dagFreeBytes = 0;
+		}
+		for (void* p : onBuild) cudaFreeAsync(p, c->stream);
+		for (void* p : onCopy) cudaFreeAsync(p, c->copyStream);
+		CPVS_CUDA(cudaStreamSynchronize(c->stream));
+		CPVS_CUDA(cudaStreamSynchronize(c->copyStream));
+	}
+	cudaMemPool_t pool;
+	CPVS_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+	CPVS_CUDA(cudaMemPoolTrimTo(pool, 0));
 	return CPVS_OK;
 }
 

@@ -91,6 +91,10 @@ CPVS_API uint64_t cpvs_ctx_launch_count(const cpvs_ctx* ctx);
  * paying a fresh device allocation inside the build. Optional; HBM is 180 GB, a 4x4x4 grid of 16K^2 terrain
  * tiles keeps 3.8 GB of DAG words. */
 CPVS_API int cpvs_ctx_reserve(cpvs_ctx* ctx, uint64_t bytes);
+/* The opposite: releases everything the context (and the contexts it created for a grid worker) keeps for recycling -- pyramid
+ * and DAG blocks, staging buffers -- and trims the pool. Handles stay valid; the next builds allocate again. Waits for the
+ * context's streams. */
+CPVS_API int cpvs_ctx_trim(cpvs_ctx* ctx);
 /* cpvs_shadow_create sizes a build from the previous build of the same shape (side, z tile, leafmasks) on this context:
  * scratch, grids and the DAG's allocation come from those numbers plus head room (predicted + predicted >> headroom_shift),
  * so the build runs without asking the device for sizes first. Every kernel stays inside its capacities; a build that

@@ -134,6 +134,14 @@ def test_worker_pulls_tiles_from_a_queue(kind, length, tile):
     def failing():
         raise RuntimeError("queue broke")
 
+    # give the recycled memory back in the middle: the next build allocates again, same words
+    ctxs[0].trim()
+    again = cgrid.GridWorker(ctxs[0], length, tile, kind)
+    again.build(tiles[:2])
+    for i, words in _cells_by_index(again).items():
+        assert np.array_equal(words, want[i]), i
+    again.close()
+
     with pytest.raises(RuntimeError, match="queue broke"):
         workers[1].build_from(failing)
     for worker in workers + [whole]:
