@@ -194,6 +194,142 @@ __global__ void __launch_bounds__(256) evaluateKernel(LookupDag d, PixelSource i
 		io.out[i] = result;
 }
 
+// Two horizontally adjacent pixels per thread, for the single-tap lookup on the lookup copy. The descent is a chain of dependent
+// loads (shortcut grid, one node per level, the leaf); the two chains of a thread advance in lockstep, so every step has two
+// loads in flight, and neighbouring pixels share most of their path: the second load usually hits the line the first one fetched.
+struct PathState {
+	u32 node;
+	u32 result;  // 0 shadow, 1 lit once `done`
+	bool done;
+};
+__device__ __forceinline__ PathState beginSlots(const LookupDag& d, bool live, int px, int py, int pz) {
+	PathState st{0u, 0u, !live};
+	if (!live) return st;
+	if (d.grid) {  // traverse.cs:78-88
+		const u32 shift = d.dagLevels - 1, res = 1u << d.gridLevels;
+		const u32 cell = __ldg(d.grid + ((u32)(pz >> shift) * res + (u32)(py >> shift)) * res + (u32)(px >> shift));
+		if (cell == kCellShadowed || cell == kCellVisible) {
+			st.done = true;
+			st.result = cell == kCellVisible ? 1u : 0u;
+			return st;
+		}
+		st.node = cell;
+	}
+	if (d.skip) {
+		const u32 shift = d.dagLevels - 1 - d.skipLevels, res = 1u << (d.gridLevels + d.skipLevels);
+		const u32 entry = __ldg(d.skip + ((u32)(pz >> shift) * res + (u32)(py >> shift)) * res + (u32)(px >> shift));
+		if (entry == kSkipShadow || entry == kSkipVisible) {
+			st.done = true;
+			st.result = entry == kSkipVisible ? 1u : 0u;
+			return st;
+		}
+		st.node = entry;
+	}
+	return st;
+}
+
+// kQueries descents on the lookup copy in lockstep; result[q] = 0 shadow / 1 lit (dead queries: 0).
+template <int kQueries>
+__device__ __forceinline__ void lookupSlotsTogether(const LookupDag& d, const bool* live, const int* px, const int* py, const int* pz, u32* result) {
+	PathState st[kQueries];
+#pragma unroll
+	for (int q = 0; q < kQueries; ++q) st[q] = beginSlots(d, live[q], px[q], py[q], pz[q]);
+	const int startLevel = (int)d.dagLevels - 2 - (d.skip ? (int)d.skipLevels : 0);
+	const u32* __restrict__ nodes = d.dag;
+	for (int level = startLevel; level >= 3; --level) {
+		bool all = true;
+#pragma unroll
+		for (int q = 0; q < kQueries; ++q) all = all && st[q].done;
+		if (all) break;
+		u32 slot[kQueries];
+#pragma unroll
+		for (int q = 0; q < kQueries; ++q) {
+			const u32 idx = ((px[q] >> level) & 1) | (((py[q] >> level) & 1) << 1) | (((pz[q] >> level) & 1) << 2);
+			slot[q] = st[q].done ? 0u : __ldg(nodes + (size_t)st[q].node * 8u + idx);
+		}
+#pragma unroll
+		for (int q = 0; q < kQueries; ++q)
+			if (!st[q].done) {
+				if (slot[q] < 2u) {
+					st[q].done = true;
+					st[q].result = slot[q];
+				} else {
+					st[q].node = slot[q] - 2u;
+				}
+			}
+	}
+	u32 row[kQueries];
+#pragma unroll
+	for (int q = 0; q < kQueries; ++q) row[q] = st[q].done ? 0u : __ldg(d.leafCodes + (size_t)st[q].node * 8u + (u32)(py[q] & 7));
+#pragma unroll
+	for (int q = 0; q < kQueries; ++q)
+		result[q] = st[q].done ? st[q].result : ((u32)(pz[q] & 7) < ((row[q] >> (4 * (px[q] & 7))) & 15u) ? 1u : 0u);
+}
+
+constexpr int kPixelsPerThread = 2;  // measured on the 4K surface G-buffer: 1 -> 60.8, 2 -> 81.1, 3 -> 78.3, 4 -> 76.4 G lookups/s
+
+template <bool kSurface>
+__global__ void __launch_bounds__(256) evaluatePairsKernel(LookupDag d, PixelSource io, u32 width, u32 height, Mat4 mat) {
+	constexpr int kPixels = kPixelsPerThread;
+	const u32 x0 = (blockIdx.x * blockDim.x + threadIdx.x) * (u32)kPixels, y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x0 >= width || y >= height) return;
+	const size_t i = (size_t)y * width + x0;
+	const int resolution = (1 << (d.dagLevels + d.gridLevels - 1)) - 1;
+	int px[kPixels], py[kPixels], pz[kPixels];
+	bool live[kPixels];
+#pragma unroll
+	for (int q = 0; q < kPixels; ++q) {
+		live[q] = x0 + (u32)q < width;
+		const u32 xq = live[q] ? x0 + (u32)q : x0;
+		float4 p;
+		if (kSurface)
+			p = surf2Dread<float4>(io.posSurface, (int)(xq * sizeof(float4)), (int)y);
+		else
+			p = io.pos[(size_t)y * width + xq];
+		float v[4];
+#pragma unroll
+		for (int r = 0; r < 4; ++r)
+			v[r] = __fadd_rn(__fadd_rn(__fmul_rn(mat.m[r], p.x), __fmul_rn(mat.m[4 + r], p.y)), __fadd_rn(__fmul_rn(mat.m[8 + r], p.z), mat.m[12 + r]));
+		px[q] = pathCoord(__fdiv_rn(v[0], v[3]), resolution);
+		py[q] = pathCoord(__fdiv_rn(v[1], v[3]), resolution);
+		pz[q] = pathCoord(__fdiv_rn(v[2], v[3]), resolution);
+	}
+	u32 result[kPixels];
+	lookupSlotsTogether<kPixels>(d, live, px, py, pz, result);
+#pragma unroll
+	for (int q = 0; q < kPixels; ++q) {
+		if (!live[q]) continue;
+		const unsigned char vis = result[q] == 1u ? 255 : 0;
+		if (kSurface)
+			surf2Dwrite(vis, io.outSurface, (int)(x0 + (u32)q), (int)y);
+		else
+			io.out[i + q] = vis;
+	}
+}
+
+// The same for plain NDC points: two consecutive points per thread.
+__global__ void __launch_bounds__(256) lookupNdcPairsKernel(LookupDag d, const float* __restrict__ ndc, long long count, unsigned char* __restrict__ out) {
+	constexpr int kPoints = 2;
+	const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * kPoints;
+	if (i0 >= count) return;
+	const int resolution = (1 << (d.dagLevels + d.gridLevels - 1)) - 1;
+	int px[kPoints], py[kPoints], pz[kPoints];
+	bool live[kPoints];
+#pragma unroll
+	for (int q = 0; q < kPoints; ++q) {
+		live[q] = i0 + q < count;
+		const long long i = live[q] ? i0 + q : i0;
+		px[q] = pathCoord(ndc[3 * i], resolution);
+		py[q] = pathCoord(ndc[3 * i + 1], resolution);
+		pz[q] = pathCoord(ndc[3 * i + 2], resolution);
+	}
+	u32 result[kPoints];
+	lookupSlotsTogether<kPoints>(d, live, px, py, pz, result);
+#pragma unroll
+	for (int q = 0; q < kPoints; ++q)
+		if (live[q]) out[i0 + q] = (unsigned char)result[q];
+}
+
 }  // namespace
 
 int launchBuildSkipGrid(const LookupDag& d, u32* skip, cudaStream_t stream) {
@@ -205,7 +341,10 @@ int launchBuildSkipGrid(const LookupDag& d, u32* skip, cudaStream_t stream) {
 
 int launchLookupNdc(const LookupDag& d, const float* ndc, long long count, unsigned char* out, cudaStream_t stream) {
 	if (count <= 0) return 0;
-	lookupNdcKernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(d, ndc, count, out);
+	if (d.leafCodes)
+		lookupNdcPairsKernel<<<(unsigned)((count + 511) / 512), 256, 0, stream>>>(d, ndc, count, out);
+	else
+		lookupNdcKernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(d, ndc, count, out);
 	return 1;
 }
 
@@ -216,7 +355,11 @@ int launchEvaluate(const LookupDag& d, const float* positions, unsigned width, u
 	for (int i = 0; i < 16; ++i) m.m[i] = matrix[i];
 	const dim3 block(8, 32), grid((width + 7) / 8, (height + 31) / 32);
 	PixelSource io{reinterpret_cast<const float4*>(positions), out, 0, 0};
-	evaluateKernel<false><<<grid, block, 0, stream>>>(d, io, width, height, m, filterSize);
+	if (filterSize <= 1 && d.leafCodes) {
+		evaluatePairsKernel<false><<<dim3((width + 8 * kPixelsPerThread - 1) / (8 * kPixelsPerThread), (height + 31) / 32), block, 0, stream>>>(d, io, width, height, m);
+	} else {
+		evaluateKernel<false><<<grid, block, 0, stream>>>(d, io, width, height, m, filterSize);
+	}
 	return 1;
 }
 
@@ -227,7 +370,11 @@ int launchEvaluateSurface(const LookupDag& d, unsigned long long positions, unsi
 	for (int i = 0; i < 16; ++i) m.m[i] = matrix[i];
 	const dim3 block(8, 32), grid((width + 7) / 8, (height + 31) / 32);
 	PixelSource io{nullptr, nullptr, (cudaSurfaceObject_t)positions, (cudaSurfaceObject_t)visibilities};
-	evaluateKernel<true><<<grid, block, 0, stream>>>(d, io, width, height, m, filterSize);
+	if (filterSize <= 1 && d.leafCodes) {
+		evaluatePairsKernel<true><<<dim3((width + 8 * kPixelsPerThread - 1) / (8 * kPixelsPerThread), (height + 31) / 32), block, 0, stream>>>(d, io, width, height, m);
+	} else {
+		evaluateKernel<true><<<grid, block, 0, stream>>>(d, io, width, height, m, filterSize);
+	}
 	return 1;
 }
 
