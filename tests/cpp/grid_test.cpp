@@ -62,6 +62,56 @@ static int buildGrid(const std::vector<int>& devices, const cpvs_grid_desc& desc
 	return 0;
 }
 
+// The worker-level calls a caller with its own scheduling uses: tiles handed out through a callback (the worker asks one tile
+// ahead), the cells assembled into a container, the recycled memory given back.
+struct TileQueue {
+	std::vector<uint32_t> xy;
+	size_t next;
+};
+static int nextTile(void* user, uint32_t* x, uint32_t* y) {
+	TileQueue* q = static_cast<TileQueue*>(user);
+	if (q->next * 2 >= q->xy.size()) return 0;
+	*x = q->xy[2 * q->next];
+	*y = q->xy[2 * q->next + 1];
+	++q->next;
+	return 1;
+}
+static int buildThroughWorker(int device, const cpvs_grid_desc& desc, std::vector<uint32_t>* dagOut, std::vector<uint32_t>* cellsOut) {
+	cpvs_ctx* ctx = nullptr;
+	CHECK(cpvs_ctx_create(device, &ctx));
+	cpvs_grid_worker* w = nullptr;
+	CHECK(cpvs_grid_worker_create(ctx, &desc, &w));
+	TileQueue q;
+	q.next = 0;
+	for (uint32_t y = 0; y < desc.length; ++y)
+		for (uint32_t x = 0; x < desc.length; ++x) {
+			q.xy.push_back(x);
+			q.xy.push_back(y);
+		}
+	CHECK(cpvs_grid_worker_build_from(w, nextTile, &q));
+	const size_t numCells = (size_t)desc.length * desc.length * desc.length;
+	std::vector<cpvs_grid_cell> cells(numCells);
+	if (cpvs_grid_worker_cells(w, cells.data(), (int)cells.size()) != (int)numCells) {
+		std::fprintf(stderr, "worker: %zu cells expected\n", numCells);
+		return 1;
+	}
+	std::vector<cpvs_cell_part> parts(numCells);
+	for (const cpvs_grid_cell& c : cells) parts[c.index] = cpvs_cell_part{c.words, c.root_mask, c.device, c.words_device};
+	cpvs_container* cont = nullptr;
+	CHECK(cpvs_container_assemble(ctx, desc.length, cells[0].num_levels, desc.leafmasks, parts.data(), &cont));
+	uint64_t words = 0;
+	uint32_t ncells = 0;
+	CHECK(cpvs_container_info(cont, &words, &ncells, nullptr, nullptr));
+	dagOut->resize(words);
+	cellsOut->resize(ncells);
+	CHECK(cpvs_container_copy(cont, dagOut->data(), cellsOut->data()));
+	CHECK(cpvs_container_destroy(cont));
+	CHECK(cpvs_grid_worker_destroy(w));
+	CHECK(cpvs_ctx_trim(ctx));
+	CHECK(cpvs_ctx_destroy(ctx));
+	return 0;
+}
+
 int main(int argc, char** argv) {
 	if (argc < 4) {
 		std::fprintf(stderr, "usage: grid_test <tile> <length> <devices...>\n");
@@ -93,6 +143,12 @@ int main(int argc, char** argv) {
 		if (buildGrid(devices, desc, points, &many)) return 1;
 		if (one.dag != many.dag || one.cells != many.cells || one.lookups != many.lookups) {
 			std::fprintf(stderr, "scene %d: %zu workers disagree with one worker (%zu vs %zu words)\n", scene, devices.size(), many.dag.size(), one.dag.size());
+			return 1;
+		}
+		std::vector<uint32_t> workerDag, workerCells;
+		if (buildThroughWorker(devices[0], desc, &workerDag, &workerCells)) return 1;
+		if (workerDag != one.dag || workerCells != one.cells) {
+			std::fprintf(stderr, "scene %d: a worker fed through the callback disagrees with cpvs_grid_build\n", scene);
 			return 1;
 		}
 		unsigned lit = 0;
