@@ -560,7 +560,7 @@ def run_own(args):
             # tiles out through the shared queue, so a rank meets other tiles in every pass: its second pass is still warming up
             # (N = 8: 307, 97, 61 ms), hence three timed passes there too.
             passes = 4
-            reps = [gridbuild.run(ctx, args.grid_tile, length, kind, rank, world, gloo, lookups=3840 * 2160, lookup_iters=4, verify=(r == 0),
+            reps = [gridbuild.run(ctx, args.grid_tile, length, kind, rank, world, gloo, lookups=3840 * 2160, lookup_iters=32, verify=(r == 0),
                                   replicate=(r == 0)) for r in range(passes)]
             by_time = sorted(reps[1:], key=lambda g: g["build_ms_max_rank"])
             g = dict(reps[0])

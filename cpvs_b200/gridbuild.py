@@ -47,7 +47,7 @@ def _barrier(group, world):
         dist.barrier(group=group)
 
 
-def run(ctx, tile, length, kind, rank=0, world=1, group=None, lookups=3840 * 2160, lookup_iters=8, verify=True, leafmasks=True,
+def run(ctx, tile, length, kind, rank=0, world=1, group=None, lookups=3840 * 2160, lookup_iters=32, verify=True, leafmasks=True,
         fetch=None, replicate=True, log=None):
     """Builds the ``length^3`` container of a ``(tile*length)^2`` virtual map and runs ``lookups`` random NDC lookups through
     it. ``kind``: a scene with a device generator; or ``fetch(x, y, out)`` for caller-provided depth tiles. Returns a dict of
@@ -216,6 +216,7 @@ def run(ctx, tile, length, kind, rank=0, world=1, group=None, lookups=3840 * 216
             cont.lookup_ndc(pts, out)
         ctx.synchronize()
         _barrier(group, world)
+        # (wall clock around back-to-back launches: at eight ranks a rank's share is a 15 us kernel, so many launches per reading)
         t0 = time.perf_counter()
         for _ in range(lookup_iters):
             cont.lookup_ndc(pts, out)
