@@ -35,6 +35,7 @@ struct WorkerTile {
 	cpvs_minmax* mm = nullptr;
 	u64 cost = 0;
 	bool built = false;
+	bool queued = false;  // taken by a build call that is still working on it
 	cudaEvent_t evDepth0 = nullptr, evDepth1 = nullptr;  // around the production of the depth tile, which runs alone on the GPU
 	std::vector<cpvs_shadow*> cells;  // z = 0 .. length-1
 };
@@ -328,6 +329,7 @@ int finishTile(cpvs_grid_worker* w, WorkerTile& t) {
 	}
 	releaseInputs(w, t);
 	t.built = true;
+	t.queued = false;
 	++w->built;
 	return CPVS_OK;
 }
@@ -363,7 +365,8 @@ int cpvs_grid_worker_build_from(cpvs_grid_worker* w, cpvs_next_tile_fn next, voi
 		while (next(user, &x, &y)) {
 			if (x >= w->desc.length || y >= w->desc.length) return fail(CPVS_EINVAL, "cpvs_grid_worker_build: tile (%u,%u) of %u", x, y, w->desc.length);
 			const size_t i = tileIndex(w, x, y);
-			if (w->tiles[i].built) continue;
+			if (w->tiles[i].built || w->tiles[i].queued) continue;  // (a tile named twice is built once)
+			w->tiles[i].queued = true;
 			*idx = i;
 			break;
 		}
