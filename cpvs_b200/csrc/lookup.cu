@@ -1,7 +1,7 @@
 // K7 -- shadow lookup (reference CompressedShadow::traverse, src/CompressedShadow.cpp:404-463, and the
 // GLSL compute shader shader/traverse.cs:41-149 it mirrors, including the top-level grid step).
 //
-// One thread per query. The path is the query's integer voxel coordinate; each level consumes one bit
+// Two queries per thread (the single-tap kernels) or one (PCF taps). The path is the query's integer voxel coordinate; each level consumes one bit
 // per axis, tests the 2-bit child code and follows the popcount-ranked pointer. Deviations from the
 // reference, both documented in SURVEY.md: paths are clamped to the volume (N5) and the grid
 // sentinels are the ones the C++ side writes (N3).
@@ -88,11 +88,6 @@ __device__ __forceinline__ u32 lookupPath(const LookupDag& d, int px, int py, in
 	return descend(dag, offset, startLevel, d.leafmasks != 0, px, py, pz);
 }
 
-__device__ __forceinline__ u32 lookupOne(const LookupDag& d, float x, float y, float z) {
-	const int resolution = (1 << (d.dagLevels + d.gridLevels - 1)) - 1;
-	return lookupPath(d, pathCoord(x, resolution), pathCoord(y, resolution), pathCoord(z, resolution));
-}
-
 // One thread per shortcut cell: runs the first skipLevels steps of the descent for the cell's path prefix.
 __global__ void __launch_bounds__(256) buildSkipGridKernel(LookupDag d, u32* __restrict__ skip) {
 	const u32 bits = d.gridLevels + d.skipLevels, res = 1u << bits;
@@ -133,12 +128,6 @@ __global__ void __launch_bounds__(256) buildSkipGridKernel(LookupDag d, u32* __r
 		offset = dag[offset + 1 + childRank(mask, idx * 2)];
 	}
 	skip[i] = offset;
-}
-
-__global__ void __launch_bounds__(256) lookupNdcKernel(LookupDag d, const float* __restrict__ ndc, long long count, unsigned char* __restrict__ out) {
-	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= count) return;
-	out[i] = (unsigned char)lookupOne(d, ndc[3 * i], ndc[3 * i + 1], ndc[3 * i + 2]);
 }
 
 struct Mat4 {
@@ -266,6 +255,107 @@ __device__ __forceinline__ void lookupSlotsTogether(const LookupDag& d, const bo
 		result[q] = st[q].done ? st[q].result : ((u32)(pz[q] & 7) < ((row[q] >> (4 * (px[q] & 7))) & 15u) ? 1u : 0u);
 }
 
+// The same on the wire format (DAGs without leafmasks, containers whose leaves are not nested): two dependent loads per level --
+// mask, then the popcount-ranked pointer -- for all queries of the thread before either is used.
+template <int kQueries>
+__device__ __forceinline__ void lookupWireTogether(const LookupDag& d, const bool* live, const int* px, const int* py, const int* pz, u32* result) {
+	u32 base[kQueries], offset[kQueries];
+	bool done[kQueries];
+#pragma unroll
+	for (int q = 0; q < kQueries; ++q) {
+		base[q] = 0u;
+		offset[q] = 0u;
+		done[q] = !live[q];
+		result[q] = 0u;
+		if (done[q]) continue;
+		if (d.grid) {  // traverse.cs:78-88
+			const u32 shift = d.dagLevels - 1, res = 1u << d.gridLevels;
+			const u32 cell = __ldg(d.grid + ((u32)(pz[q] >> shift) * res + (u32)(py[q] >> shift)) * res + (u32)(px[q] >> shift));
+			if (cell == kCellShadowed || cell == kCellVisible) {
+				done[q] = true;
+				result[q] = cell == kCellVisible ? 1u : 0u;
+				continue;
+			}
+			base[q] = cell;
+		}
+		if (d.skip) {
+			const u32 shift = d.dagLevels - 1 - d.skipLevels, res = 1u << (d.gridLevels + d.skipLevels);
+			const u32 entry = __ldg(d.skip + ((u32)(pz[q] >> shift) * res + (u32)(py[q] >> shift)) * res + (u32)(px[q] >> shift));
+			if (entry == kSkipShadow || entry == kSkipVisible) {
+				done[q] = true;
+				result[q] = entry == kSkipVisible ? 1u : 0u;
+				continue;
+			}
+			offset[q] = entry;
+		}
+	}
+	const bool leaf = d.leafmasks != 0;
+	const int startLevel = (int)d.dagLevels - 2 - (d.skip ? (int)d.skipLevels : 0), minLevel = leaf ? 3 : 0;
+	const u32* __restrict__ dag = d.dag;
+	for (int level = startLevel; level >= minLevel; --level) {
+		bool all = true;
+#pragma unroll
+		for (int q = 0; q < kQueries; ++q) all = all && done[q];
+		if (all) break;
+		u32 mask[kQueries], next[kQueries];
+#pragma unroll
+		for (int q = 0; q < kQueries; ++q) mask[q] = done[q] ? 0u : __ldg(dag + base[q] + offset[q]);
+#pragma unroll
+		for (int q = 0; q < kQueries; ++q) {
+			next[q] = 0u;
+			if (done[q]) continue;
+			const u32 idx = ((px[q] >> level) & 1) | (((py[q] >> level) & 1) << 1) | (((pz[q] >> level) & 1) << 2);
+			const u32 vis = (mask[q] >> (idx * 2)) & 3u;
+			if (vis != 2u) {
+				done[q] = true;
+				result[q] = vis & 1u;
+			} else {
+				next[q] = base[q] + offset[q] + 1 + childRank(mask[q], idx * 2);
+			}
+		}
+#pragma unroll
+		for (int q = 0; q < kQueries; ++q)
+			if (!done[q]) offset[q] = __ldg(dag + next[q]);
+	}
+	if (!leaf) {
+#pragma unroll
+		for (int q = 0; q < kQueries; ++q)
+			if (!done[q]) result[q] = 2u;  // PARTIAL at the last level (src/CompressedShadow.cpp:460-462)
+		return;
+	}
+	u32 mask[kQueries], at[kQueries];
+#pragma unroll
+	for (int q = 0; q < kQueries; ++q) mask[q] = done[q] ? 0u : __ldg(dag + base[q] + offset[q]);
+#pragma unroll
+	for (int q = 0; q < kQueries; ++q) {
+		at[q] = 0u;
+		if (done[q]) continue;
+		const u32 idx = pz[q] & 7;
+		const u32 vis = (mask[q] >> (idx * 2)) & 3u;
+		if (vis != 2u) {
+			done[q] = true;
+			result[q] = vis & 1u;
+		} else {
+			const u32 bit = (px[q] & 7) + 8 * (py[q] & 7);
+			at[q] = base[q] + offset[q] + 1 + childRank(mask[q], idx * 2) * 2 + (bit >> 5);
+		}
+	}
+#pragma unroll
+	for (int q = 0; q < kQueries; ++q)
+		if (!done[q]) {
+			const u32 bit = (px[q] & 7) + 8 * (py[q] & 7);
+			result[q] = (__ldg(dag + at[q]) >> (bit & 31)) & 1u;
+		}
+}
+
+template <int kQueries>
+__device__ __forceinline__ void lookupTogether(const LookupDag& d, const bool* live, const int* px, const int* py, const int* pz, u32* result) {
+	if (d.leafCodes)
+		lookupSlotsTogether<kQueries>(d, live, px, py, pz, result);
+	else
+		lookupWireTogether<kQueries>(d, live, px, py, pz, result);
+}
+
 constexpr int kPixelsPerThread = 2;  // measured on the 4K surface G-buffer: 1 -> 60.8, 2 -> 81.1, 3 -> 78.3, 4 -> 76.4 G lookups/s
 
 template <bool kSurface>
@@ -295,7 +385,7 @@ __global__ void __launch_bounds__(256) evaluatePairsKernel(LookupDag d, PixelSou
 		pz[q] = pathCoord(__fdiv_rn(v[2], v[3]), resolution);
 	}
 	u32 result[kPixels];
-	lookupSlotsTogether<kPixels>(d, live, px, py, pz, result);
+	lookupTogether<kPixels>(d, live, px, py, pz, result);
 #pragma unroll
 	for (int q = 0; q < kPixels; ++q) {
 		if (!live[q]) continue;
@@ -324,7 +414,7 @@ __global__ void __launch_bounds__(256) lookupNdcPairsKernel(LookupDag d, const f
 		pz[q] = pathCoord(ndc[3 * i + 2], resolution);
 	}
 	u32 result[kPoints];
-	lookupSlotsTogether<kPoints>(d, live, px, py, pz, result);
+	lookupTogether<kPoints>(d, live, px, py, pz, result);
 #pragma unroll
 	for (int q = 0; q < kPoints; ++q)
 		if (live[q]) out[i0 + q] = (unsigned char)result[q];
@@ -341,10 +431,7 @@ int launchBuildSkipGrid(const LookupDag& d, u32* skip, cudaStream_t stream) {
 
 int launchLookupNdc(const LookupDag& d, const float* ndc, long long count, unsigned char* out, cudaStream_t stream) {
 	if (count <= 0) return 0;
-	if (d.leafCodes)
-		lookupNdcPairsKernel<<<(unsigned)((count + 511) / 512), 256, 0, stream>>>(d, ndc, count, out);
-	else
-		lookupNdcKernel<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(d, ndc, count, out);
+	lookupNdcPairsKernel<<<(unsigned)((count + 511) / 512), 256, 0, stream>>>(d, ndc, count, out);
 	return 1;
 }
 
@@ -355,7 +442,7 @@ int launchEvaluate(const LookupDag& d, const float* positions, unsigned width, u
 	for (int i = 0; i < 16; ++i) m.m[i] = matrix[i];
 	const dim3 block(8, 32), grid((width + 7) / 8, (height + 31) / 32);
 	PixelSource io{reinterpret_cast<const float4*>(positions), out, 0, 0};
-	if (filterSize <= 1 && d.leafCodes) {
+	if (filterSize <= 1) {
 		evaluatePairsKernel<false><<<dim3((width + 8 * kPixelsPerThread - 1) / (8 * kPixelsPerThread), (height + 31) / 32), block, 0, stream>>>(d, io, width, height, m);
 	} else {
 		evaluateKernel<false><<<grid, block, 0, stream>>>(d, io, width, height, m, filterSize);
@@ -370,7 +457,7 @@ int launchEvaluateSurface(const LookupDag& d, unsigned long long positions, unsi
 	for (int i = 0; i < 16; ++i) m.m[i] = matrix[i];
 	const dim3 block(8, 32), grid((width + 7) / 8, (height + 31) / 32);
 	PixelSource io{nullptr, nullptr, (cudaSurfaceObject_t)positions, (cudaSurfaceObject_t)visibilities};
-	if (filterSize <= 1 && d.leafCodes) {
+	if (filterSize <= 1) {
 		evaluatePairsKernel<true><<<dim3((width + 8 * kPixelsPerThread - 1) / (8 * kPixelsPerThread), (height + 31) / 32), block, 0, stream>>>(d, io, width, height, m);
 	} else {
 		evaluateKernel<true><<<grid, block, 0, stream>>>(d, io, width, height, m, filterSize);
