@@ -148,6 +148,27 @@ def test_worker_pulls_tiles_from_a_queue(kind, length, tile):
         worker.close()
 
 
+@pytest.mark.parametrize("lanes", ["1", "3", "8"])
+def test_worker_lanes(lanes, monkeypatch):
+    """CPVS_GRID_LANES: however many contexts a worker spreads a tile's slices over, the cells are the same."""
+    length, tile, kind = 4, 256, "city"
+    tiles = [(x, y) for y in range(length) for x in range(length)][:6]
+    ctx = cpvs_b200.Context(0)
+    ref = cgrid.GridWorker(ctx, length, tile, kind)  # the default number of lanes
+    ref.build(tiles)
+    want = _cells_by_index(ref)
+    monkeypatch.setenv("CPVS_GRID_LANES", lanes)
+    ctx2 = cpvs_b200.Context(0)
+    w = cgrid.GridWorker(ctx2, length, tile, kind)
+    w.build(tiles)
+    got = _cells_by_index(w)
+    assert sorted(got) == sorted(want)
+    for i in want:
+        assert np.array_equal(got[i], want[i]), (lanes, i)
+    w.close()
+    ref.close()
+
+
 def test_cpp_caller_builds_grids_on_several_workers(tmp_path):
     """tests/cpp/grid_test.cpp: a plain C++ program against include/cpvs_b200.h + libcpvs_b200.so."""
     import torch
